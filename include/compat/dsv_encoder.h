@@ -1,0 +1,3 @@
+/* Source-compatibility shim: lets callers written against the reference's "dsv_encoder.h"
+ * (e.g. the unmodified CLI, dsv_main.c) compile against libdsv1_b200. */
+#include "../dsv1_b200.h"
