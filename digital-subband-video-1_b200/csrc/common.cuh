@@ -1,0 +1,135 @@
+/*
+ * common.cuh -- shared device/host helpers for libdsv1_b200 (sm_100a).
+ *
+ * Integer semantics follow the reference exactly:
+ * C truncating division on negatives for the LL scaling and the /4 of the Haar
+ * inverse, round-half-away-from-zero for round2/4/8, arithmetic >> on negatives.
+ */
+#pragma once
+
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef DSV_CPU_EMU
+#include <cuda_runtime.h>
+#define DSV_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define DSV_DYN_SMEM(type, name)                                   \
+    extern __shared__ __align__(16) unsigned char dsv_dyn_smem_[]; \
+    type *name = reinterpret_cast<type *>(dsv_dyn_smem_)
+#endif
+
+#define DSV_HD __host__ __device__ __forceinline__
+#define DSV_D __device__ __forceinline__
+
+/* Any CUDA failure is fatal: there is no CPU fallback to continue on. */
+#define CUDA_CHECK(expr)                                                                            \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            fprintf(stderr, "[dsv1_b200] CUDA error %d (%s) at %s:%d: %s\n", (int) e_,              \
+                    cudaGetErrorString(e_), __FILE__, __LINE__, #expr);                             \
+            abort();                                                                                \
+        }                                                                                           \
+    } while (0)
+#define KERNEL_CHECK() CUDA_CHECK(cudaGetLastError())
+
+namespace dsv {
+
+DSV_HD int imin(int a, int b) { return a < b ? a : b; }
+DSV_HD int imax(int a, int b) { return a > b ? a : b; }
+DSV_HD int iclamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+DSV_HD int iabs(int v) { return v < 0 ? -v : v; }
+DSV_HD int ceil_shift(int v, int s) { return (v + (1 << s) - 1) >> s; }
+DSV_HD int ceil_div(int a, int b) { return (a + b - 1) / b; }
+DSV_HD uint8_t clamp_u8(int v) { return (uint8_t) (v < 0 ? 0 : (v > 255 ? 255 : v)); }
+
+/* smallest L with 2^L >= n (hzcc.c:437-447) */
+DSV_HD int lb2(unsigned n)
+{
+    int l = 0;
+    while ((1u << l) < n) {
+        l++;
+    }
+    return l;
+}
+
+/* per-level base quantiser (hzcc.c:77-92) */
+DSV_HD int get_quant(int q, int isP, int level)
+{
+    if (isP) {
+        q = q * 3 / 2;
+    }
+    if (level == 1) {
+        q = q * 2 / 3;
+    } else if (level == 2) {
+        q = q * 3 / 2;
+    }
+    return q < 16 ? 16 : q;
+}
+
+/* round half away from zero, divide by 2^S (sbt.c:63-88) */
+template <int S> DSV_HD int rnd_shift(int v)
+{
+    const int half = 1 << (S - 1);
+    return v < 0 ? -((-v + half) >> S) : ((v + half) >> S);
+}
+
+/* LL scaling, C truncation (sbt.c:20-21) */
+DSV_HD int ll_down(int v) { return v * 4 / 5; }
+DSV_HD int ll_up(int v) { return v * 5 / 4; }
+/* C `/ 4` (truncate toward zero) without a divide */
+DSV_HD int div4_trunc(int v) { return (v + ((v >> 31) & 3)) >> 2; }
+
+/*
+ * Exact unsigned division by a runtime-constant divisor d for numerators < 2^31:
+ *   n / d == (n * mul) >> sh,  sh = 31 + ceil(log2 d),  mul = floor(2^sh / d) + 1
+ * (round-up method; for powers of two mul = 2^31 exactly).  Built on the host once
+ * per frame for the handful of quantisers a frame uses.
+ */
+struct FastDiv {
+    unsigned long long mul;
+    int sh;
+    int d;
+};
+static inline FastDiv make_fastdiv(int d)
+{
+    FastDiv f;
+    int l = lb2((unsigned) d);
+    f.d = d;
+    f.sh = 31 + l;
+    if ((1 << l) == d) {
+        f.mul = 1ull << 31;
+    } else {
+        f.mul = ((1ull << f.sh) / (unsigned long long) d) + 1;
+    }
+    return f;
+}
+DSV_HD unsigned fastdiv(unsigned n, const FastDiv &f) { return (unsigned) (((unsigned long long) n * f.mul) >> f.sh); }
+
+/* dead-zone quantiser / reconstruction (hzcc.c:94-128) */
+DSV_HD int dz_quant(int v, int q, const FastDiv &two_q)
+{
+    unsigned m = (unsigned) iabs(v) * 2u;
+    if (m <= (unsigned) q) {
+        return 0;
+    }
+    int r = (int) fastdiv(m + 1u, two_q);
+    return v < 0 ? -r : r;
+}
+DSV_HD int dz_dequant(int v, int q)
+{
+    int m = (iabs(v) * (2 * q) + q) >> 1;
+    return v < 0 ? -m : m;
+}
+/* top level: shift of the magnitude (hzcc.c:114-135) */
+DSV_HD int p2_quant(int v, int s) { return v < 0 ? -((-v) >> s) : (v >> s); }
+DSV_HD int p2_dequant(int v, int s) { return (int) ((unsigned) v << s); }
+
+/* Reference frame geometry (frame.c:63-120): 64-sample border, stride rounded up to 16 */
+#define DSV_BORDER 64
+DSV_HD int frame_stride(int w) { return (w + 2 * DSV_BORDER + 15) & ~15; }
+
+} // namespace dsv

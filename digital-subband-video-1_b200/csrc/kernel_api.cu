@@ -1,0 +1,86 @@
+/*
+ * kernel_api.cu -- dsvk_*: kernel-level C ABI with HOST buffers (declared in include/dsv1_b200_kernels.h).
+ *
+ * One entry point per hot-path subsystem, with the same flat signatures as the checker libraries
+ * (oracle/ref_harness.c, oracle/dsv1_port.c) so the parity tests call all three alike.  Every call
+ * copies its inputs to the GPU, runs the CUDA kernels and copies the result back: there is no host
+ * implementation behind these symbols.
+ */
+#include "common.cuh"
+#include "sbt.cuh"
+
+using namespace dsv;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    explicit DevBuf(size_t n) { CUDA_CHECK(cudaMalloc(&p, n ? n : 1)); }
+    ~DevBuf() { cudaFree(p); }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+/* device plane in the reference's bordered layout: returns pointer to sample (0,0) */
+struct DevPlane {
+    DevBuf buf;
+    int stride, rows;
+    uint8_t *origin;
+    DevPlane(int w, int h)
+        : buf((size_t) frame_stride(w) * (h + 2 * DSV_BORDER) + 256), stride(frame_stride(w)), rows(h + 2 * DSV_BORDER)
+    {
+        CUDA_CHECK(cudaMemset(buf.p, 0, (size_t) stride * rows + 256));
+        origin = buf.as<uint8_t>() + (size_t) stride * DSV_BORDER + DSV_BORDER;
+    }
+};
+
+} // namespace
+
+extern "C" int dsvk_fwd_sbt(const uint8_t *pix, int stride, int pw, int ph, int cw, int ch, int isP, int32_t *coef_out)
+{
+    if ((cw & 1) || (ch & 1) || cw < 16 || ch < 16) {
+        return -1;
+    }
+    DevPlane dp(cw, ph);
+    CUDA_CHECK(cudaMemcpy2D(dp.origin, dp.stride, pix, stride, cw, ph, cudaMemcpyHostToDevice));
+    DevBuf coef((size_t) cw * ch * 4), llx(sbt_llx_elems(cw, ch) * 4), dv(sbt_dv_elems(cw, ch) * 4), jobs(sizeof(SbtJob));
+    CUDA_CHECK(cudaMemset(coef.p, 0, (size_t) cw * ch * 4));
+    SbtJob j;
+    memset(&j, 0, sizeof(j));
+    sbt_fill_geometry(&j, pw, ph, cw, ch, isP, 0);
+    j.pix = dp.origin;
+    j.pstride = dp.stride;
+    j.coef = coef.as<int32_t>();
+    j.llx = llx.as<int32_t>();
+    j.dv = dv.as<int32_t>();
+    j.do_quant = 0;
+    j.tile_base = 0;
+    CUDA_CHECK(cudaMemcpy(jobs.p, &j, sizeof(j), cudaMemcpyHostToDevice));
+    sbt_fwd_launch(jobs.as<SbtJob>(), 1, j.tiles_x * j.tiles_y, sbt_lo_smem_bytes(cw, ch), 0);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(coef_out, coef.p, (size_t) cw * ch * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int dsvk_inv_sbt(int32_t *coef_io, int cw, int ch, int q, int isP, int c, uint8_t *pix_out, int stride, int pw, int ph)
+{
+    if ((cw & 1) || (ch & 1) || cw < 16 || ch < 16) {
+        return -1;
+    }
+    DevPlane dp(cw, ph);
+    DevBuf coef((size_t) cw * ch * 4), llx(sbt_llx_elems(cw, ch) * 4), jobs(sizeof(SbtJob));
+    CUDA_CHECK(cudaMemcpy(coef.p, coef_io, (size_t) cw * ch * 4, cudaMemcpyHostToDevice));
+    SbtJob j;
+    memset(&j, 0, sizeof(j));
+    sbt_fill_geometry(&j, pw, ph, cw, ch, isP, c);
+    sbt_fill_quant(&j, q, isP, c, 1, 1);
+    j.pix = dp.origin;
+    j.pstride = dp.stride;
+    j.coef = coef.as<int32_t>();
+    j.llx = llx.as<int32_t>();
+    j.tile_base = 0;
+    CUDA_CHECK(cudaMemcpy(jobs.p, &j, sizeof(j), cudaMemcpyHostToDevice));
+    sbt_inv_launch(jobs.as<SbtJob>(), 1, j.tiles_x * j.tiles_y, sbt_lo_smem_bytes(cw, ch), !isP, 0);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy2D(pix_out, stride, dp.origin, dp.stride, pw, ph, cudaMemcpyDeviceToHost));
+    return 0;
+}

@@ -1,0 +1,101 @@
+/*
+ * sbt.cuh -- job descriptors for the subband-transform kernels (sbt_fwd.cu, sbt_inv.cu).
+ *
+ * One "job" = one plane of one frame.  A launch takes an array of jobs in device
+ * memory so that planes x frames x sequences are batched into one grid (a single
+ * 1080p plane is only a few microseconds of HBM traffic).
+ *
+ * Decomposition (reference: sbt.c:617-714): levels 1..nlt (nlt = min(5, levels))
+ * are computed per 128x64-sample tile entirely in shared memory ("tile" kernels);
+ * the remaining levels operate on the small LL_nlt array in one CTA ("lo" kernels).
+ * The two kernels hand LL_nlt over through the job's `llx` scratch array.
+ */
+#pragma once
+#include "common.cuh"
+
+namespace dsv {
+
+#define SBT_TW 128 /* tile width  in samples */
+#define SBT_TH 64  /* tile height in samples */
+#define SBT_NLT 5  /* max levels done inside a tile (128x64 -> 4x2 LL coefficients) */
+#define SBT_TILE_THREADS 256
+#define SBT_LO_THREADS 1024
+#define SBT_STAB_SMEM 2048
+
+/* adaptive quantiser table for one plane of one frame (hzcc.c:50-92,196-258) */
+struct LevelQ {
+    int q[3]; /* [0] plain, [1] stable, [2] intra block */
+    FastDiv fd[3];
+};
+struct PlaneQ {
+    int ll_q; /* "LL" region: levels >= 4 (hzcc.c:158-188) */
+    FastDiv ll_fd;
+    LevelQ lv[2];          /* hzcc level 0,1 == transform level 3,2 */
+    int sh_plain, sh_hq;   /* hzcc level 2 == transform level 1: shift amounts */
+    int dbx[4], dby[4];    /* 14-bit fixed-point block steps per transform level 1..3 (hzcc.c:196-197) */
+    int nbh, nbv;
+};
+
+/* geometry of the positions hzcc visits twice, per transform level l in {2,1}:
+ * element (ax,ay) written by level l is ALSO the last column/row of level l+1's scan region when
+ * ax == dvx[l] (rows < dvey[l]) or ay == dvy[l] (cols < dvex[l]).  -1 = no overlap. */
+struct DvGeom {
+    int dvx[3], dvy[3], dvex[3], dvey[3];
+    int col_base[3], row_base[3]; /* offsets into the plane's dv side buffer */
+    int total;
+};
+
+struct SbtJob {
+    /* pixels: bordered-frame layout, pix -> sample (0,0) */
+    uint8_t *pix;
+    int pstride;
+    int pw, ph;
+    /* coefficients: dense, stride == cw */
+    int32_t *coef;
+    int cw, ch;
+    int32_t *llx; /* LL_nlt hand-over scratch, wo_nlt * ho_nlt ints */
+    int32_t *dv;  /* first-visit symbols of double-visited positions (encoder) / values (decoder) */
+    const uint8_t *stable;
+    int lvls, nlt;
+    int isP;
+    int plane;    /* 0 = luma (filtered inverse), 1/2 = chroma */
+    int quant;    /* frame quant (for the inverse's nudge bounds) */
+    int do_quant; /* forward: fuse quantise+dequantise into the epilogue */
+    int tiles_x, tiles_y, tile_base;
+    int hqp[16];  /* inverse: nudge bound per level (sbt.c:677-696), index = level */
+    PlaneQ pq;
+    DvGeom dg;
+};
+
+/* host helpers (sbt_host.cu) */
+int sbt_num_levels(int cw, int ch);
+void sbt_fill_geometry(SbtJob *j, int pw, int ph, int cw, int ch, int isP, int plane);
+void sbt_fill_quant(SbtJob *j, int q, int isP, int plane, int nbh, int nbv);
+size_t sbt_llx_elems(int cw, int ch);
+size_t sbt_dv_elems(int cw, int ch);
+
+/* launches; jobs is a DEVICE array, total_tiles = sum of tiles over jobs */
+void sbt_fwd_launch(const SbtJob *d_jobs, int njobs, int total_tiles, size_t lo_smem, cudaStream_t st);
+void sbt_inv_launch(const SbtJob *d_jobs, int njobs, int total_tiles, size_t lo_smem, bool any_intra, cudaStream_t st);
+size_t sbt_lo_smem_bytes(int cw, int ch);
+
+/* flat tile index -> job (jobs are sorted by tile_base) */
+DSV_D int sbt_find_job(const SbtJob *jobs, int njobs, int tile)
+{
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].tile_base <= tile) {
+            lo = mid;
+        } else {
+            hi = mid - 1;
+        }
+    }
+    return lo;
+}
+
+/* per-level geometry helpers */
+DSV_HD int sbt_ws(int dim, int lvl) { return ceil_shift(dim, lvl - 1); } /* input size of level lvl */
+DSV_HD int sbt_wo(int dim, int lvl) { return ceil_shift(dim, lvl); }     /* LL size / H offset */
+
+} // namespace dsv

@@ -227,6 +227,16 @@ def gpu():
     return _cache["gpu"]
 
 
+EMU_SO = os.path.join(ROOT, "tests", "emu", "_build", "libdsv1_emu.so")
+
+
+def emu():
+    """TEST-ONLY CPU emulation of the CUDA kernel sources (tests/emu/cuda_emu.h); never the product."""
+    if "emu" not in _cache:
+        _cache["emu"] = Lib(EMU_SO, "dsvk_", api_prefix="dsvh_")
+    return _cache["emu"]
+
+
 def have_ref():
     return os.path.exists(REF_SO)
 

@@ -1,0 +1,46 @@
+"""CUDA subband transform (sbt_fwd.cu / sbt_inv.cu) through the C ABI vs the checkers, exact integers."""
+import numpy as np
+import pytest
+
+import dsvlibs as L
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(16, 16, 16, 16), (60, 34, 60, 34), (120, 68, 120, 68), (352, 288, 352, 288), (176, 144, 176, 144),
+         (427, 240, 428, 240), (959, 539, 960, 540), (135, 67, 136, 68), (480, 270, 480, 270),
+         (1920, 1080, 1920, 1080), (854, 480, 854, 480)]
+
+
+def _content(rng, ph, cols, kind):
+    if kind == "noise":
+        return rng.integers(0, 256, size=(ph, cols), dtype=np.uint8)
+    y, x = np.mgrid[0:ph, 0:cols]
+    v = 128 + 60 * np.sin(x / 9.0) + 50 * np.cos(y / 7.0) + rng.integers(-6, 7, size=(ph, cols))
+    return np.clip(v, 0, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("dims", SIZES)
+@pytest.mark.parametrize("isP", [0, 1])
+def test_fwd_inv_vs_port(gpu, port, dims, isP):
+    pw, ph, cw, ch = dims
+    rng = np.random.default_rng(pw + 3 * ph + isP)
+    for kind in ("noise", "smooth"):
+        pix = _content(rng, ph, cw + 2, kind)
+        a = port.fwd_sbt(pix, pw, ph, cw, ch, isP)
+        b = gpu.fwd_sbt(pix, pw, ph, cw, ch, isP)
+        assert np.array_equal(a, b)
+        for step in (1, 11):
+            co = (a // step) * step
+            for c in (0, 1):
+                assert np.array_equal(port.inv_sbt(co, 313, isP, c, pw, ph), gpu.inv_sbt(co, 313, isP, c, pw, ph))
+
+
+def test_uhd_vs_reference(gpu, ref):
+    rng = np.random.default_rng(11)
+    pix = _content(rng, 2160, 3840, "smooth")
+    for isP in (0, 1):
+        a = ref.fwd_sbt(pix, 3840, 2160, 3840, 2160, isP)
+        b = gpu.fwd_sbt(pix, 3840, 2160, 3840, 2160, isP)
+        assert np.array_equal(a, b)
+        co = (a // 13) * 13
+        assert np.array_equal(ref.inv_sbt(co, 313, isP, 0, 3840, 2160), gpu.inv_sbt(co, 313, isP, 0, 3840, 2160))
