@@ -8,6 +8,7 @@
  */
 #include "common.cuh"
 #include "sbt.cuh"
+#include "hzcc.cuh"
 
 using namespace dsv;
 
@@ -83,4 +84,80 @@ extern "C" int dsvk_inv_sbt(int32_t *coef_io, int cw, int ch, int q, int isP, in
     CUDA_CHECK(cudaDeviceSynchronize());
     CUDA_CHECK(cudaMemcpy2D(pix_out, stride, dp.origin, dp.stride, pw, ph, cudaMemcpyDeviceToHost));
     return 0;
+}
+
+/* forward transform with the fused quantiser, exactly as the encoder runs it (do_quant = 1) */
+extern "C" int dsvk_fwd_sbt_q(const uint8_t *pix, int stride, int pw, int ph, int cw, int ch, int isP, int c, int q,
+                              const uint8_t *stable, int nbh, int nbv, int32_t *coef_out, int32_t *dv_out)
+{
+    if ((cw & 1) || (ch & 1) || cw < 16 || ch < 16) {
+        return -1;
+    }
+    DevPlane dp(cw, ph);
+    CUDA_CHECK(cudaMemcpy2D(dp.origin, dp.stride, pix, stride, cw, ph, cudaMemcpyHostToDevice));
+    DevBuf coef((size_t) cw * ch * 4), llx(sbt_llx_elems(cw, ch) * 4), dv(sbt_dv_elems(cw, ch) * 4), jobs(sizeof(SbtJob));
+    DevBuf stab((size_t) nbh * nbv);
+    CUDA_CHECK(cudaMemset(coef.p, 0, (size_t) cw * ch * 4));
+    CUDA_CHECK(cudaMemset(dv.p, 0, sbt_dv_elems(cw, ch) * 4));
+    CUDA_CHECK(cudaMemcpy(stab.p, stable, (size_t) nbh * nbv, cudaMemcpyHostToDevice));
+    SbtJob j;
+    memset(&j, 0, sizeof(j));
+    sbt_fill_geometry(&j, pw, ph, cw, ch, isP, c);
+    sbt_fill_quant(&j, q, isP, c, nbh, nbv);
+    j.pix = dp.origin;
+    j.pstride = dp.stride;
+    j.coef = coef.as<int32_t>();
+    j.llx = llx.as<int32_t>();
+    j.dv = dv.as<int32_t>();
+    j.stable = stab.as<uint8_t>();
+    j.do_quant = 1;
+    CUDA_CHECK(cudaMemcpy(jobs.p, &j, sizeof(j), cudaMemcpyHostToDevice));
+    sbt_fwd_launch(jobs.as<SbtJob>(), 1, j.tiles_x * j.tiles_y, sbt_lo_smem_bytes(cw, ch), 0);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(coef_out, coef.p, (size_t) cw * ch * 4, cudaMemcpyDeviceToHost));
+    if (dv_out) {
+        CUDA_CHECK(cudaMemcpy(dv_out, dv.p, (size_t) j.dg.total * 4, cudaMemcpyDeviceToHost));
+    }
+    return j.dg.total;
+}
+
+/* dsv_encode_plane semantics (hzcc.c:449-476): raw coefficients in, plane bytes out, coef <- dequantised */
+extern "C" int dsvk_encode_plane(int32_t *coef_io, int cw, int ch, int q, int isP, int c, const uint8_t *stable,
+                                 int nbh, int nbv, uint8_t *out, int out_cap)
+{
+    if ((cw & 1) || (ch & 1) || cw < 16 || ch < 16) {
+        return -1;
+    }
+    HzJob j;
+    memset(&j, 0, sizeof(j));
+    hz_fill_job(&j, cw, ch, q, isP, c, nbh, nbv);
+    const size_t cap = (size_t) cw * ch * 8 + 256;
+    DevBuf coef((size_t) cw * ch * 4), dv(sbt_dv_elems(cw, ch) * 4), stab((size_t) nbh * nbv), pkt(cap);
+    DevBuf jobs(sizeof(HzJob)), chunks(sizeof(HzChunk) * j.nchunks), frames(sizeof(HzFrame));
+    CUDA_CHECK(cudaMemcpy(coef.p, coef_io, (size_t) cw * ch * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(stab.p, stable, (size_t) nbh * nbv, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemset(dv.p, 0, sbt_dv_elems(cw, ch) * 4));
+    CUDA_CHECK(cudaMemset(pkt.p, 0, cap));
+    j.coef = coef.as<int32_t>();
+    j.dv = dv.as<int32_t>();
+    j.stable = stab.as<uint8_t>();
+    j.chunk_base = 0;
+    j.frame = 0;
+    HzFrame f;
+    memset(&f, 0, sizeof(f));
+    f.pkt = pkt.as<uint8_t>();
+    f.start_byte = 0;
+    f.nplanes = 1;
+    CUDA_CHECK(cudaMemcpy(jobs.p, &j, sizeof(j), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(frames.p, &f, sizeof(f), cudaMemcpyHostToDevice));
+    hzcc_quant_launch(jobs.as<HzJob>(), 1, cw * ch, 0);
+    hzcc_enc_launch(jobs.as<HzJob>(), 1, chunks.as<HzChunk>(), j.nchunks, frames.as<HzFrame>(), 1, 0);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(&f, frames.p, sizeof(f), cudaMemcpyDeviceToHost));
+    if ((int) f.total_bytes > out_cap) {
+        return -2;
+    }
+    CUDA_CHECK(cudaMemcpy(out, pkt.p, f.total_bytes, cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(coef_io, coef.p, (size_t) cw * ch * 4, cudaMemcpyDeviceToHost));
+    return (int) f.total_bytes;
 }

@@ -16,61 +16,9 @@
  * HBM traffic per plane: w*h bytes read + 4*cw*ch bytes written -- the algorithmic minimum.
  */
 #include "sbt.cuh"
+#include "quant.cuh"
 
 namespace dsv {
-
-DSV_D int stab_flags(const SbtJob &J, const uint8_t *stab, int lvl, int bx, int by)
-{
-    return stab[((by * J.pq.dby[lvl]) >> 14) * J.pq.nbh + ((bx * J.pq.dbx[lvl]) >> 14)];
-}
-
-/* quantise + dequantise one coefficient of transform level lvl at band-local (bx,by) */
-DSV_D int requant(const SbtJob &J, const uint8_t *stab, int lvl, int bx, int by, int v)
-{
-    if (lvl >= 4) {
-        int s = dz_quant(v, J.pq.ll_q, J.pq.ll_fd);
-        return s ? dz_dequant(s, J.pq.ll_q) : 0;
-    }
-    int f = stab_flags(J, stab, lvl, bx, by);
-    if (lvl == 1) {
-        int sh = f ? J.pq.sh_hq : J.pq.sh_plain;
-        return p2_dequant(p2_quant(v, sh), sh);
-    }
-    int sel = (f & 2) ? 2 : (f ? 1 : 0);
-    const LevelQ &L = J.pq.lv[3 - lvl];
-    int s = dz_quant(v, L.q[sel], L.fd[sel]);
-    return s ? dz_dequant(s, L.q[sel]) : 0;
-}
-
-/* store one high-band coefficient (band: 1 = LH, 2 = HL, 3 = HH) */
-DSV_D void emit_h(const SbtJob &J, const uint8_t *stab, int lvl, int band, int bx, int by, int v)
-{
-    int wo = sbt_wo(J.cw, lvl), ho = sbt_wo(J.ch, lvl);
-    int ax = bx + ((band & 1) ? wo : 0), ay = by + ((band & 2) ? ho : 0);
-    if (J.do_quant) {
-        if (lvl <= 2) {
-            /* Position also scanned (first) by hzcc level of transform level lvl+1: the reference
-             * quantises it there, writes the dequantised value back, then quantises THAT again at
-             * this level.  Keep the first symbol for the entropy coder. */
-            const DvGeom &g = J.dg;
-            bool col = (ax == g.dvx[lvl]) && (ay < g.dvey[lvl]);
-            bool row = (ay == g.dvy[lvl]) && (ax < g.dvex[lvl]);
-            if (col || row) {
-                int U = lvl + 1;
-                int woU = sbt_wo(J.cw, U), hoU = sbt_wo(J.ch, U);
-                int lx = ax >= woU ? ax - woU : ax, ly = ay >= hoU ? ay - hoU : ay;
-                int f = stab_flags(J, stab, U, lx, ly);
-                int sel = (f & 2) ? 2 : (f ? 1 : 0);
-                const LevelQ &L = J.pq.lv[3 - U];
-                int s1 = dz_quant(v, L.q[sel], L.fd[sel]);
-                J.dv[col ? g.col_base[lvl] + ay : g.row_base[lvl] + ax] = s1;
-                v = s1 ? dz_dequant(s1, L.q[sel]) : 0;
-            }
-        }
-        v = requant(J, stab, lvl, bx, by, v);
-    }
-    J.coef[(size_t) ay * J.cw + ax] = v;
-}
 
 /* forward Haar butterfly for one pair with the reference's edge rules (sbt.c:290-347) */
 DSV_D void haar_fwd_pair(int x0, int x1, int x2, int x3, bool col2, bool row2, bool scale,
@@ -217,11 +165,11 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_fwd_tile_kernel(const Sb
             if (c < 64) {
                 llA[m * 64 + k] = lo;
                 if (valid) {
-                    emit_h(J, stab, 1, 2, gk, gm, hi);
+                    emit_h(J, J.do_quant != 0, stab, 1, 2, gk, gm, hi);
                 }
             } else if (valid) {
-                emit_h(J, stab, 1, 1, gk, gm, lo);
-                emit_h(J, stab, 1, 3, gk, gm, hi);
+                emit_h(J, J.do_quant != 0, stab, 1, 1, gk, gm, lo);
+                emit_h(J, J.do_quant != 0, stab, 1, 3, gk, gm, hi);
             }
         }
     } else {
@@ -240,13 +188,13 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_fwd_tile_kernel(const Sb
                               col2, row2, false, ll, lh, hl, hh);
                 llA[iy * 64 + ix] = ll;
                 if (col2) {
-                    emit_h(J, stab, 1, 1, gx, gy, lh);
+                    emit_h(J, J.do_quant != 0, stab, 1, 1, gx, gy, lh);
                 }
                 if (row2) {
-                    emit_h(J, stab, 1, 2, gx, gy, hl);
+                    emit_h(J, J.do_quant != 0, stab, 1, 2, gx, gy, hl);
                 }
                 if (col2 && row2) {
-                    emit_h(J, stab, 1, 3, gx, gy, hh);
+                    emit_h(J, J.do_quant != 0, stab, 1, 3, gx, gy, hh);
                 }
             }
         }
@@ -269,13 +217,13 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_fwd_tile_kernel(const Sb
                               col2, row2, true, ll, lh, hl, hh);
                 llB[iy * ow + ix] = ll;
                 if (col2) {
-                    emit_h(J, stab, lvl, 1, gx, gy, lh);
+                    emit_h(J, J.do_quant != 0, stab, lvl, 1, gx, gy, lh);
                 }
                 if (row2) {
-                    emit_h(J, stab, lvl, 2, gx, gy, hl);
+                    emit_h(J, J.do_quant != 0, stab, lvl, 2, gx, gy, hl);
                 }
                 if (col2 && row2) {
-                    emit_h(J, stab, lvl, 3, gx, gy, hh);
+                    emit_h(J, J.do_quant != 0, stab, lvl, 3, gx, gy, hh);
                 }
             }
         }
@@ -331,13 +279,13 @@ __global__ void __launch_bounds__(SBT_LO_THREADS) sbt_fwd_lo_kernel(const SbtJob
                           col2, row2, true, ll, lh, hl, hh);
             B[iy * wo + ix] = ll;
             if (col2) {
-                emit_h(J, J.stable, lvl, 1, ix, iy, lh);
+                emit_h(J, J.do_quant != 0, J.stable, lvl, 1, ix, iy, lh);
             }
             if (row2) {
-                emit_h(J, J.stable, lvl, 2, ix, iy, hl);
+                emit_h(J, J.do_quant != 0, J.stable, lvl, 2, ix, iy, hl);
             }
             if (col2 && row2) {
-                emit_h(J, J.stable, lvl, 3, ix, iy, hh);
+                emit_h(J, J.do_quant != 0, J.stable, lvl, 3, ix, iy, hh);
             }
         }
         __syncthreads();

@@ -251,3 +251,15 @@ def synth_sequence(w, h, fmt, nframes, seed, cut=0, start=0):
     got = lib.synth_sequence(w, h, hs, vs, start, nframes, seed, cut, ptr(out))
     assert got == n
     return out
+
+
+def fwd_sbt_q(lib, pix, pw, ph, cw, ch, isP, c, q, stable, nbh, nbv):
+    """Forward transform with the fused quantiser (product only): returns (dequantised coefs, dv side buffer)."""
+    pix = np.ascontiguousarray(pix, dtype=np.uint8)
+    stable = np.ascontiguousarray(stable, dtype=np.uint8)
+    out = np.zeros((ch, cw), dtype=np.int32)
+    dv = np.zeros(2 * (cw + ch) + 16, dtype=np.int32)
+    n = lib.fn("fwd_sbt_q")(ptr(pix), C.c_int(pix.shape[1]), pw, ph, cw, ch, isP, c, q, ptr(stable), nbh, nbv,
+                            ptr(out, i32p), ptr(dv, i32p))
+    assert n >= 0, n
+    return out, dv[:n]
