@@ -1,0 +1,605 @@
+/*
+ * hzcc_dec.cu -- HZCC coefficient coder, decoder side (hzcc_dec, hzcc.c:295-435; dsv_decode_plane,
+ * hzcc.c:478-496; exp-Golomb readers, bs.c:147-219) as a parallel bit-FSM parse.
+ *
+ * The token stream R0, R1,V0, R2,V1, ... R(n-1),V(n-2), V(n-1) has no synchronisation markers, but it
+ * is recognised by a 7-state automaton over single bits (interleaved exp-Golomb: flag,data pairs, a
+ * terminating 1-flag, and a sign bit after every V).  Function composition of per-word transition
+ * tables is associative, so token boundaries fall out of a prefix scan:
+ *
+ *   hzdec_fsm_kernel     per 32-bit word: exit state + number of token ends for each entry state;
+ *                        composed over the CTA (8192 bits) -> one table per CTA.
+ *   hzdec_link_kernel    one CTA per plane: scan of the CTA tables from the known start state
+ *                        -> entry state and token index of every CTA.
+ *   hzdec_token_kernel   per word again, now with known entry state: every token that STARTS in the
+ *                        word is decoded by that thread (reading ahead if it is longer) into runs[]
+ *                        or vals[]; validity against plen (hzcc.c:337-339) via atomicMin.
+ *   hzdec_runsum_kernel / hzdec_scatter_kernel
+ *                        inclusive scan of (run+1) gives each non-zero's scan position; it is mapped
+ *                        to (region, x, y), dequantised with that position's quantiser and written
+ *                        into the zeroed coefficient plane.  Positions scanned twice (SURVEY.md
+ *                        Appendix B-1) keep the decoder's semantics -- later scan position wins, an
+ *                        earlier value survives only where the later one is absent -- through
+ *                        atomicCAS on the first visit.
+ * R0 (the first token), SEG(DC) and nruns are read on the host while it parses the packet head.
+ */
+#include "hzcc.cuh"
+#include "scan.cuh"
+
+namespace dsv {
+
+enum { S_R0 = 0, S_RF = 1, S_RD = 2, S_V0 = 3, S_VF = 4, S_VD = 5, S_VS = 6, S_NUM = 7 };
+
+struct FsmSum {
+    unsigned exits;      /* 3 bits per entry state */
+    unsigned cnt[S_NUM]; /* token ends seen when entering in that state */
+};
+
+DSV_D int fsm_step(int s, int bit, unsigned &ends)
+{
+    switch (s) {
+        case S_R0:
+        case S_RF:
+            if (bit) {
+                ends++;
+                return S_V0;
+            }
+            return S_RD;
+        case S_RD:
+            return S_RF;
+        case S_V0:
+        case S_VF:
+            return bit ? S_VS : S_VD;
+        case S_VD:
+            return S_VF;
+        default: /* S_VS: the sign bit */
+            ends++;
+            return S_R0;
+    }
+}
+
+DSV_D FsmSum fsm_identity()
+{
+    FsmSum r;
+    r.exits = 0;
+#pragma unroll
+    for (int s = 0; s < S_NUM; s++) {
+        r.exits |= (unsigned) s << (3 * s);
+        r.cnt[s] = 0;
+    }
+    return r;
+}
+
+/* a happens first, then b */
+DSV_D FsmSum fsm_compose(const FsmSum &a, const FsmSum &b)
+{
+    FsmSum r;
+    r.exits = 0;
+#pragma unroll
+    for (int s = 0; s < S_NUM; s++) {
+        int e = (a.exits >> (3 * s)) & 7;
+        r.exits |= ((b.exits >> (3 * e)) & 7) << (3 * s);
+        r.cnt[s] = a.cnt[s] + b.cnt[e];
+    }
+    return r;
+}
+
+DSV_D FsmSum fsm_shfl_up(const FsmSum &v, int d)
+{
+    FsmSum r;
+    r.exits = __shfl_up_sync(0xffffffffu, v.exits, d);
+#pragma unroll
+    for (int s = 0; s < S_NUM; s++) {
+        r.cnt[s] = __shfl_up_sync(0xffffffffu, v.cnt[s], d);
+    }
+    return r;
+}
+
+struct HzDecJob {
+    HzJob hz;            /* geometry, quantisers, coef plane */
+    const uint8_t *body; /* plane bytes after the plen field (device) */
+    unsigned plen;       /* declared length */
+    unsigned avail;      /* bytes that may be read from body (to the end of the packet) */
+    unsigned tok_bit0;   /* bit position (from body) of the first token after R0 */
+    int nruns, first_run, dc;
+    int ntok;            /* tokens after R0 = 2*nruns - 1 (0 if nruns == 0) */
+    int32_t *runs, *vals; /* cap entries each */
+    int cap;
+    unsigned *first_bad; /* smallest k whose V token ends at or after plen */
+    FsmSum *cta_sum;     /* fsm_ncta entries */
+    unsigned *cta_entry; /* per CTA: entry state | token ends before << 3 */
+    int fsm_cta_base, fsm_ncta;
+    int scan_blk_base, scan_nblk;
+    unsigned long long *blk_sum; /* scan_nblk entries */
+};
+
+#define HZD_THREADS 256
+#define HZD_WORD_BITS 32
+#define HZD_CTA_BITS (HZD_THREADS * HZD_WORD_BITS)
+
+DSV_D unsigned body_bit(const HzDecJob &J, unsigned long long pos)
+{
+    unsigned long long byte = pos >> 3;
+    if (byte >= J.avail) {
+        return 0;
+    }
+    return (J.body[byte] >> (7 - (pos & 7))) & 1u;
+}
+/* 32 bits starting at bit position pos (MSB first), zero past the readable area */
+DSV_D unsigned body_word(const HzDecJob &J, unsigned long long pos)
+{
+    unsigned long long byte = pos >> 3;
+    unsigned long long acc = 0;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        unsigned long long b = (byte + i < J.avail) ? J.body[byte + i] : 0;
+        acc = (acc << 8) | b;
+    }
+    return (unsigned) (acc >> (8 - (pos & 7)));
+}
+
+template <class JT> DSV_D int dec_job_of(const JT *jobs, int njobs, int blk, int JT::*base)
+{
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].*base <= blk) {
+            lo = mid;
+        } else {
+            hi = mid - 1;
+        }
+    }
+    return lo;
+}
+
+/* per-thread table for its 32-bit word */
+DSV_D FsmSum word_summary(unsigned w)
+{
+    FsmSum r;
+    r.exits = 0;
+    const int reps[5] = {S_RF, S_RD, S_VF, S_VD, S_VS};
+    unsigned ex[5], ct[5];
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+        int s = reps[c];
+        unsigned ends = 0;
+#pragma unroll 8
+        for (int i = 31; i >= 0; i--) {
+            s = fsm_step(s, (w >> i) & 1, ends);
+        }
+        ex[c] = (unsigned) s;
+        ct[c] = ends;
+    }
+    const int cls[S_NUM] = {0, 0, 1, 2, 2, 3, 4};
+#pragma unroll
+    for (int s = 0; s < S_NUM; s++) {
+        r.exits |= ex[cls[s]] << (3 * s);
+        r.cnt[s] = ct[cls[s]];
+    }
+    return r;
+}
+
+/* inclusive scan of per-thread tables over the CTA; returns this thread's EXCLUSIVE prefix, *total = CTA table */
+DSV_D FsmSum block_scan_fsm(const FsmSum &mine, FsmSum *warp_tab /* [8] shared */, FsmSum *total)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    FsmSum inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        FsmSum n = fsm_shfl_up(inc, o);
+        if (lane >= o) {
+            inc = fsm_compose(n, inc);
+        }
+    }
+    FsmSum ex = fsm_shfl_up(inc, 1);
+    if (lane == 0) {
+        ex = fsm_identity();
+    }
+    if (lane == 31) {
+        warp_tab[wid] = inc;
+    }
+    __syncthreads();
+    FsmSum pre = fsm_identity();
+    for (int w = 0; w < wid; w++) {
+        pre = fsm_compose(pre, warp_tab[w]);
+    }
+    ex = fsm_compose(pre, ex);
+    if (total) {
+        FsmSum t = fsm_identity();
+        for (int w = 0; w < (int) (blockDim.x >> 5); w++) {
+            t = fsm_compose(t, warp_tab[w]);
+        }
+        *total = t;
+    }
+    __syncthreads();
+    return ex;
+}
+
+__global__ void __launch_bounds__(HZD_THREADS) hzdec_fsm_kernel(const HzDecJob *jobs, int njobs)
+{
+    __shared__ FsmSum warp_tab[8];
+    const int jid = dec_job_of(jobs, njobs, (int) blockIdx.x, &HzDecJob::fsm_cta_base);
+    const HzDecJob &J = jobs[jid];
+    const int cta = (int) blockIdx.x - J.fsm_cta_base;
+    const unsigned long long pos = (unsigned long long) J.tok_bit0 + (unsigned long long) cta * HZD_CTA_BITS +
+                                   (unsigned long long) threadIdx.x * HZD_WORD_BITS;
+    FsmSum mine = word_summary(body_word(J, pos));
+    FsmSum total;
+    block_scan_fsm(mine, warp_tab, &total);
+    if (threadIdx.x == 0) {
+        J.cta_sum[cta] = total;
+    }
+}
+
+/* one CTA per plane: entry state / token count of every fsm CTA, from the known state after R0 */
+__global__ void __launch_bounds__(HZD_THREADS) hzdec_link_kernel(const HzDecJob *jobs)
+{
+    __shared__ FsmSum warp_tab[8];
+    __shared__ unsigned s_state, s_count;
+    const HzDecJob &J = jobs[blockIdx.x];
+    if (threadIdx.x == 0) {
+        s_state = S_R0; /* after R0 comes R1: an R token starts (hzcc.c:173-181 order) */
+        s_count = 0;
+        *J.first_bad = 0x7fffffffu;
+    }
+    __syncthreads();
+    for (int b0 = 0; b0 < J.fsm_ncta; b0 += HZD_THREADS) {
+        const int c = b0 + (int) threadIdx.x;
+        FsmSum mine = c < J.fsm_ncta ? J.cta_sum[c] : fsm_identity();
+        FsmSum total;
+        FsmSum ex = block_scan_fsm(mine, warp_tab, &total);
+        const unsigned st = s_state, ct = s_count;
+        if (c < J.fsm_ncta) {
+            unsigned e = (ex.exits >> (3 * st)) & 7;
+            J.cta_entry[c] = e | ((ct + ex.cnt[st]) << 3);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_state = (total.exits >> (3 * st)) & 7;
+            s_count = ct + total.cnt[st];
+        }
+        __syncthreads();
+    }
+    /* tokens that never complete inside the readable bits are as good as truncated (hzcc.c:337-339) */
+    if (threadIdx.x == 0 && s_count < (unsigned) J.ntok) {
+        atomicMin(J.first_bad, s_count >> 1);
+    }
+}
+
+__global__ void __launch_bounds__(HZD_THREADS) hzdec_token_kernel(const HzDecJob *jobs, int njobs)
+{
+    __shared__ FsmSum warp_tab[8];
+    const int jid = dec_job_of(jobs, njobs, (int) blockIdx.x, &HzDecJob::fsm_cta_base);
+    const HzDecJob &J = jobs[jid];
+    const int cta = (int) blockIdx.x - J.fsm_cta_base;
+    const unsigned long long pos0 = (unsigned long long) J.tok_bit0 + (unsigned long long) cta * HZD_CTA_BITS +
+                                    (unsigned long long) threadIdx.x * HZD_WORD_BITS;
+    const unsigned w = body_word(J, pos0);
+    FsmSum mine = word_summary(w);
+    FsmSum ex = block_scan_fsm(mine, warp_tab, nullptr);
+    const unsigned ce = J.cta_entry[cta];
+    const unsigned cst = ce & 7;
+    int state = (int) ((ex.exits >> (3 * cst)) & 7);
+    long long tok = (long long) (ce >> 3) + ex.cnt[cst]; /* token ends before this word */
+    const bool at_start = (state == S_R0 || state == S_V0);
+    /* index of the token currently open (if mid-token) is `tok`; our first own token is the next one */
+    long long next_tok = at_start ? tok : tok + 1;
+    const long long last_tok = (long long) J.ntok - 1;
+
+    unsigned long long pos = pos0;
+    const unsigned long long end = pos0 + HZD_WORD_BITS;
+    const unsigned long long hard_end = (unsigned long long) J.avail * 8ull + 64ull;
+    bool own = false;       /* currently inside a token this thread owns */
+    unsigned v = 1;
+    unsigned dummy = 0;
+    while (pos < hard_end) {
+        const bool starting = (state == S_R0 || state == S_V0);
+        if (starting) {
+            if (pos >= end || next_tok > last_tok) {
+                break; /* tokens starting beyond our word belong to the next thread */
+            }
+            own = true;
+            v = 1;
+            if (next_tok == last_tok) {
+                state = S_V0; /* the final token is V(n-1) even though an R is due (hzcc.c:283-285) */
+            }
+        }
+        if (!own && pos >= end) {
+            break;
+        }
+        const unsigned bit = (pos >= pos0 && pos < end) ? ((w >> (31 - (unsigned) (pos - pos0))) & 1u) : body_bit(J, pos);
+        const int prev = state;
+        state = fsm_step(state, (int) bit, dummy);
+        pos++;
+        if (own) {
+            if (prev == S_RD || prev == S_VD) {
+                v = (v << 1) | bit;
+            } else if ((prev == S_R0 || prev == S_RF) && bit) {
+                /* R token complete: token index j = next_tok -> R_{j/2+1} */
+                long long k = (next_tok >> 1) + 1;
+                if (k < J.cap) {
+                    J.runs[k] = (int32_t) (v - 1u);
+                }
+                own = false;
+                next_tok++;
+            } else if (prev == S_VS) {
+                long long k = next_tok >> 1; /* V_k: token 2k+1, or the final token 2n-2 */
+                int val = (int) v; /* UEG + 1 (bs.c:214) */
+                if (val && bit) {
+                    val = -val;
+                }
+                if (k < J.cap) {
+                    J.vals[k] = val;
+                }
+                if ((pos >> 3) >= (unsigned long long) J.plen) { /* byte pointer after the read (hzcc.c:337) */
+                    atomicMin(J.first_bad, (unsigned) (k < 0x7fffffff ? k : 0x7fffffff));
+                }
+                own = false;
+                next_tok++;
+            }
+        }
+    }
+}
+
+#define HZS_THREADS 256
+#define HZS_ITEMS 4
+#define HZS_BLOCK (HZS_THREADS * HZS_ITEMS)
+
+DSV_D unsigned long long run_plus1(const HzDecJob &J, int k)
+{
+    if (k >= J.nruns || k >= J.cap) {
+        return 0;
+    }
+    unsigned r = k == 0 ? (unsigned) J.first_run : (unsigned) J.runs[k];
+    return (unsigned long long) r + 1ull;
+}
+
+__global__ void __launch_bounds__(HZS_THREADS) hzdec_runsum_kernel(const HzDecJob *jobs, int njobs)
+{
+    __shared__ unsigned long long scratch[40];
+    const int jid = dec_job_of(jobs, njobs, (int) blockIdx.x, &HzDecJob::scan_blk_base);
+    const HzDecJob &J = jobs[jid];
+    const int blk = (int) blockIdx.x - J.scan_blk_base;
+    unsigned long long s = 0, tot;
+    for (int i = 0; i < HZS_ITEMS; i++) {
+        s += run_plus1(J, blk * HZS_BLOCK + (int) threadIdx.x * HZS_ITEMS + i);
+    }
+    block_scan_incl<OpAdd64>(s, scratch, &tot);
+    if (threadIdx.x == 0) {
+        J.blk_sum[blk] = tot;
+    }
+}
+
+/* one CTA per plane: exclusive scan of the block sums, in place */
+__global__ void __launch_bounds__(1024) hzdec_blkscan_kernel(const HzDecJob *jobs)
+{
+    __shared__ unsigned long long scratch[40];
+    __shared__ unsigned long long s_carry;
+    const HzDecJob &J = jobs[blockIdx.x];
+    if (threadIdx.x == 0) {
+        s_carry = 0;
+    }
+    __syncthreads();
+    for (int b0 = 0; b0 < J.scan_nblk; b0 += 1024) {
+        const int i = b0 + (int) threadIdx.x;
+        unsigned long long v = i < J.scan_nblk ? J.blk_sum[i] : 0, tot;
+        unsigned long long ex = block_scan_excl<OpAdd64>(v, scratch, &tot);
+        const unsigned long long carry = s_carry;
+        if (i < J.scan_nblk) {
+            J.blk_sum[i] = carry + ex;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_carry = carry + tot;
+        }
+        __syncthreads();
+    }
+}
+
+/* dequantise value v for scan position s and store it (hzcc.c:327-432) */
+DSV_D void scatter_one(const HzDecJob &D, unsigned long long s, int v)
+{
+    const HzJob &J = D.hz;
+    const HzRegions &rg = J.rg;
+    if (s >= (unsigned long long) rg.base[HZ_NREG] || s == 0) {
+        return; /* past the plane, or the DC slot which is overwritten afterwards (hzcc.c:495) */
+    }
+    int r = 0;
+    while ((int) s >= rg.base[r + 1]) {
+        r++;
+    }
+    const int k = (int) s - rg.base[r];
+    const int y = (int) fastdiv((unsigned) k, rg.fdw[r]);
+    const int x = k - y * rg.sw[r];
+    const int ax = rg.x0[r] + x, ay = rg.y0[r] + y;
+    const int lvl = rg.lvl[r];
+    int out;
+    bool first_visit = false;
+    if (r == 0) {
+        out = dz_dequant(v, J.pq.ll_q);
+    } else {
+        const int f = J.stable[((y * J.pq.dby[lvl]) >> 14) * J.pq.nbh + ((x * J.pq.dbx[lvl]) >> 14)];
+        if (lvl == 1) {
+            out = p2_dequant(v, f ? J.pq.sh_hq : J.pq.sh_plain);
+        } else {
+            const int sel = (f & 2) ? 2 : (f ? 1 : 0);
+            out = dz_dequant(v, J.pq.lv[3 - lvl].q[sel]);
+            const DvGeom &g = J.dg;
+            const int L = lvl - 1;
+            first_visit = ((ax == g.dvx[L]) && (ay < g.dvey[L])) || ((ay == g.dvy[L]) && (ax < g.dvex[L]));
+        }
+    }
+    int32_t *dst = J.coef + (size_t) ay * J.cw + ax;
+    if (first_visit) {
+        /* the next hzcc level scans this element again and overwrites it if it codes a value there */
+        atomicCAS(reinterpret_cast<unsigned *>(dst), 0u, (unsigned) out);
+    } else {
+        *dst = out;
+    }
+}
+
+__global__ void __launch_bounds__(HZS_THREADS) hzdec_scatter_kernel(const HzDecJob *jobs, int njobs)
+{
+    __shared__ unsigned long long scratch[40];
+    const int jid = dec_job_of(jobs, njobs, (int) blockIdx.x, &HzDecJob::scan_blk_base);
+    const HzDecJob &J = jobs[jid];
+    const int blk = (int) blockIdx.x - J.scan_blk_base;
+    const int k0 = blk * HZS_BLOCK + (int) threadIdx.x * HZS_ITEMS;
+    unsigned long long rp[HZS_ITEMS], s = 0, tot;
+    for (int i = 0; i < HZS_ITEMS; i++) {
+        rp[i] = run_plus1(J, k0 + i);
+        s += rp[i];
+    }
+    unsigned long long pos = J.blk_sum[blk] + block_scan_excl<OpAdd64>(s, scratch, &tot);
+    const unsigned bad = *J.first_bad;
+    const int n = J.nruns < J.cap ? J.nruns : J.cap;
+    for (int i = 0; i < HZS_ITEMS; i++) {
+        const int k = k0 + i;
+        pos += rp[i];
+        if (k < n && (unsigned) k < bad) {
+            scatter_one(J, pos - 1ull, J.vals[k]);
+        }
+    }
+    if (blk == 0 && threadIdx.x == 0) {
+        J.hz.coef[0] = J.dc;
+    }
+}
+
+/* DC when a plane has no tokens at all (no scatter blocks are launched for it) */
+__global__ void hzdec_dc_kernel(const HzDecJob *jobs, int njobs)
+{
+    int j = (int) (blockIdx.x * blockDim.x + threadIdx.x);
+    if (j < njobs) {
+        jobs[j].hz.coef[0] = jobs[j].dc;
+    }
+}
+
+size_t hzdec_job_size() { return sizeof(HzDecJob); }
+
+} // namespace dsv
+
+#include "hzcc_dec.cuh"
+#include "host/bits.h"
+
+namespace dsv {
+
+void hzdec_parse_head(const uint8_t *host_body, unsigned avail, unsigned plen, HzPlaneData *pd)
+{
+    BitReader br(host_body, avail);
+    pd->dc = br.get_seg();
+    br.align();
+    pd->nruns = (int) br.get_bits(32);
+    br.align();
+    pd->first_run = pd->nruns > 0 ? (int) br.get_ueg() : 0;
+    pd->tok_bit0 = (unsigned) br.pos;
+    pd->plen = plen;
+    pd->avail = avail;
+    pd->body = nullptr;
+}
+
+void hzdec_plan(HzDecPlan *pl, int cw, int ch)
+{
+    HzRegions r;
+    hz_fill_regions(&r, cw, ch);
+    pl->cap = r.base[HZ_NREG];
+    pl->max_bits = (size_t) cw * ch * 8 * 8 + 4096; /* plen <= 2 * framesz (dsv_decoder.c:397-401) */
+    pl->max_fsm_cta = (int) ((pl->max_bits + HZD_CTA_BITS - 1) / HZD_CTA_BITS) + 1;
+    pl->max_scan_blk = ceil_div(pl->cap, HZS_BLOCK) + 1;
+}
+
+void hzdec_alloc(HzDecBufs *b, const HzDecPlan pl[3])
+{
+    CUDA_CHECK(cudaMalloc(&b->d_jobs, 3 * sizeof(HzDecJob)));
+    b->h_jobs = malloc(3 * sizeof(HzDecJob));
+    for (int p = 0; p < 3; p++) {
+        CUDA_CHECK(cudaMalloc(&b->runs[p], (size_t) (pl[p].cap + 8) * 4));
+        CUDA_CHECK(cudaMalloc(&b->vals[p], (size_t) (pl[p].cap + 8) * 4));
+        CUDA_CHECK(cudaMalloc(&b->cta_sum[p], (size_t) pl[p].max_fsm_cta * sizeof(FsmSum)));
+        CUDA_CHECK(cudaMalloc(&b->cta_entry[p], (size_t) pl[p].max_fsm_cta * 4));
+        CUDA_CHECK(cudaMalloc(&b->blk_sum[p], (size_t) pl[p].max_scan_blk * 8));
+        CUDA_CHECK(cudaMalloc(&b->first_bad[p], 4));
+        b->plan[p] = pl[p];
+    }
+}
+
+void hzdec_free(HzDecBufs *b)
+{
+    cudaFree(b->d_jobs);
+    free(b->h_jobs);
+    for (int p = 0; p < 3; p++) {
+        cudaFree(b->runs[p]);
+        cudaFree(b->vals[p]);
+        cudaFree(b->cta_sum[p]);
+        cudaFree(b->cta_entry[p]);
+        cudaFree(b->blk_sum[p]);
+        cudaFree(b->first_bad[p]);
+    }
+    memset(b, 0, sizeof(*b));
+}
+
+/*
+ * Decode the coefficient planes described by `pd` (nplanes <= 3) into their (already zeroed) coef arrays.
+ * hz[p] carries geometry/quantisers/coef pointer; pd[p] the plane's bytes inside the device packet.
+ */
+void hzdec_launch(HzDecBufs *b, const HzJob *hz, const HzPlaneData *pd, int nplanes, cudaStream_t st)
+{
+    HzDecJob *hj = reinterpret_cast<HzDecJob *>(b->h_jobs);
+    int fsm_base = 0, scan_base = 0;
+    for (int p = 0; p < nplanes; p++) {
+        HzDecJob &J = hj[p];
+        memset(&J, 0, sizeof(J));
+        J.hz = hz[p];
+        J.body = pd[p].body;
+        J.plen = pd[p].plen;
+        J.avail = pd[p].avail;
+        J.tok_bit0 = pd[p].tok_bit0;
+        J.nruns = pd[p].nruns;
+        J.first_run = pd[p].first_run;
+        J.dc = pd[p].dc;
+        J.cap = b->plan[p].cap;
+        int n = J.nruns < 0 ? 0 : (J.nruns > J.cap ? J.cap : J.nruns);
+        J.ntok = J.nruns > 0 ? (J.nruns > 0x3fffffff ? 0x7ffffffe : 2 * J.nruns - 1) : 0;
+        J.runs = b->runs[p];
+        J.vals = b->vals[p];
+        J.first_bad = b->first_bad[p];
+        J.cta_sum = reinterpret_cast<FsmSum *>(b->cta_sum[p]);
+        J.cta_entry = b->cta_entry[p];
+        J.blk_sum = b->blk_sum[p];
+        /* bits that can hold usable tokens: up to plen (a token ending at/after plen invalidates the rest) */
+        unsigned long long lim = (unsigned long long) (J.plen < J.avail ? J.plen : J.avail) * 8ull + 64ull;
+        unsigned long long nbits = lim > J.tok_bit0 ? lim - J.tok_bit0 : 0;
+        J.fsm_ncta = J.ntok > 0 ? (int) ((nbits + HZD_CTA_BITS - 1) / HZD_CTA_BITS) : 0;
+        if (J.fsm_ncta > b->plan[p].max_fsm_cta) {
+            J.fsm_ncta = b->plan[p].max_fsm_cta;
+        }
+        J.fsm_cta_base = fsm_base;
+        fsm_base += J.fsm_ncta;
+        J.scan_nblk = ceil_div(n, HZS_BLOCK);
+        J.scan_blk_base = scan_base;
+        scan_base += J.scan_nblk;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(b->d_jobs, hj, (size_t) nplanes * sizeof(HzDecJob), cudaMemcpyHostToDevice, st));
+    const HzDecJob *dj = reinterpret_cast<const HzDecJob *>(b->d_jobs);
+    if (fsm_base > 0) {
+        DSV_LAUNCH(hzdec_fsm_kernel, dim3(fsm_base), dim3(HZD_THREADS), 0, st, dj, nplanes);
+        KERNEL_CHECK();
+    }
+    DSV_LAUNCH(hzdec_link_kernel, dim3(nplanes), dim3(HZD_THREADS), 0, st, dj);
+    KERNEL_CHECK();
+    if (fsm_base > 0) {
+        DSV_LAUNCH(hzdec_token_kernel, dim3(fsm_base), dim3(HZD_THREADS), 0, st, dj, nplanes);
+        KERNEL_CHECK();
+    }
+    DSV_LAUNCH(hzdec_dc_kernel, dim3(1), dim3(32), 0, st, dj, nplanes);
+    KERNEL_CHECK();
+    if (scan_base > 0) {
+        DSV_LAUNCH(hzdec_runsum_kernel, dim3(scan_base), dim3(HZS_THREADS), 0, st, dj, nplanes);
+        KERNEL_CHECK();
+        DSV_LAUNCH(hzdec_blkscan_kernel, dim3(nplanes), dim3(1024), 0, st, dj);
+        KERNEL_CHECK();
+        DSV_LAUNCH(hzdec_scatter_kernel, dim3(scan_base), dim3(HZS_THREADS), 0, st, dj, nplanes);
+        KERNEL_CHECK();
+    }
+}
+
+} // namespace dsv

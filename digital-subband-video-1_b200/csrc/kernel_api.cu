@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "sbt.cuh"
 #include "hzcc.cuh"
+#include "hzcc_dec.cuh"
 
 using namespace dsv;
 
@@ -160,4 +161,37 @@ extern "C" int dsvk_encode_plane(int32_t *coef_io, int cw, int ch, int q, int is
     CUDA_CHECK(cudaMemcpy(out, pkt.p, f.total_bytes, cudaMemcpyDeviceToHost));
     CUDA_CHECK(cudaMemcpy(coef_io, coef.p, (size_t) cw * ch * 4, cudaMemcpyDeviceToHost));
     return (int) f.total_bytes;
+}
+
+/* dsv_decode_plane semantics (hzcc.c:478-496): `in` points just after the 32-bit plen field */
+extern "C" int dsvk_decode_plane(const uint8_t *in, int plen, int cw, int ch, int q, int isP, int c,
+                                 const uint8_t *stable, int nbh, int nbv, int32_t *coef_out)
+{
+    if ((cw & 1) || (ch & 1) || cw < 16 || ch < 16 || plen <= 0) {
+        return -1;
+    }
+    HzJob j;
+    memset(&j, 0, sizeof(j));
+    hz_fill_job(&j, cw, ch, q, isP, c, nbh, nbv);
+    DevBuf coef((size_t) cw * ch * 4), stab((size_t) nbh * nbv), body((size_t) plen + 64);
+    CUDA_CHECK(cudaMemset(coef.p, 0, (size_t) cw * ch * 4));
+    CUDA_CHECK(cudaMemset(body.p, 0, (size_t) plen + 64));
+    CUDA_CHECK(cudaMemcpy(body.p, in, (size_t) plen, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(stab.p, stable, (size_t) nbh * nbv, cudaMemcpyHostToDevice));
+    j.coef = coef.as<int32_t>();
+    j.stable = stab.as<uint8_t>();
+    HzPlaneData pd;
+    hzdec_parse_head(in, (unsigned) plen, (unsigned) plen, &pd);
+    pd.body = body.as<uint8_t>();
+    HzDecPlan pl[3];
+    hzdec_plan(&pl[0], cw, ch);
+    pl[1] = pl[2] = pl[0];
+    pl[1].cap = pl[2].cap = 8; pl[1].max_fsm_cta = pl[2].max_fsm_cta = 1; pl[1].max_scan_blk = pl[2].max_scan_blk = 1;
+    HzDecBufs bufs;
+    hzdec_alloc(&bufs, pl);
+    hzdec_launch(&bufs, &j, &pd, 1, 0);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(coef_out, coef.p, (size_t) cw * ch * 4, cudaMemcpyDeviceToHost));
+    hzdec_free(&bufs);
+    return 0;
 }

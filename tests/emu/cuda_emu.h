@@ -273,6 +273,12 @@ static inline int atomicMin(int *p, int v)
     while (o > v && !__atomic_compare_exchange_n(p, &o, v, 0, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
     return o;
 }
+static inline unsigned atomicMin(unsigned *p, unsigned v)
+{
+    unsigned o = *p;
+    while (o > v && !__atomic_compare_exchange_n(p, &o, v, 0, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return o;
+}
 static inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned v)
 {
     __atomic_compare_exchange_n(p, &cmp, v, 0, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
