@@ -1,0 +1,605 @@
+/*
+ * hme.cu -- hierarchical motion estimation.  Replaces refine_level / dsv_hme and their helpers
+ * (hme.c:32-741): candidate inheritance from the parent level, 9-point full-pel SAD search, and at
+ * level 0 the half-pel refinement on the 14x14 centre patch, the block statistics and the
+ * intra / inter decision with its quadrant mask.
+ *
+ *   hme_level_kernel   levels > 0: one CTA per visited block.  The source block is staged once in
+ *                      shared memory as aligned 32-bit words; every candidate's SAD is accumulated
+ *                      with __vsadu4 over unaligned reference words (two aligned loads + funnel
+ *                      shift), reduced with warp shuffles; thread 0 takes the FIRST minimum in the
+ *                      reference's candidate order (strict '<', hme.c:503,531).
+ *   hme_l0_kernel      level 0: the same search, then the 32x32 half-pel image of the 16x16
+ *                      reference patch (hme.c:350-376) built in shared memory, 8 half-pel SADs,
+ *                      and ~30 block sums (variance / texture / chroma variance / quadrant
+ *                      good-vs-evil metric) reduced in one pass; thread 0 runs the decision cascade
+ *                      (hme.c:651-718).  All unsigned 32-bit wrap-arounds of the reference are kept.
+ *   hme_neigh_kernel   high_detail needs the left / top / top-left blocks' final mode and flags
+ *                      (hme.c:621-648): a second, one-thread-per-block pass.
+ *
+ * Search order, tie-breaking, clamps and the "last candidate" default follow SURVEY.md section 3.3
+ * and Appendix B-5/B-6 exactly; MV fields come out byte-identical to the reference's DSV_MV records.
+ */
+#include "motion.cuh"
+
+namespace dsv {
+
+#define HME_THREADS 256
+#define HME_SRC_STRIDE 64 /* bytes per staged block row */
+#define HP_SAD_SZ 14
+#define HP_DIM 16
+#define HP_STRIDE 32
+
+struct HmePlane {
+    const uint8_t *p;
+    int stride, w, h;
+};
+struct HmeArgs {
+    HmePlane src, ref;       /* luma at this level */
+    HmePlane srcU, srcV, refU, refV; /* level 0 only */
+    const DevMV *parent;     /* level + 1 field or null */
+    DevMV *out;
+    int2 *aux;               /* level 0: (luma_tex, src_var) per block for the neighbour pass */
+    int *nintra;
+    int level, blk_w, blk_h, nbh, nbv, hs, vs;
+};
+
+/* 4 bytes at an arbitrary address: two aligned loads + funnel shift (generic address space) */
+DSV_D unsigned ld4u(const uint8_t *p)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned *q = reinterpret_cast<const unsigned *>(a & ~(uintptr_t) 3);
+    const unsigned sh = (unsigned) (a & 3) * 8;
+    const unsigned lo = q[0];
+    if (sh == 0) {
+        return lo;
+    }
+    return __funnelshift_r(lo, q[1], sh);
+}
+
+template <int N> DSV_D void block_reduce_n(unsigned (&acc)[N], unsigned *scratch /* >= 8 * N */)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        acc[k] = __reduce_add_sync(0xffffffffu, acc[k]);
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            scratch[wid * N + k] = acc[k];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        unsigned t = 0;
+        for (int w = 0; w < nw; w++) {
+            t += scratch[w * N + k];
+        }
+        acc[k] = t;
+    }
+}
+
+struct BlockGeom {
+    int bx, by, bw, bh, words;
+    unsigned tail_mask;
+};
+
+/*
+ * Candidate selection + 9-point full-pel search (hme.c:439-541).  Every thread of the block calls;
+ * the result (full-pel dx, dy at this level and the winning SAD) is returned to all threads.
+ * s_src: staged source block (HME_SRC_STRIDE bytes per row, bytes past bw zero).
+ */
+DSV_D void search_block(const HmeArgs &A, int i, int j, const BlockGeom &G, const uint8_t *s_src, unsigned *scratch,
+                        int *s_res, int &odx, int &ody, int &obest)
+{
+    __shared__ int s_cx[8], s_cy[8], s_valid[8], s_n;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int level = A.level;
+    const int W = A.ref.w, H = A.ref.h;
+    const int rs = A.ref.stride;
+
+    if (tid == 0) {
+        int n = 0;
+        int call[8];
+        call[n] = 0;
+        s_cx[n] = 0;
+        s_cy[n] = 0;
+        n++;
+        if (A.parent) {
+            const int step = 1 << level;
+            const int pmask = ~((step << 1) - 1);
+            const int pi = i & pmask, pj = j & pmask;
+            const int ptx[5] = {0, -2, 2, 0, 0}, pty[5] = {0, 0, 0, -2, 2};
+            for (int m = 0; m < 5; m++) {
+                const int x = pi + ptx[m] * step, y = pj + pty[m] * step;
+                if (x >= 0 && x < A.nbh && y >= 0 && y < A.nbv) {
+                    const DevMV pm = A.parent[x + y * A.nbh];
+                    const int all = (int) ((unsigned) (uint16_t) pm.x | ((unsigned) (uint16_t) pm.y << 16));
+                    if (all) {
+                        bool exists = false;
+                        for (int k = 0; k < n; k++) {
+                            exists |= call[k] == all;
+                        }
+                        if (!exists) {
+                            call[n] = all;
+                            s_cx[n] = pm.x;
+                            s_cy[n] = pm.y;
+                            n++;
+                        }
+                    }
+                }
+            }
+        }
+        for (int k = 0; k < n; k++) {
+            const int dx = s_cx[k] >> level, dy = s_cy[k] >> level;
+            const int x = G.bx + dx, y = G.by + dy;
+            s_valid[k] = !(x < -DSV_BORDER || y < -DSV_BORDER || x + G.bw > W + DSV_BORDER || y + G.bh > H + DSV_BORDER);
+        }
+        s_n = n;
+    }
+    __syncthreads();
+    const int n = s_n;
+    int best_k = n - 1;
+    if (n > 1) {
+        unsigned acc[6] = {0, 0, 0, 0, 0, 0};
+        for (int idx = tid; idx < G.words * G.bh; idx += nthr) {
+            const int r = idx / G.words, wx = idx - r * G.words;
+            const unsigned m = (wx == G.words - 1) ? G.tail_mask : 0xffffffffu;
+            const unsigned a = *reinterpret_cast<const unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * wx);
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                if (k < n && s_valid[k]) {
+                    const int dx = s_cx[k] >> level, dy = s_cy[k] >> level;
+                    const unsigned b = ld4u(A.ref.p + (ptrdiff_t) (G.by + dy + r) * rs + G.bx + dx + 4 * wx) & m;
+                    acc[k] += __vsadu4(a, b);
+                }
+            }
+        }
+        block_reduce_n<6>(acc, scratch);
+        int best_score = 0x7fffffff;
+        for (int k = 0; k < n; k++) {
+            if (s_valid[k] && best_score > (int) acc[k]) {
+                best_score = (int) acc[k];
+                best_k = k;
+            }
+        }
+    }
+    int dx = s_cx[best_k] >> level, dy = s_cy[best_k] >> level;
+    dx = iclamp(dx, -G.bw - G.bx, W - G.bx);
+    dy = iclamp(dy, -G.bh - G.by, H - G.by);
+    const int xx = G.bx + dx, yy = G.by + dy;
+    const int xf[9] = {0, 1, -1, 0, 0, -1, 1, -1, 1}, yf[9] = {0, 0, 0, 1, -1, -1, -1, 1, 1};
+    unsigned acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int idx = tid; idx < G.words * G.bh; idx += nthr) {
+        const int r = idx / G.words, wx = idx - r * G.words;
+        const unsigned m = (wx == G.words - 1) ? G.tail_mask : 0xffffffffu;
+        const unsigned a = *reinterpret_cast<const unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * wx);
+        const uint8_t *rp = A.ref.p + (ptrdiff_t) (yy + r) * rs + xx + 4 * wx;
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            acc[k] += __vsadu4(a, ld4u(rp + yf[k] * rs + xf[k]) & m);
+        }
+    }
+    block_reduce_n<9>(acc, scratch);
+    int best = 0x7fffffff, m = 0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+        if (best > (int) acc[k]) {
+            best = (int) acc[k];
+            m = k;
+        }
+    }
+    odx = dx + xf[m];
+    ody = dy + yf[m];
+    obest = best;
+    (void) s_res;
+    __syncthreads();
+}
+
+DSV_D bool block_setup(const HmeArgs &A, int i, int j, BlockGeom &G, uint8_t *s_src)
+{
+    G.bx = (i * A.blk_w) >> A.level;
+    G.by = (j * A.blk_h) >> A.level;
+    if (G.bx >= A.src.w || G.by >= A.src.h) {
+        return false;
+    }
+    G.bw = imin(A.src.w - G.bx, A.blk_w);
+    G.bh = imin(A.src.h - G.by, A.blk_h);
+    G.words = (G.bw + 3) >> 2;
+    const int tail = G.bw & 3;
+    G.tail_mask = tail ? ((1u << (8 * tail)) - 1u) : 0xffffffffu;
+    for (int idx = threadIdx.x; idx < G.words * G.bh; idx += blockDim.x) {
+        const int r = idx / G.words, wx = idx - r * G.words;
+        const unsigned m = (wx == G.words - 1) ? G.tail_mask : 0xffffffffu;
+        *reinterpret_cast<unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * wx) =
+            ld4u(A.src.p + (ptrdiff_t) (G.by + r) * A.src.stride + G.bx + 4 * wx) & m;
+    }
+    __syncthreads();
+    return true;
+}
+
+DSV_D void store_mv(DevMV *dst, int x, int y, int mode, int submask, int lo_var, int lo_tex)
+{
+    DevMV m;
+    m.x = (int16_t) x;
+    m.y = (int16_t) y;
+    m.mode = (uint8_t) mode;
+    m.submask = (uint8_t) submask;
+    m.lo_var = (uint8_t) lo_var;
+    m.lo_tex = (uint8_t) lo_tex;
+    m.high_detail = 0;
+    m.pad[0] = m.pad[1] = m.pad[2] = 0;
+    *dst = m;
+}
+
+__global__ void __launch_bounds__(HME_THREADS) hme_level_kernel(HmeArgs A)
+{
+    __shared__ __align__(16) uint8_t s_src[64 * HME_SRC_STRIDE];
+    __shared__ unsigned scratch[8 * 9];
+    const int step = 1 << A.level;
+    const int i = (int) blockIdx.x * step, j = (int) blockIdx.y * step;
+    BlockGeom G;
+    if (!block_setup(A, i, j, G, s_src)) {
+        if (threadIdx.x == 0) {
+            store_mv(&A.out[i + j * A.nbh], 0, 0, 0, 0, 0, 0);
+        }
+        return;
+    }
+    int dx, dy, best;
+    search_block(A, i, j, G, s_src, scratch, nullptr, dx, dy, best);
+    if (threadIdx.x == 0) {
+        store_mv(&A.out[i + j * A.nbh], dx << A.level, dy << A.level, 0, 0, 0, 0);
+    }
+}
+
+enum {
+    SUM_S, SUM_SS, SUM_SH, SUM_SV,          /* source block: block_analysis */
+    SUM_RS, SUM_RSS,                        /* zero-MV reference block: y_sqrvar, block_intra_test mean */
+    SUM_CSU, SUM_CSSU, SUM_CSV, SUM_CSSV,   /* source chroma */
+    SUM_CRU, SUM_CRSU, SUM_CRV, SUM_CRSV,   /* reference chroma */
+    SUM_PSH, SUM_PSV, SUM_PAV, SUM_PAVS,    /* source 14x14 patch: block_texture */
+    SUM_QSH, SUM_QSV, SUM_QAV, SUM_QAVS,    /* chosen reference patch */
+    SUM_GOOD0, SUM_GOOD1, SUM_GOOD2, SUM_GOOD3, SUM_EVIL0, SUM_EVIL1, SUM_EVIL2, SUM_EVIL3,
+    SUM_COUNT
+};
+
+__global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(HmeArgs A)
+{
+    __shared__ __align__(16) uint8_t s_src[64 * HME_SRC_STRIDE];
+    __shared__ __align__(16) uint8_t s_ref0[64 * HME_SRC_STRIDE];
+    __shared__ unsigned scratch[8 * SUM_COUNT];
+    __shared__ int16_t s_hbuf[(HP_DIM + 4) * HP_DIM];
+    __shared__ uint8_t s_tmp[HP_STRIDE * HP_STRIDE];
+    __shared__ uint8_t s_refblk[HP_SAD_SZ * HP_SAD_SZ];
+    __shared__ int s_flag;
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x, j = blockIdx.y;
+    DevMV *out = &A.out[i + j * A.nbh];
+    BlockGeom G;
+    if (!block_setup(A, i, j, G, s_src)) {
+        if (tid == 0) {
+            store_mv(out, 0, 0, 0, 0, 0, 0);
+            A.aux[i + j * A.nbh] = make_int2(0, 0);
+        }
+        return;
+    }
+    int fx, fy, best;
+    search_block(A, i, j, G, s_src, scratch, nullptr, fx, fy, best);
+
+    const int rs = A.ref.stride, ss = A.src.stride;
+    const unsigned yarea = (unsigned) (G.bw * G.bh);
+    const unsigned yareasq = yarea * yarea;
+    const int cx = G.bx + ((G.bw >> 1) - (HP_SAD_SZ / 2)), cy = G.by + ((G.bh >> 1) - (HP_SAD_SZ / 2));
+    int mvx = fx, mvy = fy;
+    bool has_hp = false;
+
+    /* ---- half-pel refinement (hme.c:551-591) ---- */
+    if (best > A.blk_w * A.blk_h) {
+        int best_hp = (int) ((unsigned) (best * (HP_SAD_SZ * HP_SAD_SZ)) / yarea);
+        const uint8_t *rp0 = A.ref.p + (ptrdiff_t) (cy + mvy - 1) * rs + (cx + mvx - 1); /* hpel()'s `ref` */
+        for (int k = tid; k < (HP_DIM + 4) * HP_DIM; k += HME_THREADS) {
+            const int jj = k / HP_DIM, ii = k - jj * HP_DIM;
+            const uint8_t *p = rp0 + (ptrdiff_t) (jj - 1) * rs + ii;
+            s_hbuf[k] = (int16_t) (9 * (p[0] + p[1]) - (p[-1] + p[2]));
+        }
+        __syncthreads();
+        for (int k = tid; k < HP_DIM * HP_DIM; k += HME_THREADS) {
+            const int jj = k / HP_DIM, ii = k - jj * HP_DIM;
+            const uint8_t *p = rp0 + (ptrdiff_t) jj * rs + ii;
+            uint8_t *d = s_tmp + (2 * jj) * HP_STRIDE + 2 * ii;
+            d[0] = p[0];
+            d[HP_STRIDE] = clamp_u8((9 * (p[0] + p[rs]) - (p[-rs] + p[2 * rs]) + 8) >> 4);
+            d[1] = clamp_u8((9 * (p[0] + p[1]) - (p[-1] + p[2]) + 8) >> 4);
+            const int16_t *b = s_hbuf + k;
+            d[HP_STRIDE + 1] = clamp_u8((9 * (b[HP_DIM] + b[2 * HP_DIM]) - (b[0] + b[3 * HP_DIM]) + 128) >> 8);
+        }
+        __syncthreads();
+        const int xh[8] = {1, -1, 0, 0, -1, 1, -1, 1}, yh[8] = {0, 0, 1, -1, -1, -1, 1, 1};
+        const uint8_t *tmph = s_tmp + 2 + 2 * HP_STRIDE;
+        unsigned acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (tid < HP_SAD_SZ * HP_SAD_SZ) {
+            const int jj = tid / HP_SAD_SZ, ii = tid - jj * HP_SAD_SZ;
+            const int sp = A.src.p[(ptrdiff_t) (cy + jj) * ss + cx + ii];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                acc[k] = (unsigned) iabs(sp - (int) tmph[xh[k] + yh[k] * HP_STRIDE + 2 * ii + 2 * HP_STRIDE * jj]);
+            }
+        }
+        block_reduce_n<8>(acc, scratch);
+        int m = -1;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (best_hp > (int) acc[k]) {
+                best_hp = (int) acc[k];
+                m = k;
+            }
+        }
+        mvx <<= 1;
+        mvy <<= 1;
+        if (m != -1) {
+            mvx += xh[m];
+            mvy += yh[m];
+            if (tid < HP_SAD_SZ * HP_SAD_SZ) {
+                const int jj = tid / HP_SAD_SZ, ii = tid - jj * HP_SAD_SZ;
+                s_refblk[tid] = tmph[xh[m] + yh[m] * HP_STRIDE + 2 * ii + 2 * HP_STRIDE * jj];
+            }
+            has_hp = true;
+            best = (int) ((unsigned) best_hp * yarea / (unsigned) (HP_SAD_SZ * HP_SAD_SZ));
+        }
+    } else {
+        mvx <<= 1;
+        mvy <<= 1;
+    }
+    if (!has_hp && tid < HP_SAD_SZ * HP_SAD_SZ) {
+        const int jj = tid / HP_SAD_SZ, ii = tid - jj * HP_SAD_SZ;
+        s_refblk[tid] = A.ref.p[(ptrdiff_t) (cy + (mvy >> 1) + jj) * rs + cx + (mvx >> 1) + ii];
+    }
+    /* zero-MV reference block */
+    for (int idx = tid; idx < G.words * G.bh; idx += HME_THREADS) {
+        const int r = idx / G.words, wx = idx - r * G.words;
+        *reinterpret_cast<unsigned *>(s_ref0 + r * HME_SRC_STRIDE + 4 * wx) =
+            ld4u(A.ref.p + (ptrdiff_t) (G.by + r) * rs + G.bx + 4 * wx);
+    }
+    __syncthreads();
+
+    /* ---- block sums ---- */
+    unsigned sum[SUM_COUNT];
+#pragma unroll
+    for (int k = 0; k < SUM_COUNT; k++) {
+        sum[k] = 0;
+    }
+    const int sbw = G.bw / 2, sbh = G.bh / 2;
+    for (int k = tid; k < G.bw * G.bh; k += HME_THREADS) {
+        const int ly = k / G.bw, lx = k - ly * G.bw;
+        const uint8_t *sp = s_src + ly * HME_SRC_STRIDE + lx;
+        const uint8_t *rp = s_ref0 + ly * HME_SRC_STRIDE + lx;
+        const int pa = sp[0], pb = rp[0];
+        const int right = lx == G.bw - 1 ? pa : sp[1];
+        const int up = ly == 0 ? pa : sp[-HME_SRC_STRIDE];
+        sum[SUM_S] += (unsigned) pa;
+        sum[SUM_SS] += (unsigned) (pa * pa);
+        sum[SUM_SH] += (unsigned) iabs(pa - right);
+        sum[SUM_SV] += (unsigned) iabs(pa - up);
+        sum[SUM_RS] += (unsigned) pb;
+        sum[SUM_RSS] += (unsigned) (pb * pb);
+        if (lx < 2 * sbw && ly < 2 * sbh) { /* intra_metric on the four quadrants, hme.c:87-134 */
+            const int qxi = lx >= sbw, qyi = ly >= sbh;
+            const int qi = lx - qxi * sbw, qj = ly - qyi * sbh;
+            const int la = qi == 0 ? pa : sp[-1], lb = qi == 0 ? pb : rp[-1];
+            const int ua = qj == 0 ? pa : sp[-HME_SRC_STRIDE], ub = qj == 0 ? pb : rp[-HME_SRC_STRIDE];
+            unsigned good = (unsigned) (iabs(pa - la) + iabs(pa - ua) + iabs(pb - lb) + iabs(pb - ub));
+            unsigned evil = 0;
+            const int dif = iabs(pa - pb);
+            if (dif == 0) {
+                good += 192;
+            } else if (dif == 1) {
+                good += 128;
+            } else if (dif == 2) {
+                good += 96;
+            } else {
+                evil = (unsigned) dif;
+            }
+            const int q = qxi | (qyi << 1);
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                sum[SUM_GOOD0 + t] += q == t ? good : 0u;
+                sum[SUM_EVIL0 + t] += q == t ? evil : 0u;
+            }
+        }
+    }
+    { /* chroma variance inputs, c_maxvar hme.c:270-300 */
+        const int cbx = i * (A.blk_w >> A.hs), cby = j * (A.blk_h >> A.vs);
+        const int cbw = G.bw >> A.hs, cbh = G.bh >> A.vs;
+        for (int k = tid; k < cbw * cbh; k += HME_THREADS) {
+            const int ly = k / cbw, lx = k - ly * cbw;
+            unsigned p;
+            p = A.srcU.p[(ptrdiff_t) (cby + ly) * A.srcU.stride + cbx + lx];
+            sum[SUM_CSU] += p;
+            sum[SUM_CSSU] += p * p;
+            p = A.srcV.p[(ptrdiff_t) (cby + ly) * A.srcV.stride + cbx + lx];
+            sum[SUM_CSV] += p;
+            sum[SUM_CSSV] += p * p;
+            p = A.refU.p[(ptrdiff_t) (cby + ly) * A.refU.stride + cbx + lx];
+            sum[SUM_CRU] += p;
+            sum[SUM_CRSU] += p * p;
+            p = A.refV.p[(ptrdiff_t) (cby + ly) * A.refV.stride + cbx + lx];
+            sum[SUM_CRV] += p;
+            sum[SUM_CRSV] += p * p;
+        }
+    }
+    if (tid < HP_SAD_SZ * HP_SAD_SZ) { /* block_texture on the two 14x14 patches, hme.c:179-209 */
+        const int jj = tid / HP_SAD_SZ, ii = tid - jj * HP_SAD_SZ;
+        const uint8_t *sp = A.src.p + (ptrdiff_t) (cy + jj) * ss + cx + ii;
+        int px = sp[0];
+        int right = ii == HP_SAD_SZ - 1 ? px : sp[1];
+        int up = jj == 0 ? px : sp[-ss];
+        sum[SUM_PSH] = (unsigned) iabs(px - right);
+        sum[SUM_PSV] = (unsigned) iabs(px - up);
+        sum[SUM_PAV] = (unsigned) px;
+        sum[SUM_PAVS] = (unsigned) (px * px);
+        px = s_refblk[tid];
+        right = ii == HP_SAD_SZ - 1 ? px : s_refblk[tid + 1];
+        up = jj == 0 ? px : s_refblk[tid - HP_SAD_SZ];
+        sum[SUM_QSH] = (unsigned) iabs(px - right);
+        sum[SUM_QSV] = (unsigned) iabs(px - up);
+        sum[SUM_QAV] = (unsigned) px;
+        sum[SUM_QAVS] = (unsigned) (px * px);
+    }
+    block_reduce_n<SUM_COUNT>(sum, scratch);
+
+    /* ---- block_intra_test (hme.c:141-177): any sample the reduced-range intra path cannot represent ---- */
+    const int ravg = (int) sum[SUM_RS] / (G.bw * G.bh);
+    if (tid == 0) {
+        s_flag = 0;
+    }
+    __syncthreads();
+    {
+        int bad = 0;
+        for (int k = tid; k < G.bw * G.bh; k += HME_THREADS) {
+            const int ly = k / G.bw, lx = k - ly * G.bw;
+            const int p = s_src[ly * HME_SRC_STRIDE + lx];
+            const int d = clamp_u8((ravg + clamp_u8((p - ravg) + 128)) - 128);
+            bad |= d != p;
+        }
+        if (bad) {
+            s_flag = 1;
+        }
+    }
+    __syncthreads();
+
+    if (tid == 0) {
+        const unsigned area = yarea;
+        const unsigned luma_tex = ((sum[SUM_SH] + sum[SUM_SV]) / 2u) / area;
+        const unsigned luma_var = sum[SUM_SS] - (sum[SUM_S] * sum[SUM_S]) / area;
+        const int lo_tex = luma_tex <= 2, lo_var = luma_var < yareasq;
+        const unsigned pn = HP_SAD_SZ * HP_SAD_SZ;
+        const int src_tex = (int) (((sum[SUM_PSH] + sum[SUM_PSV]) / 2u) / pn);
+        const int src_avg = (int) (sum[SUM_PAV] / pn);
+        const int src_var = (int) (sum[SUM_PAVS] - (sum[SUM_PAV] * sum[SUM_PAV]) / pn);
+        const int ref_tex = (int) (((sum[SUM_QSH] + sum[SUM_QSV]) / 2u) / pn);
+        const int ref_avg = (int) (sum[SUM_QAV] / pn);
+        const int ref_var = (int) (sum[SUM_QAVS] - (sum[SUM_QAV] * sum[SUM_QAV]) / pn);
+        const unsigned ubest = (unsigned) best;
+        bool intra = false;
+        if (src_tex < 2 && (sum[SUM_RSS] - (sum[SUM_RS] * sum[SUM_RS]) / area) > luma_var * 2u) {
+            intra = true;
+        } else if (ref_var > src_var * 2) {
+            intra = true;
+        } else if (src_tex == 0 && ref_tex != 0) {
+            intra = true;
+        } else if (iabs(src_avg - ref_avg) > 8) {
+            intra = true;
+        } else if (luma_tex <= 10 && ubest > yareasq / 16u) {
+            intra = true;
+        } else {
+            const unsigned carea = (unsigned) ((G.bw >> A.hs) * (G.bh >> A.vs));
+            if (carea) {
+                const unsigned vsu = sum[SUM_CSSU] - (sum[SUM_CSU] * sum[SUM_CSU]) / carea;
+                const unsigned vsv = sum[SUM_CSSV] - (sum[SUM_CSV] * sum[SUM_CSV]) / carea;
+                const unsigned vru = sum[SUM_CRSU] - (sum[SUM_CRU] * sum[SUM_CRU]) / carea;
+                const unsigned vrv = sum[SUM_CRSV] - (sum[SUM_CRV] * sum[SUM_CRV]) / carea;
+                const unsigned cvarS = vsu > vsv ? vsu : vsv, cvarR = vru > vrv ? vru : vrv;
+                intra = cvarR > 4u * cvarS;
+            }
+        }
+        int mode = 0, submask = 0;
+        if (intra && !s_flag) {
+            submask = 15;
+            if (src_tex > 1) {
+                const unsigned wgt = (unsigned) ((sbw + sbh) >> 1);
+                for (int q = 0; q < 4; q++) {
+                    if (sum[SUM_GOOD0 + q] >= wgt * sum[SUM_EVIL0 + q]) {
+                        submask &= ~(1 << q);
+                    }
+                }
+            }
+            if (submask) {
+                mode = 1;
+                atomicAdd(A.nintra, 1);
+            }
+        }
+        store_mv(out, mvx, mvy, mode, submask, lo_var, lo_tex);
+        A.aux[i + j * A.nbh] = make_int2((int) luma_tex, src_var);
+    }
+}
+
+/* high_detail from the already-final left / top / top-left neighbours (hme.c:607-648) */
+__global__ void __launch_bounds__(128) hme_neigh_kernel(DevMV *mv, const int2 *aux, int nbh, int nbv)
+{
+    const int b = (int) (blockIdx.x * blockDim.x + threadIdx.x);
+    if (b >= nbh * nbv) {
+        return;
+    }
+    const int i = b % nbh, j = b / nbh;
+    unsigned thresh_tex = 1;
+    int thresh_var = HP_SAD_SZ * HP_SAD_SZ;
+    auto detailed = [&](int x, int y) {
+        const DevMV m = mv[y * nbh + x];
+        return m.mode == 0 && !m.lo_tex && !m.lo_var;
+    };
+    if (i > 0 && detailed(i - 1, j)) {
+        thresh_var *= HP_SAD_SZ;
+        thresh_tex++;
+    }
+    if (j > 0 && detailed(i, j - 1)) {
+        thresh_var *= HP_SAD_SZ;
+        thresh_tex++;
+    }
+    if (i > 0 && j > 0 && detailed(i - 1, j - 1)) {
+        thresh_var *= HP_SAD_SZ / 4;
+        thresh_tex++;
+    }
+    const int2 a = aux[b];
+    mv[b].high_detail = (uint8_t) ((unsigned) a.x > thresh_tex && a.y > thresh_var);
+}
+
+static HmePlane mk_plane(const DevFrame &f, int c)
+{
+    HmePlane p;
+    p.p = f.p[c];
+    p.stride = f.stride[c];
+    p.w = f.w[c];
+    p.h = f.h[c];
+    return p;
+}
+
+void hme_launch(const MotionGeom &g, const DevFrame *src, const DevFrame *ref, DevMV *const *mvf, int2 *aux,
+                int *d_nintra, cudaStream_t st)
+{
+    CUDA_CHECK(cudaMemsetAsync(d_nintra, 0, sizeof(int), st));
+    for (int level = g.levels; level >= 0; level--) {
+        HmeArgs A;
+        memset(&A, 0, sizeof(A));
+        A.src = mk_plane(src[level], 0);
+        A.ref = mk_plane(ref[level], 0);
+        A.parent = level < g.levels ? mvf[level + 1] : nullptr;
+        A.out = mvf[level];
+        A.aux = aux;
+        A.nintra = d_nintra;
+        A.level = level;
+        A.blk_w = g.blk_w;
+        A.blk_h = g.blk_h;
+        A.nbh = g.nbh;
+        A.nbv = g.nbv;
+        A.hs = g.hs;
+        A.vs = g.vs;
+        if (level > 0) {
+            const int step = 1 << level;
+            DSV_LAUNCH(hme_level_kernel, dim3(ceil_div(g.nbh, step), ceil_div(g.nbv, step)), dim3(HME_THREADS), 0, st, A);
+        } else {
+            A.srcU = mk_plane(src[0], 1);
+            A.srcV = mk_plane(src[0], 2);
+            A.refU = mk_plane(ref[0], 1);
+            A.refV = mk_plane(ref[0], 2);
+            DSV_LAUNCH(hme_l0_kernel, dim3(g.nbh, g.nbv), dim3(HME_THREADS), 0, st, A);
+        }
+        KERNEL_CHECK();
+    }
+    DSV_LAUNCH(hme_neigh_kernel, dim3(ceil_div(g.nbh * g.nbv, 128)), dim3(128), 0, st, mvf[0], aux, g.nbh, g.nbv);
+    KERNEL_CHECK();
+}
+
+} // namespace dsv
