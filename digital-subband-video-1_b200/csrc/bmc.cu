@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(BMC_THREADS) bmc_kernel(BmcArgs a)
         }
         const unsigned tot = block_sum_u32(acc, scratch);
         if (tid == 0) {
-            s_avg[q] = (sbw * sbh) ? (int) (tot / (unsigned) (sbw * sbh)) : 0;
+            s_avg[q] = (sbw > 0 && sbh > 0) ? (int) (tot / (unsigned) (sbw * sbh)) : 0;
         }
     }
     __syncthreads();

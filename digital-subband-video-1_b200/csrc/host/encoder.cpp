@@ -165,6 +165,7 @@ static void enc_ctx_destroy(EncCtx *c)
     for (int l = 0; l <= DSV_MAX_PYRAMID_LEVELS; l++) {
         cudaFree(c->d_mvf[l]);
     }
+    cudaFree(c->d_aux);
     cudaFree(c->d_pkt);
     cudaFree(c->d_misc);
     cudaFreeHost(c->h_in);
@@ -220,7 +221,9 @@ static EncCtx *enc_ctx_create(DSV_ENCODER *enc)
         }
         for (int l = 0; l <= enc->pyramid_levels; l++) {
             CUDA_CHECK(cudaMalloc(&c->d_mvf[l], sizeof(DevMV) * (size_t) g.nblk));
+            CUDA_CHECK(cudaMemset(c->d_mvf[l], 0, sizeof(DevMV) * (size_t) g.nblk));
         }
+        CUDA_CHECK(cudaMalloc(&c->d_aux, sizeof(int2) * (size_t) g.nblk));
     }
     return c;
 }
@@ -614,7 +617,7 @@ extern "C" int dsv_enc(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_BUF *bufs)
                 src[l + 1] = c->pyr[cur][l];
                 ref[l + 1] = c->pyr[prev][l];
             }
-            hme_launch(mg, src, ref, c->d_mvf, d_nintra, st);
+            hme_launch(mg, src, ref, c->d_mvf, c->d_aux, d_nintra, st);
             CUDA_CHECK(cudaMemcpyAsync(c->h_mv, c->d_mvf[0], sizeof(DevMV) * (size_t) g.nblk, cudaMemcpyDeviceToHost, st));
             need_sync = 1;
         }
@@ -650,7 +653,7 @@ extern "C" int dsv_enc(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_BUF *bufs)
         CUDA_CHECK(cudaMemcpyAsync(c->xf.alloc, c->pad[cur].alloc, c->xf.bytes, cudaMemcpyDeviceToDevice, st));
         if (has_ref) {
             MotionGeom mg = {g.w, g.h, g.hs, g.vs, g.blk_w, g.blk_h, g.nbh, g.nbv, enc->pyramid_levels};
-            bmc_launch(mg, c->d_mvf[0], c->recon[prev], c->pred, c->xf, 1, st);
+            bmc_launch(mg, c->d_mvf[0], c->recon[prev], &c->pred, c->xf, 1, st);
         }
     }
 

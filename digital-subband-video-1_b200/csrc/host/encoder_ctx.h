@@ -51,6 +51,7 @@ struct EncCtx {
     int cur = 0;
     DevFrame xf, pred, pad[2], recon[2], pyr[2][5];
     DevMV *d_mvf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int2 *d_aux = nullptr;
     uint8_t *d_pkt = nullptr;
     uint8_t *d_misc = nullptr;
     size_t pkt_cap = 0;

@@ -195,3 +195,144 @@ extern "C" int dsvk_decode_plane(const uint8_t *in, int plen, int cw, int ch, in
     hzdec_free(&bufs);
     return 0;
 }
+
+/* ---- motion: pyramid, HME, BMC ------------------------------------------------------------------ */
+#include "frame.cuh"
+#include "motion.cuh"
+
+namespace {
+
+/* packed planar YUV (host) -> bordered device frame, borders replicated (dsv_frame_copy + extend) */
+void upload_frame(DevFrame *f, const uint8_t *yuv, int w, int h, int subsamp)
+{
+    devframe_alloc(f, w, h, subsamp);
+    const uint8_t *s = yuv;
+    for (int c = 0; c < 3; c++) {
+        CUDA_CHECK(cudaMemcpy2D(f->p[c], f->stride[c], s, f->w[c], f->w[c], f->h[c], cudaMemcpyHostToDevice));
+        s += (size_t) f->w[c] * f->h[c];
+    }
+    frame_extend_launch(*f, 3, 0);
+}
+
+void download_frame(const DevFrame &f, uint8_t *yuv)
+{
+    uint8_t *o = yuv;
+    for (int c = 0; c < 3; c++) {
+        CUDA_CHECK(cudaMemcpy2D(o, f.w[c], f.p[c], f.stride[c], f.w[c], f.h[c], cudaMemcpyDeviceToHost));
+        o += (size_t) f.w[c] * f.h[c];
+    }
+}
+
+MotionGeom motion_geom(int w, int h, int subsamp, int blk_w, int blk_h, int levels)
+{
+    MotionGeom g;
+    g.w = w;
+    g.h = h;
+    g.hs = (subsamp >> 2) & 3;
+    g.vs = subsamp & 3;
+    g.blk_w = blk_w;
+    g.blk_h = blk_h;
+    g.nbh = ceil_div(w, blk_w);
+    g.nbv = ceil_div(h, blk_h);
+    g.levels = levels;
+    return g;
+}
+
+} // namespace
+
+extern "C" int dsvk_pyramid(const uint8_t *yuv, int w, int h, int subsamp, int levels, uint8_t *out, int *out_w, int *out_h)
+{
+    if (levels < 1 || levels > 5) {
+        return -1;
+    }
+    DevFrame f[6];
+    upload_frame(&f[0], yuv, w, h, subsamp);
+    for (int l = 0; l < levels; l++) {
+        devframe_alloc(&f[l + 1], ceil_shift(w, l + 1), ceil_shift(h, l + 1), subsamp);
+        frame_down2_luma_launch(f[l], f[l + 1], 0);
+    }
+    CUDA_CHECK(cudaDeviceSynchronize());
+    for (int l = 1; l <= levels; l++) {
+        CUDA_CHECK(cudaMemcpy2D(out, f[l].w[0], f[l].p[0], f[l].stride[0], f[l].w[0], f[l].h[0], cudaMemcpyDeviceToHost));
+        out += (size_t) f[l].w[0] * f[l].h[0];
+        out_w[l - 1] = f[l].w[0];
+        out_h[l - 1] = f[l].h[0];
+    }
+    for (int l = 0; l <= levels; l++) {
+        devframe_free(&f[l]);
+    }
+    return 0;
+}
+
+extern "C" int dsvk_hme(const uint8_t *src_yuv, const uint8_t *ref_yuv, int w, int h, int subsamp, int blk_w, int blk_h,
+                        int levels, void *mv_out)
+{
+    if (levels < 0 || levels > 5) {
+        return -1;
+    }
+    const MotionGeom g = motion_geom(w, h, subsamp, blk_w, blk_h, levels);
+    const int nblk = g.nbh * g.nbv;
+    DevFrame sf[6], rf[6];
+    upload_frame(&sf[0], src_yuv, w, h, subsamp);
+    upload_frame(&rf[0], ref_yuv, w, h, subsamp);
+    for (int l = 0; l < levels; l++) {
+        devframe_alloc(&sf[l + 1], ceil_shift(w, l + 1), ceil_shift(h, l + 1), subsamp);
+        devframe_alloc(&rf[l + 1], ceil_shift(w, l + 1), ceil_shift(h, l + 1), subsamp);
+        frame_down2_luma_launch(sf[l], sf[l + 1], 0);
+        frame_down2_luma_launch(rf[l], rf[l + 1], 0);
+    }
+    DevMV *mvf[6];
+    for (int l = 0; l <= levels; l++) {
+        CUDA_CHECK(cudaMalloc(&mvf[l], sizeof(DevMV) * (size_t) nblk));
+        CUDA_CHECK(cudaMemset(mvf[l], 0, sizeof(DevMV) * (size_t) nblk));
+    }
+    DevBuf aux(sizeof(int2) * (size_t) nblk), cnt(sizeof(int));
+    hme_launch(g, sf, rf, mvf, aux.as<int2>(), cnt.as<int>(), 0);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    int nintra = 0;
+    CUDA_CHECK(cudaMemcpy(&nintra, cnt.p, sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(mv_out, mvf[0], sizeof(DevMV) * (size_t) nblk, cudaMemcpyDeviceToHost));
+    for (int l = 0; l <= levels; l++) {
+        cudaFree(mvf[l]);
+        devframe_free(&sf[l]);
+        devframe_free(&rf[l]);
+    }
+    return nintra * 100 / nblk;
+}
+
+extern "C" int dsvk_sub_pred(const void *mvs, int w, int h, int subsamp, int blk_w, int blk_h, const uint8_t *inp_yuv,
+                             const uint8_t *ref_yuv, uint8_t *pred_out, uint8_t *resid_out)
+{
+    const MotionGeom g = motion_geom(w, h, subsamp, blk_w, blk_h, 0);
+    DevFrame inp, ref, pred;
+    upload_frame(&inp, inp_yuv, w, h, subsamp);
+    upload_frame(&ref, ref_yuv, w, h, subsamp);
+    devframe_alloc(&pred, w, h, subsamp);
+    DevBuf mv(sizeof(DevMV) * (size_t) g.nbh * g.nbv);
+    CUDA_CHECK(cudaMemcpy(mv.p, mvs, sizeof(DevMV) * (size_t) g.nbh * g.nbv, cudaMemcpyHostToDevice));
+    bmc_launch(g, mv.as<DevMV>(), ref, &pred, inp, 1, 0);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    download_frame(pred, pred_out);
+    download_frame(inp, resid_out);
+    devframe_free(&inp);
+    devframe_free(&ref);
+    devframe_free(&pred);
+    return 0;
+}
+
+extern "C" int dsvk_add_pred(const void *mvs, int w, int h, int subsamp, int blk_w, int blk_h, const uint8_t *resid_yuv,
+                             const uint8_t *ref_yuv, uint8_t *out_yuv)
+{
+    const MotionGeom g = motion_geom(w, h, subsamp, blk_w, blk_h, 0);
+    DevFrame io, ref;
+    upload_frame(&io, resid_yuv, w, h, subsamp);
+    upload_frame(&ref, ref_yuv, w, h, subsamp);
+    DevBuf mv(sizeof(DevMV) * (size_t) g.nbh * g.nbv);
+    CUDA_CHECK(cudaMemcpy(mv.p, mvs, sizeof(DevMV) * (size_t) g.nbh * g.nbv, cudaMemcpyHostToDevice));
+    bmc_launch(g, mv.as<DevMV>(), ref, nullptr, io, 2, 0);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    download_frame(io, out_yuv);
+    devframe_free(&io);
+    devframe_free(&ref);
+    return 0;
+}

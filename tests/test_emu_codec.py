@@ -1,0 +1,58 @@
+"""Kernel-logic check in the GPU-less container: the SAME .cu / host sources compiled for the test-only CPU
+emulator (tests/emu) drive a tiny sequence through dsv_enc / dsv_dec and the motion entry points, vs the
+unmodified reference.  Small sizes only (one OS thread per CUDA thread); the parity tests proper are -m gpu."""
+import subprocess
+
+import numpy as np
+import pytest
+
+import dsvlibs as L
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run(["make", "-s", "-C", L.PKG, "emu"], check=True, stdout=subprocess.DEVNULL)
+    return L.emu()
+
+
+def test_codec_tiny(emu, ref):
+    w, h, fmt, n = 96, 80, "420", 3
+    yuv = L.synth_sequence(w, h, fmt, n, 2, 0)
+    cfg = L.make_cfg(w, h, fmt, gop=12)
+    sa, pa, _ = ref.encode_sequence(cfg, yuv, n)
+    sb, pb, _ = emu.encode_sequence(cfg, yuv, n)
+    assert pa == pb and sa == sb
+    na, da, _, _ = ref.decode_stream(sa, w, h, L.SUBSAMP[fmt], n)
+    nb, db, _, _ = emu.decode_stream(sa, w, h, L.SUBSAMP[fmt], n)
+    assert na == nb == n and np.array_equal(da, db)
+
+
+def test_motion_tiny(emu, ref):
+    w, h, fmt = 112, 96, "444"
+    sub = L.SUBSAMP[fmt]
+    fr = L.synth_sequence(w, h, fmt, 1, 4, 0, start=3)
+    fs = L.synth_sequence(w, h, fmt, 1, 4, 0, start=4)
+    pr, mr = ref.hme(fs, fr, w, h, sub, 3)
+    pe, me = emu.hme(fs, fr, w, h, sub, 3)
+    assert pr == pe and all(np.array_equal(mr[k], me[k]) for k in mr.dtype.names)
+    rng = np.random.default_rng(0)
+    mv = mr.copy()
+    mv["x"] = rng.integers(-110, 111, size=mv.shape).astype(np.int16)
+    mv["y"] = rng.integers(-110, 111, size=mv.shape).astype(np.int16)
+    mv["mode"] = (rng.random(mv.shape) < 0.3).astype(np.uint8)
+    mv["submask"] = np.where(mv["mode"] == 1, rng.integers(1, 16, size=mv.shape), 0).astype(np.uint8)
+    pa, ra = ref.sub_pred(mv, w, h, sub, fs, fr)
+    pb, rb = emu.sub_pred(mv, w, h, sub, fs, fr)
+    assert np.array_equal(pa, pb) and np.array_equal(ra, rb)
+    assert np.array_equal(ref.add_pred(mv, w, h, sub, ra, fr), emu.add_pred(mv, w, h, sub, ra, fr))
+
+
+def test_hzcc_decode_small(emu, port):
+    rng = np.random.default_rng(1)
+    for cw, ch in [(16, 16), (136, 68)]:
+        for isP in (0, 1):
+            stable = rng.integers(0, 4, size=20, dtype=np.uint8)
+            co = (rng.laplace(0, 400, size=(ch, cw)) * (rng.random((ch, cw)) < 0.2)).astype(np.int32)
+            s, _ = port.encode_plane(co, 313, isP, 1, stable, 5, 4)
+            assert np.array_equal(port.decode_plane(s, cw, ch, 313, isP, 1, stable, 5, 4),
+                                  emu.decode_plane(s, cw, ch, 313, isP, 1, stable, 5, 4))

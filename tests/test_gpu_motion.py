@@ -1,0 +1,82 @@
+"""CUDA pyramid / hierarchical motion estimation / block motion compensation (frame_ops.cu, hme.cu, bmc.cu)
+through the kernel-level C ABI vs the unmodified reference (dsv_hme, dsv_sub_pred, dsv_add_pred): every
+DSV_MV byte, every predicted / residual / reconstructed sample."""
+import math
+
+import numpy as np
+import pytest
+
+import dsvlibs as L
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # w, h, fmt, seed, cut, frame pairs (ref, src)
+    (352, 288, "420", 1, 150, [(0, 1), (10, 11), (149, 150), (150, 151), (200, 201)]),
+    (176, 144, "444", 4, 14, [(2, 3), (13, 14)]),
+    (176, 144, "422", 5, 0, [(0, 1)]),
+    (176, 144, "411", 6, 0, [(7, 8)]),
+    (428, 240, "420", 7, 0, [(3, 4)]),
+    (854, 480, "420", 8, 0, [(1, 2)]),
+    (1920, 1080, "420", 2, 0, [(3, 4), (0, 1)]),
+    (1280, 720, "420", 12, 0, [(5, 6)]),
+]
+
+
+def pyr_levels(w, h):
+    """dsv_encoder.c:602-613"""
+    bw, bh, nbh, nbv = L.block_dims(w, h)
+    lv = int(math.ceil(math.log2(min(w, h))))
+    while (1 << lv) > max(nbh, nbv):
+        lv -= 1
+    return min(max(lv, 3), 5)
+
+
+def mv_equal(a, b):
+    return [k for k in a.dtype.names if not np.array_equal(a[k], b[k])]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%dx%d_%s" % (c[0], c[1], c[2]))
+def test_hme_and_bmc(gpu, ref, case):
+    w, h, fmt, seed, cut, pairs = case
+    sub = L.SUBSAMP[fmt]
+    lv = pyr_levels(w, h)
+    rng = np.random.default_rng(w + h)
+    for a, b in pairs:
+        fr = L.synth_sequence(w, h, fmt, 1, seed, cut, start=a)
+        fs = L.synth_sequence(w, h, fmt, 1, seed, cut, start=b)
+        for la, lb in zip(ref.pyramid(fs, w, h, sub, lv), gpu.pyramid(fs, w, h, sub, lv)):
+            assert np.array_equal(la, lb)
+        pr, mr = ref.hme(fs, fr, w, h, sub, lv)
+        pg, mg = gpu.hme(fs, fr, w, h, sub, lv)
+        assert mv_equal(mr, mg) == []
+        assert pr == pg
+        # BMC with the estimated field, then with exaggerated vectors and forced intra / partial masks.
+        # |mv| <= 110 half-pels keeps every filter tap inside the reference's own allocation: beyond that the
+        # reference reads heap bytes outside its frame, which nothing can reproduce.
+        for trial in range(3):
+            mv = mr.copy()
+            if trial >= 1:
+                mv["x"] = rng.integers(-110, 111, size=mv.shape).astype(np.int16)
+                mv["y"] = rng.integers(-110, 111, size=mv.shape).astype(np.int16)
+                mv["mode"] = (rng.random(mv.shape) < 0.3).astype(np.uint8)
+                mv["submask"] = np.where(mv["mode"] == 1, rng.integers(1, 16, size=mv.shape), 0).astype(np.uint8)
+            pred_r, res_r = ref.sub_pred(mv, w, h, sub, fs, fr)
+            pred_g, res_g = gpu.sub_pred(mv, w, h, sub, fs, fr)
+            assert np.array_equal(pred_r, pred_g)
+            assert np.array_equal(res_r, res_g)
+            assert np.array_equal(ref.add_pred(mv, w, h, sub, res_r, fr), gpu.add_pred(mv, w, h, sub, res_r, fr))
+
+
+def test_uhd444_hme(gpu, ref):
+    w, h, fmt = 3840, 2160, "444"
+    sub = L.SUBSAMP[fmt]
+    fr = L.synth_sequence(w, h, fmt, 1, 3, 0, start=1)
+    fs = L.synth_sequence(w, h, fmt, 1, 3, 0, start=2)
+    lv = pyr_levels(w, h)
+    pr, mr = ref.hme(fs, fr, w, h, sub, lv)
+    pg, mg = gpu.hme(fs, fr, w, h, sub, lv)
+    assert mv_equal(mr, mg) == [] and pr == pg
+    pred_r, res_r = ref.sub_pred(mr, w, h, sub, fs, fr)
+    pred_g, res_g = gpu.sub_pred(mr, w, h, sub, fs, fr)
+    assert np.array_equal(pred_r, pred_g) and np.array_equal(res_r, res_g)
