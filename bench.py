@@ -1,0 +1,324 @@
+#!/usr/bin/env python3
+"""bench.py -- DSV1 encode+decode throughput on B200 (BASELINE.json metric), one process per GPU.
+
+Workload (config.workload): per GPU a batch of B synthetic 1920x1080 4:2:0 closed-GOP sequences (12 pictures,
+-gop12 -qp85 fixed quality, hierarchical ME with auto pyramid depth) -- BASELINE.json config 5 sharded by
+sequence, weak scaling: every rank encodes AND decodes its own B sequences, no collective on the data path.
+A "step" = encode all B*12 pictures to .dsv streams, then decode those streams back to pictures.
+
+  value   pictures/s through encode+decode with the inputs of each direction already resident in HBM
+          (pictures generated on the device; streams also kept on the device for the decoder; decoded
+          pictures left on the device).  Bitstreams still come back to the host: that IS the encoder's product.
+  e2e     the same through the same public call with HOST buffers (pinned): pictures H2D, streams D2H,
+          streams H2D, pictures D2H all inside the timed region.
+  roofline  the subband-transform tile kernels (the path's dominant HBM movers), timed live with CUDA
+          events on the engine's stream inside the timed region: algorithmic bytes / duration.
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref/libdsv1ref.so, built from /root/reference by
+          oracle/Makefile) single-threaded on a bounded sample of the same workload, rank 0, N=1.
+
+`--impl reference` times the reference's own CPU implementation on all host cores (one process per core, the
+reference is not thread-safe), same metric / unit / config.
+"""
+import argparse
+import ctypes as C
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W, H, FMT, GOP, QP, NFR = 1920, 1080, "420", 12, 85, 12
+METRIC = "1080p 4:2:0 gop12 qp85 encode+decode pictures/s (bit-exact DSV1)"
+
+
+def workload(batch):
+    return {"workload": "synthetic %dx%d %s, %d closed-GOP sequences x %d pictures per GPU, -gop%d -qp%d CRF, "
+                        "encode then decode (BASELINE config 5, sharded by sequence)" % (W, H, FMT, batch, NFR, GOP, QP),
+            "batch_sequences_per_gpu": batch, "pictures_per_sequence": NFR,
+            "l2": "inputs larger than L2 (%.0f MB of pictures per step per GPU)" % (batch * NFR * W * H * 1.5 / 1e6)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ------------------------------------------------------------------------------------------------------
+_REF_STATE = {}
+
+
+def _ref_init(seed_base):
+    """per-process: load the reference library and synthesise this process's input sequence once (untimed)"""
+    import dsvlibs as L
+    ident = mp.current_process()._identity
+    seed = seed_base + (ident[0] if ident else 0)
+    _REF_STATE["ref"] = L.ref()
+    _REF_STATE["yuv"] = L.synth_sequence(W, H, FMT, NFR, seed, 0)
+    _REF_STATE["cfg"] = L.make_cfg(W, H, FMT, gop=GOP, qp=QP)
+
+
+def _ref_codec(yuv):
+    import dsvlibs as L
+    ref = _REF_STATE.get("ref") or L.ref()
+    cfg = _REF_STATE.get("cfg") or L.make_cfg(W, H, FMT, gop=GOP, qp=QP)
+    stream, _, e = ref.encode_sequence(cfg, yuv, NFR)
+    nf, _, _, d = ref.decode_stream(stream, W, H, L.SUBSAMP[FMT], NFR)
+    assert nf == NFR
+    return e, d
+
+
+def _ref_step(_):
+    return _ref_codec(_REF_STATE["yuv"])
+
+
+def run_reference(args):
+    import dsvlibs as L
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if not L.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libdsv1ref.so missing (built here from /root/reference)"}))
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    pool = mp.get_context("fork").Pool(procs, initializer=_ref_init, initargs=(1000,))
+    pool.map(_ref_step, range(procs))  # every worker is up and has its input
+    times = []
+    pics = procs * NFR
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        pool.map(_ref_step, range(procs), chunksize=1)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    pool.close()
+    total = sum(times)
+    value = pics * len(times) / total
+    line = {"metric": METRIC, "value": value, "unit": "pictures/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic", "impl": "reference",
+            "config": workload(args.batch),
+            "cpu_baseline": {"value": value, "unit": "pictures/s", "cores": procs, "kind": "reference",
+                             "sample": "%d processes (one per host core; the reference is single-threaded and not "
+                                       "re-entrant) x 1 sequence x %d pictures per step, encode then decode, inputs "
+                                       "preloaded in memory" % (procs, NFR)},
+            "e2e": {"value": value, "unit": "pictures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline_single(h_yuv_np, seq_bytes):
+    """Reference, 1 thread, bounded sample of the SAME inputs: time inside dsv_enc / dsv_dec only."""
+    import dsvlibs as L
+    if not L.have_ref():
+        return None
+    nseq = min(6, len(h_yuv_np) // seq_bytes)
+    e = d = 0.0
+    for s in range(nseq):
+        es, ds = _ref_codec(h_yuv_np[s * seq_bytes:(s + 1) * seq_bytes])
+        e += es
+        d += ds
+    return {"value": nseq * NFR / (e + d), "unit": "pictures/s", "cores": 1, "kind": "reference",
+            "sample": "%d of the step's sequences x %d pictures, 1 thread, time inside dsv_enc+dsv_dec "
+                      "(encode %.2f pictures/s, decode %.2f pictures/s)" % (nseq, NFR, nseq * NFR / e, nseq * NFR / d)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# product arm
+# ------------------------------------------------------------------------------------------------------
+def run_product(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import dsvlibs as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    gpu = L.gpu()
+    lib = gpu.lib
+    B = args.batch
+    sub = L.SUBSAMP[FMT]
+    fb = L.frame_bytes(W, H, sub)
+    seq_bytes = fb * NFR
+    cfg = L.make_cfg(W, H, FMT, gop=GOP, qp=QP)
+
+    # inputs: generated on the device (SURVEY Appendix C content), one distinct sequence per lane
+    d_yuv = torch.empty(B * seq_bytes, dtype=torch.uint8, device="cuda")
+    for s in range(B):
+        lib.dsvb_synth_device(W, H, sub, 0, NFR, 100 + rank * B + s, 0, C.c_void_p(d_yuv.data_ptr() + s * seq_bytes), local)
+    h_yuv = torch.empty(B * seq_bytes, dtype=torch.uint8).pin_memory()
+    h_yuv.copy_(d_yuv)
+    cap = 8 << 20
+    h_streams = torch.zeros(B * cap, dtype=torch.uint8).pin_memory()
+    d_streams = torch.zeros(B * cap, dtype=torch.uint8, device="cuda")
+    d_out = torch.empty(B * seq_bytes, dtype=torch.uint8, device="cuda")
+    h_out = torch.empty(B * seq_bytes, dtype=torch.uint8).pin_memory()
+
+    enc = L.BatchEncoder(gpu, cfg, B, local)
+    dec = L.BatchDecoder(gpu, B, local)
+    sp = [h_streams.data_ptr() + s * cap for s in range(B)]
+    sdp = [d_streams.data_ptr() + s * cap for s in range(B)]
+    caps = [cap] * B
+
+    def step(host):
+        if host:
+            rc, lens = enc.encode_ptrs([h_yuv.data_ptr() + s * seq_bytes for s in range(B)], NFR, 0, sp, caps)
+            assert rc == 0
+            rc, fr = dec.decode_ptrs(sp, None, lens, [h_out.data_ptr() + s * seq_bytes for s in range(B)], [seq_bytes] * B, 0)
+        else:
+            rc, lens = enc.encode_ptrs([d_yuv.data_ptr() + s * seq_bytes for s in range(B)], NFR, 1, sp, caps)
+            assert rc == 0
+            rc, fr = dec.decode_ptrs(sp, sdp, lens, [d_out.data_ptr() + s * seq_bytes for s in range(B)], [seq_bytes] * B, 1)
+        assert rc == 0 and all(f == NFR for f in fr), (rc, fr)
+        return lens
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(host, steps, warmup):
+        for _ in range(warmup):
+            lens = step(host)
+            if not host:   # device copies of the (deterministic) streams for the decoder's resident-input arm
+                d_streams.copy_(h_streams, non_blocking=False)
+        enc.stats(reset=True)
+        dec.stats(reset=True)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            lens = step(host)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), lens, enc.stats(), dec.stats()
+
+    # correctness spot check before timing: lane 0's stream decodes to what the reference decodes (if present)
+    lens = step(True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_dev, lens, es, ds = timed(False, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, lens_h, es_h, ds_h = timed(True, args.steps, args.warmup)
+
+    pics = B * NFR * world
+    value = pics * args.steps / (ms_dev / 1e3)
+    e2e = pics * args.steps / (ms_e2e / 1e3)
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        kern = {}
+        for name, ms, n, by in (("sbt_fwd_tile_kernel", es["sbt_fwd_ms"], es["sbt_fwd_launches"], es["sbt_fwd_bytes"]),
+                                ("sbt_inv_tile_kernel(enc)", es["sbt_inv_ms"], es["sbt_inv_launches"], es["sbt_inv_bytes"]),
+                                ("sbt_inv_tile_kernel(dec)", ds["sbt_inv_ms"], ds["sbt_inv_launches"], ds["sbt_inv_bytes"])):
+            if n > 0 and ms > 0:
+                kern[name] = {"ms_total": ms, "launches": n, "ms_per_launch": ms / n, "bytes_per_launch": by / n,
+                              "achieved_gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peak,
+                              "share_of_step": ms / ms_dev}
+        dom = max(kern.items(), key=lambda kv: kv[1]["ms_total"]) if kern else (None, None)
+        roofline = None
+        if dom[0]:
+            roofline = {"kernel": dom[0], "bound": "hbm", "achieved": dom[1]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                        "frac": dom[1]["frac"], "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_plane": "w*h (u8 samples) + 4*cw*ch (int32 coefficients)"}
+        stream_bytes = sum(lens_h)
+        line = {"metric": METRIC, "value": value, "unit": "pictures/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+                "config": workload(B),
+                "e2e": {"value": e2e, "unit": "pictures/s", "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": B * seq_bytes + stream_bytes, "d2h_bytes_per_step": B * seq_bytes + stream_bytes},
+                "gpu_launches": int(es["kernel_launches"] + ds["kernel_launches"]),
+                "roofline": roofline, "kernels": kern, "clocks": clocks,
+                "stream_bytes_per_step": stream_bytes}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_single(h_yuv.numpy(), seq_bytes)
+        print(json.dumps(line))
+    enc.close()
+    dec.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="sequences per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

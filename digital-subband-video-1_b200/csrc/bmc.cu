@@ -3,7 +3,7 @@
  * reconstruction (decoder).  Replaces compensate / hpelL / hpel / avgval / cpyzero / subf / addf /
  * dsv_sub_pred / dsv_add_pred / dsv_frame_add (bmc.c:29-346).
  *
- *   bmc_kernel        one CTA per motion block and plane (grid = nbh x nbv x 3 x lanes).  Inter blocks:
+ *   bmc_kernel        one CTA per motion block and plane (grid = nbh x nbv x 3 planes x lanes; one BmcArgs per lane).  Inter blocks:
  *                     luma 4-tap (-1,9,9,-1) half-pel filter, the HV phase through an int16
  *                     H-filtered strip staged in shared memory (bmc.c:124-174); chroma bilinear
  *                     (bmc.c:58-110).  Intra blocks / quadrants: integer mean of the co-located
@@ -11,7 +11,7 @@
  *                     The prediction never makes a round trip through HBM on the decoder side
  *                     (mode 2: io = clamp(pred + io - 128)); the encoder keeps it (mode 1) because the
  *                     closed-loop reconstruction adds it back after the inverse transform.
- *   frame_add_kernel  dst = clamp(dst + src - 128), 16 bytes per thread.
+ *                     The closed-loop add-back itself is recon_kernel in frame_ops.cu.
  *
  * Reads outside the picture go through the 64-sample replicated border exactly like the reference
  * (position clamp bmc.c:221-249); filter taps that step one sample past the border see the same
@@ -23,18 +23,6 @@ namespace dsv {
 
 #define BMC_THREADS 256
 
-struct BmcPlane {
-    const uint8_t *ref;
-    uint8_t *pred; /* may be null (decoder) */
-    uint8_t *io;
-    int rstride, pstride, iostride;
-    int w, h;
-};
-struct BmcArgs {
-    BmcPlane pl[3];
-    const DevMV *mv;
-    int blk_w, blk_h, nbh, nbv, hs, vs, mode;
-};
 
 DSV_D int hpf4(int a, int b, int c, int d) { return 9 * (b + c) - (a + d); }
 
@@ -54,12 +42,13 @@ DSV_D unsigned block_sum_u32(unsigned v, unsigned *scratch /* >= 33 */)
     return t;
 }
 
-__global__ void __launch_bounds__(BMC_THREADS) bmc_kernel(BmcArgs a)
+__global__ void __launch_bounds__(BMC_THREADS) bmc_kernel(const BmcArgs *args)
 {
+    const BmcArgs &a = args[blockIdx.z / 3];
     __shared__ int16_t hbuf[(DSV_BORDER + 3) * DSV_BORDER]; /* (bh + 3) x bw, bmc.c:127 */
     __shared__ unsigned scratch[40];
     __shared__ int s_avg[4];
-    const int c = blockIdx.z;
+    const int c = blockIdx.z % 3;
     const BmcPlane P = a.pl[c];
     const int sh = c ? a.hs : 0, sv = c ? a.vs : 0;
     const int bw = a.blk_w >> sh, bh = a.blk_h >> sv;
@@ -73,6 +62,14 @@ __global__ void __launch_bounds__(BMC_THREADS) bmc_kernel(BmcArgs a)
     const DevMV mv = a.mv[j * a.nbh + i];
     const int tid = threadIdx.x;
     const int npx = cw * ch;
+    if (a.mode == 1 && x + cw == P.w) {
+        /* the forward transform of a plane with odd width reads one column past it (sbt.c:583-591); in the
+         * reference that column of the residual frame still holds the replicated INPUT border
+         * (dsv_encoder.c:657-659: xf = copy of the padded input, then only w x h is replaced) */
+        for (int k = tid; k < ch; k += BMC_THREADS) {
+            P.out[(size_t) (y + k) * P.ostride + P.w] = P.in[(size_t) (y + k) * P.istride + P.w];
+        }
+    }
 
     if (mv.mode == 0) { /* DSV_MODE_INTER, bmc.c:240-254 */
         const int dx = mv.x >> sh, dy = mv.y >> sv;
@@ -114,12 +111,11 @@ __global__ void __launch_bounds__(BMC_THREADS) bmc_kernel(BmcArgs a)
                     v = (p[0] + p[1] + p[rs] + p[rs + 1] + 2) >> 2;
                 }
             }
-            const size_t o = (size_t) (y + ly) * P.iostride + x + lx;
             if (P.pred) {
                 P.pred[(size_t) (y + ly) * P.pstride + x + lx] = (uint8_t) v;
             }
-            const int cur = P.io[o];
-            P.io[o] = a.mode == 1 ? clamp_u8(cur - v + 128) : clamp_u8(v + cur - 128);
+            const int cur = P.in[(size_t) (y + ly) * P.istride + x + lx];
+            P.out[(size_t) (y + ly) * P.ostride + x + lx] = a.mode == 1 ? clamp_u8(cur - v + 128) : clamp_u8(v + cur - 128);
         }
         return;
     }
@@ -155,95 +151,45 @@ __global__ void __launch_bounds__(BMC_THREADS) bmc_kernel(BmcArgs a)
             const int q = (lx >= sbw ? 1 : 0) | (ly >= sbh ? 2 : 0);
             v = (mv.submask & (1 << q)) ? s_avg[q] : r0[(ptrdiff_t) ly * P.rstride + lx];
         }
-        const size_t o = (size_t) (y + ly) * P.iostride + x + lx;
         if (P.pred) {
             P.pred[(size_t) (y + ly) * P.pstride + x + lx] = (uint8_t) v;
         }
-        const int cur = P.io[o];
-        P.io[o] = a.mode == 1 ? clamp_u8(cur - v + 128) : clamp_u8(v + cur - 128);
+        const int cur = P.in[(size_t) (y + ly) * P.istride + x + lx];
+        P.out[(size_t) (y + ly) * P.ostride + x + lx] = a.mode == 1 ? clamp_u8(cur - v + 128) : clamp_u8(v + cur - 128);
     }
 }
 
-void bmc_launch(const MotionGeom &g, const DevMV *mv, const DevFrame &ref, const DevFrame *pred, const DevFrame &io,
-                int mode, cudaStream_t st)
+void bmc_fill_args(BmcArgs *a, const MotionGeom &g, const DevMV *d_mv, const DevFrame &ref, const DevFrame *pred,
+                   const DevFrame &in, const DevFrame &out, int mode)
 {
-    BmcArgs a;
     for (int c = 0; c < 3; c++) {
-        a.pl[c].ref = ref.p[c];
-        a.pl[c].rstride = ref.stride[c];
-        a.pl[c].pred = pred ? pred->p[c] : nullptr;
-        a.pl[c].pstride = pred ? pred->stride[c] : 0;
-        a.pl[c].io = io.p[c];
-        a.pl[c].iostride = io.stride[c];
-        a.pl[c].w = io.w[c];
-        a.pl[c].h = io.h[c];
+        a->pl[c].ref = ref.p[c];
+        a->pl[c].rstride = ref.stride[c];
+        a->pl[c].pred = pred ? pred->p[c] : nullptr;
+        a->pl[c].pstride = pred ? pred->stride[c] : 0;
+        a->pl[c].in = in.p[c];
+        a->pl[c].istride = in.stride[c];
+        a->pl[c].out = out.p[c];
+        a->pl[c].ostride = out.stride[c];
+        a->pl[c].w = out.w[c];
+        a->pl[c].h = out.h[c];
     }
-    a.mv = mv;
-    a.blk_w = g.blk_w;
-    a.blk_h = g.blk_h;
-    a.nbh = g.nbh;
-    a.nbv = g.nbv;
-    a.hs = g.hs;
-    a.vs = g.vs;
-    a.mode = mode;
-    DSV_LAUNCH(bmc_kernel, dim3(g.nbh, g.nbv, 3), dim3(BMC_THREADS), 0, st, a);
-    KERNEL_CHECK();
+    a->mv = d_mv;
+    a->blk_w = g.blk_w;
+    a->blk_h = g.blk_h;
+    a->nbh = g.nbh;
+    a->nbv = g.nbv;
+    a->hs = g.hs;
+    a->vs = g.vs;
+    a->mode = mode;
 }
 
-struct AddArgs {
-    uint8_t *dst[3];
-    const uint8_t *src[3];
-    int dstride[3], sstride[3], w[3], h[3];
-};
-
-/* dst = clamp(dst + src - 128) (addf, bmc.c:29-41); rows start 16-byte aligned in DevFrame */
-__global__ void __launch_bounds__(256) frame_add_kernel(AddArgs a)
+void bmc_launch(const BmcArgs *d_args, int n, int nbh, int nbv, cudaStream_t st)
 {
-    const int c = blockIdx.z;
-    const int y = blockIdx.y;
-    const int x0 = (int) (blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    if (y >= a.h[c] || x0 >= a.w[c]) {
-        return;
+    if (n > 0) {
+        DSV_LAUNCH(bmc_kernel, dim3(nbh, nbv, 3 * n), dim3(BMC_THREADS), 0, st, d_args);
+        KERNEL_CHECK();
     }
-    uint8_t *d = a.dst[c] + (size_t) y * a.dstride[c] + x0;
-    const uint8_t *s = a.src[c] + (size_t) y * a.sstride[c] + x0;
-    if (x0 + 16 <= a.w[c] && ((reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(s)) & 15) == 0) {
-        uint4 dv = *reinterpret_cast<const uint4 *>(d), sv = *reinterpret_cast<const uint4 *>(s);
-        unsigned dw[4] = {dv.x, dv.y, dv.z, dv.w}, sw[4] = {sv.x, sv.y, sv.z, sv.w};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            unsigned r = 0;
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                int v = (int) ((dw[k] >> (8 * b)) & 0xff) + (int) ((sw[k] >> (8 * b)) & 0xff) - 128;
-                r |= (unsigned) clamp_u8(v) << (8 * b);
-            }
-            dw[k] = r;
-        }
-        *reinterpret_cast<uint4 *>(d) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
-    } else {
-        for (int e = 0; e < 16 && x0 + e < a.w[c]; e++) {
-            d[e] = clamp_u8((int) d[e] + (int) s[e] - 128);
-        }
-    }
-}
-
-void frame_add_launch(const DevFrame &dst, const DevFrame &src, cudaStream_t st)
-{
-    AddArgs a;
-    int maxw = 0, maxh = 0;
-    for (int c = 0; c < 3; c++) {
-        a.dst[c] = dst.p[c];
-        a.src[c] = src.p[c];
-        a.dstride[c] = dst.stride[c];
-        a.sstride[c] = src.stride[c];
-        a.w[c] = dst.w[c];
-        a.h[c] = dst.h[c];
-        maxw = imax(maxw, dst.w[c]);
-        maxh = imax(maxh, dst.h[c]);
-    }
-    DSV_LAUNCH(frame_add_kernel, dim3(ceil_div(ceil_div(maxw, 16), 256), maxh, 3), dim3(256), 0, st, a);
-    KERNEL_CHECK();
 }
 
 } // namespace dsv

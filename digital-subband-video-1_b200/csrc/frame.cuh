@@ -4,6 +4,11 @@
  * back.  Keeping the exact layout means in-bounds-but-past-border reads of the motion search / half-pel
  * filters see the same bytes as the reference; a zeroed guard band in front of
  * and behind the allocation makes the few reads that leave the reference's allocation well defined.
+ *
+ * All frame-level kernels are BATCHED: a launch takes a device array of small descriptors ("lists"), one
+ * entry per plane (or plane pair) of every frame in flight, so that the lanes of a lock-step batch
+ * (sequences x planes) share one grid.  Lists are assembled by the host in a StepArena and uploaded with a
+ * single copy per pipeline phase.
  */
 #pragma once
 #include "common.cuh"
@@ -23,13 +28,74 @@ struct DevFrame {
 void devframe_alloc(DevFrame *f, int width, int height, int subsamp);
 void devframe_free(DevFrame *f);
 
-/* replicate the border of planes [0, nplanes) (dsv_extend_frame / dsv_extend_frame_luma, frame.c:263-327) */
+/* one bordered plane */
+struct PlaneRef {
+    uint8_t *p;
+    int stride, w, h;
+};
+static inline PlaneRef plane_ref(const DevFrame &f, int c)
+{
+    PlaneRef r;
+    r.p = f.p[c];
+    r.stride = f.stride[c];
+    r.w = f.w[c];
+    r.h = f.h[c];
+    return r;
+}
+
+/* list entries */
+struct IngestItem { /* packed (dense, stride == w) plane -> bordered plane, border replicated */
+    const uint8_t *src;
+    PlaneRef dst;
+};
+struct PackItem { /* bordered plane -> packed plane */
+    PlaneRef src;
+    uint8_t *dst;
+};
+struct Down2Item { /* 2x2 rounded box filter of src -> dst, border replicated */
+    PlaneRef src, dst;
+};
+struct SumItem { /* sum of all samples -> *out (zeroed by the host side of the launch) */
+    PlaneRef src;
+    unsigned long long *out;
+};
+struct ReconItem { /* dst = clamp(a + b - 128) (b.p == null: dst = a), border of dst replicated */
+    PlaneRef a, b, dst;
+};
+
+/*
+ * Host-assembled, device-mirrored scratch for one pipeline phase: the host appends descriptor arrays into
+ * pinned memory, gets back the address the same bytes will have on the device, and uploads everything
+ * with one cudaMemcpyAsync before the launches that read it.
+ */
+struct StepArena {
+    uint8_t *h = nullptr, *d = nullptr;
+    size_t cap = 0, used = 0, uploaded = 0;
+    void create(size_t bytes);
+    void destroy();
+    void reset() { used = uploaded = 0; }
+    /* returns host pointer; *dev receives the device twin */
+    void *push(size_t bytes, void **dev);
+    template <typename T> T *push_n(size_t n, T **dev)
+    {
+        void *dv;
+        T *hp = reinterpret_cast<T *>(push(n * sizeof(T), &dv));
+        *dev = reinterpret_cast<T *>(dv);
+        return hp;
+    }
+    void upload(cudaStream_t st); /* everything appended since the last upload */
+};
+
+/* launches; every list pointer is a DEVICE pointer, max_* bound the grid */
+void ingest_launch(const IngestItem *d_items, int n, int max_w, int max_h, cudaStream_t st);
+void pack_launch(const PackItem *d_items, int n, int max_w, int max_h, cudaStream_t st);
+void extend_launch(const PlaneRef *d_items, int n, int max_w, int max_h, cudaStream_t st);
+void down2_launch(const Down2Item *d_items, int n, int max_w, int max_h, cudaStream_t st);
+void sum_launch(const SumItem *d_items, int n, int max_h, cudaStream_t st);
+void recon_launch(const ReconItem *d_items, int n, int max_w, int max_h, cudaStream_t st);
+
+/* single-frame conveniences used by the kernel-level API (kernel_api.cu) */
 void frame_extend_launch(const DevFrame &f, int nplanes, cudaStream_t st);
-/* 2x2 rounded box filter of the luma plane incl. its new border (dsv_ds2x_frame_luma + extend, frame.c:240-261) */
 void frame_down2_luma_launch(const DevFrame &src, const DevFrame &dst, cudaStream_t st);
-/* sum of the luma plane -> *d_sum (unsigned long long); caller divides (dsv_frame_avg_luma, frame.c:223-238) */
-void frame_sum_luma_launch(const DevFrame &f, unsigned long long *d_sum, cudaStream_t st);
-/* plane-wise copy w x h (dsv_frame_copy without the extension, frame.c:199-217) */
-void frame_copy_launch(const DevFrame &dst, const DevFrame &src, cudaStream_t st);
 
 } // namespace dsv

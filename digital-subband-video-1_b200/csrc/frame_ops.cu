@@ -1,4 +1,14 @@
-/* frame_ops.cu -- border extension, luma pyramid level, luma sum, plane copies (frame.c). */
+/*
+ * frame_ops.cu -- batched frame plumbing kernels: ingest (packed -> bordered + border), pack (bordered ->
+ * packed), border extension, luma pyramid level (2x2 box filter + border in one pass), luma sum, and the
+ * encoder's closed-loop reconstruction (residual + prediction -> new reference incl. border).
+ * Replaces dsv_frame_copy / dsv_clone_frame / dsv_extend_frame[_luma] / dsv_ds2x_frame_luma /
+ * dsv_frame_avg_luma / dsv_frame_add (frame.c:199-327, bmc.c:304-316).
+ *
+ * Every kernel takes a device array of items (one per plane of every frame in flight); threads own 16
+ * consecutive bytes of one bordered row: interior chunks move as one 16-byte load/store, border chunks
+ * replicate the nearest edge sample (out(x,y) = in(clamp x, clamp y)).
+ */
 #include "frame.cuh"
 
 namespace dsv {
@@ -32,26 +42,108 @@ void devframe_free(DevFrame *f)
     }
 }
 
-struct PlaneRef {
-    uint8_t *p;
-    int stride, w, h;
-};
-struct ExtendArgs {
-    PlaneRef pl[3];
-    int n;
-};
-
-/* out(x,y) = in(clamp(x,0,w-1), clamp(y,0,h-1)) for every border sample; 16 bytes per thread */
-__global__ void __launch_bounds__(256) frame_extend_kernel(ExtendArgs a)
+void StepArena::create(size_t bytes)
 {
-    const PlaneRef P = a.pl[blockIdx.z];
-    const int chunks = (P.w + 2 * DSV_BORDER + 15) >> 4;
-    const int ck = (int) (blockIdx.x * blockDim.x + threadIdx.x);
-    const int y = (int) blockIdx.y - DSV_BORDER;
-    if (ck >= chunks || y >= P.h + DSV_BORDER) {
+    cap = bytes;
+    CUDA_CHECK(cudaMallocHost(&h, bytes));
+    CUDA_CHECK(cudaMalloc(&d, bytes));
+    used = uploaded = 0;
+}
+void StepArena::destroy()
+{
+    if (h) {
+        cudaFreeHost(h);
+        cudaFree(d);
+        h = d = nullptr;
+    }
+}
+void *StepArena::push(size_t bytes, void **dev)
+{
+    const size_t at = (used + 15) & ~(size_t) 15;
+    if (at + bytes > cap) {
+        fprintf(stderr, "[dsv1_b200] step arena exhausted (%zu + %zu > %zu)\n", at, bytes, cap);
+        abort();
+    }
+    used = at + bytes;
+    *dev = d + at;
+    return h + at;
+}
+void StepArena::upload(cudaStream_t st)
+{
+    if (used > uploaded) {
+        const size_t from = uploaded & ~(size_t) 15;
+        CUDA_CHECK(cudaMemcpyAsync(d + from, h + from, used - from, cudaMemcpyHostToDevice, st));
+        uploaded = used;
+    }
+}
+
+#define FO_BX 64
+#define FO_BY 4
+static dim3 fo_grid(int max_w, int max_h, int n, bool bordered)
+{
+    const int cols = bordered ? max_w + 2 * DSV_BORDER : max_w, rows = bordered ? max_h + 2 * DSV_BORDER : max_h;
+    return dim3(ceil_div(ceil_div(cols, 16), FO_BX), ceil_div(rows, FO_BY), n);
+}
+#define FO_COORDS()                                                      \
+    const int ck = (int) (blockIdx.x * FO_BX + threadIdx.x);             \
+    const int row = (int) (blockIdx.y * FO_BY + threadIdx.y)
+
+DSV_D bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+__global__ void __launch_bounds__(FO_BX *FO_BY) ingest_kernel(const IngestItem *items)
+{
+    const IngestItem it = items[blockIdx.z];
+    const PlaneRef D = it.dst;
+    FO_COORDS();
+    const int x0 = ck * 16 - DSV_BORDER, y = row - DSV_BORDER;
+    if (x0 >= D.w + DSV_BORDER || y >= D.h + DSV_BORDER) {
         return;
     }
-    const int x0 = ck * 16 - DSV_BORDER;
+    const int sy = iclamp(y, 0, D.h - 1);
+    const uint8_t *src = it.src + (size_t) sy * D.w;
+    uint8_t *dst = D.p + (ptrdiff_t) y * D.stride + x0;
+    if (x0 >= 0 && x0 + 16 <= D.w && aligned16(src + x0)) {
+        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(src + x0);
+        return;
+    }
+    const int xend = D.w + DSV_BORDER;
+#pragma unroll 4
+    for (int e = 0; e < 16; e++) {
+        const int x = x0 + e;
+        if (x < xend) {
+            dst[e] = src[iclamp(x, 0, D.w - 1)];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FO_BX *FO_BY) pack_kernel(const PackItem *items)
+{
+    const PackItem it = items[blockIdx.z];
+    const PlaneRef S = it.src;
+    FO_COORDS();
+    const int x0 = ck * 16, y = row;
+    if (x0 >= S.w || y >= S.h) {
+        return;
+    }
+    const uint8_t *src = S.p + (size_t) y * S.stride + x0;
+    uint8_t *dst = it.dst + (size_t) y * S.w + x0;
+    if (x0 + 16 <= S.w && aligned16(dst)) {
+        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(src);
+        return;
+    }
+    for (int e = 0; e < 16 && x0 + e < S.w; e++) {
+        dst[e] = src[e];
+    }
+}
+
+__global__ void __launch_bounds__(FO_BX *FO_BY) extend_kernel(const PlaneRef *items)
+{
+    const PlaneRef P = items[blockIdx.z];
+    FO_COORDS();
+    const int x0 = ck * 16 - DSV_BORDER, y = row - DSV_BORDER;
+    if (x0 >= P.w + DSV_BORDER || y >= P.h + DSV_BORDER) {
+        return;
+    }
     const bool yin = y >= 0 && y < P.h;
     if (yin && x0 >= 0 && x0 + 16 <= P.w) {
         return; /* interior */
@@ -62,77 +154,199 @@ __global__ void __launch_bounds__(256) frame_extend_kernel(ExtendArgs a)
     const int xend = P.w + DSV_BORDER;
 #pragma unroll 4
     for (int e = 0; e < 16; e++) {
-        int x = x0 + e;
+        const int x = x0 + e;
         if (x < xend && !(yin && x >= 0 && x < P.w)) {
             dst[e] = src[iclamp(x, 0, P.w - 1)];
         }
     }
 }
 
-void frame_extend_launch(const DevFrame &f, int nplanes, cudaStream_t st)
+/* dst(i,j) = (s(2i,2j) + s(2i+1,2j) + s(2i,2j+1) + s(2i+1,2j+1) + 2) >> 2 (frame.c:240-261); may read one
+ * sample into the source border (odd source sizes), which is why the source must be extended first */
+__global__ void __launch_bounds__(FO_BX *FO_BY) down2_kernel(const Down2Item *items)
 {
-    ExtendArgs a;
-    int maxw = 0, maxh = 0;
-    a.n = nplanes;
-    for (int c = 0; c < 3; c++) {
-        a.pl[c].p = f.p[c]; a.pl[c].stride = f.stride[c]; a.pl[c].w = f.w[c]; a.pl[c].h = f.h[c];
-        if (c < nplanes) {
-            maxw = imax(maxw, f.w[c]);
-            maxh = imax(maxh, f.h[c]);
-        }
-    }
-    dim3 grid(ceil_div(ceil_div(maxw + 2 * DSV_BORDER, 16), 256), maxh + 2 * DSV_BORDER, nplanes);
-    DSV_LAUNCH(frame_extend_kernel, grid, dim3(256), 0, st, a);
-    KERNEL_CHECK();
-}
-
-/* dst(i,j) = (s(2i,2j) + s(2i+1,2j) + s(2i,2j+1) + s(2i+1,2j+1) + 2) >> 2; may read one sample into the
- * source border (odd source sizes), which is why the source must be extended first */
-__global__ void __launch_bounds__(256) frame_down2_kernel(PlaneRef s, PlaneRef d)
-{
-    const int x = (int) (blockIdx.x * blockDim.x + threadIdx.x), y = (int) blockIdx.y;
-    if (x >= d.w || y >= d.h) {
+    const Down2Item it = items[blockIdx.z];
+    const PlaneRef S = it.src, D = it.dst;
+    FO_COORDS();
+    const int x0 = ck * 16 - DSV_BORDER, y = row - DSV_BORDER;
+    if (x0 >= D.w + DSV_BORDER || y >= D.h + DSV_BORDER) {
         return;
     }
-    const uint8_t *sp = s.p + (size_t) (2 * y) * s.stride + 2 * x;
-    d.p[(size_t) y * d.stride + x] = (uint8_t) ((sp[0] + sp[1] + sp[s.stride] + sp[s.stride + 1] + 2) >> 2);
+    const int sy = iclamp(y, 0, D.h - 1);
+    const uint8_t *s0 = S.p + (size_t) (2 * sy) * S.stride, *s1 = s0 + S.stride;
+    uint8_t *dst = D.p + (ptrdiff_t) y * D.stride + x0;
+    if (x0 >= 0 && x0 + 16 <= D.w) {
+        const uint4 a0 = *reinterpret_cast<const uint4 *>(s0 + 2 * x0), a1 = *reinterpret_cast<const uint4 *>(s0 + 2 * x0 + 16);
+        const uint4 b0 = *reinterpret_cast<const uint4 *>(s1 + 2 * x0), b1 = *reinterpret_cast<const uint4 *>(s1 + 2 * x0 + 16);
+        const unsigned ra[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const unsigned rb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        unsigned o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            unsigned r = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++) { /* output sample 4k+e <- source samples 8k+2e, 8k+2e+1 */
+                const unsigned wa = ra[2 * k + (e >> 1)], wb = rb[2 * k + (e >> 1)];
+                const int sh = (e & 1) * 16;
+                const unsigned v = ((wa >> sh) & 0xff) + ((wa >> (sh + 8)) & 0xff) + ((wb >> sh) & 0xff) + ((wb >> (sh + 8)) & 0xff) + 2;
+                r |= (v >> 2) << (8 * e);
+            }
+            o[k] = r;
+        }
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+        return;
+    }
+    const int xend = D.w + DSV_BORDER;
+#pragma unroll 4
+    for (int e = 0; e < 16; e++) {
+        const int x = x0 + e;
+        if (x < xend) {
+            const int sx = 2 * iclamp(x, 0, D.w - 1);
+            dst[e] = (uint8_t) ((s0[sx] + s0[sx + 1] + s1[sx] + s1[sx + 1] + 2) >> 2);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) sum_kernel(const SumItem *items)
+{
+    const SumItem it = items[blockIdx.y];
+    const PlaneRef S = it.src;
+    const int y = (int) blockIdx.x;
+    if (y >= S.h) {
+        return;
+    }
+    unsigned acc = 0;
+    for (int x = threadIdx.x; x < S.w; x += 256) {
+        acc += S.p[(size_t) y * S.stride + x];
+    }
+    acc = __reduce_add_sync(0xffffffffu, acc);
+    if ((threadIdx.x & 31) == 0 && acc) {
+        atomicAdd(it.out, (unsigned long long) acc);
+    }
+}
+
+DSV_D unsigned add4_clamp(unsigned a, unsigned b)
+{
+    unsigned r = 0;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const int v = (int) ((a >> (8 * e)) & 0xff) + (int) ((b >> (8 * e)) & 0xff) - 128;
+        r |= (unsigned) clamp_u8(v) << (8 * e);
+    }
+    return r;
+}
+
+/* dst = clamp(a + b - 128) (dsv_frame_add, bmc.c:29-41,304-316) + copy into the new reference + its border
+ * (dsv_frame_copy + dsv_extend_frame, dsv_encoder.c:662-674) in one pass */
+__global__ void __launch_bounds__(FO_BX *FO_BY) recon_kernel(const ReconItem *items)
+{
+    const ReconItem it = items[blockIdx.z];
+    const PlaneRef A = it.a, B = it.b, D = it.dst;
+    FO_COORDS();
+    const int x0 = ck * 16 - DSV_BORDER, y = row - DSV_BORDER;
+    if (x0 >= D.w + DSV_BORDER || y >= D.h + DSV_BORDER) {
+        return;
+    }
+    const int sy = iclamp(y, 0, D.h - 1);
+    const uint8_t *a = A.p + (size_t) sy * A.stride;
+    const uint8_t *b = B.p ? B.p + (size_t) sy * B.stride : nullptr;
+    uint8_t *dst = D.p + (ptrdiff_t) y * D.stride + x0;
+    if (x0 >= 0 && x0 + 16 <= D.w) {
+        uint4 va = *reinterpret_cast<const uint4 *>(a + x0);
+        if (b) {
+            const uint4 vb = *reinterpret_cast<const uint4 *>(b + x0);
+            va = make_uint4(add4_clamp(va.x, vb.x), add4_clamp(va.y, vb.y), add4_clamp(va.z, vb.z), add4_clamp(va.w, vb.w));
+        }
+        *reinterpret_cast<uint4 *>(dst) = va;
+        return;
+    }
+    const int xend = D.w + DSV_BORDER;
+#pragma unroll 4
+    for (int e = 0; e < 16; e++) {
+        const int x = x0 + e;
+        if (x < xend) {
+            const int sx = iclamp(x, 0, D.w - 1);
+            dst[e] = b ? clamp_u8((int) a[sx] + (int) b[sx] - 128) : a[sx];
+        }
+    }
+}
+
+void ingest_launch(const IngestItem *d_items, int n, int max_w, int max_h, cudaStream_t st)
+{
+    if (n > 0) {
+        DSV_LAUNCH(ingest_kernel, fo_grid(max_w, max_h, n, true), dim3(FO_BX, FO_BY), 0, st, d_items);
+        KERNEL_CHECK();
+    }
+}
+void pack_launch(const PackItem *d_items, int n, int max_w, int max_h, cudaStream_t st)
+{
+    if (n > 0) {
+        DSV_LAUNCH(pack_kernel, fo_grid(max_w, max_h, n, false), dim3(FO_BX, FO_BY), 0, st, d_items);
+        KERNEL_CHECK();
+    }
+}
+void extend_launch(const PlaneRef *d_items, int n, int max_w, int max_h, cudaStream_t st)
+{
+    if (n > 0) {
+        DSV_LAUNCH(extend_kernel, fo_grid(max_w, max_h, n, true), dim3(FO_BX, FO_BY), 0, st, d_items);
+        KERNEL_CHECK();
+    }
+}
+void down2_launch(const Down2Item *d_items, int n, int max_w, int max_h, cudaStream_t st)
+{
+    if (n > 0) {
+        DSV_LAUNCH(down2_kernel, fo_grid(max_w, max_h, n, true), dim3(FO_BX, FO_BY), 0, st, d_items);
+        KERNEL_CHECK();
+    }
+}
+void sum_launch(const SumItem *d_items, int n, int max_h, cudaStream_t st)
+{
+    if (n > 0) {
+        DSV_LAUNCH(sum_kernel, dim3(max_h, n), dim3(256), 0, st, d_items);
+        KERNEL_CHECK();
+    }
+}
+void recon_launch(const ReconItem *d_items, int n, int max_w, int max_h, cudaStream_t st)
+{
+    if (n > 0) {
+        DSV_LAUNCH(recon_kernel, fo_grid(max_w, max_h, n, true), dim3(FO_BX, FO_BY), 0, st, d_items);
+        KERNEL_CHECK();
+    }
+}
+
+/* ---- single-frame conveniences (kernel-level API): build a one-off list in device memory ---- */
+template <typename T> static T *upload_items(const T *items, int n, cudaStream_t st)
+{
+    T *d;
+    CUDA_CHECK(cudaMalloc(&d, sizeof(T) * (size_t) n));
+    CUDA_CHECK(cudaMemcpyAsync(d, items, sizeof(T) * (size_t) n, cudaMemcpyHostToDevice, st));
+    return d;
+}
+
+void frame_extend_launch(const DevFrame &f, int nplanes, cudaStream_t st)
+{
+    PlaneRef it[3];
+    int mw = 0, mh = 0;
+    for (int c = 0; c < nplanes; c++) {
+        it[c] = plane_ref(f, c);
+        mw = imax(mw, f.w[c]);
+        mh = imax(mh, f.h[c]);
+    }
+    PlaneRef *d = upload_items(it, nplanes, st);
+    extend_launch(d, nplanes, mw, mh, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(d);
 }
 
 void frame_down2_luma_launch(const DevFrame &src, const DevFrame &dst, cudaStream_t st)
 {
-    PlaneRef s{src.p[0], src.stride[0], src.w[0], src.h[0]}, d{dst.p[0], dst.stride[0], dst.w[0], dst.h[0]};
-    DSV_LAUNCH(frame_down2_kernel, dim3(ceil_div(d.w, 256), d.h), dim3(256), 0, st, s, d);
-    KERNEL_CHECK();
-    frame_extend_launch(dst, 1, st);
-}
-
-__global__ void __launch_bounds__(256) frame_sum_kernel(PlaneRef s, unsigned long long *out)
-{
-    unsigned acc = 0;
-    const int y = (int) blockIdx.x;
-    for (int x = threadIdx.x; x < s.w; x += 256) {
-        acc += s.p[(size_t) y * s.stride + x];
-    }
-    acc = __reduce_add_sync(0xffffffffu, acc);
-    if ((threadIdx.x & 31) == 0 && acc) {
-        atomicAdd(out, (unsigned long long) acc);
-    }
-}
-
-void frame_sum_luma_launch(const DevFrame &f, unsigned long long *d_sum, cudaStream_t st)
-{
-    PlaneRef s{f.p[0], f.stride[0], f.w[0], f.h[0]};
-    CUDA_CHECK(cudaMemsetAsync(d_sum, 0, sizeof(unsigned long long), st));
-    DSV_LAUNCH(frame_sum_kernel, dim3(s.h), dim3(256), 0, st, s, d_sum);
-    KERNEL_CHECK();
-}
-
-void frame_copy_launch(const DevFrame &dst, const DevFrame &src, cudaStream_t st)
-{
-    for (int c = 0; c < 3; c++) {
-        CUDA_CHECK(cudaMemcpy2DAsync(dst.p[c], dst.stride[c], src.p[c], src.stride[c], src.w[c], src.h[c],
-                                     cudaMemcpyDeviceToDevice, st));
-    }
+    Down2Item it;
+    it.src = plane_ref(src, 0);
+    it.dst = plane_ref(dst, 0);
+    Down2Item *d = upload_items(&it, 1, st);
+    down2_launch(d, 1, dst.w[0], dst.h[0], st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(d);
 }
 
 } // namespace dsv

@@ -30,19 +30,6 @@ namespace dsv {
 #define HP_DIM 16
 #define HP_STRIDE 32
 
-struct HmePlane {
-    const uint8_t *p;
-    int stride, w, h;
-};
-struct HmeArgs {
-    HmePlane src, ref;       /* luma at this level */
-    HmePlane srcU, srcV, refU, refV; /* level 0 only */
-    const DevMV *parent;     /* level + 1 field or null */
-    DevMV *out;
-    int2 *aux;               /* level 0: (luma_tex, src_var) per block for the neighbour pass */
-    int *nintra;
-    int level, blk_w, blk_h, nbh, nbv, hs, vs;
-};
 
 /* 4 bytes at an arbitrary address: two aligned loads + funnel shift (generic address space) */
 DSV_D unsigned ld4u(const uint8_t *p)
@@ -235,8 +222,9 @@ DSV_D void store_mv(DevMV *dst, int x, int y, int mode, int submask, int lo_var,
     *dst = m;
 }
 
-__global__ void __launch_bounds__(HME_THREADS) hme_level_kernel(HmeArgs A)
+__global__ void __launch_bounds__(HME_THREADS) hme_level_kernel(const HmeArgs *args)
 {
+    const HmeArgs &A = args[blockIdx.z];
     __shared__ __align__(16) uint8_t s_src[64 * HME_SRC_STRIDE];
     __shared__ unsigned scratch[8 * 9];
     const int step = 1 << A.level;
@@ -266,8 +254,9 @@ enum {
     SUM_COUNT
 };
 
-__global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(HmeArgs A)
+__global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args)
 {
+    const HmeArgs &A = args[blockIdx.z];
     __shared__ __align__(16) uint8_t s_src[64 * HME_SRC_STRIDE];
     __shared__ __align__(16) uint8_t s_ref0[64 * HME_SRC_STRIDE];
     __shared__ unsigned scratch[8 * SUM_COUNT];
@@ -527,8 +516,12 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(HmeArgs A)
 }
 
 /* high_detail from the already-final left / top / top-left neighbours (hme.c:607-648) */
-__global__ void __launch_bounds__(128) hme_neigh_kernel(DevMV *mv, const int2 *aux, int nbh, int nbv)
+__global__ void __launch_bounds__(128) hme_neigh_kernel(const HmeArgs *args)
 {
+    const HmeArgs &A = args[blockIdx.z];
+    DevMV *mv = A.out;
+    const int2 *aux = A.aux;
+    const int nbh = A.nbh, nbv = A.nbv;
     const int b = (int) (blockIdx.x * blockDim.x + threadIdx.x);
     if (b >= nbh * nbv) {
         return;
@@ -566,39 +559,48 @@ static HmePlane mk_plane(const DevFrame &f, int c)
     return p;
 }
 
-void hme_launch(const MotionGeom &g, const DevFrame *src, const DevFrame *ref, DevMV *const *mvf, int2 *aux,
-                int *d_nintra, cudaStream_t st)
+void hme_fill_args(HmeArgs *A, const MotionGeom &g, int level, const DevFrame *src, const DevFrame *ref,
+                   DevMV *const *mvf, int2 *aux, int *d_nintra)
 {
-    CUDA_CHECK(cudaMemsetAsync(d_nintra, 0, sizeof(int), st));
+    memset(A, 0, sizeof(*A));
+    A->src = mk_plane(src[level], 0);
+    A->ref = mk_plane(ref[level], 0);
+    A->parent = level < g.levels ? mvf[level + 1] : nullptr;
+    A->out = mvf[level];
+    A->aux = aux;
+    A->nintra = d_nintra;
+    A->level = level;
+    A->blk_w = g.blk_w;
+    A->blk_h = g.blk_h;
+    A->nbh = g.nbh;
+    A->nbv = g.nbv;
+    A->hs = g.hs;
+    A->vs = g.vs;
+    if (level == 0) {
+        A->srcU = mk_plane(src[0], 1);
+        A->srcV = mk_plane(src[0], 2);
+        A->refU = mk_plane(ref[0], 1);
+        A->refV = mk_plane(ref[0], 2);
+    }
+}
+
+/* d_args[level * n + lane], levels g.levels .. 0; *nintra of every lane must be zero on entry */
+void hme_launch(const HmeArgs *d_args, int n, const MotionGeom &g, cudaStream_t st)
+{
+    if (n <= 0) {
+        return;
+    }
     for (int level = g.levels; level >= 0; level--) {
-        HmeArgs A;
-        memset(&A, 0, sizeof(A));
-        A.src = mk_plane(src[level], 0);
-        A.ref = mk_plane(ref[level], 0);
-        A.parent = level < g.levels ? mvf[level + 1] : nullptr;
-        A.out = mvf[level];
-        A.aux = aux;
-        A.nintra = d_nintra;
-        A.level = level;
-        A.blk_w = g.blk_w;
-        A.blk_h = g.blk_h;
-        A.nbh = g.nbh;
-        A.nbv = g.nbv;
-        A.hs = g.hs;
-        A.vs = g.vs;
+        const HmeArgs *a = d_args + (size_t) level * n;
         if (level > 0) {
             const int step = 1 << level;
-            DSV_LAUNCH(hme_level_kernel, dim3(ceil_div(g.nbh, step), ceil_div(g.nbv, step)), dim3(HME_THREADS), 0, st, A);
+            DSV_LAUNCH(hme_level_kernel, dim3(ceil_div(g.nbh, step), ceil_div(g.nbv, step), n), dim3(HME_THREADS), 0, st, a);
         } else {
-            A.srcU = mk_plane(src[0], 1);
-            A.srcV = mk_plane(src[0], 2);
-            A.refU = mk_plane(ref[0], 1);
-            A.refV = mk_plane(ref[0], 2);
-            DSV_LAUNCH(hme_l0_kernel, dim3(g.nbh, g.nbv), dim3(HME_THREADS), 0, st, A);
+            DSV_LAUNCH(hme_l0_kernel, dim3(g.nbh, g.nbv, n), dim3(HME_THREADS), 0, st, a);
         }
         KERNEL_CHECK();
     }
-    DSV_LAUNCH(hme_neigh_kernel, dim3(ceil_div(g.nbh * g.nbv, 128)), dim3(128), 0, st, mvf[0], aux, g.nbh, g.nbv);
+    DSV_LAUNCH(hme_neigh_kernel, dim3(ceil_div(g.nbh * g.nbv, 128), 1, n), dim3(128), 0, st, d_args);
     KERNEL_CHECK();
 }
 

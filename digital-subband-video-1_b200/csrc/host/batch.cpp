@@ -1,0 +1,385 @@
+/*
+ * batch.cpp -- dsvb_*: the additive throughput API (include/dsv1_b200_batch.h) on top of the lock-step
+ * engines.  Sequences are taken in waves of `lanes`; inside a wave picture t of every lane is one engine
+ * step.  Streams come out exactly as the per-picture API emits them (metadata at every GOP start, link
+ * fields, EOS), because every lane runs the same host-side state machine (a DSV_ENCODER per lane).
+ */
+#include "dsv1_b200_batch.h"
+
+#include "dsv1_b200.h"
+
+#include "bits.h"
+#include "engine.h"
+
+using namespace dsv;
+
+namespace dsv {
+void synth_launch(int w, int h, int hs, int vs, int start, int n, int seed, int cut, uint8_t *d_out, cudaStream_t st);
+}
+
+enum {
+    CFG_W, CFG_H, CFG_SUBSAMP, CFG_FPS_NUM, CFG_FPS_DEN, CFG_ASPECT_NUM, CFG_ASPECT_DEN,
+    CFG_GOP, CFG_QUALITY, CFG_RC_MODE, CFG_BITRATE, CFG_DO_SCD, CFG_SCD_DELTA, CFG_INTRA_PCT,
+    CFG_PYR_LEVELS, CFG_STABLE_REFRESH, CFG_MAX_Q_STEP, CFG_MIN_QUALITY, CFG_MAX_QUALITY,
+    CFG_MIN_I_QUALITY, CFG_HM_NUDGE, CFG_COUNT
+};
+
+struct DSVB_ENC {
+    int cfg[CFG_COUNT];
+    int lanes, device;
+    EncEngine *eng;
+    std::vector<DSV_ENCODER> state;
+};
+
+struct DSVB_DEC {
+    int lanes, device;
+    DecEngine *eng;
+    EngineStats carried; /* stats of engines replaced after a format change */
+};
+
+static void use_device(int device) { CUDA_CHECK(cudaSetDevice(device)); }
+
+static void apply_cfg(DSV_ENCODER *enc, const int *cfg)
+{
+    DSV_META md;
+    memset(&md, 0, sizeof(md));
+    md.width = cfg[CFG_W];
+    md.height = cfg[CFG_H];
+    md.subsamp = cfg[CFG_SUBSAMP];
+    md.fps_num = cfg[CFG_FPS_NUM];
+    md.fps_den = cfg[CFG_FPS_DEN];
+    md.aspect_num = cfg[CFG_ASPECT_NUM];
+    md.aspect_den = cfg[CFG_ASPECT_DEN];
+    dsv_enc_init(enc);
+    dsv_enc_set_metadata(enc, &md);
+    enc->gop = cfg[CFG_GOP];
+    enc->scene_change_delta = cfg[CFG_SCD_DELTA];
+    enc->do_scd = cfg[CFG_DO_SCD];
+    enc->intra_pct_thresh = cfg[CFG_INTRA_PCT];
+    enc->quality = cfg[CFG_QUALITY];
+    enc->rc_mode = cfg[CFG_RC_MODE];
+    enc->bitrate = (unsigned) cfg[CFG_BITRATE];
+    enc->max_q_step = cfg[CFG_MAX_Q_STEP];
+    enc->min_quality = cfg[CFG_MIN_QUALITY];
+    enc->max_quality = cfg[CFG_MAX_QUALITY];
+    enc->min_I_frame_quality = cfg[CFG_MIN_I_QUALITY];
+    enc->rc_high_motion_nudge = cfg[CFG_HM_NUDGE];
+    enc->pyramid_levels = cfg[CFG_PYR_LEVELS];
+    enc->stable_refresh = (unsigned) cfg[CFG_STABLE_REFRESH];
+    dsv_enc_start(enc);
+}
+
+static void release_state(DSV_ENCODER *enc)
+{
+    if (enc->stability) {
+        dsv_free(enc->stability);
+        enc->stability = NULL;
+    }
+    if (enc->stable_blocks) {
+        dsv_free(enc->stable_blocks);
+        enc->stable_blocks = NULL;
+    }
+}
+
+static void fill_stats(const EngineStats &s, int device, int lanes, double *out)
+{
+    out[0] = s.sbt_fwd_ms;
+    out[1] = (double) s.sbt_fwd_launches;
+    out[2] = (double) s.sbt_fwd_bytes;
+    out[3] = s.sbt_inv_ms;
+    out[4] = (double) s.sbt_inv_launches;
+    out[5] = (double) s.sbt_inv_bytes;
+    out[6] = (double) s.kernel_launches;
+    out[7] = (double) s.h2d_bytes;
+    out[8] = (double) s.d2h_bytes;
+    out[9] = (double) s.pictures;
+    out[10] = (double) device;
+    out[11] = (double) lanes;
+}
+
+extern "C" DSVB_ENC *dsvb_enc_create(const int *cfg, int lanes, int device)
+{
+    if (lanes < 1 || lanes > 1024) {
+        return nullptr;
+    }
+    use_device(device);
+    DSVB_ENC *e = new DSVB_ENC();
+    memcpy(e->cfg, cfg, sizeof(e->cfg));
+    e->lanes = lanes;
+    e->device = device;
+    e->state.resize((size_t) lanes);
+    /* one probe state fixes the block grid and the pyramid depth for the engine */
+    DSV_ENCODER probe;
+    apply_cfg(&probe, cfg);
+    enc_prepare_state(&probe);
+    e->eng = new EncEngine(probe.vidmeta, probe.gop, probe.pyramid_levels, lanes);
+    release_state(&probe);
+    return e;
+}
+
+extern "C" void dsvb_enc_destroy(DSVB_ENC *e)
+{
+    if (e) {
+        use_device(e->device);
+        delete e->eng;
+        delete e;
+    }
+}
+
+extern "C" void dsvb_enc_stats(DSVB_ENC *e, double *stats, int reset)
+{
+    fill_stats(e->eng->stats, e->device, e->lanes, stats);
+    if (reset) {
+        e->eng->stats = EngineStats();
+    }
+}
+
+extern "C" int dsvb_encode(DSVB_ENC *e, int nseq, int nframes, const uint8_t *const *yuv, int on_device,
+                           uint8_t *const *streams, const long *caps, long *lens)
+{
+    use_device(e->device);
+    const CodecGeom &g = e->eng->geom();
+    const int L = e->lanes;
+    int rc = 0;
+    std::vector<int> ids((size_t) L);
+    std::vector<PicRef> src((size_t) L);
+    std::vector<PktSink> sinks((size_t) L);
+    std::vector<int> nb((size_t) L);
+    std::vector<DSV_BUF> bufs((size_t) 2 * L);
+    for (int base = 0; base < nseq; base += L) {
+        const int n = nseq - base < L ? nseq - base : L;
+        for (int k = 0; k < n; k++) {
+            apply_cfg(&e->state[(size_t) k], e->cfg);
+            enc_prepare_state(&e->state[(size_t) k]);
+            e->eng->bind(k, &e->state[(size_t) k]);
+            ids[(size_t) k] = k;
+            sinks[(size_t) k].at = streams[base + k];
+            sinks[(size_t) k].room = (size_t) caps[base + k];
+            sinks[(size_t) k].overflow = 0;
+        }
+        for (int t = 0; t < nframes; t++) {
+            for (int k = 0; k < n; k++) {
+                const uint8_t *f = yuv[base + k] + (size_t) t * g.frame_bytes;
+                for (int p = 0; p < 3; p++) {
+                    src[(size_t) k].plane[p] = f + g.plane_off[p];
+                    src[(size_t) k].stride[p] = g.pw[p];
+                }
+                src[(size_t) k].on_device = on_device;
+            }
+            e->eng->step(n, ids.data(), src.data(), reinterpret_cast<DSV_BUF(*)[2]>(bufs.data()), nb.data(), sinks.data());
+        }
+        for (int k = 0; k < n; k++) {
+            PktSink &sk = sinks[(size_t) k];
+            DSV_BUF eos[1];
+            dsv_enc_end_of_stream(&e->state[(size_t) k], eos);
+            if (!sk.overflow && sk.room >= eos[0].len) {
+                memcpy(sk.at, eos[0].data, eos[0].len);
+                sk.at += eos[0].len;
+                sk.room -= eos[0].len;
+            } else {
+                sk.overflow = 1;
+            }
+            dsv_buf_free(&eos[0]);
+            lens[base + k] = sk.overflow ? -1 : (long) (sk.at - streams[base + k]);
+            if (sk.overflow) {
+                rc = -1;
+            }
+            release_state(&e->state[(size_t) k]);
+        }
+    }
+    return rc;
+}
+
+extern "C" DSVB_DEC *dsvb_dec_create(int lanes, int device)
+{
+    if (lanes < 1 || lanes > 1024) {
+        return nullptr;
+    }
+    DSVB_DEC *d = new DSVB_DEC();
+    d->lanes = lanes;
+    d->device = device;
+    d->eng = nullptr;
+    return d;
+}
+
+extern "C" void dsvb_dec_destroy(DSVB_DEC *d)
+{
+    if (d) {
+        use_device(d->device);
+        delete d->eng;
+        delete d;
+    }
+}
+
+static void add_stats(EngineStats &a, const EngineStats &b)
+{
+    a.sbt_fwd_ms += b.sbt_fwd_ms;
+    a.sbt_inv_ms += b.sbt_inv_ms;
+    a.sbt_fwd_launches += b.sbt_fwd_launches;
+    a.sbt_inv_launches += b.sbt_inv_launches;
+    a.sbt_fwd_bytes += b.sbt_fwd_bytes;
+    a.sbt_inv_bytes += b.sbt_inv_bytes;
+    a.kernel_launches += b.kernel_launches;
+    a.h2d_bytes += b.h2d_bytes;
+    a.d2h_bytes += b.d2h_bytes;
+    a.pictures += b.pictures;
+}
+
+extern "C" void dsvb_dec_stats(DSVB_DEC *d, double *stats, int reset)
+{
+    EngineStats s = d->carried;
+    if (d->eng) {
+        add_stats(s, d->eng->stats);
+    }
+    fill_stats(s, d->device, d->lanes, stats);
+    if (reset) {
+        d->carried = EngineStats();
+        if (d->eng) {
+            d->eng->stats = EngineStats();
+        }
+    }
+}
+
+static unsigned be32(const uint8_t *p) { return ((unsigned) p[0] << 24) | ((unsigned) p[1] << 16) | ((unsigned) p[2] << 8) | p[3]; }
+
+extern "C" int dsvb_decode(DSVB_DEC *d, int nseq, const uint8_t *const *streams, const uint8_t *const *streams_dev,
+                           const long *lens, uint8_t *const *out, const long *out_caps, int out_on_device, int *frames)
+{
+    use_device(d->device);
+    const int L = d->lanes;
+    int rc = 0;
+    std::vector<long> pos((size_t) L);
+    std::vector<int> done((size_t) L), got_meta((size_t) L);
+    std::vector<int> ids((size_t) L), seq_of((size_t) L), codes((size_t) L);
+    std::vector<PktRef> pk((size_t) L);
+    std::vector<OutRef> outs((size_t) L);
+    std::vector<DSV_FNUM> fn((size_t) L);
+    std::vector<uint8_t *> scratch_out; /* device scratch for pictures that do not fit the caller's buffer */
+    for (int base = 0; base < nseq; base += L) {
+        const int n = nseq - base < L ? nseq - base : L;
+        for (int k = 0; k < n; k++) {
+            pos[(size_t) k] = 0;
+            done[(size_t) k] = 0;
+            got_meta[(size_t) k] = 0;
+            frames[base + k] = 0;
+            if (d->eng) {
+                d->eng->reset_lane(k);
+            }
+        }
+        for (;;) {
+            /* advance every lane to its next picture packet (metadata / EOS are host-only) */
+            int m = 0;
+            for (int k = 0; k < n; k++) {
+                const int s = base + k;
+                while (!done[(size_t) k]) {
+                    const long at = pos[(size_t) k];
+                    if (at + DSV_PACKET_HDR_SIZE > lens[s]) {
+                        done[(size_t) k] = 1;
+                        break;
+                    }
+                    const uint8_t *hdr = streams[s] + at;
+                    if (hdr[0] != DSV_FOURCC_0 || hdr[1] != DSV_FOURCC_1 || hdr[2] != DSV_FOURCC_2 || hdr[3] != DSV_FOURCC_3) {
+                        done[(size_t) k] = 1;
+                        rc = -4;
+                        break;
+                    }
+                    long size = (long) be32(hdr + DSV_PACKET_NEXT_OFFSET);
+                    if (size == 0) {
+                        size = DSV_PACKET_HDR_SIZE;
+                    }
+                    if (size < DSV_PACKET_HDR_SIZE || at + size > lens[s]) {
+                        done[(size_t) k] = 1;
+                        rc = -3;
+                        break;
+                    }
+                    const int type = hdr[DSV_PACKET_TYPE_OFFSET];
+                    pos[(size_t) k] = at + size;
+                    if (type == DSV_PT_META) {
+                        DSV_META md;
+                        memset(&md, 0, sizeof(md));
+                        parse_metadata_packet(hdr, (unsigned) size, &md);
+                        if (!meta_supported(md)) {
+                            done[(size_t) k] = 1;
+                            rc = -5;
+                            break;
+                        }
+                        if (d->eng && !d->eng->matches(md)) {
+                            if (m > 0 || frames[s] > 0 || k > 0) {
+                                done[(size_t) k] = 1; /* one picture format per call */
+                                rc = -6;
+                                break;
+                            }
+                            add_stats(d->carried, d->eng->stats);
+                            delete d->eng;
+                            d->eng = nullptr;
+                        }
+                        if (!d->eng) {
+                            d->eng = new DecEngine(md, L);
+                        }
+                        got_meta[(size_t) k] = 1;
+                        continue;
+                    }
+                    if (type == DSV_PT_EOS) {
+                        done[(size_t) k] = 1;
+                        break;
+                    }
+                    if (!DSV_PT_IS_PIC(type) || !got_meta[(size_t) k]) {
+                        continue; /* pictures before metadata are skipped (dsv_decoder.c:327-331) */
+                    }
+                    ids[(size_t) m] = k;
+                    seq_of[(size_t) m] = s;
+                    pk[(size_t) m].data = hdr;
+                    pk[(size_t) m].dev_data = streams_dev ? streams_dev[s] + at : nullptr;
+                    pk[(size_t) m].len = (unsigned) size;
+                    /* frame number decides where the picture lands: peek it (fnum follows the header) */
+                    const CodecGeom &g = d->eng->geom();
+                    const DSV_FNUM fno = be32(hdr + DSV_PACKET_HDR_SIZE);
+                    const size_t off = (size_t) fno * g.frame_bytes;
+                    if (off + g.frame_bytes > (size_t) out_caps[s]) {
+                        /* no room: decode (references must stay in step) into the lane's own frame only */
+                        for (int p = 0; p < 3; p++) {
+                            outs[(size_t) m].plane[p] = nullptr;
+                        }
+                    } else {
+                        for (int p = 0; p < 3; p++) {
+                            outs[(size_t) m].plane[p] = out[s] + off + g.plane_off[p];
+                            outs[(size_t) m].stride[p] = g.pw[p];
+                        }
+                    }
+                    outs[(size_t) m].on_device = out_on_device;
+                    m++;
+                    break;
+                }
+            }
+            if (m == 0) {
+                break;
+            }
+            d->eng->step(m, ids.data(), pk.data(), outs.data(), codes.data(), fn.data());
+            for (int q = 0; q < m; q++) {
+                if (codes[(size_t) q] == DSV_DEC_OK && outs[(size_t) q].plane[0]) {
+                    frames[seq_of[(size_t) q]]++;
+                }
+            }
+        }
+    }
+    return rc;
+}
+
+extern "C" void *dsvb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void dsvb_host_free(void *p) { cudaFreeHost(p); }
+
+extern "C" int dsvb_synth_device(int w, int h, int subsamp, int start, int n, int seed, int cut, uint8_t *d_out, int device)
+{
+    use_device(device);
+    synth_launch(w, h, (subsamp >> 2) & 3, subsamp & 3, start, n, seed, cut, d_out, 0);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    return 0;
+}

@@ -1,104 +1,20 @@
 /*
- * decoder.cpp -- the dsv_decoder.h API (dsv_decoder.c:22-145,244-472) on top of the CUDA kernels.
+ * decoder.cpp -- the dsv_decoder.h API (dsv_decoder.c:22-145,244-472) and the lock-step decode engine.
  *
  * Host code parses only what is serial and tiny: packet header, metadata, the ZBRLE stability map and
  * the four motion sub-streams (<= 2040 blocks), plus SEG(DC) / nruns / first run of each plane head.
- * The packet is copied to the device once; coefficient parsing (parallel bit-FSM), dequantisation,
+ * Each lane's packet is copied to the device once; coefficient parsing (parallel bit-FSM), dequantisation,
  * the inverse subband transform, motion compensation + reconstruction and the border extension of the
- * new reference all run as kernels on the decoder's own stream:
- *   H2D packet -> hzcc parse x3 -> SBT inverse x3 -> BMC + add (P) -> extend (refs) -> D2H frame.
+ * new references run as kernels batched over all lanes, on the engine's stream:
+ *   H2D packets -> zero coefs -> hzcc parse -> SBT inverse -> BMC + add (P) -> extend (refs) -> D2H pictures.
  * There is no CPU implementation of those stages in this library.
  */
 #include "dsv1_b200.h"
 
-#include "../frame.cuh"
-#include "../hzcc.cuh"
-#include "../hzcc_dec.cuh"
-#include "../motion.cuh"
-#include "../sbt.cuh"
 #include "bits.h"
-#include "encoder_ctx.h"
+#include "engine.h"
 
 using namespace dsv;
-
-namespace dsv {
-
-/* device context behind DSV_DECODER.ref (the reference keeps its DSV_IMAGE there, dsv_decoder.h:26-36) */
-struct DecCtx {
-    CodecGeom g;
-    CoderBufs cb;
-    HzDecBufs hz;
-    cudaStream_t st = 0;
-    DevFrame out[2]; /* out[cur] is being decoded, out[cur ^ 1] is the reference picture */
-    int cur = 0;
-    int have_ref = 0;
-    uint8_t *d_pkt = nullptr, *h_pkt = nullptr;
-    size_t pkt_cap = 0;
-    DevMV *d_mv = nullptr, *h_mv = nullptr;
-    uint8_t *h_stab = nullptr;
-    uint8_t *h_out = nullptr;
-    int max_nblk = 0;
-};
-
-} // namespace dsv
-
-static DecCtx *dec_ctx(DSV_DECODER *d) { return reinterpret_cast<DecCtx *>(d->ref); }
-
-static void dec_ctx_destroy(DecCtx *c)
-{
-    if (!c) {
-        return;
-    }
-    cudaStreamSynchronize(c->st);
-    coder_free(&c->cb);
-    hzdec_free(&c->hz);
-    devframe_free(&c->out[0]);
-    devframe_free(&c->out[1]);
-    cudaFree(c->d_pkt);
-    cudaFree(c->d_mv);
-    cudaFreeHost(c->h_pkt);
-    cudaFreeHost(c->h_mv);
-    cudaFreeHost(c->h_stab);
-    cudaFreeHost(c->h_out);
-    cudaStreamDestroy(c->st);
-    delete c;
-}
-
-static DecCtx *dec_ctx_create(const DSV_META &md)
-{
-    DecCtx *c = new DecCtx();
-    plan_geometry(&c->g, md.width, md.height, md.subsamp);
-    plan_blocks(&c->g, DSV_MIN_BLOCK_SIZE, DSV_MIN_BLOCK_SIZE); /* worst case; the real size is per picture */
-    const CodecGeom &g = c->g;
-    c->max_nblk = g.nblk;
-    CUDA_CHECK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-    coder_alloc(&c->cb, g);
-    HzDecPlan pl[3];
-    for (int p = 0; p < 3; p++) {
-        hzdec_plan(&pl[p], g.cw[p], g.ch[p]);
-    }
-    hzdec_alloc(&c->hz, pl);
-    devframe_alloc(&c->out[0], g.w, g.h, g.subsamp);
-    devframe_alloc(&c->out[1], g.w, g.h, g.subsamp);
-    /* a picture packet holds three planes of at most 2 * 4 * cw * ch bytes each (dsv_decoder.c:397-401) */
-    c->pkt_cap = g.coef_total * 8 + 4096 + (size_t) g.nblk * 64;
-    CUDA_CHECK(cudaMalloc(&c->d_pkt, c->pkt_cap + 64));
-    CUDA_CHECK(cudaMallocHost(&c->h_pkt, c->pkt_cap + 64));
-    CUDA_CHECK(cudaMalloc(&c->d_mv, sizeof(DevMV) * (size_t) g.nblk));
-    CUDA_CHECK(cudaMallocHost(&c->h_mv, sizeof(DevMV) * (size_t) g.nblk));
-    CUDA_CHECK(cudaMallocHost(&c->h_stab, (size_t) g.nblk));
-    CUDA_CHECK(cudaMallocHost(&c->h_out, g.frame_bytes));
-    return c;
-}
-
-static bool meta_supported(const DSV_META &m)
-{
-    if (m.width < 16 || m.height < 16 || (m.width & 1) || (m.height & 1) || m.width > 16384 || m.height > 16384) {
-        return false;
-    }
-    return m.subsamp == DSV_SUBSAMP_444 || m.subsamp == DSV_SUBSAMP_422 || m.subsamp == DSV_SUBSAMP_420 ||
-           m.subsamp == DSV_SUBSAMP_411;
-}
 
 static int read_packet_hdr(BitReader &br) /* dsv_decoder.c:21-48 */
 {
@@ -160,6 +76,284 @@ static void read_motion(BitReader &br, const uint8_t *pkt, unsigned pkt_len, Dev
     }
 }
 
+namespace dsv {
+
+DecEngine::DecEngine(const DSV_META &md, int lanes)
+{
+    CUDA_CHECK(cudaGetDevice(&device));
+    plan_geometry(&g_, md.width, md.height, md.subsamp);
+    plan_blocks(&g_, DSV_MIN_BLOCK_SIZE, DSV_MIN_BLOCK_SIZE); /* worst case; the real size is per picture */
+    const CodecGeom &g = g_;
+    max_nblk_ = g.nblk;
+    L_ = lanes;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    for (auto &e : ev_) {
+        CUDA_CHECK(cudaEventCreate(&e));
+    }
+    /* a picture packet holds three planes of at most 2 * 4 * cw * ch bytes each (dsv_decoder.c:397-401) */
+    pkt_cap_ = g.coef_total * 8 + 4096 + (size_t) g.nblk * 64;
+    const size_t per_lane = 3 * (sizeof(SbtJob) + hzdec_job_size()) + sizeof(BmcArgs) + 8 * sizeof(PlaneRef) + 3 * sizeof(PackItem) + 1024;
+    arena_.create(per_lane * (size_t) L_ + 4096);
+    CUDA_CHECK(cudaMalloc(&d_mv_, sizeof(DevMV) * (size_t) max_nblk_ * L_));
+    CUDA_CHECK(cudaMallocHost(&h_mv_, sizeof(DevMV) * (size_t) max_nblk_ * L_));
+    CUDA_CHECK(cudaMalloc(&d_stab_, (size_t) max_nblk_ * L_));
+    CUDA_CHECK(cudaMallocHost(&h_stab_, (size_t) max_nblk_ * L_));
+    lanes_.resize((size_t) L_);
+    for (auto &l : lanes_) {
+        CUDA_CHECK(cudaMalloc(&l.coef, g.coef_total * sizeof(int32_t)));
+        for (int p = 0; p < 3; p++) {
+            CUDA_CHECK(cudaMalloc(&l.llx[p], sbt_llx_elems(g.cw[p], g.ch[p]) * sizeof(int32_t)));
+            HzDecPlan pl;
+            hzdec_plan(&pl, g.cw[p], g.ch[p]);
+            hzdec_plane_alloc(&l.hz[p], pl);
+        }
+        devframe_alloc(&l.out[0], g.w, g.h, g.subsamp);
+        devframe_alloc(&l.out[1], g.w, g.h, g.subsamp);
+        /* packets are staged lazily: most are far smaller than the format's upper bound */
+        l.d_pkt = nullptr;
+        l.h_pkt = nullptr;
+    }
+}
+
+DecEngine::~DecEngine()
+{
+    cudaStreamSynchronize(st_);
+    for (auto &l : lanes_) {
+        cudaFree(l.coef);
+        for (int p = 0; p < 3; p++) {
+            cudaFree(l.llx[p]);
+            hzdec_plane_free(&l.hz[p]);
+        }
+        devframe_free(&l.out[0]);
+        devframe_free(&l.out[1]);
+        cudaFree(l.d_pkt);
+        cudaFreeHost(l.h_pkt);
+    }
+    arena_.destroy();
+    cudaFree(d_mv_);
+    cudaFreeHost(h_mv_);
+    cudaFree(d_stab_);
+    cudaFreeHost(h_stab_);
+    for (auto &e : ev_) {
+        cudaEventDestroy(e);
+    }
+    cudaStreamDestroy(st_);
+}
+
+void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRef *out, int *codes, DSV_FNUM *fnums)
+{
+    cudaStream_t st = st_;
+    arena_.reset();
+    SbtJob *d_sj;
+    void *d_hzj;
+    BmcArgs *d_bmc;
+    PlaneRef *d_ext;
+    PackItem *d_pack;
+    SbtJob *sj = arena_.push_n<SbtJob>((size_t) 3 * n, &d_sj);
+    uint8_t *hzj = reinterpret_cast<uint8_t *>(arena_.push(hzdec_job_size() * (size_t) 3 * n, &d_hzj));
+    BmcArgs *ba = arena_.push_n<BmcArgs>((size_t) n, &d_bmc);
+    PlaneRef *ext = arena_.push_n<PlaneRef>((size_t) 3 * n, &d_ext);
+    PackItem *pack = arena_.push_n<PackItem>((size_t) 3 * n, &d_pack);
+    HzDecDims dims;
+    int n_sj = 0, n_p = 0, n_ext = 0, n_pack = 0, tile_base = 0;
+    bool any_intra = false;
+    int blk_w = 0, blk_h = 0, nbh = 0, nbv = 0;
+
+    for (int k = 0; k < n; k++) {
+        const int li = lane_ids[k];
+        DecLane &l = lanes_[(size_t) li];
+        const uint8_t *pkt = pkts[k].data;
+        const unsigned pkt_len = pkts[k].len;
+        codes[k] = DSV_DEC_ERROR;
+        fnums[k] = (DSV_FNUM) -1;
+        l.ok = 0;
+        BitReader br(pkt, pkt_len);
+        const int pkt_type = read_packet_hdr(br);
+        if (pkt_type == -1 || !DSV_PT_IS_PIC(pkt_type) || (size_t) pkt_len > pkt_cap_) {
+            continue;
+        }
+        l.has_ref = DSV_PT_HAS_REF(pkt_type);
+        l.is_ref = DSV_PT_IS_REF(pkt_type);
+        br.align();
+        l.fnum = br.get_bits(32);
+        br.align();
+        const int bw_ = (int) (br.get_ueg() << 2), bh_ = (int) (br.get_ueg() << 2);
+        if (bw_ < DSV_MIN_BLOCK_SIZE || bh_ < DSV_MIN_BLOCK_SIZE || bw_ > DSV_MAX_BLOCK_SIZE || bh_ > DSV_MAX_BLOCK_SIZE) {
+            continue;
+        }
+        CodecGeom g = g_;
+        plan_blocks(&g, bw_, bh_);
+        if (blk_w == 0) {
+            blk_w = bw_;
+            blk_h = bh_;
+            nbh = g.nbh;
+            nbv = g.nbv;
+        } else if (blk_w != bw_ || blk_h != bh_) {
+            /* lanes of one step share the block grid (same format => same encoder choice); a stream that
+             * deviates is decoded in a later step by its caller */
+            DSV_ERROR(("mixed block sizes inside one batch step"));
+            continue;
+        }
+        uint8_t *stab = h_stab_ + (size_t) li * max_nblk_;
+        DevMV *mvs = h_mv_ + (size_t) li * max_nblk_;
+        read_stability(br, pkt, pkt_len, stab, g.nblk);
+        if (l.has_ref) {
+            read_motion(br, pkt, pkt_len, mvs, stab, g.nbh, g.nbv);
+        }
+        br.align();
+        l.quant = (int) br.get_bits(DSV_MAX_QP_BITS);
+
+        /* packet bytes on the device */
+        const uint8_t *d_pkt;
+        if (pkts[k].dev_data) {
+            d_pkt = pkts[k].dev_data;
+        } else {
+            if (!l.d_pkt) {
+                CUDA_CHECK(cudaMalloc(&l.d_pkt, pkt_cap_ + 64));
+                CUDA_CHECK(cudaMallocHost(&l.h_pkt, pkt_cap_ + 64));
+            }
+            memcpy(l.h_pkt, pkt, pkt_len);
+            memset(l.h_pkt + pkt_len, 0, 64);
+            CUDA_CHECK(cudaMemcpyAsync(l.d_pkt, l.h_pkt, (size_t) pkt_len + 64, cudaMemcpyHostToDevice, st));
+            stats.h2d_bytes += pkt_len;
+            d_pkt = l.d_pkt;
+        }
+        /* plane directory (dsv_decoder.c:383-413) */
+        l.nplanes = 0;
+        for (int p = 0; p < 3; p++) {
+            br.align();
+            const int plen = (int) br.get_bits(32);
+            br.align();
+            const int framesz = g.cw[p] * g.ch[p] * (int) sizeof(int32_t);
+            if (plen <= 0 || plen > framesz * 2) {
+                DSV_ERROR(("plane length was strange: %d", plen));
+                break;
+            }
+            const unsigned at = br.byte_pos();
+            if (at >= pkt_len) {
+                DSV_ERROR(("plane starts past the end of the packet"));
+                break;
+            }
+            hzdec_parse_head(pkt + at, pkt_len - at, (unsigned) plen, &l.pd[p]);
+            l.pd[p].body = d_pkt + at;
+            br.skip_bytes((unsigned) plen);
+            l.nplanes++;
+        }
+        fnums[k] = l.fnum;
+        if (l.has_ref && !l.have_ref) {
+            DSV_WARNING(("reference frame not found"));
+            continue; /* DSV_DEC_ERROR (dsv_decoder.c:424-427) */
+        }
+        l.ok = 1;
+        codes[k] = DSV_DEC_OK;
+
+        const DevFrame &cur = l.out[l.cur];
+        const int isP = l.has_ref;
+        any_intra |= !isP;
+        for (int p = 0; p < 3; p++) {
+            SbtJob &s = sj[n_sj];
+            memset(&s, 0, sizeof(s));
+            sbt_fill_geometry(&s, g.pw[p], g.ph[p], g.cw[p], g.ch[p], isP, p);
+            sbt_fill_quant(&s, l.quant, isP, p, g.nbh, g.nbv);
+            s.pix = s.opix = cur.p[p];
+            s.pstride = s.ostride = cur.stride[p];
+            s.coef = l.coef + g.coef_off[p];
+            s.llx = l.llx[p];
+            s.stable = d_stab_ + (size_t) li * max_nblk_;
+            s.tile_base = tile_base;
+            tile_base += s.tiles_x * s.tiles_y;
+            if (p < l.nplanes) {
+                HzJob h;
+                memset(&h, 0, sizeof(h));
+                h.cw = g.cw[p];
+                h.ch = g.ch[p];
+                h.plane = p;
+                h.isP = isP;
+                h.pq = s.pq;
+                h.dg = s.dg;
+                hz_fill_regions(&h.rg, g.cw[p], g.ch[p]);
+                h.coef = s.coef;
+                h.stable = s.stable;
+                hzdec_fill_job(hzj + hzdec_job_size() * (size_t) dims.njobs, h, l.pd[p], l.hz[p], &dims);
+            }
+            n_sj++;
+            if (l.is_ref) {
+                ext[n_ext++] = plane_ref(cur, p);
+            }
+            if (out[k].plane[p] && out[k].on_device && out[k].stride[p] == g.pw[p]) {
+                pack[n_pack].src = plane_ref(cur, p);
+                pack[n_pack].dst = out[k].plane[p];
+                n_pack++;
+            }
+        }
+        if (isP) {
+            const MotionGeom mg = {g.w, g.h, g.hs, g.vs, g.blk_w, g.blk_h, g.nbh, g.nbv, 0};
+            bmc_fill_args(&ba[n_p++], mg, d_mv_ + (size_t) li * max_nblk_, l.out[l.cur ^ 1], nullptr, cur, cur, 2);
+        }
+        /* dsv_decoder.c:405: coefficient planes start zeroed.  Planes that were never coded (corrupt plen) stay
+         * all-zero here; the reference leaves the zeroed residual plane untouched instead. */
+        CUDA_CHECK(cudaMemsetAsync(l.coef, 0, g.coef_total * sizeof(int32_t), st));
+    }
+    if (n_sj == 0) {
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        return;
+    }
+    arena_.upload(st);
+    CUDA_CHECK(cudaMemcpyAsync(d_stab_, h_stab_, (size_t) max_nblk_ * L_, cudaMemcpyHostToDevice, st));
+    if (n_p) {
+        CUDA_CHECK(cudaMemcpyAsync(d_mv_, h_mv_, sizeof(DevMV) * (size_t) max_nblk_ * L_, cudaMemcpyHostToDevice, st));
+    }
+    hzdec_launch_jobs(d_hzj, dims, st);
+    sbt_inv_launch(d_sj, n_sj, tile_base, g_.lo_smem, any_intra, st, ev_[0], ev_[1]);
+    bmc_launch(d_bmc, n_p, nbh, nbv, st);
+    extend_launch(d_ext, n_ext, g_.w, g_.h, st);
+    pack_launch(d_pack, n_pack, g_.w, g_.h, st);
+    stats.kernel_launches += 9 + (n_p ? 1 : 0) + (n_ext ? 1 : 0) + (n_pack ? 1 : 0);
+    for (int k = 0; k < n; k++) {
+        DecLane &l = lanes_[(size_t) lane_ids[k]];
+        if (!l.ok) {
+            continue;
+        }
+        const DevFrame &cur = l.out[l.cur];
+        for (int p = 0; p < 3; p++) {
+            if (!out[k].plane[p] || (out[k].on_device && out[k].stride[p] == g_.pw[p])) {
+                continue; /* nowhere to put it, or packed by pack_kernel */
+            }
+            CUDA_CHECK(cudaMemcpy2DAsync(out[k].plane[p], (size_t) out[k].stride[p], cur.p[p], (size_t) cur.stride[p], (size_t) g_.pw[p],
+                                         (size_t) g_.ph[p], out[k].on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+            if (!out[k].on_device) {
+                stats.d2h_bytes += (size_t) g_.pw[p] * g_.ph[p];
+            }
+        }
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    {
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
+        stats.sbt_inv_ms += ms;
+        stats.sbt_inv_launches++;
+        unsigned long long bytes = 0;
+        for (int p = 0; p < 3; p++) {
+            bytes += (unsigned long long) g_.pw[p] * g_.ph[p] + 4ull * g_.cw[p] * g_.ch[p];
+        }
+        stats.sbt_inv_bytes += bytes * (unsigned) (n_sj / 3);
+        stats.pictures += (unsigned) (n_sj / 3);
+    }
+    for (int k = 0; k < n; k++) {
+        DecLane &l = lanes_[(size_t) lane_ids[k]];
+        if (l.ok && l.is_ref) {
+            l.have_ref = 1;
+            l.cur ^= 1;
+        }
+    }
+}
+
+} // namespace dsv
+
+/* ---- public API: DSV_DECODER.ref (the reference keeps its DSV_IMAGE there) holds a one-lane engine ---- */
+
+static DecEngine *dec_engine(DSV_DECODER *d) { return reinterpret_cast<DecEngine *>(d->ref); }
+
 extern "C" DSV_META *dsv_get_metadata(DSV_DECODER *d)
 {
     DSV_META *m = (DSV_META *) dsv_alloc(sizeof(DSV_META));
@@ -169,8 +363,21 @@ extern "C" DSV_META *dsv_get_metadata(DSV_DECODER *d)
 
 extern "C" void dsv_dec_free(DSV_DECODER *d)
 {
-    dec_ctx_destroy(dec_ctx(d));
+    delete dec_engine(d);
     d->ref = NULL;
+}
+
+void dsv::parse_metadata_packet(const uint8_t *pkt, unsigned len, DSV_META *m) /* dsv_decoder.c:50-70 */
+{
+    BitReader br(pkt, len);
+    br.skip_bytes(DSV_PACKET_HDR_SIZE);
+    m->width = (int) br.get_ueg();
+    m->height = (int) br.get_ueg();
+    m->subsamp = (int) br.get_ueg();
+    m->fps_num = (int) br.get_ueg();
+    m->fps_den = (int) br.get_ueg();
+    m->aspect_num = (int) br.get_ueg();
+    m->aspect_den = (int) br.get_ueg();
 }
 
 extern "C" int dsv_dec(DSV_DECODER *d, DSV_BUF *buffer, DSV_FRAME **out, DSV_FNUM *fn)
@@ -186,15 +393,8 @@ extern "C" int dsv_dec(DSV_DECODER *d, DSV_BUF *buffer, DSV_FRAME **out, DSV_FNU
     }
     if (!DSV_PT_IS_PIC(pkt_type)) {
         int ret = DSV_DEC_ERROR;
-        if (pkt_type == DSV_PT_META) { /* dsv_decoder.c:50-70 */
-            DSV_META *m = &d->vidmeta;
-            m->width = (int) br.get_ueg();
-            m->height = (int) br.get_ueg();
-            m->subsamp = (int) br.get_ueg();
-            m->fps_num = (int) br.get_ueg();
-            m->fps_den = (int) br.get_ueg();
-            m->aspect_num = (int) br.get_ueg();
-            m->aspect_den = (int) br.get_ueg();
+        if (pkt_type == DSV_PT_META) {
+            parse_metadata_packet(pkt, pkt_len, &d->vidmeta);
             d->got_metadata = 1;
             ret = DSV_DEC_GOT_META;
         } else if (pkt_type == DSV_PT_EOS) {
@@ -214,119 +414,34 @@ extern "C" int dsv_dec(DSV_DECODER *d, DSV_BUF *buffer, DSV_FRAME **out, DSV_FNU
         dsv_buf_free(buffer);
         return DSV_DEC_ERROR;
     }
-    DecCtx *c = dec_ctx(d);
-    if (c && (c->g.w != md.width || c->g.h != md.height || c->g.subsamp != md.subsamp)) {
-        dec_ctx_destroy(c); /* new sequence parameters: references of the old size are useless */
-        c = nullptr;
+    DecEngine *e = dec_engine(d);
+    if (e && !e->matches(md)) {
+        delete e; /* new sequence parameters: references of the old size are useless */
+        e = nullptr;
     }
-    if (!c) {
-        c = dec_ctx_create(md);
-        d->ref = reinterpret_cast<DSV_IMAGE *>(c);
-    }
-
-    const int has_ref = DSV_PT_HAS_REF(pkt_type), is_ref = DSV_PT_IS_REF(pkt_type);
-    br.align();
-    const DSV_FNUM fno = br.get_bits(32);
-    br.align();
-    const int blk_w = (int) (br.get_ueg() << 2), blk_h = (int) (br.get_ueg() << 2);
-    if (blk_w < DSV_MIN_BLOCK_SIZE || blk_h < DSV_MIN_BLOCK_SIZE || blk_w > DSV_MAX_BLOCK_SIZE || blk_h > DSV_MAX_BLOCK_SIZE) {
-        dsv_buf_free(buffer);
-        return DSV_DEC_ERROR;
-    }
-    plan_blocks(&c->g, blk_w, blk_h);
-    const CodecGeom &g = c->g;
-    cudaStream_t st = c->st;
-
-    read_stability(br, pkt, pkt_len, c->h_stab, g.nblk);
-    if (has_ref) {
-        read_motion(br, pkt, pkt_len, c->h_mv, c->h_stab, g.nbh, g.nbv);
-    }
-    br.align();
-    const int quant = (int) br.get_bits(DSV_MAX_QP_BITS);
-
-    /* plane directory (dsv_decoder.c:383-413) */
-    HzPlaneData pd[3];
-    int nplanes = 0;
-    for (int p = 0; p < 3; p++) {
-        br.align();
-        const int plen = (int) br.get_bits(32);
-        br.align();
-        const int framesz = g.cw[p] * g.ch[p] * (int) sizeof(int32_t);
-        if (plen <= 0 || plen > framesz * 2) {
-            DSV_ERROR(("plane length was strange: %d", plen));
-            break;
-        }
-        const unsigned at = br.byte_pos();
-        if (at >= pkt_len) {
-            DSV_ERROR(("plane starts past the end of the packet"));
-            break;
-        }
-        hzdec_parse_head(pkt + at, pkt_len - at, (unsigned) plen, &pd[p]);
-        pd[p].body = c->d_pkt + at;
-        br.skip_bytes((unsigned) plen);
-        nplanes++;
-    }
-
-    /* ---- device side ---- */
-    if ((size_t) pkt_len > c->pkt_cap) {
-        DSV_ERROR(("packet larger than any valid picture (%u bytes)", pkt_len));
-        dsv_buf_free(buffer);
-        return DSV_DEC_ERROR;
-    }
-    memcpy(c->h_pkt, pkt, pkt_len);
-    memset(c->h_pkt + pkt_len, 0, 64);
-    CUDA_CHECK(cudaMemcpyAsync(c->d_pkt, c->h_pkt, (size_t) pkt_len + 64, cudaMemcpyHostToDevice, st));
-    CUDA_CHECK(cudaMemcpyAsync(c->cb.d_stab, c->h_stab, (size_t) g.nblk, cudaMemcpyHostToDevice, st));
-    if (has_ref) {
-        CUDA_CHECK(cudaMemcpyAsync(c->d_mv, c->h_mv, sizeof(DevMV) * (size_t) g.nblk, cudaMemcpyHostToDevice, st));
-    }
-    const DevFrame &cur = c->out[c->cur];
-    const DevFrame &prev = c->out[c->cur ^ 1];
-    coder_setup_jobs(&c->cb, g, cur, quant, has_ref, 0, st);
-    CUDA_CHECK(cudaMemsetAsync(c->cb.coef, 0, g.coef_total * sizeof(int32_t), st)); /* dsv_decoder.c:405 */
-    if (nplanes > 0) {
-        hzdec_launch(&c->hz, c->cb.hj, pd, nplanes, st);
-    }
-    /* planes that were never coded stay as an all-zero coefficient plane here; the reference leaves
-     * the (zeroed) residual plane untouched instead -- only reachable with a corrupt plen */
-    sbt_inv_launch(c->cb.d_sjobs, 3, c->cb.total_tiles, c->cb.lo_smem, !has_ref, st);
-
-    *fn = fno;
-    if (has_ref) {
-        if (!c->have_ref) {
-            DSV_WARNING(("reference frame not found"));
-            CUDA_CHECK(cudaStreamSynchronize(st));
-            return DSV_DEC_ERROR; /* the reference also keeps the packet buffer on this path (dsv_decoder.c:424-427) */
-        }
-        MotionGeom mg = {g.w, g.h, g.hs, g.vs, g.blk_w, g.blk_h, g.nbh, g.nbv, 0};
-        bmc_launch(mg, c->d_mv, prev, nullptr, cur, 2, st);
-    }
-    if (is_ref) {
-        frame_extend_launch(cur, 3, st); /* dsv_decoder.c:438-440 */
-    }
-    /* output: packed planes -> pinned staging -> a host frame the caller owns one reference of */
-    {
-        uint8_t *o = c->h_out;
-        for (int p = 0; p < 3; p++) {
-            CUDA_CHECK(cudaMemcpy2DAsync(o, g.pw[p], cur.p[p], cur.stride[p], g.pw[p], g.ph[p], cudaMemcpyDeviceToHost, st));
-            o += (size_t) g.pw[p] * g.ph[p];
-        }
+    if (!e) {
+        e = new DecEngine(md, 1);
+        d->ref = reinterpret_cast<DSV_IMAGE *>(e);
     }
     DSV_FRAME *f = dsv_mk_frame(md.subsamp, md.width, md.height, 1);
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    {
-        const uint8_t *s = c->h_out;
-        for (int p = 0; p < 3; p++) {
-            DSV_PLANE *pl = &f->planes[p];
-            for (int y = 0; y < pl->h; y++) {
-                memcpy(DSV_GET_LINE(pl, y), s, (size_t) pl->w);
-                s += pl->w;
-            }
-        }
+    PktRef pr = {pkt, nullptr, pkt_len};
+    OutRef o;
+    for (int p = 0; p < 3; p++) {
+        o.plane[p] = f->planes[p].data;
+        o.stride[p] = f->planes[p].stride;
     }
-    if (is_ref) {
-        c->have_ref = 1;
-        c->cur ^= 1;
+    o.on_device = 0;
+    const int lane = 0;
+    int code = DSV_DEC_ERROR;
+    e->step(1, &lane, &pr, &o, &code, fn);
+    if (code != DSV_DEC_OK) {
+        dsv_frame_ref_dec(f);
+        /* the reference frees the packet on every error path except the missing-reference one
+         * (dsv_decoder.c:356 vs 424-427) */
+        if (*fn == (DSV_FNUM) -1) {
+            dsv_buf_free(buffer);
+        }
+        return DSV_DEC_ERROR;
     }
     dsv_buf_free(buffer);
     *out = f;

@@ -1,28 +1,28 @@
 /*
- * encoder.cpp -- the dsv_encoder.h API (dsv_encoder.c:696-854) on top of the CUDA kernels.
+ * encoder.cpp -- the dsv_encoder.h API (dsv_encoder.c:696-854) and the lock-step encode engine behind it.
  *
  * Host code here does only what is serial and tiny in the reference: GOP / frame-type decisions
- * (dsv_encoder.c:575-694), the CRF quality->quant map (dsv_encoder.c:162-165), the stability tracker
- * and its ZBRLE map (dsv_encoder.c:329-408), motion-vector prediction + side-info sub-streams
- * (dsv_encoder.c:256-327, dsv.c:189-231) and packet framing (dsv_encoder.c:170-192,410-536).
- * Every per-pixel / per-coefficient / per-bit stage is a kernel launch on the encoder's own stream:
- *   H2D -> extend/pyramid -> HME -> [sync: MVs] -> BMC -> SBT fwd + quant -> HZCC -> SBT inv -> recon.
+ * (dsv_encoder.c:575-694), the CRF quality->quant map (dsv_encoder.c:162-165), the ABR controller
+ * (dsv_encoder.c:84-160,816-848), the stability tracker and its ZBRLE map (dsv_encoder.c:329-408),
+ * motion-vector prediction + side-info sub-streams (dsv_encoder.c:256-327, dsv.c:189-231) and packet
+ * framing (dsv_encoder.c:170-192,410-536).  Every per-pixel / per-coefficient / per-bit stage is a kernel
+ * launch batched over all lanes of the engine, on the engine's stream:
+ *   phase 1  ingest (+border) -> luma pyramid -> luma sum -> HME            [sync: MVs, sums, intra counts]
+ *   phase 2  host: frame types, quantiser, stability map, motion side info -> packet heads
+ *   phase 3  BMC + residual -> SBT forward + quantise -> HZCC scan/prefix/pack [event: packet sizes]
+ *            -> SBT inverse -> reconstruction + border (new references) || packets D2H   [sync]
  * There is no CPU implementation of those stages in this library.
  */
 #include "dsv1_b200.h"
 
-#include "../frame.cuh"
-#include "../hzcc.cuh"
-#include "../motion.cuh"
-#include "../sbt.cuh"
 #include "bits.h"
-#include "encoder_ctx.h"
+#include "engine.h"
 
 using namespace dsv;
 
 namespace dsv {
 
-static int size4dim(int dim) /* dsv_encoder.c:556-572 */
+int size4dim(int dim) /* dsv_encoder.c:556-572 */
 {
     if (dim > 1280) return 64;
     if (dim > 1024) return 48;
@@ -33,6 +33,7 @@ static int size4dim(int dim) /* dsv_encoder.c:556-572 */
 
 void plan_geometry(CodecGeom *g, int w, int h, int subsamp)
 {
+    memset(g, 0, sizeof(*g));
     g->w = w;
     g->h = h;
     g->subsamp = subsamp;
@@ -50,7 +51,21 @@ void plan_geometry(CodecGeom *g, int w, int h, int subsamp)
     g->coef_off[1] = (size_t) g->cw[0] * g->ch[0];
     g->coef_off[2] = g->coef_off[1] + (size_t) g->cw[1] * g->ch[1];
     g->coef_total = g->coef_off[2] + (size_t) g->cw[2] * g->ch[2];
-    g->frame_bytes = (size_t) w * h + 2 * (size_t) g->pw[1] * g->ph[1];
+    g->plane_off[0] = 0;
+    g->plane_off[1] = (size_t) w * h;
+    g->plane_off[2] = g->plane_off[1] + (size_t) g->pw[1] * g->ph[1];
+    g->frame_bytes = g->plane_off[2] + (size_t) g->pw[2] * g->ph[2];
+    g->lo_smem = 0;
+    for (int p = 0; p < 3; p++) {
+        g->tiles[p] = ceil_div(g->cw[p], SBT_TW) * ceil_div(g->ch[p], SBT_TH);
+        g->total_tiles += g->tiles[p];
+        HzRegions r;
+        hz_fill_regions(&r, g->cw[p], g->ch[p]);
+        g->chunks[p] = ceil_div(r.base[HZ_NREG], HZ_CHUNK);
+        g->total_chunks += g->chunks[p];
+        size_t s = sbt_lo_smem_bytes(g->cw[p], g->ch[p]);
+        g->lo_smem = s > g->lo_smem ? s : g->lo_smem;
+    }
 }
 
 void plan_blocks(CodecGeom *g, int blk_w, int blk_h)
@@ -62,171 +77,16 @@ void plan_blocks(CodecGeom *g, int blk_w, int blk_h)
     g->nblk = g->nbh * g->nbv;
 }
 
-/* device buffers shared by the encoder and decoder pipelines: coefficient planes + job tables */
-void coder_alloc(CoderBufs *c, const CodecGeom &g)
+bool meta_supported(const DSV_META &m)
 {
-    CUDA_CHECK(cudaMalloc(&c->coef, g.coef_total * sizeof(int32_t)));
-    for (int p = 0; p < 3; p++) {
-        CUDA_CHECK(cudaMalloc(&c->llx[p], sbt_llx_elems(g.cw[p], g.ch[p]) * sizeof(int32_t)));
-        CUDA_CHECK(cudaMalloc(&c->dv[p], sbt_dv_elems(g.cw[p], g.ch[p]) * sizeof(int32_t)));
-        CUDA_CHECK(cudaMemset(c->dv[p], 0, sbt_dv_elems(g.cw[p], g.ch[p]) * sizeof(int32_t)));
+    if (m.width < 16 || m.height < 16 || (m.width & 1) || (m.height & 1) || m.width > 16384 || m.height > 16384) {
+        return false;
     }
-    CUDA_CHECK(cudaMalloc(&c->d_sjobs, 3 * sizeof(SbtJob)));
-    CUDA_CHECK(cudaMalloc(&c->d_hjobs, 3 * sizeof(HzJob)));
-    CUDA_CHECK(cudaMalloc(&c->d_frame, sizeof(HzFrame)));
-    CUDA_CHECK(cudaMalloc(&c->d_stab, (size_t) imax(g.nblk, 1)));
-    int chunks = 0;
-    for (int p = 0; p < 3; p++) {
-        HzRegions r;
-        hz_fill_regions(&r, g.cw[p], g.ch[p]);
-        chunks += ceil_div(r.base[HZ_NREG], HZ_CHUNK);
-    }
-    c->total_chunks = chunks;
-    CUDA_CHECK(cudaMalloc(&c->d_chunks, (size_t) chunks * sizeof(HzChunk)));
-    c->lo_smem = 0;
-    for (int p = 0; p < 3; p++) {
-        size_t s = sbt_lo_smem_bytes(g.cw[p], g.ch[p]);
-        c->lo_smem = s > c->lo_smem ? s : c->lo_smem;
-    }
-}
-
-void coder_free(CoderBufs *c)
-{
-    cudaFree(c->coef);
-    for (int p = 0; p < 3; p++) {
-        cudaFree(c->llx[p]);
-        cudaFree(c->dv[p]);
-    }
-    cudaFree(c->d_sjobs);
-    cudaFree(c->d_hjobs);
-    cudaFree(c->d_frame);
-    cudaFree(c->d_stab);
-    cudaFree(c->d_chunks);
-    memset(c, 0, sizeof(*c));
-}
-
-/* fill + upload the three plane jobs of one picture */
-void coder_setup_jobs(CoderBufs *c, const CodecGeom &g, const DevFrame &pix, int quant, int isP, int do_quant,
-                      cudaStream_t st)
-{
-    int tile_base = 0, chunk_base = 0;
-    for (int p = 0; p < 3; p++) {
-        SbtJob &s = c->sj[p];
-        memset(&s, 0, sizeof(s));
-        sbt_fill_geometry(&s, g.pw[p], g.ph[p], g.cw[p], g.ch[p], isP, p);
-        sbt_fill_quant(&s, quant, isP, p, g.nbh, g.nbv);
-        s.pix = pix.p[p];
-        s.pstride = pix.stride[p];
-        s.coef = c->coef + g.coef_off[p];
-        s.llx = c->llx[p];
-        s.dv = c->dv[p];
-        s.stable = c->d_stab;
-        s.do_quant = do_quant;
-        s.tile_base = tile_base;
-        tile_base += s.tiles_x * s.tiles_y;
-
-        HzJob &h = c->hj[p];
-        memset(&h, 0, sizeof(h));
-        hz_fill_job(&h, g.cw[p], g.ch[p], quant, isP, p, g.nbh, g.nbv);
-        h.coef = s.coef;
-        h.dv = s.dv;
-        h.stable = c->d_stab;
-        h.chunk_base = chunk_base;
-        h.frame = 0;
-        chunk_base += h.nchunks;
-    }
-    c->total_tiles = tile_base;
-    CUDA_CHECK(cudaMemcpyAsync(c->d_sjobs, c->sj, sizeof(c->sj), cudaMemcpyHostToDevice, st));
-    CUDA_CHECK(cudaMemcpyAsync(c->d_hjobs, c->hj, sizeof(c->hj), cudaMemcpyHostToDevice, st));
+    return m.subsamp == DSV_SUBSAMP_444 || m.subsamp == DSV_SUBSAMP_422 || m.subsamp == DSV_SUBSAMP_420 ||
+           m.subsamp == DSV_SUBSAMP_411;
 }
 
 } // namespace dsv
-
-/* ============================================================================================== */
-
-static EncCtx *enc_ctx(DSV_ENCODER *enc) { return reinterpret_cast<EncCtx *>(enc->ref); }
-
-static void enc_ctx_destroy(EncCtx *c)
-{
-    if (!c) {
-        return;
-    }
-    cudaStreamSynchronize(c->st);
-    coder_free(&c->cb);
-    devframe_free(&c->xf);
-    devframe_free(&c->pred);
-    for (int i = 0; i < 2; i++) {
-        devframe_free(&c->pad[i]);
-        devframe_free(&c->recon[i]);
-        for (int l = 0; l < DSV_MAX_PYRAMID_LEVELS; l++) {
-            devframe_free(&c->pyr[i][l]);
-        }
-    }
-    for (int l = 0; l <= DSV_MAX_PYRAMID_LEVELS; l++) {
-        cudaFree(c->d_mvf[l]);
-    }
-    cudaFree(c->d_aux);
-    cudaFree(c->d_pkt);
-    cudaFree(c->d_misc);
-    cudaFreeHost(c->h_in);
-    cudaFreeHost(c->h_pkt);
-    cudaFreeHost(c->h_mv);
-    cudaFreeHost(c->h_misc);
-    cudaFreeHost(c->h_frame);
-    cudaStreamDestroy(c->st);
-    delete c;
-}
-
-/* created on the first dsv_enc call, when metadata, gop and pyramid settings are final */
-static EncCtx *enc_ctx_create(DSV_ENCODER *enc)
-{
-    EncCtx *c = new EncCtx();
-    const DSV_META &md = enc->vidmeta;
-    if ((md.width & 1) || (md.height & 1) || md.width < 16 || md.height < 16) {
-        DSV_ERROR(("unsupported dimensions %dx%d: width and height must be even and >= 16", md.width, md.height));
-        exit(-1);
-    }
-    plan_geometry(&c->g, md.width, md.height, md.subsamp);
-    plan_blocks(&c->g, iclamp(size4dim(md.width) & ~7, DSV_MIN_BLOCK_SIZE, DSV_MAX_BLOCK_SIZE),
-                iclamp(size4dim(md.height) & ~7, DSV_MIN_BLOCK_SIZE, DSV_MAX_BLOCK_SIZE));
-    const CodecGeom &g = c->g;
-    c->inter = enc->gop != DSV_GOP_INTRA;
-
-    CUDA_CHECK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-    coder_alloc(&c->cb, g);
-    devframe_alloc(&c->xf, g.w, g.h, g.subsamp);
-
-    /* packet upper bound as in dsv_encoder.c:472-491 */
-    size_t ub = (size_t) g.w * g.h;
-    ub *= (g.subsamp == DSV_SUBSAMP_444) ? 6 : (g.subsamp == DSV_SUBSAMP_422) ? 4 : 2;
-    c->pkt_cap = ub + 4096 + (size_t) g.nblk * 48;
-    CUDA_CHECK(cudaMalloc(&c->d_pkt, c->pkt_cap));
-    CUDA_CHECK(cudaMemset(c->d_pkt, 0, c->pkt_cap));
-    c->pkt_dirty = 0;
-    CUDA_CHECK(cudaMalloc(&c->d_misc, 64));
-    CUDA_CHECK(cudaMallocHost(&c->h_in, g.frame_bytes));
-    CUDA_CHECK(cudaMallocHost(&c->h_pkt, c->pkt_cap));
-    CUDA_CHECK(cudaMallocHost(&c->h_mv, sizeof(DevMV) * (size_t) g.nblk));
-    CUDA_CHECK(cudaMallocHost(&c->h_misc, 64));
-    CUDA_CHECK(cudaMallocHost(&c->h_frame, sizeof(HzFrame)));
-
-    if (c->inter) {
-        devframe_alloc(&c->pred, g.w, g.h, g.subsamp);
-        for (int i = 0; i < 2; i++) {
-            devframe_alloc(&c->pad[i], g.w, g.h, g.subsamp);
-            devframe_alloc(&c->recon[i], g.w, g.h, g.subsamp);
-            for (int l = 0; l < enc->pyramid_levels; l++) {
-                devframe_alloc(&c->pyr[i][l], ceil_shift(g.w, l + 1), ceil_shift(g.h, l + 1), g.subsamp);
-            }
-        }
-        for (int l = 0; l <= enc->pyramid_levels; l++) {
-            CUDA_CHECK(cudaMalloc(&c->d_mvf[l], sizeof(DevMV) * (size_t) g.nblk));
-            CUDA_CHECK(cudaMemset(c->d_mvf[l], 0, sizeof(DevMV) * (size_t) g.nblk));
-        }
-        CUDA_CHECK(cudaMalloc(&c->d_aux, sizeof(int2) * (size_t) g.nblk));
-    }
-    return c;
-}
 
 /* ---- packet pieces -------------------------------------------------------------------------- */
 
@@ -277,9 +137,9 @@ static void make_metadata_packet(DSV_ENCODER *enc, DSV_BUF *buf) /* dsv_encoder.
 }
 
 /* stability tracker + its ZBRLE map (dsv_encoder.c:329-408); also fills enc->stable_blocks */
-static void put_stable_blocks(DSV_ENCODER *enc, EncCtx *c, int isP, const DevMV *mvs, BitWriter &bw)
+static void put_stable_blocks(DSV_ENCODER *enc, const CodecGeom &g, int isP, const DevMV *mvs, BitWriter &bw)
 {
-    const int nblk = c->g.nblk;
+    const int nblk = g.nblk;
     std::vector<uint8_t> tmp((size_t) nblk * 4 + 64, 0);
     RleWriter rle(tmp.data());
     if (enc->refresh_ctr >= enc->stable_refresh) {
@@ -348,9 +208,9 @@ void dsv::predict_mv(const DevMV *mvs, int nbh, int x, int y, int *px, int *py) 
 
 /* four byte-aligned sub-streams: modes (ZBRLE), MV x, MV y (SEG of prediction error), intra masks
  * (dsv_encoder.c:256-327) */
-static void put_motion(EncCtx *c, const DevMV *mvs, BitWriter &bw)
+static void put_motion(const CodecGeom &g, const DevMV *mvs, BitWriter &bw)
 {
-    const int nbh = c->g.nbh, nbv = c->g.nbv;
+    const int nbh = g.nbh, nbv = g.nbv;
     const size_t ub = (size_t) nbh * nbv * 32;
     std::vector<uint8_t> b_mode(ub, 0), b_x(ub, 0), b_y(ub, 0), b_mask(ub, 0);
     RleWriter rle(b_mode.data());
@@ -384,63 +244,6 @@ static void put_motion(EncCtx *c, const DevMV *mvs, BitWriter &bw)
         bw.align();
         bw.concat(data[s], len[s]);
     }
-}
-
-/* ---- public API ------------------------------------------------------------------------------ */
-
-extern "C" void dsv_enc_init(DSV_ENCODER *enc) /* defaults: dsv_encoder.c:696-722 */
-{
-    memset(enc, 0, sizeof(*enc));
-    enc->prev_gop = (DSV_FNUM) -1;
-    enc->quality = DSV_QUALITY_PERCENT(85);
-    enc->gop = 24;
-    enc->pyramid_levels = 0;
-    enc->rc_mode = DSV_RATE_CONTROL_CRF;
-    enc->bitrate = INT_MAX;
-    enc->max_q_step = DSV_MAX_QUALITY / 200;
-    enc->min_quality = DSV_QUALITY_PERCENT(1);
-    enc->max_quality = DSV_QUALITY_PERCENT(95);
-    enc->min_I_frame_quality = DSV_QUALITY_PERCENT(5);
-    enc->rc_high_motion_nudge = 1;
-    enc->intra_pct_thresh = 50;
-    enc->stable_refresh = 14;
-    enc->scene_change_delta = 4;
-    enc->do_scd = 1;
-}
-
-extern "C" void dsv_enc_start(DSV_ENCODER *enc) /* dsv_encoder.c:724-734 */
-{
-    enc->quality = iclamp(enc->quality, 0, DSV_MAX_QUALITY);
-    if (enc->rc_mode != DSV_RATE_CONTROL_CRF) {
-        enc->rc_quant = (unsigned) enc->quality;
-        enc->avg_P_frame_q = enc->quality * 4 / 5;
-    }
-    enc->force_metadata = 1;
-}
-
-extern "C" void dsv_enc_free(DSV_ENCODER *enc)
-{
-    enc_ctx_destroy(enc_ctx(enc));
-    enc->ref = NULL;
-    if (enc->stability) {
-        dsv_free(enc->stability);
-        enc->stability = NULL;
-    }
-    if (enc->stable_blocks) {
-        dsv_free(enc->stable_blocks);
-        enc->stable_blocks = NULL;
-    }
-}
-
-extern "C" void dsv_enc_set_metadata(DSV_ENCODER *enc, DSV_META *md) { enc->vidmeta = *md; }
-extern "C" void dsv_enc_force_metadata(DSV_ENCODER *enc) { enc->force_metadata = 1; }
-
-extern "C" void dsv_enc_end_of_stream(DSV_ENCODER *enc, DSV_BUF *bufs) /* dsv_encoder.c:765-778 */
-{
-    dsv_mk_buf(&bufs[0], DSV_PACKET_HDR_SIZE);
-    BitWriter bw(bufs[0].data);
-    put_packet_hdr(bw, DSV_PT_EOS);
-    set_links(enc, &bufs[0], 1);
 }
 
 /* ABR controller (dsv_encoder.c:84-160): host-only, needs every previous packet's size, hence 1 GPU */
@@ -529,15 +332,583 @@ static void rate_control_update(DSV_ENCODER *enc, int isP, unsigned pkt_len) /* 
     }
 }
 
-extern "C" int dsv_enc(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_BUF *bufs)
-{
-    if (bufs == NULL) {
-        DSV_ERROR(("null buffer list passed to encoder!"));
-        return 0;
-    }
-    const int w = enc->vidmeta.width, h = enc->vidmeta.height;
 
-    /* block size / pyramid depth (dsv_encoder.c:588-613) -- fixed for the life of the encoder */
+/* ============================================================================================== */
+/* lock-step encode engine                                                                        */
+/* ============================================================================================== */
+
+namespace dsv {
+
+struct LaneMisc { /* device/pinned per-lane scalars */
+    unsigned long long luma_sum;
+    int nintra;
+    int pad;
+};
+
+EncEngine::EncEngine(const DSV_META &md, int gop, int pyramid_levels, int lanes)
+{
+    if (!meta_supported(md)) {
+        DSV_ERROR(("unsupported picture format %dx%d subsamp %d: width and height must be even and >= 16", md.width,
+                   md.height, md.subsamp));
+        exit(-1);
+    }
+    CUDA_CHECK(cudaGetDevice(&device));
+    plan_geometry(&g_, md.width, md.height, md.subsamp);
+    plan_blocks(&g_, iclamp(size4dim(md.width) & ~7, DSV_MIN_BLOCK_SIZE, DSV_MAX_BLOCK_SIZE),
+                iclamp(size4dim(md.height) & ~7, DSV_MIN_BLOCK_SIZE, DSV_MAX_BLOCK_SIZE));
+    inter_ = gop != DSV_GOP_INTRA;
+    levels_ = pyramid_levels;
+    L_ = lanes;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    for (auto &e : ev_) {
+        CUDA_CHECK(cudaEventCreate(&e));
+    }
+    const size_t per_lane = 3 * (sizeof(SbtJob) + sizeof(HzJob)) + sizeof(HzFrame) + (size_t) (levels_ + 1) * sizeof(HmeArgs) +
+                            sizeof(BmcArgs) + 16 * sizeof(ReconItem) + 2048;
+    arena_.create(per_lane * (size_t) L_ + 4096);
+    CUDA_CHECK(cudaMalloc(&d_mv0_, sizeof(DevMV) * (size_t) g_.nblk * L_));
+    CUDA_CHECK(cudaMemset(d_mv0_, 0, sizeof(DevMV) * (size_t) g_.nblk * L_));
+    CUDA_CHECK(cudaMallocHost(&h_mv0_, sizeof(DevMV) * (size_t) g_.nblk * L_));
+    memset(h_mv0_, 0, sizeof(DevMV) * (size_t) g_.nblk * L_);
+    CUDA_CHECK(cudaMalloc(&d_stab_, (size_t) g_.nblk * L_));
+    CUDA_CHECK(cudaMallocHost(&h_stab_, (size_t) g_.nblk * L_));
+    CUDA_CHECK(cudaMalloc(&d_misc_, sizeof(LaneMisc) * (size_t) L_));
+    CUDA_CHECK(cudaMallocHost(&h_misc_, sizeof(LaneMisc) * (size_t) L_));
+    CUDA_CHECK(cudaMalloc(&d_chunks_, sizeof(HzChunk) * (size_t) g_.total_chunks * L_));
+    CUDA_CHECK(cudaMalloc(&d_frames_, sizeof(HzFrame) * (size_t) L_));
+    CUDA_CHECK(cudaMallocHost(&h_frames_, sizeof(HzFrame) * (size_t) L_));
+    lanes_.resize((size_t) L_);
+    for (int i = 0; i < L_; i++) {
+        alloc_lane(lanes_[(size_t) i]);
+        lanes_[(size_t) i].d_mvf[0] = d_mv0_ + (size_t) i * g_.nblk;
+    }
+}
+
+void EncEngine::alloc_lane(EncLane &l)
+{
+    const CodecGeom &g = g_;
+    CUDA_CHECK(cudaMalloc(&l.coef, g.coef_total * sizeof(int32_t)));
+    for (int p = 0; p < 3; p++) {
+        CUDA_CHECK(cudaMalloc(&l.llx[p], sbt_llx_elems(g.cw[p], g.ch[p]) * sizeof(int32_t)));
+        CUDA_CHECK(cudaMalloc(&l.dv[p], sbt_dv_elems(g.cw[p], g.ch[p]) * sizeof(int32_t)));
+        CUDA_CHECK(cudaMemset(l.dv[p], 0, sbt_dv_elems(g.cw[p], g.ch[p]) * sizeof(int32_t)));
+    }
+    /* packet upper bound as in dsv_encoder.c:472-491 */
+    size_t ub = (size_t) g.w * g.h;
+    ub *= (g.subsamp == DSV_SUBSAMP_444) ? 6 : (g.subsamp == DSV_SUBSAMP_422) ? 4 : 2;
+    const size_t pkt_cap = ub + 4096 + (size_t) g.nblk * 48;
+    CUDA_CHECK(cudaMalloc(&l.d_pkt, pkt_cap));
+    CUDA_CHECK(cudaMemset(l.d_pkt, 0, pkt_cap));
+    CUDA_CHECK(cudaMalloc(&l.d_in, g.frame_bytes + 64));
+    CUDA_CHECK(cudaMallocHost(&l.h_head, 512 + (size_t) g.nblk * 48));
+    devframe_alloc(&l.xf, g.w, g.h, g.subsamp);
+    if (inter_) {
+        devframe_alloc(&l.pred, g.w, g.h, g.subsamp);
+        for (int i = 0; i < 2; i++) {
+            devframe_alloc(&l.pad[i], g.w, g.h, g.subsamp);
+            devframe_alloc(&l.recon[i], g.w, g.h, g.subsamp);
+            for (int k = 0; k < levels_; k++) {
+                devframe_alloc(&l.pyr[i][k], ceil_shift(g.w, k + 1), ceil_shift(g.h, k + 1), g.subsamp);
+            }
+        }
+        for (int k = 1; k <= levels_; k++) {
+            CUDA_CHECK(cudaMalloc(&l.d_mvf[k], sizeof(DevMV) * (size_t) g.nblk));
+            CUDA_CHECK(cudaMemset(l.d_mvf[k], 0, sizeof(DevMV) * (size_t) g.nblk));
+        }
+        CUDA_CHECK(cudaMalloc(&l.d_aux, sizeof(int2) * (size_t) g.nblk));
+    }
+}
+
+void EncEngine::free_lane(EncLane &l)
+{
+    cudaFree(l.coef);
+    for (int p = 0; p < 3; p++) {
+        cudaFree(l.llx[p]);
+        cudaFree(l.dv[p]);
+    }
+    cudaFree(l.d_pkt);
+    cudaFree(l.d_in);
+    cudaFreeHost(l.h_head);
+    devframe_free(&l.xf);
+    devframe_free(&l.pred);
+    for (int i = 0; i < 2; i++) {
+        devframe_free(&l.pad[i]);
+        devframe_free(&l.recon[i]);
+        for (int k = 0; k < DSV_MAX_PYRAMID_LEVELS; k++) {
+            devframe_free(&l.pyr[i][k]);
+        }
+    }
+    for (int k = 1; k <= DSV_MAX_PYRAMID_LEVELS; k++) {
+        cudaFree(l.d_mvf[k]);
+    }
+    cudaFree(l.d_aux);
+}
+
+EncEngine::~EncEngine()
+{
+    cudaStreamSynchronize(st_);
+    for (auto &l : lanes_) {
+        free_lane(l);
+    }
+    arena_.destroy();
+    cudaFree(d_mv0_);
+    cudaFreeHost(h_mv0_);
+    cudaFree(d_stab_);
+    cudaFreeHost(h_stab_);
+    cudaFree(d_misc_);
+    cudaFreeHost(h_misc_);
+    cudaFree(d_chunks_);
+    cudaFree(d_frames_);
+    cudaFreeHost(h_frames_);
+    for (auto &e : ev_) {
+        cudaEventDestroy(e);
+    }
+    cudaStreamDestroy(st_);
+}
+
+void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bufs)[2], int *nbufs, PktSink *sinks)
+{
+    const CodecGeom &g = g_;
+    cudaStream_t st = st_;
+    const MotionGeom mg = {g.w, g.h, g.hs, g.vs, g.blk_w, g.blk_h, g.nbh, g.nbv, levels_};
+    LaneMisc *h_misc = reinterpret_cast<LaneMisc *>(h_misc_), *d_misc = reinterpret_cast<LaneMisc *>(d_misc_);
+    arena_.reset();
+
+    /* ---- phase 1: ingest, pyramid, luma sums, motion search -------------------------------------- */
+    IngestItem *d_ing;
+    IngestItem *ing = arena_.push_n<IngestItem>((size_t) 3 * n, &d_ing);
+    for (int k = 0; k < n; k++) {
+        EncLane &l = lanes_[(size_t) lane_ids[k]];
+        l.fnum = l.enc->next_fnum++;
+        const DevFrame &dst = inter_ ? l.pad[l.cur] : l.xf;
+        for (int p = 0; p < 3; p++) {
+            const uint8_t *packed;
+            const size_t pbytes = (size_t) g.pw[p] * g.ph[p];
+            if (src[k].on_device && src[k].stride[p] == g.pw[p]) {
+                packed = src[k].plane[p];
+            } else {
+                uint8_t *stage = l.d_in + g.plane_off[p];
+                CUDA_CHECK(cudaMemcpy2DAsync(stage, (size_t) g.pw[p], src[k].plane[p], (size_t) src[k].stride[p], (size_t) g.pw[p],
+                                             (size_t) g.ph[p], src[k].on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+                if (!src[k].on_device) {
+                    stats.h2d_bytes += pbytes;
+                }
+                packed = stage;
+            }
+            ing[3 * k + p].src = packed;
+            ing[3 * k + p].dst = plane_ref(dst, p);
+        }
+    }
+    /* GOP bookkeeping (dsv_encoder.c:624-652): host state only */
+    int n_search = 0, n_sum = 0;
+    for (int k = 0; k < n; k++) {
+        EncLane &l = lanes_[(size_t) lane_ids[k]];
+        DSV_ENCODER *enc = l.enc;
+        l.gop_start = 0;
+        l.is_ref = l.has_ref = l.forced_intra = 0;
+        if (enc->force_metadata || ((enc->prev_gop + (DSV_FNUM) enc->gop) <= l.fnum)) {
+            l.gop_start = 1;
+            enc->prev_gop = l.fnum;
+            enc->force_metadata = 0;
+        }
+        if (inter_) {
+            l.is_ref = 1;
+            l.has_ref = !l.gop_start;
+            if (l.has_ref && !l.have_ref) {
+                DSV_ASSERT(0 && "P frame without a reference");
+            }
+            n_search += l.has_ref;
+            n_sum += enc->do_scd ? 1 : 0;
+        }
+    }
+    Down2Item *d_dn[DSV_MAX_PYRAMID_LEVELS] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    SumItem *d_sum = nullptr;
+    HmeArgs *d_hme = nullptr;
+    if (inter_) {
+        for (int lv = 0; lv < levels_; lv++) {
+            Down2Item *dn = arena_.push_n<Down2Item>((size_t) n, &d_dn[lv]);
+            for (int k = 0; k < n; k++) {
+                EncLane &l = lanes_[(size_t) lane_ids[k]];
+                dn[k].src = plane_ref(lv == 0 ? l.pad[l.cur] : l.pyr[l.cur][lv - 1], 0);
+                dn[k].dst = plane_ref(l.pyr[l.cur][lv], 0);
+            }
+        }
+        if (n_sum) {
+            SumItem *sm = arena_.push_n<SumItem>((size_t) n_sum, &d_sum);
+            int q = 0;
+            for (int k = 0; k < n; k++) {
+                EncLane &l = lanes_[(size_t) lane_ids[k]];
+                if (l.enc->do_scd) {
+                    sm[q].src = plane_ref(l.pyr[l.cur][levels_ - 1], 0);
+                    sm[q].out = &d_misc[lane_ids[k]].luma_sum;
+                    q++;
+                }
+            }
+        }
+        if (n_search) { /* speculative: a scene change below simply discards the vectors */
+            HmeArgs *ha = arena_.push_n<HmeArgs>((size_t) (levels_ + 1) * n_search, &d_hme);
+            int q = 0;
+            for (int k = 0; k < n; k++) {
+                EncLane &l = lanes_[(size_t) lane_ids[k]];
+                if (!l.has_ref) {
+                    continue;
+                }
+                DevFrame sf[DSV_MAX_PYRAMID_LEVELS + 1], rf[DSV_MAX_PYRAMID_LEVELS + 1];
+                sf[0] = l.pad[l.cur];
+                rf[0] = l.pad[l.cur ^ 1];
+                for (int lv = 0; lv < levels_; lv++) {
+                    sf[lv + 1] = l.pyr[l.cur][lv];
+                    rf[lv + 1] = l.pyr[l.cur ^ 1][lv];
+                }
+                for (int lv = 0; lv <= levels_; lv++) {
+                    hme_fill_args(&ha[(size_t) lv * n_search + q], mg, lv, sf, rf, l.d_mvf, l.d_aux, &d_misc[lane_ids[k]].nintra);
+                }
+                q++;
+            }
+        }
+    }
+    arena_.upload(st);
+    ingest_launch(d_ing, 3 * n, g.w, g.h, st);
+    stats.kernel_launches += 1;
+    bool need_sync = false;
+    if (inter_) {
+        for (int lv = 0; lv < levels_; lv++) {
+            down2_launch(d_dn[lv], n, ceil_shift(g.w, lv + 1), ceil_shift(g.h, lv + 1), st);
+        }
+        stats.kernel_launches += (unsigned) levels_;
+        if (n_sum || n_search) {
+            CUDA_CHECK(cudaMemsetAsync(d_misc_, 0, sizeof(LaneMisc) * (size_t) L_, st));
+        }
+        if (n_sum) {
+            sum_launch(d_sum, n_sum, ceil_shift(g.h, levels_), st);
+            stats.kernel_launches += 1;
+        }
+        if (n_search) {
+            hme_launch(d_hme, n_search, mg, st);
+            stats.kernel_launches += (unsigned) levels_ + 2;
+            CUDA_CHECK(cudaMemcpyAsync(h_mv0_, d_mv0_, sizeof(DevMV) * (size_t) g.nblk * L_, cudaMemcpyDeviceToHost, st));
+        }
+        if (n_sum || n_search) {
+            CUDA_CHECK(cudaMemcpyAsync(h_misc_, d_misc_, sizeof(LaneMisc) * (size_t) L_, cudaMemcpyDeviceToHost, st));
+            need_sync = true;
+        }
+    }
+    if (need_sync) {
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+
+    /* ---- phase 2: host decisions + packet heads --------------------------------------------------- */
+    int n_p = 0, n_ref = 0;
+    for (int k = 0; k < n; k++) {
+        const int li = lane_ids[k];
+        EncLane &l = lanes_[(size_t) li];
+        DSV_ENCODER *enc = l.enc;
+        if (inter_) {
+            if (enc->do_scd) { /* check_scene_change, dsv_encoder.c:538-554 */
+                const DevFrame &top = l.pyr[l.cur][levels_ - 1];
+                int al = (int) (h_misc[li].luma_sum / (unsigned long long) (top.w[0] * top.h[0]));
+                if (iabs(enc->prev_avg_luma - al) > enc->scene_change_delta) {
+                    l.has_ref = 0;
+                    l.forced_intra = 1;
+                }
+                enc->prev_avg_luma = al;
+            }
+            if (l.has_ref) { /* motion_est's verdict, dsv_encoder.c:246-253 */
+                int pct = h_misc[li].nintra * 100 / g.nblk;
+                l.forced_intra = 0;
+                if (pct > enc->intra_pct_thresh) {
+                    l.has_ref = 0;
+                    l.forced_intra = 1;
+                }
+            }
+        }
+        const int isP = l.has_ref;
+        const int quality = rate_control_quality(enc, isP, l.forced_intra);
+        l.quant = DSV_MAX_QUALITY - ((DSV_MAX_QUALITY - 5) * quality / DSV_MAX_QUALITY); /* dsv_encoder.c:165 */
+
+        const DevMV *mvs = h_mv0_ + (size_t) li * g.nblk;
+        memset(l.h_head, 0, 256 + (size_t) g.nblk * 48);
+        BitWriter bw(l.h_head);
+        put_packet_hdr(bw, DSV_MAKE_PT(l.is_ref, l.has_ref));
+        bw.align();
+        bw.put_bits(32, l.fnum);
+        bw.align();
+        bw.put_ueg((uint32_t) (g.blk_w >> 2));
+        bw.put_ueg((uint32_t) (g.blk_h >> 2));
+        bw.align();
+        put_stable_blocks(enc, g, isP, mvs, bw);
+        if (l.has_ref) {
+            bw.align();
+            put_motion(g, mvs, bw);
+        }
+        bw.align();
+        bw.put_bits(DSV_MAX_QP_BITS, (uint32_t) l.quant);
+        bw.align(); /* dsv_encode_plane aligns before each plane (hzcc.c:457) */
+        l.head_bytes = bw.byte_pos();
+        memcpy(h_stab_ + (size_t) li * g.nblk, enc->stable_blocks, (size_t) g.nblk);
+        n_p += l.has_ref;
+        n_ref += l.is_ref;
+    }
+
+    /* ---- phase 3: residual, transform, entropy coding, closed-loop reconstruction ------------------ */
+    SbtJob *d_sj;
+    HzJob *d_hj;
+    HzFrame *d_hf = d_frames_;
+    BmcArgs *d_bmc = nullptr;
+    ReconItem *d_rec = nullptr;
+    PlaneRef *d_ext = nullptr;
+    SbtJob *sj = arena_.push_n<SbtJob>((size_t) 3 * n, &d_sj);
+    HzJob *hj = arena_.push_n<HzJob>((size_t) 3 * n, &d_hj);
+    BmcArgs *ba = n_p ? arena_.push_n<BmcArgs>((size_t) n_p, &d_bmc) : nullptr;
+    const int n_i_ref = n_ref - n_p;
+    ReconItem *rec = n_p ? arena_.push_n<ReconItem>((size_t) 3 * n_p, &d_rec) : nullptr;
+    PlaneRef *ext = n_i_ref > 0 ? arena_.push_n<PlaneRef>((size_t) 3 * n_i_ref, &d_ext) : nullptr;
+    int tile_base = 0, qp = 0, qi = 0;
+    bool any_intra = false;
+    for (int k = 0; k < n; k++) {
+        const int li = lane_ids[k];
+        EncLane &l = lanes_[(size_t) li];
+        const int isP = l.has_ref;
+        any_intra |= !isP;
+        const DevFrame &fwd_in = isP ? l.xf : (inter_ ? l.pad[l.cur] : l.xf);
+        const DevFrame &inv_out = isP ? l.xf : (inter_ ? l.recon[l.cur] : l.xf);
+        if (isP) {
+            bmc_fill_args(&ba[qp], mg, l.d_mvf[0], l.recon[l.cur ^ 1], &l.pred, l.pad[l.cur], l.xf, 1);
+        }
+        if (l.pkt_dirty) {
+            CUDA_CHECK(cudaMemsetAsync(l.d_pkt, 0, (size_t) l.pkt_dirty + 64, st));
+        }
+        for (int p = 0; p < 3; p++) {
+            SbtJob &s = sj[3 * k + p];
+            memset(&s, 0, sizeof(s));
+            sbt_fill_geometry(&s, g.pw[p], g.ph[p], g.cw[p], g.ch[p], isP, p);
+            sbt_fill_quant(&s, l.quant, isP, p, g.nbh, g.nbv);
+            s.pix = fwd_in.p[p];
+            s.pstride = fwd_in.stride[p];
+            s.opix = inv_out.p[p];
+            s.ostride = inv_out.stride[p];
+            s.coef = l.coef + g.coef_off[p];
+            s.llx = l.llx[p];
+            s.dv = l.dv[p];
+            s.stable = d_stab_ + (size_t) li * g.nblk;
+            s.do_quant = 1;
+            s.tile_base = tile_base;
+            tile_base += s.tiles_x * s.tiles_y;
+
+            HzJob &h = hj[3 * k + p];
+            memset(&h, 0, sizeof(h));
+            h.cw = g.cw[p];
+            h.ch = g.ch[p];
+            h.plane = p;
+            h.isP = isP;
+            h.pq = s.pq;
+            h.dg = s.dg;
+            hz_fill_regions(&h.rg, g.cw[p], g.ch[p]);
+            h.nchunks = g.chunks[p];
+            h.coef = s.coef;
+            h.dv = s.dv;
+            h.stable = s.stable;
+            h.chunk_base = k * g.total_chunks + (p > 0 ? g.chunks[0] : 0) + (p > 1 ? g.chunks[1] : 0);
+            h.frame = k;
+            if (l.is_ref) {
+                if (isP) {
+                    rec[3 * qp + p].a = plane_ref(l.xf, p);
+                    rec[3 * qp + p].b = plane_ref(l.pred, p);
+                    rec[3 * qp + p].dst = plane_ref(l.recon[l.cur], p);
+                } else {
+                    ext[3 * qi + p] = plane_ref(l.recon[l.cur], p);
+                }
+            }
+        }
+        HzFrame &hf = h_frames_[k];
+        memset(&hf, 0, sizeof(hf));
+        hf.pkt = l.d_pkt;
+        hf.start_byte = l.head_bytes;
+        hf.nplanes = 3;
+        hf.job[0] = 3 * k;
+        hf.job[1] = 3 * k + 1;
+        hf.job[2] = 3 * k + 2;
+        if (isP) {
+            qp++;
+        } else if (l.is_ref) {
+            qi++;
+        }
+    }
+    arena_.upload(st);
+    CUDA_CHECK(cudaMemcpyAsync(d_stab_, h_stab_, (size_t) g.nblk * L_, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(d_hf, h_frames_, sizeof(HzFrame) * (size_t) n, cudaMemcpyHostToDevice, st));
+    if (n_p) {
+        bmc_launch(d_bmc, n_p, g.nbh, g.nbv, st);
+        stats.kernel_launches += 1;
+    }
+    sbt_fwd_launch(d_sj, 3 * n, tile_base, g.lo_smem, st, ev_[0], ev_[1]);
+    hzcc_enc_launch(d_hj, 3 * n, d_chunks_, n * g.total_chunks, d_hf, n, st);
+    stats.kernel_launches += 5;
+    CUDA_CHECK(cudaMemcpyAsync(h_frames_, d_hf, sizeof(HzFrame) * (size_t) n, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaEventRecord(ev_[4], st));
+    if (n_ref) {
+        /* closed loop: reconstruct exactly what the decoder will (dsv_encoder.c:525,662-674) */
+        sbt_inv_launch(d_sj, 3 * n, tile_base, g.lo_smem, any_intra, st, ev_[2], ev_[3]);
+        recon_launch(d_rec, 3 * n_p, g.w, g.h, st);
+        extend_launch(d_ext, 3 * n_i_ref, g.w, g.h, st);
+        stats.kernel_launches += 2 + (n_p ? 1 : 0) + (n_i_ref > 0 ? 1 : 0);
+    }
+    CUDA_CHECK(cudaEventSynchronize(ev_[4])); /* packet sizes are known; reconstruction keeps running */
+
+    for (int k = 0; k < n; k++) {
+        EncLane &l = lanes_[(size_t) lane_ids[k]];
+        DSV_ENCODER *enc = l.enc;
+        const unsigned total = h_frames_[k].total_bytes;
+        DSV_BUF outbuf;
+        int nb = 0;
+        if (sinks) { /* caller-provided stream memory: metadata packet, then the picture, back to back */
+            PktSink &sk = sinks[k];
+            if (l.gop_start) {
+                DSV_BUF meta;
+                make_metadata_packet(enc, &meta);
+                if (sk.room >= meta.len) {
+                    memcpy(sk.at, meta.data, meta.len);
+                    bufs[k][nb].data = sk.at;
+                    bufs[k][nb].len = meta.len;
+                    sk.at += meta.len;
+                    sk.room -= meta.len;
+                } else {
+                    sk.overflow = 1;
+                    bufs[k][nb].data = nullptr;
+                    bufs[k][nb].len = 0;
+                }
+                nb++;
+                dsv_buf_free(&meta);
+            }
+            if (sk.room >= total && !sk.overflow) {
+                outbuf.data = sk.at;
+                outbuf.len = total;
+                sk.at += total;
+                sk.room -= total;
+            } else {
+                sk.overflow = 1;
+                outbuf.data = nullptr;
+                outbuf.len = 0;
+            }
+        } else {
+            dsv_mk_buf(&outbuf, (int) total + 8);
+            outbuf.len = total;
+            if (l.gop_start) {
+                make_metadata_packet(enc, &bufs[k][nb++]);
+            }
+        }
+        if (outbuf.data) {
+            memcpy(outbuf.data, l.h_head, l.head_bytes);
+            CUDA_CHECK(cudaMemcpyAsync(outbuf.data + l.head_bytes, l.d_pkt + l.head_bytes, total - l.head_bytes, cudaMemcpyDeviceToHost, st));
+            stats.d2h_bytes += total - l.head_bytes;
+        }
+        l.pkt_dirty = total;
+        bufs[k][nb++] = outbuf;
+        nbufs[k] = nb;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    {
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
+        stats.sbt_fwd_ms += ms;
+        stats.sbt_fwd_launches++;
+        unsigned long long bytes = 0;
+        for (int p = 0; p < 3; p++) {
+            bytes += (unsigned long long) g.cw[p] * g.ph[p] + 4ull * g.cw[p] * g.ch[p];
+        }
+        stats.sbt_fwd_bytes += bytes * (unsigned) n;
+        if (n_ref) {
+            CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[2], ev_[3]));
+            stats.sbt_inv_ms += ms;
+            stats.sbt_inv_launches++;
+            stats.sbt_inv_bytes += bytes * (unsigned) n;
+        }
+        stats.pictures += (unsigned) n;
+    }
+    for (int k = 0; k < n; k++) {
+        EncLane &l = lanes_[(size_t) lane_ids[k]];
+        DSV_ENCODER *enc = l.enc;
+        if (l.is_ref) {
+            l.have_ref = 1;
+            l.cur ^= 1;
+        }
+        if (l.has_ref) {
+            enc->refresh_ctr++;
+        }
+        DSV_BUF *pic = &bufs[k][nbufs[k] - 1];
+        if (pic->data) {
+            rate_control_update(enc, l.has_ref, pic->len);
+            set_links(enc, pic, 0);
+        }
+    }
+}
+
+} // namespace dsv
+
+/* ---- public API ------------------------------------------------------------------------------ */
+
+/* DSV_ENCODER.ref (the reference's "used internally" slot) holds the one-lane engine */
+static EncEngine *enc_engine(DSV_ENCODER *enc) { return reinterpret_cast<EncEngine *>(enc->ref); }
+
+extern "C" void dsv_enc_init(DSV_ENCODER *enc) /* defaults: dsv_encoder.c:696-722 */
+{
+    memset(enc, 0, sizeof(*enc));
+    enc->prev_gop = (DSV_FNUM) -1;
+    enc->quality = DSV_QUALITY_PERCENT(85);
+    enc->gop = 24;
+    enc->pyramid_levels = 0;
+    enc->rc_mode = DSV_RATE_CONTROL_CRF;
+    enc->bitrate = INT_MAX;
+    enc->max_q_step = DSV_MAX_QUALITY / 200;
+    enc->min_quality = DSV_QUALITY_PERCENT(1);
+    enc->max_quality = DSV_QUALITY_PERCENT(95);
+    enc->min_I_frame_quality = DSV_QUALITY_PERCENT(5);
+    enc->rc_high_motion_nudge = 1;
+    enc->intra_pct_thresh = 50;
+    enc->stable_refresh = 14;
+    enc->scene_change_delta = 4;
+    enc->do_scd = 1;
+}
+
+extern "C" void dsv_enc_start(DSV_ENCODER *enc) /* dsv_encoder.c:724-734 */
+{
+    enc->quality = iclamp(enc->quality, 0, DSV_MAX_QUALITY);
+    if (enc->rc_mode != DSV_RATE_CONTROL_CRF) {
+        enc->rc_quant = (unsigned) enc->quality;
+        enc->avg_P_frame_q = enc->quality * 4 / 5;
+    }
+    enc->force_metadata = 1;
+}
+
+extern "C" void dsv_enc_free(DSV_ENCODER *enc)
+{
+    delete enc_engine(enc);
+    enc->ref = NULL;
+    if (enc->stability) {
+        dsv_free(enc->stability);
+        enc->stability = NULL;
+    }
+    if (enc->stable_blocks) {
+        dsv_free(enc->stable_blocks);
+        enc->stable_blocks = NULL;
+    }
+}
+
+extern "C" void dsv_enc_set_metadata(DSV_ENCODER *enc, DSV_META *md) { enc->vidmeta = *md; }
+extern "C" void dsv_enc_force_metadata(DSV_ENCODER *enc) { enc->force_metadata = 1; }
+
+extern "C" void dsv_enc_end_of_stream(DSV_ENCODER *enc, DSV_BUF *bufs) /* dsv_encoder.c:765-778 */
+{
+    dsv_mk_buf(&bufs[0], DSV_PACKET_HDR_SIZE);
+    BitWriter bw(bufs[0].data);
+    put_packet_hdr(bw, DSV_PT_EOS);
+    set_links(enc, &bufs[0], 1);
+}
+
+/* block grid, stability arrays and pyramid depth (dsv_encoder.c:588-613): fixed for the life of the encoder */
+void dsv::enc_prepare_state(DSV_ENCODER *enc)
+{
+    const int w = enc->vidmeta.width, h = enc->vidmeta.height;
     const int blk_w = iclamp(size4dim(w) & ~7, DSV_MIN_BLOCK_SIZE, DSV_MAX_BLOCK_SIZE);
     const int blk_h = iclamp(size4dim(h) & ~7, DSV_MIN_BLOCK_SIZE, DSV_MAX_BLOCK_SIZE);
     const int nbh = ceil_div(w, blk_w), nbv = ceil_div(h, blk_h);
@@ -553,184 +924,34 @@ extern "C" int dsv_enc(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_BUF *bufs)
         }
         enc->pyramid_levels = iclamp(lvls, 3, DSV_MAX_PYRAMID_LEVELS);
     }
-    if (enc->ref == NULL) {
-        enc->ref = reinterpret_cast<DSV_ENCDATA *>(enc_ctx_create(enc));
-    }
-    EncCtx *c = enc_ctx(enc);
-    const CodecGeom &g = c->g;
-    cudaStream_t st = c->st;
-    const DSV_FNUM fnum = enc->next_fnum++;
-    const int cur = c->cur, prev = cur ^ 1;
+}
 
-    /* ---- input: caller memory -> pinned staging -> device (valid only during this call) ---- */
-    {
-        uint8_t *o = c->h_in;
-        for (int p = 0; p < 3; p++) {
-            const DSV_PLANE *pl = &frame->planes[p];
-            for (int y = 0; y < g.ph[p]; y++) {
-                memcpy(o, pl->data + (size_t) y * pl->stride, (size_t) g.pw[p]);
-                o += g.pw[p];
-            }
-        }
-        const DevFrame &dst = c->inter ? c->pad[cur] : c->xf;
-        const uint8_t *s = c->h_in;
-        for (int p = 0; p < 3; p++) {
-            CUDA_CHECK(cudaMemcpy2DAsync(dst.p[p], dst.stride[p], s, g.pw[p], g.pw[p], g.ph[p], cudaMemcpyHostToDevice, st));
-            s += (size_t) g.pw[p] * g.ph[p];
-        }
-        frame_extend_launch(dst, 3, st); /* clone + extend (dsv_encoder.c:617-623, frame.c:218-220) */
+extern "C" int dsv_enc(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_BUF *bufs)
+{
+    if (bufs == NULL) {
+        DSV_ERROR(("null buffer list passed to encoder!"));
+        return 0;
     }
+    enc_prepare_state(enc);
+    if (enc->ref == NULL) { /* created on the first call, when metadata, gop and pyramid settings are final */
+        EncEngine *e = new EncEngine(enc->vidmeta, enc->gop, enc->pyramid_levels, 1);
+        e->bind(0, enc);
+        enc->ref = reinterpret_cast<DSV_ENCDATA *>(e);
+    }
+    EncEngine *e = enc_engine(enc);
+    PicRef src;
+    for (int p = 0; p < 3; p++) {
+        src.plane[p] = frame->planes[p].data;
+        src.stride[p] = frame->planes[p].stride;
+    }
+    src.on_device = 0;
+    const int lane = 0;
+    DSV_BUF out[1][2];
+    int nb = 0;
+    e->step(1, &lane, &src, out, &nb);
     dsv_frame_ref_dec(frame); /* the encoder owns the reference it was given (dsv_encoder.c:38-40,801) */
-
-    /* ---- GOP bookkeeping (dsv_encoder.c:624-652) ---- */
-    int gop_start = 0, is_ref = 0, has_ref = 0, forced_intra = 0;
-    if (enc->force_metadata || ((enc->prev_gop + (DSV_FNUM) enc->gop) <= fnum)) {
-        gop_start = 1;
-        enc->prev_gop = fnum;
-        enc->force_metadata = 0;
+    for (int i = 0; i < nb; i++) {
+        bufs[i] = out[0][i];
     }
-    if (c->inter) {
-        is_ref = 1;
-        has_ref = !gop_start && c->have_ref;
-        if (!gop_start && !c->have_ref) {
-            DSV_ASSERT(0 && "P frame without a reference");
-        }
-        /* pyramid of the ORIGINAL frame: used by this frame's search and by the next frame as its reference */
-        const DevFrame *below = &c->pad[cur];
-        for (int l = 0; l < enc->pyramid_levels; l++) {
-            frame_down2_luma_launch(*below, c->pyr[cur][l], st);
-            below = &c->pyr[cur][l];
-        }
-        unsigned long long *d_sum = reinterpret_cast<unsigned long long *>(c->d_misc);
-        int *d_nintra = reinterpret_cast<int *>(c->d_misc + 8);
-        int need_sync = 0;
-        if (enc->do_scd) {
-            frame_sum_luma_launch(c->pyr[cur][enc->pyramid_levels - 1], d_sum, st);
-            need_sync = 1;
-        }
-        if (has_ref) { /* speculative: a scene change below simply discards the vectors */
-            MotionGeom mg = {g.w, g.h, g.hs, g.vs, g.blk_w, g.blk_h, g.nbh, g.nbv, enc->pyramid_levels};
-            DevFrame src[DSV_MAX_PYRAMID_LEVELS + 1], ref[DSV_MAX_PYRAMID_LEVELS + 1];
-            src[0] = c->pad[cur];
-            ref[0] = c->pad[prev];
-            for (int l = 0; l < enc->pyramid_levels; l++) {
-                src[l + 1] = c->pyr[cur][l];
-                ref[l + 1] = c->pyr[prev][l];
-            }
-            hme_launch(mg, src, ref, c->d_mvf, c->d_aux, d_nintra, st);
-            CUDA_CHECK(cudaMemcpyAsync(c->h_mv, c->d_mvf[0], sizeof(DevMV) * (size_t) g.nblk, cudaMemcpyDeviceToHost, st));
-            need_sync = 1;
-        }
-        if (need_sync) {
-            CUDA_CHECK(cudaMemcpyAsync(c->h_misc, c->d_misc, 16, cudaMemcpyDeviceToHost, st));
-            CUDA_CHECK(cudaStreamSynchronize(st));
-        }
-        if (enc->do_scd) { /* check_scene_change, dsv_encoder.c:538-554 */
-            const DevFrame &top = c->pyr[cur][enc->pyramid_levels - 1];
-            int al = (int) (*reinterpret_cast<unsigned long long *>(c->h_misc) / (unsigned long long) (top.w[0] * top.h[0]));
-            if (iabs(enc->prev_avg_luma - al) > enc->scene_change_delta) {
-                has_ref = 0;
-                forced_intra = 1;
-            }
-            enc->prev_avg_luma = al;
-        }
-        if (has_ref) { /* motion_est's verdict, dsv_encoder.c:246-253 */
-            int nintra = *reinterpret_cast<int *>(c->h_misc + 8);
-            int pct = nintra * 100 / g.nblk;
-            forced_intra = 0;
-            if (pct > enc->intra_pct_thresh) {
-                has_ref = 0;
-                forced_intra = 1;
-            }
-        }
-    }
-    const int isP = has_ref;
-    const int quality = rate_control_quality(enc, isP, forced_intra);
-    const int quant = DSV_MAX_QUALITY - ((DSV_MAX_QUALITY - 5) * quality / DSV_MAX_QUALITY); /* dsv_encoder.c:165 */
-
-    /* ---- residual formation (dsv_encoder.c:657-660) ---- */
-    if (c->inter) {
-        CUDA_CHECK(cudaMemcpyAsync(c->xf.alloc, c->pad[cur].alloc, c->xf.bytes, cudaMemcpyDeviceToDevice, st));
-        if (has_ref) {
-            MotionGeom mg = {g.w, g.h, g.hs, g.vs, g.blk_w, g.blk_h, g.nbh, g.nbv, enc->pyramid_levels};
-            bmc_launch(mg, c->d_mvf[0], c->recon[prev], &c->pred, c->xf, 1, st);
-        }
-    }
-
-    /* ---- packet head on the host: header, frame number, block size, stability, motion ---- */
-    memset(c->h_pkt, 0, 256 + (size_t) g.nblk * 48);
-    BitWriter bw(c->h_pkt);
-    put_packet_hdr(bw, DSV_MAKE_PT(is_ref, has_ref));
-    bw.align();
-    bw.put_bits(32, fnum);
-    bw.align();
-    bw.put_ueg((uint32_t) (g.blk_w >> 2));
-    bw.put_ueg((uint32_t) (g.blk_h >> 2));
-    bw.align();
-    put_stable_blocks(enc, c, isP, c->h_mv, bw);
-    if (has_ref) {
-        bw.align();
-        put_motion(c, c->h_mv, bw);
-    }
-    bw.align();
-    bw.put_bits(DSV_MAX_QP_BITS, (uint32_t) quant);
-    bw.align(); /* dsv_encode_plane aligns before each plane (hzcc.c:457) */
-    const unsigned head_bytes = bw.byte_pos();
-
-    /* ---- device side of encode_picture (dsv_encoder.c:513-526) ---- */
-    if (c->pkt_dirty) {
-        CUDA_CHECK(cudaMemsetAsync(c->d_pkt, 0, imin((int) c->pkt_cap, (int) c->pkt_dirty + 64), st));
-    }
-    CUDA_CHECK(cudaMemcpyAsync(c->d_pkt, c->h_pkt, head_bytes, cudaMemcpyHostToDevice, st));
-    CUDA_CHECK(cudaMemcpyAsync(c->cb.d_stab, enc->stable_blocks, (size_t) g.nblk, cudaMemcpyHostToDevice, st));
-    coder_setup_jobs(&c->cb, g, c->xf, quant, isP, 1, st);
-    HzFrame hf;
-    memset(&hf, 0, sizeof(hf));
-    hf.pkt = c->d_pkt;
-    hf.start_byte = head_bytes;
-    hf.nplanes = 3;
-    hf.job[0] = 0; hf.job[1] = 1; hf.job[2] = 2;
-    *c->h_frame = hf;
-    CUDA_CHECK(cudaMemcpyAsync(c->cb.d_frame, c->h_frame, sizeof(HzFrame), cudaMemcpyHostToDevice, st));
-    sbt_fwd_launch(c->cb.d_sjobs, 3, c->cb.total_tiles, c->cb.lo_smem, st);
-    hzcc_enc_launch(c->cb.d_hjobs, 3, c->cb.d_chunks, c->cb.total_chunks, c->cb.d_frame, 1, st);
-    CUDA_CHECK(cudaMemcpyAsync(c->h_frame, c->cb.d_frame, sizeof(HzFrame), cudaMemcpyDeviceToHost, st));
-    if (is_ref) {
-        /* closed loop: reconstruct exactly what the decoder will (dsv_encoder.c:525,662-674) */
-        sbt_inv_launch(c->cb.d_sjobs, 3, c->cb.total_tiles, c->cb.lo_smem, !isP, st);
-        if (has_ref) {
-            frame_add_launch(c->xf, c->pred, st);
-        }
-        frame_copy_launch(c->recon[cur], c->xf, st);
-        frame_extend_launch(c->recon[cur], 3, st);
-    }
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    const unsigned total = c->h_frame->total_bytes;
-    if (total > c->pkt_cap - 64) {
-        DSV_ERROR(("packet exceeds the output bound"));
-        exit(-1);
-    }
-    DSV_BUF outbuf;
-    dsv_mk_buf(&outbuf, (int) total + 8);
-    outbuf.len = total;
-    memcpy(outbuf.data, c->h_pkt, head_bytes);
-    CUDA_CHECK(cudaMemcpyAsync(outbuf.data + head_bytes, c->d_pkt + head_bytes, total - head_bytes, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    c->pkt_dirty = total;
-    if (is_ref) {
-        c->have_ref = 1;
-        c->cur ^= 1;
-    }
-
-    int nbuf = 0;
-    if (gop_start) {
-        make_metadata_packet(enc, &bufs[nbuf++]);
-    }
-    bufs[nbuf++] = outbuf;
-    if (isP) {
-        enc->refresh_ctr++;
-    }
-    rate_control_update(enc, isP, outbuf.len);
-    set_links(enc, &bufs[nbuf - 1], 0);
-    return nbuf;
+    return nb;
 }

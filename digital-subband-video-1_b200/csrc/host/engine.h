@@ -1,0 +1,174 @@
+/*
+ * engine.h -- lock-step batch engines behind both public APIs.
+ *
+ * An engine owns L "lanes" (independent sequences, each with its own reference frames, coefficient planes,
+ * packet buffer and rate/stability state) and advances all active lanes by one picture per step(): every
+ * pipeline stage is ONE kernel launch over the planes / blocks / chunks of all lanes, host<->device
+ * synchronisation happens a fixed number of times per step regardless of L.
+ *   dsv_enc / dsv_dec (dsv1_b200.h)          = an engine with one lane, one step per call
+ *   dsvb_encode / dsvb_decode (dsv1_b200_batch.h) = L lanes, closed-GOP / whole-sequence sharding
+ */
+#pragma once
+#include <vector>
+
+#include "dsv1_b200.h"
+
+#include "../frame.cuh"
+#include "../hzcc.cuh"
+#include "../hzcc_dec.cuh"
+#include "../motion.cuh"
+#include "../sbt.cuh"
+
+namespace dsv {
+
+struct CodecGeom {
+    int w, h, subsamp, hs, vs;
+    int pw[3], ph[3]; /* plane sizes */
+    int cw[3], ch[3]; /* coefficient plane sizes (frame.c:29-61) */
+    size_t coef_off[3], coef_total;
+    size_t frame_bytes; /* packed planar frame */
+    size_t plane_off[3];
+    int blk_w, blk_h, nbh, nbv, nblk;
+    int tiles[3], total_tiles;   /* SBT tiles per plane / picture */
+    int chunks[3], total_chunks; /* HZCC encoder chunks per plane / picture */
+    size_t lo_smem;
+};
+
+void plan_geometry(CodecGeom *g, int w, int h, int subsamp);
+void plan_blocks(CodecGeom *g, int blk_w, int blk_h);
+int size4dim(int dim);
+void predict_mv(const DevMV *mvs, int nbh, int x, int y, int *px, int *py);
+
+/* where one input / output picture lives */
+struct PicRef {
+    const uint8_t *plane[3];
+    int stride[3];
+    int on_device;
+};
+
+/* live timing of the dominant kernels (CUDA events on the engine's stream) + work counters */
+struct EngineStats {
+    double sbt_fwd_ms = 0, sbt_inv_ms = 0;
+    unsigned long long sbt_fwd_launches = 0, sbt_inv_launches = 0;
+    unsigned long long sbt_fwd_bytes = 0, sbt_inv_bytes = 0; /* algorithmic: w*h + 4*cw*ch per plane */
+    unsigned long long kernel_launches = 0;
+    unsigned long long h2d_bytes = 0, d2h_bytes = 0;
+    unsigned long long pictures = 0;
+};
+
+struct EncLane {
+    DSV_ENCODER *enc = nullptr; /* host-side state of this sequence */
+    DevFrame pad[2], recon[2], pyr[2][DSV_MAX_PYRAMID_LEVELS], xf, pred;
+    int cur = 0, have_ref = 0;
+    DevMV *d_mvf[DSV_MAX_PYRAMID_LEVELS + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int2 *d_aux = nullptr;
+    int32_t *coef = nullptr, *llx[3] = {nullptr, nullptr, nullptr}, *dv[3] = {nullptr, nullptr, nullptr};
+    uint8_t *d_pkt = nullptr, *d_in = nullptr;
+    unsigned pkt_dirty = 0;
+    uint8_t *h_head = nullptr; /* pinned: packet head assembled on the host */
+    /* per-step decisions */
+    DSV_FNUM fnum = 0;
+    int gop_start = 0, is_ref = 0, has_ref = 0, forced_intra = 0, quant = 0;
+    unsigned head_bytes = 0;
+};
+
+/* optional destination for a lane's packets: written back to back at `at` instead of into fresh DSV_BUFs */
+struct PktSink {
+    uint8_t *at;
+    size_t room;
+    int overflow;
+};
+
+class EncEngine {
+public:
+    EncEngine(const DSV_META &md, int gop, int pyramid_levels, int lanes);
+    ~EncEngine();
+    /* encode one picture on each of lane_ids[0..n): src[k] is that lane's input, bufs[k] receives 1 or 2
+     * packets (metadata first), nbufs[k] their count */
+    void step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bufs)[2], int *nbufs, PktSink *sinks = nullptr);
+    /* attach a sequence's host state to a lane and forget the lane's references */
+    void bind(int lane, DSV_ENCODER *enc)
+    {
+        lanes_[(size_t) lane].enc = enc;
+        lanes_[(size_t) lane].have_ref = 0;
+    }
+    int lanes() const { return L_; }
+    const CodecGeom &geom() const { return g_; }
+    EngineStats stats;
+    int device = 0;
+
+private:
+    void alloc_lane(EncLane &l);
+    void free_lane(EncLane &l);
+    CodecGeom g_;
+    bool inter_;
+    int levels_;
+    int L_;
+    cudaStream_t st_ = 0;
+    cudaEvent_t ev_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<EncLane> lanes_;
+    StepArena arena_;
+    /* lane-major arrays shared by all lanes so that one copy moves every lane's data */
+    DevMV *d_mv0_ = nullptr, *h_mv0_ = nullptr;  /* level-0 motion fields */
+    uint8_t *d_stab_ = nullptr, *h_stab_ = nullptr;
+    uint8_t *d_misc_ = nullptr, *h_misc_ = nullptr; /* per lane: u64 luma sum, i32 intra count, pad */
+    HzChunk *d_chunks_ = nullptr;
+    HzFrame *d_frames_ = nullptr, *h_frames_ = nullptr;
+};
+
+struct DecLane {
+    DevFrame out[2];
+    int cur = 0, have_ref = 0;
+    int32_t *coef = nullptr, *llx[3] = {nullptr, nullptr, nullptr};
+    HzDecPlaneBufs hz[3];
+    uint8_t *d_pkt = nullptr, *h_pkt = nullptr;
+    /* per-step */
+    int has_ref = 0, is_ref = 0, quant = 0, nplanes = 0, ok = 0;
+    DSV_FNUM fnum = 0;
+    HzPlaneData pd[3];
+};
+
+/* one packet of one lane */
+struct PktRef {
+    const uint8_t *data;     /* host bytes (always needed: the head is parsed on the host) */
+    const uint8_t *dev_data; /* optional device copy of the same bytes (skips the H2D copy) */
+    unsigned len;
+};
+struct OutRef {
+    uint8_t *plane[3];
+    int stride[3];
+    int on_device;
+};
+
+class DecEngine {
+public:
+    DecEngine(const DSV_META &md, int lanes);
+    ~DecEngine();
+    /* decode one PICTURE packet on each of lane_ids[0..n); codes[k] = DSV_DEC_OK / DSV_DEC_ERROR, fnums[k] =
+     * frame number; on OK the picture is written to out[k] */
+    void step(int n, const int *lane_ids, const PktRef *pkts, const OutRef *out, int *codes, DSV_FNUM *fnums);
+    const CodecGeom &geom() const { return g_; }
+    int lanes() const { return L_; }
+    void reset_lane(int lane) { lanes_[(size_t) lane].have_ref = 0; }
+    bool matches(const DSV_META &md) const { return md.width == g_.w && md.height == g_.h && md.subsamp == g_.subsamp; }
+    EngineStats stats;
+    int device = 0;
+
+private:
+    CodecGeom g_;
+    int L_;
+    int max_nblk_;
+    size_t pkt_cap_;
+    cudaStream_t st_ = 0;
+    cudaEvent_t ev_[2] = {nullptr, nullptr};
+    std::vector<DecLane> lanes_;
+    StepArena arena_;
+    DevMV *d_mv_ = nullptr, *h_mv_ = nullptr;
+    uint8_t *d_stab_ = nullptr, *h_stab_ = nullptr;
+};
+
+bool meta_supported(const DSV_META &m);
+void enc_prepare_state(DSV_ENCODER *enc);
+void parse_metadata_packet(const uint8_t *pkt, unsigned len, DSV_META *m);
+
+} // namespace dsv

@@ -507,97 +507,91 @@ void hzdec_plan(HzDecPlan *pl, int cw, int ch)
     pl->max_scan_blk = ceil_div(pl->cap, HZS_BLOCK) + 1;
 }
 
-void hzdec_alloc(HzDecBufs *b, const HzDecPlan pl[3])
+void hzdec_plane_alloc(HzDecPlaneBufs *b, const HzDecPlan &pl)
 {
-    CUDA_CHECK(cudaMalloc(&b->d_jobs, 3 * sizeof(HzDecJob)));
-    b->h_jobs = malloc(3 * sizeof(HzDecJob));
-    for (int p = 0; p < 3; p++) {
-        CUDA_CHECK(cudaMalloc(&b->runs[p], (size_t) (pl[p].cap + 8) * 4));
-        CUDA_CHECK(cudaMalloc(&b->vals[p], (size_t) (pl[p].cap + 8) * 4));
-        CUDA_CHECK(cudaMalloc(&b->cta_sum[p], (size_t) pl[p].max_fsm_cta * sizeof(FsmSum)));
-        CUDA_CHECK(cudaMalloc(&b->cta_entry[p], (size_t) pl[p].max_fsm_cta * 4));
-        CUDA_CHECK(cudaMalloc(&b->blk_sum[p], (size_t) pl[p].max_scan_blk * 8));
-        CUDA_CHECK(cudaMalloc(&b->first_bad[p], 4));
-        b->plan[p] = pl[p];
-    }
+    CUDA_CHECK(cudaMalloc(&b->runs, (size_t) (pl.cap + 8) * 4));
+    CUDA_CHECK(cudaMalloc(&b->vals, (size_t) (pl.cap + 8) * 4));
+    CUDA_CHECK(cudaMalloc(&b->cta_sum, (size_t) pl.max_fsm_cta * sizeof(FsmSum)));
+    CUDA_CHECK(cudaMalloc(&b->cta_entry, (size_t) pl.max_fsm_cta * 4));
+    CUDA_CHECK(cudaMalloc(&b->blk_sum, (size_t) pl.max_scan_blk * 8));
+    CUDA_CHECK(cudaMalloc(&b->first_bad, 4));
+    b->plan = pl;
 }
 
-void hzdec_free(HzDecBufs *b)
+void hzdec_plane_free(HzDecPlaneBufs *b)
 {
-    cudaFree(b->d_jobs);
-    free(b->h_jobs);
-    for (int p = 0; p < 3; p++) {
-        cudaFree(b->runs[p]);
-        cudaFree(b->vals[p]);
-        cudaFree(b->cta_sum[p]);
-        cudaFree(b->cta_entry[p]);
-        cudaFree(b->blk_sum[p]);
-        cudaFree(b->first_bad[p]);
-    }
+    cudaFree(b->runs);
+    cudaFree(b->vals);
+    cudaFree(b->cta_sum);
+    cudaFree(b->cta_entry);
+    cudaFree(b->blk_sum);
+    cudaFree(b->first_bad);
     memset(b, 0, sizeof(*b));
 }
 
-/*
- * Decode the coefficient planes described by `pd` (nplanes <= 3) into their (already zeroed) coef arrays.
- * hz[p] carries geometry/quantisers/coef pointer; pd[p] the plane's bytes inside the device packet.
- */
-void hzdec_launch(HzDecBufs *b, const HzJob *hz, const HzPlaneData *pd, int nplanes, cudaStream_t st)
+/* fill one job record (host memory, hzdec_job_size() bytes) and advance the launch-wide block counters */
+void hzdec_fill_job(void *slot, const HzJob &hz, const HzPlaneData &pd, const HzDecPlaneBufs &b, HzDecDims *dims)
 {
-    HzDecJob *hj = reinterpret_cast<HzDecJob *>(b->h_jobs);
-    int fsm_base = 0, scan_base = 0;
-    for (int p = 0; p < nplanes; p++) {
-        HzDecJob &J = hj[p];
-        memset(&J, 0, sizeof(J));
-        J.hz = hz[p];
-        J.body = pd[p].body;
-        J.plen = pd[p].plen;
-        J.avail = pd[p].avail;
-        J.tok_bit0 = pd[p].tok_bit0;
-        J.nruns = pd[p].nruns;
-        J.first_run = pd[p].first_run;
-        J.dc = pd[p].dc;
-        J.cap = b->plan[p].cap;
-        int n = J.nruns < 0 ? 0 : (J.nruns > J.cap ? J.cap : J.nruns);
-        J.ntok = J.nruns > 0 ? (J.nruns > 0x3fffffff ? 0x7ffffffe : 2 * J.nruns - 1) : 0;
-        J.runs = b->runs[p];
-        J.vals = b->vals[p];
-        J.first_bad = b->first_bad[p];
-        J.cta_sum = reinterpret_cast<FsmSum *>(b->cta_sum[p]);
-        J.cta_entry = b->cta_entry[p];
-        J.blk_sum = b->blk_sum[p];
-        /* bits that can hold usable tokens: up to plen (a token ending at/after plen invalidates the rest) */
-        unsigned long long lim = (unsigned long long) (J.plen < J.avail ? J.plen : J.avail) * 8ull + 64ull;
-        unsigned long long nbits = lim > J.tok_bit0 ? lim - J.tok_bit0 : 0;
-        J.fsm_ncta = J.ntok > 0 ? (int) ((nbits + HZD_CTA_BITS - 1) / HZD_CTA_BITS) : 0;
-        if (J.fsm_ncta > b->plan[p].max_fsm_cta) {
-            J.fsm_ncta = b->plan[p].max_fsm_cta;
-        }
-        J.fsm_cta_base = fsm_base;
-        fsm_base += J.fsm_ncta;
-        J.scan_nblk = ceil_div(n, HZS_BLOCK);
-        J.scan_blk_base = scan_base;
-        scan_base += J.scan_nblk;
+    HzDecJob &J = *reinterpret_cast<HzDecJob *>(slot);
+    memset(&J, 0, sizeof(J));
+    J.hz = hz;
+    J.body = pd.body;
+    J.plen = pd.plen;
+    J.avail = pd.avail;
+    J.tok_bit0 = pd.tok_bit0;
+    J.nruns = pd.nruns;
+    J.first_run = pd.first_run;
+    J.dc = pd.dc;
+    J.cap = b.plan.cap;
+    int n = J.nruns < 0 ? 0 : (J.nruns > J.cap ? J.cap : J.nruns);
+    J.ntok = J.nruns > 0 ? (J.nruns > 0x3fffffff ? 0x7ffffffe : 2 * J.nruns - 1) : 0;
+    J.runs = b.runs;
+    J.vals = b.vals;
+    J.first_bad = b.first_bad;
+    J.cta_sum = reinterpret_cast<FsmSum *>(b.cta_sum);
+    J.cta_entry = b.cta_entry;
+    J.blk_sum = b.blk_sum;
+    /* bits that can hold usable tokens: up to plen (a token ending at/after plen invalidates the rest) */
+    unsigned long long lim = (unsigned long long) (J.plen < J.avail ? J.plen : J.avail) * 8ull + 64ull;
+    unsigned long long nbits = lim > J.tok_bit0 ? lim - J.tok_bit0 : 0;
+    J.fsm_ncta = J.ntok > 0 ? (int) ((nbits + HZD_CTA_BITS - 1) / HZD_CTA_BITS) : 0;
+    if (J.fsm_ncta > b.plan.max_fsm_cta) {
+        J.fsm_ncta = b.plan.max_fsm_cta;
     }
-    CUDA_CHECK(cudaMemcpyAsync(b->d_jobs, hj, (size_t) nplanes * sizeof(HzDecJob), cudaMemcpyHostToDevice, st));
-    const HzDecJob *dj = reinterpret_cast<const HzDecJob *>(b->d_jobs);
-    if (fsm_base > 0) {
-        DSV_LAUNCH(hzdec_fsm_kernel, dim3(fsm_base), dim3(HZD_THREADS), 0, st, dj, nplanes);
+    J.fsm_cta_base = dims->fsm_total;
+    dims->fsm_total += J.fsm_ncta;
+    J.scan_nblk = ceil_div(n, HZS_BLOCK);
+    J.scan_blk_base = dims->scan_total;
+    dims->scan_total += J.scan_nblk;
+    dims->njobs++;
+}
+
+/* d_jobs: device array of dims.njobs job records (planes of every picture in flight), coef planes zeroed */
+void hzdec_launch_jobs(const void *d_jobs, const HzDecDims &dims, cudaStream_t st)
+{
+    const HzDecJob *dj = reinterpret_cast<const HzDecJob *>(d_jobs);
+    const int nj = dims.njobs;
+    if (nj <= 0) {
+        return;
+    }
+    if (dims.fsm_total > 0) {
+        DSV_LAUNCH(hzdec_fsm_kernel, dim3(dims.fsm_total), dim3(HZD_THREADS), 0, st, dj, nj);
         KERNEL_CHECK();
     }
-    DSV_LAUNCH(hzdec_link_kernel, dim3(nplanes), dim3(HZD_THREADS), 0, st, dj);
+    DSV_LAUNCH(hzdec_link_kernel, dim3(nj), dim3(HZD_THREADS), 0, st, dj);
     KERNEL_CHECK();
-    if (fsm_base > 0) {
-        DSV_LAUNCH(hzdec_token_kernel, dim3(fsm_base), dim3(HZD_THREADS), 0, st, dj, nplanes);
+    if (dims.fsm_total > 0) {
+        DSV_LAUNCH(hzdec_token_kernel, dim3(dims.fsm_total), dim3(HZD_THREADS), 0, st, dj, nj);
         KERNEL_CHECK();
     }
-    DSV_LAUNCH(hzdec_dc_kernel, dim3(1), dim3(32), 0, st, dj, nplanes);
+    DSV_LAUNCH(hzdec_dc_kernel, dim3(ceil_div(nj, 32)), dim3(32), 0, st, dj, nj);
     KERNEL_CHECK();
-    if (scan_base > 0) {
-        DSV_LAUNCH(hzdec_runsum_kernel, dim3(scan_base), dim3(HZS_THREADS), 0, st, dj, nplanes);
+    if (dims.scan_total > 0) {
+        DSV_LAUNCH(hzdec_runsum_kernel, dim3(dims.scan_total), dim3(HZS_THREADS), 0, st, dj, nj);
         KERNEL_CHECK();
-        DSV_LAUNCH(hzdec_blkscan_kernel, dim3(nplanes), dim3(1024), 0, st, dj);
+        DSV_LAUNCH(hzdec_blkscan_kernel, dim3(nj), dim3(1024), 0, st, dj);
         KERNEL_CHECK();
-        DSV_LAUNCH(hzdec_scatter_kernel, dim3(scan_base), dim3(HZS_THREADS), 0, st, dj, nplanes);
+        DSV_LAUNCH(hzdec_scatter_kernel, dim3(dims.scan_total), dim3(HZS_THREADS), 0, st, dj, nj);
         KERNEL_CHECK();
     }
 }

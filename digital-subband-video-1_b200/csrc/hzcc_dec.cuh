@@ -19,22 +19,28 @@ struct HzPlaneData {
     int nruns, first_run, dc;
 };
 
-struct HzDecBufs {
-    void *d_jobs;
-    void *h_jobs;
-    int32_t *runs[3], *vals[3];
-    void *cta_sum[3];
-    unsigned *cta_entry[3];
-    unsigned long long *blk_sum[3];
-    unsigned *first_bad[3];
-    HzDecPlan plan[3];
+/* device scratch of one coefficient plane in flight */
+struct HzDecPlaneBufs {
+    int32_t *runs, *vals;
+    void *cta_sum;
+    unsigned *cta_entry;
+    unsigned long long *blk_sum;
+    unsigned *first_bad;
+    HzDecPlan plan;
+};
+
+/* launch-wide totals accumulated by hzdec_fill_job */
+struct HzDecDims {
+    int njobs = 0, fsm_total = 0, scan_total = 0;
 };
 
 /* host: read SEG(DC), nruns and the first run from the plane head (hzcc.c:309-316,485-486) */
 void hzdec_parse_head(const uint8_t *host_body, unsigned avail, unsigned plen, HzPlaneData *pd);
 void hzdec_plan(HzDecPlan *pl, int cw, int ch);
-void hzdec_alloc(HzDecBufs *b, const HzDecPlan pl[3]);
-void hzdec_free(HzDecBufs *b);
-void hzdec_launch(HzDecBufs *b, const HzJob *hz, const HzPlaneData *pd, int nplanes, cudaStream_t st);
+void hzdec_plane_alloc(HzDecPlaneBufs *b, const HzDecPlan &pl);
+void hzdec_plane_free(HzDecPlaneBufs *b);
+size_t hzdec_job_size();
+void hzdec_fill_job(void *slot, const HzJob &hz, const HzPlaneData &pd, const HzDecPlaneBufs &b, HzDecDims *dims);
+void hzdec_launch_jobs(const void *d_jobs, const HzDecDims &dims, cudaStream_t st);
 
 } // namespace dsv

@@ -11,6 +11,8 @@
 #include "hzcc.cuh"
 #include "hzcc_dec.cuh"
 
+#include <vector>
+
 using namespace dsv;
 
 namespace {
@@ -77,6 +79,8 @@ extern "C" int dsvk_inv_sbt(int32_t *coef_io, int cw, int ch, int q, int isP, in
     sbt_fill_quant(&j, q, isP, c, 1, 1);
     j.pix = dp.origin;
     j.pstride = dp.stride;
+    j.opix = dp.origin;
+    j.ostride = dp.stride;
     j.coef = coef.as<int32_t>();
     j.llx = llx.as<int32_t>();
     j.tile_base = 0;
@@ -183,16 +187,19 @@ extern "C" int dsvk_decode_plane(const uint8_t *in, int plen, int cw, int ch, in
     HzPlaneData pd;
     hzdec_parse_head(in, (unsigned) plen, (unsigned) plen, &pd);
     pd.body = body.as<uint8_t>();
-    HzDecPlan pl[3];
-    hzdec_plan(&pl[0], cw, ch);
-    pl[1] = pl[2] = pl[0];
-    pl[1].cap = pl[2].cap = 8; pl[1].max_fsm_cta = pl[2].max_fsm_cta = 1; pl[1].max_scan_blk = pl[2].max_scan_blk = 1;
-    HzDecBufs bufs;
-    hzdec_alloc(&bufs, pl);
-    hzdec_launch(&bufs, &j, &pd, 1, 0);
+    HzDecPlan pl;
+    hzdec_plan(&pl, cw, ch);
+    HzDecPlaneBufs bufs;
+    hzdec_plane_alloc(&bufs, pl);
+    HzDecDims dims;
+    std::vector<uint8_t> slot(hzdec_job_size());
+    hzdec_fill_job(slot.data(), j, pd, bufs, &dims);
+    DevBuf djob(hzdec_job_size());
+    CUDA_CHECK(cudaMemcpy(djob.p, slot.data(), hzdec_job_size(), cudaMemcpyHostToDevice));
+    hzdec_launch_jobs(djob.p, dims, 0);
     CUDA_CHECK(cudaDeviceSynchronize());
     CUDA_CHECK(cudaMemcpy(coef_out, coef.p, (size_t) cw * ch * 4, cudaMemcpyDeviceToHost));
-    hzdec_free(&bufs);
+    hzdec_plane_free(&bufs);
     return 0;
 }
 
@@ -286,8 +293,14 @@ extern "C" int dsvk_hme(const uint8_t *src_yuv, const uint8_t *ref_yuv, int w, i
         CUDA_CHECK(cudaMalloc(&mvf[l], sizeof(DevMV) * (size_t) nblk));
         CUDA_CHECK(cudaMemset(mvf[l], 0, sizeof(DevMV) * (size_t) nblk));
     }
-    DevBuf aux(sizeof(int2) * (size_t) nblk), cnt(sizeof(int));
-    hme_launch(g, sf, rf, mvf, aux.as<int2>(), cnt.as<int>(), 0);
+    DevBuf aux(sizeof(int2) * (size_t) nblk), cnt(sizeof(int)), dargs(sizeof(HmeArgs) * (size_t) (levels + 1));
+    CUDA_CHECK(cudaMemset(cnt.p, 0, sizeof(int)));
+    std::vector<HmeArgs> ha((size_t) levels + 1);
+    for (int l = 0; l <= levels; l++) {
+        hme_fill_args(&ha[(size_t) l], g, l, sf, rf, mvf, aux.as<int2>(), cnt.as<int>());
+    }
+    CUDA_CHECK(cudaMemcpy(dargs.p, ha.data(), sizeof(HmeArgs) * ha.size(), cudaMemcpyHostToDevice));
+    hme_launch(dargs.as<HmeArgs>(), 1, g, 0);
     CUDA_CHECK(cudaDeviceSynchronize());
     int nintra = 0;
     CUDA_CHECK(cudaMemcpy(&nintra, cnt.p, sizeof(int), cudaMemcpyDeviceToHost));
@@ -310,7 +323,11 @@ extern "C" int dsvk_sub_pred(const void *mvs, int w, int h, int subsamp, int blk
     devframe_alloc(&pred, w, h, subsamp);
     DevBuf mv(sizeof(DevMV) * (size_t) g.nbh * g.nbv);
     CUDA_CHECK(cudaMemcpy(mv.p, mvs, sizeof(DevMV) * (size_t) g.nbh * g.nbv, cudaMemcpyHostToDevice));
-    bmc_launch(g, mv.as<DevMV>(), ref, &pred, inp, 1, 0);
+    BmcArgs ba;
+    bmc_fill_args(&ba, g, mv.as<DevMV>(), ref, &pred, inp, inp, 1);
+    DevBuf dargs(sizeof(BmcArgs));
+    CUDA_CHECK(cudaMemcpy(dargs.p, &ba, sizeof(ba), cudaMemcpyHostToDevice));
+    bmc_launch(dargs.as<BmcArgs>(), 1, g.nbh, g.nbv, 0);
     CUDA_CHECK(cudaDeviceSynchronize());
     download_frame(pred, pred_out);
     download_frame(inp, resid_out);
@@ -329,7 +346,11 @@ extern "C" int dsvk_add_pred(const void *mvs, int w, int h, int subsamp, int blk
     upload_frame(&ref, ref_yuv, w, h, subsamp);
     DevBuf mv(sizeof(DevMV) * (size_t) g.nbh * g.nbv);
     CUDA_CHECK(cudaMemcpy(mv.p, mvs, sizeof(DevMV) * (size_t) g.nbh * g.nbv, cudaMemcpyHostToDevice));
-    bmc_launch(g, mv.as<DevMV>(), ref, nullptr, io, 2, 0);
+    BmcArgs ba;
+    bmc_fill_args(&ba, g, mv.as<DevMV>(), ref, nullptr, io, io, 2);
+    DevBuf dargs(sizeof(BmcArgs));
+    CUDA_CHECK(cudaMemcpy(dargs.p, &ba, sizeof(ba), cudaMemcpyHostToDevice));
+    bmc_launch(dargs.as<BmcArgs>(), 1, g.nbh, g.nbv, 0);
     CUDA_CHECK(cudaDeviceSynchronize());
     download_frame(io, out_yuv);
     devframe_free(&io);

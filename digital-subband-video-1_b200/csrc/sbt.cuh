@@ -46,9 +46,12 @@ struct DvGeom {
 };
 
 struct SbtJob {
-    /* pixels: bordered-frame layout, pix -> sample (0,0) */
+    /* pixels: bordered-frame layout, pix -> sample (0,0): forward input */
     uint8_t *pix;
     int pstride;
+    /* inverse output (may be a different frame than the forward input, e.g. the new reference) */
+    uint8_t *opix;
+    int ostride;
     int pw, ph;
     /* coefficients: dense, stride == cw */
     int32_t *coef;
@@ -75,8 +78,11 @@ size_t sbt_llx_elems(int cw, int ch);
 size_t sbt_dv_elems(int cw, int ch);
 
 /* launches; jobs is a DEVICE array, total_tiles = sum of tiles over jobs */
-void sbt_fwd_launch(const SbtJob *d_jobs, int njobs, int total_tiles, size_t lo_smem, cudaStream_t st);
-void sbt_inv_launch(const SbtJob *d_jobs, int njobs, int total_tiles, size_t lo_smem, bool any_intra, cudaStream_t st);
+/* ev0/ev1 (optional) are recorded right before / after the tile kernel, for live roofline timing */
+void sbt_fwd_launch(const SbtJob *d_jobs, int njobs, int total_tiles, size_t lo_smem, cudaStream_t st,
+                    cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
+void sbt_inv_launch(const SbtJob *d_jobs, int njobs, int total_tiles, size_t lo_smem, bool any_intra, cudaStream_t st,
+                    cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 size_t sbt_lo_smem_bytes(int cw, int ch);
 
 /* flat tile index -> job (jobs are sorted by tile_base) */

@@ -300,13 +300,20 @@ __global__ void __launch_bounds__(SBT_LO_THREADS) sbt_fwd_lo_kernel(const SbtJob
     }
 }
 
-void sbt_fwd_launch(const SbtJob *d_jobs, int njobs, int total_tiles, size_t lo_smem, cudaStream_t st)
+void sbt_fwd_launch(const SbtJob *d_jobs, int njobs, int total_tiles, size_t lo_smem, cudaStream_t st,
+                    cudaEvent_t ev0, cudaEvent_t ev1)
 {
     if (lo_smem > 48 * 1024) {
         CUDA_CHECK(cudaFuncSetAttribute(sbt_fwd_lo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) lo_smem));
     }
+    if (ev0) {
+        CUDA_CHECK(cudaEventRecord(ev0, st));
+    }
     DSV_LAUNCH(sbt_fwd_tile_kernel, dim3(total_tiles), dim3(SBT_TILE_THREADS), 0, st, d_jobs, njobs);
     KERNEL_CHECK();
+    if (ev1) {
+        CUDA_CHECK(cudaEventRecord(ev1, st));
+    }
     DSV_LAUNCH(sbt_fwd_lo_kernel, dim3(njobs), dim3(SBT_LO_THREADS), lo_smem, st, d_jobs);
     KERNEL_CHECK();
 }

@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_inv_tile_kernel(const Sb
             if (ly >= rows || ck * 16 >= cols) {
                 continue;
             }
-            uint8_t *dst = J.pix + (size_t) (gy0 + ly) * J.pstride + gx0 + ck * 16;
+            uint8_t *dst = J.opix + (size_t) (gy0 + ly) * J.ostride + gx0 + ck * 16;
             const uint8_t *srcb = outb + ly * SBT_TW + ck * 16;
             if (ck * 16 + 16 <= cols && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
                 *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(srcb);
@@ -366,7 +366,8 @@ __global__ void __launch_bounds__(SBT_LO_THREADS) sbt_inv_lo_kernel(const SbtJob
     }
 }
 
-void sbt_inv_launch(const SbtJob *d_jobs, int njobs, int total_tiles, size_t lo_smem, bool any_intra, cudaStream_t st)
+void sbt_inv_launch(const SbtJob *d_jobs, int njobs, int total_tiles, size_t lo_smem, bool any_intra, cudaStream_t st,
+                    cudaEvent_t ev0, cudaEvent_t ev1)
 {
     size_t tile_smem = inv_tile_smem(any_intra);
     if (lo_smem > 48 * 1024) {
@@ -375,8 +376,14 @@ void sbt_inv_launch(const SbtJob *d_jobs, int njobs, int total_tiles, size_t lo_
     CUDA_CHECK(cudaFuncSetAttribute(sbt_inv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tile_smem));
     DSV_LAUNCH(sbt_inv_lo_kernel, dim3(njobs), dim3(SBT_LO_THREADS), lo_smem, st, d_jobs);
     KERNEL_CHECK();
+    if (ev0) {
+        CUDA_CHECK(cudaEventRecord(ev0, st));
+    }
     DSV_LAUNCH(sbt_inv_tile_kernel, dim3(total_tiles), dim3(SBT_TILE_THREADS), tile_smem, st, d_jobs, njobs);
     KERNEL_CHECK();
+    if (ev1) {
+        CUDA_CHECK(cudaEventRecord(ev1, st));
+    }
 }
 
 } // namespace dsv

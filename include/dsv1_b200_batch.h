@@ -1,0 +1,69 @@
+/*
+ * dsv1_b200_batch.h -- additive throughput API of libdsv1_b200.so (not in the reference).
+ *
+ * The reference API (dsv_enc / dsv_dec, dsv_encoder.h:112-121, dsv_decoder.h:52-59) is synchronous and
+ * one-picture-at-a-time.  Independent sequences (closed GOPs, whole clips) have no data dependence on
+ * each other, so this API runs up to `lanes` of them in LOCK STEP on one GPU: picture t of every lane goes
+ * through each pipeline stage in one batched kernel launch.  The bytes produced for a sequence are exactly
+ * the bytes the per-picture API produces for it (same code path with one lane); tests/test_gpu_batch.py
+ * checks that.  One object per GPU and host thread; objects on different GPUs are independent (no
+ * collective: segments are gathered in order on the host).
+ *
+ * cfg is the 21-int option block of tools/api_harness.c (the fields dsv_main.c:463-489 sets on
+ * DSV_ENCODER / DSV_META): w h subsamp fps_num fps_den aspect_num aspect_den gop quality rc_mode bitrate
+ * do_scd scd_delta intra_pct pyr_levels stable_refresh max_q_step min_quality max_quality min_i_quality hm_nudge
+ */
+#ifndef DSV1_B200_BATCH_H
+#define DSV1_B200_BATCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct DSVB_ENC DSVB_ENC;
+typedef struct DSVB_DEC DSVB_DEC;
+
+#define DSVB_NSTATS 12
+/* stats[]: 0 sbt_fwd_ms 1 sbt_fwd_launches 2 sbt_fwd_bytes 3 sbt_inv_ms 4 sbt_inv_launches 5 sbt_inv_bytes
+ *          6 kernel_launches 7 h2d_bytes 8 d2h_bytes 9 pictures 10 device 11 lanes */
+
+DSVB_ENC *dsvb_enc_create(const int *cfg, int lanes, int device);
+void dsvb_enc_destroy(DSVB_ENC *e);
+/*
+ * Encode nseq sequences of nframes pictures each.  yuv[s]: packed planar pictures of sequence s back to
+ * back, in host memory (on_device = 0; pinned memory avoids a staging copy) or device memory (1).
+ * streams[s] (host, caps[s] bytes) receives the complete .dsv stream (META, PIC..., EOS) of sequence s,
+ * lens[s] its length.  Returns 0, or -1 if a stream buffer is too small.
+ */
+int dsvb_encode(DSVB_ENC *e, int nseq, int nframes, const uint8_t *const *yuv, int on_device,
+                uint8_t *const *streams, const long *caps, long *lens);
+void dsvb_enc_stats(DSVB_ENC *e, double *stats, int reset);
+
+DSVB_DEC *dsvb_dec_create(int lanes, int device);
+void dsvb_dec_destroy(DSVB_DEC *d);
+/*
+ * Decode nseq .dsv streams of one picture format.  streams[s]/lens[s]: host bytes (always required: packet
+ * heads are parsed on the host).  streams_dev (optional, may be NULL): device copies of the same bytes;
+ * when given no packet is copied host->device.  out[s]: packed planar pictures at offset
+ * fnum * frame_bytes, in host (out_on_device = 0) or device (1) memory of out_caps[s] bytes.
+ * frames[s] receives the number of pictures decoded.  Returns 0, or a negative value on a malformed container.
+ */
+int dsvb_decode(DSVB_DEC *d, int nseq, const uint8_t *const *streams, const uint8_t *const *streams_dev,
+                const long *lens, uint8_t *const *out, const long *out_caps, int out_on_device, int *frames);
+void dsvb_dec_stats(DSVB_DEC *d, double *stats, int reset);
+
+/* pinned host memory for inputs / outputs of the calls above */
+void *dsvb_host_alloc(size_t bytes);
+void dsvb_host_free(void *p);
+
+/* SURVEY.md Appendix-C synthetic content, generated on the GPU straight into DEVICE memory (bench / test
+ * utility; bit-identical to oracle/synth.c): n pictures starting at index `start`, packed planar */
+int dsvb_synth_device(int w, int h, int subsamp, int start, int n, int seed, int cut, uint8_t *d_out, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSV1_B200_BATCH_H */

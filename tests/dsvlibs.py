@@ -263,3 +263,84 @@ def fwd_sbt_q(lib, pix, pw, ph, cw, ch, isP, c, q, stable, nbh, nbv):
                             ptr(out, i32p), ptr(dv, i32p))
     assert n >= 0, n
     return out, dv[:n]
+
+
+# -- additive batch API (include/dsv1_b200_batch.h) ---------------------------------------------------
+NSTATS = 12
+STAT_KEYS = ["sbt_fwd_ms", "sbt_fwd_launches", "sbt_fwd_bytes", "sbt_inv_ms", "sbt_inv_launches", "sbt_inv_bytes",
+             "kernel_launches", "h2d_bytes", "d2h_bytes", "pictures", "device", "lanes"]
+
+
+class BatchEncoder:
+    """dsvb_enc_*: `lanes` sequences in lock step on one GPU."""
+
+    def __init__(self, lib, cfg, lanes, device=0):
+        self.lib = lib.lib
+        self.lib.dsvb_enc_create.restype = C.c_void_p
+        self.h = C.c_void_p(self.lib.dsvb_enc_create(cfg, lanes, device))
+        assert self.h.value, "dsvb_enc_create failed"
+        self.cfg = cfg
+
+    def encode_ptrs(self, yuv_ptrs, nframes, on_device, stream_ptrs, caps):
+        n = len(yuv_ptrs)
+        a_y = (C.c_void_p * n)(*yuv_ptrs)
+        a_s = (C.c_void_p * n)(*stream_ptrs)
+        a_c = (C.c_long * n)(*caps)
+        lens = (C.c_long * n)()
+        rc = self.lib.dsvb_encode(self.h, n, nframes, a_y, int(on_device), a_s, a_c, lens)
+        return rc, list(lens)
+
+    def encode(self, seqs, nframes):
+        """seqs: list of uint8 numpy arrays (host). Returns list of bytes."""
+        outs = [np.zeros(len(s) * 2 + 65536, dtype=np.uint8) for s in seqs]
+        rc, lens = self.encode_ptrs([s.ctypes.data for s in seqs], nframes, 0, [o.ctypes.data for o in outs],
+                                    [len(o) for o in outs])
+        assert rc == 0, rc
+        return [o[:n].tobytes() for o, n in zip(outs, lens)]
+
+    def stats(self, reset=False):
+        st = (C.c_double * NSTATS)()
+        self.lib.dsvb_enc_stats(self.h, st, int(reset))
+        return dict(zip(STAT_KEYS, list(st)))
+
+    def close(self):
+        if self.h:
+            self.lib.dsvb_enc_destroy(self.h)
+            self.h = None
+
+
+class BatchDecoder:
+    def __init__(self, lib, lanes, device=0):
+        self.lib = lib.lib
+        self.lib.dsvb_dec_create.restype = C.c_void_p
+        self.h = C.c_void_p(self.lib.dsvb_dec_create(lanes, device))
+        assert self.h.value
+
+    def decode_ptrs(self, stream_ptrs, stream_dev_ptrs, lens, out_ptrs, out_caps, out_on_device):
+        n = len(stream_ptrs)
+        a_s = (C.c_void_p * n)(*stream_ptrs)
+        a_d = (C.c_void_p * n)(*stream_dev_ptrs) if stream_dev_ptrs else None
+        a_l = (C.c_long * n)(*lens)
+        a_o = (C.c_void_p * n)(*out_ptrs)
+        a_c = (C.c_long * n)(*out_caps)
+        fr = (C.c_int * n)()
+        rc = self.lib.dsvb_decode(self.h, n, a_s, a_d, a_l, a_o, a_c, int(out_on_device), fr)
+        return rc, list(fr)
+
+    def decode(self, streams, frame_bytes, nframes):
+        bufs = [np.frombuffer(s, dtype=np.uint8) for s in streams]
+        outs = [np.zeros(frame_bytes * nframes, dtype=np.uint8) for _ in streams]
+        rc, fr = self.decode_ptrs([b.ctypes.data for b in bufs], None, [len(b) for b in bufs],
+                                  [o.ctypes.data for o in outs], [len(o) for o in outs], 0)
+        assert rc == 0, rc
+        return outs, fr
+
+    def stats(self, reset=False):
+        st = (C.c_double * NSTATS)()
+        self.lib.dsvb_dec_stats(self.h, st, int(reset))
+        return dict(zip(STAT_KEYS, list(st)))
+
+    def close(self):
+        if self.h:
+            self.lib.dsvb_dec_destroy(self.h)
+            self.h = None

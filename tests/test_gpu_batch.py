@@ -1,0 +1,77 @@
+"""Additive batch API (dsvb_*, include/dsv1_b200_batch.h): lanes in lock step produce exactly the bytes the
+per-picture API produces; device-resident inputs/outputs; the CUDA synthetic-content generator equals
+oracle/synth.c."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import dsvlibs as L
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "streams.json")))
+
+
+def test_synth_device_matches_oracle(gpu):
+    import torch
+    for (w, h, fmt, n, seed, cut, start) in [(352, 288, "420", 3, 1, 2, 0), (176, 144, "444", 2, 4, 0, 13),
+                                             (176, 144, "411", 2, 6, 0, 1), (1920, 1080, "420", 1, 2, 0, 5)]:
+        sub = L.SUBSAMP[fmt]
+        fb = L.frame_bytes(w, h, sub)
+        d = torch.zeros(fb * n, dtype=torch.uint8, device="cuda")
+        gpu.lib.dsvb_synth_device(w, h, sub, start, n, seed, cut, C.c_void_p(d.data_ptr()), 0)
+        assert np.array_equal(d.cpu().numpy(), L.synth_sequence(w, h, fmt, n, seed, cut, start=start))
+
+
+@pytest.mark.parametrize("case", [(352, 288, "420", 13, 12, 5, 3), (176, 144, "444", 9, 4, 7, 4), (640, 360, "420", 6, 0, 3, 2)])
+def test_batch_equals_per_picture_api(gpu, case):
+    w, h, fmt, n, gop, nseq, lanes = case
+    sub = L.SUBSAMP[fmt]
+    cfg = L.make_cfg(w, h, fmt, gop=gop)
+    seqs = [L.synth_sequence(w, h, fmt, n, 40 + s, 7 if s == 1 else 0) for s in range(nseq)]
+    want = [gpu.encode_sequence(cfg, s, n)[0] for s in seqs]
+    be = L.BatchEncoder(gpu, cfg, lanes)
+    got = be.encode(seqs, n)
+    be.close()
+    assert got == want
+    bd = L.BatchDecoder(gpu, lanes)
+    outs, fr = bd.decode(want, L.frame_bytes(w, h, sub), n)
+    bd.close()
+    assert fr == [n] * nseq
+    for s, o in zip(want, outs):
+        nf, d, _, _ = gpu.decode_stream(s, w, h, sub, n)
+        assert nf == n and np.array_equal(d, o)
+
+
+def test_batch_hd_golden_device_resident(gpu):
+    """HD gop12 golden vector through the batch API with device-resident pictures in and out."""
+    import torch
+    g = GOLD["hd_gop12"]
+    w, h, fmt, n = g["w"], g["h"], g["fmt"], g["frames"]
+    sub = L.SUBSAMP[fmt]
+    fb = L.frame_bytes(w, h, sub)
+    d_yuv = torch.zeros(fb * n, dtype=torch.uint8, device="cuda")
+    gpu.lib.dsvb_synth_device(w, h, sub, 0, n, g["seed"], g["cut"], C.c_void_p(d_yuv.data_ptr()), 0)
+    cfg = L.make_cfg(w, h, fmt, gop=g["gop"], qp=g["qp"])
+    be = L.BatchEncoder(gpu, cfg, 2)
+    out = np.zeros(2 * (16 << 20), dtype=np.uint8)
+    ptrs = [out.ctypes.data, out.ctypes.data + (16 << 20)]
+    rc, lens = be.encode_ptrs([d_yuv.data_ptr(), d_yuv.data_ptr()], n, 1, ptrs, [16 << 20] * 2)
+    be.close()
+    assert rc == 0 and lens[0] == lens[1] == g["dsv_len"]
+    s0 = out[:lens[0]].tobytes()
+    assert hashlib.md5(s0).hexdigest() == g["dsv_md5"]
+    assert out[16 << 20:(16 << 20) + lens[1]].tobytes() == s0
+    d_stream = torch.from_numpy(out[:lens[0]].copy()).cuda()
+    d_out = torch.zeros(fb * n, dtype=torch.uint8, device="cuda")
+    bd = L.BatchDecoder(gpu, 2)
+    rc, fr = bd.decode_ptrs([ptrs[0]], [d_stream.data_ptr()], [lens[0]], [d_out.data_ptr()], [fb * n], 1)
+    st = bd.stats()
+    bd.close()
+    assert rc == 0 and fr == [n]
+    assert hashlib.md5(d_out.cpu().numpy().tobytes()).hexdigest() == g["dec_md5"]
+    assert st["h2d_bytes"] == 0 and st["d2h_bytes"] == 0   # nothing crossed PCIe for the pictures or the packets
