@@ -288,7 +288,12 @@ __global__ void __launch_bounds__(HZD_THREADS) hzdec_token_kernel(const HzDecJob
 
     unsigned long long pos = pos0;
     const unsigned long long end = pos0 + HZD_WORD_BITS;
-    const unsigned long long hard_end = (unsigned long long) J.avail * 8ull + 64ull;
+    /* a well-formed token (32-bit value) is at most 66 bits long; anything longer is corrupt data, and letting
+     * every thread chase a never-ending token to the end of the packet would be quadratic work */
+    unsigned long long hard_end = (unsigned long long) J.avail * 8ull + 64ull;
+    if (hard_end > end + 160ull) {
+        hard_end = end + 160ull;
+    }
     bool own = false;       /* currently inside a token this thread owns */
     unsigned v = 1;
     unsigned dummy = 0;
