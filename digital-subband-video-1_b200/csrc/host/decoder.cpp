@@ -155,8 +155,7 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
     PlaneRef *ext = arena_.push_n<PlaneRef>((size_t) 3 * n, &d_ext);
     PackItem *pack = arena_.push_n<PackItem>((size_t) 3 * n, &d_pack);
     HzDecDims dims;
-    int n_sj = 0, n_p = 0, n_ext = 0, n_pack = 0, tile_base = 0;
-    bool any_intra = false;
+    int n_sj = 0, n_p = 0, n_ext = 0, n_pack = 0;
     int blk_w = 0, blk_h = 0, nbh = 0, nbv = 0;
 
     for (int k = 0; k < n; k++) {
@@ -249,7 +248,6 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
 
         const DevFrame &cur = l.out[l.cur];
         const int isP = l.has_ref;
-        any_intra |= !isP;
         for (int p = 0; p < 3; p++) {
             SbtJob &s = sj[n_sj];
             memset(&s, 0, sizeof(s));
@@ -260,8 +258,6 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
             s.coef = l.coef + g.coef_off[p];
             s.llx = l.llx[p];
             s.stable = d_stab_ + (size_t) li * max_nblk_;
-            s.tile_base = tile_base;
-            tile_base += s.tiles_x * s.tiles_y;
             if (p < l.nplanes) {
                 HzJob h;
                 memset(&h, 0, sizeof(h));
@@ -298,17 +294,18 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
         CUDA_CHECK(cudaStreamSynchronize(st));
         return;
     }
+    const SbtDims sdims = sbt_assign_tiles(sj, n_sj);
     arena_.upload(st);
     CUDA_CHECK(cudaMemcpyAsync(d_stab_, h_stab_, (size_t) max_nblk_ * L_, cudaMemcpyHostToDevice, st));
     if (n_p) {
         CUDA_CHECK(cudaMemcpyAsync(d_mv_, h_mv_, sizeof(DevMV) * (size_t) max_nblk_ * L_, cudaMemcpyHostToDevice, st));
     }
     hzdec_launch_jobs(d_hzj, dims, st);
-    sbt_inv_launch(d_sj, n_sj, tile_base, g_.lo_smem, any_intra, st, ev_[0], ev_[1]);
+    sbt_inv_launch(d_sj, sdims, g_.lo_smem, st, ev_[0], ev_[1]);
     bmc_launch(d_bmc, n_p, nbh, nbv, st);
     extend_launch(d_ext, n_ext, g_.w, g_.h, st);
     pack_launch(d_pack, n_pack, g_.w, g_.h, st);
-    stats.kernel_launches += 9 + (n_p ? 1 : 0) + (n_ext ? 1 : 0) + (n_pack ? 1 : 0);
+    stats.kernel_launches += 10 + (n_p ? 1 : 0) + (n_ext ? 1 : 0) + (n_pack ? 1 : 0);
     for (int k = 0; k < n; k++) {
         DecLane &l = lanes_[(size_t) lane_ids[k]];
         if (!l.ok) {

@@ -663,13 +663,11 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     const int n_i_ref = n_ref - n_p;
     ReconItem *rec = n_p ? arena_.push_n<ReconItem>((size_t) 3 * n_p, &d_rec) : nullptr;
     PlaneRef *ext = n_i_ref > 0 ? arena_.push_n<PlaneRef>((size_t) 3 * n_i_ref, &d_ext) : nullptr;
-    int tile_base = 0, qp = 0, qi = 0;
-    bool any_intra = false;
+    int qp = 0, qi = 0;
     for (int k = 0; k < n; k++) {
         const int li = lane_ids[k];
         EncLane &l = lanes_[(size_t) li];
         const int isP = l.has_ref;
-        any_intra |= !isP;
         const DevFrame &fwd_in = isP ? l.xf : (inter_ ? l.pad[l.cur] : l.xf);
         const DevFrame &inv_out = isP ? l.xf : (inter_ ? l.recon[l.cur] : l.xf);
         if (isP) {
@@ -692,8 +690,6 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
             s.dv = l.dv[p];
             s.stable = d_stab_ + (size_t) li * g.nblk;
             s.do_quant = 1;
-            s.tile_base = tile_base;
-            tile_base += s.tiles_x * s.tiles_y;
 
             HzJob &h = hj[3 * k + p];
             memset(&h, 0, sizeof(h));
@@ -734,6 +730,7 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
             qi++;
         }
     }
+    const SbtDims sdims = sbt_assign_tiles(sj, 3 * n);
     arena_.upload(st);
     CUDA_CHECK(cudaMemcpyAsync(d_stab_, h_stab_, (size_t) g.nblk * L_, cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemcpyAsync(d_hf, h_frames_, sizeof(HzFrame) * (size_t) n, cudaMemcpyHostToDevice, st));
@@ -741,17 +738,17 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         bmc_launch(d_bmc, n_p, g.nbh, g.nbv, st);
         stats.kernel_launches += 1;
     }
-    sbt_fwd_launch(d_sj, 3 * n, tile_base, g.lo_smem, st, ev_[0], ev_[1]);
+    sbt_fwd_launch(d_sj, sdims, g.lo_smem, st, ev_[0], ev_[1]);
     hzcc_enc_launch(d_hj, 3 * n, d_chunks_, n * g.total_chunks, d_hf, n, st);
-    stats.kernel_launches += 5;
+    stats.kernel_launches += 6;
     CUDA_CHECK(cudaMemcpyAsync(h_frames_, d_hf, sizeof(HzFrame) * (size_t) n, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaEventRecord(ev_[4], st));
     if (n_ref) {
         /* closed loop: reconstruct exactly what the decoder will (dsv_encoder.c:525,662-674) */
-        sbt_inv_launch(d_sj, 3 * n, tile_base, g.lo_smem, any_intra, st, ev_[2], ev_[3]);
+        sbt_inv_launch(d_sj, sdims, g.lo_smem, st, ev_[2], ev_[3]);
         recon_launch(d_rec, 3 * n_p, g.w, g.h, st);
         extend_launch(d_ext, 3 * n_i_ref, g.w, g.h, st);
-        stats.kernel_launches += 2 + (n_p ? 1 : 0) + (n_i_ref > 0 ? 1 : 0);
+        stats.kernel_launches += 3 + (n_p ? 1 : 0) + (n_i_ref > 0 ? 1 : 0);
     }
     CUDA_CHECK(cudaEventSynchronize(ev_[4])); /* packet sizes are known; reconstruction keeps running */
 

@@ -57,9 +57,9 @@ extern "C" int dsvk_fwd_sbt(const uint8_t *pix, int stride, int pw, int ph, int 
     j.llx = llx.as<int32_t>();
     j.dv = dv.as<int32_t>();
     j.do_quant = 0;
-    j.tile_base = 0;
+    const SbtDims dims = sbt_assign_tiles(&j, 1);
     CUDA_CHECK(cudaMemcpy(jobs.p, &j, sizeof(j), cudaMemcpyHostToDevice));
-    sbt_fwd_launch(jobs.as<SbtJob>(), 1, j.tiles_x * j.tiles_y, sbt_lo_smem_bytes(cw, ch), 0);
+    sbt_fwd_launch(jobs.as<SbtJob>(), dims, sbt_lo_smem_bytes(cw, ch), 0);
     CUDA_CHECK(cudaDeviceSynchronize());
     CUDA_CHECK(cudaMemcpy(coef_out, coef.p, (size_t) cw * ch * 4, cudaMemcpyDeviceToHost));
     return 0;
@@ -83,9 +83,9 @@ extern "C" int dsvk_inv_sbt(int32_t *coef_io, int cw, int ch, int q, int isP, in
     j.ostride = dp.stride;
     j.coef = coef.as<int32_t>();
     j.llx = llx.as<int32_t>();
-    j.tile_base = 0;
+    const SbtDims dims = sbt_assign_tiles(&j, 1);
     CUDA_CHECK(cudaMemcpy(jobs.p, &j, sizeof(j), cudaMemcpyHostToDevice));
-    sbt_inv_launch(jobs.as<SbtJob>(), 1, j.tiles_x * j.tiles_y, sbt_lo_smem_bytes(cw, ch), !isP, 0);
+    sbt_inv_launch(jobs.as<SbtJob>(), dims, sbt_lo_smem_bytes(cw, ch), 0);
     CUDA_CHECK(cudaDeviceSynchronize());
     CUDA_CHECK(cudaMemcpy2D(pix_out, stride, dp.origin, dp.stride, pw, ph, cudaMemcpyDeviceToHost));
     return 0;
@@ -116,8 +116,9 @@ extern "C" int dsvk_fwd_sbt_q(const uint8_t *pix, int stride, int pw, int ph, in
     j.dv = dv.as<int32_t>();
     j.stable = stab.as<uint8_t>();
     j.do_quant = 1;
+    const SbtDims dims = sbt_assign_tiles(&j, 1);
     CUDA_CHECK(cudaMemcpy(jobs.p, &j, sizeof(j), cudaMemcpyHostToDevice));
-    sbt_fwd_launch(jobs.as<SbtJob>(), 1, j.tiles_x * j.tiles_y, sbt_lo_smem_bytes(cw, ch), 0);
+    sbt_fwd_launch(jobs.as<SbtJob>(), dims, sbt_lo_smem_bytes(cw, ch), 0);
     CUDA_CHECK(cudaDeviceSynchronize());
     CUDA_CHECK(cudaMemcpy(coef_out, coef.p, (size_t) cw * ch * 4, cudaMemcpyDeviceToHost));
     if (dv_out) {

@@ -5,10 +5,12 @@
  * memory so that planes x frames x sequences are batched into one grid (a single
  * 1080p plane is only a few microseconds of HBM traffic).
  *
- * Decomposition (reference: sbt.c:617-714): levels 1..nlt (nlt = min(5, levels))
- * are computed per 128x64-sample tile entirely in shared memory ("tile" kernels);
- * the remaining levels operate on the small LL_nlt array in one CTA ("lo" kernels).
- * The two kernels hand LL_nlt over through the job's `llx` scratch array.
+ * Decomposition (reference: sbt.c:617-714), three kernels per direction:
+ *   "tile" (hi)  levels 1-2 per 128x64-sample tile: the streaming part (94 % of the coefficients), no
+ *                serial tail -- every thread has work at both levels;
+ *   "mid"        levels 3..nlt (nlt = min(5, levels)) per 128x64 block of LL_2;
+ *   "lo"         the remaining levels on the small LL_nlt array, one CTA per plane.
+ * They hand LL_2 and LL_nlt over through the job's `llx` scratch array (LL_nlt first, LL_2 at ll2_off).
  */
 #pragma once
 #include "common.cuh"
@@ -17,7 +19,8 @@ namespace dsv {
 
 #define SBT_TW 128 /* tile width  in samples */
 #define SBT_TH 64  /* tile height in samples */
-#define SBT_NLT 5  /* max levels done inside a tile (128x64 -> 4x2 LL coefficients) */
+#define SBT_NLT 5  /* levels done before the lo kernel */
+#define SBT_HI 2   /* levels done by the streaming tile kernel */
 #define SBT_TILE_THREADS 256
 #define SBT_LO_THREADS 1024
 #define SBT_STAB_SMEM 2048
@@ -56,7 +59,8 @@ struct SbtJob {
     /* coefficients: dense, stride == cw */
     int32_t *coef;
     int cw, ch;
-    int32_t *llx; /* LL_nlt hand-over scratch, wo_nlt * ho_nlt ints */
+    int32_t *llx; /* hand-over scratch: LL_nlt (wo_nlt * ho_nlt ints), then LL_2 at ll2_off */
+    int ll2_off;
     int32_t *dv;  /* first-visit symbols of double-visited positions (encoder) / values (decoder) */
     const uint8_t *stable;
     int lvls, nlt;
@@ -65,6 +69,7 @@ struct SbtJob {
     int quant;    /* frame quant (for the inverse's nudge bounds) */
     int do_quant; /* forward: fuse quantise+dequantise into the epilogue */
     int tiles_x, tiles_y, tile_base;
+    int mtiles_x, mtiles_y, mtile_base; /* mid kernel: 128x64 blocks of LL_2 */
     int hqp[16];  /* inverse: nudge bound per level (sbt.c:677-696), index = level */
     PlaneQ pq;
     DvGeom dg;
@@ -78,20 +83,28 @@ size_t sbt_llx_elems(int cw, int ch);
 size_t sbt_dv_elems(int cw, int ch);
 
 /* launches; jobs is a DEVICE array, total_tiles = sum of tiles over jobs */
+/* grid sizes of one launch over an array of jobs */
+struct SbtDims {
+    int njobs = 0, tiles = 0, mtiles = 0;
+    bool any_intra = false;
+};
+/* assigns tile_base / mtile_base of jobs[0..n) (host copies, in launch order) and returns the totals */
+SbtDims sbt_assign_tiles(SbtJob *jobs, int n);
+
 /* ev0/ev1 (optional) are recorded right before / after the tile kernel, for live roofline timing */
-void sbt_fwd_launch(const SbtJob *d_jobs, int njobs, int total_tiles, size_t lo_smem, cudaStream_t st,
+void sbt_fwd_launch(const SbtJob *d_jobs, const SbtDims &dims, size_t lo_smem, cudaStream_t st,
                     cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
-void sbt_inv_launch(const SbtJob *d_jobs, int njobs, int total_tiles, size_t lo_smem, bool any_intra, cudaStream_t st,
+void sbt_inv_launch(const SbtJob *d_jobs, const SbtDims &dims, size_t lo_smem, cudaStream_t st,
                     cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 size_t sbt_lo_smem_bytes(int cw, int ch);
 
-/* flat tile index -> job (jobs are sorted by tile_base) */
-DSV_D int sbt_find_job(const SbtJob *jobs, int njobs, int tile)
+/* flat tile index -> job (jobs are sorted by tile_base / mtile_base) */
+template <bool MID> DSV_D int sbt_find_job(const SbtJob *jobs, int njobs, int tile)
 {
     int lo = 0, hi = njobs - 1;
     while (lo < hi) {
         int mid = (lo + hi + 1) >> 1;
-        if (jobs[mid].tile_base <= tile) {
+        if ((MID ? jobs[mid].mtile_base : jobs[mid].tile_base) <= tile) {
             lo = mid;
         } else {
             hi = mid - 1;

@@ -5,10 +5,26 @@ namespace dsv {
 
 int sbt_num_levels(int cw, int ch) { return lb2((unsigned) imax(cw, ch)); } /* sbt.c:617-628 */
 
-size_t sbt_llx_elems(int cw, int ch)
+static size_t llx_head_elems(int cw, int ch)
 {
     int nlt = imin(SBT_NLT, sbt_num_levels(cw, ch));
-    return (size_t) sbt_wo(cw, nlt) * sbt_wo(ch, nlt);
+    return ((size_t) sbt_wo(cw, nlt) * sbt_wo(ch, nlt) + 3) & ~(size_t) 3;
+}
+
+size_t sbt_llx_elems(int cw, int ch) { return llx_head_elems(cw, ch) + (size_t) sbt_wo(cw, SBT_HI) * sbt_wo(ch, SBT_HI) + 4; }
+
+SbtDims sbt_assign_tiles(SbtJob *jobs, int n)
+{
+    SbtDims d;
+    d.njobs = n;
+    for (int i = 0; i < n; i++) {
+        jobs[i].tile_base = d.tiles;
+        d.tiles += jobs[i].tiles_x * jobs[i].tiles_y;
+        jobs[i].mtile_base = d.mtiles;
+        d.mtiles += jobs[i].mtiles_x * jobs[i].mtiles_y;
+        d.any_intra |= !jobs[i].isP;
+    }
+    return d;
 }
 
 size_t sbt_dv_elems(int cw, int ch) { return (size_t) 2 * (cw + ch) + 16; }
@@ -34,6 +50,9 @@ void sbt_fill_geometry(SbtJob *j, int pw, int ph, int cw, int ch, int isP, int p
     j->nlt = imin(SBT_NLT, j->lvls);
     j->tiles_x = ceil_div(cw, SBT_TW);
     j->tiles_y = ceil_div(ch, SBT_TH);
+    j->mtiles_x = ceil_div(sbt_wo(cw, SBT_HI), SBT_TW);
+    j->mtiles_y = ceil_div(sbt_wo(ch, SBT_HI), SBT_TH);
+    j->ll2_off = (int) llx_head_elems(cw, ch);
 
     /* double-visited positions: level l (2,1) elements that level l+1's hzcc scan also covers */
     DvGeom &g = j->dg;

@@ -49,44 +49,214 @@ struct Win {
     int qa, qb; /* pair range y */
 };
 
+/* window storage for the LL arrays 1..5 levels above the kernel's base level: 66x34, 36x20, 20x12, 12x8, 8x6 */
 #define INV_W1 66
 #define INV_H1 34
 #define INV_LL1_ELEMS (INV_W1 * INV_H1)
-/* window storage for LL_1..LL_5: 66x34, 36x20, 20x12, 12x8, 8x6 */
 #define INV_OFF2 (INV_LL1_ELEMS)
 #define INV_OFF3 (INV_OFF2 + 36 * 20)
 #define INV_OFF4 (INV_OFF3 + 20 * 12)
 #define INV_OFF5 (INV_OFF4 + 12 * 8)
 #define INV_WIN_ELEMS (INV_OFF5 + 8 * 6)
-/* I frames: three more level-1 band windows + the column-pass output (2 x 66 columns x 64 rows) */
-#define INV_I_EXTRA (3 * INV_LL1_ELEMS + 2 * INV_W1 * SBT_TH)
-#define INV_OUT_BYTES (SBT_TW * SBT_TH)
+/* I frames: column-pass output of the inverse B4T, [64 rows][low 68 | high 68] */
+#define INV_VSTRIDE 136
+#define INV_I_EXTRA (SBT_TH * INV_VSTRIDE)
 
 static size_t inv_tile_smem(bool anyI)
 {
-    return (size_t) (INV_WIN_ELEMS + (anyI ? INV_I_EXTRA : 0)) * sizeof(int32_t) + INV_OUT_BYTES;
+    return (size_t) (INV_OFF3 + (anyI ? INV_I_EXTRA : 0)) * sizeof(int32_t);
 }
 
+DSV_D unsigned pack4_u8(int a, int b, int c, int d)
+{
+    return (unsigned) clamp_u8(a + 128) | ((unsigned) clamp_u8(b + 128) << 8) | ((unsigned) clamp_u8(c + 128) << 16) |
+           ((unsigned) clamp_u8(d + 128) << 24);
+}
+
+/* store 8 reconstructed samples of one output row (sbc2int, sbt.c:594-614): only pw x ph is written */
+DSV_D void store_row8(const SbtJob &J, int oy, int ox, const int *v)
+{
+    if (oy >= J.ph || ox >= J.pw) {
+        return;
+    }
+    uint8_t *dst = J.opix + (size_t) oy * J.ostride + ox;
+    if (ox + 8 <= J.pw && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+        *reinterpret_cast<uint2 *>(dst) = make_uint2(pack4_u8(v[0], v[1], v[2], v[3]), pack4_u8(v[4], v[5], v[6], v[7]));
+    } else {
+        for (int e = 0; e < 8 && ox + e < J.pw; e++) {
+            dst[e] = clamp_u8(v[e] + 128);
+        }
+    }
+}
+
+template <bool MID> DSV_D void inv_load_job(SbtJob *sJ, const SbtJob *jobs, int njobs)
+{
+    const int job = sbt_find_job<MID>(jobs, njobs, (int) blockIdx.x);
+    const int *src = reinterpret_cast<const int *>(&jobs[job]);
+    int *dst = reinterpret_cast<int *>(sJ);
+    for (int i = threadIdx.x; i < (int) (sizeof(SbtJob) / sizeof(int)); i += blockDim.x) {
+        dst[i] = src[i];
+    }
+    __syncthreads();
+}
+
+/* window geometry, top-down from the tile of level-`base` outputs (base 0 = samples) to level `top` */
+DSV_D void inv_windows(const SbtJob &J, Win *W, int base, int top, int gx0, int gy0)
+{
+    const bool isI = !J.isP, filtered = J.plane == 0;
+    int a = gx0, b = imin(gx0 + SBT_TW, base ? sbt_wo(J.cw, base) : J.cw);
+    int ha = gy0, hb = imin(gy0 + SBT_TH, base ? sbt_wo(J.ch, base) : J.ch);
+    W[base].a = a; W[base].b = b; W[base].ha = ha; W[base].hb = hb;
+    for (int l = base + 1; l <= top; l++) {
+        int halo = (l == 1 && isI) ? 1 : (filtered ? 1 : 0);
+        int wo = sbt_wo(J.cw, l), ho = sbt_wo(J.ch, l);
+        Win w;
+        w.pa = a >> 1; w.pb = ((b - 1) >> 1) + 1;
+        w.qa = ha >> 1; w.qb = ((hb - 1) >> 1) + 1;
+        w.a = imax(w.pa - halo, 0); w.b = imin(w.pb + halo, wo);
+        w.ha = imax(w.qa - halo, 0); w.hb = imin(w.qb + halo, ho);
+        W[l] = w;
+        a = w.a; b = w.b; ha = w.ha; hb = w.hb;
+    }
+}
+
+/*
+ * One inverse Haar level, one pair per thread (inv / inv_simple, sbt.c:352-574): LL window `src` of level lvl
+ * -> values of level lvl-1, written either into the next window (dst_win, geometry o) or, when dst_plane is
+ * given, into a dense global LL plane of row pitch dst_pitch restricted to the rectangle o.
+ */
+DSV_D void inv_haar_level(const SbtJob &J, int lvl, const Win &w, const Win &o, const int32_t *src, int32_t *dst_win,
+                          int32_t *dst_plane, int dst_pitch)
+{
+    const int cw = J.cw, ch = J.ch;
+    const bool filtered = J.plane == 0;
+    const int ww = w.b - w.a;
+    const int oww = o.b - o.a;
+    const int ws = sbt_ws(cw, lvl), hs = sbt_ws(ch, lvl), wo = sbt_wo(cw, lvl), ho = sbt_wo(ch, lvl);
+    const bool scale = lvl > 1; /* LL scaled by 5/4 at every level this function is used for (sbt.c:20-22) */
+    const int bound = J.hqp[lvl];
+    const int npx = w.pb - w.pa, npy = w.qb - w.qa;
+    for (int task = threadIdx.x; task < npx * npy; task += blockDim.x) {
+        const int jx = w.pa + task % npx, jy = w.qa + task / npx;
+        const bool col2 = 2 * jx + 1 < ws, row2 = 2 * jy + 1 < hs;
+        const int32_t *pc = src + (jy - w.ha) * ww + (jx - w.a);
+        int LL = scale ? ll_up(pc[0]) : pc[0];
+        int v00, v01 = 0, v10 = 0, v11 = 0;
+        if (col2 && row2) {
+            int LH = J.coef[(size_t) jy * cw + wo + jx];
+            int HL = J.coef[(size_t) (ho + jy) * cw + jx];
+            int HH = J.coef[(size_t) (ho + jy) * cw + wo + jx];
+            if (filtered) {
+                if (jx > 0) {
+                    int lp = pc[-1];
+                    int ln = (jx + 1 < wo) ? pc[1] : J.coef[(size_t) jy * cw + wo];
+                    if (scale) {
+                        lp = ll_up(lp);
+                        ln = ll_up(ln);
+                    }
+                    LH = smooth_nudge(LL, lp, ln, LH, bound);
+                }
+                if (jy > 0) {
+                    int lp = pc[-ww];
+                    int ln = (jy + 1 < ho) ? pc[ww] : J.coef[(size_t) ho * cw + jx];
+                    if (scale) {
+                        lp = ll_up(lp);
+                        ln = ll_up(ln);
+                    }
+                    HL = smooth_nudge(LL, lp, ln, HL, bound);
+                }
+            }
+            v00 = div4_trunc(LL + LH + HL + HH);
+            v01 = div4_trunc(LL - LH + HL - HH);
+            v10 = div4_trunc(LL + LH - HL - HH);
+            v11 = div4_trunc(LL - LH - HL + HH);
+        } else if (row2) {
+            int HL = J.coef[(size_t) (ho + jy) * cw + jx];
+            v00 = div4_trunc(LL + HL);
+            v10 = div4_trunc(LL - HL);
+        } else if (col2) {
+            int LH = J.coef[(size_t) jy * cw + wo + jx];
+            v00 = div4_trunc(LL + LH);
+            v01 = div4_trunc(LL - LH);
+        } else {
+            v00 = div4_trunc(LL);
+        }
+        const int ox = 2 * jx, oy = 2 * jy;
+        const bool x0ok = ox >= o.a && ox < o.b, x1ok = col2 && ox + 1 >= o.a && ox + 1 < o.b;
+        const bool y0ok = oy >= o.ha && oy < o.hb, y1ok = row2 && oy + 1 >= o.ha && oy + 1 < o.hb;
+        if (dst_plane) {
+            if (y0ok) {
+                if (x0ok) dst_plane[(size_t) oy * dst_pitch + ox] = v00;
+                if (x1ok) dst_plane[(size_t) oy * dst_pitch + ox + 1] = v01;
+            }
+            if (y1ok) {
+                if (x0ok) dst_plane[(size_t) (oy + 1) * dst_pitch + ox] = v10;
+                if (x1ok) dst_plane[(size_t) (oy + 1) * dst_pitch + ox + 1] = v11;
+            }
+        } else {
+            if (y0ok) {
+                if (x0ok) dst_win[(oy - o.ha) * oww + (ox - o.a)] = v00;
+                if (x1ok) dst_win[(oy - o.ha) * oww + (ox + 1 - o.a)] = v01;
+            }
+            if (y1ok) {
+                if (x0ok) dst_win[(oy + 1 - o.ha) * oww + (ox - o.a)] = v10;
+                if (x1ok) dst_win[(oy + 1 - o.ha) * oww + (ox + 1 - o.a)] = v11;
+            }
+        }
+    }
+}
+
+/*
+ * Mid kernel: levels nlt..3 for one 128x64 block of LL_2.  LL_nlt window from the lo kernel's hand-over array,
+ * result into the dense LL_2 hand-over plane.
+ */
+__global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_inv_mid_kernel(const SbtJob *jobs, int njobs)
+{
+    __shared__ int32_t sm[INV_WIN_ELEMS];
+    __shared__ SbtJob J;
+    __shared__ Win W[SBT_NLT + 1];
+    const int tid = threadIdx.x;
+    inv_load_job<true>(&J, jobs, njobs);
+    const int t = (int) blockIdx.x - J.mtile_base;
+    const int tx = t % J.mtiles_x, ty = t / J.mtiles_x;
+    const int nlt = J.nlt;
+    int32_t *win[SBT_NLT + 1];
+    win[SBT_HI + 1] = sm;
+    win[SBT_HI + 2] = sm + INV_OFF2;
+    win[SBT_HI + 3] = sm + INV_OFF3;
+    if (tid == 0) {
+        inv_windows(J, W, SBT_HI, nlt, tx * SBT_TW, ty * SBT_TH);
+    }
+    __syncthreads();
+    {
+        const Win w = W[nlt];
+        const int ww = w.b - w.a, wh = w.hb - w.ha, wo = sbt_wo(J.cw, nlt);
+        for (int i = tid; i < ww * wh; i += SBT_TILE_THREADS) {
+            int x = i % ww, y = i / ww;
+            win[nlt][y * ww + x] = J.llx[(w.ha + y) * wo + w.a + x];
+        }
+    }
+    __syncthreads();
+    for (int lvl = nlt; lvl > SBT_HI; lvl--) {
+        const bool last = lvl == SBT_HI + 1;
+        inv_haar_level(J, lvl, W[lvl], W[lvl - 1], win[lvl], last ? nullptr : win[lvl - 1], last ? J.llx + J.ll2_off : nullptr,
+                       sbt_wo(J.cw, SBT_HI));
+        __syncthreads();
+    }
+}
+
+/*
+ * Streaming kernel: levels 2 and 1 of one 128x64-sample tile.  Level 2 (with its one-coefficient halo) one pair
+ * per thread from the LL_2 hand-over plane; level 1 with a thread owning 4 adjacent pairs = 8x2 output samples,
+ * 16-byte coefficient loads and 8-byte sample stores.
+ */
 __global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_inv_tile_kernel(const SbtJob *jobs, int njobs)
 {
     DSV_DYN_SMEM(int32_t, sm);
     __shared__ SbtJob J;
-    __shared__ Win W[SBT_NLT + 1];
-    __shared__ int s_job;
+    __shared__ Win W[SBT_HI + 1];
     const int tid = threadIdx.x;
-
-    if (tid == 0) {
-        s_job = sbt_find_job(jobs, njobs, (int) blockIdx.x);
-    }
-    __syncthreads();
-    {
-        const int *src = reinterpret_cast<const int *>(&jobs[s_job]);
-        int *dst = reinterpret_cast<int *>(&J);
-        for (int i = tid; i < (int) (sizeof(SbtJob) / sizeof(int)); i += SBT_TILE_THREADS) {
-            dst[i] = src[i];
-        }
-    }
-    __syncthreads();
+    inv_load_job<false>(&J, jobs, njobs);
 
     const int t = (int) blockIdx.x - J.tile_base;
     const int tx = t % J.tiles_x, ty = t / J.tiles_x;
@@ -94,199 +264,146 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_inv_tile_kernel(const Sb
     const int cw = J.cw, ch = J.ch;
     const bool isI = !J.isP;
     const bool filtered = J.plane == 0;
-    const int nlt = J.nlt;
 
-    int32_t *win[SBT_NLT + 1];
-    win[1] = sm;
-    win[2] = sm + INV_OFF2;
-    win[3] = sm + INV_OFF3;
-    win[4] = sm + INV_OFF4;
-    win[5] = sm + INV_OFF5;
-    int32_t *ibase = sm + INV_WIN_ELEMS; /* I frames only */
-    uint8_t *outb = reinterpret_cast<uint8_t *>(sm + INV_WIN_ELEMS + (isI ? INV_I_EXTRA : 0));
-
-    /* ---- window geometry, top-down from the sample tile ---------------------------------- */
+    int32_t *win1 = sm, *win2 = sm + INV_OFF2;
+    int32_t *ibase = sm + INV_OFF3; /* I frames only */
     if (tid == 0) {
-        int a = gx0, b = imin(gx0 + SBT_TW, cw), ha = gy0, hb = imin(gy0 + SBT_TH, ch);
-        W[0].a = a; W[0].b = b; W[0].ha = ha; W[0].hb = hb;
-        for (int l = 1; l <= nlt; l++) {
-            int halo = (l == 1 && isI) ? 1 : (filtered ? 1 : 0);
-            int wo = sbt_wo(cw, l), ho = sbt_wo(ch, l);
-            Win w;
-            w.pa = a >> 1; w.pb = ((b - 1) >> 1) + 1;
-            w.qa = ha >> 1; w.qb = ((hb - 1) >> 1) + 1;
-            w.a = imax(w.pa - halo, 0); w.b = imin(w.pb + halo, wo);
-            w.ha = imax(w.qa - halo, 0); w.hb = imin(w.qb + halo, ho);
-            W[l] = w;
-            a = w.a; b = w.b; ha = w.ha; hb = w.hb;
-        }
+        inv_windows(J, W, 0, SBT_HI, gx0, gy0);
     }
     __syncthreads();
-
-    /* ---- load LL_nlt window from the lo kernel's hand-over array -------------------------- */
     {
-        const Win w = W[nlt];
-        const int ww = w.b - w.a, wh = w.hb - w.ha, wo = sbt_wo(cw, nlt);
+        const Win w = W[2];
+        const int ww = w.b - w.a, wh = w.hb - w.ha, wo = sbt_wo(cw, 2);
+        const int32_t *ll2 = J.llx + J.ll2_off;
         for (int i = tid; i < ww * wh; i += SBT_TILE_THREADS) {
             int x = i % ww, y = i / ww;
-            win[nlt][y * ww + x] = J.llx[(w.ha + y) * wo + w.a + x];
+            win2[y * ww + x] = ll2[(size_t) (w.ha + y) * wo + w.a + x];
         }
     }
     __syncthreads();
+    inv_haar_level(J, 2, W[2], W[1], win2, win1, nullptr, 0);
+    __syncthreads();
 
-    /* ---- Haar levels nlt .. 2 (and 1 for P frames) --------------------------------------- */
-    const int last_haar = isI ? 2 : 1;
-    for (int lvl = nlt; lvl >= last_haar; lvl--) {
-        const Win w = W[lvl];
-        const Win o = W[lvl - 1];
-        const int ww = w.b - w.a;
-        const int oww = o.b - o.a;
-        const int ws = sbt_ws(cw, lvl), hs = sbt_ws(ch, lvl), wo = sbt_wo(cw, lvl), ho = sbt_wo(ch, lvl);
-        const bool scale = lvl > 1;
-        const int bound = J.hqp[lvl];
-        const int32_t *src = win[lvl];
-        const int npx = w.pb - w.pa, npy = w.qb - w.qa;
-        for (int task = tid; task < npx * npy; task += SBT_TILE_THREADS) {
-            const int jx = w.pa + task % npx, jy = w.qa + task / npx;
-            const bool col2 = 2 * jx + 1 < ws, row2 = 2 * jy + 1 < hs;
-            const int32_t *pc = src + (jy - w.ha) * ww + (jx - w.a);
-            int LL = scale ? ll_up(pc[0]) : pc[0];
-            int v00, v01 = 0, v10 = 0, v11 = 0;
-            if (col2 && row2) {
-                int LH = J.coef[(size_t) jy * cw + wo + jx];
-                int HL = J.coef[(size_t) (ho + jy) * cw + jx];
-                int HH = J.coef[(size_t) (ho + jy) * cw + wo + jx];
-                if (filtered) {
-                    if (jx > 0) {
-                        int lp = pc[-1];
-                        int ln = (jx + 1 < wo) ? pc[1] : J.coef[(size_t) jy * cw + wo];
-                        if (scale) {
-                            lp = ll_up(lp);
-                            ln = ll_up(ln);
-                        }
-                        LH = smooth_nudge(LL, lp, ln, LH, bound);
-                    }
-                    if (jy > 0) {
-                        int lp = pc[-ww];
-                        int ln = (jy + 1 < ho) ? pc[ww] : J.coef[(size_t) ho * cw + jx];
-                        if (scale) {
-                            lp = ll_up(lp);
-                            ln = ll_up(ln);
-                        }
-                        HL = smooth_nudge(LL, lp, ln, HL, bound);
-                    }
-                }
-                v00 = div4_trunc(LL + LH + HL + HH);
-                v01 = div4_trunc(LL - LH + HL - HH);
-                v10 = div4_trunc(LL + LH - HL - HH);
-                v11 = div4_trunc(LL - LH - HL + HH);
-            } else if (row2) {
-                int HL = J.coef[(size_t) (ho + jy) * cw + jx];
-                v00 = div4_trunc(LL + HL);
-                v10 = div4_trunc(LL - HL);
-            } else if (col2) {
-                int LH = J.coef[(size_t) jy * cw + wo + jx];
-                v00 = div4_trunc(LL + LH);
-                v01 = div4_trunc(LL - LH);
-            } else {
-                v00 = div4_trunc(LL);
-            }
-            const int ox = 2 * jx, oy = 2 * jy;
-            if (lvl > 1) {
-                int32_t *dst = win[lvl - 1];
-                bool x0ok = ox >= o.a && ox < o.b, x1ok = col2 && ox + 1 >= o.a && ox + 1 < o.b;
-                bool y0ok = oy >= o.ha && oy < o.hb, y1ok = row2 && oy + 1 >= o.ha && oy + 1 < o.hb;
-                if (y0ok) {
-                    if (x0ok) dst[(oy - o.ha) * oww + (ox - o.a)] = v00;
-                    if (x1ok) dst[(oy - o.ha) * oww + (ox + 1 - o.a)] = v01;
-                }
-                if (y1ok) {
-                    if (x0ok) dst[(oy + 1 - o.ha) * oww + (ox - o.a)] = v10;
-                    if (x1ok) dst[(oy + 1 - o.ha) * oww + (ox + 1 - o.a)] = v11;
-                }
-            } else { /* sbc2int: +128, clamp (sbt.c:594-614); tile-local staging for wide stores */
-                int lx = ox - gx0, ly = oy - gy0;
-                outb[ly * SBT_TW + lx] = clamp_u8(v00 + 128);
-                if (col2) outb[ly * SBT_TW + lx + 1] = clamp_u8(v01 + 128);
-                if (row2) {
-                    outb[(ly + 1) * SBT_TW + lx] = clamp_u8(v10 + 128);
-                    if (col2) outb[(ly + 1) * SBT_TW + lx + 1] = clamp_u8(v11 + 128);
-                }
-            }
-        }
-        __syncthreads();
-    }
-
-    /* ---- level 1 of I frames: inverse B4T, columns then rows (sbt.c:253-265) --------------- */
-    if (isI) {
+    /* ---- level 1 of P frames: a thread owns 4 adjacent pairs = 8 x 2 output samples (cw, ch are even, so
+     * every pair is complete; no LL scaling at level 1 of P frames) ---------------------------------- */
+    if (!isI) {
         const Win w = W[1];
-        const int ww = w.b - w.a, wh = w.hb - w.ha;
+        const int ww = w.b - w.a;
         const int wo = cw >> 1, ho = ch >> 1;
-        int32_t *bLH = ibase, *bHL = ibase + INV_LL1_ELEMS, *bHH = ibase + 2 * INV_LL1_ELEMS;
-        int32_t *vL = ibase + 3 * INV_LL1_ELEMS;      /* [64][66] column-pass output, low columns  */
-        int32_t *vH = vL + INV_W1 * SBT_TH;           /* same for the high columns                 */
-        const int32_t *bLL = win[1];
-        for (int i = tid; i < ww * wh; i += SBT_TILE_THREADS) {
-            int x = i % ww, y = i / ww;
-            int bx = w.a + x, by = w.ha + y;
-            bLH[i] = J.coef[(size_t) by * cw + wo + bx];
-            bHL[i] = J.coef[(size_t) (ho + by) * cw + bx];
-            bHH[i] = J.coef[(size_t) (ho + by) * cw + wo + bx];
-        }
-        __syncthreads();
-        const int rows = W[0].hb - W[0].ha, cols = W[0].b - W[0].a;
-        /* column pass: out[2m] = r8(L[m-1]+3L[m]+H[m-1]-3H[m]); out[2m+1] = r8(3L[m]+L[m+1]+3H[m]-H[m+1]) */
-        for (int task = tid; task < 2 * ww * rows; task += SBT_TILE_THREADS) {
-            int c = task % (2 * ww), ly = task / (2 * ww);
-            int y = gy0 + ly, m = y >> 1;
-            bool hcol = c >= ww;
-            int x = hcol ? c - ww : c;
-            const int32_t *Lc = (hcol ? bLH : bLL) + x;
-            const int32_t *Hc = (hcol ? bHH : bHL) + x;
-            int m0 = imax(m - 1, 0) - w.ha, m1 = m - w.ha, m2 = imin(m + 1, ho - 1) - w.ha;
-            int r;
-            if (!(y & 1)) {
-                r = rnd_shift<3>(Lc[m0 * ww] + 3 * Lc[m1 * ww] + Hc[m0 * ww] - 3 * Hc[m1 * ww]);
-            } else {
-                r = rnd_shift<3>(3 * Lc[m1 * ww] + Lc[m2 * ww] + 3 * Hc[m1 * ww] - Hc[m2 * ww]);
-            }
-            (hcol ? vH : vL)[ly * INV_W1 + x] = r;
-        }
-        __syncthreads();
-        /* row pass + sbc2int */
-        for (int task = tid; task < cols * rows; task += SBT_TILE_THREADS) {
-            int lx = task % cols, ly = task / cols;
-            int x = gx0 + lx, k = x >> 1;
-            const int32_t *L = vL + ly * INV_W1, *H = vH + ly * INV_W1;
-            int k0 = imax(k - 1, 0) - w.a, k1 = k - w.a, k2 = imin(k + 1, wo - 1) - w.a;
-            int r;
-            if (!(x & 1)) {
-                r = rnd_shift<3>(L[k0] + 3 * L[k1] + H[k0] - 3 * H[k1]);
-            } else {
-                r = rnd_shift<3>(3 * L[k1] + L[k2] + 3 * H[k1] - H[k2]);
-            }
-            outb[ly * SBT_TW + lx] = clamp_u8(r + 128);
-        }
-        __syncthreads();
-    }
-
-    /* ---- store the sample tile (only pw x ph is written, sbt.c:603-613) -------------------- */
-    {
-        const int rows = imin(SBT_TH, J.ph - gy0), cols = imin(SBT_TW, J.pw - gx0);
-        for (int task = tid; task < SBT_TH * (SBT_TW / 16); task += SBT_TILE_THREADS) {
-            int ly = task >> 3, ck = task & 7;
-            if (ly >= rows || ck * 16 >= cols) {
+        const int bound = J.hqp[1];
+        const int32_t *LLw = win1;
+        for (int g = tid; g < (SBT_TW / 8) * (SBT_TH / 2); g += SBT_TILE_THREADS) {
+            const int qrow = g >> 4, qc = (g & 15) * 4;
+            const int jy = ty * (SBT_TH / 2) + qrow, jx = tx * (SBT_TW / 2) + qc;
+            if (jy >= ho || jx >= wo) {
                 continue;
             }
-            uint8_t *dst = J.opix + (size_t) (gy0 + ly) * J.ostride + gx0 + ck * 16;
-            const uint8_t *srcb = outb + ly * SBT_TW + ck * 16;
-            if (ck * 16 + 16 <= cols && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(srcb);
+            const int nv = imin(4, wo - jx);
+            const int32_t *pLH = J.coef + (size_t) jy * cw + wo + jx;
+            const int32_t *pHL = J.coef + (size_t) (ho + jy) * cw + jx;
+            const int32_t *pHH = pHL + wo;
+            int LH[4] = {0, 0, 0, 0}, HL[4] = {0, 0, 0, 0}, HH[4] = {0, 0, 0, 0};
+            if (nv == 4 && ((reinterpret_cast<uintptr_t>(pLH) | reinterpret_cast<uintptr_t>(pHL) | reinterpret_cast<uintptr_t>(pHH)) & 15) == 0) {
+                const int4 a = *reinterpret_cast<const int4 *>(pLH), b = *reinterpret_cast<const int4 *>(pHL), c = *reinterpret_cast<const int4 *>(pHH);
+                LH[0] = a.x; LH[1] = a.y; LH[2] = a.z; LH[3] = a.w;
+                HL[0] = b.x; HL[1] = b.y; HL[2] = b.z; HL[3] = b.w;
+                HH[0] = c.x; HH[1] = c.y; HH[2] = c.z; HH[3] = c.w;
             } else {
-                for (int e = 0; e < 16 && ck * 16 + e < cols; e++) {
-                    dst[e] = srcb[e];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (i < nv) {
+                        LH[i] = pLH[i];
+                        HL[i] = pHL[i];
+                        HH[i] = pHH[i];
+                    }
                 }
             }
+            const int32_t *pc = LLw + (jy - w.ha) * ww + (jx - w.a);
+            int r0[8], r1[8];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int LL = i < nv ? pc[i] : 0;
+                if (filtered && i < nv) {
+                    if (jx + i > 0) {
+                        const int lp = pc[i - 1];
+                        const int ln = (jx + i + 1 < wo) ? pc[i + 1] : J.coef[(size_t) jy * cw + wo];
+                        LH[i] = smooth_nudge(LL, lp, ln, LH[i], bound);
+                    }
+                    if (jy > 0) {
+                        const int lp = pc[i - ww];
+                        const int ln = (jy + 1 < ho) ? pc[i + ww] : J.coef[(size_t) ho * cw + jx + i];
+                        HL[i] = smooth_nudge(LL, lp, ln, HL[i], bound);
+                    }
+                }
+                r0[2 * i] = div4_trunc(LL + LH[i] + HL[i] + HH[i]);
+                r0[2 * i + 1] = div4_trunc(LL - LH[i] + HL[i] - HH[i]);
+                r1[2 * i] = div4_trunc(LL + LH[i] - HL[i] - HH[i]);
+                r1[2 * i + 1] = div4_trunc(LL - LH[i] - HL[i] + HH[i]);
+            }
+            store_row8(J, 2 * jy, 2 * jx, r0);
+            store_row8(J, 2 * jy + 1, 2 * jx, r1);
+        }
+    }
+
+    /* ---- level 1 of I frames: inverse B4T, columns then rows (sbt.c:129-163,204-238,253-265) ----------
+     * out[2m]   = r8(L[m-1] + 3L[m] + H[m-1] - 3H[m]),  out[2m+1] = r8(3L[m] + L[m+1] + 3H[m] - H[m+1]),
+     * L[-1] := L[0], L[n/2] := L[n/2-1] (same for H).  Column pass: a thread walks down one column of the
+     * LL|HL (low) or LH|HH (high) pair with a sliding 3-row window (coalesced 4-byte loads across the warp);
+     * row pass: a thread owns 8 adjacent output samples of one row and stores them with one 8-byte store. */
+    if (isI) {
+        const Win w = W[1];
+        const int ww = w.b - w.a;
+        const int wo = cw >> 1, ho = ch >> 1;
+        int32_t *vbuf = ibase; /* [SBT_TH][INV_VSTRIDE]: low columns at 0.., high columns at 68.. */
+        const int32_t *bLL = win1;
+        const int rows = W[0].hb - W[0].ha; /* output rows of this tile (<= 64, even) */
+        const int m_lo = gy0 >> 1, nm = rows >> 1;
+        /* tasks: (column in window) x (low | high) x (two halves of the row-pair range) */
+        const int half = (nm + 1) >> 1;
+        for (int task = tid; task < 4 * ww; task += SBT_TILE_THREADS) {
+            const int part = task / (2 * ww), c = task - part * 2 * ww;
+            const bool hcol = c >= ww;
+            const int x = hcol ? c - ww : c; /* window column */
+            const int gx = w.a + x;          /* band column */
+            const int mA = m_lo + part * half, mB = imin(m_lo + nm, mA + half);
+            if (mA >= mB) {
+                continue;
+            }
+            auto ldL = [&](int m) -> int {
+                return hcol ? J.coef[(size_t) m * cw + wo + gx] : bLL[(m - w.ha) * ww + x];
+            };
+            auto ldH = [&](int m) -> int {
+                return J.coef[(size_t) (ho + m) * cw + (hcol ? wo : 0) + gx];
+            };
+            int Lp = ldL(imax(mA - 1, 0)), Hp = ldH(imax(mA - 1, 0));
+            int Lc = ldL(mA), Hc = ldH(mA);
+            int32_t *vcol = vbuf + (hcol ? 68 : 0) + x;
+            for (int m = mA; m < mB; m++) {
+                const int mn = imin(m + 1, ho - 1);
+                const int Ln = ldL(mn), Hn = ldH(mn);
+                const int ly = 2 * (m - m_lo);
+                vcol[ly * INV_VSTRIDE] = rnd_shift<3>(Lp + 3 * Lc + Hp - 3 * Hc);
+                vcol[(ly + 1) * INV_VSTRIDE] = rnd_shift<3>(3 * Lc + Ln + 3 * Hc - Hn);
+                Lp = Lc; Hp = Hc; Lc = Ln; Hc = Hn;
+            }
+        }
+        __syncthreads();
+        for (int g = tid; g < (SBT_TW / 8) * SBT_TH; g += SBT_TILE_THREADS) {
+            const int ly = g >> 4, k0l = (g & 15) * 4;
+            const int k0 = tx * (SBT_TW / 2) + k0l; /* first of 4 band columns -> 8 samples */
+            if (ly >= rows || k0 >= wo) {
+                continue;
+            }
+            const int32_t *L = vbuf + ly * INV_VSTRIDE - w.a, *H = L + 68;
+            int v[8];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int k = imin(k0 + i, wo - 1);
+                const int kp = imax(k - 1, 0), kn = imin(k + 1, wo - 1);
+                v[2 * i] = rnd_shift<3>(L[kp] + 3 * L[k] + H[kp] - 3 * H[k]);
+                v[2 * i + 1] = rnd_shift<3>(3 * L[k] + L[kn] + 3 * H[k] - H[kn]);
+            }
+            store_row8(J, gy0 + ly, 2 * k0, v);
         }
     }
 }
@@ -366,20 +483,26 @@ __global__ void __launch_bounds__(SBT_LO_THREADS) sbt_inv_lo_kernel(const SbtJob
     }
 }
 
-void sbt_inv_launch(const SbtJob *d_jobs, int njobs, int total_tiles, size_t lo_smem, bool any_intra, cudaStream_t st,
-                    cudaEvent_t ev0, cudaEvent_t ev1)
+void sbt_inv_launch(const SbtJob *d_jobs, const SbtDims &dims, size_t lo_smem, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1)
 {
-    size_t tile_smem = inv_tile_smem(any_intra);
+    if (dims.njobs <= 0) {
+        return;
+    }
+    const size_t tile_smem = inv_tile_smem(dims.any_intra);
     if (lo_smem > 48 * 1024) {
         CUDA_CHECK(cudaFuncSetAttribute(sbt_inv_lo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) lo_smem));
     }
-    CUDA_CHECK(cudaFuncSetAttribute(sbt_inv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tile_smem));
-    DSV_LAUNCH(sbt_inv_lo_kernel, dim3(njobs), dim3(SBT_LO_THREADS), lo_smem, st, d_jobs);
+    if (tile_smem > 48 * 1024) {
+        CUDA_CHECK(cudaFuncSetAttribute(sbt_inv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tile_smem));
+    }
+    DSV_LAUNCH(sbt_inv_lo_kernel, dim3(dims.njobs), dim3(SBT_LO_THREADS), lo_smem, st, d_jobs);
+    KERNEL_CHECK();
+    DSV_LAUNCH(sbt_inv_mid_kernel, dim3(dims.mtiles), dim3(SBT_TILE_THREADS), 0, st, d_jobs, dims.njobs);
     KERNEL_CHECK();
     if (ev0) {
         CUDA_CHECK(cudaEventRecord(ev0, st));
     }
-    DSV_LAUNCH(sbt_inv_tile_kernel, dim3(total_tiles), dim3(SBT_TILE_THREADS), tile_smem, st, d_jobs, njobs);
+    DSV_LAUNCH(sbt_inv_tile_kernel, dim3(dims.tiles), dim3(SBT_TILE_THREADS), tile_smem, st, d_jobs, dims.njobs);
     KERNEL_CHECK();
     if (ev1) {
         CUDA_CHECK(cudaEventRecord(ev1, st));

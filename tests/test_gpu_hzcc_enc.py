@@ -50,7 +50,8 @@ def test_uhd_vs_reference(gpu, ref):
     assert np.array_equal(ca, cb) and np.array_equal(sa, sb)
 
 
-@pytest.mark.parametrize("dims", [(352, 288, 352, 288), (959, 539, 960, 540), (427, 240, 428, 240), (1920, 1080, 1920, 1080)])
+@pytest.mark.parametrize("dims", [(352, 288, 352, 288), (959, 539, 960, 540), (427, 240, 428, 240), (1920, 1080, 1920, 1080),
+                                  (214, 120, 214, 120), (107, 60, 108, 60), (240, 135, 240, 136)])
 def test_fused_quant_equals_separate(gpu, port, dims):
     """SBT epilogue quantiser == transform followed by encode_plane's in-place write-back."""
     pw, ph, cw, ch = dims
