@@ -87,6 +87,9 @@ size_t sbt_dv_elems(int cw, int ch);
 struct SbtDims {
     int njobs = 0, tiles = 0, mtiles = 0;
     bool any_intra = false;
+    /* uniform launches (the engines: planes Y,U,V of many pictures of one format): jobs come in groups of gsz
+     * with identical tile counts per position, so tile -> job is arithmetic; gsz == 0: binary search */
+    int gsz = 0, tg = 0, c0 = 0, c1 = 0, mtg = 0, mc0 = 0, mc1 = 0;
 };
 /* assigns tile_base / mtile_base of jobs[0..n) (host copies, in launch order) and returns the totals */
 SbtDims sbt_assign_tiles(SbtJob *jobs, int n);
@@ -97,6 +100,9 @@ void sbt_fwd_launch(const SbtJob *d_jobs, const SbtDims &dims, size_t lo_smem, c
 void sbt_inv_launch(const SbtJob *d_jobs, const SbtDims &dims, size_t lo_smem, cudaStream_t st,
                     cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 size_t sbt_lo_smem_bytes(int cw, int ch);
+
+/* flat tile index -> (job, tile within job) */
+template <bool MID> DSV_D int sbt_locate(const SbtJob *jobs, const SbtDims &d, int bid, int *tile);
 
 /* flat tile index -> job (jobs are sorted by tile_base / mtile_base) */
 template <bool MID> DSV_D int sbt_find_job(const SbtJob *jobs, int njobs, int tile)
@@ -111,6 +117,20 @@ template <bool MID> DSV_D int sbt_find_job(const SbtJob *jobs, int njobs, int ti
         }
     }
     return lo;
+}
+
+template <bool MID> DSV_D int sbt_locate(const SbtJob *jobs, const SbtDims &d, int bid, int *tile)
+{
+    if (d.gsz) {
+        const int tg = MID ? d.mtg : d.tg, c0 = MID ? d.mc0 : d.c0, c1 = MID ? d.mc1 : d.c1;
+        const int grp = bid / tg, r = bid - grp * tg;
+        const int k = (r >= c0) + (r >= c0 + c1);
+        *tile = r - (k == 0 ? 0 : (k == 1 ? c0 : c0 + c1));
+        return grp * d.gsz + k;
+    }
+    const int job = sbt_find_job<MID>(jobs, d.njobs, bid);
+    *tile = bid - (MID ? jobs[job].mtile_base : jobs[job].tile_base);
+    return job;
 }
 
 /* per-level geometry helpers */

@@ -78,8 +78,11 @@ DSV_D void store_n(int32_t *dst, const int *v, int n, int nvalid)
     } else if (nvalid == n && n == 2 && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
         *reinterpret_cast<int2 *>(dst) = make_int2(v[0], v[1]);
     } else {
-        for (int i = 0; i < nvalid; i++) {
-            dst[i] = v[i];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (i < n && i < nvalid) {
+                dst[i] = v[i];
+            }
         }
     }
 }
@@ -97,10 +100,13 @@ DSV_D void emit_quads(const SbtJob &J, const uint8_t *stab, int lvl, int wo, int
     const int cw = J.cw;
     if (J.do_quant) {
         if (lvl <= 2 && (J.dg.dvx[lvl] >= 0 || J.dg.dvy[lvl] >= 0)) {
-            for (int i = 0; i < nvalid; i++) {
-                emit_h(J, true, stab, lvl, 1, bx + i, by, lh[i]);
-                emit_h(J, true, stab, lvl, 2, bx + i, by, hl[i]);
-                emit_h(J, true, stab, lvl, 3, bx + i, by, hh[i]);
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                if (i < nvalid) {
+                    emit_h(J, true, stab, lvl, 1, bx + i, by, lh[i]);
+                    emit_h(J, true, stab, lvl, 2, bx + i, by, hl[i]);
+                    emit_h(J, true, stab, lvl, 3, bx + i, by, hh[i]);
+                }
             }
             return;
         }
@@ -141,22 +147,24 @@ DSV_D int fwd_sample(const SbtJob &J, int r, int c)
 
 /* one-barrier prologue shared by the tile kernels: every thread finds the job (same broadcast loads), the
  * job record is copied to shared memory */
-template <bool MID> DSV_D void load_job(SbtJob *sJ, const SbtJob *jobs, int njobs)
+template <bool MID> DSV_D int load_job(SbtJob *sJ, const SbtJob *jobs, const SbtDims &dims)
 {
-    const int job = sbt_find_job<MID>(jobs, njobs, (int) blockIdx.x);
+    int tile;
+    const int job = sbt_locate<MID>(jobs, dims, (int) blockIdx.x, &tile);
     const int *src = reinterpret_cast<const int *>(&jobs[job]);
     int *dst = reinterpret_cast<int *>(sJ);
     for (int i = threadIdx.x; i < (int) (sizeof(SbtJob) / sizeof(int)); i += blockDim.x) {
         dst[i] = src[i];
     }
     __syncthreads();
+    return tile;
 }
 
 /* 8 samples of rows r0, r0+1 starting at column c0 as two pairs of packed words; samples outside w x ph read as
  * 128 (i.e. 0 after the -128 offset, sbt.c:576-592), nv = valid quads (1..4) */
-DSV_D void load_quads_slow(const SbtJob &J, int r0, int c0, int nv, unsigned (&w0)[2], unsigned (&w1)[2])
+DSV_D void load_quads_slow(const SbtJob &J, int r0, int c0, int nv, unsigned &w00, unsigned &w01, unsigned &w10, unsigned &w11)
 {
-    w0[0] = w0[1] = w1[0] = w1[1] = 0x80808080u;
+    w00 = w01 = w10 = w11 = 0x80808080u;
     const bool ok0 = r0 < J.ph, ok1 = r0 + 1 < J.ph;
     const uint8_t *p0 = J.pix + (size_t) r0 * J.pstride + c0, *p1 = p0 + J.pstride;
 #pragma unroll
@@ -165,11 +173,11 @@ DSV_D void load_quads_slow(const SbtJob &J, int r0, int c0, int nv, unsigned (&w
             const unsigned a = ok0 ? p0[e] : 128u, b = ok1 ? p1[e] : 128u;
             const unsigned m = ~(0xffu << (8 * (e & 3)));
             if (e < 4) {
-                w0[0] = (w0[0] & m) | (a << (8 * (e & 3)));
-                w1[0] = (w1[0] & m) | (b << (8 * (e & 3)));
+                w00 = (w00 & m) | (a << (8 * (e & 3)));
+                w10 = (w10 & m) | (b << (8 * (e & 3)));
             } else {
-                w0[1] = (w0[1] & m) | (a << (8 * (e & 3)));
-                w1[1] = (w1[1] & m) | (b << (8 * (e & 3)));
+                w01 = (w01 & m) | (a << (8 * (e & 3)));
+                w11 = (w11 & m) | (b << (8 * (e & 3)));
             }
         }
     }
@@ -179,15 +187,14 @@ DSV_D void load_quads_slow(const SbtJob &J, int r0, int c0, int nv, unsigned (&w
  * Streaming kernel: levels 1 and 2 of one 128x64-sample tile.  LL_2 (32x16 values) goes to the job's ll2
  * hand-over plane for the mid kernel.
  */
-__global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_fwd_tile_kernel(const SbtJob *jobs, int njobs)
+__global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_fwd_tile_kernel(const SbtJob *jobs, const SbtDims dims)
 {
     DSV_DYN_SMEM(int16_t, s_hb); /* I frames only: B4T row-pass strip, (64 + 2) x FWD_HB_STRIDE int16 */
     __shared__ SbtJob J;
     __shared__ __align__(16) int32_t s_ll1[(SBT_TW / 2) * (SBT_TH / 2)];
     const int tid = threadIdx.x;
-    load_job<false>(&J, jobs, njobs);
+    const int t = load_job<false>(&J, jobs, dims);
 
-    const int t = (int) blockIdx.x - J.tile_base;
     const int tx = t % J.tiles_x, ty = t / J.tiles_x;
     const int gx0 = tx * SBT_TW, gy0 = ty * SBT_TH;
     const int cw = J.cw, ch = J.ch;
@@ -217,7 +224,7 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_fwd_tile_kernel(const Sb
                 const uint2 b = *reinterpret_cast<const uint2 *>(J.pix + (size_t) (r0 + 1) * J.pstride + c0);
                 w0[it][0] = a.x; w0[it][1] = a.y; w1[it][0] = b.x; w1[it][1] = b.y;
             } else if (nv[it] > 0) {
-                load_quads_slow(J, r0, c0, nv[it], w0[it], w1[it]);
+                load_quads_slow(J, r0, c0, nv[it], w0[it][0], w0[it][1], w1[it][0], w1[it][1]);
             }
         }
 #pragma unroll
@@ -310,12 +317,15 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_fwd_tile_kernel(const Sb
             int32_t *row0 = J.coef + (size_t) gm * cw + gk, *row1 = J.coef + (size_t) (ho1 + gm) * cw + gk;
             if (J.do_quant && (J.dg.dvx[1] >= 0 || J.dg.dvy[1] >= 0)) {
                 /* odd next-level size: some of these positions are scanned twice */
-                for (int i = 0; i < nv; i++) {
-                    if (!hcol) {
-                        emit_h(J, true, stab, 1, 2, gk + i, gm, hi[i]);
-                    } else {
-                        emit_h(J, true, stab, 1, 1, gk + i, gm, lo[i]);
-                        emit_h(J, true, stab, 1, 3, gk + i, gm, hi[i]);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (i < nv) {
+                        if (!hcol) {
+                            emit_h(J, true, stab, 1, 2, gk + i, gm, hi[i]);
+                        } else {
+                            emit_h(J, true, stab, 1, 1, gk + i, gm, lo[i]);
+                            emit_h(J, true, stab, 1, 3, gk + i, gm, hi[i]);
+                        }
                     }
                 }
                 continue;
@@ -370,8 +380,12 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_fwd_tile_kernel(const Sb
             if (all2) {
                 emit_quads<2>(J, stab, 2, wo, ho, gx, gy, nv, lh, hl, hh);
             } else {
-                for (int i = 0; i < nv; i++) {
-                    const bool col2 = 2 * (gx + i) + 1 < ws;
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const bool col2 = i < nv && 2 * (gx + i) + 1 < ws;
+                    if (i >= nv) {
+                        continue;
+                    }
                     if (col2) {
                         emit_h(J, J.do_quant != 0, stab, 2, 1, gx + i, gy, lh[i]);
                     }
@@ -391,14 +405,13 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_fwd_tile_kernel(const Sb
  * Mid kernel: levels 3..nlt of one 128x64 block of LL_2 (= a 512x256-sample region), one quad per thread
  * per level (6 % of the coefficients); LL_nlt goes to the llx hand-over array.
  */
-__global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_fwd_mid_kernel(const SbtJob *jobs, int njobs)
+__global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_fwd_mid_kernel(const SbtJob *jobs, const SbtDims dims)
 {
     __shared__ SbtJob J;
     __shared__ __align__(16) int32_t s_a[SBT_TW * SBT_TH];
     __shared__ __align__(16) int32_t s_b[(SBT_TW / 2) * (SBT_TH / 2)];
     const int tid = threadIdx.x;
-    load_job<true>(&J, jobs, njobs);
-    const int t = (int) blockIdx.x - J.mtile_base;
+    const int t = load_job<true>(&J, jobs, dims);
     const int tx = t % J.mtiles_x, ty = t / J.mtiles_x;
     const int cw = J.cw, ch = J.ch;
     const uint8_t *stab = J.stable;
@@ -521,12 +534,12 @@ void sbt_fwd_launch(const SbtJob *d_jobs, const SbtDims &dims, size_t lo_smem, c
     if (ev0) {
         CUDA_CHECK(cudaEventRecord(ev0, st));
     }
-    DSV_LAUNCH(sbt_fwd_tile_kernel, dim3(dims.tiles), dim3(SBT_TILE_THREADS), hb, st, d_jobs, dims.njobs);
+    DSV_LAUNCH(sbt_fwd_tile_kernel, dim3(dims.tiles), dim3(SBT_TILE_THREADS), hb, st, d_jobs, dims);
     KERNEL_CHECK();
     if (ev1) {
         CUDA_CHECK(cudaEventRecord(ev1, st));
     }
-    DSV_LAUNCH(sbt_fwd_mid_kernel, dim3(dims.mtiles), dim3(SBT_TILE_THREADS), 0, st, d_jobs, dims.njobs);
+    DSV_LAUNCH(sbt_fwd_mid_kernel, dim3(dims.mtiles), dim3(SBT_TILE_THREADS), 0, st, d_jobs, dims);
     KERNEL_CHECK();
     DSV_LAUNCH(sbt_fwd_lo_kernel, dim3(dims.njobs), dim3(SBT_LO_THREADS), lo_smem, st, d_jobs);
     KERNEL_CHECK();

@@ -24,6 +24,22 @@ SbtDims sbt_assign_tiles(SbtJob *jobs, int n)
         d.mtiles += jobs[i].mtiles_x * jobs[i].mtiles_y;
         d.any_intra |= !jobs[i].isP;
     }
+    /* uniform groups? */
+    const int gsz = (n % 3 == 0) ? 3 : 1;
+    bool uni = true;
+    for (int i = gsz; i < n && uni; i++) {
+        uni = jobs[i].tiles_x * jobs[i].tiles_y == jobs[i % gsz].tiles_x * jobs[i % gsz].tiles_y &&
+              jobs[i].mtiles_x * jobs[i].mtiles_y == jobs[i % gsz].mtiles_x * jobs[i % gsz].mtiles_y;
+    }
+    if (uni && n > 0) {
+        d.gsz = gsz;
+        d.c0 = jobs[0].tiles_x * jobs[0].tiles_y;
+        d.mc0 = jobs[0].mtiles_x * jobs[0].mtiles_y;
+        d.c1 = gsz == 3 ? jobs[1].tiles_x * jobs[1].tiles_y : 0;
+        d.mc1 = gsz == 3 ? jobs[1].mtiles_x * jobs[1].mtiles_y : 0;
+        d.tg = gsz == 3 ? d.c0 + d.c1 + jobs[2].tiles_x * jobs[2].tiles_y : d.c0;
+        d.mtg = gsz == 3 ? d.mc0 + d.mc1 + jobs[2].mtiles_x * jobs[2].mtiles_y : d.mc0;
+    }
     return d;
 }
 

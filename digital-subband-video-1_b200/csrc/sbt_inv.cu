@@ -83,21 +83,26 @@ DSV_D void store_row8(const SbtJob &J, int oy, int ox, const int *v)
     if (ox + 8 <= J.pw && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
         *reinterpret_cast<uint2 *>(dst) = make_uint2(pack4_u8(v[0], v[1], v[2], v[3]), pack4_u8(v[4], v[5], v[6], v[7]));
     } else {
-        for (int e = 0; e < 8 && ox + e < J.pw; e++) {
-            dst[e] = clamp_u8(v[e] + 128);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            if (ox + e < J.pw) {
+                dst[e] = clamp_u8(v[e] + 128);
+            }
         }
     }
 }
 
-template <bool MID> DSV_D void inv_load_job(SbtJob *sJ, const SbtJob *jobs, int njobs)
+template <bool MID> DSV_D int inv_load_job(SbtJob *sJ, const SbtJob *jobs, const SbtDims &dims)
 {
-    const int job = sbt_find_job<MID>(jobs, njobs, (int) blockIdx.x);
+    int tile;
+    const int job = sbt_locate<MID>(jobs, dims, (int) blockIdx.x, &tile);
     const int *src = reinterpret_cast<const int *>(&jobs[job]);
     int *dst = reinterpret_cast<int *>(sJ);
     for (int i = threadIdx.x; i < (int) (sizeof(SbtJob) / sizeof(int)); i += blockDim.x) {
         dst[i] = src[i];
     }
     __syncthreads();
+    return tile;
 }
 
 /* window geometry, top-down from the tile of level-`base` outputs (base 0 = samples) to level `top` */
@@ -210,14 +215,13 @@ DSV_D void inv_haar_level(const SbtJob &J, int lvl, const Win &w, const Win &o, 
  * Mid kernel: levels nlt..3 for one 128x64 block of LL_2.  LL_nlt window from the lo kernel's hand-over array,
  * result into the dense LL_2 hand-over plane.
  */
-__global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_inv_mid_kernel(const SbtJob *jobs, int njobs)
+__global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_inv_mid_kernel(const SbtJob *jobs, const SbtDims dims)
 {
     __shared__ int32_t sm[INV_WIN_ELEMS];
     __shared__ SbtJob J;
     __shared__ Win W[SBT_NLT + 1];
     const int tid = threadIdx.x;
-    inv_load_job<true>(&J, jobs, njobs);
-    const int t = (int) blockIdx.x - J.mtile_base;
+    const int t = inv_load_job<true>(&J, jobs, dims);
     const int tx = t % J.mtiles_x, ty = t / J.mtiles_x;
     const int nlt = J.nlt;
     int32_t *win[SBT_NLT + 1];
@@ -250,15 +254,14 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_inv_mid_kernel(const Sbt
  * per thread from the LL_2 hand-over plane; level 1 with a thread owning 4 adjacent pairs = 8x2 output samples,
  * 16-byte coefficient loads and 8-byte sample stores.
  */
-__global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_inv_tile_kernel(const SbtJob *jobs, int njobs)
+__global__ void __launch_bounds__(SBT_TILE_THREADS, 5) sbt_inv_tile_kernel(const SbtJob *jobs, const SbtDims dims)
 {
     DSV_DYN_SMEM(int32_t, sm);
     __shared__ SbtJob J;
     __shared__ Win W[SBT_HI + 1];
     const int tid = threadIdx.x;
-    inv_load_job<false>(&J, jobs, njobs);
+    const int t = inv_load_job<false>(&J, jobs, dims);
 
-    const int t = (int) blockIdx.x - J.tile_base;
     const int tx = t % J.tiles_x, ty = t / J.tiles_x;
     const int gx0 = tx * SBT_TW, gy0 = ty * SBT_TH;
     const int cw = J.cw, ch = J.ch;
@@ -497,12 +500,12 @@ void sbt_inv_launch(const SbtJob *d_jobs, const SbtDims &dims, size_t lo_smem, c
     }
     DSV_LAUNCH(sbt_inv_lo_kernel, dim3(dims.njobs), dim3(SBT_LO_THREADS), lo_smem, st, d_jobs);
     KERNEL_CHECK();
-    DSV_LAUNCH(sbt_inv_mid_kernel, dim3(dims.mtiles), dim3(SBT_TILE_THREADS), 0, st, d_jobs, dims.njobs);
+    DSV_LAUNCH(sbt_inv_mid_kernel, dim3(dims.mtiles), dim3(SBT_TILE_THREADS), 0, st, d_jobs, dims);
     KERNEL_CHECK();
     if (ev0) {
         CUDA_CHECK(cudaEventRecord(ev0, st));
     }
-    DSV_LAUNCH(sbt_inv_tile_kernel, dim3(dims.tiles), dim3(SBT_TILE_THREADS), tile_smem, st, d_jobs, dims.njobs);
+    DSV_LAUNCH(sbt_inv_tile_kernel, dim3(dims.tiles), dim3(SBT_TILE_THREADS), tile_smem, st, d_jobs, dims);
     KERNEL_CHECK();
     if (ev1) {
         CUDA_CHECK(cudaEventRecord(ev1, st));
