@@ -42,10 +42,43 @@ DSV_D unsigned block_sum_u32(unsigned v, unsigned *scratch /* >= 33 */)
     return t;
 }
 
+/* combine 4 predicted samples with the current word and store (prediction word kept when asked) */
+DSV_D void bmc_store4(const BmcPlane &P, int mode, int gx, int gy, int nvalid, bool vec, int p0, int p1, int p2, int p3)
+{
+    const size_t io = (size_t) gy * P.istride + gx, oo = (size_t) gy * P.ostride + gx;
+    if (vec && nvalid == 4) {
+        const unsigned cur = *reinterpret_cast<const unsigned *>(P.in + io);
+        unsigned out;
+        if (mode == 1) {
+            out = pack_u8x4(byte_of(cur, 0) - p0 + 128, byte_of(cur, 1) - p1 + 128, byte_of(cur, 2) - p2 + 128, byte_of(cur, 3) - p3 + 128);
+        } else {
+            out = pack_u8x4(byte_of(cur, 0) + p0 - 128, byte_of(cur, 1) + p1 - 128, byte_of(cur, 2) + p2 - 128, byte_of(cur, 3) + p3 - 128);
+        }
+        *reinterpret_cast<unsigned *>(P.out + oo) = out;
+        if (P.pred) {
+            *reinterpret_cast<unsigned *>(P.pred + (size_t) gy * P.pstride + gx) =
+                (unsigned) p0 | ((unsigned) p1 << 8) | ((unsigned) p2 << 16) | ((unsigned) p3 << 24);
+        }
+        return;
+    }
+    const int pv[4] = {p0, p1, p2, p3};
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        if (e < nvalid) {
+            const int cur = P.in[io + e];
+            P.out[oo + e] = mode == 1 ? clamp_u8(cur - pv[e] + 128) : clamp_u8(pv[e] + cur - 128);
+            if (P.pred) {
+                P.pred[(size_t) gy * P.pstride + gx + e] = (uint8_t) pv[e];
+            }
+        }
+    }
+}
+
+/* a thread owns 4 horizontally adjacent samples; frames keep rows 4-byte aligned at multiples of 4 */
 __global__ void __launch_bounds__(BMC_THREADS) bmc_kernel(const BmcArgs *args)
 {
     const BmcArgs &a = args[blockIdx.z / 3];
-    __shared__ int16_t hbuf[(DSV_BORDER + 3) * DSV_BORDER]; /* (bh + 3) x bw, bmc.c:127 */
+    __shared__ __align__(8) int16_t hbuf[(DSV_BORDER + 3) * DSV_BORDER]; /* (bh + 3) x bw, bmc.c:127 */
     __shared__ unsigned scratch[40];
     __shared__ int s_avg[4];
     const int c = blockIdx.z % 3;
@@ -61,8 +94,16 @@ __global__ void __launch_bounds__(BMC_THREADS) bmc_kernel(const BmcArgs *args)
     }
     const DevMV mv = a.mv[j * a.nbh + i];
     const int tid = threadIdx.x;
-    const int npx = cw * ch;
-    if (a.mode == 1 && x + cw == P.w) {
+    const int mode = a.mode;
+    const int words = (cw + 3) >> 2;
+    int wsh = 0;
+    while ((1 << wsh) < words) {
+        wsh++;
+    }
+    const int wmask = (1 << wsh) - 1;
+    const bool walign = ((x & 3) == 0) && ((P.istride | P.ostride | P.pstride) & 3) == 0 &&
+                        ((reinterpret_cast<uintptr_t>(P.in) | reinterpret_cast<uintptr_t>(P.out) | reinterpret_cast<uintptr_t>(P.pred)) & 3) == 0;
+    if (mode == 1 && x + cw == P.w) {
         /* the forward transform of a plane with odd width reads one column past it (sbt.c:583-591); in the
          * reference that column of the residual frame still holds the replicated INPUT border
          * (dsv_encoder.c:657-659: xf = copy of the padded input, then only w x h is replaced) */
@@ -79,43 +120,77 @@ __global__ void __launch_bounds__(BMC_THREADS) bmc_kernel(const BmcArgs *args)
         const int phase = ((dx & 1) << 1) | (dy & 1);
         const uint8_t *r0 = P.ref + (ptrdiff_t) py * P.rstride + px;
         const int rs = P.rstride;
+        const int hstride = words * 4; /* int16 per staged row */
         if (c == 0 && phase == 3) {
-            for (int k = tid; k < (ch + 3) * cw; k += BMC_THREADS) {
-                const int ly = k / cw, lx = k - ly * cw;
-                const uint8_t *p = r0 + (ptrdiff_t) (ly - 1) * rs + lx;
-                hbuf[k] = (int16_t) hpf4(p[-1], p[0], p[1], p[2]);
+            for (int k = tid; k < ((ch + 3) << wsh); k += BMC_THREADS) {
+                const int ly = k >> wsh, wx = k & wmask;
+                if (wx >= words) {
+                    continue;
+                }
+                const uint8_t *p = r0 + (ptrdiff_t) (ly - 1) * rs + 4 * wx;
+                const unsigned wa = ld4u(p - 1), wb = ld4u(p + 3); /* p[-1..2], p[3..6] */
+                const int b0 = byte_of(wa, 0), b1 = byte_of(wa, 1), b2 = byte_of(wa, 2), b3 = byte_of(wa, 3);
+                const int b4 = byte_of(wb, 0), b5 = byte_of(wb, 1), b6 = byte_of(wb, 2);
+                int16_t *d = hbuf + ly * hstride + 4 * wx;
+                d[0] = (int16_t) hpf4(b0, b1, b2, b3);
+                d[1] = (int16_t) hpf4(b1, b2, b3, b4);
+                d[2] = (int16_t) hpf4(b2, b3, b4, b5);
+                d[3] = (int16_t) hpf4(b3, b4, b5, b6);
             }
             __syncthreads();
         }
-        for (int k = tid; k < npx; k += BMC_THREADS) {
-            const int ly = k / cw, lx = k - ly * cw;
+        for (int k = tid; k < (ch << wsh); k += BMC_THREADS) {
+            const int ly = k >> wsh, wx = k & wmask;
+            if (wx >= words) {
+                continue;
+            }
+            const int lx = 4 * wx;
             const uint8_t *p = r0 + (ptrdiff_t) ly * rs + lx;
-            int v;
+            int v0, v1, v2, v3;
             if (phase == 0) {
-                v = p[0];
+                const unsigned w = ld4u(p);
+                v0 = byte_of(w, 0); v1 = byte_of(w, 1); v2 = byte_of(w, 2); v3 = byte_of(w, 3);
             } else if (c == 0) {
                 if (phase == 1) {
-                    v = clamp_u8((hpf4(p[-rs], p[0], p[rs], p[2 * rs]) + 8) >> 4);
+                    const unsigned wa = ld4u(p - rs), wb = ld4u(p), wc = ld4u(p + rs), wd = ld4u(p + 2 * rs);
+                    v0 = clamp_u8((hpf4(byte_of(wa, 0), byte_of(wb, 0), byte_of(wc, 0), byte_of(wd, 0)) + 8) >> 4);
+                    v1 = clamp_u8((hpf4(byte_of(wa, 1), byte_of(wb, 1), byte_of(wc, 1), byte_of(wd, 1)) + 8) >> 4);
+                    v2 = clamp_u8((hpf4(byte_of(wa, 2), byte_of(wb, 2), byte_of(wc, 2), byte_of(wd, 2)) + 8) >> 4);
+                    v3 = clamp_u8((hpf4(byte_of(wa, 3), byte_of(wb, 3), byte_of(wc, 3), byte_of(wd, 3)) + 8) >> 4);
                 } else if (phase == 2) {
-                    v = clamp_u8((hpf4(p[-1], p[0], p[1], p[2]) + 8) >> 4);
+                    const unsigned wa = ld4u(p - 1), wb = ld4u(p + 3);
+                    const int b0 = byte_of(wa, 0), b1 = byte_of(wa, 1), b2 = byte_of(wa, 2), b3 = byte_of(wa, 3);
+                    const int b4 = byte_of(wb, 0), b5 = byte_of(wb, 1), b6 = byte_of(wb, 2);
+                    v0 = clamp_u8((hpf4(b0, b1, b2, b3) + 8) >> 4);
+                    v1 = clamp_u8((hpf4(b1, b2, b3, b4) + 8) >> 4);
+                    v2 = clamp_u8((hpf4(b2, b3, b4, b5) + 8) >> 4);
+                    v3 = clamp_u8((hpf4(b3, b4, b5, b6) + 8) >> 4);
                 } else {
-                    const int16_t *b = hbuf + k;
-                    v = clamp_u8((hpf4(b[0], b[cw], b[2 * cw], b[3 * cw]) + 128) >> 8);
+                    const int16_t *b = hbuf + ly * hstride + lx;
+                    const short4 ra = *reinterpret_cast<const short4 *>(b), rb = *reinterpret_cast<const short4 *>(b + hstride);
+                    const short4 rc = *reinterpret_cast<const short4 *>(b + 2 * hstride), rd = *reinterpret_cast<const short4 *>(b + 3 * hstride);
+                    v0 = clamp_u8((hpf4(ra.x, rb.x, rc.x, rd.x) + 128) >> 8);
+                    v1 = clamp_u8((hpf4(ra.y, rb.y, rc.y, rd.y) + 128) >> 8);
+                    v2 = clamp_u8((hpf4(ra.z, rb.z, rc.z, rd.z) + 128) >> 8);
+                    v3 = clamp_u8((hpf4(ra.w, rb.w, rc.w, rd.w) + 128) >> 8);
                 }
             } else {
+                unsigned w;
                 if (phase == 1) {
-                    v = (p[0] + p[rs] + 1) >> 1;
+                    w = avg_up_u8x4(ld4u(p), ld4u(p + rs));
+                    v0 = byte_of(w, 0); v1 = byte_of(w, 1); v2 = byte_of(w, 2); v3 = byte_of(w, 3);
                 } else if (phase == 2) {
-                    v = (p[0] + p[1] + 1) >> 1;
+                    w = avg_up_u8x4(ld4u(p), ld4u(p + 1));
+                    v0 = byte_of(w, 0); v1 = byte_of(w, 1); v2 = byte_of(w, 2); v3 = byte_of(w, 3);
                 } else {
-                    v = (p[0] + p[1] + p[rs] + p[rs + 1] + 2) >> 2;
+                    const unsigned wa = ld4u(p), wb = ld4u(p + 1), wc = ld4u(p + rs), wd = ld4u(p + rs + 1);
+                    v0 = (byte_of(wa, 0) + byte_of(wb, 0) + byte_of(wc, 0) + byte_of(wd, 0) + 2) >> 2;
+                    v1 = (byte_of(wa, 1) + byte_of(wb, 1) + byte_of(wc, 1) + byte_of(wd, 1) + 2) >> 2;
+                    v2 = (byte_of(wa, 2) + byte_of(wb, 2) + byte_of(wc, 2) + byte_of(wd, 2) + 2) >> 2;
+                    v3 = (byte_of(wa, 3) + byte_of(wb, 3) + byte_of(wc, 3) + byte_of(wd, 3) + 2) >> 2;
                 }
             }
-            if (P.pred) {
-                P.pred[(size_t) (y + ly) * P.pstride + x + lx] = (uint8_t) v;
-            }
-            const int cur = P.in[(size_t) (y + ly) * P.istride + x + lx];
-            P.out[(size_t) (y + ly) * P.ostride + x + lx] = a.mode == 1 ? clamp_u8(cur - v + 128) : clamp_u8(v + cur - 128);
+            bmc_store4(P, mode, x + lx, y + ly, imin(4, cw - lx), walign, v0, v1, v2, v3);
         }
         return;
     }
@@ -140,22 +215,25 @@ __global__ void __launch_bounds__(BMC_THREADS) bmc_kernel(const BmcArgs *args)
         }
     }
     __syncthreads();
-    for (int k = tid; k < npx; k += BMC_THREADS) {
-        const int ly = k / cw, lx = k - ly * cw;
-        int v;
-        if (whole) {
-            v = s_avg[0];
-        } else if (lx >= 2 * sbw || ly >= 2 * sbh) {
-            v = 0; /* odd edge blocks: the quadrants do not cover the last row/column (zeroed frame) */
-        } else {
-            const int q = (lx >= sbw ? 1 : 0) | (ly >= sbh ? 2 : 0);
-            v = (mv.submask & (1 << q)) ? s_avg[q] : r0[(ptrdiff_t) ly * P.rstride + lx];
+    for (int k = tid; k < (ch << wsh); k += BMC_THREADS) {
+        const int ly = k >> wsh, wx = k & wmask;
+        if (wx >= words) {
+            continue;
         }
-        if (P.pred) {
-            P.pred[(size_t) (y + ly) * P.pstride + x + lx] = (uint8_t) v;
+        int v[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int lx = 4 * wx + e;
+            if (whole) {
+                v[e] = s_avg[0];
+            } else if (lx >= 2 * sbw || ly >= 2 * sbh) {
+                v[e] = 0; /* odd edge blocks: the quadrants do not cover the last row/column (zeroed frame) */
+            } else {
+                const int q = (lx >= sbw ? 1 : 0) | (ly >= sbh ? 2 : 0);
+                v[e] = (mv.submask & (1 << q)) ? s_avg[q] : (lx < cw ? (int) r0[(ptrdiff_t) ly * P.rstride + lx] : 0);
+            }
         }
-        const int cur = P.in[(size_t) (y + ly) * P.istride + x + lx];
-        P.out[(size_t) (y + ly) * P.ostride + x + lx] = a.mode == 1 ? clamp_u8(cur - v + 128) : clamp_u8(v + cur - 128);
+        bmc_store4(P, mode, x + 4 * wx, y + ly, imin(4, cw - 4 * wx), walign, v[0], v[1], v[2], v[3]);
     }
 }
 

@@ -21,6 +21,25 @@
     type *name = reinterpret_cast<type *>(dsv_dyn_smem_)
 #endif
 
+/* asynchronous global -> shared copies (LDGSTS): issue early, wait once (cp.async; the emulator copies at once) */
+#ifndef DSV_CPU_EMU
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
+{
+    unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+#else
+static inline void cp_async16(void *smem, const void *gmem) { memcpy(smem, gmem, 16); }
+static inline void cp_async4(void *smem, const void *gmem) { memcpy(smem, gmem, 4); }
+static inline void cp_async_wait_all() {}
+#endif
+
 #define DSV_HD __host__ __device__ __forceinline__
 #define DSV_D __device__ __forceinline__
 
@@ -127,6 +146,27 @@ DSV_HD int dz_dequant(int v, int q)
 /* top level: shift of the magnitude (hzcc.c:114-135) */
 DSV_HD int p2_quant(int v, int s) { return v < 0 ? -((-v) >> s) : (v >> s); }
 DSV_HD int p2_dequant(int v, int s) { return (int) ((unsigned) v << s); }
+
+/* 4 bytes at an arbitrary address: two aligned loads + funnel shift (any address space); reads up to 3 bytes
+ * past p + 3, which every frame allocation covers with its guard band */
+DSV_D unsigned ld4u(const uint8_t *p)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned *q = reinterpret_cast<const unsigned *>(a & ~(uintptr_t) 3);
+    const unsigned sh = (unsigned) (a & 3) * 8;
+    const unsigned lo = q[0];
+    if (sh == 0) {
+        return lo;
+    }
+    return __funnelshift_r(lo, q[1], sh);
+}
+DSV_HD int byte_of(unsigned w, int i) { return (int) ((w >> (8 * i)) & 0xff); }
+DSV_HD unsigned pack_u8x4(int a, int b, int c, int d)
+{
+    return (unsigned) clamp_u8(a) | ((unsigned) clamp_u8(b) << 8) | ((unsigned) clamp_u8(c) << 16) | ((unsigned) clamp_u8(d) << 24);
+}
+/* per-byte (a + b + 1) >> 1 */
+DSV_HD unsigned avg_up_u8x4(unsigned a, unsigned b) { return (a | b) - (((a ^ b) >> 1) & 0x7f7f7f7fu); }
 
 /* Reference frame geometry (frame.c:63-120): 64-sample border, stride rounded up to 16 */
 #define DSV_BORDER 64

@@ -59,6 +59,17 @@ struct SumItem { /* sum of all samples -> *out (zeroed by the host side of the l
     PlaneRef src;
     unsigned long long *out;
 };
+struct ZeroItem { /* clear `bytes` bytes at p (16-byte aligned): done by a kernel, NOT cudaMemsetAsync, because memsets
+                    run on a copy engine and would queue behind the large PCIe transfers of the copy stream */
+    void *p;
+    size_t bytes;
+};
+struct CopyItem { /* control-plane data moved by SMs through mapped pinned host memory (zero copy): the DMA engines stay
+                    free for the bulk picture traffic of the copy stream, behind which engine copies would queue */
+    void *dst;
+    const void *src;
+    size_t bytes;
+};
 struct ReconItem { /* dst = clamp(a + b - 128) (b.p == null: dst = a), border of dst replicated */
     PlaneRef a, b, dst;
 };
@@ -93,6 +104,11 @@ void extend_launch(const PlaneRef *d_items, int n, int max_w, int max_h, cudaStr
 void down2_launch(const Down2Item *d_items, int n, int max_w, int max_h, cudaStream_t st);
 void sum_launch(const SumItem *d_items, int n, int max_h, cudaStream_t st);
 void recon_launch(const ReconItem *d_items, int n, int max_w, int max_h, cudaStream_t st);
+void zero_launch(const ZeroItem *d_items, int n, size_t max_bytes, cudaStream_t st);
+/* items may live in mapped pinned host memory; one of dst/src of every item is device memory, the other may be
+ * mapped pinned host memory */
+void copy_launch(const CopyItem *items, int n, size_t max_bytes, cudaStream_t st);
+void copy1_launch(void *dst, const void *src, size_t bytes, cudaStream_t st);
 
 /* single-frame conveniences used by the kernel-level API (kernel_api.cu) */
 void frame_extend_launch(const DevFrame &f, int nplanes, cudaStream_t st);

@@ -72,7 +72,7 @@ void StepArena::upload(cudaStream_t st)
 {
     if (used > uploaded) {
         const size_t from = uploaded & ~(size_t) 15;
-        CUDA_CHECK(cudaMemcpyAsync(d + from, h + from, used - from, cudaMemcpyHostToDevice, st));
+        copy1_launch(d + from, h + from, used - from, st); /* SM copy from mapped pinned memory, see CopyItem */
         uploaded = used;
     }
 }
@@ -268,6 +268,95 @@ __global__ void __launch_bounds__(FO_BX *FO_BY) recon_kernel(const ReconItem *it
             const int sx = iclamp(x, 0, D.w - 1);
             dst[e] = b ? clamp_u8((int) a[sx] + (int) b[sx] - 128) : a[sx];
         }
+    }
+}
+
+#define ZERO_PER_CTA (256 * 16 * 8)
+__global__ void __launch_bounds__(256) zero_kernel(const ZeroItem *items)
+{
+    const ZeroItem it = items[blockIdx.y];
+    const size_t base = (size_t) blockIdx.x * ZERO_PER_CTA;
+    uint8_t *p = reinterpret_cast<uint8_t *>(it.p);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const size_t off = base + ((size_t) k * 256 + threadIdx.x) * 16;
+        if (off + 16 <= it.bytes) {
+            *reinterpret_cast<uint4 *>(p + off) = make_uint4(0, 0, 0, 0);
+        } else if (off < it.bytes) {
+            for (size_t e = off; e < it.bytes; e++) {
+                p[e] = 0;
+            }
+        }
+    }
+}
+
+void zero_launch(const ZeroItem *d_items, int n, size_t max_bytes, cudaStream_t st)
+{
+    if (n > 0 && max_bytes > 0) {
+        DSV_LAUNCH(zero_kernel, dim3((unsigned) ((max_bytes + ZERO_PER_CTA - 1) / ZERO_PER_CTA), n), dim3(256), 0, st, d_items);
+        KERNEL_CHECK();
+    }
+}
+
+#define COPY_PER_CTA (256 * 16 * 4)
+/* chunks are aligned to the DESTINATION (16-byte stores, important when it is host memory across PCIe); the source
+ * is read with whatever alignment it has */
+DSV_D void copy_span(uint8_t *dst, const uint8_t *src, size_t bytes, size_t base)
+{
+    const size_t lead = (size_t) ((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15);
+    const bool src_al = ((reinterpret_cast<uintptr_t>(src) + lead) & 15) == 0;
+    if (base == 0 && threadIdx.x == 0) {
+        for (size_t e = 0; e < lead && e < bytes; e++) {
+            dst[e] = src[e];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const size_t off = lead + base + ((size_t) k * 256 + threadIdx.x) * 16;
+        if (off >= bytes) {
+            return;
+        }
+        if (off + 16 <= bytes) {
+            uint4 v;
+            if (src_al) {
+                v = *reinterpret_cast<const uint4 *>(src + off);
+            } else {
+                v = make_uint4(ld4u(src + off), ld4u(src + off + 4), ld4u(src + off + 8), ld4u(src + off + 12));
+            }
+            *reinterpret_cast<uint4 *>(dst + off) = v;
+        } else {
+            for (size_t e = off; e < bytes; e++) {
+                dst[e] = src[e];
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(256) copy_kernel(const CopyItem *items)
+{
+    const CopyItem it = items[blockIdx.y];
+    copy_span(reinterpret_cast<uint8_t *>(it.dst), reinterpret_cast<const uint8_t *>(it.src), it.bytes, (size_t) blockIdx.x * COPY_PER_CTA);
+}
+__global__ void __launch_bounds__(256) copy1_kernel(CopyItem it)
+{
+    copy_span(reinterpret_cast<uint8_t *>(it.dst), reinterpret_cast<const uint8_t *>(it.src), it.bytes, (size_t) blockIdx.x * COPY_PER_CTA);
+}
+
+void copy_launch(const CopyItem *items, int n, size_t max_bytes, cudaStream_t st)
+{
+    if (n > 0 && max_bytes > 0) {
+        DSV_LAUNCH(copy_kernel, dim3((unsigned) ((max_bytes + COPY_PER_CTA - 1) / COPY_PER_CTA), n), dim3(256), 0, st, items);
+        KERNEL_CHECK();
+    }
+}
+void copy1_launch(void *dst, const void *src, size_t bytes, cudaStream_t st)
+{
+    if (bytes > 0) {
+        CopyItem it;
+        it.dst = dst;
+        it.src = src;
+        it.bytes = bytes;
+        DSV_LAUNCH(copy1_kernel, dim3((unsigned) ((bytes + COPY_PER_CTA - 1) / COPY_PER_CTA)), dim3(256), 0, st, it);
+        KERNEL_CHECK();
     }
 }
 

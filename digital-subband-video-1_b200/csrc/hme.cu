@@ -31,19 +31,6 @@ namespace dsv {
 #define HP_STRIDE 32
 
 
-/* 4 bytes at an arbitrary address: two aligned loads + funnel shift (generic address space) */
-DSV_D unsigned ld4u(const uint8_t *p)
-{
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const unsigned *q = reinterpret_cast<const unsigned *>(a & ~(uintptr_t) 3);
-    const unsigned sh = (unsigned) (a & 3) * 8;
-    const unsigned lo = q[0];
-    if (sh == 0) {
-        return lo;
-    }
-    return __funnelshift_r(lo, q[1], sh);
-}
-
 template <int N> DSV_D void block_reduce_n(unsigned (&acc)[N], unsigned *scratch /* >= 8 * N */)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;

@@ -39,6 +39,17 @@ struct DSVB_DEC {
 
 static void use_device(int device) { CUDA_CHECK(cudaSetDevice(device)); }
 
+/* pinned (cudaMallocHost / cudaHostRegister) host memory is addressable by kernels under UVA */
+static int host_mapped(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 static void apply_cfg(DSV_ENCODER *enc, const int *cfg)
 {
     DSV_META md;
@@ -142,7 +153,7 @@ extern "C" int dsvb_encode(DSVB_ENC *e, int nseq, int nframes, const uint8_t *co
     const int L = e->lanes;
     int rc = 0;
     std::vector<int> ids((size_t) L);
-    std::vector<PicRef> src((size_t) L);
+    std::vector<PicRef> src((size_t) L), next((size_t) L);
     std::vector<PktSink> sinks((size_t) L);
     std::vector<int> nb((size_t) L);
     std::vector<DSV_BUF> bufs((size_t) 2 * L);
@@ -156,16 +167,29 @@ extern "C" int dsvb_encode(DSVB_ENC *e, int nseq, int nframes, const uint8_t *co
             sinks[(size_t) k].at = streams[base + k];
             sinks[(size_t) k].room = (size_t) caps[base + k];
             sinks[(size_t) k].overflow = 0;
+            sinks[(size_t) k].mapped = host_mapped(streams[base + k]);
         }
-        for (int t = 0; t < nframes; t++) {
+        auto pictures = [&](int t, std::vector<PicRef> &dst) {
             for (int k = 0; k < n; k++) {
                 const uint8_t *f = yuv[base + k] + (size_t) t * g.frame_bytes;
                 for (int p = 0; p < 3; p++) {
-                    src[(size_t) k].plane[p] = f + g.plane_off[p];
-                    src[(size_t) k].stride[p] = g.pw[p];
+                    dst[(size_t) k].plane[p] = f + g.plane_off[p];
+                    dst[(size_t) k].stride[p] = g.pw[p];
                 }
-                src[(size_t) k].on_device = on_device;
+                dst[(size_t) k].on_device = on_device;
             }
+        };
+        /* host pictures: picture t+1 crosses PCIe on the copy stream while picture t is being encoded */
+        if (!on_device && nframes > 0) {
+            pictures(0, next);
+            e->eng->prefetch(n, ids.data(), next.data());
+        }
+        for (int t = 0; t < nframes; t++) {
+            if (!on_device && t + 1 < nframes) {
+                pictures(t + 1, next);
+                e->eng->prefetch(n, ids.data(), next.data());
+            }
+            pictures(t, src);
             e->eng->step(n, ids.data(), src.data(), reinterpret_cast<DSV_BUF(*)[2]>(bufs.data()), nb.data(), sinks.data());
         }
         for (int k = 0; k < n; k++) {
@@ -361,6 +385,9 @@ extern "C" int dsvb_decode(DSVB_DEC *d, int nseq, const uint8_t *const *streams,
                 }
             }
         }
+    }
+    if (d->eng) {
+        d->eng->flush(); /* the last pictures are still leaving on the copy stream */
     }
     return rc;
 }

@@ -78,6 +78,12 @@ static void read_motion(BitReader &br, const uint8_t *pkt, unsigned pkt_len, Dev
 
 namespace dsv {
 
+static bool host_packed(const CodecGeom &g, const OutRef &r)
+{
+    return !r.on_device && r.plane[0] && r.stride[0] == g.pw[0] && r.stride[1] == g.pw[1] && r.stride[2] == g.pw[2] &&
+           r.plane[1] == r.plane[0] + g.plane_off[1] && r.plane[2] == r.plane[0] + g.plane_off[2];
+}
+
 DecEngine::DecEngine(const DSV_META &md, int lanes)
 {
     CUDA_CHECK(cudaGetDevice(&device));
@@ -87,17 +93,24 @@ DecEngine::DecEngine(const DSV_META &md, int lanes)
     max_nblk_ = g.nblk;
     L_ = lanes;
     CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&st_copy_, cudaStreamNonBlocking));
     for (auto &e : ev_) {
         CUDA_CHECK(cudaEventCreate(&e));
     }
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_done_, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_copied_[0], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_copied_[1], cudaEventDisableTiming));
     /* a picture packet holds three planes of at most 2 * 4 * cw * ch bytes each (dsv_decoder.c:397-401) */
     pkt_cap_ = g.coef_total * 8 + 4096 + (size_t) g.nblk * 64;
-    const size_t per_lane = 3 * (sizeof(SbtJob) + hzdec_job_size()) + sizeof(BmcArgs) + 8 * sizeof(PlaneRef) + 3 * sizeof(PackItem) + 1024;
+    const size_t per_lane = 3 * (sizeof(SbtJob) + hzdec_job_size()) + sizeof(BmcArgs) + 8 * sizeof(PlaneRef) + 3 * sizeof(PackItem) + sizeof(ZeroItem) + sizeof(CopyItem) + 1024;
     arena_.create(per_lane * (size_t) L_ + 4096);
     CUDA_CHECK(cudaMalloc(&d_mv_, sizeof(DevMV) * (size_t) max_nblk_ * L_));
     CUDA_CHECK(cudaMallocHost(&h_mv_, sizeof(DevMV) * (size_t) max_nblk_ * L_));
     CUDA_CHECK(cudaMalloc(&d_stab_, (size_t) max_nblk_ * L_));
     CUDA_CHECK(cudaMallocHost(&h_stab_, (size_t) max_nblk_ * L_));
+    out_pitch_ = (g.frame_bytes + 255) & ~(size_t) 255;
+    CUDA_CHECK(cudaMalloc(&d_out_all_[0], out_pitch_ * L_ + 256));
+    CUDA_CHECK(cudaMalloc(&d_out_all_[1], out_pitch_ * L_ + 256));
     lanes_.resize((size_t) L_);
     for (auto &l : lanes_) {
         CUDA_CHECK(cudaMalloc(&l.coef, g.coef_total * sizeof(int32_t)));
@@ -118,6 +131,7 @@ DecEngine::DecEngine(const DSV_META &md, int lanes)
 DecEngine::~DecEngine()
 {
     cudaStreamSynchronize(st_);
+    cudaStreamSynchronize(st_copy_);
     for (auto &l : lanes_) {
         cudaFree(l.coef);
         for (int p = 0; p < 3; p++) {
@@ -130,6 +144,8 @@ DecEngine::~DecEngine()
         cudaFreeHost(l.h_pkt);
     }
     arena_.destroy();
+    cudaFree(d_out_all_[0]);
+    cudaFree(d_out_all_[1]);
     cudaFree(d_mv_);
     cudaFreeHost(h_mv_);
     cudaFree(d_stab_);
@@ -137,8 +153,14 @@ DecEngine::~DecEngine()
     for (auto &e : ev_) {
         cudaEventDestroy(e);
     }
+    cudaEventDestroy(ev_done_);
+    cudaEventDestroy(ev_copied_[0]);
+    cudaEventDestroy(ev_copied_[1]);
+    cudaStreamDestroy(st_copy_);
     cudaStreamDestroy(st_);
 }
+
+void DecEngine::flush() { CUDA_CHECK(cudaStreamSynchronize(st_copy_)); }
 
 void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRef *out, int *codes, DSV_FNUM *fnums)
 {
@@ -154,6 +176,13 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
     BmcArgs *ba = arena_.push_n<BmcArgs>((size_t) n, &d_bmc);
     PlaneRef *ext = arena_.push_n<PlaneRef>((size_t) 3 * n, &d_ext);
     PackItem *pack = arena_.push_n<PackItem>((size_t) 3 * n, &d_pack);
+    ZeroItem *d_zero;
+    ZeroItem *zero = arena_.push_n<ZeroItem>((size_t) n, &d_zero);
+    int n_zero = 0;
+    CopyItem *d_cpy;
+    CopyItem *cpy = arena_.push_n<CopyItem>((size_t) n, &d_cpy);
+    int n_cpy = 0;
+    size_t max_cpy = 0;
     HzDecDims dims;
     int n_sj = 0, n_p = 0, n_ext = 0, n_pack = 0;
     int blk_w = 0, blk_h = 0, nbh = 0, nbv = 0;
@@ -209,11 +238,15 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
         } else {
             if (!l.d_pkt) {
                 CUDA_CHECK(cudaMalloc(&l.d_pkt, pkt_cap_ + 64));
-                CUDA_CHECK(cudaMallocHost(&l.h_pkt, pkt_cap_ + 64));
+                CUDA_CHECK(cudaMallocHost(&l.h_pkt, pkt_cap_ + 80));
             }
             memcpy(l.h_pkt, pkt, pkt_len);
             memset(l.h_pkt + pkt_len, 0, 64);
-            CUDA_CHECK(cudaMemcpyAsync(l.d_pkt, l.h_pkt, (size_t) pkt_len + 64, cudaMemcpyHostToDevice, st));
+            cpy[n_cpy].dst = l.d_pkt;
+            cpy[n_cpy].src = l.h_pkt;
+            cpy[n_cpy].bytes = ((size_t) pkt_len + 64 + 15) & ~(size_t) 15;
+            max_cpy = max_cpy > cpy[n_cpy].bytes ? max_cpy : cpy[n_cpy].bytes;
+            n_cpy++;
             stats.h2d_bytes += pkt_len;
             d_pkt = l.d_pkt;
         }
@@ -280,6 +313,11 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
                 pack[n_pack].src = plane_ref(cur, p);
                 pack[n_pack].dst = out[k].plane[p];
                 n_pack++;
+            } else if (out[k].plane[p] && host_packed(g, out[k])) {
+                /* host destination, packed layout: pack on the device, one contiguous copy later */
+                pack[n_pack].src = plane_ref(cur, p);
+                pack[n_pack].dst = d_out_all_[step_no_ & 1] + out_pitch_ * li + g.plane_off[p];
+                n_pack++;
             }
         }
         if (isP) {
@@ -288,41 +326,84 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
         }
         /* dsv_decoder.c:405: coefficient planes start zeroed.  Planes that were never coded (corrupt plen) stay
          * all-zero here; the reference leaves the zeroed residual plane untouched instead. */
-        CUDA_CHECK(cudaMemsetAsync(l.coef, 0, g.coef_total * sizeof(int32_t), st));
+        zero[n_zero].p = l.coef;
+        zero[n_zero].bytes = g.coef_total * sizeof(int32_t);
+        n_zero++;
     }
     if (n_sj == 0) {
         CUDA_CHECK(cudaStreamSynchronize(st));
         return;
     }
     const SbtDims sdims = sbt_assign_tiles(sj, n_sj);
-    arena_.upload(st);
-    CUDA_CHECK(cudaMemcpyAsync(d_stab_, h_stab_, (size_t) max_nblk_ * L_, cudaMemcpyHostToDevice, st));
-    if (n_p) {
-        CUDA_CHECK(cudaMemcpyAsync(d_mv_, h_mv_, sizeof(DevMV) * (size_t) max_nblk_ * L_, cudaMemcpyHostToDevice, st));
+    /* pictures of earlier steps may still be leaving on the copy stream: the frame buffers written now were read
+     * by the copies of step t-2 (references alternate), or of step t-1 where that step had non-reference pictures */
+    CUDA_CHECK(cudaStreamWaitEvent(st, ev_copied_[step_no_ & 1], 0));
+    if (prev_nonref_) {
+        CUDA_CHECK(cudaStreamWaitEvent(st, ev_copied_[(step_no_ ^ 1) & 1], 0));
     }
+    arena_.upload(st);
+    copy_launch(d_cpy, n_cpy, max_cpy, st);
+    copy1_launch(d_stab_, h_stab_, (size_t) max_nblk_ * L_, st);
+    if (n_p) {
+        copy1_launch(d_mv_, h_mv_, sizeof(DevMV) * (size_t) max_nblk_ * L_, st);
+    }
+    zero_launch(d_zero, n_zero, g_.coef_total * sizeof(int32_t), st);
     hzdec_launch_jobs(d_hzj, dims, st);
     sbt_inv_launch(d_sj, sdims, g_.lo_smem, st, ev_[0], ev_[1]);
     bmc_launch(d_bmc, n_p, nbh, nbv, st);
     extend_launch(d_ext, n_ext, g_.w, g_.h, st);
     pack_launch(d_pack, n_pack, g_.w, g_.h, st);
-    stats.kernel_launches += 10 + (n_p ? 1 : 0) + (n_ext ? 1 : 0) + (n_pack ? 1 : 0);
-    for (int k = 0; k < n; k++) {
-        DecLane &l = lanes_[(size_t) lane_ids[k]];
-        if (!l.ok) {
-            continue;
+    stats.kernel_launches += 14 + (n_p ? 1 : 0) + (n_ext ? 1 : 0) + (n_pack ? 1 : 0);
+    CUDA_CHECK(cudaEventRecord(ev_done_, st));
+    CUDA_CHECK(cudaStreamWaitEvent(st_copy_, ev_done_, 0));
+    bool nonref = false;
+    {
+        /* packed host destinations at a constant distance (the batch API): one strided copy for all lanes */
+        bool uniform = n > 0;
+        const ptrdiff_t delta = n > 1 && out[0].plane[0] && out[1].plane[0] ? out[1].plane[0] - out[0].plane[0] : (ptrdiff_t) g_.frame_bytes;
+        for (int k = 0; k < n && uniform; k++) {
+            uniform = lane_ids[k] == k && lanes_[(size_t) k].ok && host_packed(g_, out[k]) && out[k].plane[0] == out[0].plane[0] + delta * k;
         }
-        const DevFrame &cur = l.out[l.cur];
-        for (int p = 0; p < 3; p++) {
-            if (!out[k].plane[p] || (out[k].on_device && out[k].stride[p] == g_.pw[p])) {
-                continue; /* nowhere to put it, or packed by pack_kernel */
+        uniform = uniform && delta >= (ptrdiff_t) g_.frame_bytes;
+        uint8_t *stage = d_out_all_[step_no_ & 1];
+        if (uniform) {
+            CUDA_CHECK(cudaMemcpy2DAsync(out[0].plane[0], (size_t) delta, stage, out_pitch_, g_.frame_bytes, (size_t) n, cudaMemcpyDeviceToHost, st_copy_));
+            stats.d2h_bytes += g_.frame_bytes * (size_t) n;
+        }
+        for (int k = 0; k < n; k++) {
+            const int li = lane_ids[k];
+            DecLane &l = lanes_[(size_t) li];
+            if (!l.ok) {
+                continue;
             }
-            CUDA_CHECK(cudaMemcpy2DAsync(out[k].plane[p], (size_t) out[k].stride[p], cur.p[p], (size_t) cur.stride[p], (size_t) g_.pw[p],
-                                         (size_t) g_.ph[p], out[k].on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-            if (!out[k].on_device) {
-                stats.d2h_bytes += (size_t) g_.pw[p] * g_.ph[p];
+            nonref |= !l.is_ref;
+            if (uniform || !out[k].plane[0] || out[k].on_device) {
+                if (out[k].on_device) { /* strided device destination (not handled by pack_kernel) */
+                    const DevFrame &cur = l.out[l.cur];
+                    for (int p = 0; p < 3; p++) {
+                        if (out[k].plane[p] && out[k].stride[p] != g_.pw[p]) {
+                            CUDA_CHECK(cudaMemcpy2DAsync(out[k].plane[p], (size_t) out[k].stride[p], cur.p[p], (size_t) cur.stride[p], (size_t) g_.pw[p],
+                                                         (size_t) g_.ph[p], cudaMemcpyDeviceToDevice, st_copy_));
+                        }
+                    }
+                }
+                continue;
             }
+            if (host_packed(g_, out[k])) {
+                CUDA_CHECK(cudaMemcpyAsync(out[k].plane[0], stage + out_pitch_ * li, g_.frame_bytes, cudaMemcpyDeviceToHost, st_copy_));
+            } else { /* strided host frame (dsv_dec): straight from the bordered frame */
+                const DevFrame &cur = l.out[l.cur];
+                for (int p = 0; p < 3; p++) {
+                    CUDA_CHECK(cudaMemcpy2DAsync(out[k].plane[p], (size_t) out[k].stride[p], cur.p[p], (size_t) cur.stride[p], (size_t) g_.pw[p],
+                                                 (size_t) g_.ph[p], cudaMemcpyDeviceToHost, st_copy_));
+                }
+            }
+            stats.d2h_bytes += g_.frame_bytes;
         }
     }
+    CUDA_CHECK(cudaEventRecord(ev_copied_[step_no_ & 1], st_copy_));
+    prev_nonref_ = nonref;
+    step_no_++;
     CUDA_CHECK(cudaStreamSynchronize(st));
     {
         float ms = 0;
@@ -431,6 +512,7 @@ extern "C" int dsv_dec(DSV_DECODER *d, DSV_BUF *buffer, DSV_FRAME **out, DSV_FNU
     const int lane = 0;
     int code = DSV_DEC_ERROR;
     e->step(1, &lane, &pr, &o, &code, fn);
+    e->flush();
     if (code != DSV_DEC_OK) {
         dsv_frame_ref_dec(f);
         /* the reference frees the packet on every error path except the missing-reference one

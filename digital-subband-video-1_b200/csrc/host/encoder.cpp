@@ -360,11 +360,14 @@ EncEngine::EncEngine(const DSV_META &md, int gop, int pyramid_levels, int lanes)
     levels_ = pyramid_levels;
     L_ = lanes;
     CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&st_copy_, cudaStreamNonBlocking));
     for (auto &e : ev_) {
         CUDA_CHECK(cudaEventCreate(&e));
     }
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_pref_[0], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_pref_[1], cudaEventDisableTiming));
     const size_t per_lane = 3 * (sizeof(SbtJob) + sizeof(HzJob)) + sizeof(HzFrame) + (size_t) (levels_ + 1) * sizeof(HmeArgs) +
-                            sizeof(BmcArgs) + 16 * sizeof(ReconItem) + 2048;
+                            sizeof(BmcArgs) + 16 * sizeof(ReconItem) + 2 * sizeof(ZeroItem) + 2048;
     arena_.create(per_lane * (size_t) L_ + 4096);
     CUDA_CHECK(cudaMalloc(&d_mv0_, sizeof(DevMV) * (size_t) g_.nblk * L_));
     CUDA_CHECK(cudaMemset(d_mv0_, 0, sizeof(DevMV) * (size_t) g_.nblk * L_));
@@ -377,10 +380,16 @@ EncEngine::EncEngine(const DSV_META &md, int gop, int pyramid_levels, int lanes)
     CUDA_CHECK(cudaMalloc(&d_chunks_, sizeof(HzChunk) * (size_t) g_.total_chunks * L_));
     CUDA_CHECK(cudaMalloc(&d_frames_, sizeof(HzFrame) * (size_t) L_));
     CUDA_CHECK(cudaMallocHost(&h_frames_, sizeof(HzFrame) * (size_t) L_));
+    CUDA_CHECK(cudaMallocHost(&h_pk_, sizeof(CopyItem) * (size_t) L_));
+    in_pitch_ = (g_.frame_bytes + 255) & ~(size_t) 255;
+    CUDA_CHECK(cudaMalloc(&d_in_all_[0], in_pitch_ * L_ + 256));
+    CUDA_CHECK(cudaMalloc(&d_in_all_[1], in_pitch_ * L_ + 256));
     lanes_.resize((size_t) L_);
     for (int i = 0; i < L_; i++) {
         alloc_lane(lanes_[(size_t) i]);
         lanes_[(size_t) i].d_mvf[0] = d_mv0_ + (size_t) i * g_.nblk;
+        lanes_[(size_t) i].d_in[0] = d_in_all_[0] + in_pitch_ * i;
+        lanes_[(size_t) i].d_in[1] = d_in_all_[1] + in_pitch_ * i;
     }
 }
 
@@ -399,7 +408,6 @@ void EncEngine::alloc_lane(EncLane &l)
     const size_t pkt_cap = ub + 4096 + (size_t) g.nblk * 48;
     CUDA_CHECK(cudaMalloc(&l.d_pkt, pkt_cap));
     CUDA_CHECK(cudaMemset(l.d_pkt, 0, pkt_cap));
-    CUDA_CHECK(cudaMalloc(&l.d_in, g.frame_bytes + 64));
     CUDA_CHECK(cudaMallocHost(&l.h_head, 512 + (size_t) g.nblk * 48));
     devframe_alloc(&l.xf, g.w, g.h, g.subsamp);
     if (inter_) {
@@ -427,7 +435,6 @@ void EncEngine::free_lane(EncLane &l)
         cudaFree(l.dv[p]);
     }
     cudaFree(l.d_pkt);
-    cudaFree(l.d_in);
     cudaFreeHost(l.h_head);
     devframe_free(&l.xf);
     devframe_free(&l.pred);
@@ -451,6 +458,8 @@ EncEngine::~EncEngine()
         free_lane(l);
     }
     arena_.destroy();
+    cudaFree(d_in_all_[0]);
+    cudaFree(d_in_all_[1]);
     cudaFree(d_mv0_);
     cudaFreeHost(h_mv0_);
     cudaFree(d_stab_);
@@ -460,10 +469,71 @@ EncEngine::~EncEngine()
     cudaFree(d_chunks_);
     cudaFree(d_frames_);
     cudaFreeHost(h_frames_);
+    cudaFreeHost(h_pk_);
     for (auto &e : ev_) {
         cudaEventDestroy(e);
     }
+    cudaEventDestroy(ev_pref_[0]);
+    cudaEventDestroy(ev_pref_[1]);
+    cudaStreamDestroy(st_copy_);
     cudaStreamDestroy(st_);
+}
+
+static bool packed_pic(const CodecGeom &g, const PicRef &r)
+{
+    return r.stride[0] == g.pw[0] && r.stride[1] == g.pw[1] && r.stride[2] == g.pw[2] &&
+           r.plane[1] == r.plane[0] + g.plane_off[1] && r.plane[2] == r.plane[0] + g.plane_off[2];
+}
+
+void EncEngine::prefetch(int n, const int *lane_ids, const PicRef *src)
+{
+    const CodecGeom &g = g_;
+    bool used[2] = {false, false};
+    /* common case (the batch API): lanes 0..n-1, packed pictures at a constant distance from each other and all
+     * lanes on the same staging parity -> ONE strided copy for the whole step instead of 3n API calls */
+    bool uniform = n > 0 && !src[0].on_device;
+    const ptrdiff_t delta = n > 1 ? src[1].plane[0] - src[0].plane[0] : (ptrdiff_t) g.frame_bytes;
+    for (int k = 0; k < n && uniform; k++) {
+        uniform = lane_ids[k] == k && !src[k].on_device && packed_pic(g, src[k]) && lanes_[(size_t) k].in_sel == lanes_[0].in_sel &&
+                  src[k].plane[0] == src[0].plane[0] + delta * k;
+    }
+    if (uniform && delta >= (ptrdiff_t) g.frame_bytes) {
+        const int b = lanes_[0].in_sel;
+        CUDA_CHECK(cudaMemcpy2DAsync(d_in_all_[b], in_pitch_, src[0].plane[0], (size_t) delta, g.frame_bytes, (size_t) n, cudaMemcpyHostToDevice, st_copy_));
+        stats.h2d_bytes += g.frame_bytes * (size_t) n;
+        for (int k = 0; k < n; k++) {
+            EncLane &l = lanes_[(size_t) k];
+            l.stage_src[b] = src[k].plane[0];
+            l.in_sel ^= 1;
+        }
+        CUDA_CHECK(cudaEventRecord(ev_pref_[b], st_copy_));
+        return;
+    }
+    for (int k = 0; k < n; k++) {
+        EncLane &l = lanes_[(size_t) lane_ids[k]];
+        if (src[k].on_device) {
+            continue;
+        }
+        const int b = l.in_sel;
+        uint8_t *buf = l.d_in[b];
+        if (packed_pic(g, src[k])) {
+            CUDA_CHECK(cudaMemcpyAsync(buf, src[k].plane[0], g.frame_bytes, cudaMemcpyHostToDevice, st_copy_));
+        } else {
+            for (int p = 0; p < 3; p++) {
+                CUDA_CHECK(cudaMemcpy2DAsync(buf + g.plane_off[p], (size_t) g.pw[p], src[k].plane[p], (size_t) src[k].stride[p], (size_t) g.pw[p],
+                                             (size_t) g.ph[p], cudaMemcpyHostToDevice, st_copy_));
+            }
+        }
+        stats.h2d_bytes += g.frame_bytes;
+        l.stage_src[b] = src[k].plane[0];
+        l.in_sel ^= 1;
+        used[b] = true;
+    }
+    for (int b = 0; b < 2; b++) {
+        if (used[b]) {
+            CUDA_CHECK(cudaEventRecord(ev_pref_[b], st_copy_));
+        }
+    }
 }
 
 void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bufs)[2], int *nbufs, PktSink *sinks)
@@ -477,26 +547,50 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     /* ---- phase 1: ingest, pyramid, luma sums, motion search -------------------------------------- */
     IngestItem *d_ing;
     IngestItem *ing = arena_.push_n<IngestItem>((size_t) 3 * n, &d_ing);
+    bool wait_pref[2] = {false, false};
     for (int k = 0; k < n; k++) {
         EncLane &l = lanes_[(size_t) lane_ids[k]];
         l.fnum = l.enc->next_fnum++;
         const DevFrame &dst = inter_ ? l.pad[l.cur] : l.xf;
+        int pb = -1;
+        if (!src[k].on_device) {
+            pb = l.stage_src[0] == src[k].plane[0] ? 0 : (l.stage_src[1] == src[k].plane[0] ? 1 : -1);
+        }
+        const bool prefetched = pb >= 0;
+        if (prefetched) {
+            wait_pref[pb] = true;
+            l.stage_src[pb] = nullptr;
+        }
+        uint8_t *stage_buf = prefetched ? l.d_in[pb] : l.d_in[l.in_sel];
+        bool staged = false;
         for (int p = 0; p < 3; p++) {
             const uint8_t *packed;
             const size_t pbytes = (size_t) g.pw[p] * g.ph[p];
             if (src[k].on_device && src[k].stride[p] == g.pw[p]) {
                 packed = src[k].plane[p];
+            } else if (prefetched) {
+                packed = stage_buf + g.plane_off[p];
             } else {
-                uint8_t *stage = l.d_in + g.plane_off[p];
+                uint8_t *stage = stage_buf + g.plane_off[p];
                 CUDA_CHECK(cudaMemcpy2DAsync(stage, (size_t) g.pw[p], src[k].plane[p], (size_t) src[k].stride[p], (size_t) g.pw[p],
                                              (size_t) g.ph[p], src[k].on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
                 if (!src[k].on_device) {
                     stats.h2d_bytes += pbytes;
                 }
                 packed = stage;
+                staged = true;
             }
             ing[3 * k + p].src = packed;
             ing[3 * k + p].dst = plane_ref(dst, p);
+        }
+        if (staged) {
+            l.stage_src[l.in_sel] = nullptr;
+            l.in_sel ^= 1;
+        }
+    }
+    for (int b = 0; b < 2; b++) {
+        if (wait_pref[b]) {
+            CUDA_CHECK(cudaStreamWaitEvent(st, ev_pref_[b], 0));
         }
     }
     /* GOP bookkeeping (dsv_encoder.c:624-652): host state only */
@@ -567,6 +661,10 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
             }
         }
     }
+    ZeroItem *d_zmisc;
+    ZeroItem *zmisc = arena_.push_n<ZeroItem>(1, &d_zmisc);
+    zmisc->p = d_misc_;
+    zmisc->bytes = sizeof(LaneMisc) * (size_t) L_;
     arena_.upload(st);
     ingest_launch(d_ing, 3 * n, g.w, g.h, st);
     stats.kernel_launches += 1;
@@ -577,7 +675,7 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         }
         stats.kernel_launches += (unsigned) levels_;
         if (n_sum || n_search) {
-            CUDA_CHECK(cudaMemsetAsync(d_misc_, 0, sizeof(LaneMisc) * (size_t) L_, st));
+            zero_launch(d_zmisc, 1, sizeof(LaneMisc) * (size_t) L_, st);
         }
         if (n_sum) {
             sum_launch(d_sum, n_sum, ceil_shift(g.h, levels_), st);
@@ -586,10 +684,10 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         if (n_search) {
             hme_launch(d_hme, n_search, mg, st);
             stats.kernel_launches += (unsigned) levels_ + 2;
-            CUDA_CHECK(cudaMemcpyAsync(h_mv0_, d_mv0_, sizeof(DevMV) * (size_t) g.nblk * L_, cudaMemcpyDeviceToHost, st));
+            copy1_launch(h_mv0_, d_mv0_, sizeof(DevMV) * (size_t) g.nblk * L_, st);
         }
         if (n_sum || n_search) {
-            CUDA_CHECK(cudaMemcpyAsync(h_misc_, d_misc_, sizeof(LaneMisc) * (size_t) L_, cudaMemcpyDeviceToHost, st));
+            copy1_launch(h_misc_, d_misc_, sizeof(LaneMisc) * (size_t) L_, st);
             need_sync = true;
         }
     }
@@ -664,6 +762,10 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     ReconItem *rec = n_p ? arena_.push_n<ReconItem>((size_t) 3 * n_p, &d_rec) : nullptr;
     PlaneRef *ext = n_i_ref > 0 ? arena_.push_n<PlaneRef>((size_t) 3 * n_i_ref, &d_ext) : nullptr;
     int qp = 0, qi = 0;
+    ZeroItem *d_zero;
+    ZeroItem *zero = arena_.push_n<ZeroItem>((size_t) n, &d_zero);
+    int n_zero = 0;
+    size_t max_zero = 0;
     for (int k = 0; k < n; k++) {
         const int li = lane_ids[k];
         EncLane &l = lanes_[(size_t) li];
@@ -674,7 +776,10 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
             bmc_fill_args(&ba[qp], mg, l.d_mvf[0], l.recon[l.cur ^ 1], &l.pred, l.pad[l.cur], l.xf, 1);
         }
         if (l.pkt_dirty) {
-            CUDA_CHECK(cudaMemsetAsync(l.d_pkt, 0, (size_t) l.pkt_dirty + 64, st));
+            zero[n_zero].p = l.d_pkt;
+            zero[n_zero].bytes = ((size_t) l.pkt_dirty + 64 + 15) & ~(size_t) 15;
+            max_zero = max_zero > zero[n_zero].bytes ? max_zero : zero[n_zero].bytes;
+            n_zero++;
         }
         for (int p = 0; p < 3; p++) {
             SbtJob &s = sj[3 * k + p];
@@ -732,8 +837,9 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     }
     const SbtDims sdims = sbt_assign_tiles(sj, 3 * n);
     arena_.upload(st);
-    CUDA_CHECK(cudaMemcpyAsync(d_stab_, h_stab_, (size_t) g.nblk * L_, cudaMemcpyHostToDevice, st));
-    CUDA_CHECK(cudaMemcpyAsync(d_hf, h_frames_, sizeof(HzFrame) * (size_t) n, cudaMemcpyHostToDevice, st));
+    copy1_launch(d_stab_, h_stab_, (size_t) g.nblk * L_, st);
+    copy1_launch(d_hf, h_frames_, sizeof(HzFrame) * (size_t) n, st);
+    zero_launch(d_zero, n_zero, max_zero, st);
     if (n_p) {
         bmc_launch(d_bmc, n_p, g.nbh, g.nbv, st);
         stats.kernel_launches += 1;
@@ -741,7 +847,7 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     sbt_fwd_launch(d_sj, sdims, g.lo_smem, st, ev_[0], ev_[1]);
     hzcc_enc_launch(d_hj, 3 * n, d_chunks_, n * g.total_chunks, d_hf, n, st);
     stats.kernel_launches += 6;
-    CUDA_CHECK(cudaMemcpyAsync(h_frames_, d_hf, sizeof(HzFrame) * (size_t) n, cudaMemcpyDeviceToHost, st));
+    copy1_launch(h_frames_, d_hf, sizeof(HzFrame) * (size_t) n, st);
     CUDA_CHECK(cudaEventRecord(ev_[4], st));
     if (n_ref) {
         /* closed loop: reconstruct exactly what the decoder will (dsv_encoder.c:525,662-674) */
@@ -751,6 +857,9 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         stats.kernel_launches += 3 + (n_p ? 1 : 0) + (n_i_ref > 0 ? 1 : 0);
     }
     CUDA_CHECK(cudaEventSynchronize(ev_[4])); /* packet sizes are known; reconstruction keeps running */
+    CopyItem *pk = reinterpret_cast<CopyItem *>(h_pk_); /* mapped pinned: read by the copy kernel in place */
+    int n_pk = 0;
+    size_t max_pk = 0;
 
     for (int k = 0; k < n; k++) {
         EncLane &l = lanes_[(size_t) lane_ids[k]];
@@ -796,13 +905,22 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         }
         if (outbuf.data) {
             memcpy(outbuf.data, l.h_head, l.head_bytes);
-            CUDA_CHECK(cudaMemcpyAsync(outbuf.data + l.head_bytes, l.d_pkt + l.head_bytes, total - l.head_bytes, cudaMemcpyDeviceToHost, st));
+            if (sinks && sinks[k].mapped) {
+                pk[n_pk].dst = outbuf.data + l.head_bytes;
+                pk[n_pk].src = l.d_pkt + l.head_bytes;
+                pk[n_pk].bytes = total - l.head_bytes;
+                max_pk = max_pk > pk[n_pk].bytes ? max_pk : pk[n_pk].bytes;
+                n_pk++;
+            } else {
+                CUDA_CHECK(cudaMemcpyAsync(outbuf.data + l.head_bytes, l.d_pkt + l.head_bytes, total - l.head_bytes, cudaMemcpyDeviceToHost, st));
+            }
             stats.d2h_bytes += total - l.head_bytes;
         }
         l.pkt_dirty = total;
         bufs[k][nb++] = outbuf;
         nbufs[k] = nb;
     }
+    copy_launch(pk, n_pk, max_pk, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
     {
         float ms = 0;

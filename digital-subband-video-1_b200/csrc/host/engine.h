@@ -63,7 +63,9 @@ struct EncLane {
     DevMV *d_mvf[DSV_MAX_PYRAMID_LEVELS + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int2 *d_aux = nullptr;
     int32_t *coef = nullptr, *llx[3] = {nullptr, nullptr, nullptr}, *dv[3] = {nullptr, nullptr, nullptr};
-    uint8_t *d_pkt = nullptr, *d_in = nullptr;
+    uint8_t *d_pkt = nullptr, *d_in[2] = {nullptr, nullptr};
+    int in_sel = 0;                 /* staging buffer the next inline copy / prefetch writes */
+    const uint8_t *stage_src[2] = {nullptr, nullptr}; /* host picture on its way into / held by each staging buffer */
     unsigned pkt_dirty = 0;
     uint8_t *h_head = nullptr; /* pinned: packet head assembled on the host */
     /* per-step decisions */
@@ -77,6 +79,7 @@ struct PktSink {
     uint8_t *at;
     size_t room;
     int overflow;
+    int mapped; /* destination is mapped pinned host memory: packets leave through an SM copy kernel */
 };
 
 class EncEngine {
@@ -86,6 +89,8 @@ public:
     /* encode one picture on each of lane_ids[0..n): src[k] is that lane's input, bufs[k] receives 1 or 2
      * packets (metadata first), nbufs[k] their count */
     void step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bufs)[2], int *nbufs, PktSink *sinks = nullptr);
+    /* start copying the NEXT step's host pictures to the device on the copy stream while the current step computes */
+    void prefetch(int n, const int *lane_ids, const PicRef *src);
     /* attach a sequence's host state to a lane and forget the lane's references */
     void bind(int lane, DSV_ENCODER *enc)
     {
@@ -104,8 +109,9 @@ private:
     bool inter_;
     int levels_;
     int L_;
-    cudaStream_t st_ = 0;
+    cudaStream_t st_ = 0, st_copy_ = 0;
     cudaEvent_t ev_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_pref_[2] = {nullptr, nullptr}; /* per staging-buffer parity: prefetch copies done */
     std::vector<EncLane> lanes_;
     StepArena arena_;
     /* lane-major arrays shared by all lanes so that one copy moves every lane's data */
@@ -114,6 +120,9 @@ private:
     uint8_t *d_misc_ = nullptr, *h_misc_ = nullptr; /* per lane: u64 luma sum, i32 intra count, pad */
     HzChunk *d_chunks_ = nullptr;
     HzFrame *d_frames_ = nullptr, *h_frames_ = nullptr;
+    void *h_pk_ = nullptr; /* packet egress copy list (mapped pinned) */
+    uint8_t *d_in_all_[2] = {nullptr, nullptr}; /* packed-picture staging of all lanes, lane pitch in_pitch_ */
+    size_t in_pitch_ = 0;
 };
 
 struct DecLane {
@@ -147,6 +156,8 @@ public:
     /* decode one PICTURE packet on each of lane_ids[0..n); codes[k] = DSV_DEC_OK / DSV_DEC_ERROR, fnums[k] =
      * frame number; on OK the picture is written to out[k] */
     void step(int n, const int *lane_ids, const PktRef *pkts, const OutRef *out, int *codes, DSV_FNUM *fnums);
+    /* host-destined pictures leave on the copy stream while the next step computes: wait for all of them */
+    void flush();
     const CodecGeom &geom() const { return g_; }
     int lanes() const { return L_; }
     void reset_lane(int lane) { lanes_[(size_t) lane].have_ref = 0; }
@@ -159,12 +170,17 @@ private:
     int L_;
     int max_nblk_;
     size_t pkt_cap_;
-    cudaStream_t st_ = 0;
+    cudaStream_t st_ = 0, st_copy_ = 0;
     cudaEvent_t ev_[2] = {nullptr, nullptr};
+    cudaEvent_t ev_done_ = nullptr, ev_copied_[2] = {nullptr, nullptr};
+    unsigned long long step_no_ = 0;
+    bool prev_nonref_ = false;
     std::vector<DecLane> lanes_;
     StepArena arena_;
     DevMV *d_mv_ = nullptr, *h_mv_ = nullptr;
     uint8_t *d_stab_ = nullptr, *h_stab_ = nullptr;
+    uint8_t *d_out_all_[2] = {nullptr, nullptr}; /* packed-picture egress staging of all lanes (step parity) */
+    size_t out_pitch_ = 0;
 };
 
 bool meta_supported(const DSV_META &m);

@@ -75,3 +75,31 @@ def test_batch_hd_golden_device_resident(gpu):
     assert rc == 0 and fr == [n]
     assert hashlib.md5(d_out.cpu().numpy().tobytes()).hexdigest() == g["dec_md5"]
     assert st["h2d_bytes"] == 0 and st["d2h_bytes"] == 0   # nothing crossed PCIe for the pictures or the packets
+
+
+def test_batch_contiguous_host_buffers(gpu):
+    """Sequences back to back in ONE host buffer (constant distance): the single strided-copy ingest / egress path."""
+    w, h, fmt, n, nseq, lanes = 352, 288, "420", 7, 6, 4
+    sub = L.SUBSAMP[fmt]
+    fb = L.frame_bytes(w, h, sub)
+    cfg = L.make_cfg(w, h, fmt, gop=12)
+    big = np.concatenate([L.synth_sequence(w, h, fmt, n, 60 + s, 0) for s in range(nseq)])
+    want = [gpu.encode_sequence(cfg, big[s * n * fb:(s + 1) * n * fb], n)[0] for s in range(nseq)]
+    cap = 1 << 20
+    outs = np.zeros(nseq * cap, dtype=np.uint8)
+    be = L.BatchEncoder(gpu, cfg, lanes)
+    rc, lens = be.encode_ptrs([big.ctypes.data + s * n * fb for s in range(nseq)], n, 0,
+                              [outs.ctypes.data + s * cap for s in range(nseq)], [cap] * nseq)
+    be.close()
+    assert rc == 0
+    got = [outs[s * cap:s * cap + lens[s]].tobytes() for s in range(nseq)]
+    assert got == want
+    dec_all = np.zeros(nseq * n * fb, dtype=np.uint8)
+    bd = L.BatchDecoder(gpu, lanes)
+    rc, fr = bd.decode_ptrs([outs.ctypes.data + s * cap for s in range(nseq)], None, lens,
+                            [dec_all.ctypes.data + s * n * fb for s in range(nseq)], [n * fb] * nseq, 0)
+    bd.close()
+    assert rc == 0 and fr == [n] * nseq
+    for s in range(nseq):
+        nf, d, _, _ = gpu.decode_stream(want[s], w, h, sub, n)
+        assert np.array_equal(d, dec_all[s * n * fb:(s + 1) * n * fb])
