@@ -31,7 +31,9 @@ namespace dsv {
 #define HP_STRIDE 32
 
 
-template <int N> DSV_D void block_reduce_n(unsigned (&acc)[N], unsigned *scratch /* >= 8 * N */)
+/* block-wide sums of N per-thread values; every thread gets all totals.  scratch: >= 9 * N words.
+ * Stage 1: one REDUX per value per warp; stage 2: thread k adds the warp partials of value k. */
+template <int N> DSV_D void block_reduce_n(unsigned (&acc)[N], unsigned *scratch)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
@@ -46,13 +48,17 @@ template <int N> DSV_D void block_reduce_n(unsigned (&acc)[N], unsigned *scratch
         }
     }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < N; k++) {
+    if ((int) threadIdx.x < N) {
         unsigned t = 0;
         for (int w = 0; w < nw; w++) {
-            t += scratch[w * N + k];
+            t += scratch[w * N + threadIdx.x];
         }
-        acc[k] = t;
+        scratch[8 * N + threadIdx.x] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        acc[k] = scratch[8 * N + k];
     }
 }
 
@@ -213,7 +219,7 @@ __global__ void __launch_bounds__(HME_THREADS) hme_level_kernel(const HmeArgs *a
 {
     const HmeArgs &A = args[blockIdx.z];
     __shared__ __align__(16) uint8_t s_src[64 * HME_SRC_STRIDE];
-    __shared__ unsigned scratch[8 * 9];
+    __shared__ unsigned scratch[9 * 9];
     const int step = 1 << A.level;
     const int i = (int) blockIdx.x * step, j = (int) blockIdx.y * step;
     BlockGeom G;
@@ -246,7 +252,7 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
     const HmeArgs &A = args[blockIdx.z];
     __shared__ __align__(16) uint8_t s_src[64 * HME_SRC_STRIDE];
     __shared__ __align__(16) uint8_t s_ref0[64 * HME_SRC_STRIDE];
-    __shared__ unsigned scratch[8 * SUM_COUNT];
+    __shared__ unsigned scratch[9 * SUM_COUNT];
     __shared__ int16_t s_hbuf[(HP_DIM + 4) * HP_DIM];
     __shared__ uint8_t s_tmp[HP_STRIDE * HP_STRIDE];
     __shared__ uint8_t s_refblk[HP_SAD_SZ * HP_SAD_SZ];
@@ -348,62 +354,73 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
         sum[k] = 0;
     }
     const int sbw = G.bw / 2, sbh = G.bh / 2;
-    for (int k = tid; k < G.bw * G.bh; k += HME_THREADS) {
-        const int ly = k / G.bw, lx = k - ly * G.bw;
-        const uint8_t *sp = s_src + ly * HME_SRC_STRIDE + lx;
-        const uint8_t *rp = s_ref0 + ly * HME_SRC_STRIDE + lx;
-        const int pa = sp[0], pb = rp[0];
-        const int right = lx == G.bw - 1 ? pa : sp[1];
-        const int up = ly == 0 ? pa : sp[-HME_SRC_STRIDE];
-        sum[SUM_S] += (unsigned) pa;
-        sum[SUM_SS] += (unsigned) (pa * pa);
-        sum[SUM_SH] += (unsigned) iabs(pa - right);
-        sum[SUM_SV] += (unsigned) iabs(pa - up);
-        sum[SUM_RS] += (unsigned) pb;
-        sum[SUM_RSS] += (unsigned) (pb * pb);
-        if (lx < 2 * sbw && ly < 2 * sbh) { /* intra_metric on the four quadrants, hme.c:87-134 */
-            const int qxi = lx >= sbw, qyi = ly >= sbh;
-            const int qi = lx - qxi * sbw, qj = ly - qyi * sbh;
-            const int la = qi == 0 ? pa : sp[-1], lb = qi == 0 ? pb : rp[-1];
-            const int ua = qj == 0 ? pa : sp[-HME_SRC_STRIDE], ub = qj == 0 ? pb : rp[-HME_SRC_STRIDE];
-            unsigned good = (unsigned) (iabs(pa - la) + iabs(pa - ua) + iabs(pb - lb) + iabs(pb - ub));
-            unsigned evil = 0;
-            const int dif = iabs(pa - pb);
-            if (dif == 0) {
-                good += 192;
-            } else if (dif == 1) {
-                good += 128;
-            } else if (dif == 2) {
-                good += 96;
-            } else {
-                evil = (unsigned) dif;
+    const int lane = tid & 31, wid = tid >> 5;
+    /* rows go to warps, columns to lanes: the quadrant row is warp-uniform, no per-sample divisions */
+    for (int ly = wid; ly < G.bh; ly += HME_THREADS / 32) {
+        const int qyi = ly >= sbh;
+        const bool inq_y = ly < 2 * sbh;
+        const int qj = ly - qyi * sbh;
+        unsigned good0 = 0, good1 = 0, evil0 = 0, evil1 = 0;
+        for (int lx = lane; lx < G.bw; lx += 32) {
+            const uint8_t *sp = s_src + ly * HME_SRC_STRIDE + lx;
+            const uint8_t *rp = s_ref0 + ly * HME_SRC_STRIDE + lx;
+            const int pa = sp[0], pb = rp[0];
+            const int right = lx == G.bw - 1 ? pa : sp[1];
+            const int up = ly == 0 ? pa : sp[-HME_SRC_STRIDE];
+            sum[SUM_S] += (unsigned) pa;
+            sum[SUM_SS] += (unsigned) (pa * pa);
+            sum[SUM_SH] += (unsigned) iabs(pa - right);
+            sum[SUM_SV] += (unsigned) iabs(pa - up);
+            sum[SUM_RS] += (unsigned) pb;
+            sum[SUM_RSS] += (unsigned) (pb * pb);
+            if (inq_y && lx < 2 * sbw) { /* intra_metric on the four quadrants, hme.c:87-134 */
+                const int qxi = lx >= sbw;
+                const int qi = lx - qxi * sbw;
+                const int la = qi == 0 ? pa : sp[-1], lb = qi == 0 ? pb : rp[-1];
+                const int ua = qj == 0 ? pa : up, ub = qj == 0 ? pb : rp[-HME_SRC_STRIDE];
+                unsigned good = (unsigned) (iabs(pa - la) + iabs(pa - ua) + iabs(pb - lb) + iabs(pb - ub));
+                unsigned evil = 0;
+                const int dif = iabs(pa - pb);
+                if (dif > 2) {
+                    evil = (unsigned) dif;
+                } else {
+                    good += dif == 0 ? 192u : (dif == 1 ? 128u : 96u);
+                }
+                good0 += qxi ? 0u : good;
+                good1 += qxi ? good : 0u;
+                evil0 += qxi ? 0u : evil;
+                evil1 += qxi ? evil : 0u;
             }
-            const int q = qxi | (qyi << 1);
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                sum[SUM_GOOD0 + t] += q == t ? good : 0u;
-                sum[SUM_EVIL0 + t] += q == t ? evil : 0u;
-            }
+        }
+        if (qyi) {
+            sum[SUM_GOOD2] += good0; sum[SUM_GOOD3] += good1; sum[SUM_EVIL2] += evil0; sum[SUM_EVIL3] += evil1;
+        } else {
+            sum[SUM_GOOD0] += good0; sum[SUM_GOOD1] += good1; sum[SUM_EVIL0] += evil0; sum[SUM_EVIL1] += evil1;
         }
     }
     { /* chroma variance inputs, c_maxvar hme.c:270-300 */
         const int cbx = i * (A.blk_w >> A.hs), cby = j * (A.blk_h >> A.vs);
         const int cbw = G.bw >> A.hs, cbh = G.bh >> A.vs;
-        for (int k = tid; k < cbw * cbh; k += HME_THREADS) {
-            const int ly = k / cbw, lx = k - ly * cbw;
-            unsigned p;
-            p = A.srcU.p[(ptrdiff_t) (cby + ly) * A.srcU.stride + cbx + lx];
-            sum[SUM_CSU] += p;
-            sum[SUM_CSSU] += p * p;
-            p = A.srcV.p[(ptrdiff_t) (cby + ly) * A.srcV.stride + cbx + lx];
-            sum[SUM_CSV] += p;
-            sum[SUM_CSSV] += p * p;
-            p = A.refU.p[(ptrdiff_t) (cby + ly) * A.refU.stride + cbx + lx];
-            sum[SUM_CRU] += p;
-            sum[SUM_CRSU] += p * p;
-            p = A.refV.p[(ptrdiff_t) (cby + ly) * A.refV.stride + cbx + lx];
-            sum[SUM_CRV] += p;
-            sum[SUM_CRSV] += p * p;
+        for (int ly = wid; ly < cbh; ly += HME_THREADS / 32) {
+            const uint8_t *su = A.srcU.p + (ptrdiff_t) (cby + ly) * A.srcU.stride + cbx;
+            const uint8_t *sv = A.srcV.p + (ptrdiff_t) (cby + ly) * A.srcV.stride + cbx;
+            const uint8_t *ru = A.refU.p + (ptrdiff_t) (cby + ly) * A.refU.stride + cbx;
+            const uint8_t *rv = A.refV.p + (ptrdiff_t) (cby + ly) * A.refV.stride + cbx;
+            for (int lx = lane; lx < cbw; lx += 32) {
+                unsigned p;
+                p = su[lx];
+                sum[SUM_CSU] += p;
+                sum[SUM_CSSU] += p * p;
+                p = sv[lx];
+                sum[SUM_CSV] += p;
+                sum[SUM_CSSV] += p * p;
+                p = ru[lx];
+                sum[SUM_CRU] += p;
+                sum[SUM_CRSU] += p * p;
+                p = rv[lx];
+                sum[SUM_CRV] += p;
+                sum[SUM_CRSV] += p * p;
+            }
         }
     }
     if (tid < HP_SAD_SZ * HP_SAD_SZ) { /* block_texture on the two 14x14 patches, hme.c:179-209 */
@@ -434,11 +451,12 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
     __syncthreads();
     {
         int bad = 0;
-        for (int k = tid; k < G.bw * G.bh; k += HME_THREADS) {
-            const int ly = k / G.bw, lx = k - ly * G.bw;
-            const int p = s_src[ly * HME_SRC_STRIDE + lx];
-            const int d = clamp_u8((ravg + clamp_u8((p - ravg) + 128)) - 128);
-            bad |= d != p;
+        for (int ly = wid; ly < G.bh; ly += HME_THREADS / 32) {
+            for (int lx = lane; lx < G.bw; lx += 32) {
+                const int p = s_src[ly * HME_SRC_STRIDE + lx];
+                const int d = clamp_u8((ravg + clamp_u8((p - ravg) + 128)) - 128);
+                bad |= d != p;
+            }
         }
         if (bad) {
             s_flag = 1;

@@ -101,24 +101,44 @@ DSV_D int hz_job_of_chunk(const HzJob *jobs, int njobs, int chunk)
     return lo;
 }
 
-/* quantised symbol at scan position s (0 if s is past the end) */
-DSV_D int hz_symbol(const HzJob &J, int s)
+/* position inside the scan order: region + region-local coordinates */
+struct HzCursor {
+    int r, x, y;
+};
+
+DSV_D void hz_locate(const HzRegions &rg, int s, HzCursor &c)
 {
-    const HzRegions &rg = J.rg;
-    if (s >= rg.base[HZ_NREG]) {
-        return 0;
-    }
     int r = 0;
-    while (s >= rg.base[r + 1]) {
+    while (r < HZ_NREG - 1 && s >= rg.base[r + 1]) {
         r++;
     }
     const int k = s - rg.base[r];
-    const int y = (int) fastdiv((unsigned) k, rg.fdw[r]);
-    const int x = k - y * rg.sw[r];
+    c.r = r;
+    c.y = (int) fastdiv((unsigned) k, rg.fdw[r]);
+    c.x = k - c.y * rg.sw[r];
+}
+
+DSV_D void hz_advance(const HzRegions &rg, HzCursor &c)
+{
+    if (++c.x == rg.sw[c.r]) {
+        c.x = 0;
+        if (++c.y == rg.sh[c.r]) {
+            c.y = 0;
+            c.r++;
+        }
+    }
+}
+
+/* quantised symbol at the cursor (which must be inside the plane's scan order): re-derived from the dequantised
+ * coefficient the SBT epilogue stored; zero coefficients (the vast majority) cost one load and a compare */
+DSV_D int hz_symbol_at(const HzJob &J, const HzCursor &c)
+{
+    const HzRegions &rg = J.rg;
+    const int r = c.r, x = c.x, y = c.y;
     const int ax = rg.x0[r] + x, ay = rg.y0[r] + y;
     const int lvl = rg.lvl[r];
     if (r == 0) {
-        if (k == 0) {
+        if ((x | y) == 0) {
             return 0; /* DC travels separately (hzcc.c:166,462-465) */
         }
         int v = J.coef[(size_t) ay * J.cw + ax];
@@ -127,10 +147,12 @@ DSV_D int hz_symbol(const HzJob &J, int s)
     if (lvl >= 2) { /* first visit of a position that the next hzcc level scans again */
         const DvGeom &g = J.dg;
         const int L = lvl - 1;
-        bool col = (ax == g.dvx[L]) && (ay < g.dvey[L]);
-        bool row = (ay == g.dvy[L]) && (ax < g.dvex[L]);
-        if (col || row) {
-            return J.dv[col ? g.col_base[L] + ay : g.row_base[L] + ax];
+        if (g.dvx[L] >= 0 || g.dvy[L] >= 0) {
+            bool col = (ax == g.dvx[L]) && (ay < g.dvey[L]);
+            bool row = (ay == g.dvy[L]) && (ax < g.dvex[L]);
+            if (col || row) {
+                return J.dv[col ? g.col_base[L] + ay : g.row_base[L] + ax];
+            }
         }
     }
     int v = J.coef[(size_t) ay * J.cw + ax];
@@ -166,9 +188,18 @@ DSV_D void chunk_load(const HzJob &J, int chunk_local, int sym[HZ_ITEMS], int &b
 {
     base = chunk_local * HZ_CHUNK + (int) threadIdx.x * HZ_ITEMS;
     unsigned long long mine = KEY_NONE;
+    const int total = J.rg.base[HZ_NREG];
+    HzCursor cur;
+    if (base < total) {
+        hz_locate(J.rg, base, cur);
+    }
 #pragma unroll
     for (int i = 0; i < HZ_ITEMS; i++) {
-        sym[i] = hz_symbol(J, base + i);
+        sym[i] = 0;
+        if (base + i < total) {
+            sym[i] = hz_symbol_at(J, cur);
+            hz_advance(J.rg, cur);
+        }
         if (sym[i]) {
             mine = mk_key(base + i, sym[i]);
         }
