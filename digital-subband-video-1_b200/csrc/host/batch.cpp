@@ -106,6 +106,7 @@ static void fill_stats(const EngineStats &s, int device, int lanes, double *out)
     out[9] = (double) s.pictures;
     out[10] = (double) device;
     out[11] = (double) lanes;
+    out[12] = s.host_ms;
 }
 
 extern "C" DSVB_ENC *dsvb_enc_create(const int *cfg, int lanes, int device)
@@ -247,6 +248,7 @@ static void add_stats(EngineStats &a, const EngineStats &b)
     a.h2d_bytes += b.h2d_bytes;
     a.d2h_bytes += b.d2h_bytes;
     a.pictures += b.pictures;
+    a.host_ms += b.host_ms;
 }
 
 extern "C" void dsvb_dec_stats(DSVB_DEC *d, double *stats, int reset)

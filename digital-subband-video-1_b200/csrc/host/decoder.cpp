@@ -183,6 +183,7 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
     CopyItem *cpy = arena_.push_n<CopyItem>((size_t) n, &d_cpy);
     int n_cpy = 0;
     size_t max_cpy = 0;
+    const double t_host0 = host_now_ms();
     HzDecDims dims;
     int n_sj = 0, n_p = 0, n_ext = 0, n_pack = 0;
     int blk_w = 0, blk_h = 0, nbh = 0, nbv = 0;
@@ -330,6 +331,7 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
         zero[n_zero].bytes = g.coef_total * sizeof(int32_t);
         n_zero++;
     }
+    stats.host_ms += host_now_ms() - t_host0;
     if (n_sj == 0) {
         CUDA_CHECK(cudaStreamSynchronize(st));
         return;

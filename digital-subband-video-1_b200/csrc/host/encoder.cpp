@@ -140,7 +140,7 @@ static void make_metadata_packet(DSV_ENCODER *enc, DSV_BUF *buf) /* dsv_encoder.
 static void put_stable_blocks(DSV_ENCODER *enc, const CodecGeom &g, int isP, const DevMV *mvs, BitWriter &bw)
 {
     const int nblk = g.nblk;
-    std::vector<uint8_t> tmp((size_t) nblk * 4 + 64, 0);
+    std::vector<uint8_t> tmp((size_t) nblk + 64, 0); /* ZBRLE: at most ~1 bit per block plus the final run */
     RleWriter rle(tmp.data());
     if (enc->refresh_ctr >= enc->stable_refresh) {
         enc->refresh_ctr = 0;
@@ -211,7 +211,8 @@ void dsv::predict_mv(const DevMV *mvs, int nbh, int x, int y, int *px, int *py) 
 static void put_motion(const CodecGeom &g, const DevMV *mvs, BitWriter &bw)
 {
     const int nbh = g.nbh, nbv = g.nbv;
-    const size_t ub = (size_t) nbh * nbv * 32;
+    /* worst case per block: 1-2 bits of mode run, SEG of a 16-bit delta (34 bits), 5 mask bits */
+    const size_t ub = (size_t) nbh * nbv * 6 + 64;
     std::vector<uint8_t> b_mode(ub, 0), b_x(ub, 0), b_y(ub, 0), b_mask(ub, 0);
     RleWriter rle(b_mode.data());
     BitWriter wx(b_x.data()), wy(b_y.data()), wm(b_mask.data());
@@ -384,6 +385,14 @@ EncEngine::EncEngine(const DSV_META &md, int gop, int pyramid_levels, int lanes)
     in_pitch_ = (g_.frame_bytes + 255) & ~(size_t) 255;
     CUDA_CHECK(cudaMalloc(&d_in_all_[0], in_pitch_ * L_ + 256));
     CUDA_CHECK(cudaMalloc(&d_in_all_[1], in_pitch_ * L_ + 256));
+    if (L_ > 1) {
+        int nt = (int) std::thread::hardware_concurrency() / 2;
+        if (const char *e = getenv("DSV_HOST_THREADS")) {
+            nt = atoi(e);
+        }
+        nt = iclamp(nt, 1, 8);
+        pool_ = new HostPool(nt - 1); /* the calling thread works too */
+    }
     lanes_.resize((size_t) L_);
     for (int i = 0; i < L_; i++) {
         alloc_lane(lanes_[(size_t) i]);
@@ -454,6 +463,7 @@ void EncEngine::free_lane(EncLane &l)
 EncEngine::~EncEngine()
 {
     cudaStreamSynchronize(st_);
+    delete pool_;
     for (auto &l : lanes_) {
         free_lane(l);
     }
@@ -696,8 +706,9 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     }
 
     /* ---- phase 2: host decisions + packet heads --------------------------------------------------- */
+    const double t_host0 = host_now_ms();
     int n_p = 0, n_ref = 0;
-    for (int k = 0; k < n; k++) {
+    const std::function<void(int)> lane_head = [&](int k) {
         const int li = lane_ids[k];
         EncLane &l = lanes_[(size_t) li];
         DSV_ENCODER *enc = l.enc;
@@ -725,7 +736,7 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         l.quant = DSV_MAX_QUALITY - ((DSV_MAX_QUALITY - 5) * quality / DSV_MAX_QUALITY); /* dsv_encoder.c:165 */
 
         const DevMV *mvs = h_mv0_ + (size_t) li * g.nblk;
-        memset(l.h_head, 0, 256 + (size_t) g.nblk * 48);
+        memset(l.h_head, 0, 256 + (size_t) g.nblk * 12); /* head <= 20 + stability map + 4 motion sub-streams (<= ~10 B per block) */
         BitWriter bw(l.h_head);
         put_packet_hdr(bw, DSV_MAKE_PT(l.is_ref, l.has_ref));
         bw.align();
@@ -744,9 +755,20 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         bw.align(); /* dsv_encode_plane aligns before each plane (hzcc.c:457) */
         l.head_bytes = bw.byte_pos();
         memcpy(h_stab_ + (size_t) li * g.nblk, enc->stable_blocks, (size_t) g.nblk);
+    };
+    if (pool_) {
+        pool_->run(n, lane_head);
+    } else {
+        for (int k = 0; k < n; k++) {
+            lane_head(k);
+        }
+    }
+    for (int k = 0; k < n; k++) {
+        const EncLane &l = lanes_[(size_t) lane_ids[k]];
         n_p += l.has_ref;
         n_ref += l.is_ref;
     }
+    stats.host_ms += host_now_ms() - t_host0;
 
     /* ---- phase 3: residual, transform, entropy coding, closed-loop reconstruction ------------------ */
     SbtJob *d_sj;

@@ -9,6 +9,13 @@
  *   dsvb_encode / dsvb_decode (dsv1_b200_batch.h) = L lanes, closed-GOP / whole-sequence sharding
  */
 #pragma once
+#include <time.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "dsv1_b200.h"
@@ -54,6 +61,91 @@ struct EngineStats {
     unsigned long long kernel_launches = 0;
     unsigned long long h2d_bytes = 0, d2h_bytes = 0;
     unsigned long long pictures = 0;
+    double host_ms = 0; /* serial host work inside the steps (side info, packet heads, parsing) */
+};
+
+/* persistent worker threads for the per-lane serial host work of a step (side info, packet heads): lanes are
+ * independent, so phase 2 of a 32-lane step need not be 32x the single-lane time while the GPU waits */
+class HostPool {
+public:
+    explicit HostPool(int nthreads)
+    {
+        for (int i = 0; i < nthreads; i++) {
+            th_.emplace_back([this] { worker(); });
+        }
+    }
+    ~HostPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            quit_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : th_) {
+            t.join();
+        }
+    }
+    void run(int n, const std::function<void(int)> &f)
+    {
+        if (th_.empty() || n <= 1) {
+            for (int i = 0; i < n; i++) {
+                f(i);
+            }
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = &f;
+            n_ = n;
+            next_.store(0);
+            pending_.store(n);
+            epoch_++;
+        }
+        cv_.notify_all();
+        drain();
+        std::unique_lock<std::mutex> lk(m_);
+        cv_done_.wait(lk, [this] { return pending_.load() == 0; });
+        fn_ = nullptr;
+    }
+
+private:
+    void drain()
+    {
+        for (;;) {
+            const int i = next_.fetch_add(1);
+            if (i >= n_) {
+                return;
+            }
+            (*fn_)(i);
+            if (pending_.fetch_sub(1) == 1) {
+                std::lock_guard<std::mutex> lk(m_);
+                cv_done_.notify_all();
+            }
+        }
+    }
+    void worker()
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return quit_ || epoch_ != seen; });
+                if (quit_) {
+                    return;
+                }
+                seen = epoch_;
+            }
+            drain();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, cv_done_;
+    const std::function<void(int)> *fn_ = nullptr;
+    int n_ = 0;
+    std::atomic<int> next_{0}, pending_{0};
+    unsigned long long epoch_ = 0;
+    bool quit_ = false;
 };
 
 struct EncLane {
@@ -121,6 +213,7 @@ private:
     HzChunk *d_chunks_ = nullptr;
     HzFrame *d_frames_ = nullptr, *h_frames_ = nullptr;
     void *h_pk_ = nullptr; /* packet egress copy list (mapped pinned) */
+    HostPool *pool_ = nullptr;
     uint8_t *d_in_all_[2] = {nullptr, nullptr}; /* packed-picture staging of all lanes, lane pitch in_pitch_ */
     size_t in_pitch_ = 0;
 };
@@ -183,6 +276,12 @@ private:
     size_t out_pitch_ = 0;
 };
 
+static inline double host_now_ms()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
 bool meta_supported(const DSV_META &m);
 void enc_prepare_state(DSV_ENCODER *enc);
 void parse_metadata_packet(const uint8_t *pkt, unsigned len, DSV_META *m);

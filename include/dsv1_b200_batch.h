@@ -26,9 +26,9 @@ extern "C" {
 typedef struct DSVB_ENC DSVB_ENC;
 typedef struct DSVB_DEC DSVB_DEC;
 
-#define DSVB_NSTATS 12
+#define DSVB_NSTATS 13
 /* stats[]: 0 sbt_fwd_ms 1 sbt_fwd_launches 2 sbt_fwd_bytes 3 sbt_inv_ms 4 sbt_inv_launches 5 sbt_inv_bytes
- *          6 kernel_launches 7 h2d_bytes 8 d2h_bytes 9 pictures 10 device 11 lanes */
+ *          6 kernel_launches 7 h2d_bytes 8 d2h_bytes 9 pictures 10 device 11 lanes 12 host_ms */
 
 DSVB_ENC *dsvb_enc_create(const int *cfg, int lanes, int device);
 void dsvb_enc_destroy(DSVB_ENC *e);

@@ -26,3 +26,7 @@ ms, _ = t(lambda: dec.decode_ptrs(sp, None, lens, [h_out.data_ptr() + s * sb for
 ms, _ = t(lambda: dec.decode_ptrs(sp, sdp, lens, [d_out.data_ptr() + s * sb for s in range(B)], [sb] * B, 1)); print("dec device %.1f ms  %.0f pic/s" % (ms, B * NFR / ms * 1e3))
 ms, _ = t(lambda: d_yuv.copy_(h_yuv, non_blocking=True)); print("H2D %.1f ms %.1f GB/s" % (ms, B * sb / ms / 1e6))
 ms, _ = t(lambda: h_out.copy_(d_out, non_blocking=True)); print("D2H %.1f ms %.1f GB/s" % (ms, B * sb / ms / 1e6))
+enc.stats(reset=True); dec.stats(reset=True)
+enc.encode_ptrs([d_yuv.data_ptr() + s * sb for s in range(B)], NFR, 1, sp, [cap] * B)
+dec.decode_ptrs(sp, sdp, lens, [d_out.data_ptr() + s * sb for s in range(B)], [sb] * B, 1)
+print("host ms inside steps: enc %.2f dec %.2f (per call)" % (enc.stats()["host_ms"], dec.stats()["host_ms"]))
