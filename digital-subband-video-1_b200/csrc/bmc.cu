@@ -74,14 +74,10 @@ DSV_D void bmc_store4(const BmcPlane &P, int mode, int gx, int gy, int nvalid, b
     }
 }
 
-/* a thread owns 4 horizontally adjacent samples; frames keep rows 4-byte aligned at multiples of 4 */
-__global__ void __launch_bounds__(BMC_THREADS) bmc_kernel(const BmcArgs *args)
+/* one motion block of one plane; a thread owns 4 horizontally adjacent samples (frames keep rows 4-byte aligned
+ * at multiples of 4) */
+DSV_D void bmc_block_plane(const BmcArgs &a, const int c, int16_t *hbuf, unsigned *scratch, int *s_avg)
 {
-    const BmcArgs &a = args[blockIdx.z / 3];
-    __shared__ __align__(8) int16_t hbuf[(DSV_BORDER + 3) * DSV_BORDER]; /* (bh + 3) x bw, bmc.c:127 */
-    __shared__ unsigned scratch[40];
-    __shared__ int s_avg[4];
-    const int c = blockIdx.z % 3;
     const BmcPlane P = a.pl[c];
     const int sh = c ? a.hs : 0, sv = c ? a.vs : 0;
     const int bw = a.blk_w >> sh, bh = a.blk_h >> sv;
@@ -237,6 +233,20 @@ __global__ void __launch_bounds__(BMC_THREADS) bmc_kernel(const BmcArgs *args)
     }
 }
 
+/* one CTA per motion block and lane, all three planes in turn (a chroma block alone is too little work to pay
+ * for a CTA launch) */
+__global__ void __launch_bounds__(BMC_THREADS) bmc_kernel(const BmcArgs *args)
+{
+    __shared__ __align__(8) int16_t hbuf[(DSV_BORDER + 3) * DSV_BORDER]; /* (bh + 3) x bw, bmc.c:127 */
+    __shared__ unsigned scratch[40];
+    __shared__ int s_avg[4];
+    const BmcArgs &a = args[blockIdx.z];
+    for (int c = 0; c < 3; c++) {
+        bmc_block_plane(a, c, hbuf, scratch, s_avg);
+        __syncthreads(); /* hbuf / s_avg are reused by the next plane */
+    }
+}
+
 void bmc_fill_args(BmcArgs *a, const MotionGeom &g, const DevMV *d_mv, const DevFrame &ref, const DevFrame *pred,
                    const DevFrame &in, const DevFrame &out, int mode)
 {
@@ -265,7 +275,7 @@ void bmc_fill_args(BmcArgs *a, const MotionGeom &g, const DevMV *d_mv, const Dev
 void bmc_launch(const BmcArgs *d_args, int n, int nbh, int nbv, cudaStream_t st)
 {
     if (n > 0) {
-        DSV_LAUNCH(bmc_kernel, dim3(nbh, nbv, 3 * n), dim3(BMC_THREADS), 0, st, d_args);
+        DSV_LAUNCH(bmc_kernel, dim3(nbh, nbv, n), dim3(BMC_THREADS), 0, st, d_args);
         KERNEL_CHECK();
     }
 }

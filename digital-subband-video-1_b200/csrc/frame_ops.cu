@@ -79,14 +79,16 @@ void StepArena::upload(cudaStream_t st)
 
 #define FO_BX 64
 #define FO_BY 4
+#define FO_RY 1 /* row groups per CTA (measured: more rows per CTA is slower -- fewer CTAs in flight to hide latency) */
 static dim3 fo_grid(int max_w, int max_h, int n, bool bordered)
 {
     const int cols = bordered ? max_w + 2 * DSV_BORDER : max_w, rows = bordered ? max_h + 2 * DSV_BORDER : max_h;
-    return dim3(ceil_div(ceil_div(cols, 16), FO_BX), ceil_div(rows, FO_BY), n);
+    return dim3(ceil_div(ceil_div(cols, 16), FO_BX), ceil_div(rows, FO_BY * FO_RY), n);
 }
-#define FO_COORDS()                                                      \
+/* body runs once per (16-byte chunk ck, row) owned by the thread */
+#define FO_FOREACH_ROW()                                                 \
     const int ck = (int) (blockIdx.x * FO_BX + threadIdx.x);             \
-    const int row = (int) (blockIdx.y * FO_BY + threadIdx.y)
+    for (int row = (int) (blockIdx.y * FO_BY * FO_RY + threadIdx.y), fo_i = 0; fo_i < FO_RY; fo_i++, row += FO_BY)
 
 DSV_D bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -94,24 +96,26 @@ __global__ void __launch_bounds__(FO_BX *FO_BY) ingest_kernel(const IngestItem *
 {
     const IngestItem it = items[blockIdx.z];
     const PlaneRef D = it.dst;
-    FO_COORDS();
-    const int x0 = ck * 16 - DSV_BORDER, y = row - DSV_BORDER;
-    if (x0 >= D.w + DSV_BORDER || y >= D.h + DSV_BORDER) {
-        return;
-    }
-    const int sy = iclamp(y, 0, D.h - 1);
-    const uint8_t *src = it.src + (size_t) sy * D.w;
-    uint8_t *dst = D.p + (ptrdiff_t) y * D.stride + x0;
-    if (x0 >= 0 && x0 + 16 <= D.w && aligned16(src + x0)) {
-        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(src + x0);
-        return;
-    }
-    const int xend = D.w + DSV_BORDER;
-#pragma unroll 4
-    for (int e = 0; e < 16; e++) {
-        const int x = x0 + e;
-        if (x < xend) {
-            dst[e] = src[iclamp(x, 0, D.w - 1)];
+    FO_FOREACH_ROW()
+    {
+        const int x0 = ck * 16 - DSV_BORDER, y = row - DSV_BORDER;
+        if (x0 >= D.w + DSV_BORDER || y >= D.h + DSV_BORDER) {
+            continue;
+        }
+        const int sy = iclamp(y, 0, D.h - 1);
+        const uint8_t *src = it.src + (size_t) sy * D.w;
+        uint8_t *dst = D.p + (ptrdiff_t) y * D.stride + x0;
+        if (x0 >= 0 && x0 + 16 <= D.w && aligned16(src + x0)) {
+            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(src + x0);
+            continue;
+        }
+        const int xend = D.w + DSV_BORDER;
+    #pragma unroll 4
+        for (int e = 0; e < 16; e++) {
+            const int x = x0 + e;
+            if (x < xend) {
+                dst[e] = src[iclamp(x, 0, D.w - 1)];
+            }
         }
     }
 }
@@ -120,43 +124,47 @@ __global__ void __launch_bounds__(FO_BX *FO_BY) pack_kernel(const PackItem *item
 {
     const PackItem it = items[blockIdx.z];
     const PlaneRef S = it.src;
-    FO_COORDS();
-    const int x0 = ck * 16, y = row;
-    if (x0 >= S.w || y >= S.h) {
-        return;
-    }
-    const uint8_t *src = S.p + (size_t) y * S.stride + x0;
-    uint8_t *dst = it.dst + (size_t) y * S.w + x0;
-    if (x0 + 16 <= S.w && aligned16(dst)) {
-        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(src);
-        return;
-    }
-    for (int e = 0; e < 16 && x0 + e < S.w; e++) {
-        dst[e] = src[e];
+    FO_FOREACH_ROW()
+    {
+        const int x0 = ck * 16, y = row;
+        if (x0 >= S.w || y >= S.h) {
+            continue;
+        }
+        const uint8_t *src = S.p + (size_t) y * S.stride + x0;
+        uint8_t *dst = it.dst + (size_t) y * S.w + x0;
+        if (x0 + 16 <= S.w && aligned16(dst)) {
+            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(src);
+            continue;
+        }
+        for (int e = 0; e < 16 && x0 + e < S.w; e++) {
+            dst[e] = src[e];
+        }
     }
 }
 
 __global__ void __launch_bounds__(FO_BX *FO_BY) extend_kernel(const PlaneRef *items)
 {
     const PlaneRef P = items[blockIdx.z];
-    FO_COORDS();
-    const int x0 = ck * 16 - DSV_BORDER, y = row - DSV_BORDER;
-    if (x0 >= P.w + DSV_BORDER || y >= P.h + DSV_BORDER) {
-        return;
-    }
-    const bool yin = y >= 0 && y < P.h;
-    if (yin && x0 >= 0 && x0 + 16 <= P.w) {
-        return; /* interior */
-    }
-    const int sy = iclamp(y, 0, P.h - 1);
-    const uint8_t *src = P.p + (size_t) sy * P.stride;
-    uint8_t *dst = P.p + (ptrdiff_t) y * P.stride + x0;
-    const int xend = P.w + DSV_BORDER;
-#pragma unroll 4
-    for (int e = 0; e < 16; e++) {
-        const int x = x0 + e;
-        if (x < xend && !(yin && x >= 0 && x < P.w)) {
-            dst[e] = src[iclamp(x, 0, P.w - 1)];
+    FO_FOREACH_ROW()
+    {
+        const int x0 = ck * 16 - DSV_BORDER, y = row - DSV_BORDER;
+        if (x0 >= P.w + DSV_BORDER || y >= P.h + DSV_BORDER) {
+            continue;
+        }
+        const bool yin = y >= 0 && y < P.h;
+        if (yin && x0 >= 0 && x0 + 16 <= P.w) {
+            continue; /* interior */
+        }
+        const int sy = iclamp(y, 0, P.h - 1);
+        const uint8_t *src = P.p + (size_t) sy * P.stride;
+        uint8_t *dst = P.p + (ptrdiff_t) y * P.stride + x0;
+        const int xend = P.w + DSV_BORDER;
+    #pragma unroll 4
+        for (int e = 0; e < 16; e++) {
+            const int x = x0 + e;
+            if (x < xend && !(yin && x >= 0 && x < P.w)) {
+                dst[e] = src[iclamp(x, 0, P.w - 1)];
+            }
         }
     }
 }
@@ -167,42 +175,44 @@ __global__ void __launch_bounds__(FO_BX *FO_BY) down2_kernel(const Down2Item *it
 {
     const Down2Item it = items[blockIdx.z];
     const PlaneRef S = it.src, D = it.dst;
-    FO_COORDS();
-    const int x0 = ck * 16 - DSV_BORDER, y = row - DSV_BORDER;
-    if (x0 >= D.w + DSV_BORDER || y >= D.h + DSV_BORDER) {
-        return;
-    }
-    const int sy = iclamp(y, 0, D.h - 1);
-    const uint8_t *s0 = S.p + (size_t) (2 * sy) * S.stride, *s1 = s0 + S.stride;
-    uint8_t *dst = D.p + (ptrdiff_t) y * D.stride + x0;
-    if (x0 >= 0 && x0 + 16 <= D.w) {
-        const uint4 a0 = *reinterpret_cast<const uint4 *>(s0 + 2 * x0), a1 = *reinterpret_cast<const uint4 *>(s0 + 2 * x0 + 16);
-        const uint4 b0 = *reinterpret_cast<const uint4 *>(s1 + 2 * x0), b1 = *reinterpret_cast<const uint4 *>(s1 + 2 * x0 + 16);
-        const unsigned ra[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const unsigned rb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        unsigned o[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            unsigned r = 0;
-#pragma unroll
-            for (int e = 0; e < 4; e++) { /* output sample 4k+e <- source samples 8k+2e, 8k+2e+1 */
-                const unsigned wa = ra[2 * k + (e >> 1)], wb = rb[2 * k + (e >> 1)];
-                const int sh = (e & 1) * 16;
-                const unsigned v = ((wa >> sh) & 0xff) + ((wa >> (sh + 8)) & 0xff) + ((wb >> sh) & 0xff) + ((wb >> (sh + 8)) & 0xff) + 2;
-                r |= (v >> 2) << (8 * e);
-            }
-            o[k] = r;
+    FO_FOREACH_ROW()
+    {
+        const int x0 = ck * 16 - DSV_BORDER, y = row - DSV_BORDER;
+        if (x0 >= D.w + DSV_BORDER || y >= D.h + DSV_BORDER) {
+            continue;
         }
-        *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
-        return;
-    }
-    const int xend = D.w + DSV_BORDER;
-#pragma unroll 4
-    for (int e = 0; e < 16; e++) {
-        const int x = x0 + e;
-        if (x < xend) {
-            const int sx = 2 * iclamp(x, 0, D.w - 1);
-            dst[e] = (uint8_t) ((s0[sx] + s0[sx + 1] + s1[sx] + s1[sx + 1] + 2) >> 2);
+        const int sy = iclamp(y, 0, D.h - 1);
+        const uint8_t *s0 = S.p + (size_t) (2 * sy) * S.stride, *s1 = s0 + S.stride;
+        uint8_t *dst = D.p + (ptrdiff_t) y * D.stride + x0;
+        if (x0 >= 0 && x0 + 16 <= D.w) {
+            const uint4 a0 = *reinterpret_cast<const uint4 *>(s0 + 2 * x0), a1 = *reinterpret_cast<const uint4 *>(s0 + 2 * x0 + 16);
+            const uint4 b0 = *reinterpret_cast<const uint4 *>(s1 + 2 * x0), b1 = *reinterpret_cast<const uint4 *>(s1 + 2 * x0 + 16);
+            const unsigned ra[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const unsigned rb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            unsigned o[4];
+    #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                unsigned r = 0;
+    #pragma unroll
+                for (int e = 0; e < 4; e++) { /* output sample 4k+e <- source samples 8k+2e, 8k+2e+1 */
+                    const unsigned wa = ra[2 * k + (e >> 1)], wb = rb[2 * k + (e >> 1)];
+                    const int sh = (e & 1) * 16;
+                    const unsigned v = ((wa >> sh) & 0xff) + ((wa >> (sh + 8)) & 0xff) + ((wb >> sh) & 0xff) + ((wb >> (sh + 8)) & 0xff) + 2;
+                    r |= (v >> 2) << (8 * e);
+                }
+                o[k] = r;
+            }
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+            continue;
+        }
+        const int xend = D.w + DSV_BORDER;
+    #pragma unroll 4
+        for (int e = 0; e < 16; e++) {
+            const int x = x0 + e;
+            if (x < xend) {
+                const int sx = 2 * iclamp(x, 0, D.w - 1);
+                dst[e] = (uint8_t) ((s0[sx] + s0[sx + 1] + s1[sx] + s1[sx + 1] + 2) >> 2);
+            }
         }
     }
 }
@@ -242,31 +252,33 @@ __global__ void __launch_bounds__(FO_BX *FO_BY) recon_kernel(const ReconItem *it
 {
     const ReconItem it = items[blockIdx.z];
     const PlaneRef A = it.a, B = it.b, D = it.dst;
-    FO_COORDS();
-    const int x0 = ck * 16 - DSV_BORDER, y = row - DSV_BORDER;
-    if (x0 >= D.w + DSV_BORDER || y >= D.h + DSV_BORDER) {
-        return;
-    }
-    const int sy = iclamp(y, 0, D.h - 1);
-    const uint8_t *a = A.p + (size_t) sy * A.stride;
-    const uint8_t *b = B.p ? B.p + (size_t) sy * B.stride : nullptr;
-    uint8_t *dst = D.p + (ptrdiff_t) y * D.stride + x0;
-    if (x0 >= 0 && x0 + 16 <= D.w) {
-        uint4 va = *reinterpret_cast<const uint4 *>(a + x0);
-        if (b) {
-            const uint4 vb = *reinterpret_cast<const uint4 *>(b + x0);
-            va = make_uint4(add4_clamp(va.x, vb.x), add4_clamp(va.y, vb.y), add4_clamp(va.z, vb.z), add4_clamp(va.w, vb.w));
+    FO_FOREACH_ROW()
+    {
+        const int x0 = ck * 16 - DSV_BORDER, y = row - DSV_BORDER;
+        if (x0 >= D.w + DSV_BORDER || y >= D.h + DSV_BORDER) {
+            continue;
         }
-        *reinterpret_cast<uint4 *>(dst) = va;
-        return;
-    }
-    const int xend = D.w + DSV_BORDER;
-#pragma unroll 4
-    for (int e = 0; e < 16; e++) {
-        const int x = x0 + e;
-        if (x < xend) {
-            const int sx = iclamp(x, 0, D.w - 1);
-            dst[e] = b ? clamp_u8((int) a[sx] + (int) b[sx] - 128) : a[sx];
+        const int sy = iclamp(y, 0, D.h - 1);
+        const uint8_t *a = A.p + (size_t) sy * A.stride;
+        const uint8_t *b = B.p ? B.p + (size_t) sy * B.stride : nullptr;
+        uint8_t *dst = D.p + (ptrdiff_t) y * D.stride + x0;
+        if (x0 >= 0 && x0 + 16 <= D.w) {
+            uint4 va = *reinterpret_cast<const uint4 *>(a + x0);
+            if (b) {
+                const uint4 vb = *reinterpret_cast<const uint4 *>(b + x0);
+                va = make_uint4(add4_clamp(va.x, vb.x), add4_clamp(va.y, vb.y), add4_clamp(va.z, vb.z), add4_clamp(va.w, vb.w));
+            }
+            *reinterpret_cast<uint4 *>(dst) = va;
+            continue;
+        }
+        const int xend = D.w + DSV_BORDER;
+    #pragma unroll 4
+        for (int e = 0; e < 16; e++) {
+            const int x = x0 + e;
+            if (x < xend) {
+                const int sx = iclamp(x, 0, D.w - 1);
+                dst[e] = b ? clamp_u8((int) a[sx] + (int) b[sx] - 128) : a[sx];
+            }
         }
     }
 }

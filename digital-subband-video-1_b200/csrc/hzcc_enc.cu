@@ -190,13 +190,26 @@ DSV_D void chunk_load(const HzJob &J, int chunk_local, int sym[HZ_ITEMS], int &b
     unsigned long long mine = KEY_NONE;
     const int total = J.rg.base[HZ_NREG];
     HzCursor cur;
+    bool all_zero = false;
     if (base < total) {
         hz_locate(J.rg, base, cur);
+        /* the thread's 8 positions usually sit in one row of one region, contiguous in memory: two 16-byte loads
+         * tell whether there is anything to quantise at all (rarely, in a P picture) */
+        const HzRegions &rg = J.rg;
+        const int r = cur.r, lvl = rg.lvl[r];
+        const bool dv = r > 0 && lvl >= 2 && (J.dg.dvx[lvl - 1] >= 0 || J.dg.dvy[lvl - 1] >= 0);
+        if (!dv && cur.x + HZ_ITEMS <= rg.sw[r] && !(r == 0 && (cur.x | cur.y) == 0)) {
+            const int32_t *p = J.coef + (size_t) (rg.y0[r] + cur.y) * J.cw + rg.x0[r] + cur.x;
+            if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+                const int4 a = *reinterpret_cast<const int4 *>(p), b = *reinterpret_cast<const int4 *>(p + 4);
+                all_zero = (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) == 0;
+            }
+        }
     }
 #pragma unroll
     for (int i = 0; i < HZ_ITEMS; i++) {
         sym[i] = 0;
-        if (base + i < total) {
+        if (!all_zero && base + i < total) {
             sym[i] = hz_symbol_at(J, cur);
             hz_advance(J.rg, cur);
         }
@@ -207,58 +220,81 @@ DSV_D void chunk_load(const HzJob &J, int chunk_local, int sym[HZ_ITEMS], int &b
     excl_key = block_scan_excl<OpMaxS64>(mine, scratch, &chunk_last);
 }
 
-__global__ void __launch_bounds__(HZ_THREADS) hzcc_scan_kernel(const HzJob *jobs, int njobs, HzChunk *chunks)
+#define HZ_CPB 1 /* chunks per CTA (measured: 8 is slower; most chunks of a P picture still hold a few non-zeros) */
+
+/* (re)load the job record of `chunk` into shared memory unless the cached one already covers it */
+DSV_D void hz_cache_job(HzJob *sJ, int *s_have, const HzJob *jobs, int njobs, int chunk)
+{
+    __syncthreads(); /* everybody is done with the previous chunk (and with *sJ) */
+    const bool hit = *s_have && chunk >= sJ->chunk_base && chunk < sJ->chunk_base + sJ->nchunks;
+    __syncthreads();
+    if (!hit) {
+        const int jid = hz_job_of_chunk(jobs, njobs, chunk);
+        const int *src = reinterpret_cast<const int *>(&jobs[jid]);
+        int *dst = reinterpret_cast<int *>(sJ);
+        for (int i = threadIdx.x; i < (int) (sizeof(HzJob) / sizeof(int)); i += HZ_THREADS) {
+            dst[i] = src[i];
+        }
+        if (threadIdx.x == 0) {
+            *s_have = 1;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(HZ_THREADS) hzcc_scan_kernel(const HzJob *jobs, int njobs, HzChunk *chunks, int total_chunks)
 {
     __shared__ HzJob J;
     __shared__ unsigned long long scratch[40];
-    __shared__ int s_first;
+    __shared__ int s_first, s_have;
     const int tid = threadIdx.x;
-    const int chunk = blockIdx.x;
-    {
-        int jid = hz_job_of_chunk(jobs, njobs, chunk);
-        const int *src = reinterpret_cast<const int *>(&jobs[jid]);
-        int *dst = reinterpret_cast<int *>(&J);
-        for (int i = tid; i < (int) (sizeof(HzJob) / sizeof(int)); i += HZ_THREADS) {
-            dst[i] = src[i];
+    if (tid == 0) {
+        s_have = 0;
+    }
+    for (int ci = 0; ci < HZ_CPB; ci++) {
+        const int chunk = (int) blockIdx.x * HZ_CPB + ci;
+        if (chunk >= total_chunks) {
+            return;
         }
+        hz_cache_job(&J, &s_have, jobs, njobs, chunk);
         if (tid == 0) {
             s_first = -1;
         }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    int sym[HZ_ITEMS], base;
-    unsigned long long excl, last;
-    chunk_load(J, chunk - J.chunk_base, sym, base, scratch, excl, last);
+        int sym[HZ_ITEMS], base;
+        unsigned long long excl, last;
+        chunk_load(J, chunk - J.chunk_base, sym, base, scratch, excl, last);
 
-    int prev_pos = key_pos(excl), prev_sym = key_sym(excl);
-    unsigned bits = 0, cnt = 0;
+        int prev_pos = key_pos(excl), prev_sym = key_sym(excl);
+        unsigned bits = 0, cnt = 0;
 #pragma unroll
-    for (int i = 0; i < HZ_ITEMS; i++) {
-        if (sym[i]) {
-            if (prev_pos >= 0) {
-                bits += group_bits(base + i, prev_pos, prev_sym);
-            } else {
-                s_first = base + i; /* exactly one thread sees the chunk's first non-zero */
+        for (int i = 0; i < HZ_ITEMS; i++) {
+            if (sym[i]) {
+                if (prev_pos >= 0) {
+                    bits += group_bits(base + i, prev_pos, prev_sym);
+                } else {
+                    s_first = base + i; /* exactly one thread sees the chunk's first non-zero */
+                }
+                prev_pos = base + i;
+                prev_sym = sym[i];
+                cnt++;
             }
-            prev_pos = base + i;
-            prev_sym = sym[i];
-            cnt++;
         }
-    }
-    unsigned long long tot;
-    block_scan_incl<OpAdd64>(((unsigned long long) cnt << 40) | bits, scratch, &tot);
-    if (tid == 0) {
-        HzChunk c;
-        c.cnt = (int) (tot >> 40);
-        c.bits_inner = (unsigned) (tot & 0xFFFFFFFFFFull);
-        c.first_pos = s_first;
-        c.last_pos = key_pos(last);
-        c.last_sym = key_sym(last);
-        c.prev_pos = -1;
-        c.prev_sym = 0;
-        c.bit_off = 0;
-        chunks[chunk] = c;
+        unsigned long long tot;
+        block_scan_incl<OpAdd64>(((unsigned long long) cnt << 40) | bits, scratch, &tot);
+        if (tid == 0) {
+            HzChunk c;
+            c.cnt = (int) (tot >> 40);
+            c.bits_inner = (unsigned) (tot & 0xFFFFFFFFFFull);
+            c.first_pos = s_first;
+            c.last_pos = key_pos(last);
+            c.last_sym = key_sym(last);
+            c.prev_pos = -1;
+            c.prev_sym = 0;
+            c.bit_off = 0;
+            chunks[chunk] = c;
+        }
     }
 }
 
@@ -395,63 +431,65 @@ DSV_D void or_bits_atomic(unsigned *words, unsigned long long bitpos, int len, u
 }
 
 __global__ void __launch_bounds__(HZ_THREADS) hzcc_pack_kernel(const HzJob *jobs, int njobs, const HzChunk *chunks,
-                                                               const HzFrame *frames)
+                                                               const HzFrame *frames, int total_chunks)
 {
     __shared__ HzJob J;
     __shared__ unsigned long long scratch[40];
+    __shared__ int s_have;
     const int tid = threadIdx.x;
-    const int chunk = blockIdx.x;
-    {
-        int jid = hz_job_of_chunk(jobs, njobs, chunk);
-        const int *src = reinterpret_cast<const int *>(&jobs[jid]);
-        int *dst = reinterpret_cast<int *>(&J);
-        for (int i = tid; i < (int) (sizeof(HzJob) / sizeof(int)); i += HZ_THREADS) {
-            dst[i] = src[i];
-        }
+    if (tid == 0) {
+        s_have = 0;
     }
     __syncthreads();
-    const HzChunk C = chunks[chunk];
-    if (C.cnt == 0) {
-        return; /* uniform for the whole block */
-    }
-    int sym[HZ_ITEMS], base;
-    unsigned long long excl, last;
-    chunk_load(J, chunk - J.chunk_base, sym, base, scratch, excl, last);
-
-    int prev_pos = key_pos(excl), prev_sym = key_sym(excl);
-    if (prev_pos < 0) { /* nothing earlier in this chunk: continue from the previous chunks */
-        prev_pos = C.prev_pos;
-        prev_sym = C.prev_sym;
-    }
-    const int pp0 = prev_pos, ps0 = prev_sym;
-    unsigned long long bits = 0;
-#pragma unroll
-    for (int i = 0; i < HZ_ITEMS; i++) {
-        if (sym[i]) {
-            bits += group_bits(base + i, prev_pos, prev_sym);
-            prev_pos = base + i;
-            prev_sym = sym[i];
+    for (int ci = 0; ci < HZ_CPB; ci++) {
+        const int chunk = (int) blockIdx.x * HZ_CPB + ci;
+        if (chunk >= total_chunks) {
+            return;
         }
-    }
-    unsigned long long tot;
-    unsigned long long off = C.bit_off + block_scan_excl<OpAdd64>(bits, scratch, &tot);
-    unsigned *words = reinterpret_cast<unsigned *>(frames[J.frame].pkt);
-    prev_pos = pp0;
-    prev_sym = ps0;
-#pragma unroll
-    for (int i = 0; i < HZ_ITEMS; i++) {
-        if (sym[i]) {
-            unsigned run = (unsigned) (base + i - prev_pos - 1);
-            int l = ueg_len(run);
-            or_bits_atomic(words, off, l, ueg_code(run));
-            off += (unsigned long long) l;
-            if (prev_pos >= 0) {
-                l = neg_len(prev_sym);
-                or_bits_atomic(words, off, l, neg_code(prev_sym));
-                off += (unsigned long long) l;
+        const HzChunk C = chunks[chunk];
+        if (C.cnt == 0) {
+            continue; /* nothing to write (most chunks of a P picture); uniform for the whole block */
+        }
+        hz_cache_job(&J, &s_have, jobs, njobs, chunk);
+        int sym[HZ_ITEMS], base;
+        unsigned long long excl, last;
+        chunk_load(J, chunk - J.chunk_base, sym, base, scratch, excl, last);
+
+        int prev_pos = key_pos(excl), prev_sym = key_sym(excl);
+        if (prev_pos < 0) { /* nothing earlier in this chunk: continue from the previous chunks */
+            prev_pos = C.prev_pos;
+            prev_sym = C.prev_sym;
+        }
+        const int pp0 = prev_pos, ps0 = prev_sym;
+        unsigned long long bits = 0;
+    #pragma unroll
+        for (int i = 0; i < HZ_ITEMS; i++) {
+            if (sym[i]) {
+                bits += group_bits(base + i, prev_pos, prev_sym);
+                prev_pos = base + i;
+                prev_sym = sym[i];
             }
-            prev_pos = base + i;
-            prev_sym = sym[i];
+        }
+        unsigned long long tot;
+        unsigned long long off = C.bit_off + block_scan_excl<OpAdd64>(bits, scratch, &tot);
+        unsigned *words = reinterpret_cast<unsigned *>(frames[J.frame].pkt);
+        prev_pos = pp0;
+        prev_sym = ps0;
+    #pragma unroll
+        for (int i = 0; i < HZ_ITEMS; i++) {
+            if (sym[i]) {
+                unsigned run = (unsigned) (base + i - prev_pos - 1);
+                int l = ueg_len(run);
+                or_bits_atomic(words, off, l, ueg_code(run));
+                off += (unsigned long long) l;
+                if (prev_pos >= 0) {
+                    l = neg_len(prev_sym);
+                    or_bits_atomic(words, off, l, neg_code(prev_sym));
+                    off += (unsigned long long) l;
+                }
+                prev_pos = base + i;
+                prev_sym = sym[i];
+            }
         }
     }
 }
@@ -459,11 +497,11 @@ __global__ void __launch_bounds__(HZ_THREADS) hzcc_pack_kernel(const HzJob *jobs
 void hzcc_enc_launch(const HzJob *d_jobs, int njobs, HzChunk *d_chunks, int total_chunks,
                      HzFrame *d_frames, int nframes, cudaStream_t st)
 {
-    DSV_LAUNCH(hzcc_scan_kernel, dim3(total_chunks), dim3(HZ_THREADS), 0, st, d_jobs, njobs, d_chunks);
+    DSV_LAUNCH(hzcc_scan_kernel, dim3(ceil_div(total_chunks, HZ_CPB)), dim3(HZ_THREADS), 0, st, d_jobs, njobs, d_chunks, total_chunks);
     KERNEL_CHECK();
     DSV_LAUNCH(hzcc_prefix_kernel, dim3(nframes), dim3(HZP_THREADS), 0, st, d_jobs, d_chunks, d_frames);
     KERNEL_CHECK();
-    DSV_LAUNCH(hzcc_pack_kernel, dim3(total_chunks), dim3(HZ_THREADS), 0, st, d_jobs, njobs, d_chunks, d_frames);
+    DSV_LAUNCH(hzcc_pack_kernel, dim3(ceil_div(total_chunks, HZ_CPB)), dim3(HZ_THREADS), 0, st, d_jobs, njobs, d_chunks, d_frames, total_chunks);
     KERNEL_CHECK();
 }
 
