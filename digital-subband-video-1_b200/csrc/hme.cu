@@ -355,9 +355,64 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
     }
     const int sbw = G.bw / 2, sbh = G.bh / 2;
     const int lane = tid & 31, wid = tid >> 5;
-    /* rows go to warps, columns to lanes: the quadrant row is warp-uniform, no per-sample divisions */
-    for (int ly = wid; ly < G.bh; ly += HME_THREADS / 32) {
-        const int qyi = ly >= sbh;
+    if ((G.bw & 7) == 0) {
+        /* four samples per step: the block sums of block_analysis / y_sqrvar / intra_metric are sums of absolute
+         * differences and squares, i.e. __vsadu4 / __dp4a on packed words (the staged rows are 4-byte aligned) */
+        const int words = G.bw >> 2;
+        unsigned good[4] = {0, 0, 0, 0}, evil[4] = {0, 0, 0, 0};
+        for (int idx = tid; idx < G.bh * 16; idx += HME_THREADS) {
+            const int ly = idx >> 4, wx = idx & 15;
+            if (wx >= words) {
+                continue;
+            }
+            const int lx0 = 4 * wx;
+            const uint8_t *sp = s_src + ly * HME_SRC_STRIDE + lx0;
+            const uint8_t *rp = s_ref0 + ly * HME_SRC_STRIDE + lx0;
+            const unsigned w = *reinterpret_cast<const unsigned *>(sp), r = *reinterpret_cast<const unsigned *>(rp);
+            const unsigned nxt = lx0 + 4 < G.bw ? (unsigned) sp[4] : (w >> 24);
+            const unsigned wr = (w >> 8) | (nxt << 24);
+            const unsigned up = ly == 0 ? w : *reinterpret_cast<const unsigned *>(sp - HME_SRC_STRIDE);
+            sum[SUM_S] += __vsadu4(w, 0u);
+            sum[SUM_SS] = __dp4a(w, w, sum[SUM_SS]);
+            sum[SUM_SH] += __vsadu4(w, wr);
+            sum[SUM_SV] += __vsadu4(w, up);
+            sum[SUM_RS] += __vsadu4(r, 0u);
+            sum[SUM_RSS] = __dp4a(r, r, sum[SUM_RSS]);
+            if (ly < 2 * sbh) { /* intra_metric on the four quadrants, hme.c:87-134 */
+                const int qxi = lx0 >= sbw, qyi = ly >= sbh;
+                const int qi0 = lx0 - qxi * sbw, qj = ly - qyi * sbh;
+                const unsigned wl = (w << 8) | (qi0 == 0 ? (w & 0xffu) : (unsigned) sp[-1]);
+                const unsigned rl = (r << 8) | (qi0 == 0 ? (r & 0xffu) : (unsigned) rp[-1]);
+                const unsigned ua = qj == 0 ? w : up;
+                const unsigned ub = qj == 0 ? r : *reinterpret_cast<const unsigned *>(rp - HME_SRC_STRIDE);
+                unsigned g = __vsadu4(w, wl) + __vsadu4(w, ua) + __vsadu4(r, rl) + __vsadu4(r, ub);
+                unsigned e = 0;
+                const unsigned d = __vabsdiffu4(w, r);
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const unsigned v = (d >> (8 * b)) & 0xffu;
+                    if (v > 2u) {
+                        e += v;
+                    } else {
+                        g += v == 0u ? 192u : (v == 1u ? 128u : 96u);
+                    }
+                }
+                const int q = qxi | (qyi << 1);
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    good[t] += q == t ? g : 0u;
+                    evil[t] += q == t ? e : 0u;
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            sum[SUM_GOOD0 + t] += good[t];
+            sum[SUM_EVIL0 + t] += evil[t];
+        }
+    } else
+    /* general widths -- rows go to warps, columns to lanes: the quadrant row is warp-uniform, no per-sample divisions */
+    for (int ly = wid; ly < G.bh; ly += HME_THREADS / 32) {        const int qyi = ly >= sbh;
         const bool inq_y = ly < 2 * sbh;
         const int qj = ly - qyi * sbh;
         unsigned good0 = 0, good1 = 0, evil0 = 0, evil1 = 0;

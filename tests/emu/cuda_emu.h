@@ -220,6 +220,11 @@ static inline unsigned __vsadu4(unsigned a, unsigned b)
     }
     return r;
 }
+static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c)
+{
+    for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xff) * ((b >> (8 * i)) & 0xff);
+    return c;
+}
 static inline unsigned __sad(int a, int b, unsigned c) { return c + (unsigned) (a > b ? a - b : b - a); }
 static inline unsigned __usad(unsigned a, unsigned b, unsigned c) { return c + (a > b ? a - b : b - a); }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned) (((unsigned long long) a * b) >> 32); }
