@@ -237,9 +237,17 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
         if (pkts[k].dev_data) {
             d_pkt = pkts[k].dev_data;
         } else {
-            if (!l.d_pkt) {
-                CUDA_CHECK(cudaMalloc(&l.d_pkt, pkt_cap_ + 64));
-                CUDA_CHECK(cudaMallocHost(&l.h_pkt, pkt_cap_ + 80));
+            if ((size_t) pkt_len + 80 > l.pkt_alloc) {
+                /* staging grows with the largest packet seen (the format's upper bound, 8 bytes per coefficient,
+                 * would pin hundreds of MB per lane at UHD); the previous step has completed, nothing is in flight */
+                cudaFree(l.d_pkt);
+                cudaFreeHost(l.h_pkt);
+                l.pkt_alloc = (size_t) pkt_len * 2 + (256 << 10);
+                if (l.pkt_alloc > pkt_cap_ + 80) {
+                    l.pkt_alloc = pkt_cap_ + 80;
+                }
+                CUDA_CHECK(cudaMalloc(&l.d_pkt, l.pkt_alloc));
+                CUDA_CHECK(cudaMallocHost(&l.h_pkt, l.pkt_alloc));
             }
             memcpy(l.h_pkt, pkt, pkt_len);
             memset(l.h_pkt + pkt_len, 0, 64);
@@ -503,7 +511,7 @@ extern "C" int dsv_dec(DSV_DECODER *d, DSV_BUF *buffer, DSV_FRAME **out, DSV_FNU
         e = new DecEngine(md, 1);
         d->ref = reinterpret_cast<DSV_IMAGE *>(e);
     }
-    DSV_FRAME *f = dsv_mk_frame(md.subsamp, md.width, md.height, 1);
+    DSV_FRAME *f = mk_frame_pinned(md.subsamp, md.width, md.height);
     PktRef pr = {pkt, nullptr, pkt_len};
     OutRef o;
     for (int p = 0; p < 3; p++) {

@@ -224,6 +224,7 @@ struct DecLane {
     int32_t *coef = nullptr, *llx[3] = {nullptr, nullptr, nullptr};
     HzDecPlaneBufs hz[3];
     uint8_t *d_pkt = nullptr, *h_pkt = nullptr;
+    size_t pkt_alloc = 0;
     /* per-step */
     int has_ref = 0, is_ref = 0, quant = 0, nplanes = 0, ok = 0;
     DSV_FNUM fnum = 0;
@@ -282,6 +283,7 @@ static inline double host_now_ms()
     clock_gettime(CLOCK_MONOTONIC, &ts);
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
+DSV_FRAME *mk_frame_pinned(int format, int width, int height); /* support.cpp */
 bool meta_supported(const DSV_META &m);
 void enc_prepare_state(DSV_ENCODER *enc);
 void parse_metadata_packet(const uint8_t *pkt, unsigned len, DSV_META *m);

@@ -7,6 +7,11 @@
 #include "dsv1_b200.h"
 
 #include <atomic>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "../common.cuh"
 
 extern "C" {
 
@@ -122,6 +127,84 @@ DSV_FRAME *dsv_load_planar_frame(int format, void *data, int width, int height)
     return f;
 }
 
+} /* extern "C" */
+
+/* ---- pinned picture pool ---------------------------------------------------------------------------
+ * Pictures handed out by dsv_dec live in page-locked memory so the decoder's device->host copy is a straight
+ * DMA at PCIe speed (a pageable destination is staged through a bounce buffer at a fraction of that).
+ * Page-locking is slow, so the storage is recycled: dsv_frame_ref_dec returns it here instead of freeing. */
+namespace {
+struct PinnedPool {
+    std::mutex m;
+    std::unordered_map<size_t, std::vector<uint8_t *>> idle;
+    std::unordered_map<uint8_t *, size_t> owned;
+};
+PinnedPool &pinned_pool()
+{
+    static PinnedPool *p = new PinnedPool(); /* never destroyed: frames may outlive static destruction order */
+    return *p;
+}
+uint8_t *pinned_get(size_t bytes)
+{
+    PinnedPool &pp = pinned_pool();
+    {
+        std::lock_guard<std::mutex> lk(pp.m);
+        auto it = pp.idle.find(bytes);
+        if (it != pp.idle.end() && !it->second.empty()) {
+            uint8_t *p = it->second.back();
+            it->second.pop_back();
+            return p;
+        }
+    }
+    uint8_t *p = nullptr;
+    CUDA_CHECK(cudaMallocHost(&p, bytes));
+    std::lock_guard<std::mutex> lk(pp.m);
+    pp.owned[p] = bytes;
+    return p;
+}
+bool pinned_put(uint8_t *p)
+{
+    PinnedPool &pp = pinned_pool();
+    std::lock_guard<std::mutex> lk(pp.m);
+    auto it = pp.owned.find(p);
+    if (it == pp.owned.end()) {
+        return false;
+    }
+    pp.idle[it->second].push_back(p);
+    return true;
+}
+} // namespace
+
+namespace dsv {
+DSV_FRAME *mk_frame_pinned(int format, int width, int height);
+}
+
+/* bordered frame (same layout as dsv_mk_frame(..., 1)) in pinned memory; contents are NOT cleared */
+DSV_FRAME *dsv::mk_frame_pinned(int format, int width, int height)
+{
+    DSV_FRAME *f = (DSV_FRAME *) dsv_alloc(sizeof(DSV_FRAME));
+    const int ext = DSV_MAX_BLOCK_SIZE;
+    const int hs = DSV_FORMAT_H_SHIFT(format), vs = DSV_FORMAT_V_SHIFT(format);
+    const int cw = DSV_ROUND_SHIFT(width, hs), ch = DSV_ROUND_SHIFT(height, vs);
+    f->refcount = 1;
+    f->format = format;
+    f->width = width;
+    f->height = height;
+    f->border = 1;
+    set_plane(&f->planes[0], format, width, height, (int) DSV_ROUND_POW2(width + 2 * ext, 4), 0, 0, height + 2 * ext);
+    set_plane(&f->planes[1], format, cw, ch, (int) DSV_ROUND_POW2(cw + 2 * ext, 4), hs, vs, ch + 2 * ext);
+    set_plane(&f->planes[2], format, cw, ch, (int) DSV_ROUND_POW2(cw + 2 * ext, 4), hs, vs, ch + 2 * ext);
+    f->alloc = pinned_get((size_t) f->planes[0].len + f->planes[1].len + f->planes[2].len);
+    uint8_t *at = f->alloc;
+    for (int c = 0; c < 3; c++) {
+        f->planes[c].data = at + f->planes[c].stride * ext + ext;
+        at += f->planes[c].len;
+    }
+    return f;
+}
+
+extern "C" {
+
 DSV_FRAME *dsv_frame_ref_inc(DSV_FRAME *frame)
 {
     DSV_ASSERT(frame && frame->refcount > 0);
@@ -133,7 +216,7 @@ void dsv_frame_ref_dec(DSV_FRAME *frame)
 {
     DSV_ASSERT(frame && frame->refcount > 0);
     if (--frame->refcount == 0) {
-        if (frame->alloc) {
+        if (frame->alloc && !pinned_put(frame->alloc)) {
             dsv_free(frame->alloc);
         }
         dsv_free(frame);

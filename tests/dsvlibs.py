@@ -39,7 +39,7 @@ def make_cfg(w, h, fmt="420", gop=12, qp=85, rc_mode=0, **kw):
              quality=qp_to_quality(qp), rc_mode=rc_mode, bitrate=0, do_scd=1, scd_delta=4, intra_pct=50,
              pyr_levels=0, stable_refresh=0, max_q_step=MAX_QUALITY // 200, min_quality=qp_to_quality(1),
              max_quality=qp_to_quality(100), min_i_quality=qp_to_quality(5), hm_nudge=1)
-    d.update(kw)
+    d.update(kw)   # e.g. quality=..., bitrate=... (ABR: the CLI scales quality by 3/2, dsv_main.c:476-478)
     if d["stable_refresh"] == 0:
         d["stable_refresh"] = min(max(d["gop"] - 1, 1), 14)
     return (C.c_int * len(CFG_KEYS))(*[int(d[k]) for k in CFG_KEYS])

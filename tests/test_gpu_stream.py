@@ -74,3 +74,45 @@ def test_decoder_error_paths(gpu):
     bad[pk[0]] = ord("X")   # corrupt the FourCC of the first picture packet
     nf, _, _, _ = gpu.decode_stream(bytes(bad), w, h, L.SUBSAMP[fmt], n)
     assert nf <= 1
+
+
+@pytest.mark.parametrize("case", [(352, 288, "420", 40, 26, 17, 12, 800000), (640, 360, "420", 20, 27, 0, 12, 2500000)])
+def test_abr_rate_control_vs_reference(gpu, ref, case):
+    """ABR (the CLI's default mode, dsv_encoder.c:84-160,816-848): every picture's quantiser depends on the sizes of the
+    packets before it, so a single byte of difference anywhere would snowball -- the stream must still be identical."""
+    w, h, fmt, n, seed, cut, gop, bitrate = case
+    yuv = L.synth_sequence(w, h, fmt, n, seed, cut)
+    cfg = L.make_cfg(w, h, fmt, gop=gop, qp=70, rc_mode=1, bitrate=bitrate, quality=L.qp_to_quality(70) * 3 // 2)
+    sa, pa, _ = ref.encode_sequence(cfg, yuv, n)
+    sb, pb, _ = gpu.encode_sequence(cfg, yuv, n)
+    assert pa == pb and sa == sb
+    na, da, _, _ = ref.decode_stream(sa, w, h, L.SUBSAMP[fmt], n)
+    nb, db, _, _ = gpu.decode_stream(sa, w, h, L.SUBSAMP[fmt], n)
+    assert na == nb == n and np.array_equal(da, db)
+
+
+def test_corrupt_streams_do_not_hang_or_crash(gpu):
+    """Bit flips / truncation inside picture packets: the decoder must come back (any return code) in bounded time."""
+    w, h, fmt, n = 352, 288, "420", 6
+    yuv = L.synth_sequence(w, h, fmt, n, 33, 0)
+    stream, pk, _ = gpu.encode_sequence(L.make_cfg(w, h, fmt, gop=12), yuv, n)
+    rng = np.random.default_rng(5)
+    off = [0]
+    for p in pk:
+        off.append(off[-1] + p)
+    for trial in range(12):
+        bad = bytearray(stream)
+        k = int(rng.integers(1, len(pk) - 1))            # some packet after the first metadata packet
+        lo, hi = off[k] + 14, off[k + 1]
+        if hi - lo < 8:
+            continue
+        for _ in range(int(rng.integers(1, 40))):
+            at = int(rng.integers(lo, hi))
+            bad[at] ^= 1 << int(rng.integers(0, 8))
+        nf, _, _, _ = gpu.decode_stream(bytes(bad), w, h, L.SUBSAMP[fmt], n)
+        assert -8 <= nf <= n
+    # zeroed coefficient area: never-ending exp-Golomb prefixes
+    bad = bytearray(stream)
+    bad[off[1] + 64:off[2]] = bytes(off[2] - off[1] - 64)
+    nf, _, _, _ = gpu.decode_stream(bytes(bad), w, h, L.SUBSAMP[fmt], n)
+    assert nf <= n
