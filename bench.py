@@ -282,19 +282,20 @@ def run_product(args):
                               "achieved_gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peak,
                               "share_of_step": ms / ms_dev}
         dom = max(kern.items(), key=lambda kv: kv[1]["ms_total"]) if kern else (None, None)
-        # DRAM traffic per launch from the committed `ncu --set full` captures (profiles/r1_ncu_sbt_tile_kernels_b16_split.txt,
-        # 16 lanes = 248.8 MB algorithmic): dram__bytes_read+write = 211.9 MB (forward), 235.1 MB (inverse); scaled to
-        # this launch's plane count.  Both are BELOW the algorithmic bytes (L2 absorbs part of the write-back).
-        traffic_ratio = {"sbt_fwd_tile_kernel": 211.9 / 248.8, "sbt_inv_tile_kernel(enc)": 235.1 / 248.8,
-                         "sbt_inv_tile_kernel(dec)": 235.1 / 248.8}
+        # DRAM traffic per launch from the committed `ncu --set full` capture of this very workload
+        # (profiles/r1_ncu_sbt_tile_kernels_final_b32.txt, 32 lanes = 497.7 MB algorithmic): dram__bytes_read+write =
+        # 446.9 MB (forward), 486.6 MB (inverse); scaled to this launch's plane count.  Both are BELOW the algorithmic
+        # bytes (L2 absorbs part of the write-back): no wasted re-reads.
+        traffic_ratio = {"sbt_fwd_tile_kernel": 446.9 / 497.7, "sbt_inv_tile_kernel(enc)": 486.6 / 497.7,
+                         "sbt_inv_tile_kernel(dec)": 486.6 / 497.7}
         for name, kv in kern.items():
             kv["traffic_bytes_per_launch"] = kv["bytes_per_launch"] * traffic_ratio[name]
         roofline = None
         if dom[0]:
             roofline = {"kernel": dom[0], "bound": "hbm", "achieved": dom[1]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                         "frac": dom[1]["frac"], "traffic": dom[1]["traffic_bytes_per_launch"], "peak_source": peak_src,
-                        "traffic_source": "ncu --set full capture of the same kernel at 16 lanes, scaled by planes per launch "
-                                          "(profiles/r1_ncu_sbt_tile_kernels_b16_split.txt)",
+                        "traffic_source": "ncu --set full capture of the same kernel and workload, scaled by planes per launch "
+                                          "(profiles/r1_ncu_sbt_tile_kernels_final_b32.txt)",
                         "algorithmic_bytes_per_plane": "w*h (u8 samples) + 4*cw*ch (int32 coefficients)",
                         "all_sbt_tile_kernels": {k: round(v["frac"], 3) for k, v in kern.items()}}
         stream_bytes = sum(lens_h)
