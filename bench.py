@@ -176,6 +176,42 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # product arm
 # ------------------------------------------------------------------------------------------------------
+def _cpulist(txt):
+    cpus = set()
+    for part in txt.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_near_gpu(torch, local, world):
+    """One process per GPU: run this rank's host threads (and first-touch its pinned staging memory) on the CPUs of
+    the NUMA node the GPU hangs off, and size the library's host thread pool to this rank's share of the cores.
+    Pure placement -- no effect on results."""
+    note = "none"
+    try:
+        try:
+            pr = torch.cuda.get_device_properties(local)
+            bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        except AttributeError:
+            q = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                               capture_output=True, text=True, timeout=20).stdout.strip().lower()
+            dom, rest = q.split(":", 1)
+            bdf = dom[-4:] + ":" + rest
+        cpus = _cpulist(open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read()) & os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            note = "numa-local cpus (%d)" % len(cpus)
+    except Exception as e:  # topology not exposed: leave the scheduler alone
+        note = "unbound (%s)" % type(e).__name__
+    share = max(2, min(8, len(os.sched_getaffinity(0)) * (1 if world == 1 else 2) // max(1, world)))
+    os.environ.setdefault("DSV_HOST_THREADS", str(share))
+    return note + ", host threads %s" % os.environ["DSV_HOST_THREADS"]
+
+
+
 def run_product(args):
     import numpy as np
     import torch
@@ -188,6 +224,7 @@ def run_product(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
     torch.cuda.set_device(local)
+    pin_note = bind_near_gpu(torch, local, world)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     gpu = L.gpu()
@@ -306,7 +343,7 @@ def run_product(args):
                 "e2e": {"value": e2e, "unit": "pictures/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": B * seq_bytes + stream_bytes, "d2h_bytes_per_step": B * seq_bytes + stream_bytes},
                 "gpu_launches": int(es["kernel_launches"] + ds["kernel_launches"]),
-                "roofline": roofline, "kernels": kern, "clocks": clocks,
+                "roofline": roofline, "kernels": kern, "clocks": clocks, "host_placement": pin_note,
                 "stream_bytes_per_step": stream_bytes}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_single(h_yuv.numpy(), seq_bytes)

@@ -161,9 +161,17 @@ DSV_D unsigned ld4u(const uint8_t *p)
     return __funnelshift_r(lo, q[1], sh);
 }
 DSV_HD int byte_of(unsigned w, int i) { return (int) ((w >> (8 * i)) & 0xff); }
+/* four ints -> four saturated bytes, a in the lowest byte: two cvt.pack.sat instructions on the device */
 DSV_HD unsigned pack_u8x4(int a, int b, int c, int d)
 {
+#if defined(__CUDA_ARCH__)
+    unsigned hi, r;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(a), "r"(hi));
+    return r;
+#else
     return (unsigned) clamp_u8(a) | ((unsigned) clamp_u8(b) << 8) | ((unsigned) clamp_u8(c) << 16) | ((unsigned) clamp_u8(d) << 24);
+#endif
 }
 /* per-byte (a + b + 1) >> 1 */
 DSV_HD unsigned avg_up_u8x4(unsigned a, unsigned b) { return (a | b) - (((a ^ b) >> 1) & 0x7f7f7f7fu); }

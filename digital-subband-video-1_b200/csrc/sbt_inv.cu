@@ -42,6 +42,18 @@ DSV_D int smooth_nudge(int c, int lp, int ln, int hb, int bound)
     return hb + iclamp(t, -bound, bound);
 }
 
+/* same, on the two LL differences mn0 = lp - c and mx0 = c - ln (so lp - ln = mn0 + mx0) */
+DSV_D int smooth_nudge_d(int mn0, int mx0, int hb, int bound)
+{
+    const int mx = imin(imax(mn0, mx0), 0), mn = imax(imin(mn0, mx0), 0);
+    if (mx == mn) {
+        return hb;
+    }
+    int t = iclamp(rnd_shift<2>(mn0 + mx0), mx, mn);
+    t = rnd_shift<1>(t - 2 * hb);
+    return hb + iclamp(t, -bound, bound);
+}
+
 struct Win {
     int a, b;   /* x range [a,b) in LL coordinates of this level */
     int ha, hb; /* y range */
@@ -67,11 +79,7 @@ static size_t inv_tile_smem(bool anyI)
     return (size_t) (INV_OFF3 + (anyI ? INV_I_EXTRA : 0)) * sizeof(int32_t);
 }
 
-DSV_D unsigned pack4_u8(int a, int b, int c, int d)
-{
-    return (unsigned) clamp_u8(a + 128) | ((unsigned) clamp_u8(b + 128) << 8) | ((unsigned) clamp_u8(c + 128) << 16) |
-           ((unsigned) clamp_u8(d + 128) << 24);
-}
+DSV_D unsigned pack4_u8(int a, int b, int c, int d) { return pack_u8x4(a + 128, b + 128, c + 128, d + 128); }
 
 /* store 8 reconstructed samples of one output row (sbc2int, sbt.c:594-614): only pw x ph is written */
 DSV_D void store_row8(const SbtJob &J, int oy, int ox, const int *v)
@@ -118,10 +126,14 @@ DSV_D void inv_windows(const SbtJob &J, Win *W, int base, int top, int gx0, int 
         Win w;
         w.pa = a >> 1; w.pb = ((b - 1) >> 1) + 1;
         w.qa = ha >> 1; w.qb = ((hb - 1) >> 1) + 1;
-        w.a = imax(w.pa - halo, 0); w.b = imin(w.pb + halo, wo);
-        w.ha = imax(w.qa - halo, 0); w.hb = imin(w.qb + halo, ho);
+        /* level 1 of a filtered P plane: one extra column / row past the LL quadrant holds the value the
+         * reference reads as "next LL" of the last pair, so the streaming loop has no
+         * edge cases */
+        const int ext = (l == 1 && filtered && !isI) ? 1 : 0;
+        w.a = imax(w.pa - halo, 0); w.b = imin(w.pb + halo, wo + ext);
+        w.ha = imax(w.qa - halo, 0); w.hb = imin(w.qb + halo, ho + ext);
         W[l] = w;
-        a = w.a; b = w.b; ha = w.ha; hb = w.hb;
+        a = w.a; b = imin(w.b, wo); ha = w.ha; hb = imin(w.hb, ho); /* the extra column / row is not produced by level l+1 */
     }
 }
 
@@ -285,6 +297,20 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, 5) sbt_inv_tile_kernel(const
     }
     __syncthreads();
     inv_haar_level(J, 2, W[2], W[1], win2, win1, nullptr, 0);
+    if (!isI && filtered) {
+        const Win w = W[1];
+        const int ww = w.b - w.a, wo = cw >> 1, ho = ch >> 1;
+        if (w.b == wo + 1) { /* right plane edge: "next LL" of the last pair of row y is LH[0] of that row */
+            for (int y = w.ha + tid; y < imin(w.hb, ho); y += SBT_TILE_THREADS) {
+                win1[(y - w.ha) * ww + (wo - w.a)] = J.coef[(size_t) y * cw + wo];
+            }
+        }
+        if (w.hb == ho + 1) { /* bottom plane edge: HL row 0 */
+            for (int x = w.a + tid; x < imin(w.b, wo); x += SBT_TILE_THREADS) {
+                win1[(ho - w.ha) * ww + (x - w.a)] = J.coef[(size_t) ho * cw + x];
+            }
+        }
+    }
     __syncthreads();
 
     /* ---- level 1 of P frames: a thread owns 4 adjacent pairs = 8 x 2 output samples (cw, ch are even, so
@@ -323,25 +349,42 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, 5) sbt_inv_tile_kernel(const
             }
             const int32_t *pc = LLw + (jy - w.ha) * ww + (jx - w.a);
             int r0[8], r1[8];
+            int Lc[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const int LL = i < nv ? pc[i] : 0;
-                if (filtered && i < nv) {
-                    if (jx + i > 0) {
-                        const int lp = pc[i - 1];
-                        const int ln = (jx + i + 1 < wo) ? pc[i + 1] : J.coef[(size_t) jy * cw + wo];
-                        LH[i] = smooth_nudge(LL, lp, ln, LH[i], bound);
-                    }
-                    if (jy > 0) {
-                        const int lp = pc[i - ww];
-                        const int ln = (jy + 1 < ho) ? pc[i + ww] : J.coef[(size_t) ho * cw + jx + i];
-                        HL[i] = smooth_nudge(LL, lp, ln, HL[i], bound);
+                Lc[i] = pc[i];
+            }
+            if (filtered) {
+                /* horizontal nudges share the LL differences of neighbouring pairs; the window already holds the
+                 * reference's "next LL" values past the quadrant, only the first column / row of the plane is special */
+                int d[5];
+                d[0] = (jx > 0 ? pc[-1] : Lc[0]) - Lc[0];
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    d[i + 1] = Lc[i] - Lc[i + 1];
+                }
+                d[4] = Lc[3] - pc[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (i > 0 || jx > 0) {
+                        LH[i] = smooth_nudge_d(d[i], d[i + 1], LH[i], bound);
                     }
                 }
-                r0[2 * i] = div4_trunc(LL + LH[i] + HL[i] + HH[i]);
-                r0[2 * i + 1] = div4_trunc(LL - LH[i] + HL[i] - HH[i]);
-                r1[2 * i] = div4_trunc(LL + LH[i] - HL[i] - HH[i]);
-                r1[2 * i + 1] = div4_trunc(LL - LH[i] - HL[i] + HH[i]);
+                if (jy > 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        HL[i] = smooth_nudge_d(pc[i - ww] - Lc[i], Lc[i] - pc[i + ww], HL[i], bound);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int LL = Lc[i];
+                const int sa = LL + LH[i], sb = LL - LH[i], sc = HL[i] + HH[i], sd = HL[i] - HH[i];
+                r0[2 * i] = div4_trunc(sa + sc);
+                r0[2 * i + 1] = div4_trunc(sb + sd);
+                r1[2 * i] = div4_trunc(sa - sc);
+                r1[2 * i + 1] = div4_trunc(sb - sd);
             }
             store_row8(J, 2 * jy, 2 * jx, r0);
             store_row8(J, 2 * jy + 1, 2 * jx, r1);
