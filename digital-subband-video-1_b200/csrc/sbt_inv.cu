@@ -129,7 +129,7 @@ DSV_D void inv_windows(const SbtJob &J, Win *W, int base, int top, int gx0, int 
         /* level 1 of a filtered P plane: one extra column / row past the LL quadrant holds the value the
          * reference reads as "next LL" of the last pair, so the streaming loop has no
          * edge cases */
-        const int ext = (l == 1 && filtered && !isI) ? 1 : 0;
+        const int ext = (filtered && ((l == 1 && !isI) || (l == 2 && base == 0))) ? 1 : 0;
         w.a = imax(w.pa - halo, 0); w.b = imin(w.pb + halo, wo + ext);
         w.ha = imax(w.qa - halo, 0); w.hb = imin(w.qb + halo, ho + ext);
         W[l] = w;
@@ -287,16 +287,87 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, 5) sbt_inv_tile_kernel(const
     }
     __syncthreads();
     {
+        /* LL_2 window, already scaled by 5/4 (sbt.c:20-22) and, for filtered planes, extended by the column / row
+         * the reference reads as "next LL" of the last pair (Appendix B-2) */
         const Win w = W[2];
-        const int ww = w.b - w.a, wh = w.hb - w.ha, wo = sbt_wo(cw, 2);
+        const int ww = w.b - w.a, wh = w.hb - w.ha, wo = sbt_wo(cw, 2), ho = sbt_wo(ch, 2);
         const int32_t *ll2 = J.llx + J.ll2_off;
         for (int i = tid; i < ww * wh; i += SBT_TILE_THREADS) {
-            int x = i % ww, y = i / ww;
-            win2[y * ww + x] = ll2[(size_t) (w.ha + y) * wo + w.a + x];
+            const int y = (i * ((1 << 20) / ww + 1)) >> 20, x = i - y * ww; /* i / ww for i < 2^10, ww <= 36 */
+            const int gx = w.a + x, gy = w.ha + y;
+            int v = 0;
+            if (gx < wo && gy < ho) {
+                v = ll2[(size_t) gy * wo + gx];
+            } else if (gx == wo && gy < ho) {
+                v = J.coef[(size_t) gy * cw + wo];
+            } else if (gy == ho && gx < wo) {
+                v = J.coef[(size_t) ho * cw + gx];
+            }
+            win2[i] = ll_up(v);
         }
     }
     __syncthreads();
-    inv_haar_level(J, 2, W[2], W[1], win2, win1, nullptr, 0);
+    {
+        /* level 2 (Haar with LL scaling, both frame types): one pair per thread into the LL_1 window */
+        const Win w = W[2], o = W[1];
+        const int ww = w.b - w.a, oww = o.b - o.a;
+        const int ws = sbt_ws(cw, 2), hs = sbt_ws(ch, 2), wo = sbt_wo(cw, 2), ho = sbt_wo(ch, 2);
+        const int bound = J.hqp[2];
+        const int npx = w.pb - w.pa, npy = w.qb - w.qa;
+        const int mag = (1 << 20) / npx + 1;
+        const int o_b = imin(o.b, ws), o_hb = imin(o.hb, hs); /* level 2 produces LL_1 proper only */
+        for (int task = tid; task < npx * npy; task += SBT_TILE_THREADS) {
+            const int ty2 = (task * mag) >> 20, tx2 = task - ty2 * npx;
+            const int jx = w.pa + tx2, jy = w.qa + ty2;
+            const bool col2 = 2 * jx + 1 < ws, row2 = 2 * jy + 1 < hs;
+            const int32_t *pc = win2 + (jy - w.ha) * ww + (jx - w.a);
+            const int LL = pc[0];
+            int v00, v01 = 0, v10 = 0, v11 = 0;
+            if (col2 && row2) {
+                const int32_t *pb = J.coef + (size_t) jy * cw + wo + jx;
+                int LH = pb[0];
+                const int32_t *pb2 = J.coef + (size_t) (ho + jy) * cw + jx;
+                int HL = pb2[0];
+                const int HH = pb2[wo];
+                if (filtered) {
+                    if (jx > 0) {
+                        LH = smooth_nudge_d(pc[-1] - LL, LL - pc[1], LH, bound);
+                    }
+                    if (jy > 0) {
+                        HL = smooth_nudge_d(pc[-ww] - LL, LL - pc[ww], HL, bound);
+                    }
+                }
+                const int sa = LL + LH, sb = LL - LH, sc = HL + HH, sd = HL - HH;
+                v00 = div4_trunc(sa + sc);
+                v01 = div4_trunc(sb + sd);
+                v10 = div4_trunc(sa - sc);
+                v11 = div4_trunc(sb - sd);
+            } else if (row2) {
+                const int HL = J.coef[(size_t) (ho + jy) * cw + jx];
+                v00 = div4_trunc(LL + HL);
+                v10 = div4_trunc(LL - HL);
+            } else if (col2) {
+                const int LH = J.coef[(size_t) jy * cw + wo + jx];
+                v00 = div4_trunc(LL + LH);
+                v01 = div4_trunc(LL - LH);
+            } else {
+                v00 = div4_trunc(LL);
+            }
+            const int ox = 2 * jx, oy = 2 * jy;
+            const bool x0ok = ox >= o.a && ox < o_b, x1ok = col2 && ox + 1 >= o.a && ox + 1 < o_b;
+            const bool y0ok = oy >= o.ha && oy < o_hb, y1ok = row2 && oy + 1 >= o.ha && oy + 1 < o_hb;
+            int32_t *dst = win1 + (oy - o.ha) * oww + (ox - o.a);
+            if (y0ok) {
+                if (x0ok) dst[0] = v00;
+                if (x1ok) dst[1] = v01;
+            }
+            if (y1ok) {
+                if (x0ok) dst[oww] = v10;
+                if (x1ok) dst[oww + 1] = v11;
+            }
+        }
+    }
+    __syncthreads();
     if (!isI && filtered) {
         const Win w = W[1];
         const int ww = w.b - w.a, wo = cw >> 1, ho = ch >> 1;
