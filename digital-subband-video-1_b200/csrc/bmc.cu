@@ -78,7 +78,7 @@ DSV_D void bmc_store4(const BmcPlane &P, int mode, int gx, int gy, int nvalid, b
  * at multiples of 4) */
 DSV_D void bmc_block_plane(const BmcArgs &a, const int c, int16_t *hbuf, unsigned *scratch, int *s_avg)
 {
-    const BmcPlane P = a.pl[c];
+    const BmcPlane &P = a.pl[c];
     const int sh = c ? a.hs : 0, sv = c ? a.vs : 0;
     const int bw = a.blk_w >> sh, bh = a.blk_h >> sv;
     const int i = blockIdx.x, j = blockIdx.y;
@@ -92,10 +92,7 @@ DSV_D void bmc_block_plane(const BmcArgs &a, const int c, int16_t *hbuf, unsigne
     const int tid = threadIdx.x;
     const int mode = a.mode;
     const int words = (cw + 3) >> 2;
-    int wsh = 0;
-    while ((1 << wsh) < words) {
-        wsh++;
-    }
+    const int wsh = words > 1 ? 32 - __clz(words - 1) : 0; /* ceil(log2(words)) */
     const int wmask = (1 << wsh) - 1;
     const bool walign = ((x & 3) == 0) && ((P.istride | P.ostride | P.pstride) & 3) == 0 &&
                         ((reinterpret_cast<uintptr_t>(P.in) | reinterpret_cast<uintptr_t>(P.out) | reinterpret_cast<uintptr_t>(P.pred)) & 3) == 0;

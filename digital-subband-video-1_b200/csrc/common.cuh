@@ -154,11 +154,7 @@ DSV_D unsigned ld4u(const uint8_t *p)
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
     const unsigned *q = reinterpret_cast<const unsigned *>(a & ~(uintptr_t) 3);
     const unsigned sh = (unsigned) (a & 3) * 8;
-    const unsigned lo = q[0];
-    if (sh == 0) {
-        return lo;
-    }
-    return __funnelshift_r(lo, q[1], sh);
+    return __funnelshift_r(q[0], q[1], sh); /* sh == 0 yields q[0]; q[1] is always readable (guard band / padding) */
 }
 DSV_HD int byte_of(unsigned w, int i) { return (int) ((w >> (8 * i)) & 0xff); }
 /* four ints -> four saturated bytes, a in the lowest byte: two cvt.pack.sat instructions on the device */

@@ -107,6 +107,9 @@ static void fill_stats(const EngineStats &s, int device, int lanes, double *out)
     out[10] = (double) device;
     out[11] = (double) lanes;
     out[12] = s.host_ms;
+    out[13] = s.bmc_ms;
+    out[14] = (double) s.bmc_launches;
+    out[15] = (double) s.bmc_bytes;
 }
 
 extern "C" DSVB_ENC *dsvb_enc_create(const int *cfg, int lanes, int device)
@@ -249,6 +252,9 @@ static void add_stats(EngineStats &a, const EngineStats &b)
     a.d2h_bytes += b.d2h_bytes;
     a.pictures += b.pictures;
     a.host_ms += b.host_ms;
+    a.bmc_ms += b.bmc_ms;
+    a.bmc_launches += b.bmc_launches;
+    a.bmc_bytes += b.bmc_bytes;
 }
 
 extern "C" void dsvb_dec_stats(DSVB_DEC *d, double *stats, int reset)

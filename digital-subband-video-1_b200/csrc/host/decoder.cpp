@@ -360,7 +360,13 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
     zero_launch(d_zero, n_zero, g_.coef_total * sizeof(int32_t), st);
     hzdec_launch_jobs(d_hzj, dims, st);
     sbt_inv_launch(d_sj, sdims, g_.lo_smem, st, ev_[0], ev_[1]);
+    if (n_p) {
+        CUDA_CHECK(cudaEventRecord(ev_[2], st));
+    }
     bmc_launch(d_bmc, n_p, nbh, nbv, st);
+    if (n_p) {
+        CUDA_CHECK(cudaEventRecord(ev_[3], st));
+    }
     extend_launch(d_ext, n_ext, g_.w, g_.h, st);
     pack_launch(d_pack, n_pack, g_.w, g_.h, st);
     stats.kernel_launches += 14 + (n_p ? 1 : 0) + (n_ext ? 1 : 0) + (n_pack ? 1 : 0);
@@ -425,6 +431,12 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
             bytes += (unsigned long long) g_.pw[p] * g_.ph[p] + 4ull * g_.cw[p] * g_.ch[p];
         }
         stats.sbt_inv_bytes += bytes * (unsigned) (n_sj / 3);
+        if (n_p) {
+            CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[2], ev_[3]));
+            stats.bmc_ms += ms;
+            stats.bmc_launches++;
+            stats.bmc_bytes += 3ull * g_.frame_bytes * (unsigned) n_p;
+        }
         stats.pictures += (unsigned) (n_sj / 3);
     }
     for (int k = 0; k < n; k++) {

@@ -863,7 +863,9 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     copy1_launch(d_hf, h_frames_, sizeof(HzFrame) * (size_t) n, st);
     zero_launch(d_zero, n_zero, max_zero, st);
     if (n_p) {
+        CUDA_CHECK(cudaEventRecord(ev_[5], st));
         bmc_launch(d_bmc, n_p, g.nbh, g.nbv, st);
+        CUDA_CHECK(cudaEventRecord(ev_[6], st));
         stats.kernel_launches += 1;
     }
     sbt_fwd_launch(d_sj, sdims, g.lo_smem, st, ev_[0], ev_[1]);
@@ -959,6 +961,12 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
             stats.sbt_inv_ms += ms;
             stats.sbt_inv_launches++;
             stats.sbt_inv_bytes += bytes * (unsigned) n;
+        }
+        if (n_p) {
+            CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[5], ev_[6]));
+            stats.bmc_ms += ms;
+            stats.bmc_launches++;
+            stats.bmc_bytes += 4ull * g.frame_bytes * (unsigned) n_p;
         }
         stats.pictures += (unsigned) n;
     }

@@ -58,6 +58,8 @@ struct EngineStats {
     double sbt_fwd_ms = 0, sbt_inv_ms = 0;
     unsigned long long sbt_fwd_launches = 0, sbt_inv_launches = 0;
     unsigned long long sbt_fwd_bytes = 0, sbt_inv_bytes = 0; /* algorithmic: w*h + 4*cw*ch per plane */
+    double bmc_ms = 0;
+    unsigned long long bmc_launches = 0, bmc_bytes = 0; /* algorithmic: 4 B per sample (encoder), 3 (decoder) */
     unsigned long long kernel_launches = 0;
     unsigned long long h2d_bytes = 0, d2h_bytes = 0;
     unsigned long long pictures = 0;
@@ -202,7 +204,7 @@ private:
     int levels_;
     int L_;
     cudaStream_t st_ = 0, st_copy_ = 0;
-    cudaEvent_t ev_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_pref_[2] = {nullptr, nullptr}; /* per staging-buffer parity: prefetch copies done */
     std::vector<EncLane> lanes_;
     StepArena arena_;
@@ -265,7 +267,7 @@ private:
     int max_nblk_;
     size_t pkt_cap_;
     cudaStream_t st_ = 0, st_copy_ = 0;
-    cudaEvent_t ev_[2] = {nullptr, nullptr};
+    cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_done_ = nullptr, ev_copied_[2] = {nullptr, nullptr};
     unsigned long long step_no_ = 0;
     bool prev_nonref_ = false;

@@ -26,9 +26,10 @@ extern "C" {
 typedef struct DSVB_ENC DSVB_ENC;
 typedef struct DSVB_DEC DSVB_DEC;
 
-#define DSVB_NSTATS 13
+#define DSVB_NSTATS 16
 /* stats[]: 0 sbt_fwd_ms 1 sbt_fwd_launches 2 sbt_fwd_bytes 3 sbt_inv_ms 4 sbt_inv_launches 5 sbt_inv_bytes
- *          6 kernel_launches 7 h2d_bytes 8 d2h_bytes 9 pictures 10 device 11 lanes 12 host_ms */
+ *          6 kernel_launches 7 h2d_bytes 8 d2h_bytes 9 pictures 10 device 11 lanes 12 host_ms
+ *          13 bmc_ms 14 bmc_launches 15 bmc_bytes */
 
 DSVB_ENC *dsvb_enc_create(const int *cfg, int lanes, int device);
 void dsvb_enc_destroy(DSVB_ENC *e);

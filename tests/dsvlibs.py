@@ -266,9 +266,9 @@ def fwd_sbt_q(lib, pix, pw, ph, cw, ch, isP, c, q, stable, nbh, nbv):
 
 
 # -- additive batch API (include/dsv1_b200_batch.h) ---------------------------------------------------
-NSTATS = 13
+NSTATS = 16
 STAT_KEYS = ["sbt_fwd_ms", "sbt_fwd_launches", "sbt_fwd_bytes", "sbt_inv_ms", "sbt_inv_launches", "sbt_inv_bytes",
-             "kernel_launches", "h2d_bytes", "d2h_bytes", "pictures", "device", "lanes", "host_ms"]
+             "kernel_launches", "h2d_bytes", "d2h_bytes", "pictures", "device", "lanes", "host_ms", "bmc_ms", "bmc_launches", "bmc_bytes"]
 
 
 class BatchEncoder:
