@@ -70,6 +70,21 @@ struct CopyItem { /* control-plane data moved by SMs through mapped pinned host 
     const void *src;
     size_t bytes;
 };
+struct DevMV;
+struct DrawItem { /* debug overlay (overlay.cu) painted in place on a picture whose three planes are dense */
+    uint8_t *dst[3];
+    int stride[3], w[3], h[3];
+    const DevMV *mvs;
+    const uint8_t *stab;
+    int blk_w, blk_h, nbh, nbv;
+    int mode; /* DSV_DRAW_* bits (dsv_decoder.h:38-40) */
+};
+struct To420Item { /* chroma plane -> dense 4:2:0 chroma plane of dw x dh samples (out420.cu) */
+    PlaneRef src;
+    uint8_t *dst;
+    int dw, dh;
+    int hpass; /* 1: 4:4:4 source (horizontal then vertical pass), 0: vertical pass only */
+};
 struct ReconItem { /* dst = clamp(a + b - 128) (b.p == null: dst = a), border of dst replicated */
     PlaneRef a, b, dst;
 };
@@ -109,6 +124,8 @@ void zero_launch(const ZeroItem *d_items, int n, size_t max_bytes, cudaStream_t 
  * mapped pinned host memory */
 void copy_launch(const CopyItem *items, int n, size_t max_bytes, cudaStream_t st);
 void copy1_launch(void *dst, const void *src, size_t bytes, cudaStream_t st);
+void overlay_launch(const DrawItem *d_items, int n, cudaStream_t st);
+void to420_launch(const To420Item *d_items, int n, int max_dw, int max_dh, cudaStream_t st);
 
 /* single-frame conveniences used by the kernel-level API (kernel_api.cu) */
 void frame_extend_launch(const DevFrame &f, int nplanes, cudaStream_t st);

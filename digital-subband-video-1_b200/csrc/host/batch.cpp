@@ -33,6 +33,7 @@ struct DSVB_ENC {
 
 struct DSVB_DEC {
     int lanes, device;
+    int draw_info = 0, out420 = 0;
     DecEngine *eng;
     EngineStats carried; /* stats of engines replaced after a format change */
 };
@@ -257,6 +258,22 @@ static void add_stats(EngineStats &a, const EngineStats &b)
     a.bmc_bytes += b.bmc_bytes;
 }
 
+extern "C" void dsvb_dec_set_draw_info(DSVB_DEC *d, int mode)
+{
+    d->draw_info = mode;
+    if (d->eng) {
+        d->eng->draw_mode = mode;
+    }
+}
+
+extern "C" void dsvb_dec_set_out420p(DSVB_DEC *d, int on)
+{
+    d->out420 = on;
+    if (d->eng) {
+        d->eng->set_out420(on != 0);
+    }
+}
+
 extern "C" void dsvb_dec_stats(DSVB_DEC *d, double *stats, int reset)
 {
     EngineStats s = d->carried;
@@ -347,6 +364,8 @@ extern "C" int dsvb_decode(DSVB_DEC *d, int nseq, const uint8_t *const *streams,
                         }
                         if (!d->eng) {
                             d->eng = new DecEngine(md, L);
+                            d->eng->draw_mode = d->draw_info;
+                            d->eng->set_out420(d->out420 != 0);
                         }
                         got_meta[(size_t) k] = 1;
                         continue;
@@ -364,7 +383,7 @@ extern "C" int dsvb_decode(DSVB_DEC *d, int nseq, const uint8_t *const *streams,
                     pk[(size_t) m].dev_data = streams_dev ? streams_dev[s] + at : nullptr;
                     pk[(size_t) m].len = (unsigned) size;
                     /* frame number decides where the picture lands: peek it (fnum follows the header) */
-                    const CodecGeom &g = d->eng->geom();
+                    const CodecGeom &g = d->eng->out_geom();
                     const DSV_FNUM fno = be32(hdr + DSV_PACKET_HDR_SIZE);
                     const size_t off = (size_t) fno * g.frame_bytes;
                     if (off + g.frame_bytes > (size_t) out_caps[s]) {

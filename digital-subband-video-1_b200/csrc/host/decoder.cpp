@@ -102,13 +102,19 @@ DecEngine::DecEngine(const DSV_META &md, int lanes)
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_copied_[1], cudaEventDisableTiming));
     /* a picture packet holds three planes of at most 2 * 4 * cw * ch bytes each (dsv_decoder.c:397-401) */
     pkt_cap_ = g.coef_total * 8 + 4096 + (size_t) g.nblk * 64;
-    const size_t per_lane = 3 * (sizeof(SbtJob) + hzdec_job_size()) + sizeof(BmcArgs) + 8 * sizeof(PlaneRef) + 3 * sizeof(PackItem) + sizeof(ZeroItem) + sizeof(CopyItem) + 1024;
+    const size_t per_lane = 3 * (sizeof(SbtJob) + hzdec_job_size()) + sizeof(BmcArgs) + 8 * sizeof(PlaneRef) + 3 * sizeof(PackItem) + sizeof(ZeroItem) + sizeof(CopyItem) + sizeof(DrawItem) + sizeof(PackItem) + 2 * sizeof(To420Item) + 1024;
     arena_.create(per_lane * (size_t) L_ + 4096);
     CUDA_CHECK(cudaMalloc(&d_mv_, sizeof(DevMV) * (size_t) max_nblk_ * L_));
     CUDA_CHECK(cudaMallocHost(&h_mv_, sizeof(DevMV) * (size_t) max_nblk_ * L_));
     CUDA_CHECK(cudaMalloc(&d_stab_, (size_t) max_nblk_ * L_));
     CUDA_CHECK(cudaMallocHost(&h_stab_, (size_t) max_nblk_ * L_));
-    out_pitch_ = (g.frame_bytes + 255) & ~(size_t) 255;
+    og_ = g_;
+    {
+        CodecGeom g420;
+        plan_geometry(&g420, md.width, md.height, DSV_SUBSAMP_420);
+        const size_t fb = g.frame_bytes > g420.frame_bytes ? g.frame_bytes : g420.frame_bytes;
+        out_pitch_ = (fb + 255) & ~(size_t) 255;
+    }
     CUDA_CHECK(cudaMalloc(&d_out_all_[0], out_pitch_ * L_ + 256));
     CUDA_CHECK(cudaMalloc(&d_out_all_[1], out_pitch_ * L_ + 256));
     lanes_.resize((size_t) L_);
@@ -142,6 +148,7 @@ DecEngine::~DecEngine()
         devframe_free(&l.out[1]);
         cudaFree(l.d_pkt);
         cudaFreeHost(l.h_pkt);
+        cudaFree(l.d_draw);
     }
     arena_.destroy();
     cudaFree(d_out_all_[0]);
@@ -162,6 +169,15 @@ DecEngine::~DecEngine()
 
 void DecEngine::flush() { CUDA_CHECK(cudaStreamSynchronize(st_copy_)); }
 
+void DecEngine::set_out420(bool on)
+{
+    if (on && g_.subsamp != DSV_SUBSAMP_420) {
+        plan_geometry(&og_, g_.w, g_.h, DSV_SUBSAMP_420);
+    } else {
+        og_ = g_;
+    }
+}
+
 void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRef *out, int *codes, DSV_FNUM *fnums)
 {
     cudaStream_t st = st_;
@@ -176,6 +192,13 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
     BmcArgs *ba = arena_.push_n<BmcArgs>((size_t) n, &d_bmc);
     PlaneRef *ext = arena_.push_n<PlaneRef>((size_t) 3 * n, &d_ext);
     PackItem *pack = arena_.push_n<PackItem>((size_t) 3 * n, &d_pack);
+    DrawItem *d_draw;
+    DrawItem *draw = arena_.push_n<DrawItem>((size_t) n, &d_draw);
+    PackItem *d_pack2;
+    PackItem *pack2 = arena_.push_n<PackItem>((size_t) n, &d_pack2);
+    To420Item *d_cv;
+    To420Item *cv = arena_.push_n<To420Item>((size_t) 2 * n, &d_cv);
+    int n_draw = 0, n_pack2 = 0, n_cv = 0;
     ZeroItem *d_zero;
     ZeroItem *zero = arena_.push_n<ZeroItem>((size_t) n, &d_zero);
     int n_zero = 0;
@@ -196,6 +219,7 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
         codes[k] = DSV_DEC_ERROR;
         fnums[k] = (DSV_FNUM) -1;
         l.ok = 0;
+        l.drawn = 0;
         BitReader br(pkt, pkt_len);
         const int pkt_type = read_packet_hdr(br);
         if (pkt_type == -1 || !DSV_PT_IS_PIC(pkt_type) || (size_t) pkt_len > pkt_cap_) {
@@ -318,14 +342,88 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
             if (l.is_ref) {
                 ext[n_ext++] = plane_ref(cur, p);
             }
-            if (out[k].plane[p] && out[k].on_device && out[k].stride[p] == g.pw[p]) {
-                pack[n_pack].src = plane_ref(cur, p);
-                pack[n_pack].dst = out[k].plane[p];
-                n_pack++;
-            } else if (out[k].plane[p] && host_packed(g, out[k])) {
+        }
+        /*
+         * Where the picture goes.  F[p]: dense destination in the OUTPUT format (the caller's device planes, or the
+         * staging buffer a packed host destination is served from); strided destinations are copied straight from
+         * the bordered frame later.  The overlay is painted on a dense copy, never on the frame the next picture
+         * predicts from; -out420p converts chroma on the way out.
+         */
+        const CodecGeom &og = og_;
+        const bool conv = og.subsamp != g.subsamp;
+        const bool hostp = host_packed(og, out[k]);
+        bool dense_out = true;
+        for (int p = 0; p < 3; p++) {
+            dense_out = dense_out && out[k].plane[p] && out[k].on_device && out[k].stride[p] == og.pw[p];
+        }
+        bool want_out = out[k].plane[0] != nullptr;
+        if (conv && want_out && !dense_out && !hostp) {
+            DSV_ERROR(("4:2:0 output needs a dense destination"));
+            want_out = false;
+        }
+        l.noout = !want_out;
+        l.drawn = draw_mode && isP && want_out;
+        const bool scratch = l.drawn && (conv || (!dense_out && !hostp));
+        if (scratch && !l.d_draw) {
+            CUDA_CHECK(cudaMalloc(&l.d_draw, g.frame_bytes + 256));
+        }
+        if (scratch && !conv) {
+            l.drawn = 2; /* the picture leaves from the overlay's own copy */
+        }
+        DrawItem *di = nullptr;
+        if (l.drawn) {
+            di = &draw[n_draw++];
+            memset(di, 0, sizeof(*di));
+            di->mvs = d_mv_ + (size_t) li * max_nblk_;
+            di->stab = d_stab_ + (size_t) li * max_nblk_;
+            di->blk_w = g.blk_w;
+            di->blk_h = g.blk_h;
+            di->nbh = g.nbh;
+            di->nbv = g.nbv;
+            di->mode = draw_mode;
+        }
+        for (int p = 0; p < 3 && want_out; p++) {
+            uint8_t *F = nullptr;
+            if (out[k].plane[p] && out[k].on_device && out[k].stride[p] == og.pw[p] && (dense_out || (!l.drawn && !conv))) {
+                F = out[k].plane[p];
+            } else if (out[k].plane[p] && hostp) {
                 /* host destination, packed layout: pack on the device, one contiguous copy later */
-                pack[n_pack].src = plane_ref(cur, p);
-                pack[n_pack].dst = d_out_all_[step_no_ & 1] + out_pitch_ * li + g.plane_off[p];
+                F = d_out_all_[step_no_ & 1] + out_pitch_ * li + og.plane_off[p];
+            }
+            /* N: dense picture in the stream's own format, the overlay's canvas */
+            uint8_t *N = scratch ? l.d_draw + g.plane_off[p] : F;
+            PlaneRef from = plane_ref(cur, p);
+            if (l.drawn) {
+                pack[n_pack].src = from;
+                pack[n_pack].dst = N;
+                n_pack++;
+                di->dst[p] = N;
+                di->stride[p] = g.pw[p];
+                di->w[p] = g.pw[p];
+                di->h[p] = g.ph[p];
+                from.p = N;
+                from.stride = g.pw[p];
+                if (!conv) {
+                    continue;
+                }
+            }
+            if (!F) {
+                continue;
+            }
+            if (conv && p > 0) {
+                To420Item &t = cv[n_cv++];
+                t.src = from;
+                t.dst = F;
+                t.dw = og.pw[p];
+                t.dh = og.ph[p];
+                t.hpass = g.subsamp == DSV_SUBSAMP_444;
+            } else if (l.drawn) { /* luma of a drawn + converted picture: canvas -> destination */
+                pack2[n_pack2].src = from;
+                pack2[n_pack2].dst = F;
+                n_pack2++;
+            } else {
+                pack[n_pack].src = from;
+                pack[n_pack].dst = F;
                 n_pack++;
             }
         }
@@ -369,35 +467,45 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
     }
     extend_launch(d_ext, n_ext, g_.w, g_.h, st);
     pack_launch(d_pack, n_pack, g_.w, g_.h, st);
-    stats.kernel_launches += 14 + (n_p ? 1 : 0) + (n_ext ? 1 : 0) + (n_pack ? 1 : 0);
+    overlay_launch(d_draw, n_draw, st);
+    pack_launch(d_pack2, n_pack2, g_.w, g_.h, st);
+    to420_launch(d_cv, n_cv, og_.pw[1], og_.ph[1], st);
+    stats.kernel_launches += 14 + (n_p ? 1 : 0) + (n_ext ? 1 : 0) + (n_pack ? 1 : 0) + (n_draw ? 1 : 0) + (n_pack2 ? 1 : 0) + (n_cv ? 1 : 0);
     CUDA_CHECK(cudaEventRecord(ev_done_, st));
     CUDA_CHECK(cudaStreamWaitEvent(st_copy_, ev_done_, 0));
     bool nonref = false;
     {
         /* packed host destinations at a constant distance (the batch API): one strided copy for all lanes */
         bool uniform = n > 0;
-        const ptrdiff_t delta = n > 1 && out[0].plane[0] && out[1].plane[0] ? out[1].plane[0] - out[0].plane[0] : (ptrdiff_t) g_.frame_bytes;
+        const ptrdiff_t delta = n > 1 && out[0].plane[0] && out[1].plane[0] ? out[1].plane[0] - out[0].plane[0] : (ptrdiff_t) og_.frame_bytes;
         for (int k = 0; k < n && uniform; k++) {
-            uniform = lane_ids[k] == k && lanes_[(size_t) k].ok && host_packed(g_, out[k]) && out[k].plane[0] == out[0].plane[0] + delta * k;
+            uniform = lane_ids[k] == k && lanes_[(size_t) k].ok && host_packed(og_, out[k]) && out[k].plane[0] == out[0].plane[0] + delta * k;
         }
-        uniform = uniform && delta >= (ptrdiff_t) g_.frame_bytes;
+        uniform = uniform && delta >= (ptrdiff_t) og_.frame_bytes;
         uint8_t *stage = d_out_all_[step_no_ & 1];
         if (uniform) {
-            CUDA_CHECK(cudaMemcpy2DAsync(out[0].plane[0], (size_t) delta, stage, out_pitch_, g_.frame_bytes, (size_t) n, cudaMemcpyDeviceToHost, st_copy_));
-            stats.d2h_bytes += g_.frame_bytes * (size_t) n;
+            CUDA_CHECK(cudaMemcpy2DAsync(out[0].plane[0], (size_t) delta, stage, out_pitch_, og_.frame_bytes, (size_t) n, cudaMemcpyDeviceToHost, st_copy_));
+            stats.d2h_bytes += og_.frame_bytes * (size_t) n;
         }
         for (int k = 0; k < n; k++) {
             const int li = lane_ids[k];
             DecLane &l = lanes_[(size_t) li];
-            if (!l.ok) {
+            if (!l.ok || l.noout) {
                 continue;
             }
-            nonref |= !l.is_ref;
+            nonref |= !l.is_ref || l.drawn == 2; /* the overlay's copy is single-buffered */
             if (uniform || !out[k].plane[0] || out[k].on_device) {
                 if (out[k].on_device) { /* strided device destination (not handled by pack_kernel) */
                     const DevFrame &cur = l.out[l.cur];
+                    const bool via_draw = l.drawn == 2;
                     for (int p = 0; p < 3; p++) {
-                        if (out[k].plane[p] && out[k].stride[p] != g_.pw[p]) {
+                        if (!out[k].plane[p]) {
+                            continue;
+                        }
+                        if (via_draw) {
+                            CUDA_CHECK(cudaMemcpy2DAsync(out[k].plane[p], (size_t) out[k].stride[p], l.d_draw + g_.plane_off[p], (size_t) g_.pw[p],
+                                                         (size_t) g_.pw[p], (size_t) g_.ph[p], cudaMemcpyDeviceToDevice, st_copy_));
+                        } else if (out[k].stride[p] != og_.pw[p]) {
                             CUDA_CHECK(cudaMemcpy2DAsync(out[k].plane[p], (size_t) out[k].stride[p], cur.p[p], (size_t) cur.stride[p], (size_t) g_.pw[p],
                                                          (size_t) g_.ph[p], cudaMemcpyDeviceToDevice, st_copy_));
                         }
@@ -405,16 +513,18 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
                 }
                 continue;
             }
-            if (host_packed(g_, out[k])) {
-                CUDA_CHECK(cudaMemcpyAsync(out[k].plane[0], stage + out_pitch_ * li, g_.frame_bytes, cudaMemcpyDeviceToHost, st_copy_));
-            } else { /* strided host frame (dsv_dec): straight from the bordered frame */
+            if (host_packed(og_, out[k])) {
+                CUDA_CHECK(cudaMemcpyAsync(out[k].plane[0], stage + out_pitch_ * li, og_.frame_bytes, cudaMemcpyDeviceToHost, st_copy_));
+            } else { /* strided host frame (dsv_dec): straight from the bordered frame, or from the overlay's copy */
                 const DevFrame &cur = l.out[l.cur];
                 for (int p = 0; p < 3; p++) {
-                    CUDA_CHECK(cudaMemcpy2DAsync(out[k].plane[p], (size_t) out[k].stride[p], cur.p[p], (size_t) cur.stride[p], (size_t) g_.pw[p],
+                    const uint8_t *src = l.drawn == 2 ? l.d_draw + g_.plane_off[p] : cur.p[p];
+                    const size_t sstride = l.drawn == 2 ? (size_t) g_.pw[p] : (size_t) cur.stride[p];
+                    CUDA_CHECK(cudaMemcpy2DAsync(out[k].plane[p], (size_t) out[k].stride[p], src, sstride, (size_t) g_.pw[p],
                                                  (size_t) g_.ph[p], cudaMemcpyDeviceToHost, st_copy_));
                 }
             }
-            stats.d2h_bytes += g_.frame_bytes;
+            stats.d2h_bytes += og_.frame_bytes;
         }
     }
     CUDA_CHECK(cudaEventRecord(ev_copied_[step_no_ & 1], st_copy_));
@@ -523,6 +633,7 @@ extern "C" int dsv_dec(DSV_DECODER *d, DSV_BUF *buffer, DSV_FRAME **out, DSV_FNU
         e = new DecEngine(md, 1);
         d->ref = reinterpret_cast<DSV_IMAGE *>(e);
     }
+    e->draw_mode = d->draw_info;
     DSV_FRAME *f = mk_frame_pinned(md.subsamp, md.width, md.height);
     PktRef pr = {pkt, nullptr, pkt_len};
     OutRef o;

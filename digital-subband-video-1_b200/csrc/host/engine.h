@@ -227,8 +227,9 @@ struct DecLane {
     HzDecPlaneBufs hz[3];
     uint8_t *d_pkt = nullptr, *h_pkt = nullptr;
     size_t pkt_alloc = 0;
+    uint8_t *d_draw = nullptr; /* dense copy of the picture for the debug overlay (lazy) */
     /* per-step */
-    int has_ref = 0, is_ref = 0, quant = 0, nplanes = 0, ok = 0;
+    int has_ref = 0, is_ref = 0, quant = 0, nplanes = 0, ok = 0, drawn = 0, noout = 0;
     DSV_FNUM fnum = 0;
     HzPlaneData pd[3];
 };
@@ -252,9 +253,14 @@ public:
     /* decode one PICTURE packet on each of lane_ids[0..n); codes[k] = DSV_DEC_OK / DSV_DEC_ERROR, fnums[k] =
      * frame number; on OK the picture is written to out[k] */
     void step(int n, const int *lane_ids, const PktRef *pkts, const OutRef *out, int *codes, DSV_FNUM *fnums);
+    int draw_mode = 0; /* DSV_DECODER.draw_info: overlay painted on the OUTPUT of P pictures (dsv_decoder.c:441-447) */
     /* host-destined pictures leave on the copy stream while the next step computes: wait for all of them */
     void flush();
     const CodecGeom &geom() const { return g_; }
+    /* -out420p (dsv_main.c:674-699): pictures leave as 4:2:0 whatever the stream's subsampling; out_geom() is
+     * the layout of what step() writes */
+    void set_out420(bool on);
+    const CodecGeom &out_geom() const { return og_; }
     int lanes() const { return L_; }
     void reset_lane(int lane) { lanes_[(size_t) lane].have_ref = 0; }
     bool matches(const DSV_META &md) const { return md.width == g_.w && md.height == g_.h && md.subsamp == g_.subsamp; }
@@ -262,7 +268,7 @@ public:
     int device = 0;
 
 private:
-    CodecGeom g_;
+    CodecGeom g_, og_;
     int L_;
     int max_nblk_;
     size_t pkt_cap_;

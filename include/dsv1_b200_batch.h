@@ -55,6 +55,12 @@ void dsvb_dec_destroy(DSVB_DEC *d);
 int dsvb_decode(DSVB_DEC *d, int nseq, const uint8_t *const *streams, const uint8_t *const *streams_dev,
                 const long *lens, uint8_t *const *out, const long *out_caps, int out_on_device, int *frames);
 void dsvb_dec_stats(DSVB_DEC *d, double *stats, int reset);
+/* DSV_DECODER.draw_info for the streams decoded from now on (DSV_DRAW_* bits, dsv_decoder.h:38-41): the debug
+ * overlay is painted on the pictures written to `out`, never on the decoder's own references */
+void dsvb_dec_set_draw_info(DSVB_DEC *d, int mode);
+/* the CLI's -out420p (dsv_main.c:674-699, util.c:54-93): when on, pictures of 4:4:4 / 4:2:2 / 4:1:1 streams are
+ * written to `out` as packed 4:2:0 (frame size w*h + 2*ceil(w/2)*ceil(h/2)), converted on the device */
+void dsvb_dec_set_out420p(DSVB_DEC *d, int on);
 
 /* pinned host memory for inputs / outputs of the calls above */
 void *dsvb_host_alloc(size_t bytes);

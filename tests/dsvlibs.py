@@ -191,13 +191,15 @@ class Lib:
         assert n > 0, n
         return out[:n].tobytes(), list(pk[:npk.value]), sec.value
 
-    def decode_stream(self, stream, w, h, subsamp, nframes):
+    def decode_stream(self, stream, w, h, subsamp, nframes, draw_info=0, to_420p=0):
+        """draw_info: DSV_DECODER.draw_info (CLI -drawinfo); to_420p: the CLI's -out420p conversion of the output."""
         s = np.frombuffer(stream, dtype=np.uint8)
-        cap = frame_bytes(w, h, subsamp) * nframes
+        cap = frame_bytes(w, h, SUBSAMP["420"] if to_420p else subsamp) * nframes
         out = np.zeros(cap, dtype=np.uint8)
         meta = (C.c_int * 7)()
         sec = C.c_double(0)
-        n = self.fn("decode_stream", api=True)(ptr(s), C.c_long(len(s)), ptr(out), C.c_long(cap), meta, C.byref(sec))
+        n = self.fn("decode_stream_ex", api=True)(ptr(s), C.c_long(len(s)), ptr(out), C.c_long(cap), meta, C.byref(sec),
+                                                  C.c_int(draw_info), C.c_int(to_420p))
         return n, out, list(meta), sec.value
 
 
@@ -326,6 +328,12 @@ class BatchDecoder:
         fr = (C.c_int * n)()
         rc = self.lib.dsvb_decode(self.h, n, a_s, a_d, a_l, a_o, a_c, int(out_on_device), fr)
         return rc, list(fr)
+
+    def set_draw_info(self, mode):
+        self.lib.dsvb_dec_set_draw_info(self.h, int(mode))
+
+    def set_out420p(self, on):
+        self.lib.dsvb_dec_set_out420p(self.h, int(on))
 
     def decode(self, streams, frame_bytes, nframes):
         bufs = [np.frombuffer(s, dtype=np.uint8) for s in streams]

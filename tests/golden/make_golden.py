@@ -2,6 +2,8 @@
 """Regenerates tests/golden/streams.json by running the UNMODIFIED reference (oracle/_ref/libdsv1ref.so,
 built by oracle/Makefile from /root/reference) on SURVEY.md Appendix-C synthetic content.
 
+output_options.json pins the decoder's output options (debug overlay, 4:2:0 conversion) the same way.
+
 Each entry pins: md5 of the input yuv, md5 + length of the reference .dsv stream (CRF, -rc_mode1 in CLI
 terms) and md5 of the reference decoder's output.  Run in the build container:  python tests/golden/make_golden.py
 """
@@ -30,8 +32,40 @@ CASES = [
 ]
 
 
+# decoder output options (CLI -drawinfo / -out420p): name, w, h, fmt, frames, seed, cut, gop, qp, extra cfg
+OUTPUT_CASES = [
+    ("cif_overlay", 352, 288, "420", 8, 21, 4, 12, 30, {}),
+    ("edge_intra_444", 200, 120, "444", 4, 5, 2, 12, 60, dict(do_scd=0, intra_pct=100)),  # intra dots spill past luma
+    ("edge_intra_422", 208, 104, "422", 4, 7, 2, 12, 40, dict(do_scd=0, intra_pct=100)),
+    ("qcif_411", 176, 144, "411", 5, 6, 0, 12, 95, {}),
+    ("hd_444", 1920, 1080, "444", 4, 9, 2, 12, 70, dict(do_scd=0, intra_pct=100)),
+]
+
+
+def output_options(ref):
+    out = {}
+    for name, w, h, fmt, n, seed, cut, gop, qp, kw in OUTPUT_CASES:
+        yuv = L.synth_sequence(w, h, fmt, n, seed, cut)
+        cfg = L.make_cfg(w, h, fmt, gop=gop, qp=qp, **kw)
+        stream, _, _ = ref.encode_sequence(cfg, yuv, n)
+        e = dict(w=w, h=h, fmt=fmt, frames=n, seed=seed, cut=cut, gop=gop, qp=qp, cfg=kw,
+                 dsv_md5=hashlib.md5(stream).hexdigest(), dec={})
+        for draw in (0, 1, 2, 4, 7):
+            for to420 in (0, 1):
+                nf, dec, _, _ = ref.decode_stream(stream, w, h, L.SUBSAMP[fmt], n, draw_info=draw, to_420p=to420)
+                assert nf == n
+                e["dec"]["draw%d_420p%d" % (draw, to420)] = hashlib.md5(dec.tobytes()).hexdigest()
+        out[name] = e
+        print(name, e["dsv_md5"], flush=True)
+    json.dump(out, open(os.path.join(HERE, "output_options.json"), "w"), indent=1, sort_keys=True)
+
+
 def main():
     ref = L.ref()
+    if "--outputs-only" in sys.argv:
+        output_options(ref)
+        return
+    output_options(ref)
     out = {}
     for name, w, h, fmt, n, seed, cut, gop, qp in CASES:
         yuv = L.synth_sequence(w, h, fmt, n, seed, cut)

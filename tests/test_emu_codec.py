@@ -56,3 +56,30 @@ def test_hzcc_decode_small(emu, port):
             s, _ = port.encode_plane(co, 313, isP, 1, stable, 5, 4)
             assert np.array_equal(port.decode_plane(s, cw, ch, 313, isP, 1, stable, 5, 4),
                                   emu.decode_plane(s, cw, ch, 313, isP, 1, stable, 5, 4))
+
+
+def test_decoder_output_options_tiny(emu, ref):
+    """-drawinfo overlay (incl. intra dots that spill past the luma plane on edge blocks) and -out420p, through
+    dsv_dec and through the batch decoder's device-side conversion, vs the reference CLI's procedure."""
+    w, h, fmt, n = 120, 88, "444", 3
+    sub = L.SUBSAMP[fmt]
+    yuv = L.synth_sequence(w, h, fmt, n, 5, 2)
+    cfg = L.make_cfg(w, h, fmt, gop=12, qp=60, do_scd=0, intra_pct=100)
+    s, _, _ = ref.encode_sequence(cfg, yuv, n)
+    plain = ref.decode_stream(s, w, h, sub, n)[1]
+    for draw, to420 in ((7, 0), (5, 1)):
+        na, da, _, _ = ref.decode_stream(s, w, h, sub, n, draw_info=draw, to_420p=to420)
+        if not to420:
+            nb, db, _, _ = emu.decode_stream(s, w, h, sub, n, draw_info=draw, to_420p=to420)
+            assert na == nb == n and np.array_equal(da, db)
+        bd = L.BatchDecoder(emu, 2)
+        bd.set_draw_info(draw)
+        bd.set_out420p(to420)
+        outs, fr = bd.decode([s, s], L.frame_bytes(w, h, L.SUBSAMP["420"] if to420 else sub), n)
+        bd.close()
+        assert fr == [n, n] and np.array_equal(outs[0], da) and np.array_equal(outs[1], da)
+        if draw and not to420:
+            fb = L.frame_bytes(w, h, sub)
+            a, p = da.reshape(n, fb), plain.reshape(n, fb)
+            assert (a[:, :w * h] != p[:, :w * h]).any()
+            assert (a[:, w * h:] != p[:, w * h:]).any()  # the reference's unchecked intra dots reached chroma

@@ -116,3 +116,41 @@ def test_corrupt_streams_do_not_hang_or_crash(gpu):
     bad[off[1] + 64:off[2]] = bytes(off[2] - off[1] - 64)
     nf, _, _, _ = gpu.decode_stream(bytes(bad), w, h, L.SUBSAMP[fmt], n)
     assert nf <= n
+
+
+OUTG = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "output_options.json")))
+
+
+@pytest.mark.parametrize("name", sorted(OUTG))
+def test_decoder_output_options_golden(gpu, name):
+    """DSV_DECODER.draw_info (CLI -drawinfo; dsv_decoder.c:147-243) painted by overlay.cu, and the CLI's -out420p
+    conversion, vs md5s of the unmodified reference (tests/golden/output_options.json)."""
+    g = OUTG[name]
+    w, h, fmt, n = g["w"], g["h"], g["fmt"], g["frames"]
+    sub = L.SUBSAMP[fmt]
+    yuv = L.synth_sequence(w, h, fmt, n, g["seed"], g["cut"])
+    cfg = L.make_cfg(w, h, fmt, gop=g["gop"], qp=g["qp"], **g["cfg"])
+    stream, _, _ = gpu.encode_sequence(cfg, yuv, n)
+    assert hashlib.md5(stream).hexdigest() == g["dsv_md5"]
+    for key, md5 in sorted(g["dec"].items()):
+        draw, to420 = int(key[4]), int(key[-1])
+        nf, dec, _, _ = gpu.decode_stream(stream, w, h, sub, n, draw_info=draw, to_420p=to420)
+        assert nf == n and hashlib.md5(dec.tobytes()).hexdigest() == md5, key
+    # batch decoder: overlay and conversion both on the device, host-packed and device-resident destinations
+    import torch
+    for draw, to420 in ((7, 1), (7, 0), (0, 1)):
+        want = g["dec"]["draw%d_420p%d" % (draw, to420)]
+        fb = L.frame_bytes(w, h, L.SUBSAMP["420"] if to420 else sub)
+        bd = L.BatchDecoder(gpu, 2)
+        bd.set_draw_info(draw)
+        bd.set_out420p(to420)
+        outs, fr = bd.decode([stream, stream, stream], fb, n)
+        assert fr == [n] * 3
+        assert all(hashlib.md5(o.tobytes()).hexdigest() == want for o in outs)
+        d_out = torch.zeros(fb * n, dtype=torch.uint8, device="cuda")
+        sb = np.frombuffer(stream, dtype=np.uint8)
+        rc, fr = bd.decode_ptrs([sb.ctypes.data], None, [len(sb)], [d_out.data_ptr()], [fb * n], 1)
+        torch.cuda.synchronize()
+        bd.close()
+        assert rc == 0 and fr == [n]
+        assert hashlib.md5(d_out.cpu().numpy().tobytes()).hexdigest() == want

@@ -22,6 +22,7 @@
 #include "dsv.h"
 #include "dsv_encoder.h"
 #include "dsv_decoder.h"
+#include "util.h"
 
 #ifndef HPFX
 #error "compile with -DHPFX=ref_ or -DHPFX=dsvh_"
@@ -152,8 +153,8 @@ FN(encode_sequence)(const int *cfg, const uint8_t *yuv, int nframes,
  * meta_out (7 ints) receives width,height,subsamp,fps_num,fps_den,aspect_num,aspect_den.
  */
 int
-FN(decode_stream)(const uint8_t *stream, long len, uint8_t *yuv_out, long out_cap,
-                  int *meta_out, double *seconds)
+FN(decode_stream_ex)(const uint8_t *stream, long len, uint8_t *yuv_out, long out_cap,
+                     int *meta_out, double *seconds, int draw_info, int to_420p)
 {
     DSV_DECODER dec;
     DSV_META *meta = NULL;
@@ -162,6 +163,7 @@ FN(decode_stream)(const uint8_t *stream, long len, uint8_t *yuv_out, long out_ca
     double t0, acc = 0.0;
 
     memset(&dec, 0, sizeof(dec));
+    dec.draw_info = draw_info; /* dsv_main.c:639 */
     while (pos + DSV_PACKET_HDR_SIZE <= len) {
         const uint8_t *hdr = stream + pos;
         DSV_BUF buffer;
@@ -204,19 +206,40 @@ FN(decode_stream)(const uint8_t *stream, long len, uint8_t *yuv_out, long out_ca
             continue;
         }
         {
-            long fsz = frame_bytes(meta->width, meta->height, meta->subsamp);
+            /* -out420p (dsv_main.c:674-699): chroma goes 444 -> 422 -> 420 through the util.c filters */
+            const int conv = to_420p && meta->subsamp != DSV_SUBSAMP_420;
+            DSV_FRAME *f420 = NULL;
+            long fsz = frame_bytes(meta->width, meta->height, conv ? DSV_SUBSAMP_420 : meta->subsamp);
             long off = (long) fno * fsz;
             int c, y;
+            if (conv) {
+                f420 = dsv_mk_frame(DSV_SUBSAMP_420, frame->width, frame->height, 0);
+                if (meta->subsamp == DSV_SUBSAMP_444) {
+                    DSV_FRAME *f422 = dsv_mk_frame(DSV_SUBSAMP_422, frame->width, frame->height, 0);
+                    for (c = 1; c < 3; c++) {
+                        conv444to422(&frame->planes[c], &f422->planes[c]);
+                        conv422to420(&f422->planes[c], &f420->planes[c]);
+                    }
+                    dsv_frame_ref_dec(f422);
+                } else {
+                    for (c = 1; c < 3; c++) {
+                        conv422to420(&frame->planes[c], &f420->planes[c]);
+                    }
+                }
+            }
             if (off + fsz <= out_cap) {
                 uint8_t *o = yuv_out + off;
                 for (c = 0; c < 3; c++) {
-                    DSV_PLANE *p = &frame->planes[c];
+                    DSV_PLANE *p = (conv && c > 0) ? &f420->planes[c] : &frame->planes[c];
                     for (y = 0; y < p->h; y++) {
                         memcpy(o, DSV_GET_LINE(p, y), (size_t) p->w);
                         o += p->w;
                     }
                 }
                 nfr++;
+            }
+            if (f420) {
+                dsv_frame_ref_dec(f420);
             }
         }
         dsv_frame_ref_dec(frame);
@@ -238,4 +261,11 @@ FN(decode_stream)(const uint8_t *stream, long len, uint8_t *yuv_out, long out_ca
         *seconds = acc;
     }
     return nfr;
+}
+
+int
+FN(decode_stream)(const uint8_t *stream, long len, uint8_t *yuv_out, long out_cap,
+                  int *meta_out, double *seconds)
+{
+    return FN(decode_stream_ex)(stream, len, yuv_out, out_cap, meta_out, seconds, 0, 0);
 }
