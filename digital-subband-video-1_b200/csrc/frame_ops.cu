@@ -142,29 +142,50 @@ __global__ void __launch_bounds__(FO_BX *FO_BY) pack_kernel(const PackItem *item
     }
 }
 
+/* Border replication only touches the frame's rim: the work items are the 16-byte chunks of the 2 x 64 border rows
+ * (full bordered width, copied from the first / last row) followed by 16 slots per interior row of which 9 cover
+ * the left and right border (4 chunks left, up to 5 right when w is not a multiple of 16). */
+#define EXT_SIDE_SLOTS 16
 __global__ void __launch_bounds__(FO_BX *FO_BY) extend_kernel(const PlaneRef *items)
 {
     const PlaneRef P = items[blockIdx.z];
-    FO_FOREACH_ROW()
-    {
-        const int x0 = ck * 16 - DSV_BORDER, y = row - DSV_BORDER;
-        if (x0 >= P.w + DSV_BORDER || y >= P.h + DSV_BORDER) {
-            continue;
+    const int C = (P.w + 2 * DSV_BORDER + 15) >> 4;
+    const int nb = 2 * DSV_BORDER * C;
+    const int idx = (int) (blockIdx.x * (FO_BX * FO_BY) + threadIdx.y * FO_BX + threadIdx.x);
+    int x0, y;
+    if (idx < nb) {
+        const int r = idx / C;
+        x0 = (idx - r * C) * 16 - DSV_BORDER;
+        y = r < DSV_BORDER ? r - DSV_BORDER : P.h + (r - DSV_BORDER);
+    } else {
+        const int j = idx - nb, c = j & (EXT_SIDE_SLOTS - 1);
+        y = j / EXT_SIDE_SLOTS;
+        if (y >= P.h || c >= 9) {
+            return;
         }
-        const bool yin = y >= 0 && y < P.h;
-        if (yin && x0 >= 0 && x0 + 16 <= P.w) {
-            continue; /* interior */
+        x0 = c < 4 ? 16 * c - DSV_BORDER : (P.w & ~15) + 16 * (c - 4);
+    }
+    const bool yin = y >= 0 && y < P.h;
+    const int sy = iclamp(y, 0, P.h - 1);
+    const uint8_t *src = P.p + (size_t) sy * P.stride;
+    uint8_t *dst = P.p + (ptrdiff_t) y * P.stride + x0;
+    const int xend = P.w + DSV_BORDER;
+    if (aligned16(dst) && x0 + 16 <= xend) {
+        if (x0 + 16 <= 0 || x0 >= P.w) { /* all 16 samples repeat the row's first / last sample */
+            const unsigned v = (x0 < 0 ? src[0] : src[P.w - 1]) * 0x01010101u;
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(v, v, v, v);
+            return;
         }
-        const int sy = iclamp(y, 0, P.h - 1);
-        const uint8_t *src = P.p + (size_t) sy * P.stride;
-        uint8_t *dst = P.p + (ptrdiff_t) y * P.stride + x0;
-        const int xend = P.w + DSV_BORDER;
-    #pragma unroll 4
-        for (int e = 0; e < 16; e++) {
-            const int x = x0 + e;
-            if (x < xend && !(yin && x >= 0 && x < P.w)) {
-                dst[e] = src[iclamp(x, 0, P.w - 1)];
-            }
+        if (!yin && x0 >= 0 && x0 + 16 <= P.w && aligned16(src + x0)) {
+            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(src + x0);
+            return;
+        }
+    }
+#pragma unroll 4
+    for (int e = 0; e < 16; e++) {
+        const int x = x0 + e;
+        if (x < xend && !(yin && x >= 0 && x < P.w)) {
+            dst[e] = src[iclamp(x, 0, P.w - 1)];
         }
     }
 }
@@ -389,7 +410,8 @@ void pack_launch(const PackItem *d_items, int n, int max_w, int max_h, cudaStrea
 void extend_launch(const PlaneRef *d_items, int n, int max_w, int max_h, cudaStream_t st)
 {
     if (n > 0) {
-        DSV_LAUNCH(extend_kernel, fo_grid(max_w, max_h, n, true), dim3(FO_BX, FO_BY), 0, st, d_items);
+        const int items = 2 * DSV_BORDER * ((max_w + 2 * DSV_BORDER + 15) >> 4) + EXT_SIDE_SLOTS * max_h;
+        DSV_LAUNCH(extend_kernel, dim3(ceil_div(items, FO_BX * FO_BY), 1, n), dim3(FO_BX, FO_BY), 0, st, d_items);
         KERNEL_CHECK();
     }
 }

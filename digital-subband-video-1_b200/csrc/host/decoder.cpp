@@ -94,8 +94,11 @@ DecEngine::DecEngine(const DSV_META &md, int lanes)
     L_ = lanes;
     CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&st_copy_, cudaStreamNonBlocking));
-    for (auto &e : ev_) {
-        CUDA_CHECK(cudaEventCreate(&e));
+    for (int q = 0; q < 2; q++) {
+        for (auto &e : ev_[q]) {
+            CUDA_CHECK(cudaEventCreate(&e));
+        }
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_end_[q], cudaEventDisableTiming));
     }
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_done_, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_copied_[0], cudaEventDisableTiming));
@@ -103,11 +106,13 @@ DecEngine::DecEngine(const DSV_META &md, int lanes)
     /* a picture packet holds three planes of at most 2 * 4 * cw * ch bytes each (dsv_decoder.c:397-401) */
     pkt_cap_ = g.coef_total * 8 + 4096 + (size_t) g.nblk * 64;
     const size_t per_lane = 3 * (sizeof(SbtJob) + hzdec_job_size()) + sizeof(BmcArgs) + 8 * sizeof(PlaneRef) + 3 * sizeof(PackItem) + sizeof(ZeroItem) + sizeof(CopyItem) + sizeof(DrawItem) + sizeof(PackItem) + 2 * sizeof(To420Item) + 1024;
-    arena_.create(per_lane * (size_t) L_ + 4096);
     CUDA_CHECK(cudaMalloc(&d_mv_, sizeof(DevMV) * (size_t) max_nblk_ * L_));
-    CUDA_CHECK(cudaMallocHost(&h_mv_, sizeof(DevMV) * (size_t) max_nblk_ * L_));
     CUDA_CHECK(cudaMalloc(&d_stab_, (size_t) max_nblk_ * L_));
-    CUDA_CHECK(cudaMallocHost(&h_stab_, (size_t) max_nblk_ * L_));
+    for (int q = 0; q < 2; q++) {
+        arena_[q].create(per_lane * (size_t) L_ + 4096);
+        CUDA_CHECK(cudaMallocHost(&h_mv_[q], sizeof(DevMV) * (size_t) max_nblk_ * L_));
+        CUDA_CHECK(cudaMallocHost(&h_stab_[q], (size_t) max_nblk_ * L_));
+    }
     og_ = g_;
     {
         CodecGeom g420;
@@ -130,7 +135,6 @@ DecEngine::DecEngine(const DSV_META &md, int lanes)
         devframe_alloc(&l.out[1], g.w, g.h, g.subsamp);
         /* packets are staged lazily: most are far smaller than the format's upper bound */
         l.d_pkt = nullptr;
-        l.h_pkt = nullptr;
     }
 }
 
@@ -147,18 +151,25 @@ DecEngine::~DecEngine()
         devframe_free(&l.out[0]);
         devframe_free(&l.out[1]);
         cudaFree(l.d_pkt);
-        cudaFreeHost(l.h_pkt);
+        cudaFreeHost(l.h_pkt[0]);
+        cudaFreeHost(l.h_pkt[1]);
         cudaFree(l.d_draw);
     }
-    arena_.destroy();
+    arena_[0].destroy();
+    arena_[1].destroy();
     cudaFree(d_out_all_[0]);
     cudaFree(d_out_all_[1]);
     cudaFree(d_mv_);
-    cudaFreeHost(h_mv_);
+    cudaFreeHost(h_mv_[0]);
+    cudaFreeHost(h_mv_[1]);
     cudaFree(d_stab_);
-    cudaFreeHost(h_stab_);
-    for (auto &e : ev_) {
-        cudaEventDestroy(e);
+    cudaFreeHost(h_stab_[0]);
+    cudaFreeHost(h_stab_[1]);
+    for (int q = 0; q < 2; q++) {
+        for (auto &e : ev_[q]) {
+            cudaEventDestroy(e);
+        }
+        cudaEventDestroy(ev_end_[q]);
     }
     cudaEventDestroy(ev_done_);
     cudaEventDestroy(ev_copied_[0]);
@@ -167,7 +178,41 @@ DecEngine::~DecEngine()
     cudaStreamDestroy(st_);
 }
 
-void DecEngine::flush() { CUDA_CHECK(cudaStreamSynchronize(st_copy_)); }
+void DecEngine::flush()
+{
+    CUDA_CHECK(cudaStreamSynchronize(st_));
+    CUDA_CHECK(cudaStreamSynchronize(st_copy_));
+    collect(0);
+    collect(1);
+}
+
+/* the step that last used this parity's host buffers must have left the GPU before they are rewritten; its kernel
+ * timings are read at the same moment */
+void DecEngine::collect(int parity)
+{
+    Pending &pd = pending_[parity];
+    if (!pd.valid) {
+        return;
+    }
+    CUDA_CHECK(cudaEventSynchronize(ev_end_[parity]));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[parity][0], ev_[parity][1]));
+    stats.sbt_inv_ms += ms;
+    stats.sbt_inv_launches++;
+    unsigned long long bytes = 0;
+    for (int p = 0; p < 3; p++) {
+        bytes += (unsigned long long) g_.pw[p] * g_.ph[p] + 4ull * g_.cw[p] * g_.ch[p];
+    }
+    stats.sbt_inv_bytes += bytes * (unsigned) pd.pictures;
+    if (pd.p_pictures) {
+        CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[parity][2], ev_[parity][3]));
+        stats.bmc_ms += ms;
+        stats.bmc_launches++;
+        stats.bmc_bytes += 3ull * g_.frame_bytes * (unsigned) pd.p_pictures;
+    }
+    stats.pictures += (unsigned) pd.pictures;
+    pd.valid = false;
+}
 
 void DecEngine::set_out420(bool on)
 {
@@ -181,6 +226,13 @@ void DecEngine::set_out420(bool on)
 void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRef *out, int *codes, DSV_FNUM *fnums)
 {
     cudaStream_t st = st_;
+    const int par = (int) (step_no_ & 1);
+    collect(par);
+    StepArena &arena_ = this->arena_[par];
+    uint8_t *const h_stab_ = this->h_stab_[par];
+    DevMV *const h_mv_ = this->h_mv_[par];
+    cudaEvent_t *const ev_ = this->ev_[par];
+    int step_nblk = 0; /* lanes of a step share the block grid: vectors / stability bits are packed at that pitch */
     arena_.reset();
     SbtJob *d_sj;
     void *d_hzj;
@@ -247,8 +299,9 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
             DSV_ERROR(("mixed block sizes inside one batch step"));
             continue;
         }
-        uint8_t *stab = h_stab_ + (size_t) li * max_nblk_;
-        DevMV *mvs = h_mv_ + (size_t) li * max_nblk_;
+        step_nblk = g.nblk;
+        uint8_t *stab = h_stab_ + (size_t) li * step_nblk;
+        DevMV *mvs = h_mv_ + (size_t) li * step_nblk;
         read_stability(br, pkt, pkt_len, stab, g.nblk);
         if (l.has_ref) {
             read_motion(br, pkt, pkt_len, mvs, stab, g.nbh, g.nbv);
@@ -264,19 +317,23 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
             if ((size_t) pkt_len + 80 > l.pkt_alloc) {
                 /* staging grows with the largest packet seen (the format's upper bound, 8 bytes per coefficient,
                  * would pin hundreds of MB per lane at UHD); the previous step has completed, nothing is in flight */
+                CUDA_CHECK(cudaStreamSynchronize(st)); /* earlier steps may still read the old staging */
                 cudaFree(l.d_pkt);
-                cudaFreeHost(l.h_pkt);
+                cudaFreeHost(l.h_pkt[0]);
+                cudaFreeHost(l.h_pkt[1]);
                 l.pkt_alloc = (size_t) pkt_len * 2 + (256 << 10);
                 if (l.pkt_alloc > pkt_cap_ + 80) {
                     l.pkt_alloc = pkt_cap_ + 80;
                 }
                 CUDA_CHECK(cudaMalloc(&l.d_pkt, l.pkt_alloc));
-                CUDA_CHECK(cudaMallocHost(&l.h_pkt, l.pkt_alloc));
+                CUDA_CHECK(cudaMallocHost(&l.h_pkt[0], l.pkt_alloc));
+                CUDA_CHECK(cudaMallocHost(&l.h_pkt[1], l.pkt_alloc));
             }
-            memcpy(l.h_pkt, pkt, pkt_len);
-            memset(l.h_pkt + pkt_len, 0, 64);
+            uint8_t *h_pkt = l.h_pkt[par];
+            memcpy(h_pkt, pkt, pkt_len);
+            memset(h_pkt + pkt_len, 0, 64);
             cpy[n_cpy].dst = l.d_pkt;
-            cpy[n_cpy].src = l.h_pkt;
+            cpy[n_cpy].src = h_pkt;
             cpy[n_cpy].bytes = ((size_t) pkt_len + 64 + 15) & ~(size_t) 15;
             max_cpy = max_cpy > cpy[n_cpy].bytes ? max_cpy : cpy[n_cpy].bytes;
             n_cpy++;
@@ -323,7 +380,7 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
             s.pstride = s.ostride = cur.stride[p];
             s.coef = l.coef + g.coef_off[p];
             s.llx = l.llx[p];
-            s.stable = d_stab_ + (size_t) li * max_nblk_;
+            s.stable = d_stab_ + (size_t) li * step_nblk;
             if (p < l.nplanes) {
                 HzJob h;
                 memset(&h, 0, sizeof(h));
@@ -374,8 +431,8 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
         if (l.drawn) {
             di = &draw[n_draw++];
             memset(di, 0, sizeof(*di));
-            di->mvs = d_mv_ + (size_t) li * max_nblk_;
-            di->stab = d_stab_ + (size_t) li * max_nblk_;
+            di->mvs = d_mv_ + (size_t) li * step_nblk;
+            di->stab = d_stab_ + (size_t) li * step_nblk;
             di->blk_w = g.blk_w;
             di->blk_h = g.blk_h;
             di->nbh = g.nbh;
@@ -429,7 +486,7 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
         }
         if (isP) {
             const MotionGeom mg = {g.w, g.h, g.hs, g.vs, g.blk_w, g.blk_h, g.nbh, g.nbv, 0};
-            bmc_fill_args(&ba[n_p++], mg, d_mv_ + (size_t) li * max_nblk_, l.out[l.cur ^ 1], nullptr, cur, cur, 2);
+            bmc_fill_args(&ba[n_p++], mg, d_mv_ + (size_t) li * step_nblk, l.out[l.cur ^ 1], nullptr, cur, cur, 2);
         }
         /* dsv_decoder.c:405: coefficient planes start zeroed.  Planes that were never coded (corrupt plen) stay
          * all-zero here; the reference leaves the zeroed residual plane untouched instead. */
@@ -451,9 +508,9 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
     }
     arena_.upload(st);
     copy_launch(d_cpy, n_cpy, max_cpy, st);
-    copy1_launch(d_stab_, h_stab_, (size_t) max_nblk_ * L_, st);
+    copy1_launch(d_stab_, h_stab_, (size_t) step_nblk * L_, st);
     if (n_p) {
-        copy1_launch(d_mv_, h_mv_, sizeof(DevMV) * (size_t) max_nblk_ * L_, st);
+        copy1_launch(d_mv_, h_mv_, sizeof(DevMV) * (size_t) step_nblk * L_, st);
     }
     zero_launch(d_zero, n_zero, g_.coef_total * sizeof(int32_t), st);
     hzdec_launch_jobs(d_hzj, dims, st);
@@ -530,25 +587,11 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
     CUDA_CHECK(cudaEventRecord(ev_copied_[step_no_ & 1], st_copy_));
     prev_nonref_ = nonref;
     step_no_++;
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    {
-        float ms = 0;
-        CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
-        stats.sbt_inv_ms += ms;
-        stats.sbt_inv_launches++;
-        unsigned long long bytes = 0;
-        for (int p = 0; p < 3; p++) {
-            bytes += (unsigned long long) g_.pw[p] * g_.ph[p] + 4ull * g_.cw[p] * g_.ch[p];
-        }
-        stats.sbt_inv_bytes += bytes * (unsigned) (n_sj / 3);
-        if (n_p) {
-            CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[2], ev_[3]));
-            stats.bmc_ms += ms;
-            stats.bmc_launches++;
-            stats.bmc_bytes += 3ull * g_.frame_bytes * (unsigned) n_p;
-        }
-        stats.pictures += (unsigned) (n_sj / 3);
-    }
+    /* no wait here: the caller parses the next packets while this step runs (see collect()) */
+    CUDA_CHECK(cudaEventRecord(ev_end_[par], st));
+    pending_[par].valid = true;
+    pending_[par].pictures = n_sj / 3;
+    pending_[par].p_pictures = n_p;
     for (int k = 0; k < n; k++) {
         DecLane &l = lanes_[(size_t) lane_ids[k]];
         if (l.ok && l.is_ref) {

@@ -225,7 +225,7 @@ struct DecLane {
     int cur = 0, have_ref = 0;
     int32_t *coef = nullptr, *llx[3] = {nullptr, nullptr, nullptr};
     HzDecPlaneBufs hz[3];
-    uint8_t *d_pkt = nullptr, *h_pkt = nullptr;
+    uint8_t *d_pkt = nullptr, *h_pkt[2] = {nullptr, nullptr}; /* host staging alternates with the step parity */
     size_t pkt_alloc = 0;
     uint8_t *d_draw = nullptr; /* dense copy of the picture for the debug overlay (lazy) */
     /* per-step */
@@ -273,14 +273,22 @@ private:
     int max_nblk_;
     size_t pkt_cap_;
     cudaStream_t st_ = 0, st_copy_ = 0;
-    cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+    /* a step's host-side inputs (descriptor arena, vectors, stability bits, packet staging) and its timing events
+     * exist twice: the host parses step t+1 while the GPU still runs step t */
+    cudaEvent_t ev_[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    cudaEvent_t ev_end_[2] = {nullptr, nullptr};
+    struct Pending {
+        bool valid = false;
+        int pictures = 0, p_pictures = 0;
+    } pending_[2];
+    void collect(int parity);
     cudaEvent_t ev_done_ = nullptr, ev_copied_[2] = {nullptr, nullptr};
     unsigned long long step_no_ = 0;
     bool prev_nonref_ = false;
     std::vector<DecLane> lanes_;
-    StepArena arena_;
-    DevMV *d_mv_ = nullptr, *h_mv_ = nullptr;
-    uint8_t *d_stab_ = nullptr, *h_stab_ = nullptr;
+    StepArena arena_[2];
+    DevMV *d_mv_ = nullptr, *h_mv_[2] = {nullptr, nullptr};
+    uint8_t *d_stab_ = nullptr, *h_stab_[2] = {nullptr, nullptr};
     uint8_t *d_out_all_[2] = {nullptr, nullptr}; /* packed-picture egress staging of all lanes (step parity) */
     size_t out_pitch_ = 0;
 };
