@@ -365,6 +365,7 @@ EncEngine::EncEngine(const DSV_META &md, int gop, int pyramid_levels, int lanes)
     for (auto &e : ev_) {
         CUDA_CHECK(cudaEventCreate(&e));
     }
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_search_, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_pref_[0], cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_pref_[1], cudaEventDisableTiming));
     const size_t per_lane = 3 * (sizeof(SbtJob) + sizeof(HzJob)) + sizeof(HzFrame) + (size_t) (levels_ + 1) * sizeof(HmeArgs) +
@@ -483,6 +484,7 @@ EncEngine::~EncEngine()
     for (auto &e : ev_) {
         cudaEventDestroy(e);
     }
+    cudaEventDestroy(ev_search_);
     cudaEventDestroy(ev_pref_[0]);
     cudaEventDestroy(ev_pref_[1]);
     cudaStreamDestroy(st_copy_);
@@ -671,6 +673,21 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
             }
         }
     }
+    /* motion compensation is launched right behind the search, before the host has seen the vectors: it depends on
+     * nothing the host decides except "this stays a P picture", and when a scene change or the intra share turns
+     * the picture into an I picture its output (prediction + residual frames) is simply not used.  The GPU works
+     * on it while the host writes the packet heads. */
+    BmcArgs *d_bmc = nullptr;
+    if (n_search) {
+        BmcArgs *ba = arena_.push_n<BmcArgs>((size_t) n_search, &d_bmc);
+        int q = 0;
+        for (int k = 0; k < n; k++) {
+            EncLane &l = lanes_[(size_t) lane_ids[k]];
+            if (l.has_ref) {
+                bmc_fill_args(&ba[q++], mg, l.d_mvf[0], l.recon[l.cur ^ 1], &l.pred, l.pad[l.cur], l.xf, 1);
+            }
+        }
+    }
     ZeroItem *d_zmisc;
     ZeroItem *zmisc = arena_.push_n<ZeroItem>(1, &d_zmisc);
     zmisc->p = d_misc_;
@@ -699,10 +716,17 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         if (n_sum || n_search) {
             copy1_launch(h_misc_, d_misc_, sizeof(LaneMisc) * (size_t) L_, st);
             need_sync = true;
+            CUDA_CHECK(cudaEventRecord(ev_search_, st));
+        }
+        if (n_search) {
+            CUDA_CHECK(cudaEventRecord(ev_[5], st));
+            bmc_launch(d_bmc, n_search, g.nbh, g.nbv, st);
+            CUDA_CHECK(cudaEventRecord(ev_[6], st));
+            stats.kernel_launches += 1;
         }
     }
     if (need_sync) {
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(cudaEventSynchronize(ev_search_));
     }
 
     /* ---- phase 2: host decisions + packet heads --------------------------------------------------- */
@@ -774,12 +798,10 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     SbtJob *d_sj;
     HzJob *d_hj;
     HzFrame *d_hf = d_frames_;
-    BmcArgs *d_bmc = nullptr;
     ReconItem *d_rec = nullptr;
     PlaneRef *d_ext = nullptr;
     SbtJob *sj = arena_.push_n<SbtJob>((size_t) 3 * n, &d_sj);
     HzJob *hj = arena_.push_n<HzJob>((size_t) 3 * n, &d_hj);
-    BmcArgs *ba = n_p ? arena_.push_n<BmcArgs>((size_t) n_p, &d_bmc) : nullptr;
     const int n_i_ref = n_ref - n_p;
     ReconItem *rec = n_p ? arena_.push_n<ReconItem>((size_t) 3 * n_p, &d_rec) : nullptr;
     PlaneRef *ext = n_i_ref > 0 ? arena_.push_n<PlaneRef>((size_t) 3 * n_i_ref, &d_ext) : nullptr;
@@ -794,9 +816,6 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         const int isP = l.has_ref;
         const DevFrame &fwd_in = isP ? l.xf : (inter_ ? l.pad[l.cur] : l.xf);
         const DevFrame &inv_out = isP ? l.xf : (inter_ ? l.recon[l.cur] : l.xf);
-        if (isP) {
-            bmc_fill_args(&ba[qp], mg, l.d_mvf[0], l.recon[l.cur ^ 1], &l.pred, l.pad[l.cur], l.xf, 1);
-        }
         if (l.pkt_dirty) {
             zero[n_zero].p = l.d_pkt;
             zero[n_zero].bytes = ((size_t) l.pkt_dirty + 64 + 15) & ~(size_t) 15;
@@ -862,12 +881,6 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     copy1_launch(d_stab_, h_stab_, (size_t) g.nblk * L_, st);
     copy1_launch(d_hf, h_frames_, sizeof(HzFrame) * (size_t) n, st);
     zero_launch(d_zero, n_zero, max_zero, st);
-    if (n_p) {
-        CUDA_CHECK(cudaEventRecord(ev_[5], st));
-        bmc_launch(d_bmc, n_p, g.nbh, g.nbv, st);
-        CUDA_CHECK(cudaEventRecord(ev_[6], st));
-        stats.kernel_launches += 1;
-    }
     sbt_fwd_launch(d_sj, sdims, g.lo_smem, st, ev_[0], ev_[1]);
     hzcc_enc_launch(d_hj, 3 * n, d_chunks_, n * g.total_chunks, d_hf, n, st);
     stats.kernel_launches += 6;
@@ -962,11 +975,11 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
             stats.sbt_inv_launches++;
             stats.sbt_inv_bytes += bytes * (unsigned) n;
         }
-        if (n_p) {
+        if (n_search) {
             CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[5], ev_[6]));
             stats.bmc_ms += ms;
             stats.bmc_launches++;
-            stats.bmc_bytes += 4ull * g.frame_bytes * (unsigned) n_p;
+            stats.bmc_bytes += 4ull * g.frame_bytes * (unsigned) n_search;
         }
         stats.pictures += (unsigned) n;
     }

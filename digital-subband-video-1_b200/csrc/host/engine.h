@@ -205,6 +205,7 @@ private:
     int L_;
     cudaStream_t st_ = 0, st_copy_ = 0;
     cudaEvent_t ev_[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_search_ = nullptr; /* vectors and luma sums are on the host */
     cudaEvent_t ev_pref_[2] = {nullptr, nullptr}; /* per staging-buffer parity: prefetch copies done */
     std::vector<EncLane> lanes_;
     StepArena arena_;
