@@ -24,7 +24,6 @@ namespace dsv {
 #define BMC_THREADS 256
 
 
-DSV_D int hpf4(int a, int b, int c, int d) { return 9 * (b + c) - (a + d); }
 
 DSV_D unsigned block_sum_u32(unsigned v, unsigned *scratch /* >= 33 */)
 {
@@ -42,10 +41,12 @@ DSV_D unsigned block_sum_u32(unsigned v, unsigned *scratch /* >= 33 */)
     return t;
 }
 
-/* combine 4 predicted samples with the current word and store (prediction word kept when asked) */
-DSV_D void bmc_store4(const BmcPlane &P, int mode, int gx, int gy, int nvalid, bool vec, int p0, int p1, int p2, int p3)
+/* combine 4 predicted samples (packed, sample 0 in the lowest byte) with the current word and store (prediction
+ * word kept when asked) */
+DSV_D void bmc_store4(const BmcPlane &P, int mode, int gx, int gy, int nvalid, bool vec, unsigned pw)
 {
     const size_t io = (size_t) gy * P.istride + gx, oo = (size_t) gy * P.ostride + gx;
+    const int p0 = byte_of(pw, 0), p1 = byte_of(pw, 1), p2 = byte_of(pw, 2), p3 = byte_of(pw, 3);
     if (vec && nvalid == 4) {
         const unsigned cur = *reinterpret_cast<const unsigned *>(P.in + io);
         unsigned out;
@@ -56,8 +57,7 @@ DSV_D void bmc_store4(const BmcPlane &P, int mode, int gx, int gy, int nvalid, b
         }
         *reinterpret_cast<unsigned *>(P.out + oo) = out;
         if (P.pred) {
-            *reinterpret_cast<unsigned *>(P.pred + (size_t) gy * P.pstride + gx) =
-                (unsigned) p0 | ((unsigned) p1 << 8) | ((unsigned) p2 << 16) | ((unsigned) p3 << 24);
+            *reinterpret_cast<unsigned *>(P.pred + (size_t) gy * P.pstride + gx) = pw;
         }
         return;
     }
@@ -120,15 +120,17 @@ DSV_D void bmc_block_plane(const BmcArgs &a, const int c, int16_t *hbuf, unsigne
                 if (wx >= words) {
                     continue;
                 }
-                const uint8_t *p = r0 + (ptrdiff_t) (ly - 1) * rs + 4 * wx;
-                const unsigned wa = ld4u(p - 1), wb = ld4u(p + 3); /* p[-1..2], p[3..6] */
-                const int b0 = byte_of(wa, 0), b1 = byte_of(wa, 1), b2 = byte_of(wa, 2), b3 = byte_of(wa, 3);
-                const int b4 = byte_of(wb, 0), b5 = byte_of(wb, 1), b6 = byte_of(wb, 2);
-                int16_t *d = hbuf + ly * hstride + 4 * wx;
-                d[0] = (int16_t) hpf4(b0, b1, b2, b3);
-                d[1] = (int16_t) hpf4(b1, b2, b3, b4);
-                d[2] = (int16_t) hpf4(b2, b3, b4, b5);
-                d[3] = (int16_t) hpf4(b3, b4, b5, b6);
+                /* bytes p[-1..6] of the row: three aligned words, shifted once; the taps of sample e are the four
+                 * bytes starting at e */
+                const uint8_t *p = r0 + (ptrdiff_t) (ly - 1) * rs + 4 * wx - 1;
+                const unsigned *q = reinterpret_cast<const unsigned *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t) 3);
+                const unsigned bsh = ((unsigned) reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
+                const unsigned q0 = q[0], q1 = q[1], q2 = q[2];
+                const unsigned wa = __funnelshift_r(q0, q1, bsh), wb = __funnelshift_r(q1, q2, bsh);
+                const int h0 = hp_taps_u8x4(wa), h1 = hp_taps_u8x4(__funnelshift_r(wa, wb, 8));
+                const int h2 = hp_taps_u8x4(__funnelshift_r(wa, wb, 16)), h3 = hp_taps_u8x4(__funnelshift_r(wa, wb, 24));
+                *reinterpret_cast<uint2 *>(hbuf + ly * hstride + 4 * wx) =
+                    make_uint2(__byte_perm((unsigned) h0, (unsigned) h1, 0x5410), __byte_perm((unsigned) h2, (unsigned) h3, 0x5410));
             }
             __syncthreads();
         }
@@ -139,51 +141,59 @@ DSV_D void bmc_block_plane(const BmcArgs &a, const int c, int16_t *hbuf, unsigne
             }
             const int lx = 4 * wx;
             const uint8_t *p = r0 + (ptrdiff_t) ly * rs + lx;
-            int v0, v1, v2, v3;
+            unsigned pw; /* the four predicted samples, saturated to 8 bits */
             if (phase == 0) {
-                const unsigned w = ld4u(p);
-                v0 = byte_of(w, 0); v1 = byte_of(w, 1); v2 = byte_of(w, 2); v3 = byte_of(w, 3);
+                pw = ld4u(p);
             } else if (c == 0) {
                 if (phase == 1) {
+                    int v0, v1, v2, v3;
                     const unsigned wa = ld4u(p - rs), wb = ld4u(p), wc = ld4u(p + rs), wd = ld4u(p + 2 * rs);
-                    v0 = clamp_u8((hpf4(byte_of(wa, 0), byte_of(wb, 0), byte_of(wc, 0), byte_of(wd, 0)) + 8) >> 4);
-                    v1 = clamp_u8((hpf4(byte_of(wa, 1), byte_of(wb, 1), byte_of(wc, 1), byte_of(wd, 1)) + 8) >> 4);
-                    v2 = clamp_u8((hpf4(byte_of(wa, 2), byte_of(wb, 2), byte_of(wc, 2), byte_of(wd, 2)) + 8) >> 4);
-                    v3 = clamp_u8((hpf4(byte_of(wa, 3), byte_of(wb, 3), byte_of(wc, 3), byte_of(wd, 3)) + 8) >> 4);
+                    /* 4x4 byte transpose: column e of the four rows becomes one word */
+                    const unsigned ab0 = __byte_perm(wa, wb, 0x5140), ab1 = __byte_perm(wa, wb, 0x7362);
+                    const unsigned cd0 = __byte_perm(wc, wd, 0x5140), cd1 = __byte_perm(wc, wd, 0x7362);
+                    v0 = (hp_taps_u8x4(__byte_perm(ab0, cd0, 0x5410)) + 8) >> 4;
+                    v1 = (hp_taps_u8x4(__byte_perm(ab0, cd0, 0x7632)) + 8) >> 4;
+                    v2 = (hp_taps_u8x4(__byte_perm(ab1, cd1, 0x5410)) + 8) >> 4;
+                    v3 = (hp_taps_u8x4(__byte_perm(ab1, cd1, 0x7632)) + 8) >> 4;
+                    pw = pack_u8x4(v0, v1, v2, v3);
                 } else if (phase == 2) {
+                    int v0, v1, v2, v3;
                     const unsigned wa = ld4u(p - 1), wb = ld4u(p + 3);
-                    const int b0 = byte_of(wa, 0), b1 = byte_of(wa, 1), b2 = byte_of(wa, 2), b3 = byte_of(wa, 3);
-                    const int b4 = byte_of(wb, 0), b5 = byte_of(wb, 1), b6 = byte_of(wb, 2);
-                    v0 = clamp_u8((hpf4(b0, b1, b2, b3) + 8) >> 4);
-                    v1 = clamp_u8((hpf4(b1, b2, b3, b4) + 8) >> 4);
-                    v2 = clamp_u8((hpf4(b2, b3, b4, b5) + 8) >> 4);
-                    v3 = clamp_u8((hpf4(b3, b4, b5, b6) + 8) >> 4);
+                    v0 = (hp_taps_u8x4(wa) + 8) >> 4; /* saturated by the pack below */
+                    v1 = (hp_taps_u8x4(__funnelshift_r(wa, wb, 8)) + 8) >> 4;
+                    v2 = (hp_taps_u8x4(__funnelshift_r(wa, wb, 16)) + 8) >> 4;
+                    v3 = (hp_taps_u8x4(__funnelshift_r(wa, wb, 24)) + 8) >> 4;
+                    pw = pack_u8x4(v0, v1, v2, v3);
                 } else {
+                    int v0, v1, v2, v3;
                     const int16_t *b = hbuf + ly * hstride + lx;
-                    const short4 ra = *reinterpret_cast<const short4 *>(b), rb = *reinterpret_cast<const short4 *>(b + hstride);
-                    const short4 rc = *reinterpret_cast<const short4 *>(b + 2 * hstride), rd = *reinterpret_cast<const short4 *>(b + 3 * hstride);
-                    v0 = clamp_u8((hpf4(ra.x, rb.x, rc.x, rd.x) + 128) >> 8);
-                    v1 = clamp_u8((hpf4(ra.y, rb.y, rc.y, rd.y) + 128) >> 8);
-                    v2 = clamp_u8((hpf4(ra.z, rb.z, rc.z, rd.z) + 128) >> 8);
-                    v3 = clamp_u8((hpf4(ra.w, rb.w, rc.w, rd.w) + 128) >> 8);
+                    /* rows ly-1 .. ly+2 of the 16-bit H-filtered image; (row a, row b) and (row c, row d) of one column
+                     * are paired into a word each and run through dp2a with the taps (-1, 9) and (9, -1) */
+                    const uint2 ra = *reinterpret_cast<const uint2 *>(b), rb = *reinterpret_cast<const uint2 *>(b + hstride);
+                    const uint2 rc = *reinterpret_cast<const uint2 *>(b + 2 * hstride), rd = *reinterpret_cast<const uint2 *>(b + 3 * hstride);
+                    const unsigned t_ab = 0x09ffu, t_cd = 0xff09u;
+                    v0 = dp2a_lo_s16(__byte_perm(rc.x, rd.x, 0x5410), t_cd, dp2a_lo_s16(__byte_perm(ra.x, rb.x, 0x5410), t_ab, 128)) >> 8;
+                    v1 = dp2a_lo_s16(__byte_perm(rc.x, rd.x, 0x7632), t_cd, dp2a_lo_s16(__byte_perm(ra.x, rb.x, 0x7632), t_ab, 128)) >> 8;
+                    v2 = dp2a_lo_s16(__byte_perm(rc.y, rd.y, 0x5410), t_cd, dp2a_lo_s16(__byte_perm(ra.y, rb.y, 0x5410), t_ab, 128)) >> 8;
+                    v3 = dp2a_lo_s16(__byte_perm(rc.y, rd.y, 0x7632), t_cd, dp2a_lo_s16(__byte_perm(ra.y, rb.y, 0x7632), t_ab, 128)) >> 8;
+                    pw = pack_u8x4(v0, v1, v2, v3);
                 }
             } else {
-                unsigned w;
                 if (phase == 1) {
-                    w = avg_up_u8x4(ld4u(p), ld4u(p + rs));
-                    v0 = byte_of(w, 0); v1 = byte_of(w, 1); v2 = byte_of(w, 2); v3 = byte_of(w, 3);
+                    pw = avg_up_u8x4(ld4u(p), ld4u(p + rs));
                 } else if (phase == 2) {
-                    w = avg_up_u8x4(ld4u(p), ld4u(p + 1));
-                    v0 = byte_of(w, 0); v1 = byte_of(w, 1); v2 = byte_of(w, 2); v3 = byte_of(w, 3);
+                    pw = avg_up_u8x4(ld4u(p), ld4u(p + 1));
                 } else {
+                    int v0, v1, v2, v3;
                     const unsigned wa = ld4u(p), wb = ld4u(p + 1), wc = ld4u(p + rs), wd = ld4u(p + rs + 1);
                     v0 = (byte_of(wa, 0) + byte_of(wb, 0) + byte_of(wc, 0) + byte_of(wd, 0) + 2) >> 2;
                     v1 = (byte_of(wa, 1) + byte_of(wb, 1) + byte_of(wc, 1) + byte_of(wd, 1) + 2) >> 2;
                     v2 = (byte_of(wa, 2) + byte_of(wb, 2) + byte_of(wc, 2) + byte_of(wd, 2) + 2) >> 2;
                     v3 = (byte_of(wa, 3) + byte_of(wb, 3) + byte_of(wc, 3) + byte_of(wd, 3) + 2) >> 2;
+                    pw = pack_u8x4(v0, v1, v2, v3);
                 }
             }
-            bmc_store4(P, mode, x + lx, y + ly, imin(4, cw - lx), walign, v0, v1, v2, v3);
+            bmc_store4(P, mode, x + lx, y + ly, imin(4, cw - lx), walign, pw);
         }
         return;
     }
@@ -226,13 +236,15 @@ DSV_D void bmc_block_plane(const BmcArgs &a, const int c, int16_t *hbuf, unsigne
                 v[e] = (mv.submask & (1 << q)) ? s_avg[q] : (lx < cw ? (int) r0[(ptrdiff_t) ly * P.rstride + lx] : 0);
             }
         }
-        bmc_store4(P, mode, x + 4 * wx, y + ly, imin(4, cw - 4 * wx), walign, v[0], v[1], v[2], v[3]);
+        bmc_store4(P, mode, x + 4 * wx, y + ly, imin(4, cw - 4 * wx), walign, pack_u8x4(v[0], v[1], v[2], v[3]));
     }
 }
 
 /* one CTA per motion block and lane, all three planes in turn (a chroma block alone is too little work to pay
  * for a CTA launch) */
-__global__ void __launch_bounds__(BMC_THREADS) bmc_kernel(const BmcArgs *args)
+/* 6 CTAs per SM (40 registers): the kernel is latency-bound, measured 268 us per 32 HD pictures against 308 us at 48
+ * registers / 5 CTAs and 290 us at 32 registers with spills; unrolling the word loop is slower as well */
+__global__ void __launch_bounds__(BMC_THREADS, 6) bmc_kernel(const BmcArgs *args)
 {
     __shared__ __align__(8) int16_t hbuf[(DSV_BORDER + 3) * DSV_BORDER]; /* (bh + 3) x bw, bmc.c:127 */
     __shared__ unsigned scratch[40];

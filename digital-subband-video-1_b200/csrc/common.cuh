@@ -100,7 +100,19 @@ template <int S> DSV_HD int rnd_shift(int v)
 DSV_HD int ll_down(int v) { return v * 4 / 5; }
 DSV_HD int ll_up(int v) { return v * 5 / 4; }
 /* C `/ 4` (truncate toward zero) without a divide */
-DSV_HD int div4_trunc(int v) { return (v + ((v >> 31) & 3)) >> 2; }
+DSV_HD int div4_trunc(int v) { return v / 4; } /* the compiler's sign word + LEA.HI + shift: 3 instructions */
+
+/* m such that (i * m) >> 20 == i / d for 0 <= i < 1024 and 1 <= d <= 64: floor(2^20 / d) + 1.  On the device the
+ * floor comes from a correctly rounded float reciprocal (error < 0.125 / d, below the smallest non-zero fractional
+ * part 1 / d of 2^20 / d, so the truncation is exact) instead of a ~25-instruction integer divide. */
+DSV_HD int magic20(int d)
+{
+#ifdef __CUDA_ARCH__
+    return (int) (1048576.0f * __frcp_rn((float) d)) + 1;
+#else
+    return (1 << 20) / d + 1;
+#endif
+}
 
 /*
  * Exact unsigned division by a runtime-constant divisor d for numerators < 2^31:
@@ -170,6 +182,29 @@ DSV_HD unsigned pack_u8x4(int a, int b, int c, int d)
 #endif
 }
 /* per-byte (a + b + 1) >> 1 */
+/* the half-pel kernel -a + 9b + 9c - d (bmc.c:124-174, hme.c:302-348) over the four bytes of w, a in the lowest
+ * byte: one dp4a with the taps as signed bytes */
+DSV_HD int hp_taps_u8x4(unsigned w)
+{
+#if defined(__CUDA_ARCH__)
+    int r;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0xff0909ffu), "r"(0));
+    return r;
+#else
+    return 9 * (int) (((w >> 8) & 0xffu) + ((w >> 16) & 0xffu)) - (int) ((w & 0xffu) + (w >> 24));
+#endif
+}
+/* c + lo16(v) * t0 + hi16(v) * t1: v holds two signed 16-bit values, t0 / t1 are the two low signed bytes of taps */
+DSV_HD int dp2a_lo_s16(unsigned v, unsigned taps, int c)
+{
+#if defined(__CUDA_ARCH__)
+    int r;
+    asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(taps), "r"(c));
+    return r;
+#else
+    return c + (int) (int16_t) (v & 0xffffu) * (int) (int8_t) (taps & 0xffu) + (int) (int16_t) (v >> 16) * (int) (int8_t) ((taps >> 8) & 0xffu);
+#endif
+}
 DSV_HD unsigned avg_up_u8x4(unsigned a, unsigned b) { return (a | b) - (((a ^ b) >> 1) & 0x7f7f7f7fu); }
 
 /* Reference frame geometry (frame.c:63-120): 64-sample border, stride rounded up to 16 */

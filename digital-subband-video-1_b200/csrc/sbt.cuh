@@ -69,6 +69,7 @@ struct SbtJob {
     int quant;    /* frame quant (for the inverse's nudge bounds) */
     int do_quant; /* forward: fuse quantise+dequantise into the epilogue */
     int tiles_x, tiles_y, tile_base;
+    FastDiv tiles_x_fd, mtiles_x_fd; /* tile index -> (row, column) without an integer divide per thread */
     int mtiles_x, mtiles_y, mtile_base; /* mid kernel: 128x64 blocks of LL_2 */
     int hqp[16];  /* inverse: nudge bound per level (sbt.c:677-696), index = level */
     PlaneQ pq;
@@ -90,6 +91,7 @@ struct SbtDims {
     /* uniform launches (the engines: planes Y,U,V of many pictures of one format): jobs come in groups of gsz
      * with identical tile counts per position, so tile -> job is arithmetic; gsz == 0: binary search */
     int gsz = 0, tg = 0, c0 = 0, c1 = 0, mtg = 0, mc0 = 0, mc1 = 0;
+    FastDiv tg_fd = {1ull << 31, 31, 1}, mtg_fd = {1ull << 31, 31, 1};
 };
 /* assigns tile_base / mtile_base of jobs[0..n) (host copies, in launch order) and returns the totals */
 SbtDims sbt_assign_tiles(SbtJob *jobs, int n);
@@ -123,7 +125,7 @@ template <bool MID> DSV_D int sbt_locate(const SbtJob *jobs, const SbtDims &d, i
 {
     if (d.gsz) {
         const int tg = MID ? d.mtg : d.tg, c0 = MID ? d.mc0 : d.c0, c1 = MID ? d.mc1 : d.c1;
-        const int grp = bid / tg, r = bid - grp * tg;
+        const int grp = (int) fastdiv((unsigned) bid, MID ? d.mtg_fd : d.tg_fd), r = bid - grp * tg;
         const int k = (r >= c0) + (r >= c0 + c1);
         *tile = r - (k == 0 ? 0 : (k == 1 ? c0 : c0 + c1));
         return grp * d.gsz + k;

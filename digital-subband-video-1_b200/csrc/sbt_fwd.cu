@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_fwd_tile_kernel(const Sb
     const int tid = threadIdx.x;
     const int t = load_job<false>(&J, jobs, dims);
 
-    const int tx = t % J.tiles_x, ty = t / J.tiles_x;
+    const int ty = (int) fastdiv((unsigned) t, J.tiles_x_fd), tx = t - ty * J.tiles_x;
     const int gx0 = tx * SBT_TW, gy0 = ty * SBT_TH;
     const int cw = J.cw, ch = J.ch;
     const bool isI = !J.isP;
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_fwd_mid_kernel(const Sbt
     __shared__ __align__(16) int32_t s_b[(SBT_TW / 2) * (SBT_TH / 2)];
     const int tid = threadIdx.x;
     const int t = load_job<true>(&J, jobs, dims);
-    const int tx = t % J.mtiles_x, ty = t / J.mtiles_x;
+    const int ty = (int) fastdiv((unsigned) t, J.mtiles_x_fd), tx = t - ty * J.mtiles_x;
     const int cw = J.cw, ch = J.ch;
     const uint8_t *stab = J.stable;
     {

@@ -39,6 +39,8 @@ SbtDims sbt_assign_tiles(SbtJob *jobs, int n)
         d.mc1 = gsz == 3 ? jobs[1].mtiles_x * jobs[1].mtiles_y : 0;
         d.tg = gsz == 3 ? d.c0 + d.c1 + jobs[2].tiles_x * jobs[2].tiles_y : d.c0;
         d.mtg = gsz == 3 ? d.mc0 + d.mc1 + jobs[2].mtiles_x * jobs[2].mtiles_y : d.mc0;
+        d.tg_fd = make_fastdiv(d.tg > 0 ? d.tg : 1);
+        d.mtg_fd = make_fastdiv(d.mtg > 0 ? d.mtg : 1);
     }
     return d;
 }
@@ -68,6 +70,8 @@ void sbt_fill_geometry(SbtJob *j, int pw, int ph, int cw, int ch, int isP, int p
     j->tiles_y = ceil_div(ch, SBT_TH);
     j->mtiles_x = ceil_div(sbt_wo(cw, SBT_HI), SBT_TW);
     j->mtiles_y = ceil_div(sbt_wo(ch, SBT_HI), SBT_TH);
+    j->tiles_x_fd = make_fastdiv(j->tiles_x);
+    j->mtiles_x_fd = make_fastdiv(j->mtiles_x);
     j->ll2_off = (int) llx_head_elems(cw, ch);
 
     /* double-visited positions: level l (2,1) elements that level l+1's hzcc scan also covers */

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_inv_mid_kernel(const Sbt
     __shared__ Win W[SBT_NLT + 1];
     const int tid = threadIdx.x;
     const int t = inv_load_job<true>(&J, jobs, dims);
-    const int tx = t % J.mtiles_x, ty = t / J.mtiles_x;
+    const int ty = (int) fastdiv((unsigned) t, J.mtiles_x_fd), tx = t - ty * J.mtiles_x;
     const int nlt = J.nlt;
     int32_t *win[SBT_NLT + 1];
     win[SBT_HI + 1] = sm;
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, 5) sbt_inv_tile_kernel(const
     const int tid = threadIdx.x;
     const int t = inv_load_job<false>(&J, jobs, dims);
 
-    const int tx = t % J.tiles_x, ty = t / J.tiles_x;
+    const int ty = (int) fastdiv((unsigned) t, J.tiles_x_fd), tx = t - ty * J.tiles_x;
     const int gx0 = tx * SBT_TW, gy0 = ty * SBT_TH;
     const int cw = J.cw, ch = J.ch;
     const bool isI = !J.isP;
@@ -292,8 +292,9 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, 5) sbt_inv_tile_kernel(const
         const Win w = W[2];
         const int ww = w.b - w.a, wh = w.hb - w.ha, wo = sbt_wo(cw, 2), ho = sbt_wo(ch, 2);
         const int32_t *ll2 = J.llx + J.ll2_off;
+        const int wmag = magic20(ww);
         for (int i = tid; i < ww * wh; i += SBT_TILE_THREADS) {
-            const int y = (i * ((1 << 20) / ww + 1)) >> 20, x = i - y * ww; /* i / ww for i < 2^10, ww <= 36 */
+            const int y = (i * wmag) >> 20, x = i - y * ww; /* i / ww for i < 2^10, ww <= 36 */
             const int gx = w.a + x, gy = w.ha + y;
             int v = 0;
             if (gx < wo && gy < ho) {
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, 5) sbt_inv_tile_kernel(const
         const int ws = sbt_ws(cw, 2), hs = sbt_ws(ch, 2), wo = sbt_wo(cw, 2), ho = sbt_wo(ch, 2);
         const int bound = J.hqp[2];
         const int npx = w.pb - w.pa, npy = w.qb - w.qa;
-        const int mag = (1 << 20) / npx + 1;
+        const int mag = magic20(npx);
         const int o_b = imin(o.b, ws), o_hb = imin(o.hb, hs); /* level 2 produces LL_1 proper only */
         for (int task = tid; task < npx * npy; task += SBT_TILE_THREADS) {
             const int ty2 = (task * mag) >> 20, tx2 = task - ty2 * npx;

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "digital-subband-video-1_b200")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libdsv1ref.so")
 PORT_SO = os.path.join(ROOT, "oracle", "_ref", "libdsv1port.so")
-GPU_SO = os.path.join(PKG, "libdsv1_b200.so")
+GPU_SO = os.environ.get("DSV1_B200_LIB", os.path.join(PKG, "libdsv1_b200.so"))  # the override is for A/B builds of one kernel
 REF_CLI = os.path.join(ROOT, "oracle", "_ref", "dsv1")
 
 SUBSAMP = {"444": 0x0, "422": 0x4, "420": 0x5, "411": 0x8}
