@@ -215,7 +215,10 @@ DSV_D void store_mv(DevMV *dst, int x, int y, int mode, int submask, int lo_var,
     *dst = m;
 }
 
-__global__ void __launch_bounds__(HME_THREADS) hme_level_kernel(const HmeArgs *args)
+#ifndef HME_LV_MINB
+#define HME_LV_MINB 8 /* measured: 8 -> 24.1 us, default -> 26.5, 5 -> 28.7 */
+#endif
+__global__ void __launch_bounds__(HME_THREADS, HME_LV_MINB) hme_level_kernel(const HmeArgs *args)
 {
     const HmeArgs &A = args[blockIdx.z];
     __shared__ __align__(16) uint8_t s_src[64 * HME_SRC_STRIDE];
@@ -247,7 +250,10 @@ enum {
     SUM_COUNT
 };
 
-__global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args)
+#ifndef HME_L0_MINB
+#define HME_L0_MINB 6 /* CTAs per SM, measured per 32 HD pictures: 6 -> 709 us, 5 -> 721, 4 (compiler default) -> 757, 3 -> 823 */
+#endif
+__global__ void __launch_bounds__(HME_THREADS, HME_L0_MINB) hme_l0_kernel(const HmeArgs *args)
 {
     const HmeArgs &A = args[blockIdx.z];
     __shared__ __align__(16) uint8_t s_src[64 * HME_SRC_STRIDE];

@@ -242,7 +242,10 @@ DSV_D void hz_cache_job(HzJob *sJ, int *s_have, const HzJob *jobs, int njobs, in
     }
 }
 
-__global__ void __launch_bounds__(HZ_THREADS) hzcc_scan_kernel(const HzJob *jobs, int njobs, HzChunk *chunks, int total_chunks)
+#ifndef HZ_SCAN_MINB
+#define HZ_SCAN_MINB 8 /* measured: 8 -> 252 us, default (40 registers) -> 268 */
+#endif
+__global__ void __launch_bounds__(HZ_THREADS, HZ_SCAN_MINB) hzcc_scan_kernel(const HzJob *jobs, int njobs, HzChunk *chunks, int total_chunks)
 {
     __shared__ HzJob J;
     __shared__ unsigned long long scratch[40];
@@ -430,7 +433,10 @@ DSV_D void or_bits_atomic(unsigned *words, unsigned long long bitpos, int len, u
     }
 }
 
-__global__ void __launch_bounds__(HZ_THREADS) hzcc_pack_kernel(const HzJob *jobs, int njobs, const HzChunk *chunks,
+#ifndef HZ_PACK_MINB
+#define HZ_PACK_MINB 8 /* measured: 8 -> 193 us, 6 -> 202, default (48 registers) -> 216 */
+#endif
+__global__ void __launch_bounds__(HZ_THREADS, HZ_PACK_MINB) hzcc_pack_kernel(const HzJob *jobs, int njobs, const HzChunk *chunks,
                                                                const HzFrame *frames, int total_chunks)
 {
     __shared__ HzJob J;

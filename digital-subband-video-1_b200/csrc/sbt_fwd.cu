@@ -187,7 +187,10 @@ DSV_D void load_quads_slow(const SbtJob &J, int r0, int c0, int nv, unsigned &w0
  * Streaming kernel: levels 1 and 2 of one 128x64-sample tile.  LL_2 (32x16 values) goes to the job's ll2
  * hand-over plane for the mid kernel.
  */
-__global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_fwd_tile_kernel(const SbtJob *jobs, const SbtDims dims)
+#ifndef SBT_FWD_MINB
+#define SBT_FWD_MINB 8 /* CTAs per SM, measured per 32 HD pictures: 8 -> 118.4 us, 6 (compiler default) -> 120.0, 5 -> 125.0 */
+#endif
+__global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_FWD_MINB) sbt_fwd_tile_kernel(const SbtJob *jobs, const SbtDims dims)
 {
     DSV_DYN_SMEM(int16_t, s_hb); /* I frames only: B4T row-pass strip, (64 + 2) x FWD_HB_STRIDE int16 */
     __shared__ SbtJob J;
