@@ -382,12 +382,13 @@ def run_product(args):
                               "share_of_step": ms / ms_dev}
         sbt = {k: v for k, v in kern.items() if k.startswith("sbt_")}
         dom = max(sbt.items(), key=lambda kv: kv[1]["ms_total"]) if sbt else (None, None)
-        # DRAM traffic per launch from the committed `ncu --set full` capture of this very workload
-        # (profiles/r1_ncu_sbt_tile_kernels_final_b32.txt, 32 lanes = 497.7 MB algorithmic): dram__bytes_read+write =
-        # 446.9 MB (forward), 486.6 MB (inverse); scaled to this launch's plane count.  Both are BELOW the algorithmic
+        # DRAM traffic per launch from the committed `ncu --set full` captures of this very workload: forward
+        # (profiles/r1_ncu_sbt_tile_kernels_final_b32.txt, 32 lanes = 497.7 MB algorithmic) dram__bytes_read+write =
+        # 446.9 MB; inverse (profiles/r1_ncu_sbt_tile_kernels_final_b64.txt, 64 lanes = 995.3 MB algorithmic) 797.5 MB
+        # read + 185.0 MB written = 982.5 MB; scaled to this launch's plane count.  Both are BELOW the algorithmic
         # bytes (L2 absorbs part of the write-back): no wasted re-reads.
-        traffic_ratio = {"sbt_fwd_tile_kernel": 446.9 / 497.7, "sbt_inv_tile_kernel(enc)": 486.6 / 497.7,
-                         "sbt_inv_tile_kernel(dec)": 486.6 / 497.7}  # inverse re-captured after tuning: unchanged within 2 %
+        traffic_ratio = {"sbt_fwd_tile_kernel": 446.9 / 497.7, "sbt_inv_tile_kernel(enc)": 982.5 / 995.3,
+                         "sbt_inv_tile_kernel(dec)": 982.5 / 995.3}
         for name, kv in kern.items():
             if name in traffic_ratio:
                 kv["traffic_bytes_per_launch"] = kv["bytes_per_launch"] * traffic_ratio[name]
@@ -396,7 +397,7 @@ def run_product(args):
             roofline = {"kernel": dom[0], "bound": "hbm", "achieved": dom[1]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                         "frac": dom[1]["frac"], "traffic": dom[1]["traffic_bytes_per_launch"], "peak_source": peak_src,
                         "traffic_source": "ncu --set full capture of the same kernel and workload, scaled by planes per launch "
-                                          "(profiles/r1_ncu_sbt_tile_kernels_final_b32.txt)",
+                                          "(profiles/r1_ncu_sbt_tile_kernels_final_b64.txt; forward: ..._final_b32.txt)",
                         "algorithmic_bytes_per_plane": "w*h (u8 samples) + 4*cw*ch (int32 coefficients)",
                         "all_sbt_bmc_kernels": {k: round(v["frac"], 3) for k, v in kern.items()}}
         stream_bytes = sum(lens_h)
