@@ -226,6 +226,8 @@ def run_product(args):
     torch.cuda.set_device(local)
     pin_note = bind_near_gpu(torch, local, world)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     gpu = L.gpu()
     lib = gpu.lib
