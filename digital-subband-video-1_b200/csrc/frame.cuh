@@ -85,9 +85,6 @@ struct To420Item { /* chroma plane -> dense 4:2:0 chroma plane of dw x dh sample
     int dw, dh;
     int hpass; /* 1: 4:4:4 source (horizontal then vertical pass), 0: vertical pass only */
 };
-struct ReconItem { /* dst = clamp(a + b - 128) (b.p == null: dst = a), border of dst replicated */
-    PlaneRef a, b, dst;
-};
 
 /*
  * Host-assembled, device-mirrored scratch for one pipeline phase: the host appends descriptor arrays into
@@ -118,7 +115,6 @@ void pack_launch(const PackItem *d_items, int n, int max_w, int max_h, cudaStrea
 void extend_launch(const PlaneRef *d_items, int n, int max_w, int max_h, cudaStream_t st);
 void down2_launch(const Down2Item *d_items, int n, int max_w, int max_h, cudaStream_t st);
 void sum_launch(const SumItem *d_items, int n, int max_h, cudaStream_t st);
-void recon_launch(const ReconItem *d_items, int n, int max_w, int max_h, cudaStream_t st);
 void zero_launch(const ZeroItem *d_items, int n, size_t max_bytes, cudaStream_t st);
 /* items may live in mapped pinned host memory; one of dst/src of every item is device memory, the other may be
  * mapped pinned host memory */

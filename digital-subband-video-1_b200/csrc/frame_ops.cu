@@ -1,9 +1,9 @@
 /*
  * frame_ops.cu -- batched frame plumbing kernels: ingest (packed -> bordered + border), pack (bordered ->
- * packed), border extension, luma pyramid level (2x2 box filter + border in one pass), luma sum, and the
- * encoder's closed-loop reconstruction (residual + prediction -> new reference incl. border).
+ * packed), border extension, luma pyramid level (2x2 box filter + border in one pass), luma sum.
  * Replaces dsv_frame_copy / dsv_clone_frame / dsv_extend_frame[_luma] / dsv_ds2x_frame_luma /
- * dsv_frame_avg_luma / dsv_frame_add (frame.c:199-327, bmc.c:304-316).
+ * dsv_frame_avg_luma (frame.c:199-327); dsv_frame_add (bmc.c:304-316) is fused into the inverse transform's
+ * store (sbt_inv.cu: SbtJob.addp).
  *
  * Every kernel takes a device array of items (one per plane of every frame in flight); threads own 16
  * consecutive bytes of one bordered row: interior chunks move as one 16-byte load/store, border chunks
@@ -267,43 +267,6 @@ DSV_D unsigned add4_clamp(unsigned a, unsigned b)
     return r;
 }
 
-/* dst = clamp(a + b - 128) (dsv_frame_add, bmc.c:29-41,304-316) + copy into the new reference + its border
- * (dsv_frame_copy + dsv_extend_frame, dsv_encoder.c:662-674) in one pass */
-__global__ void __launch_bounds__(FO_BX *FO_BY) recon_kernel(const ReconItem *items)
-{
-    const ReconItem it = items[blockIdx.z];
-    const PlaneRef A = it.a, B = it.b, D = it.dst;
-    FO_FOREACH_ROW()
-    {
-        const int x0 = ck * 16 - DSV_BORDER, y = row - DSV_BORDER;
-        if (x0 >= D.w + DSV_BORDER || y >= D.h + DSV_BORDER) {
-            continue;
-        }
-        const int sy = iclamp(y, 0, D.h - 1);
-        const uint8_t *a = A.p + (size_t) sy * A.stride;
-        const uint8_t *b = B.p ? B.p + (size_t) sy * B.stride : nullptr;
-        uint8_t *dst = D.p + (ptrdiff_t) y * D.stride + x0;
-        if (x0 >= 0 && x0 + 16 <= D.w) {
-            uint4 va = *reinterpret_cast<const uint4 *>(a + x0);
-            if (b) {
-                const uint4 vb = *reinterpret_cast<const uint4 *>(b + x0);
-                va = make_uint4(add4_clamp(va.x, vb.x), add4_clamp(va.y, vb.y), add4_clamp(va.z, vb.z), add4_clamp(va.w, vb.w));
-            }
-            *reinterpret_cast<uint4 *>(dst) = va;
-            continue;
-        }
-        const int xend = D.w + DSV_BORDER;
-    #pragma unroll 4
-        for (int e = 0; e < 16; e++) {
-            const int x = x0 + e;
-            if (x < xend) {
-                const int sx = iclamp(x, 0, D.w - 1);
-                dst[e] = b ? clamp_u8((int) a[sx] + (int) b[sx] - 128) : a[sx];
-            }
-        }
-    }
-}
-
 #define ZERO_PER_CTA (256 * 16 * 8)
 __global__ void __launch_bounds__(256) zero_kernel(const ZeroItem *items)
 {
@@ -426,13 +389,6 @@ void sum_launch(const SumItem *d_items, int n, int max_h, cudaStream_t st)
 {
     if (n > 0) {
         DSV_LAUNCH(sum_kernel, dim3(max_h, n), dim3(256), 0, st, d_items);
-        KERNEL_CHECK();
-    }
-}
-void recon_launch(const ReconItem *d_items, int n, int max_w, int max_h, cudaStream_t st)
-{
-    if (n > 0) {
-        DSV_LAUNCH(recon_kernel, fo_grid(max_w, max_h, n, true), dim3(FO_BX, FO_BY), 0, st, d_items);
         KERNEL_CHECK();
     }
 }

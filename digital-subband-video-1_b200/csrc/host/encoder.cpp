@@ -369,7 +369,7 @@ EncEngine::EncEngine(const DSV_META &md, int gop, int pyramid_levels, int lanes)
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_pref_[0], cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_pref_[1], cudaEventDisableTiming));
     const size_t per_lane = 3 * (sizeof(SbtJob) + sizeof(HzJob)) + sizeof(HzFrame) + (size_t) (levels_ + 1) * sizeof(HmeArgs) +
-                            sizeof(BmcArgs) + 16 * sizeof(ReconItem) + 2 * sizeof(ZeroItem) + 2048;
+                            sizeof(BmcArgs) + 8 * sizeof(PlaneRef) + 2 * sizeof(ZeroItem) + 2048;
     arena_.create(per_lane * (size_t) L_ + 4096);
     CUDA_CHECK(cudaMalloc(&d_mv0_, sizeof(DevMV) * (size_t) g_.nblk * L_));
     CUDA_CHECK(cudaMemset(d_mv0_, 0, sizeof(DevMV) * (size_t) g_.nblk * L_));
@@ -798,14 +798,11 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     SbtJob *d_sj;
     HzJob *d_hj;
     HzFrame *d_hf = d_frames_;
-    ReconItem *d_rec = nullptr;
     PlaneRef *d_ext = nullptr;
     SbtJob *sj = arena_.push_n<SbtJob>((size_t) 3 * n, &d_sj);
     HzJob *hj = arena_.push_n<HzJob>((size_t) 3 * n, &d_hj);
-    const int n_i_ref = n_ref - n_p;
-    ReconItem *rec = n_p ? arena_.push_n<ReconItem>((size_t) 3 * n_p, &d_rec) : nullptr;
-    PlaneRef *ext = n_i_ref > 0 ? arena_.push_n<PlaneRef>((size_t) 3 * n_i_ref, &d_ext) : nullptr;
-    int qp = 0, qi = 0;
+    PlaneRef *ext = n_ref > 0 ? arena_.push_n<PlaneRef>((size_t) 3 * n_ref, &d_ext) : nullptr;
+    int qi = 0;
     ZeroItem *d_zero;
     ZeroItem *zero = arena_.push_n<ZeroItem>((size_t) n, &d_zero);
     int n_zero = 0;
@@ -815,7 +812,8 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         EncLane &l = lanes_[(size_t) li];
         const int isP = l.has_ref;
         const DevFrame &fwd_in = isP ? l.xf : (inter_ ? l.pad[l.cur] : l.xf);
-        const DevFrame &inv_out = isP ? l.xf : (inter_ ? l.recon[l.cur] : l.xf);
+        /* P pictures: the inverse transform adds the prediction on its way out and writes the reconstruction */
+        const DevFrame &inv_out = inter_ ? l.recon[l.cur] : l.xf;
         if (l.pkt_dirty) {
             zero[n_zero].p = l.d_pkt;
             zero[n_zero].bytes = ((size_t) l.pkt_dirty + 64 + 15) & ~(size_t) 15;
@@ -831,6 +829,10 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
             s.pstride = fwd_in.stride[p];
             s.opix = inv_out.p[p];
             s.ostride = inv_out.stride[p];
+            if (isP) {
+                s.addp = l.pred.p[p];
+                s.addstride = l.pred.stride[p];
+            }
             s.coef = l.coef + g.coef_off[p];
             s.llx = l.llx[p];
             s.dv = l.dv[p];
@@ -853,13 +855,7 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
             h.chunk_base = k * g.total_chunks + (p > 0 ? g.chunks[0] : 0) + (p > 1 ? g.chunks[1] : 0);
             h.frame = k;
             if (l.is_ref) {
-                if (isP) {
-                    rec[3 * qp + p].a = plane_ref(l.xf, p);
-                    rec[3 * qp + p].b = plane_ref(l.pred, p);
-                    rec[3 * qp + p].dst = plane_ref(l.recon[l.cur], p);
-                } else {
-                    ext[3 * qi + p] = plane_ref(l.recon[l.cur], p);
-                }
+                ext[3 * qi + p] = plane_ref(l.recon[l.cur], p);
             }
         }
         HzFrame &hf = h_frames_[k];
@@ -870,9 +866,7 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         hf.job[0] = 3 * k;
         hf.job[1] = 3 * k + 1;
         hf.job[2] = 3 * k + 2;
-        if (isP) {
-            qp++;
-        } else if (l.is_ref) {
+        if (l.is_ref) {
             qi++;
         }
     }
@@ -889,9 +883,8 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     if (n_ref) {
         /* closed loop: reconstruct exactly what the decoder will (dsv_encoder.c:525,662-674) */
         sbt_inv_launch(d_sj, sdims, g.lo_smem, st, ev_[2], ev_[3]);
-        recon_launch(d_rec, 3 * n_p, g.w, g.h, st);
-        extend_launch(d_ext, 3 * n_i_ref, g.w, g.h, st);
-        stats.kernel_launches += 3 + (n_p ? 1 : 0) + (n_i_ref > 0 ? 1 : 0);
+        extend_launch(d_ext, 3 * n_ref, g.w, g.h, st);
+        stats.kernel_launches += 4;
     }
     CUDA_CHECK(cudaEventSynchronize(ev_[4])); /* packet sizes are known; reconstruction keeps running */
     CopyItem *pk = reinterpret_cast<CopyItem *>(h_pk_); /* mapped pinned: read by the copy kernel in place */

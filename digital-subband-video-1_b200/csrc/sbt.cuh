@@ -55,6 +55,10 @@ struct SbtJob {
     /* inverse output (may be a different frame than the forward input, e.g. the new reference) */
     uint8_t *opix;
     int ostride;
+    /* inverse only, optional: a prediction plane added on the way out, opix = clamp(sample + addp - 128)
+     * (dsv_add_pred / addf, bmc.c:304-346) -- the encoder's closed-loop reconstruction without a separate pass */
+    const uint8_t *addp;
+    int addstride;
     int pw, ph;
     /* coefficients: dense, stride == cw */
     int32_t *coef;

@@ -88,6 +88,26 @@ DSV_D void store_row8(const SbtJob &J, int oy, int ox, const int *v)
         return;
     }
     uint8_t *dst = J.opix + (size_t) oy * J.ostride + ox;
+    if (J.addp) {
+        const uint8_t *ap = J.addp + (size_t) oy * J.addstride + ox;
+        if (ox + 8 <= J.pw && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(ap)) & 7) == 0) {
+            const uint2 p = *reinterpret_cast<const uint2 *>(ap);
+            int o[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                o[e] = clamp_u8(v[e] + 128) + byte_of(e < 4 ? p.x : p.y, e & 3) - 128;
+            }
+            *reinterpret_cast<uint2 *>(dst) = make_uint2(pack_u8x4(o[0], o[1], o[2], o[3]), pack_u8x4(o[4], o[5], o[6], o[7]));
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                if (ox + e < J.pw) {
+                    dst[e] = clamp_u8(clamp_u8(v[e] + 128) + ap[e] - 128);
+                }
+            }
+        }
+        return;
+    }
     if (ox + 8 <= J.pw && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
         *reinterpret_cast<uint2 *>(dst) = make_uint2(pack4_u8(v[0], v[1], v[2], v[3]), pack4_u8(v[4], v[5], v[6], v[7]));
     } else {
