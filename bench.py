@@ -400,7 +400,8 @@ def run_product(args):
                         "frac": dom[1]["frac"], "traffic": dom[1]["traffic_bytes_per_launch"], "peak_source": peak_src,
                         "traffic_source": "ncu --set full capture of the same kernel and workload, scaled by planes per launch "
                                           "(profiles/r1_ncu_sbt_tile_kernels_final_b64.txt; forward: ..._final_b32.txt)",
-                        "algorithmic_bytes_per_plane": "w*h (u8 samples) + 4*cw*ch (int32 coefficients)",
+                        "algorithmic_bytes_per_plane": "w*h (u8 samples) + 4*cw*ch (int32 coefficients); the encoder's inverse of a P picture "
+                                                       "also reads the prediction it adds on the way out (+ w*h)",
                         "all_sbt_bmc_kernels": {k: round(v["frac"], 3) for k, v in kern.items()}}
         stream_bytes = sum(lens_h)
         line = {"metric": METRIC, "value": value, "unit": "pictures/s", "n_gpus": world, "steps": args.steps,

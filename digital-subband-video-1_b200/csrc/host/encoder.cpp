@@ -966,7 +966,8 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
             CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[2], ev_[3]));
             stats.sbt_inv_ms += ms;
             stats.sbt_inv_launches++;
-            stats.sbt_inv_bytes += bytes * (unsigned) n;
+            /* P pictures also read the prediction (one more byte per sample) on the way out */
+            stats.sbt_inv_bytes += bytes * (unsigned) n + (unsigned long long) g.frame_bytes * (unsigned) n_p;
         }
         if (n_search) {
             CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[5], ev_[6]));

@@ -286,7 +286,11 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_inv_mid_kernel(const Sbt
  * per thread from the LL_2 hand-over plane; level 1 with a thread owning 4 adjacent pairs = 8x2 output samples,
  * 16-byte coefficient loads and 8-byte sample stores.
  */
-__global__ void __launch_bounds__(SBT_TILE_THREADS, 5) sbt_inv_tile_kernel(const SbtJob *jobs, const SbtDims dims)
+#ifndef SBT_INV_MINB
+#define SBT_INV_MINB 6 /* CTAs per SM, measured per 32 HD pictures (decoder / encoder with fused prediction add):
+                          6 -> 181 / 213 us, 8 -> 183 / 211, 5 -> 183 / 219, 4 -> 202 / 245 */
+#endif
+__global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_INV_MINB) sbt_inv_tile_kernel(const SbtJob *jobs, const SbtDims dims)
 {
     DSV_DYN_SMEM(int32_t, sm);
     __shared__ SbtJob J;
