@@ -26,3 +26,15 @@ def test_sbt(emu, port, dims, isP):
     co = (a // 7) * 7
     for c in (0, 1):
         assert np.array_equal(port.inv_sbt(co, 313, isP, c, pw, ph), emu.inv_sbt(co, 313, isP, c, pw, ph))
+
+
+@pytest.mark.parametrize("dims", [(120, 68, 120, 68), (427, 240, 428, 240)])
+def test_inverse_sparse(emu, port, dims):
+    """Mostly-zero coefficient planes (what P pictures look like): flat LL areas next to isolated values."""
+    from test_gpu_sbt import sparse_coefs
+    pw, ph, cw, ch = dims
+    rng = np.random.default_rng(pw)
+    for density in (0.0, 0.002):
+        co = sparse_coefs(rng, cw, ch, density)
+        for c in (0, 1):
+            assert np.array_equal(port.inv_sbt(co, 313, 1, c, pw, ph), emu.inv_sbt(co, 313, 1, c, pw, ph)), (density, c)
