@@ -21,25 +21,6 @@
     type *name = reinterpret_cast<type *>(dsv_dyn_smem_)
 #endif
 
-/* asynchronous global -> shared copies (LDGSTS): issue early, wait once (cp.async; the emulator copies at once) */
-#ifndef DSV_CPU_EMU
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
-{
-    unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
-{
-    unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-#else
-static inline void cp_async16(void *smem, const void *gmem) { memcpy(smem, gmem, 16); }
-static inline void cp_async4(void *smem, const void *gmem) { memcpy(smem, gmem, 4); }
-static inline void cp_async_wait_all() {}
-#endif
-
 #define DSV_HD __host__ __device__ __forceinline__
 #define DSV_D __device__ __forceinline__
 
