@@ -31,3 +31,48 @@ def test_reference_cli_links(tmp_path):
     # usage text only: anything further needs a GPU
     r = subprocess.run([exe], capture_output=True, text=True)
     assert "usage" in (r.stdout + r.stderr).lower() or r.returncode in (0, 1)
+
+
+def _declared_functions(header):
+    """Function names declared at file scope of a C header (comments, preprocessor lines, struct bodies dropped)."""
+    import re
+    src = open(header).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"\\\n", "", src)
+    src = re.sub(r"^\s*#.*?$", "", src, flags=re.M)
+    src = src.replace('extern "C" {', "")
+    depth, out = 0, []
+    for ch in src:
+        if ch == "{":
+            depth += 1
+        elif ch == "}":
+            depth = max(0, depth - 1)
+        elif depth == 0:
+            out.append(ch)
+    names = set()
+    for stmt in "".join(out).split(";"):
+        st = stmt.strip()
+        if not st or st.startswith("typedef"):
+            continue
+        m = re.search(r"\b([a-z_][a-z0-9_]*)\s*\((?:[^()]|\([^()]*\))*\)\s*$", st, flags=re.S)
+        if m:
+            names.add(m.group(1))
+    return names
+
+
+def test_every_declared_function_is_exported():
+    """include/*.h is the contract: each function it declares must be a symbol of the shared library, and
+    include/exports.txt must list exactly those (plus data symbols)."""
+    if not os.path.exists(L.GPU_SO):
+        subprocess.run(["make", "-s", "-C", L.PKG], check=True)
+    lib = ctypes.CDLL(L.GPU_SO)
+    declared = set()
+    for h in ("dsv1_b200.h", "dsv1_b200_batch.h", "dsv1_b200_kernels.h"):
+        fns = _declared_functions(os.path.join(L.ROOT, "include", h))
+        assert len(fns) >= 9, (h, fns)
+        declared |= fns
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), sym
+    listed = set(open(os.path.join(L.ROOT, "include", "exports.txt")).read().split())
+    assert declared <= listed, sorted(declared - listed)
+    assert listed - declared <= {"dsv_lvlname"}, sorted(listed - declared)  # the only data symbol
