@@ -876,7 +876,7 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     copy1_launch(d_hf, h_frames_, sizeof(HzFrame) * (size_t) n, st);
     zero_launch(d_zero, n_zero, max_zero, st);
     sbt_fwd_launch(d_sj, sdims, g.lo_smem, st, ev_[0], ev_[1]);
-    hzcc_enc_launch(d_hj, 3 * n, d_chunks_, n * g.total_chunks, d_hf, n, st);
+    hzcc_enc_launch(d_hj, 3 * n, d_chunks_, n * g.total_chunks, d_hf, n, st, g.total_chunks, g.chunks[0], g.chunks[1]);
     stats.kernel_launches += 6;
     copy1_launch(h_frames_, d_hf, sizeof(HzFrame) * (size_t) n, st);
     CUDA_CHECK(cudaEventRecord(ev_[4], st));

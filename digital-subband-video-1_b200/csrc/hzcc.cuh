@@ -66,8 +66,15 @@ struct HzFrame {
 void hz_fill_regions(HzRegions *r, int cw, int ch);
 void hz_fill_job(HzJob *j, int cw, int ch, int q, int isP, int plane, int nbh, int nbv);
 void hzcc_quant_launch(const HzJob *d_jobs, int njobs, int max_elems, cudaStream_t st);
+/* chunk -> job without a search when the jobs are the planes Y,U,V of pictures of one format (per_pic == 0: search) */
+struct HzMap {
+    int per_pic, c0, c1;
+    FastDiv per_pic_fd;
+};
+/* chunks_per_pic > 0 declares that regular layout: job 3k+p covers chunks [k * chunks_per_pic + offset_p, ...) with
+ * chunks_y / chunks_u chunks in the first two planes */
 void hzcc_enc_launch(const HzJob *d_jobs, int njobs, HzChunk *d_chunks, int total_chunks,
-                     HzFrame *d_frames, int nframes, cudaStream_t st);
+                     HzFrame *d_frames, int nframes, cudaStream_t st, int chunks_per_pic = 0, int chunks_y = 0, int chunks_u = 0);
 
 /* ---- interleaved exp-Golomb code construction (bs.c:128-145) -------------------------------- */
 DSV_HD unsigned long long spread_bits(unsigned v)

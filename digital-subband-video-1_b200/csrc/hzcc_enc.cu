@@ -87,8 +87,16 @@ void hzcc_quant_launch(const HzJob *d_jobs, int njobs, int max_elems, cudaStream
     KERNEL_CHECK();
 }
 
-DSV_D int hz_job_of_chunk(const HzJob *jobs, int njobs, int chunk)
+/* chunk -> job.  The engines launch the planes Y,U,V of many pictures of ONE format: chunk counts repeat with period
+ * 3, so the job is arithmetic (map.per_pic > 0); a per-CTA binary search over the job table costs several dependent
+ * global loads -- more than half the lifetime of a CTA that handles 2048 coefficients.  The search remains for
+ * irregular launches (kernel-level API). */
+DSV_D int hz_job_of_chunk(const HzJob *jobs, int njobs, int chunk, const HzMap &map)
 {
+    if (map.per_pic > 0) {
+        const int pic = (int) fastdiv((unsigned) chunk, map.per_pic_fd), r = chunk - pic * map.per_pic;
+        return 3 * pic + (r >= map.c0) + (r >= map.c0 + map.c1);
+    }
     int lo = 0, hi = njobs - 1;
     while (lo < hi) {
         int mid = (lo + hi + 1) >> 1;
@@ -223,13 +231,13 @@ DSV_D void chunk_load(const HzJob &J, int chunk_local, int sym[HZ_ITEMS], int &b
 #define HZ_CPB 1 /* chunks per CTA (measured: 8 is slower; most chunks of a P picture still hold a few non-zeros) */
 
 /* (re)load the job record of `chunk` into shared memory unless the cached one already covers it */
-DSV_D void hz_cache_job(HzJob *sJ, int *s_have, const HzJob *jobs, int njobs, int chunk)
+DSV_D void hz_cache_job(HzJob *sJ, int *s_have, const HzJob *jobs, int njobs, int chunk, const HzMap &map)
 {
     __syncthreads(); /* everybody is done with the previous chunk (and with *sJ) */
     const bool hit = *s_have && chunk >= sJ->chunk_base && chunk < sJ->chunk_base + sJ->nchunks;
     __syncthreads();
     if (!hit) {
-        const int jid = hz_job_of_chunk(jobs, njobs, chunk);
+        const int jid = hz_job_of_chunk(jobs, njobs, chunk, map);
         const int *src = reinterpret_cast<const int *>(&jobs[jid]);
         int *dst = reinterpret_cast<int *>(sJ);
         for (int i = threadIdx.x; i < (int) (sizeof(HzJob) / sizeof(int)); i += HZ_THREADS) {
@@ -245,7 +253,7 @@ DSV_D void hz_cache_job(HzJob *sJ, int *s_have, const HzJob *jobs, int njobs, in
 #ifndef HZ_SCAN_MINB
 #define HZ_SCAN_MINB 8 /* measured: 8 -> 252 us, default (40 registers) -> 268 */
 #endif
-__global__ void __launch_bounds__(HZ_THREADS, HZ_SCAN_MINB) hzcc_scan_kernel(const HzJob *jobs, int njobs, HzChunk *chunks, int total_chunks)
+__global__ void __launch_bounds__(HZ_THREADS, HZ_SCAN_MINB) hzcc_scan_kernel(const HzJob *jobs, int njobs, HzChunk *chunks, int total_chunks, const HzMap map)
 {
     __shared__ HzJob J;
     __shared__ unsigned long long scratch[40];
@@ -259,7 +267,7 @@ __global__ void __launch_bounds__(HZ_THREADS, HZ_SCAN_MINB) hzcc_scan_kernel(con
         if (chunk >= total_chunks) {
             return;
         }
-        hz_cache_job(&J, &s_have, jobs, njobs, chunk);
+        hz_cache_job(&J, &s_have, jobs, njobs, chunk, map);
         if (tid == 0) {
             s_first = -1;
         }
@@ -437,7 +445,7 @@ DSV_D void or_bits_atomic(unsigned *words, unsigned long long bitpos, int len, u
 #define HZ_PACK_MINB 8 /* measured: 8 -> 193 us, 6 -> 202, default (48 registers) -> 216 */
 #endif
 __global__ void __launch_bounds__(HZ_THREADS, HZ_PACK_MINB) hzcc_pack_kernel(const HzJob *jobs, int njobs, const HzChunk *chunks,
-                                                               const HzFrame *frames, int total_chunks)
+                                                               const HzFrame *frames, int total_chunks, const HzMap map)
 {
     __shared__ HzJob J;
     __shared__ unsigned long long scratch[40];
@@ -456,7 +464,7 @@ __global__ void __launch_bounds__(HZ_THREADS, HZ_PACK_MINB) hzcc_pack_kernel(con
         if (C.cnt == 0) {
             continue; /* nothing to write (most chunks of a P picture); uniform for the whole block */
         }
-        hz_cache_job(&J, &s_have, jobs, njobs, chunk);
+        hz_cache_job(&J, &s_have, jobs, njobs, chunk, map);
         int sym[HZ_ITEMS], base;
         unsigned long long excl, last;
         chunk_load(J, chunk - J.chunk_base, sym, base, scratch, excl, last);
@@ -501,13 +509,18 @@ __global__ void __launch_bounds__(HZ_THREADS, HZ_PACK_MINB) hzcc_pack_kernel(con
 }
 
 void hzcc_enc_launch(const HzJob *d_jobs, int njobs, HzChunk *d_chunks, int total_chunks,
-                     HzFrame *d_frames, int nframes, cudaStream_t st)
+                     HzFrame *d_frames, int nframes, cudaStream_t st, int chunks_per_pic, int chunks_y, int chunks_u)
 {
-    DSV_LAUNCH(hzcc_scan_kernel, dim3(ceil_div(total_chunks, HZ_CPB)), dim3(HZ_THREADS), 0, st, d_jobs, njobs, d_chunks, total_chunks);
+    HzMap map;
+    map.per_pic = chunks_per_pic;
+    map.c0 = chunks_y;
+    map.c1 = chunks_u;
+    map.per_pic_fd = make_fastdiv(chunks_per_pic > 0 ? chunks_per_pic : 1);
+    DSV_LAUNCH(hzcc_scan_kernel, dim3(ceil_div(total_chunks, HZ_CPB)), dim3(HZ_THREADS), 0, st, d_jobs, njobs, d_chunks, total_chunks, map);
     KERNEL_CHECK();
     DSV_LAUNCH(hzcc_prefix_kernel, dim3(nframes), dim3(HZP_THREADS), 0, st, d_jobs, d_chunks, d_frames);
     KERNEL_CHECK();
-    DSV_LAUNCH(hzcc_pack_kernel, dim3(ceil_div(total_chunks, HZ_CPB)), dim3(HZ_THREADS), 0, st, d_jobs, njobs, d_chunks, d_frames, total_chunks);
+    DSV_LAUNCH(hzcc_pack_kernel, dim3(ceil_div(total_chunks, HZ_CPB)), dim3(HZ_THREADS), 0, st, d_jobs, njobs, d_chunks, d_frames, total_chunks, map);
     KERNEL_CHECK();
 }
 
