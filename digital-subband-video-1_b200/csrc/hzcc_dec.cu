@@ -152,8 +152,35 @@ template <class JT> DSV_D int dec_job_of(const JT *jobs, int njobs, int blk, int
     return lo;
 }
 
-/* per-thread table for its 32-bit word */
-DSV_D FsmSum word_summary(unsigned w)
+/*
+ * Per-thread table for its 32-bit word.  Walking the word bit by bit for each of the five distinguishable entry
+ * states is a chain of 160 dependent steps -- and P pictures are so small that a launch has only a few CTAs per
+ * picture, so that chain IS the kernel's run time.  Each CTA therefore first builds a byte-wise transition table in
+ * shared memory (state, byte) -> (exit state | token ends << 3): 7 x 16 nibble entries by stepping, the 7 x 256 byte
+ * entries by composing two nibbles; a word is then four lookups per entry state.
+ */
+#define FSM_TAB_BYTES (S_NUM * 256)
+DSV_D void fsm_build_table(uint8_t *tab /* shared, FSM_TAB_BYTES */, uint8_t *nib /* shared, S_NUM * 16 */)
+{
+    for (int e = threadIdx.x; e < S_NUM * 16; e += blockDim.x) {
+        int s = e >> 4;
+        unsigned ends = 0;
+#pragma unroll
+        for (int i = 3; i >= 0; i--) {
+            s = fsm_step(s, (e >> i) & 1, ends);
+        }
+        nib[e] = (uint8_t) ((unsigned) s | (ends << 3));
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < FSM_TAB_BYTES; e += blockDim.x) {
+        const unsigned hi = nib[((e >> 8) << 4) | ((e >> 4) & 15)];
+        const unsigned lo = nib[((hi & 7u) << 4) | (e & 15)];
+        tab[e] = (uint8_t) ((lo & 7u) | (((hi >> 3) + (lo >> 3)) << 3)); /* at most 6 token ends per byte */
+    }
+    __syncthreads();
+}
+
+DSV_D FsmSum word_summary(unsigned w, const uint8_t *tab)
 {
     FsmSum r;
     r.exits = 0;
@@ -161,13 +188,14 @@ DSV_D FsmSum word_summary(unsigned w)
     unsigned ex[5], ct[5];
 #pragma unroll
     for (int c = 0; c < 5; c++) {
-        int s = reps[c];
-        unsigned ends = 0;
-#pragma unroll 8
-        for (int i = 31; i >= 0; i--) {
-            s = fsm_step(s, (w >> i) & 1, ends);
+        unsigned s = (unsigned) reps[c], ends = 0;
+#pragma unroll
+        for (int b = 3; b >= 0; b--) {
+            const unsigned t = tab[(s << 8) | ((w >> (8 * b)) & 0xffu)];
+            s = t & 7u;
+            ends += t >> 3;
         }
-        ex[c] = (unsigned) s;
+        ex[c] = s;
         ct[c] = ends;
     }
     const int cls[S_NUM] = {0, 0, 1, 2, 2, 3, 4};
@@ -218,12 +246,15 @@ DSV_D FsmSum block_scan_fsm(const FsmSum &mine, FsmSum *warp_tab /* [8] shared *
 __global__ void __launch_bounds__(HZD_THREADS) hzdec_fsm_kernel(const HzDecJob *jobs, int njobs)
 {
     __shared__ FsmSum warp_tab[8];
+    __shared__ uint8_t s_tab[FSM_TAB_BYTES], s_nib[S_NUM * 16];
     const int jid = dec_job_of(jobs, njobs, (int) blockIdx.x, &HzDecJob::fsm_cta_base);
     const HzDecJob &J = jobs[jid];
     const int cta = (int) blockIdx.x - J.fsm_cta_base;
     const unsigned long long pos = (unsigned long long) J.tok_bit0 + (unsigned long long) cta * HZD_CTA_BITS +
                                    (unsigned long long) threadIdx.x * HZD_WORD_BITS;
-    FsmSum mine = word_summary(body_word(J, pos));
+    const unsigned w = body_word(J, pos); /* in flight while the table is built */
+    fsm_build_table(s_tab, s_nib);
+    FsmSum mine = word_summary(w, s_tab);
     FsmSum total;
     block_scan_fsm(mine, warp_tab, &total);
     if (threadIdx.x == 0) {
@@ -269,13 +300,15 @@ __global__ void __launch_bounds__(HZD_THREADS) hzdec_link_kernel(const HzDecJob 
 __global__ void __launch_bounds__(HZD_THREADS) hzdec_token_kernel(const HzDecJob *jobs, int njobs)
 {
     __shared__ FsmSum warp_tab[8];
+    __shared__ uint8_t s_tab[FSM_TAB_BYTES], s_nib[S_NUM * 16];
     const int jid = dec_job_of(jobs, njobs, (int) blockIdx.x, &HzDecJob::fsm_cta_base);
     const HzDecJob &J = jobs[jid];
     const int cta = (int) blockIdx.x - J.fsm_cta_base;
     const unsigned long long pos0 = (unsigned long long) J.tok_bit0 + (unsigned long long) cta * HZD_CTA_BITS +
                                     (unsigned long long) threadIdx.x * HZD_WORD_BITS;
     const unsigned w = body_word(J, pos0);
-    FsmSum mine = word_summary(w);
+    fsm_build_table(s_tab, s_nib);
+    FsmSum mine = word_summary(w, s_tab);
     FsmSum ex = block_scan_fsm(mine, warp_tab, nullptr);
     const unsigned ce = J.cta_entry[cta];
     const unsigned cst = ce & 7;
