@@ -1,3 +1,5 @@
+import signal
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)  # quiet under `| head`
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 print("value",round(d["value"],1),"e2e",round(d["e2e"]["value"],1),"ms/step",round(d["ms_per_step"],2),"launches",d["gpu_launches"])
