@@ -64,6 +64,7 @@ template <int N> DSV_D void block_reduce_n(unsigned (&acc)[N], unsigned *scratch
 
 struct BlockGeom {
     int bx, by, bw, bh, words;
+    int wmag; /* (idx * wmag) >> 20 == idx / words for idx < 1024 (a block has at most 16 x 64 words) */
     unsigned tail_mask;
 };
 
@@ -126,7 +127,7 @@ DSV_D void search_block(const HmeArgs &A, int i, int j, const BlockGeom &G, cons
     if (n > 1) {
         unsigned acc[6] = {0, 0, 0, 0, 0, 0};
         for (int idx = tid; idx < G.words * G.bh; idx += nthr) {
-            const int r = idx / G.words, wx = idx - r * G.words;
+            const int r = (idx * G.wmag) >> 20, wx = idx - r * G.words;
             const unsigned m = (wx == G.words - 1) ? G.tail_mask : 0xffffffffu;
             const unsigned a = *reinterpret_cast<const unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * wx);
 #pragma unroll
@@ -154,7 +155,7 @@ DSV_D void search_block(const HmeArgs &A, int i, int j, const BlockGeom &G, cons
     const int xf[9] = {0, 1, -1, 0, 0, -1, 1, -1, 1}, yf[9] = {0, 0, 0, 1, -1, -1, -1, 1, 1};
     unsigned acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int idx = tid; idx < G.words * G.bh; idx += nthr) {
-        const int r = idx / G.words, wx = idx - r * G.words;
+        const int r = (idx * G.wmag) >> 20, wx = idx - r * G.words;
         const unsigned m = (wx == G.words - 1) ? G.tail_mask : 0xffffffffu;
         const unsigned a = *reinterpret_cast<const unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * wx);
         const uint8_t *rp = A.ref.p + (ptrdiff_t) (yy + r) * rs + xx + 4 * wx;
@@ -189,10 +190,11 @@ DSV_D bool block_setup(const HmeArgs &A, int i, int j, BlockGeom &G, uint8_t *s_
     G.bw = imin(A.src.w - G.bx, A.blk_w);
     G.bh = imin(A.src.h - G.by, A.blk_h);
     G.words = (G.bw + 3) >> 2;
+    G.wmag = magic20(G.words);
     const int tail = G.bw & 3;
     G.tail_mask = tail ? ((1u << (8 * tail)) - 1u) : 0xffffffffu;
     for (int idx = threadIdx.x; idx < G.words * G.bh; idx += blockDim.x) {
-        const int r = idx / G.words, wx = idx - r * G.words;
+        const int r = (idx * G.wmag) >> 20, wx = idx - r * G.words;
         const unsigned m = (wx == G.words - 1) ? G.tail_mask : 0xffffffffu;
         *reinterpret_cast<unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * wx) =
             ld4u(A.src.p + (ptrdiff_t) (G.by + r) * A.src.stride + G.bx + 4 * wx) & m;
@@ -347,7 +349,7 @@ __global__ void __launch_bounds__(HME_THREADS, HME_L0_MINB) hme_l0_kernel(const 
     }
     /* zero-MV reference block */
     for (int idx = tid; idx < G.words * G.bh; idx += HME_THREADS) {
-        const int r = idx / G.words, wx = idx - r * G.words;
+        const int r = (idx * G.wmag) >> 20, wx = idx - r * G.words;
         *reinterpret_cast<unsigned *>(s_ref0 + r * HME_SRC_STRIDE + 4 * wx) =
             ld4u(A.ref.p + (ptrdiff_t) (G.by + r) * rs + G.bx + 4 * wx);
     }
@@ -511,12 +513,21 @@ __global__ void __launch_bounds__(HME_THREADS, HME_L0_MINB) hme_l0_kernel(const 
     }
     __syncthreads();
     {
+        /* clamp_u8(ravg + clamp_u8(p - ravg + 128) - 128) != p  <=>  the inner clamp is active  <=>  p outside
+         * [ravg - 128, ravg + 127]; four samples per step from the staged words */
+        const int lo = ravg - 128, hi = ravg + 127;
         int bad = 0;
-        for (int ly = wid; ly < G.bh; ly += HME_THREADS / 32) {
-            for (int lx = lane; lx < G.bw; lx += 32) {
-                const int p = s_src[ly * HME_SRC_STRIDE + lx];
-                const int d = clamp_u8((ravg + clamp_u8((p - ravg) + 128)) - 128);
-                bad |= d != p;
+        if (lo > 0 || hi < 255) {
+            const int tail = G.bw & 3;
+            for (int idx = tid; idx < G.words * G.bh; idx += HME_THREADS) {
+                const int r = (idx * G.wmag) >> 20, wx = idx - r * G.words;
+                const unsigned w = *reinterpret_cast<const unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * wx);
+                const int nb = (wx == G.words - 1 && tail) ? tail : 4;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int p = byte_of(w, e);
+                    bad |= (e < nb) & ((p < lo) | (p > hi));
+                }
             }
         }
         if (bad) {
