@@ -83,3 +83,38 @@ def test_decoder_output_options_tiny(emu, ref):
             a, p = da.reshape(n, fb), plain.reshape(n, fb)
             assert (a[:, :w * h] != p[:, :w * h]).any()
             assert (a[:, w * h:] != p[:, w * h:]).any()  # the reference's unchecked intra dots reached chroma
+
+
+def test_batch_api_ragged_and_small_buffers(emu):
+    """Batch API edge cases on the host side of the engines: streams of different lengths sharing lanes (a lane that
+    runs out of packets idles while the others go on; more streams than lanes), an output buffer with room for only
+    some pictures, a stream buffer that is too small."""
+    w, h, fmt = 64, 48, "420"
+    sub = L.SUBSAMP[fmt]
+    fb = L.frame_bytes(w, h, sub)
+    cfg = L.make_cfg(w, h, fmt, gop=12, qp=70)
+    counts = [1, 3, 2]
+    seqs = [L.synth_sequence(w, h, fmt, n, 50 + i, 0) for i, n in enumerate(counts)]
+    streams = [emu.encode_sequence(cfg, s, n)[0] for s, n in zip(seqs, counts)]
+    want = [emu.decode_stream(s, w, h, sub, n)[1] for s, n in zip(streams, counts)]
+    bd = L.BatchDecoder(emu, 2)
+    outs, fr = bd.decode(streams, fb, 3)
+    assert fr == counts
+    for o, wnt, n in zip(outs, want, counts):
+        assert np.array_equal(o[:fb * n], wnt)
+    # room for the first picture only: later pictures are decoded (references stay in step) but not delivered
+    bufs = [np.frombuffer(s, dtype=np.uint8) for s in streams]
+    small = [np.zeros(fb, dtype=np.uint8) for _ in streams]
+    rc, fr = bd.decode_ptrs([b.ctypes.data for b in bufs], None, [len(b) for b in bufs], [o.ctypes.data for o in small],
+                            [fb] * 3, 0)
+    bd.close()
+    assert rc == 0 and fr == [1, 1, 1]
+    for o, wnt in zip(small, want):
+        assert np.array_equal(o, wnt[:fb])
+    # encoder: a stream buffer that cannot hold the packets is reported, not overrun
+    be = L.BatchEncoder(emu, cfg, 2)
+    guard = np.full(4096, 0xAB, dtype=np.uint8)
+    rc, lens = be.encode_ptrs([seqs[1].ctypes.data], 3, 0, [guard.ctypes.data], [64])
+    be.close()
+    assert rc == -1
+    assert (guard[64:] == 0xAB).all()
