@@ -118,3 +118,25 @@ def test_batch_api_ragged_and_small_buffers(emu):
     be.close()
     assert rc == -1
     assert (guard[64:] == 0xAB).all()
+
+
+def test_odd_geometry_tiny(emu, ref):
+    """Widths that leave partial words / partial blocks at the right and bottom edges (block 16x16 on 54x38: the
+    last block column is 6 samples wide): search, block statistics, reduced-range intra test, whole codec."""
+    w, h, fmt, n = 54, 38, "420", 3
+    sub = L.SUBSAMP[fmt]
+    fr = L.synth_sequence(w, h, fmt, 1, 6, 0, start=0)
+    fs = L.synth_sequence(w, h, fmt, 1, 8, 0, start=1).copy()
+    y = fs[:w * h].reshape(h, w)
+    y[:, w - 12:] = 255
+    y[h - 9:, :] = 0
+    pr, mr = ref.hme(fs, fr, w, h, sub, 3)
+    pe, me = emu.hme(fs, fr, w, h, sub, 3)
+    assert pr == pe and all(np.array_equal(mr[k], me[k]) for k in mr.dtype.names if k != "pad")
+    assert (mr["mode"] == 1).any()
+    yuv = L.synth_sequence(w, h, fmt, n, 6, 2)
+    cfg = L.make_cfg(w, h, fmt, gop=12, qp=60, do_scd=0, intra_pct=100)
+    sa, _, _ = ref.encode_sequence(cfg, yuv, n)
+    sb, _, _ = emu.encode_sequence(cfg, yuv, n)
+    assert sa == sb
+    assert np.array_equal(ref.decode_stream(sa, w, h, sub, n)[1], emu.decode_stream(sa, w, h, sub, n)[1])
