@@ -207,6 +207,7 @@ extern "C" int dsvk_decode_plane(const uint8_t *in, int plen, int cw, int ch, in
 /* ---- motion: pyramid, HME, BMC ------------------------------------------------------------------ */
 #include "frame.cuh"
 #include "motion.cuh"
+#include "dsv1_b200.h"
 
 namespace {
 
@@ -307,6 +308,69 @@ extern "C" int dsvk_hme(const uint8_t *src_yuv, const uint8_t *ref_yuv, int w, i
     CUDA_CHECK(cudaMemcpy(&nintra, cnt.p, sizeof(int), cudaMemcpyDeviceToHost));
     CUDA_CHECK(cudaMemcpy(mv_out, mvf[0], sizeof(DevMV) * (size_t) nblk, cudaMemcpyDeviceToHost));
     for (int l = 0; l <= levels; l++) {
+        cudaFree(mvf[l]);
+        devframe_free(&sf[l]);
+        devframe_free(&rf[l]);
+    }
+    return nintra * 100 / nblk;
+}
+
+/* a caller's host frame -> device frame, border included when the caller's frame has one (the search reads it) */
+static void upload_host_frame(DevFrame *f, const DSV_FRAME *src)
+{
+    devframe_alloc(f, src->width, src->height, src->format);
+    for (int c = 0; c < 3; c++) {
+        const DSV_PLANE &pl = src->planes[c];
+        if (src->border && pl.stride >= pl.w + 2 * DSV_BORDER) {
+            const int rows = pl.h + 2 * DSV_BORDER, cols = pl.w + 2 * DSV_BORDER;
+            CUDA_CHECK(cudaMemcpy2D(f->p[c] - (ptrdiff_t) DSV_BORDER * f->stride[c] - DSV_BORDER, (size_t) f->stride[c],
+                                    pl.data - (ptrdiff_t) DSV_BORDER * pl.stride - DSV_BORDER, (size_t) pl.stride, (size_t) cols, (size_t) rows,
+                                    cudaMemcpyHostToDevice));
+        } else {
+            CUDA_CHECK(cudaMemcpy2D(f->p[c], (size_t) f->stride[c], pl.data, (size_t) pl.stride, (size_t) pl.w, (size_t) pl.h, cudaMemcpyHostToDevice));
+        }
+    }
+    if (!src->border) {
+        frame_extend_launch(*f, 3, 0);
+    }
+}
+
+/* drop-in for the reference's exported dsv_hme (dsv_encoder.h:122-132, hme.c:730-741) */
+extern "C" int dsv_hme(DSV_HME *hme)
+{
+    const DSV_PARAMS *pr = hme->params;
+    const int levels = hme->levels;
+    if (levels < 0 || levels > DSV_MAX_PYRAMID_LEVELS) {
+        return 0;
+    }
+    const DSV_FRAME *top = hme->src[0];
+    MotionGeom g = motion_geom(top->width, top->height, top->format, pr->blk_w, pr->blk_h, levels);
+    g.nbh = pr->nblocks_h;
+    g.nbv = pr->nblocks_v;
+    const int nblk = g.nbh * g.nbv;
+    DevFrame sf[DSV_MAX_PYRAMID_LEVELS + 1], rf[DSV_MAX_PYRAMID_LEVELS + 1];
+    DevMV *mvf[DSV_MAX_PYRAMID_LEVELS + 1];
+    for (int l = 0; l <= levels; l++) {
+        upload_host_frame(&sf[l], hme->src[l]);
+        upload_host_frame(&rf[l], hme->ref[l]);
+        CUDA_CHECK(cudaMalloc(&mvf[l], sizeof(DevMV) * (size_t) nblk));
+        CUDA_CHECK(cudaMemset(mvf[l], 0, sizeof(DevMV) * (size_t) nblk));
+    }
+    DevBuf aux(sizeof(int2) * (size_t) nblk), cnt(sizeof(int)), dargs(sizeof(HmeArgs) * (size_t) (levels + 1));
+    CUDA_CHECK(cudaMemset(cnt.p, 0, sizeof(int)));
+    std::vector<HmeArgs> ha((size_t) levels + 1);
+    for (int l = 0; l <= levels; l++) {
+        hme_fill_args(&ha[(size_t) l], g, l, sf, rf, mvf, aux.as<int2>(), cnt.as<int>());
+    }
+    CUDA_CHECK(cudaMemcpy(dargs.p, ha.data(), sizeof(HmeArgs) * ha.size(), cudaMemcpyHostToDevice));
+    hme_launch(dargs.as<HmeArgs>(), 1, g, 0);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    int nintra = 0;
+    CUDA_CHECK(cudaMemcpy(&nintra, cnt.p, sizeof(int), cudaMemcpyDeviceToHost));
+    static_assert(sizeof(DSV_MV) == sizeof(DevMV), "DevMV is the device twin of DSV_MV");
+    for (int l = 0; l <= levels; l++) {
+        hme->mvf[l] = (DSV_MV *) dsv_alloc((int) (sizeof(DSV_MV) * (size_t) nblk));
+        CUDA_CHECK(cudaMemcpy(hme->mvf[l], mvf[l], sizeof(DevMV) * (size_t) nblk, cudaMemcpyDeviceToHost));
         cudaFree(mvf[l]);
         devframe_free(&sf[l]);
         devframe_free(&rf[l]);

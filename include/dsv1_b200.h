@@ -282,6 +282,21 @@ void dsv_enc_start(DSV_ENCODER *enc);                             /* dsv_encoder
 int dsv_enc(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_BUF *bufs);
 void dsv_enc_end_of_stream(DSV_ENCODER *enc, DSV_BUF *bufs);      /* dsv_encoder.c:765-778 */
 
+/* "used internally" by the reference encoder but exported by it (dsv_encoder.h:122-132, hme.c:730-741):
+ * hierarchical motion estimation over caller-built pyramids.  src[i] / ref[i] are level-i frames WITH borders
+ * (level 0 = full size; only luma matters above level 0), levels = index of the coarsest level.  On return
+ * mvf[i] (i = 0..levels) are dsv_alloc'd arrays of nblocks_h * nblocks_v vectors the caller frees with dsv_free;
+ * the value is the percentage of intra blocks at level 0.  Here the frames are copied to the GPU, searched by the
+ * same kernels the encoder uses, and the fields copied back. */
+typedef struct {
+    DSV_PARAMS *params;
+    DSV_FRAME *src[DSV_MAX_PYRAMID_LEVELS + 1];
+    DSV_FRAME *ref[DSV_MAX_PYRAMID_LEVELS + 1];
+    DSV_MV *mvf[DSV_MAX_PYRAMID_LEVELS + 1];
+    int levels;
+} DSV_HME;
+int dsv_hme(DSV_HME *hme);
+
 /* ------------------------------------------------------------------------- */
 /* Decoder (dsv_decoder.h:26-59)                                              */
 /* ------------------------------------------------------------------------- */

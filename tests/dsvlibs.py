@@ -142,6 +142,15 @@ class Lib:
         pct = self.fn("hme")(ptr(src), ptr(ref), w, h, subsamp, bw, bh, levels, ptr(mv))
         return pct, mv.view(MV_DTYPE)
 
+    def hme_api(self, src, ref, w, h, subsamp, levels):
+        """dsv_hme through its exported DSV_HME interface (tools/api_harness.c builds the pyramids): intra percentage and
+        the vector fields of every level, level 0 first."""
+        bw, bh, nbh, nbv = block_dims(w, h)
+        mv = np.zeros((levels + 1) * nbh * nbv * 12, dtype=np.uint8)
+        pct = self.fn("hme_api", api=True)(ptr(np.ascontiguousarray(src, dtype=np.uint8)), ptr(np.ascontiguousarray(ref, dtype=np.uint8)),
+                                           w, h, subsamp, bw, bh, levels, ptr(mv))
+        return pct, mv.view(MV_DTYPE).reshape(levels + 1, nbh * nbv)
+
     def pyramid(self, yuv, w, h, subsamp, levels):
         yuv = np.ascontiguousarray(yuv, dtype=np.uint8)
         out = np.zeros(w * h, dtype=np.uint8)

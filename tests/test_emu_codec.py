@@ -140,3 +140,15 @@ def test_odd_geometry_tiny(emu, ref):
     sb, _, _ = emu.encode_sequence(cfg, yuv, n)
     assert sa == sb
     assert np.array_equal(ref.decode_stream(sa, w, h, sub, n)[1], emu.decode_stream(sa, w, h, sub, n)[1])
+
+
+def test_dsv_hme_exported_interface_tiny(emu, ref):
+    """The reference also exports dsv_hme(DSV_HME *): same call, caller-built pyramids, all levels compared."""
+    w, h, fmt, lv = 90, 70, "444", 2
+    sub = L.SUBSAMP[fmt]
+    fr = L.synth_sequence(w, h, fmt, 1, 4, 0, start=3)
+    fs = L.synth_sequence(w, h, fmt, 1, 9, 0, start=4)
+    pr, mr = ref.hme_api(fs, fr, w, h, sub, lv)
+    pe, me = emu.hme_api(fs, fr, w, h, sub, lv)
+    assert pr == pe and all(np.array_equal(mr[k], me[k]) for k in mr.dtype.names if k != "pad")
+    assert (mr[0]["mode"] == 1).any() and (mr[1]["x"] != 0).any()

@@ -80,3 +80,18 @@ def test_uhd444_hme(gpu, ref):
     pred_r, res_r = ref.sub_pred(mr, w, h, sub, fs, fr)
     pred_g, res_g = gpu.sub_pred(mr, w, h, sub, fs, fr)
     assert np.array_equal(pred_r, pred_g) and np.array_equal(res_r, res_g)
+
+
+def test_dsv_hme_exported_interface(gpu, ref):
+    """dsv_hme(DSV_HME *) itself (dsv_encoder.h:122-132): caller-built bordered pyramids in, dsv_alloc'd vector
+    fields of every level out -- driven by tools/api_harness.c for both libraries."""
+    for (w, h, fmt, lv) in [(176, 144, "420", 3), (90, 70, "444", 2), (640, 360, "422", 4), (1920, 1080, "420", 4)]:
+        sub = L.SUBSAMP[fmt]
+        fr = L.synth_sequence(w, h, fmt, 1, 4, 0, start=3)
+        fs = L.synth_sequence(w, h, fmt, 1, 9 if w < 1000 else 4, 0, start=4)
+        pr, mr = ref.hme_api(fs, fr, w, h, sub, lv)
+        pg, mg = gpu.hme_api(fs, fr, w, h, sub, lv)
+        assert pr == pg
+        for k in mr.dtype.names:
+            if k != "pad":
+                assert np.array_equal(mr[k], mg[k]), (w, h, fmt, k)

@@ -5,7 +5,7 @@
 #define S(t) printf("sizeof %s %zu\n", #t, sizeof(t))
 #define O(t,f) printf("offsetof %s.%s %zu\n", #t, #f, offsetof(t,f))
 int main(void){
- S(DSV_META);S(DSV_PLANE);S(DSV_COEFS);S(DSV_FRAME);S(DSV_MV);S(DSV_PARAMS);S(DSV_BUF);S(DSV_ENCODER);S(DSV_DECODER);
+ S(DSV_META);S(DSV_PLANE);S(DSV_COEFS);S(DSV_FRAME);S(DSV_MV);S(DSV_PARAMS);S(DSV_BUF);S(DSV_ENCODER);S(DSV_DECODER);S(DSV_HME);
  O(DSV_PLANE,data);O(DSV_PLANE,len);O(DSV_PLANE,format);O(DSV_PLANE,stride);O(DSV_PLANE,w);O(DSV_PLANE,h);O(DSV_PLANE,hs);O(DSV_PLANE,vs);
  O(DSV_FRAME,alloc);O(DSV_FRAME,planes);O(DSV_FRAME,refcount);O(DSV_FRAME,format);O(DSV_FRAME,width);O(DSV_FRAME,height);O(DSV_FRAME,border);
  O(DSV_MV,u);O(DSV_MV,mode);O(DSV_MV,submask);O(DSV_MV,lo_var);O(DSV_MV,lo_tex);O(DSV_MV,high_detail);
@@ -16,5 +16,6 @@ int main(void){
  O(DSV_ENCODER,stable_blocks);O(DSV_ENCODER,prev_gop);O(DSV_ENCODER,prev_avg_luma);
  O(DSV_DECODER,vidmeta);O(DSV_DECODER,ref);O(DSV_DECODER,draw_info);O(DSV_DECODER,got_metadata);
  O(DSV_PARAMS,vidmeta);O(DSV_PARAMS,is_ref);O(DSV_PARAMS,has_ref);O(DSV_PARAMS,blk_w);O(DSV_PARAMS,blk_h);O(DSV_PARAMS,nblocks_h);O(DSV_PARAMS,nblocks_v);
+ O(DSV_HME,params);O(DSV_HME,src);O(DSV_HME,ref);O(DSV_HME,mvf);O(DSV_HME,levels);
  O(DSV_BUF,data);O(DSV_BUF,len);O(DSV_META,width);O(DSV_META,aspect_den);
  return 0;}

@@ -269,3 +269,77 @@ FN(decode_stream)(const uint8_t *stream, long len, uint8_t *yuv_out, long out_ca
 {
     return FN(decode_stream_ex)(stream, len, yuv_out, out_cap, meta_out, seconds, 0, 0);
 }
+
+/*
+ * dsv_hme through its exported interface (dsv_encoder.h:122-132): the caller owns the pyramids.  Builds bordered
+ * frames for `levels` + 1 levels of src and ref (2x2 rounded box filter on luma, like the encoder's pyramid), runs
+ * dsv_hme and returns the intra percentage; mv_out receives the vector fields of all levels, level 0 first
+ * ((levels + 1) * nblocks * sizeof(DSV_MV) bytes).
+ */
+static DSV_FRAME *harness_half(DSV_FRAME *prev)
+{
+    int w = (prev->width + 1) / 2, h = (prev->height + 1) / 2, x, y;
+    DSV_FRAME *f = dsv_mk_frame(prev->format, w, h, 1);
+    DSV_PLANE *s = &prev->planes[0], *d = &f->planes[0];
+    for (y = 0; y < h; y++) {
+        for (x = 0; x < w; x++) {
+            /* may read one sample into the (replicated) border of the level above */
+            int a = DSV_GET_LINE(s, 2 * y)[2 * x], b = DSV_GET_LINE(s, 2 * y)[2 * x + 1];
+            int c = DSV_GET_LINE(s, 2 * y + 1)[2 * x], e = DSV_GET_LINE(s, 2 * y + 1)[2 * x + 1];
+            DSV_GET_LINE(d, y)[x] = (uint8_t) ((a + b + c + e + 2) >> 2);
+        }
+    }
+    return dsv_extend_frame(f);
+}
+
+static DSV_FRAME *harness_bordered(const uint8_t *yuv, int w, int h, int subsamp)
+{
+    DSV_FRAME *wrap = dsv_load_planar_frame(subsamp, (void *) yuv, w, h);
+    DSV_FRAME *f = dsv_clone_frame(wrap, 1);
+    dsv_frame_ref_dec(wrap);
+    return f;
+}
+
+int
+FN(hme_api)(const uint8_t *src_yuv, const uint8_t *ref_yuv, int w, int h, int subsamp, int blk_w, int blk_h,
+            int levels, uint8_t *mv_out)
+{
+    DSV_HME hme;
+    DSV_PARAMS params;
+    DSV_META meta;
+    int i, pct, nblk;
+
+    if (levels < 0 || levels > DSV_MAX_PYRAMID_LEVELS) {
+        return -1;
+    }
+    memset(&hme, 0, sizeof(hme));
+    memset(&params, 0, sizeof(params));
+    memset(&meta, 0, sizeof(meta));
+    meta.width = w;
+    meta.height = h;
+    meta.subsamp = subsamp;
+    params.vidmeta = &meta;
+    params.has_ref = 1;
+    params.is_ref = 1;
+    params.blk_w = blk_w;
+    params.blk_h = blk_h;
+    params.nblocks_h = (w + blk_w - 1) / blk_w;
+    params.nblocks_v = (h + blk_h - 1) / blk_h;
+    nblk = params.nblocks_h * params.nblocks_v;
+    hme.params = &params;
+    hme.levels = levels;
+    hme.src[0] = harness_bordered(src_yuv, w, h, subsamp);
+    hme.ref[0] = harness_bordered(ref_yuv, w, h, subsamp);
+    for (i = 1; i <= levels; i++) {
+        hme.src[i] = harness_half(hme.src[i - 1]);
+        hme.ref[i] = harness_half(hme.ref[i - 1]);
+    }
+    pct = dsv_hme(&hme);
+    for (i = 0; i <= levels; i++) {
+        memcpy(mv_out + (size_t) i * nblk * sizeof(DSV_MV), hme.mvf[i], (size_t) nblk * sizeof(DSV_MV));
+        dsv_free(hme.mvf[i]);
+        dsv_frame_ref_dec(hme.src[i]);
+        dsv_frame_ref_dec(hme.ref[i]);
+    }
+    return pct;
+}
