@@ -264,6 +264,80 @@ DSV_FRAME *dsv_clone_frame(DSV_FRAME *s, int border)
     return d;
 }
 
+/* ---- the remaining frame helpers dsv.h declares (host frames, host arithmetic: they are part of the public header,
+ * the codec itself does these steps in frame_ops.cu / sbt_inv.cu on the device) ------------------------------------ */
+void dsv_frame_add(DSV_FRAME *dst, DSV_FRAME *src) /* bmc.c:304-316: dst = clamp(dst + src - 128) */
+{
+    for (int c = 0; c < 3; c++) {
+        DSV_PLANE *s = &src->planes[c], *d = &dst->planes[c];
+        for (int y = 0; y < d->h; y++) {
+            uint8_t *o = DSV_GET_LINE(d, y);
+            const uint8_t *a = DSV_GET_LINE(s, y);
+            for (int x = 0; x < d->w; x++) {
+                const int v = o[x] + a[x] - 128;
+                o[x] = (uint8_t) (v < 0 ? 0 : (v > 255 ? 255 : v));
+            }
+        }
+    }
+}
+
+int dsv_frame_avg_luma(DSV_FRAME *frame) /* frame.c:223-238 */
+{
+    const DSV_PLANE *p = &frame->planes[0];
+    long long acc = 0;
+    for (int y = 0; y < p->h; y++) {
+        const uint8_t *line = DSV_GET_LINE(p, y);
+        for (int x = 0; x < p->w; x++) {
+            acc += line[x];
+        }
+    }
+    return (int) (acc / ((long long) p->w * p->h));
+}
+
+void dsv_ds2x_frame_luma(DSV_FRAME *dst, DSV_FRAME *src) /* frame.c:240-261: rounded 2x2 mean, luma only */
+{
+    const DSV_PLANE *s = &src->planes[0];
+    DSV_PLANE *d = &dst->planes[0];
+    for (int y = 0; y < d->h; y++) {
+        const uint8_t *r0 = DSV_GET_LINE(s, 2 * y), *r1 = r0 + s->stride; /* an odd source size reads its border */
+        uint8_t *o = DSV_GET_LINE(d, y);
+        for (int x = 0; x < d->w; x++) {
+            o[x] = (uint8_t) ((r0[2 * x] + r0[2 * x + 1] + r1[2 * x] + r1[2 * x + 1] + 2) >> 2);
+        }
+    }
+}
+
+DSV_FRAME *dsv_extend_frame_luma(DSV_FRAME *frame) /* frame.c:297-327 */
+{
+    if (!frame->border) {
+        return frame;
+    }
+    const int B = DSV_MAX_BLOCK_SIZE;
+    DSV_PLANE *p = &frame->planes[0];
+    for (int y = 0; y < p->h; y++) {
+        uint8_t *line = DSV_GET_LINE(p, y);
+        memset(line - B, line[0], B);
+        memset(line + p->w, line[p->w - 1], B);
+    }
+    for (int j = 1; j <= B; j++) {
+        memcpy(DSV_GET_XY(p, -B, -j), DSV_GET_XY(p, -B, 0), p->w + 2 * B);
+        memcpy(DSV_GET_XY(p, -B, p->h - 1 + j), DSV_GET_XY(p, -B, p->h - 1), p->w + 2 * B);
+    }
+    return frame;
+}
+
+void dsv_plane_xy(DSV_FRAME *frame, DSV_PLANE *out, int c, int x, int y) /* frame.c:329-342: a window into plane c */
+{
+    const DSV_PLANE *p = &frame->planes[c];
+    out->format = p->format;
+    out->data = DSV_GET_XY(p, x, y);
+    out->stride = p->stride;
+    out->w = p->w - x > 0 ? p->w - x : 0;
+    out->h = p->h - y > 0 ? p->h - y : 0;
+    out->hs = p->hs;
+    out->vs = p->vs;
+}
+
 void dsv_mk_coefs(DSV_COEFS *c, int format, int width, int height)
 {
     const int hs = DSV_FORMAT_H_SHIFT(format), vs = DSV_FORMAT_V_SHIFT(format);

@@ -179,6 +179,11 @@ void dsv_frame_ref_dec(DSV_FRAME *frame);                                       
 void dsv_frame_copy(DSV_FRAME *dst, DSV_FRAME *src);                              /* frame.c:199-221 */
 DSV_FRAME *dsv_clone_frame(DSV_FRAME *f, int border);                             /* frame.c:166-175 */
 DSV_FRAME *dsv_extend_frame(DSV_FRAME *frame);                                    /* frame.c:263-295 */
+void dsv_frame_add(DSV_FRAME *dst, DSV_FRAME *src);                               /* bmc.c:304-316 */
+int dsv_frame_avg_luma(DSV_FRAME *frame);                                         /* frame.c:223-238 */
+void dsv_ds2x_frame_luma(DSV_FRAME *dest, DSV_FRAME *src);                        /* frame.c:240-261 */
+DSV_FRAME *dsv_extend_frame_luma(DSV_FRAME *frame);                               /* frame.c:297-327 */
+void dsv_plane_xy(DSV_FRAME *f, DSV_PLANE *out, int c, int x, int y);             /* frame.c:329-342 */
 void dsv_mk_coefs(DSV_COEFS *c, int format, int width, int height);               /* frame.c:29-61 */
 
 /* logging (dsv.h:215-247, dsv.c:19-39) */

@@ -343,3 +343,65 @@ FN(hme_api)(const uint8_t *src_yuv, const uint8_t *ref_yuv, int w, int h, int su
     }
     return pct;
 }
+
+/*
+ * The frame helpers of dsv.h that the codec path itself does not go through (dsv_ds2x_frame_luma,
+ * dsv_extend_frame_luma, dsv_frame_avg_luma, dsv_frame_add, dsv_plane_xy): exercised on one picture, everything
+ * they produce is written to out so that the two libraries can be compared byte for byte.  Host-only: needs no GPU.
+ * Returns the number of bytes written (or -1 if out_cap is too small).
+ */
+long
+FN(frame_helpers_probe)(const uint8_t *yuv, int w, int h, int subsamp, uint8_t *out, long out_cap)
+{
+    DSV_FRAME *a = harness_bordered(yuv, w, h, subsamp);
+    DSV_FRAME *half = dsv_mk_frame(subsamp, (w + 1) / 2, (h + 1) / 2, 1);
+    DSV_FRAME *sum = dsv_clone_frame(a, 0), *other = dsv_clone_frame(a, 0);
+    DSV_PLANE win, *hp = &half->planes[0];
+    long n = 0;
+    int c, y, meta[8];
+    int B = 64; /* DSV_FRAME_BORDER */
+
+    dsv_ds2x_frame_luma(half, a);
+    dsv_extend_frame_luma(half);
+    /* make `other` differ from `sum` so that both clamps of the add are reached */
+    for (y = 0; y < other->planes[0].h; y++) {
+        uint8_t *line = DSV_GET_LINE(&other->planes[0], y);
+        int x;
+        for (x = 0; x < other->planes[0].w; x++) {
+            line[x] = (uint8_t) (255 - line[x] + ((x ^ y) & 63));
+        }
+    }
+    dsv_frame_add(sum, other);
+    memset(&win, 0, sizeof(win));
+    dsv_plane_xy(a, &win, 1, 3, 2);
+    meta[0] = dsv_frame_avg_luma(a);
+    meta[1] = dsv_frame_avg_luma(half);
+    meta[2] = win.w;
+    meta[3] = win.h;
+    meta[4] = win.stride;
+    meta[5] = (int) (win.data - a->planes[1].data);
+    meta[6] = win.hs * 16 + win.vs;
+    meta[7] = win.format;
+    if ((long) sizeof(meta) + (long) (hp->w + 2 * B) * (hp->h + 2 * B) + frame_bytes(w, h, subsamp) > out_cap) {
+        n = -1;
+    } else {
+        memcpy(out, meta, sizeof(meta));
+        n = (long) sizeof(meta);
+        for (y = -B; y < hp->h + B; y++) { /* the half-size luma with its border */
+            memcpy(out + n, DSV_GET_XY(hp, -B, y), (size_t) (hp->w + 2 * B));
+            n += hp->w + 2 * B;
+        }
+        for (c = 0; c < 3; c++) {
+            DSV_PLANE *p = &sum->planes[c];
+            for (y = 0; y < p->h; y++) {
+                memcpy(out + n, DSV_GET_LINE(p, y), (size_t) p->w);
+                n += p->w;
+            }
+        }
+    }
+    dsv_frame_ref_dec(a);
+    dsv_frame_ref_dec(half);
+    dsv_frame_ref_dec(sum);
+    dsv_frame_ref_dec(other);
+    return n;
+}
