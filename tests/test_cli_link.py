@@ -99,3 +99,16 @@ def test_public_frame_helpers_match_reference():
             assert n > 0, n
             outs.append(o[:n])
         assert np.array_equal(outs[0], outs[1]), (w, h, fmt)
+
+
+def test_nothing_the_reference_headers_declare_is_missing():
+    """Every function the reference's public headers declare (dsv.h, dsv_encoder.h, dsv_decoder.h, util.h) is in
+    include/exports.txt -- a caller of any of them links."""
+    if not os.path.exists("/root/reference/dsv.h"):
+        pytest.skip("reference tree not present")
+    declared = set()
+    for h in ("dsv.h", "dsv_encoder.h", "dsv_decoder.h", "util.h"):
+        declared |= _declared_functions(os.path.join("/root/reference", h))
+    assert len(declared) >= 36
+    listed = set(open(os.path.join(L.ROOT, "include", "exports.txt")).read().split())
+    assert declared <= listed, sorted(declared - listed)
