@@ -11,8 +11,14 @@ A "step" = encode all B*12 pictures to .dsv streams, then decode those streams b
           pictures left on the device).  Bitstreams still come back to the host: that IS the encoder's product.
   e2e     the same through the same public call with HOST buffers (pinned): pictures H2D, streams D2H,
           streams H2D, pictures D2H all inside the timed region.
-  roofline  the subband-transform tile kernels (the path's dominant HBM movers), timed live with CUDA
-          events on the engine's stream inside the timed region: algorithmic bytes / duration.
+  roofline  the kernel with the largest total time in the device-resident timed region; `kernels` lists every
+          kernel >= 1 % of the step.  Every launch is bracketed by CUDA events on the engine's stream
+          (csrc/ktime.cu): algorithmic bytes / duration.  `traffic` comes from profiles/traffic.json (parsed
+          from a committed ncu --set full capture) or is null.
+  encode_/decode_pictures_per_s  the two directions of the device-resident step separately (N=1).
+  verified  the cpu_baseline leg's reference streams / pictures are compared with the GPU's for the same
+          sequences; on a mismatch no line is printed.
+  --config 2|3|4|5  BASELINE.json configs (5 = headline metric, default).
   cpu_baseline  the UNMODIFIED reference (oracle/_ref/libdsv1ref.so, built from /root/reference by
           oracle/Makefile) single-threaded on a bounded sample of the same workload, rank 0, N=1.
 
@@ -34,13 +40,36 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 W, H, FMT, GOP, QP, NFR = 1920, 1080, "420", 12, 85, 12
 METRIC = "1080p 4:2:0 gop12 qp85 encode+decode pictures/s (bit-exact DSV1)"
+# BASELINE.json configs[1..4] (index = --config).  5 is the headline (the metric is quoted on it); 2-4 are the
+# reference's single-sequence operating points (dsv_main.c:463-489) run as a batch of independent sequences.
+CONFIGS = {
+    2: dict(w=1920, h=1080, fmt="420", gop=0, nfr=12, batch=64, tag="BASELINE config 2, -gop0 intra-only",
+            metric="1080p 4:2:0 gop0 (intra-only) qp85 encode+decode pictures/s (bit-exact DSV1)"),
+    3: dict(w=1920, h=1080, fmt="420", gop=12, nfr=24, batch=32, tag="BASELINE config 3, -gop12 inter, 24-picture sequences",
+            metric="1080p 4:2:0 gop12 qp85 encode+decode pictures/s, 24-picture sequences (bit-exact DSV1)"),
+    4: dict(w=3840, h=2160, fmt="444", gop=12, nfr=6, batch=16, tag="BASELINE config 4, 2160p 4:4:4 -gop12",
+            metric="2160p 4:4:4 gop12 qp85 encode+decode pictures/s (bit-exact DSV1)"),
+    5: dict(w=1920, h=1080, fmt="420", gop=12, nfr=12, batch=64, tag="BASELINE config 5, sharded by sequence",
+            metric=METRIC),
+}
 
 
-def workload(batch):
+def select_config(args):
+    global W, H, FMT, GOP, NFR, METRIC
+    c = CONFIGS[args.config]
+    W, H, FMT, GOP, NFR, METRIC = c["w"], c["h"], c["fmt"], c["gop"], c["nfr"], c["metric"]
+    if args.batch is None:
+        args.batch = c["batch"]
+    args.tag = c["tag"]
+
+
+def workload(batch, tag="BASELINE config 5, sharded by sequence"):
+    import dsvlibs as L
+    fb = L.frame_bytes(W, H, L.SUBSAMP[FMT])
     return {"workload": "synthetic %dx%d %s, %d closed-GOP sequences x %d pictures per GPU, -gop%d -qp%d CRF, "
-                        "encode then decode (BASELINE config 5, sharded by sequence)" % (W, H, FMT, batch, NFR, GOP, QP),
+                        "encode then decode (%s)" % (W, H, FMT, batch, NFR, GOP, QP, tag),
             "batch_sequences_per_gpu": batch, "pictures_per_sequence": NFR,
-            "l2": "inputs larger than L2 (%.0f MB of pictures per step per GPU)" % (batch * NFR * W * H * 1.5 / 1e6)}
+            "l2": "inputs larger than L2 (%.0f MB of pictures per step per GPU)" % (batch * NFR * fb / 1e6)}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -59,14 +88,14 @@ def _ref_init(seed_base):
     _REF_STATE["cfg"] = L.make_cfg(W, H, FMT, gop=GOP, qp=QP)
 
 
-def _ref_codec(yuv):
+def _ref_codec(yuv, keep=False):
     import dsvlibs as L
     ref = _REF_STATE.get("ref") or L.ref()
     cfg = _REF_STATE.get("cfg") or L.make_cfg(W, H, FMT, gop=GOP, qp=QP)
     stream, _, e = ref.encode_sequence(cfg, yuv, NFR)
-    nf, _, _, d = ref.decode_stream(stream, W, H, L.SUBSAMP[FMT], NFR)
+    nf, dec, _, d = ref.decode_stream(stream, W, H, L.SUBSAMP[FMT], NFR)
     assert nf == NFR
-    return e, d
+    return (e, d, stream, dec) if keep else (e, d)
 
 
 def _ref_step(_):
@@ -86,10 +115,11 @@ def run_reference(args):
     pool = mp.get_context("fork").Pool(procs, initializer=_ref_init, initargs=(1000,))
     pool.map(_ref_step, range(procs))  # every worker is up and has its input
     times = []
-    pics = procs * NFR
+    nseq = args.batch  # the product arm's step: `batch` sequences, spread over the host cores
+    pics = nseq * NFR
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        pool.map(_ref_step, range(procs), chunksize=1)
+        pool.map(_ref_step, range(nseq), chunksize=1)
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
@@ -99,11 +129,11 @@ def run_reference(args):
     line = {"metric": METRIC, "value": value, "unit": "pictures/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic", "impl": "reference",
-            "config": workload(args.batch),
+            "config": workload(args.batch, args.tag),
             "cpu_baseline": {"value": value, "unit": "pictures/s", "cores": procs, "kind": "reference",
-                             "sample": "%d processes (one per host core; the reference is single-threaded and not "
-                                       "re-entrant) x 1 sequence x %d pictures per step, encode then decode, inputs "
-                                       "preloaded in memory" % (procs, NFR)},
+                             "sample": "%d sequences x %d pictures per step, encode then decode, spread over %d processes "
+                                       "(one per host core; the reference is single-threaded and not re-entrant), each "
+                                       "process re-coding its own preloaded sequence" % (nseq, NFR, procs)},
             "e2e": {"value": value, "unit": "pictures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -112,16 +142,19 @@ def cpu_baseline_single(h_yuv_np, seq_bytes):
     """Reference, 1 thread, bounded sample of the SAME inputs: time inside dsv_enc / dsv_dec only."""
     import dsvlibs as L
     if not L.have_ref():
-        return None
-    nseq = min(6, len(h_yuv_np) // seq_bytes)
+        return None, []
+    nseq = min(max(1, int(6 * (1920 * 1080 * 1.5 * 12) / seq_bytes)), 6, len(h_yuv_np) // seq_bytes)
     e = d = 0.0
+    kept = []
     for s in range(nseq):
-        es, ds = _ref_codec(h_yuv_np[s * seq_bytes:(s + 1) * seq_bytes])
+        es, ds, stream, dec = _ref_codec(h_yuv_np[s * seq_bytes:(s + 1) * seq_bytes], keep=True)
         e += es
         d += ds
+        kept.append((stream, dec))
     return {"value": nseq * NFR / (e + d), "unit": "pictures/s", "cores": 1, "kind": "reference",
+            "encode_pictures_per_s": nseq * NFR / e, "decode_pictures_per_s": nseq * NFR / d,
             "sample": "%d of the step's sequences x %d pictures, 1 thread, time inside dsv_enc+dsv_dec "
-                      "(encode %.2f pictures/s, decode %.2f pictures/s)" % (nseq, NFR, nseq * NFR / e, nseq * NFR / d)}
+                      "(encode %.2f pictures/s, decode %.2f pictures/s)" % (nseq, NFR, nseq * NFR / e, nseq * NFR / d)}, kept
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -212,6 +245,52 @@ def bind_near_gpu(torch, local, world):
 
 
 
+# kernel name -> (bound, algorithmic bytes per PICTURE as f(geometry) or None, which pictures pass through it)
+def kernel_models(L):
+    sub = L.SUBSAMP[FMT]
+    fb = L.frame_bytes(W, H, sub)
+    planes, coefs = L.plane_dims(W, H, sub), L.coef_dims(W, H, sub)
+    sbt = sum(pw * ph for pw, ph in planes) + 4 * sum(cw * ch for cw, ch in coefs)
+    coef4 = 4 * sum(cw * ch for cw, ch in coefs)
+    return {
+        "sbt_fwd_tile_kernel": ("hbm", sbt), "sbt_inv_tile_kernel": ("hbm", sbt), "bmc_kernel": ("hbm", None),
+        "hzcc_scan_kernel": ("hbm", coef4), "hzcc_pack_kernel": ("hbm", coef4), "zero_kernel": ("hbm", None),
+        "ingest_kernel": ("hbm", 2 * fb), "pack_kernel": ("hbm", 2 * fb), "down2_kernel": ("hbm", None),
+        "hme_l0_kernel": ("issue", 2 * fb), "hme_level_kernel": ("issue", None), "hme_neigh_kernel": ("latency", None),
+    }
+
+
+def kernel_table(L, B, steps, ms_dev, peak, es, ds, ekt, dkt):
+    """every kernel that takes >= 1 % of the device-resident step: live CUDA-event time (events around each launch on
+    the engine's stream), launches, share of the step, and for the streaming kernels algorithmic GB/s vs the measured peak"""
+    models = kernel_models(L)
+    exact = {("enc", "sbt_fwd_tile_kernel"): es["sbt_fwd_bytes"], ("enc", "sbt_inv_tile_kernel"): es["sbt_inv_bytes"],
+             ("dec", "sbt_inv_tile_kernel"): ds["sbt_inv_bytes"], ("enc", "bmc_kernel"): es["bmc_bytes"], ("dec", "bmc_kernel"): ds["bmc_bytes"]}
+    pictures = B * NFR * steps
+    out = {}
+    for side, kt in (("enc", ekt), ("dec", dkt)):
+        for name, v in kt.items():
+            if v["ms"] < 0.01 * ms_dev:
+                continue
+            bound, per_pic = models.get(name, ("latency", None))
+            by = exact.get((side, name), per_pic * pictures if per_pic else None)
+            row = {"ms_total": v["ms"], "launches": v["launches"], "ms_per_launch": v["ms"] / v["launches"],
+                   "share_of_step": v["ms"] / ms_dev, "bound": bound}
+            if by:
+                row.update(bytes_per_launch=by / v["launches"], achieved_gbs=by / v["ms"] / 1e6, frac=by / v["ms"] / 1e6 / peak)
+            out["%s(%s)" % (name, side)] = row
+    return out
+
+
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, parsed by tools/ncu_traffic.py from an `ncu --set full`
+    capture of this workload and committed as profiles/traffic.json; absent -> no traffic claim"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
+
+
 def run_product(args):
     import numpy as np
     import torch
@@ -243,7 +322,7 @@ def run_product(args):
         lib.dsvb_synth_device(W, H, sub, 0, NFR, 100 + rank * B + s, 0, C.c_void_p(d_yuv.data_ptr() + s * seq_bytes), local)
     h_yuv = torch.empty(B * seq_bytes, dtype=torch.uint8).pin_memory()
     h_yuv.copy_(d_yuv)
-    cap = 8 << 20
+    cap = max(8 << 20, (seq_bytes // 3 + 4095) & ~4095)
     h_streams = torch.zeros(B * cap, dtype=torch.uint8).pin_memory()
     d_streams = torch.zeros(B * cap, dtype=torch.uint8, device="cuda")
     d_out = torch.empty(B * seq_bytes, dtype=torch.uint8, device="cuda")
@@ -255,16 +334,23 @@ def run_product(args):
     sdp = [d_streams.data_ptr() + s * cap for s in range(B)]
     caps = [cap] * B
 
+    split = {"enc_s": 0.0, "dec_s": 0.0}
+
     def step(host):
+        t0 = time.perf_counter()
         if host:
             rc, lens = enc.encode_ptrs([h_yuv.data_ptr() + s * seq_bytes for s in range(B)], NFR, 0, sp, caps)
             assert rc == 0
+            t1 = time.perf_counter()
             rc, fr = dec.decode_ptrs(sp, None, lens, [h_out.data_ptr() + s * seq_bytes for s in range(B)], [seq_bytes] * B, 0)
         else:
             rc, lens = enc.encode_ptrs([d_yuv.data_ptr() + s * seq_bytes for s in range(B)], NFR, 1, sp, caps)
             assert rc == 0
+            t1 = time.perf_counter()
             rc, fr = dec.decode_ptrs(sp, sdp, lens, [d_out.data_ptr() + s * seq_bytes for s in range(B)], [seq_bytes] * B, 1)
         assert rc == 0 and all(f == NFR for f in fr), (rc, fr)
+        split["enc_s"] += t1 - t0   # both calls return when their products are complete (streams on the host /
+        split["dec_s"] += time.perf_counter() - t1   # pictures at their destination)
         return lens
 
     # end-to-end arm: steps are software-pipelined two deep, the way a transcoding service runs: one host thread
@@ -335,6 +421,9 @@ def run_product(args):
             lens = step(host)
         enc.stats(reset=True)
         dec.stats(reset=True)
+        enc.kernel_times(reset=True)
+        dec.kernel_times(reset=True)
+        split["enc_s"] = split["dec_s"] = 0.0
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -349,7 +438,7 @@ def run_product(args):
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), lens, enc.stats(), dec.stats()
+        return float(t.item()), lens, enc.stats(), dec.stats(), enc.kernel_times(), dec.kernel_times(), dict(split)
 
     # first pass through the host arm; its (deterministic) streams are then parked in HBM for the decoder's
     # resident-input arm
@@ -357,9 +446,9 @@ def run_product(args):
     d_streams.copy_(h_streams, non_blocking=False)
     torch.cuda.synchronize()
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_dev, lens, es, ds = timed(False, args.steps, args.warmup)
+    ms_dev, lens, es, ds, ekt, dkt, split_dev = timed(False, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
-    ms_e2e, lens_h, es_h, ds_h = timed(True, args.steps, args.warmup)
+    ms_e2e, lens_h, es_h, ds_h, _, _, _ = timed(True, args.steps, args.warmup)
 
     pics = B * NFR * world
     value = pics * args.steps / (ms_dev / 1e3)
@@ -372,51 +461,53 @@ def run_product(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        kern = {}
-        for name, ms, n, by in (("sbt_fwd_tile_kernel", es["sbt_fwd_ms"], es["sbt_fwd_launches"], es["sbt_fwd_bytes"]),
-                                ("sbt_inv_tile_kernel(enc)", es["sbt_inv_ms"], es["sbt_inv_launches"], es["sbt_inv_bytes"]),
-                                ("sbt_inv_tile_kernel(dec)", ds["sbt_inv_ms"], ds["sbt_inv_launches"], ds["sbt_inv_bytes"]),
-                                ("bmc_kernel(enc)", es["bmc_ms"], es["bmc_launches"], es["bmc_bytes"]),
-                                ("bmc_kernel(dec)", ds["bmc_ms"], ds["bmc_launches"], ds["bmc_bytes"])):
-            if n > 0 and ms > 0:
-                kern[name] = {"ms_total": ms, "launches": n, "ms_per_launch": ms / n, "bytes_per_launch": by / n,
-                              "achieved_gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peak,
-                              "share_of_step": ms / ms_dev}
-        sbt = {k: v for k, v in kern.items() if k.startswith("sbt_")}
-        dom = max(sbt.items(), key=lambda kv: kv[1]["ms_total"]) if sbt else (None, None)
-        # DRAM traffic per launch from the committed `ncu --set full` captures of this very workload: forward
-        # (profiles/r1_ncu_sbt_tile_kernels_final_b32.txt, 32 lanes = 497.7 MB algorithmic) dram__bytes_read+write =
-        # 446.9 MB; inverse (profiles/r1_ncu_sbt_tile_kernels_final_b64.txt, 64 lanes = 995.3 MB algorithmic) 797.5 MB
-        # read + 185.0 MB written = 982.5 MB; scaled to this launch's plane count.  Both are BELOW the algorithmic
-        # bytes (L2 absorbs part of the write-back): no wasted re-reads.
-        traffic_ratio = {"sbt_fwd_tile_kernel": 446.9 / 497.7, "sbt_inv_tile_kernel(enc)": 982.5 / 995.3,
-                         "sbt_inv_tile_kernel(dec)": 982.5 / 995.3}
-        for name, kv in kern.items():
-            if name in traffic_ratio:
-                kv["traffic_bytes_per_launch"] = kv["bytes_per_launch"] * traffic_ratio[name]
+        kern = kernel_table(L, B, args.steps, ms_dev, peak, es, ds, ekt, dkt)
+        dom = max(kern.items(), key=lambda kv: kv[1]["ms_total"]) if kern else (None, None)
+        traffic = measured_traffic()
         roofline = None
         if dom[0]:
-            roofline = {"kernel": dom[0], "bound": "hbm", "achieved": dom[1]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                        "frac": dom[1]["frac"], "traffic": dom[1]["traffic_bytes_per_launch"], "peak_source": peak_src,
-                        "traffic_source": "ncu --set full capture of the same kernel and workload, scaled by planes per launch "
-                                          "(profiles/r1_ncu_sbt_tile_kernels_final_b64.txt; forward: ..._final_b32.txt)",
-                        "algorithmic_bytes_per_plane": "w*h (u8 samples) + 4*cw*ch (int32 coefficients); the encoder's inverse of a P picture "
-                                                       "also reads the prediction it adds on the way out (+ w*h)",
-                        "all_sbt_bmc_kernels": {k: round(v["frac"], 3) for k, v in kern.items()}}
+            k = dom[1]
+            tr = traffic.get(dom[0].split("(")[0])
+            roofline = {"kernel": dom[0], "bound": "hbm", "limited_by": k["bound"],
+                        "achieved": k.get("achieved_gbs"), "peak": peak, "unit": "GB/s", "frac": k.get("frac"),
+                        "traffic": (tr["dram_bytes_per_launch"] if tr else None), "traffic_source": (tr["source"] if tr else None),
+                        "peak_source": peak_src,
+                        "algorithmic_bytes": "per picture: SBT w*h (u8) + 4*cw*ch (int32) per plane (+ w*h prediction read in the encoder's "
+                                             "inverse of a P picture); BMC 4 B (encoder) / 3 B (decoder) per sample; HZCC scan and pack "
+                                             "4*cw*ch each; HME level 0: source + reference luma and chroma once (2 x frame bytes)",
+                        "north_star_kernels": {n: round(v["frac"], 3) for n, v in kern.items()
+                                               if v.get("frac") is not None and (n.startswith("sbt_") or n.startswith("bmc_"))}}
         stream_bytes = sum(lens_h)
         line = {"metric": METRIC, "value": value, "unit": "pictures/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
-                "config": dict(workload(B), e2e_schedule="steps pipelined two deep: decode of step k overlaps encode of step k+1 "
-                                                         "(two host threads, double-buffered streams, full-duplex PCIe)"
-                               if args.e2e_pipeline else "encode then decode, one step at a time"),
+                "config": workload(B, args.tag),
+                "encode_pictures_per_s": pics * args.steps / split_dev["enc_s"] if world == 1 else None,
+                "decode_pictures_per_s": pics * args.steps / split_dev["dec_s"] if world == 1 else None,
                 "e2e": {"value": e2e, "unit": "pictures/s", "ms_per_step": ms_e2e / args.steps,
-                        "h2d_bytes_per_step": B * seq_bytes + stream_bytes, "d2h_bytes_per_step": B * seq_bytes + stream_bytes},
+                        "h2d_bytes_per_step": B * seq_bytes + stream_bytes, "d2h_bytes_per_step": B * seq_bytes + stream_bytes,
+                        "schedule": "steps pipelined two deep: decode of step k overlaps encode of step k+1 (two host threads, "
+                                    "double-buffered streams, full-duplex PCIe)" if args.e2e_pipeline
+                                    else "encode then decode, one step at a time"},
                 "gpu_launches": int(es["kernel_launches"] + ds["kernel_launches"]),
                 "roofline": roofline, "kernels": kern, "clocks": clocks, "host_placement": pin_note,
                 "stream_bytes_per_step": stream_bytes}
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_single(h_yuv.numpy(), seq_bytes)
+            # the reference codes a sample of the very sequences the timed steps just processed; its streams and
+            # decoded pictures must equal the bytes the GPU produced for them in the last timed host-buffer step
+            line["cpu_baseline"], kept = cpu_baseline_single(h_yuv.numpy(), seq_bytes)
+            last = h_streams2 if (args.e2e_pipeline and args.steps % 2 == 0) else h_streams
+            hs_np, ho_np = last.numpy(), h_out.numpy()
+            for s_i, (r_stream, r_dec) in enumerate(kept):
+                g_stream = bytes(hs_np[s_i * cap:s_i * cap + lens_h[s_i]])
+                if g_stream != r_stream:
+                    raise SystemExit("bench.py: stream of sequence %d differs from the reference (%d vs %d bytes) -- no number printed"
+                                     % (s_i, len(g_stream), len(r_stream)))
+                if not np.array_equal(ho_np[s_i * seq_bytes:(s_i + 1) * seq_bytes], r_dec):
+                    raise SystemExit("bench.py: decoded pictures of sequence %d differ from the reference -- no number printed" % s_i)
+            line["verified"] = {"sequences": len(kept), "pictures": len(kept) * NFR,
+                                "what": "streams byte-for-byte and decoded pictures sample-for-sample equal to the unmodified reference "
+                                        "for the first %d sequences of the last timed host-buffer step" % len(kept)}
         print(json.dumps(line))
     enc.close()
     dec.close()
@@ -430,11 +521,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="sequences per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="sequences per GPU per step (default: the config's)")
+    ap.add_argument("--config", type=int, default=5, choices=sorted(CONFIGS), help="BASELINE.json configs index (5 = headline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e-pipeline", dest="e2e_pipeline", action="store_false",
                     help="e2e arm: strictly one step at a time instead of decode(k) overlapping encode(k+1)")
     args = ap.parse_args()
+    select_config(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -1,262 +1,407 @@
 /*
  * bmc.cu -- half-pel block motion compensation, fused with residual formation (encoder) or
  * reconstruction (decoder).  Replaces compensate / hpelL / hpel / avgval / cpyzero / subf / addf /
- * dsv_sub_pred / dsv_add_pred / dsv_frame_add (bmc.c:29-346).
+ * dsv_sub_pred / dsv_add_pred (bmc.c:29-346).
  *
- *   bmc_kernel        one CTA per motion block and plane (grid = nbh x nbv x 3 planes x lanes; one BmcArgs per lane).  Inter blocks:
- *                     luma 4-tap (-1,9,9,-1) half-pel filter, the HV phase through an int16
- *                     H-filtered strip staged in shared memory (bmc.c:124-174); chroma bilinear
- *                     (bmc.c:58-110).  Intra blocks / quadrants: integer mean of the co-located
- *                     reference (sub)block (bmc.c:256-298), one block-wide reduction.
- *                     The prediction never makes a round trip through HBM on the decoder side
- *                     (mode 2: io = clamp(pred + io - 128)); the encoder keeps it (mode 1) because the
- *                     closed-loop reconstruction adds it back after the inverse transform.
- *                     The closed-loop add-back itself is recon_kernel in frame_ops.cu.
+ * Streaming formulation: the unit of work is a strip of 16 samples x R rows of ONE motion block (R = 8 luma,
+ * 4 chroma), one strip per thread, the strips of all blocks / planes / lanes flattened into one grid.  A thread
+ * keeps everything in registers -- no shared memory, no barriers:
+ *
+ *   luma    every inter block goes through the SAME separable 4-tap path whatever its half-pel phase: the phase
+ *           only selects the tap words, (-1,9,9,-1) or (0,16,0,0), per direction.  With 16 = the taps' DC gain
+ *           the four cases of hpelL (bmc.c:124-174) are reproduced exactly:
+ *             (16 (9(b+c)-(a+d)) + 128) >> 8 == (9(b+c)-(a+d) + 8) >> 4   and   (256 p + 128) >> 8 == p.
+ *           So warps never diverge on the phase.  The H pass is one dp4a per sample on funnel-shifted words of the
+ *           row; rows slide through a register window of vertically paired 16-bit H results, the V pass is two
+ *           dp2a per sample.
+ *   chroma  bilinear (bmc.c:58-110) as one dp4a per sample with phase-selected weights summing to 4:
+ *             (4a + 2) >> 2 == a,  (2a + 2b + 2) >> 2 == (a + b + 1) >> 1,  (a + b + c + d + 2) >> 2.
+ *   intra   (bmc.c:255-298) blocks take the co-located reference through the same path (zero vector) and
+ *           overwrite the flagged quadrants with the block / quadrant means that bmc_means_kernel (one warp per
+ *           intra block, a launch that exits at once for inter blocks) left in a small table.
+ *
+ * The prediction never makes a round trip through HBM on the decoder side (mode 2: io = clamp(pred + io - 128));
+ * the encoder keeps it (mode 1) because the closed-loop reconstruction adds it back in the inverse transform's
+ * store (sbt_inv.cu).  Plane rows are 16-byte aligned, so whole strips move as 16-byte loads / stores; strips cut
+ * by the picture edge or by block widths that are not multiples of 16 fall back to words / bytes.
  *
  * Reads outside the picture go through the 64-sample replicated border exactly like the reference
  * (position clamp bmc.c:221-249); filter taps that step one sample past the border see the same
- * neighbouring bytes because DevFrame keeps the reference's strides and plane order.
+ * neighbouring bytes because DevFrame keeps the reference's strides and plane order.  Taps with weight zero
+ * read (and ignore) bytes the reference does not touch; they stay inside the frame allocation's guard bands.
  */
 #include "motion.cuh"
 
 namespace dsv {
 
 #define BMC_THREADS 256
+#define BMC_RL 8 /* luma rows per strip */
+#define BMC_RC 4 /* chroma rows per strip */
 
-
-
-DSV_D unsigned block_sum_u32(unsigned v, unsigned *scratch /* >= 33 */)
+/* c + sum of the four unsigned bytes of w times the four signed bytes of taps */
+DSV_HD int dp4a_us(unsigned w, unsigned taps, int c)
 {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    v = __reduce_add_sync(0xffffffffu, v);
-    __syncthreads();
-    if (lane == 0) {
-        scratch[wid] = v;
+#if defined(__CUDA_ARCH__)
+    int r;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(taps), "r"(c));
+    return r;
+#else
+    int r = c;
+    for (int i = 0; i < 4; i++) {
+        r += (int) ((w >> (8 * i)) & 0xffu) * (int) (int8_t) ((taps >> (8 * i)) & 0xffu);
     }
-    __syncthreads();
-    unsigned t = 0;
-    for (int i = 0; i < nw; i++) {
-        t += scratch[i];
-    }
-    return t;
+    return r;
+#endif
 }
 
-/* combine 4 predicted samples (packed, sample 0 in the lowest byte) with the current word and store (prediction
- * word kept when asked) */
-DSV_D void bmc_store4(const BmcPlane &P, int mode, int gx, int gy, int nvalid, bool vec, unsigned pw)
+/* out = clamp(in -/+ pred +/- 128) on four packed samples */
+DSV_D unsigned bmc_combine4(unsigned cur, unsigned pw, int mode)
+{
+    const int p0 = byte_of(pw, 0), p1 = byte_of(pw, 1), p2 = byte_of(pw, 2), p3 = byte_of(pw, 3);
+    if (mode == 1) {
+        return pack_u8x4(byte_of(cur, 0) - p0 + 128, byte_of(cur, 1) - p1 + 128, byte_of(cur, 2) - p2 + 128, byte_of(cur, 3) - p3 + 128);
+    }
+    return pack_u8x4(byte_of(cur, 0) + p0 - 128, byte_of(cur, 1) + p1 - 128, byte_of(cur, 2) + p2 - 128, byte_of(cur, 3) + p3 - 128);
+}
+
+/* one row of a strip: 16 predicted samples in pw[4] (sample 0 in the lowest byte of pw[0]); n = valid samples */
+DSV_D void bmc_store_row(const BmcPlane &P, int mode, int gx, int gy, int n, bool vec16, const unsigned pw[4])
 {
     const size_t io = (size_t) gy * P.istride + gx, oo = (size_t) gy * P.ostride + gx;
-    const int p0 = byte_of(pw, 0), p1 = byte_of(pw, 1), p2 = byte_of(pw, 2), p3 = byte_of(pw, 3);
-    if (vec && nvalid == 4) {
-        const unsigned cur = *reinterpret_cast<const unsigned *>(P.in + io);
-        unsigned out;
-        if (mode == 1) {
-            out = pack_u8x4(byte_of(cur, 0) - p0 + 128, byte_of(cur, 1) - p1 + 128, byte_of(cur, 2) - p2 + 128, byte_of(cur, 3) - p3 + 128);
-        } else {
-            out = pack_u8x4(byte_of(cur, 0) + p0 - 128, byte_of(cur, 1) + p1 - 128, byte_of(cur, 2) + p2 - 128, byte_of(cur, 3) + p3 - 128);
-        }
-        *reinterpret_cast<unsigned *>(P.out + oo) = out;
+    if (vec16) { /* n == 16 and every row of the three frames 16-byte aligned at gx */
+        const uint4 cur = *reinterpret_cast<const uint4 *>(P.in + io);
+        uint4 o;
+        o.x = bmc_combine4(cur.x, pw[0], mode);
+        o.y = bmc_combine4(cur.y, pw[1], mode);
+        o.z = bmc_combine4(cur.z, pw[2], mode);
+        o.w = bmc_combine4(cur.w, pw[3], mode);
+        *reinterpret_cast<uint4 *>(P.out + oo) = o;
         if (P.pred) {
-            *reinterpret_cast<unsigned *>(P.pred + (size_t) gy * P.pstride + gx) = pw;
+            *reinterpret_cast<uint4 *>(P.pred + (size_t) gy * P.pstride + gx) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
         }
         return;
     }
-    const int pv[4] = {p0, p1, p2, p3};
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-        if (e < nvalid) {
-            const int cur = P.in[io + e];
-            P.out[oo + e] = mode == 1 ? clamp_u8(cur - pv[e] + 128) : clamp_u8(pv[e] + cur - 128);
-            if (P.pred) {
-                P.pred[(size_t) gy * P.pstride + gx + e] = (uint8_t) pv[e];
+    for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            if (4 * k + e < n) {
+                const int pv = byte_of(pw[k], e);
+                const int cur = P.in[io + 4 * k + e];
+                P.out[oo + 4 * k + e] = mode == 1 ? clamp_u8(cur - pv + 128) : clamp_u8(pv + cur - 128);
+                if (P.pred) {
+                    P.pred[(size_t) gy * P.pstride + gx + 4 * k + e] = (uint8_t) pv;
+                }
             }
         }
     }
 }
 
-/* one motion block of one plane; a thread owns 4 horizontally adjacent samples (frames keep rows 4-byte aligned
- * at multiples of 4) */
-DSV_D void bmc_block_plane(const BmcArgs &a, const int c, int16_t *hbuf, unsigned *scratch, int *s_avg)
+/* intra blocks (bmc.c:255-298): the flagged quadrants become their mean, the others keep the co-located reference
+ * already in pw; odd edge blocks: the quadrants do not cover the last row / column (zeroed frame in the reference) */
+DSV_D void bmc_intra_row(unsigned pw[4], const DevMV &mv, unsigned means, int lx, int ly, int cw, int ch)
+{
+    const bool whole = mv.submask == 15;
+    const int sbw = cw / 2, sbh = ch / 2;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        unsigned w = 0;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int x = lx + 4 * k + e;
+            unsigned v;
+            if (whole) {
+                v = means & 0xffu;
+            } else if (x >= 2 * sbw || ly >= 2 * sbh) {
+                v = 0;
+            } else {
+                const int q = (x >= sbw ? 1 : 0) | (ly >= sbh ? 2 : 0);
+                v = (mv.submask & (1 << q)) ? ((means >> (8 * q)) & 0xffu) : (unsigned) byte_of(pw[k], e);
+            }
+            w |= v << (8 * e);
+        }
+        pw[k] = w;
+    }
+}
+
+struct BmcStrip {
+    int b;          /* block index */
+    int x, y;       /* block origin in the plane */
+    int cw, ch;     /* clipped block size */
+    int lx, ly;     /* strip origin inside the block */
+    int n, rows;    /* valid samples per row / rows */
+    int px, py;     /* clamped integer reference position of the block */
+    int xh, yh;     /* half-pel flags */
+    bool intra, vec16;
+    DevMV mv;
+};
+
+template <int R> DSV_D bool bmc_strip_setup(const BmcArgs &a, const int c, const int u, BmcStrip &s)
 {
     const BmcPlane &P = a.pl[c];
     const int sh = c ? a.hs : 0, sv = c ? a.vs : 0;
     const int bw = a.blk_w >> sh, bh = a.blk_h >> sv;
-    const int i = blockIdx.x, j = blockIdx.y;
-    const int x = i * bw, y = j * bh;
-    const int cw = (x + bw >= P.w) ? P.w - x : bw;
-    const int ch = (y + bh >= P.h) ? P.h - y : bh;
-    if (cw <= 0 || ch <= 0) {
-        return;
+    const int segs = (bw + 15) >> 4, rgs = (bh + R - 1) / R, upb = segs * rgs;
+    if (u >= upb * a.nbh * a.nbv) {
+        return false;
     }
-    const DevMV mv = a.mv[j * a.nbh + i];
-    const int tid = threadIdx.x;
-    const int mode = a.mode;
-    const int words = (cw + 3) >> 2;
-    const int wsh = words > 1 ? 32 - __clz(words - 1) : 0; /* ceil(log2(words)) */
-    const int wmask = (1 << wsh) - 1;
-    const bool walign = ((x & 3) == 0) && ((P.istride | P.ostride | P.pstride) & 3) == 0 &&
-                        ((reinterpret_cast<uintptr_t>(P.in) | reinterpret_cast<uintptr_t>(P.out) | reinterpret_cast<uintptr_t>(P.pred)) & 3) == 0;
-    if (mode == 1 && x + cw == P.w) {
-        /* the forward transform of a plane with odd width reads one column past it (sbt.c:583-591); in the
-         * reference that column of the residual frame still holds the replicated INPUT border
-         * (dsv_encoder.c:657-659: xf = copy of the padded input, then only w x h is replaced) */
-        for (int k = tid; k < ch; k += BMC_THREADS) {
-            P.out[(size_t) (y + k) * P.ostride + P.w] = P.in[(size_t) (y + k) * P.istride + P.w];
-        }
+    s.b = u / upb;
+    const int r = u - s.b * upb;
+    const int rg = r / segs, seg = r - rg * segs;
+    const int j = s.b / a.nbh, i = s.b - j * a.nbh;
+    s.x = i * bw;
+    s.y = j * bh;
+    s.cw = (s.x + bw >= P.w) ? P.w - s.x : bw;
+    s.ch = (s.y + bh >= P.h) ? P.h - s.y : bh;
+    s.lx = 16 * seg;
+    s.ly = R * rg;
+    if (s.lx >= s.cw || s.ly >= s.ch) {
+        return false;
     }
-
-    if (mv.mode == 0) { /* DSV_MODE_INTER, bmc.c:240-254 */
-        const int dx = mv.x >> sh, dy = mv.y >> sv;
-        const int limx = (P.w - bw) + DSV_BORDER - 1, limy = (P.h - bh) + DSV_BORDER - 1;
-        const int px = iclamp(x + (dx >> 1), -DSV_BORDER, limx);
-        const int py = iclamp(y + (dy >> 1), -DSV_BORDER, limy);
-        const int phase = ((dx & 1) << 1) | (dy & 1);
-        const uint8_t *r0 = P.ref + (ptrdiff_t) py * P.rstride + px;
-        const int rs = P.rstride;
-        const int hstride = words * 4; /* int16 per staged row */
-        if (c == 0 && phase == 3) {
-            for (int k = tid; k < ((ch + 3) << wsh); k += BMC_THREADS) {
-                const int ly = k >> wsh, wx = k & wmask;
-                if (wx >= words) {
-                    continue;
-                }
-                /* bytes p[-1..6] of the row: three aligned words, shifted once; the taps of sample e are the four
-                 * bytes starting at e */
-                const uint8_t *p = r0 + (ptrdiff_t) (ly - 1) * rs + 4 * wx - 1;
-                const unsigned *q = reinterpret_cast<const unsigned *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t) 3);
-                const unsigned bsh = ((unsigned) reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
-                const unsigned q0 = q[0], q1 = q[1], q2 = q[2];
-                const unsigned wa = __funnelshift_r(q0, q1, bsh), wb = __funnelshift_r(q1, q2, bsh);
-                const int h0 = hp_taps_u8x4(wa), h1 = hp_taps_u8x4(__funnelshift_r(wa, wb, 8));
-                const int h2 = hp_taps_u8x4(__funnelshift_r(wa, wb, 16)), h3 = hp_taps_u8x4(__funnelshift_r(wa, wb, 24));
-                *reinterpret_cast<uint2 *>(hbuf + ly * hstride + 4 * wx) =
-                    make_uint2(__byte_perm((unsigned) h0, (unsigned) h1, 0x5410), __byte_perm((unsigned) h2, (unsigned) h3, 0x5410));
-            }
-            __syncthreads();
-        }
-        for (int k = tid; k < (ch << wsh); k += BMC_THREADS) {
-            const int ly = k >> wsh, wx = k & wmask;
-            if (wx >= words) {
-                continue;
-            }
-            const int lx = 4 * wx;
-            const uint8_t *p = r0 + (ptrdiff_t) ly * rs + lx;
-            unsigned pw; /* the four predicted samples, saturated to 8 bits */
-            if (phase == 0) {
-                pw = ld4u(p);
-            } else if (c == 0) {
-                if (phase == 1) {
-                    int v0, v1, v2, v3;
-                    const unsigned wa = ld4u(p - rs), wb = ld4u(p), wc = ld4u(p + rs), wd = ld4u(p + 2 * rs);
-                    /* 4x4 byte transpose: column e of the four rows becomes one word */
-                    const unsigned ab0 = __byte_perm(wa, wb, 0x5140), ab1 = __byte_perm(wa, wb, 0x7362);
-                    const unsigned cd0 = __byte_perm(wc, wd, 0x5140), cd1 = __byte_perm(wc, wd, 0x7362);
-                    v0 = (hp_taps_u8x4(__byte_perm(ab0, cd0, 0x5410)) + 8) >> 4;
-                    v1 = (hp_taps_u8x4(__byte_perm(ab0, cd0, 0x7632)) + 8) >> 4;
-                    v2 = (hp_taps_u8x4(__byte_perm(ab1, cd1, 0x5410)) + 8) >> 4;
-                    v3 = (hp_taps_u8x4(__byte_perm(ab1, cd1, 0x7632)) + 8) >> 4;
-                    pw = pack_u8x4(v0, v1, v2, v3);
-                } else if (phase == 2) {
-                    int v0, v1, v2, v3;
-                    const unsigned wa = ld4u(p - 1), wb = ld4u(p + 3);
-                    v0 = (hp_taps_u8x4(wa) + 8) >> 4; /* saturated by the pack below */
-                    v1 = (hp_taps_u8x4(__funnelshift_r(wa, wb, 8)) + 8) >> 4;
-                    v2 = (hp_taps_u8x4(__funnelshift_r(wa, wb, 16)) + 8) >> 4;
-                    v3 = (hp_taps_u8x4(__funnelshift_r(wa, wb, 24)) + 8) >> 4;
-                    pw = pack_u8x4(v0, v1, v2, v3);
-                } else {
-                    int v0, v1, v2, v3;
-                    const int16_t *b = hbuf + ly * hstride + lx;
-                    /* rows ly-1 .. ly+2 of the 16-bit H-filtered image; (row a, row b) and (row c, row d) of one column
-                     * are paired into a word each and run through dp2a with the taps (-1, 9) and (9, -1) */
-                    const uint2 ra = *reinterpret_cast<const uint2 *>(b), rb = *reinterpret_cast<const uint2 *>(b + hstride);
-                    const uint2 rc = *reinterpret_cast<const uint2 *>(b + 2 * hstride), rd = *reinterpret_cast<const uint2 *>(b + 3 * hstride);
-                    const unsigned t_ab = 0x09ffu, t_cd = 0xff09u;
-                    v0 = dp2a_lo_s16(__byte_perm(rc.x, rd.x, 0x5410), t_cd, dp2a_lo_s16(__byte_perm(ra.x, rb.x, 0x5410), t_ab, 128)) >> 8;
-                    v1 = dp2a_lo_s16(__byte_perm(rc.x, rd.x, 0x7632), t_cd, dp2a_lo_s16(__byte_perm(ra.x, rb.x, 0x7632), t_ab, 128)) >> 8;
-                    v2 = dp2a_lo_s16(__byte_perm(rc.y, rd.y, 0x5410), t_cd, dp2a_lo_s16(__byte_perm(ra.y, rb.y, 0x5410), t_ab, 128)) >> 8;
-                    v3 = dp2a_lo_s16(__byte_perm(rc.y, rd.y, 0x7632), t_cd, dp2a_lo_s16(__byte_perm(ra.y, rb.y, 0x7632), t_ab, 128)) >> 8;
-                    pw = pack_u8x4(v0, v1, v2, v3);
-                }
-            } else {
-                if (phase == 1) {
-                    pw = avg_up_u8x4(ld4u(p), ld4u(p + rs));
-                } else if (phase == 2) {
-                    pw = avg_up_u8x4(ld4u(p), ld4u(p + 1));
-                } else {
-                    int v0, v1, v2, v3;
-                    const unsigned wa = ld4u(p), wb = ld4u(p + 1), wc = ld4u(p + rs), wd = ld4u(p + rs + 1);
-                    v0 = (byte_of(wa, 0) + byte_of(wb, 0) + byte_of(wc, 0) + byte_of(wd, 0) + 2) >> 2;
-                    v1 = (byte_of(wa, 1) + byte_of(wb, 1) + byte_of(wc, 1) + byte_of(wd, 1) + 2) >> 2;
-                    v2 = (byte_of(wa, 2) + byte_of(wb, 2) + byte_of(wc, 2) + byte_of(wd, 2) + 2) >> 2;
-                    v3 = (byte_of(wa, 3) + byte_of(wb, 3) + byte_of(wc, 3) + byte_of(wd, 3) + 2) >> 2;
-                    pw = pack_u8x4(v0, v1, v2, v3);
-                }
-            }
-            bmc_store4(P, mode, x + lx, y + ly, imin(4, cw - lx), walign, pw);
-        }
-        return;
+    s.n = imin(16, s.cw - s.lx);
+    s.rows = imin(R, s.ch - s.ly);
+    s.mv = a.mv[s.b];
+    s.intra = s.mv.mode != 0;
+    const int dx = s.intra ? 0 : (s.mv.x >> sh), dy = s.intra ? 0 : (s.mv.y >> sv);
+    s.px = iclamp(s.x + (dx >> 1), -DSV_BORDER, (P.w - bw) + DSV_BORDER - 1); /* bmc.c:240-249 */
+    s.py = iclamp(s.y + (dy >> 1), -DSV_BORDER, (P.h - bh) + DSV_BORDER - 1);
+    if (s.intra) { /* co-located, never clamped (bmc.c:262,287) */
+        s.px = s.x;
+        s.py = s.y;
     }
-
-    /* intra block: mean of the co-located reference block, whole or per quadrant (bmc.c:255-298) */
-    const bool whole = mv.submask == 15;
-    const int sbw = whole ? cw : cw / 2, sbh = whole ? ch : ch / 2;
-    const uint8_t *r0 = P.ref + (ptrdiff_t) y * P.rstride + x;
-    const int nq = whole ? 1 : 4;
-    for (int q = 0; q < nq; q++) {
-        const int qx = (q & 1) * sbw, qy = (q >> 1) * sbh;
-        unsigned acc = 0;
-        if (whole || (mv.submask & (1 << q))) {
-            for (int k = tid; k < sbw * sbh; k += BMC_THREADS) {
-                const int ly = k / sbw, lx = k - ly * sbw;
-                acc += r0[(ptrdiff_t) (qy + ly) * P.rstride + qx + lx];
-            }
-        }
-        const unsigned tot = block_sum_u32(acc, scratch);
-        if (tid == 0) {
-            s_avg[q] = (sbw > 0 && sbh > 0) ? (int) (tot / (unsigned) (sbw * sbh)) : 0;
-        }
-    }
-    __syncthreads();
-    for (int k = tid; k < (ch << wsh); k += BMC_THREADS) {
-        const int ly = k >> wsh, wx = k & wmask;
-        if (wx >= words) {
-            continue;
-        }
-        int v[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int lx = 4 * wx + e;
-            if (whole) {
-                v[e] = s_avg[0];
-            } else if (lx >= 2 * sbw || ly >= 2 * sbh) {
-                v[e] = 0; /* odd edge blocks: the quadrants do not cover the last row/column (zeroed frame) */
-            } else {
-                const int q = (lx >= sbw ? 1 : 0) | (ly >= sbh ? 2 : 0);
-                v[e] = (mv.submask & (1 << q)) ? s_avg[q] : (lx < cw ? (int) r0[(ptrdiff_t) ly * P.rstride + lx] : 0);
-            }
-        }
-        bmc_store4(P, mode, x + 4 * wx, y + ly, imin(4, cw - 4 * wx), walign, pack_u8x4(v[0], v[1], v[2], v[3]));
-    }
+    s.xh = dx & 1;
+    s.yh = dy & 1;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(P.in) | reinterpret_cast<uintptr_t>(P.out) | reinterpret_cast<uintptr_t>(P.pred) |
+                         (uintptr_t) (unsigned) (P.istride | P.ostride | P.pstride | (s.x + s.lx));
+    s.vec16 = s.n == 16 && (al & 15) == 0;
+    return true;
 }
 
-/* one CTA per motion block and lane, all three planes in turn (a chroma block alone is too little work to pay
- * for a CTA launch) */
-/* 6 CTAs per SM (40 registers): the kernel is latency-bound, measured 268 us per 32 HD pictures against 308 us at 48
- * registers / 5 CTAs and 290 us at 32 registers with spills; unrolling the word loop is slower as well */
-__global__ void __launch_bounds__(BMC_THREADS, 6) bmc_kernel(const BmcArgs *args)
+/* the forward transform of a plane with odd width reads one column past it (sbt.c:583-591); in the reference
+ * that column of the residual frame still holds the replicated INPUT border (dsv_encoder.c:657-659: xf = copy
+ * of the padded input, then only w x h is replaced) */
+DSV_D void bmc_edge_column(const BmcPlane &P, const BmcStrip &s, int mode)
 {
-    __shared__ __align__(8) int16_t hbuf[(DSV_BORDER + 3) * DSV_BORDER]; /* (bh + 3) x bw, bmc.c:127 */
-    __shared__ unsigned scratch[40];
-    __shared__ int s_avg[4];
-    const BmcArgs &a = args[blockIdx.z];
-    for (int c = 0; c < 3; c++) {
-        bmc_block_plane(a, c, hbuf, scratch, s_avg);
-        __syncthreads(); /* hbuf / s_avg are reused by the next plane */
+    if (mode == 1 && s.x + s.cw == P.w && s.lx + s.n == s.cw) {
+        for (int k = 0; k < s.rows; k++) {
+            const int gy = s.y + s.ly + k;
+            P.out[(size_t) gy * P.ostride + P.w] = P.in[(size_t) gy * P.istride + P.w];
+        }
     }
 }
 
-void bmc_fill_args(BmcArgs *a, const MotionGeom &g, const DevMV *d_mv, const DevFrame &ref, const DevFrame *pred,
+DSV_D void bmc_luma_strip(const BmcArgs &a, const int u)
+{
+    BmcStrip s = {};
+    if (!bmc_strip_setup<BMC_RL>(a, 0, u, s)) {
+        return;
+    }
+    const BmcPlane &P = a.pl[0];
+    const unsigned means = s.intra ? a.means[s.b] : 0u;
+    /* taps: bytes (p[-1], p[0], p[1], p[2]); pairs (row a, row b) and (row c, row d) */
+    const unsigned th = s.xh ? 0xff0909ffu : 0x00001000u;
+    const unsigned t_ab = s.yh ? 0x09ffu : 0x1000u, t_cd = s.yh ? 0xff09u : 0x0000u;
+    const int rs = P.rstride;
+    /* first byte needed: one row above and one sample left of the strip's reference position */
+    const uint8_t *src = P.ref + (ptrdiff_t) (s.py + s.ly - 1) * rs + (s.px + s.lx - 1);
+    const unsigned bsh = ((unsigned) reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
+    const unsigned *q = reinterpret_cast<const unsigned *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t) 3);
+    const int qs = rs >> 2; /* strides are multiples of 16 */
+
+    int hprev[16];
+    unsigned pr0[16], pr1[16]; /* vertical pairs (row r-3, r-2) and (row r-2, r-1) of 16-bit H results */
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        hprev[e] = 0;
+        pr0[e] = pr1[e] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < BMC_RL + 3; r++) {
+        if (r >= s.rows + 3) {
+            break;
+        }
+        {
+            const unsigned *qr = q + (ptrdiff_t) r * qs;
+            const unsigned w0 = qr[0], w1 = qr[1], w2 = qr[2], w3 = qr[3], w4 = qr[4], w5 = qr[5];
+            unsigned v[5];
+            v[0] = __funnelshift_r(w0, w1, bsh);
+            v[1] = __funnelshift_r(w1, w2, bsh);
+            v[2] = __funnelshift_r(w2, w3, bsh);
+            v[3] = __funnelshift_r(w3, w4, bsh);
+            v[4] = __funnelshift_r(w4, w5, bsh);
+            int h[16];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                h[4 * k + 0] = dp4a_us(v[k], th, 0);
+                h[4 * k + 1] = dp4a_us(__funnelshift_r(v[k], v[k + 1], 8), th, 0);
+                h[4 * k + 2] = dp4a_us(__funnelshift_r(v[k], v[k + 1], 16), th, 0);
+                h[4 * k + 3] = dp4a_us(__funnelshift_r(v[k], v[k + 1], 24), th, 0);
+            }
+            unsigned pr2[16]; /* pair (row r-1, row r) */
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                pr2[e] = __byte_perm((unsigned) hprev[e], (unsigned) h[e], 0x5410);
+                hprev[e] = h[e];
+            }
+            if (r >= 3) { /* output row r-3: rows a,b = pair (r-3, r-2), rows c,d = pair (r-1, r) */
+                unsigned pw[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int v0 = dp2a_lo_s16(pr2[4 * k + 0], t_cd, dp2a_lo_s16(pr0[4 * k + 0], t_ab, 128)) >> 8;
+                    const int v1 = dp2a_lo_s16(pr2[4 * k + 1], t_cd, dp2a_lo_s16(pr0[4 * k + 1], t_ab, 128)) >> 8;
+                    const int v2 = dp2a_lo_s16(pr2[4 * k + 2], t_cd, dp2a_lo_s16(pr0[4 * k + 2], t_ab, 128)) >> 8;
+                    const int v3 = dp2a_lo_s16(pr2[4 * k + 3], t_cd, dp2a_lo_s16(pr0[4 * k + 3], t_ab, 128)) >> 8;
+                    pw[k] = pack_u8x4(v0, v1, v2, v3);
+                }
+                if (s.intra) {
+                    bmc_intra_row(pw, s.mv, means, s.lx, s.ly + r - 3, s.cw, s.ch);
+                }
+                bmc_store_row(P, a.mode, s.x + s.lx, s.y + s.ly + r - 3, s.n, s.vec16, pw);
+            }
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                pr0[e] = pr1[e];
+                pr1[e] = pr2[e];
+            }
+        }
+    }
+    bmc_edge_column(P, s, a.mode);
+}
+
+DSV_D void bmc_chroma_strip(const BmcArgs &a, const int c, const int u)
+{
+    BmcStrip s = {};
+    if (!bmc_strip_setup<BMC_RC>(a, c, u, s)) {
+        return;
+    }
+    const BmcPlane &P = a.pl[c];
+    const unsigned means = s.intra ? a.means[(size_t) c * a.nbh * a.nbv + s.b] : 0u;
+    /* weights for (p[0], p[1], p[rs], p[rs + 1]) */
+    const unsigned wt = s.xh ? (s.yh ? 0x01010101u : 0x00000202u) : (s.yh ? 0x00020002u : 0x00000004u);
+    const int rs = P.rstride;
+    const uint8_t *src = P.ref + (ptrdiff_t) (s.py + s.ly) * rs + (s.px + s.lx);
+    const unsigned bsh = ((unsigned) reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
+    const unsigned *q = reinterpret_cast<const unsigned *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t) 3);
+    const int qs = rs >> 2;
+
+    unsigned top[16]; /* (p[e], p[e + 1]) of the row above in the two low bytes */
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        top[e] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < BMC_RC + 1; r++) {
+        if (r >= s.rows + 1) {
+            break;
+        }
+        {
+            const unsigned *qr = q + (ptrdiff_t) r * qs;
+            const unsigned w0 = qr[0], w1 = qr[1], w2 = qr[2], w3 = qr[3], w4 = qr[4];
+            unsigned v[5];
+            v[0] = __funnelshift_r(w0, w1, bsh);
+            v[1] = __funnelshift_r(w1, w2, bsh);
+            v[2] = __funnelshift_r(w2, w3, bsh);
+            v[3] = __funnelshift_r(w3, w4, bsh);
+            v[4] = w4 >> bsh; /* only sample 16 is needed */
+            unsigned cur[16];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                cur[4 * k + 0] = v[k];
+                cur[4 * k + 1] = __funnelshift_r(v[k], v[k + 1], 8);
+                cur[4 * k + 2] = __funnelshift_r(v[k], v[k + 1], 16);
+                cur[4 * k + 3] = __funnelshift_r(v[k], v[k + 1], 24);
+            }
+            if (r >= 1) {
+                unsigned pw[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int v0 = dp4a_us(__byte_perm(top[4 * k + 0], cur[4 * k + 0], 0x5410), wt, 2) >> 2;
+                    const int v1 = dp4a_us(__byte_perm(top[4 * k + 1], cur[4 * k + 1], 0x5410), wt, 2) >> 2;
+                    const int v2 = dp4a_us(__byte_perm(top[4 * k + 2], cur[4 * k + 2], 0x5410), wt, 2) >> 2;
+                    const int v3 = dp4a_us(__byte_perm(top[4 * k + 3], cur[4 * k + 3], 0x5410), wt, 2) >> 2;
+                    pw[k] = pack_u8x4(v0, v1, v2, v3);
+                }
+                if (s.intra) {
+                    bmc_intra_row(pw, s.mv, means, s.lx, s.ly + r - 1, s.cw, s.ch);
+                }
+                bmc_store_row(P, a.mode, s.x + s.lx, s.y + s.ly + r - 1, s.n, s.vec16, pw);
+            }
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                top[e] = cur[e];
+            }
+        }
+    }
+    bmc_edge_column(P, s, a.mode);
+}
+
+/* grid.x = [luma strips | U strips | V strips] in CTAs of BMC_THREADS strips, grid.y = lane */
+__global__ void __launch_bounds__(BMC_THREADS, 2) bmc_kernel(const BmcArgs *args, int ctas_l, int ctas_c)
+{
+    const BmcArgs &a = args[blockIdx.y];
+    int cta = blockIdx.x;
+    if (cta < ctas_l) {
+        bmc_luma_strip(a, cta * BMC_THREADS + threadIdx.x);
+        return;
+    }
+    cta -= ctas_l;
+    const int c = cta < ctas_c ? 1 : 2;
+    if (c == 2) {
+        cta -= ctas_c;
+    }
+    bmc_chroma_strip(a, c, cta * BMC_THREADS + threadIdx.x);
+}
+
+/* means of the intra blocks: one warp per block, planes in turn; a word per (plane, block) holds the four quadrant
+ * means (avgval, bmc.c:176-190), or the block mean four times for an all-intra block */
+__global__ void __launch_bounds__(BMC_THREADS) bmc_means_kernel(const BmcArgs *args)
+{
+    const BmcArgs &a = args[blockIdx.y];
+    const int nblk = a.nbh * a.nbv;
+    const int b = blockIdx.x * (BMC_THREADS / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= nblk) {
+        return;
+    }
+    const DevMV mv = a.mv[b];
+    if (mv.mode == 0) {
+        return;
+    }
+    const int j = b / a.nbh, i = b - j * a.nbh;
+    for (int c = 0; c < 3; c++) {
+        const BmcPlane &P = a.pl[c];
+        const int sh = c ? a.hs : 0, sv = c ? a.vs : 0;
+        const int bw = a.blk_w >> sh, bh = a.blk_h >> sv;
+        const int x = i * bw, y = j * bh;
+        const int cw = (x + bw >= P.w) ? P.w - x : bw;
+        const int ch = (y + bh >= P.h) ? P.h - y : bh;
+        const bool whole = mv.submask == 15;
+        const int sbw = whole ? cw : cw / 2, sbh = whole ? ch : ch / 2;
+        unsigned word = 0;
+        for (int qd = 0; qd < (whole ? 1 : 4); qd++) {
+            unsigned acc = 0;
+            if (whole || (mv.submask & (1 << qd))) {
+                const uint8_t *r0 = P.ref + (ptrdiff_t) (y + (qd >> 1) * sbh) * P.rstride + x + (qd & 1) * sbw;
+                for (int ly = 0; ly < sbh; ly++) {
+                    for (int lx = lane; lx < sbw; lx += 32) {
+                        acc += r0[(ptrdiff_t) ly * P.rstride + lx];
+                    }
+                }
+            }
+            acc = __reduce_add_sync(0xffffffffu, acc);
+            const unsigned m = (sbw > 0 && sbh > 0) ? acc / (unsigned) (sbw * sbh) : 0u;
+            word |= m << (8 * qd);
+        }
+        if (whole) {
+            word *= 0x01010101u;
+        }
+        if (lane == 0 && cw > 0 && ch > 0) {
+            a.means[(size_t) c * nblk + b] = word;
+        }
+    }
+}
+
+void bmc_fill_args(BmcArgs *a, const MotionGeom &g, const DevMV *d_mv, uint32_t *d_means, const DevFrame &ref, const DevFrame *pred,
                    const DevFrame &in, const DevFrame &out, int mode)
 {
     for (int c = 0; c < 3; c++) {
@@ -272,6 +417,7 @@ void bmc_fill_args(BmcArgs *a, const MotionGeom &g, const DevMV *d_mv, const Dev
         a->pl[c].h = out.h[c];
     }
     a->mv = d_mv;
+    a->means = d_means;
     a->blk_w = g.blk_w;
     a->blk_h = g.blk_h;
     a->nbh = g.nbh;
@@ -281,12 +427,24 @@ void bmc_fill_args(BmcArgs *a, const MotionGeom &g, const DevMV *d_mv, const Dev
     a->mode = mode;
 }
 
-void bmc_launch(const BmcArgs *d_args, int n, int nbh, int nbv, cudaStream_t st)
+static int bmc_ctas(int bw, int bh, int rows, int nblk)
 {
-    if (n > 0) {
-        DSV_LAUNCH(bmc_kernel, dim3(nbh, nbv, n), dim3(BMC_THREADS), 0, st, d_args);
-        KERNEL_CHECK();
+    const long long units = (long long) ((bw + 15) >> 4) * ((bh + rows - 1) / rows) * nblk;
+    return (int) ((units + BMC_THREADS - 1) / BMC_THREADS);
+}
+
+void bmc_launch(const BmcArgs *d_args, int n, const MotionGeom &g, cudaStream_t st)
+{
+    if (n <= 0) {
+        return;
     }
+    const int nblk = g.nbh * g.nbv;
+    const int ctas_l = bmc_ctas(g.blk_w, g.blk_h, BMC_RL, nblk);
+    const int ctas_c = bmc_ctas(g.blk_w >> g.hs, g.blk_h >> g.vs, BMC_RC, nblk);
+    DSV_LAUNCH(bmc_means_kernel, dim3((nblk + BMC_THREADS / 32 - 1) / (BMC_THREADS / 32), n), dim3(BMC_THREADS), 0, st, d_args);
+    KERNEL_CHECK();
+    DSV_LAUNCH(bmc_kernel, dim3(ctas_l + 2 * ctas_c, n), dim3(BMC_THREADS), 0, st, d_args, ctas_l, ctas_c);
+    KERNEL_CHECK();
 }
 
 } // namespace dsv

@@ -14,8 +14,14 @@
 
 #ifndef DSV_CPU_EMU
 #include <cuda_runtime.h>
-#define DSV_LAUNCH(kernel, grid, block, smem, stream, ...) \
-    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+/* every launch goes through here: when the calling thread has a KernelTimes collector active (an engine step,
+ * ktime.cu) the launch is bracketed by two CUDA events on its stream, keyed by the kernel's name */
+#define DSV_LAUNCH(kernel, grid, block, smem, stream, ...)               \
+    do {                                                                 \
+        static const int kt_slot_ = dsv::kt_slot(#kernel);               \
+        dsv::KtScope kt_scope_(kt_slot_, (stream));                      \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);      \
+    } while (0)
 #define DSV_DYN_SMEM(type, name)                                   \
     extern __shared__ __align__(16) unsigned char dsv_dyn_smem_[]; \
     type *name = reinterpret_cast<type *>(dsv_dyn_smem_)
@@ -37,6 +43,55 @@
 #define KERNEL_CHECK() CUDA_CHECK(cudaGetLastError())
 
 namespace dsv {
+
+/* ---- per-kernel live timing (ktime.cu) ---------------------------------------------------------- */
+#define KT_MAX_SLOTS 64
+int kt_slot(const char *kernel_name);      /* registers the name on first use; -1 when the table is full */
+int kt_count();
+const char *kt_name(int slot);
+struct KernelTimes {
+    struct Rec {
+        int slot;
+        cudaEvent_t e0, e1;
+    };
+    /* two generations: a decoder step's records are read when its parity comes round again */
+    Rec *recs[2] = {nullptr, nullptr};
+    int n[2] = {0, 0}, cap[2] = {0, 0};
+    int gen = 0;
+    double ms[KT_MAX_SLOTS] = {0};
+    unsigned long long launches[KT_MAX_SLOTS] = {0};
+    void open(int generation) { gen = generation; }
+    Rec *next();
+    void collect(int generation); /* the events of that generation must have completed */
+    void reset();
+    void destroy();
+};
+extern thread_local KernelTimes *kt_current;
+struct KtActivate { /* RAII: launches of this thread are attributed to `t` while the object lives */
+    KernelTimes *prev;
+    explicit KtActivate(KernelTimes *t) : prev(kt_current) { kt_current = t; }
+    ~KtActivate() { kt_current = prev; }
+};
+#ifndef DSV_CPU_EMU
+struct KtScope {
+    KernelTimes::Rec *r = nullptr;
+    cudaStream_t st;
+    KtScope(int slot, cudaStream_t s) : st(s)
+    {
+        if (kt_current && slot >= 0) {
+            r = kt_current->next();
+            r->slot = slot;
+            cudaEventRecord(r->e0, st);
+        }
+    }
+    ~KtScope()
+    {
+        if (r) {
+            cudaEventRecord(r->e1, st);
+        }
+    }
+};
+#endif
 
 DSV_HD int imin(int a, int b) { return a < b ? a : b; }
 DSV_HD int imax(int a, int b) { return a > b ? a : b; }

@@ -150,6 +150,25 @@ extern "C" void dsvb_enc_stats(DSVB_ENC *e, double *stats, int reset)
     }
 }
 
+static void fill_ktimes(KernelTimes *kt, double *ms, double *launches, int reset)
+{
+    const int n = kt_count();
+    for (int i = 0; i < n; i++) {
+        ms[i] = kt ? kt->ms[i] : 0.0;
+        launches[i] = kt ? (double) kt->launches[i] : 0.0;
+    }
+    if (kt && reset) {
+        kt->reset();
+    }
+}
+
+extern "C" int dsvb_kernel_count(void) { return kt_count(); }
+extern "C" const char *dsvb_kernel_name(int i) { return kt_name(i); }
+extern "C" void dsvb_enc_kernel_times(DSVB_ENC *e, double *ms, double *launches, int reset)
+{
+    fill_ktimes(&e->eng->ktimes, ms, launches, reset);
+}
+
 extern "C" int dsvb_encode(DSVB_ENC *e, int nseq, int nframes, const uint8_t *const *yuv, int on_device,
                            uint8_t *const *streams, const long *caps, long *lens)
 {
@@ -272,6 +291,11 @@ extern "C" void dsvb_dec_set_out420p(DSVB_DEC *d, int on)
     if (d->eng) {
         d->eng->set_out420(on != 0);
     }
+}
+
+extern "C" void dsvb_dec_kernel_times(DSVB_DEC *d, double *ms, double *launches, int reset)
+{
+    fill_ktimes(d->eng ? &d->eng->ktimes : nullptr, ms, launches, reset);
 }
 
 extern "C" void dsvb_dec_stats(DSVB_DEC *d, double *stats, int reset)

@@ -107,6 +107,7 @@ DecEngine::DecEngine(const DSV_META &md, int lanes)
     pkt_cap_ = g.coef_total * 8 + 4096 + (size_t) g.nblk * 64;
     const size_t per_lane = 3 * (sizeof(SbtJob) + hzdec_job_size()) + sizeof(BmcArgs) + 8 * sizeof(PlaneRef) + 3 * sizeof(PackItem) + sizeof(ZeroItem) + sizeof(CopyItem) + sizeof(DrawItem) + sizeof(PackItem) + 2 * sizeof(To420Item) + 1024;
     CUDA_CHECK(cudaMalloc(&d_mv_, sizeof(DevMV) * (size_t) max_nblk_ * L_));
+    CUDA_CHECK(cudaMalloc(&d_means_, sizeof(uint32_t) * 3 * (size_t) max_nblk_ * L_));
     CUDA_CHECK(cudaMalloc(&d_stab_, (size_t) max_nblk_ * L_));
     for (int q = 0; q < 2; q++) {
         arena_[q].create(per_lane * (size_t) L_ + 4096);
@@ -160,6 +161,7 @@ DecEngine::~DecEngine()
     cudaFree(d_out_all_[0]);
     cudaFree(d_out_all_[1]);
     cudaFree(d_mv_);
+    cudaFree(d_means_);
     cudaFreeHost(h_mv_[0]);
     cudaFreeHost(h_mv_[1]);
     cudaFree(d_stab_);
@@ -171,6 +173,7 @@ DecEngine::~DecEngine()
         }
         cudaEventDestroy(ev_end_[q]);
     }
+    ktimes.destroy();
     cudaEventDestroy(ev_done_);
     cudaEventDestroy(ev_copied_[0]);
     cudaEventDestroy(ev_copied_[1]);
@@ -195,6 +198,7 @@ void DecEngine::collect(int parity)
         return;
     }
     CUDA_CHECK(cudaEventSynchronize(ev_end_[parity]));
+    ktimes.collect(parity);
     float ms = 0;
     CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[parity][0], ev_[parity][1]));
     stats.sbt_inv_ms += ms;
@@ -228,6 +232,8 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
     cudaStream_t st = st_;
     const int par = (int) (step_no_ & 1);
     collect(par);
+    KtActivate kt_on(&ktimes);
+    ktimes.open(par);
     StepArena &arena_ = this->arena_[par];
     uint8_t *const h_stab_ = this->h_stab_[par];
     DevMV *const h_mv_ = this->h_mv_[par];
@@ -486,7 +492,7 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
         }
         if (isP) {
             const MotionGeom mg = {g.w, g.h, g.hs, g.vs, g.blk_w, g.blk_h, g.nbh, g.nbv, 0};
-            bmc_fill_args(&ba[n_p++], mg, d_mv_ + (size_t) li * step_nblk, l.out[l.cur ^ 1], nullptr, cur, cur, 2);
+            bmc_fill_args(&ba[n_p++], mg, d_mv_ + (size_t) li * step_nblk, d_means_ + 3 * (size_t) li * step_nblk, l.out[l.cur ^ 1], nullptr, cur, cur, 2);
         }
         /* dsv_decoder.c:405: coefficient planes start zeroed.  Planes that were never coded (corrupt plen) stay
          * all-zero here; the reference leaves the zeroed residual plane untouched instead. */
@@ -518,7 +524,10 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
     if (n_p) {
         CUDA_CHECK(cudaEventRecord(ev_[2], st));
     }
-    bmc_launch(d_bmc, n_p, nbh, nbv, st);
+    {
+        const MotionGeom mg = {g_.w, g_.h, g_.hs, g_.vs, blk_w, blk_h, nbh, nbv, 0};
+        bmc_launch(d_bmc, n_p, mg, st);
+    }
     if (n_p) {
         CUDA_CHECK(cudaEventRecord(ev_[3], st));
     }

@@ -372,6 +372,7 @@ EncEngine::EncEngine(const DSV_META &md, int gop, int pyramid_levels, int lanes)
                             sizeof(BmcArgs) + 8 * sizeof(PlaneRef) + 2 * sizeof(ZeroItem) + 2048;
     arena_.create(per_lane * (size_t) L_ + 4096);
     CUDA_CHECK(cudaMalloc(&d_mv0_, sizeof(DevMV) * (size_t) g_.nblk * L_));
+    CUDA_CHECK(cudaMalloc(&d_means_, sizeof(uint32_t) * 3 * (size_t) g_.nblk * L_));
     CUDA_CHECK(cudaMemset(d_mv0_, 0, sizeof(DevMV) * (size_t) g_.nblk * L_));
     CUDA_CHECK(cudaMallocHost(&h_mv0_, sizeof(DevMV) * (size_t) g_.nblk * L_));
     memset(h_mv0_, 0, sizeof(DevMV) * (size_t) g_.nblk * L_);
@@ -472,6 +473,7 @@ EncEngine::~EncEngine()
     cudaFree(d_in_all_[0]);
     cudaFree(d_in_all_[1]);
     cudaFree(d_mv0_);
+    cudaFree(d_means_);
     cudaFreeHost(h_mv0_);
     cudaFree(d_stab_);
     cudaFreeHost(h_stab_);
@@ -484,6 +486,7 @@ EncEngine::~EncEngine()
     for (auto &e : ev_) {
         cudaEventDestroy(e);
     }
+    ktimes.destroy();
     cudaEventDestroy(ev_search_);
     cudaEventDestroy(ev_pref_[0]);
     cudaEventDestroy(ev_pref_[1]);
@@ -554,6 +557,8 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     cudaStream_t st = st_;
     const MotionGeom mg = {g.w, g.h, g.hs, g.vs, g.blk_w, g.blk_h, g.nbh, g.nbv, levels_};
     LaneMisc *h_misc = reinterpret_cast<LaneMisc *>(h_misc_), *d_misc = reinterpret_cast<LaneMisc *>(d_misc_);
+    KtActivate kt_on(&ktimes);
+    ktimes.open(0);
     arena_.reset();
 
     /* ---- phase 1: ingest, pyramid, luma sums, motion search -------------------------------------- */
@@ -684,7 +689,7 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         for (int k = 0; k < n; k++) {
             EncLane &l = lanes_[(size_t) lane_ids[k]];
             if (l.has_ref) {
-                bmc_fill_args(&ba[q++], mg, l.d_mvf[0], l.recon[l.cur ^ 1], &l.pred, l.pad[l.cur], l.xf, 1);
+                bmc_fill_args(&ba[q++], mg, l.d_mvf[0], d_means_ + 3 * (size_t) lane_ids[k] * g.nblk, l.recon[l.cur ^ 1], &l.pred, l.pad[l.cur], l.xf, 1);
             }
         }
     }
@@ -720,7 +725,7 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         }
         if (n_search) {
             CUDA_CHECK(cudaEventRecord(ev_[5], st));
-            bmc_launch(d_bmc, n_search, g.nbh, g.nbv, st);
+            bmc_launch(d_bmc, n_search, mg, st);
             CUDA_CHECK(cudaEventRecord(ev_[6], st));
             stats.kernel_launches += 1;
         }
@@ -952,6 +957,7 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     }
     copy_launch(pk, n_pk, max_pk, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
+    ktimes.collect(0);
     {
         float ms = 0;
         CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));

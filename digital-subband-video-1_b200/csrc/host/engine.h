@@ -194,6 +194,7 @@ public:
     int lanes() const { return L_; }
     const CodecGeom &geom() const { return g_; }
     EngineStats stats;
+    KernelTimes ktimes; /* every launch of step(), by kernel name */
     int device = 0;
 
 private:
@@ -211,6 +212,7 @@ private:
     StepArena arena_;
     /* lane-major arrays shared by all lanes so that one copy moves every lane's data */
     DevMV *d_mv0_ = nullptr, *h_mv0_ = nullptr;  /* level-0 motion fields */
+    uint32_t *d_means_ = nullptr;                /* intra block / quadrant means of the compensation (bmc.cu) */
     uint8_t *d_stab_ = nullptr, *h_stab_ = nullptr;
     uint8_t *d_misc_ = nullptr, *h_misc_ = nullptr; /* per lane: u64 luma sum, i32 intra count, pad */
     HzChunk *d_chunks_ = nullptr;
@@ -266,6 +268,7 @@ public:
     void reset_lane(int lane) { lanes_[(size_t) lane].have_ref = 0; }
     bool matches(const DSV_META &md) const { return md.width == g_.w && md.height == g_.h && md.subsamp == g_.subsamp; }
     EngineStats stats;
+    KernelTimes ktimes; /* every launch of step(), by kernel name; read one step late (collect) */
     int device = 0;
 
 private:
@@ -289,6 +292,7 @@ private:
     std::vector<DecLane> lanes_;
     StepArena arena_[2];
     DevMV *d_mv_ = nullptr, *h_mv_[2] = {nullptr, nullptr};
+    uint32_t *d_means_ = nullptr; /* intra block / quadrant means of the compensation (bmc.cu) */
     uint8_t *d_stab_ = nullptr, *h_stab_[2] = {nullptr, nullptr};
     uint8_t *d_out_all_[2] = {nullptr, nullptr}; /* packed-picture egress staging of all lanes (step parity) */
     size_t out_pitch_ = 0;

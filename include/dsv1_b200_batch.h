@@ -62,6 +62,15 @@ void dsvb_dec_set_draw_info(DSVB_DEC *d, int mode);
  * written to `out` as packed 4:2:0 (frame size w*h + 2*ceil(w/2)*ceil(h/2)), converted on the device */
 void dsvb_dec_set_out420p(DSVB_DEC *d, int on);
 
+/* Live per-kernel timing: every kernel launch of an engine step is bracketed by CUDA events on the engine's stream.
+ * dsvb_kernel_count() names are registered so far (at most 64, in order of first launch); ms[i] / launches[i]
+ * (arrays of at least 64 doubles) receive the accumulated device time and launch count of kernel i since the last
+ * reset.  The decoder reads a step's events when the step has left the GPU (dsvb_decode returns after that). */
+int dsvb_kernel_count(void);
+const char *dsvb_kernel_name(int i);
+void dsvb_enc_kernel_times(DSVB_ENC *e, double *ms, double *launches, int reset);
+void dsvb_dec_kernel_times(DSVB_DEC *d, double *ms, double *launches, int reset);
+
 /* pinned host memory for inputs / outputs of the calls above */
 void *dsvb_host_alloc(size_t bytes);
 void dsvb_host_free(void *p);

@@ -165,8 +165,8 @@ class Lib:
             off += n
         return res
 
-    def sub_pred(self, mv, w, h, subsamp, inp, ref):
-        bw, bh, nbh, nbv = block_dims(w, h)
+    def sub_pred(self, mv, w, h, subsamp, inp, ref, blk=None):
+        bw, bh, nbh, nbv = block_dims(w, h) if blk is None else blk
         n = frame_bytes(w, h, subsamp)
         pred = np.zeros(n, dtype=np.uint8)
         res = np.zeros(n, dtype=np.uint8)
@@ -176,8 +176,8 @@ class Lib:
         assert r == 0
         return pred, res
 
-    def add_pred(self, mv, w, h, subsamp, resid, ref):
-        bw, bh, nbh, nbv = block_dims(w, h)
+    def add_pred(self, mv, w, h, subsamp, resid, ref, blk=None):
+        bw, bh, nbh, nbv = block_dims(w, h) if blk is None else blk
         n = frame_bytes(w, h, subsamp)
         out = np.zeros(n, dtype=np.uint8)
         mvb = np.ascontiguousarray(mv).view(np.uint8)
@@ -282,6 +282,14 @@ STAT_KEYS = ["sbt_fwd_ms", "sbt_fwd_launches", "sbt_fwd_bytes", "sbt_inv_ms", "s
              "kernel_launches", "h2d_bytes", "d2h_bytes", "pictures", "device", "lanes", "host_ms", "bmc_ms", "bmc_launches", "bmc_bytes"]
 
 
+def _kernel_times(lib, fn, handle, reset):
+    ms = (C.c_double * 64)()
+    ln = (C.c_double * 64)()
+    getattr(lib, fn)(handle, ms, ln, int(reset))
+    lib.dsvb_kernel_name.restype = C.c_char_p
+    return {lib.dsvb_kernel_name(i).decode(): {"ms": ms[i], "launches": ln[i]} for i in range(lib.dsvb_kernel_count()) if ln[i] > 0}
+
+
 class BatchEncoder:
     """dsvb_enc_*: `lanes` sequences in lock step on one GPU."""
 
@@ -313,6 +321,10 @@ class BatchEncoder:
         st = (C.c_double * NSTATS)()
         self.lib.dsvb_enc_stats(self.h, st, int(reset))
         return dict(zip(STAT_KEYS, list(st)))
+
+    def kernel_times(self, reset=False):
+        """{kernel name: {ms, launches}} of every launch made by the engine's steps since the last reset"""
+        return _kernel_times(self.lib, "dsvb_enc_kernel_times", self.h, reset)
 
     def close(self):
         if self.h:
@@ -356,6 +368,9 @@ class BatchDecoder:
         st = (C.c_double * NSTATS)()
         self.lib.dsvb_dec_stats(self.h, st, int(reset))
         return dict(zip(STAT_KEYS, list(st)))
+
+    def kernel_times(self, reset=False):
+        return _kernel_times(self.lib, "dsvb_dec_kernel_times", self.h, reset)
 
     def close(self):
         if self.h:

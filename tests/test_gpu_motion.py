@@ -95,3 +95,35 @@ def test_dsv_hme_exported_interface(gpu, ref):
         for k in mr.dtype.names:
             if k != "pad":
                 assert np.array_equal(mr[k], mg[k]), (w, h, fmt, k)
+
+
+STRIP_CASES = [
+    (112, 96, "444", None), (100, 70, "420", None), (103, 75, "411", (24, 16)), (90, 66, "422", (20, 28)),
+    (132, 52, "420", (64, 48)), (75, 49, "420", (36, 20)), (1920, 1080, "420", None), (1280, 720, "422", (44, 52)),
+    (854, 480, "411", None), (3840, 2160, "444", None),
+]
+
+
+@pytest.mark.parametrize("case", STRIP_CASES, ids=lambda c: "%dx%d-%s-%s" % (c[0], c[1], c[2], "auto" if c[3] is None else "%dx%d" % c[3]))
+def test_bmc_strips_random_fields(gpu, ref, case):
+    """The streaming compensation on random frames and random vector fields (all half-pel phases, vectors clamping
+    into the border, whole / partial intra blocks), block widths that are not multiples of 16, every subsampling."""
+    w, h, fmt, blk = case
+    sub = L.SUBSAMP[fmt]
+    blk = L.block_dims(w, h) if blk is None else (blk[0], blk[1], (w + blk[0] - 1) // blk[0], (h + blk[1] - 1) // blk[1])
+    rng = np.random.default_rng(w * 131 + h)
+    n = L.frame_bytes(w, h, sub)
+    fr = rng.integers(0, 256, size=n, dtype=np.uint8)
+    fs = rng.integers(0, 256, size=n, dtype=np.uint8)
+    for amp, intra in ((110, 0.3), (5, 0.0)):
+        nblk = blk[2] * blk[3]
+        mv = np.zeros(nblk, dtype=L.MV_DTYPE)
+        mv["x"] = rng.integers(-amp, amp + 1, size=nblk).astype(np.int16)
+        mv["y"] = rng.integers(-amp, amp + 1, size=nblk).astype(np.int16)
+        mv["mode"] = (rng.random(nblk) < intra).astype(np.uint8)
+        mv["submask"] = np.where(mv["mode"] == 1, rng.integers(1, 16, size=nblk), 0).astype(np.uint8)
+        pa, ra = ref.sub_pred(mv, w, h, sub, fs, fr, blk)
+        pb, rb = gpu.sub_pred(mv, w, h, sub, fs, fr, blk)
+        assert np.array_equal(pa, pb), "prediction differs"
+        assert np.array_equal(ra, rb), "residual differs"
+        assert np.array_equal(ref.add_pred(mv, w, h, sub, ra, fr, blk), gpu.add_pred(mv, w, h, sub, ra, fr, blk))
