@@ -3,9 +3,10 @@
  * reconstruction (decoder).  Replaces compensate / hpelL / hpel / avgval / cpyzero / subf / addf /
  * dsv_sub_pred / dsv_add_pred (bmc.c:29-346).
  *
- * Streaming formulation: the unit of work is a strip of 16 samples x R rows of ONE motion block (R = 8 luma,
- * 4 chroma), one strip per thread, the strips of all blocks / planes / lanes flattened into one grid.  A thread
- * keeps everything in registers -- no shared memory, no barriers:
+ * Streaming formulation: the unit of work is a strip of 8 samples x R rows of ONE motion block (R = 16 luma,
+ * 8 chroma), one strip per thread, the strips of all blocks / planes / lanes flattened into one grid.  A thread
+ * keeps everything in registers -- no shared memory, no barriers -- and keeps BMC_PF reference rows plus three
+ * rows of the current picture in flight (explicit prefetch rings):
  *
  *   luma    every inter block goes through the SAME separable 4-tap path whatever its half-pel phase: the phase
  *           only selects the tap words, (-1,9,9,-1) or (0,16,0,0), per direction.  With 16 = the taps' DC gain
@@ -17,13 +18,13 @@
  *   chroma  bilinear (bmc.c:58-110) as one dp4a per sample with phase-selected weights summing to 4:
  *             (4a + 2) >> 2 == a,  (2a + 2b + 2) >> 2 == (a + b + 1) >> 1,  (a + b + c + d + 2) >> 2.
  *   intra   (bmc.c:255-298) blocks take the co-located reference through the same path (zero vector) and
- *           overwrite the flagged quadrants with the block / quadrant means that bmc_means_kernel (one warp per
- *           intra block, a launch that exits at once for inter blocks) left in a small table.
+ *           overwrite the flagged quadrants with the block / quadrant means, which the strip's thread sums itself
+ *           (a separate pass over all blocks measured 13-45 us per launch to find, usually, nothing).
  *
  * The prediction never makes a round trip through HBM on the decoder side (mode 2: io = clamp(pred + io - 128));
  * the encoder keeps it (mode 1) because the closed-loop reconstruction adds it back in the inverse transform's
- * store (sbt_inv.cu).  Plane rows are 16-byte aligned, so whole strips move as 16-byte loads / stores; strips cut
- * by the picture edge or by block widths that are not multiples of 16 fall back to words / bytes.
+ * store (sbt_inv.cu).  Plane rows are 16-byte aligned, so whole strip rows move as 8-byte loads / stores; strips cut
+ * by the picture edge or by block widths that are not multiples of 8 fall back to bytes.
  *
  * Reads outside the picture go through the 64-sample replicated border exactly like the reference
  * (position clamp bmc.c:221-249); filter taps that step one sample past the border see the same
@@ -35,8 +36,15 @@
 namespace dsv {
 
 #define BMC_THREADS 256
-#define BMC_RL 8 /* luma rows per strip */
-#define BMC_RC 4 /* chroma rows per strip */
+#define BMC_W 8   /* samples per strip row */
+#define BMC_RL 16 /* luma rows per strip */
+#define BMC_RC 8  /* chroma rows per strip */
+#ifndef BMC_PF
+#define BMC_PF 4  /* reference rows in flight per thread */
+#endif
+#ifndef BMC_MINB
+#define BMC_MINB 3 /* CTAs per SM the register budget is held to: 369 us per 64 HD pictures at 2 (96 registers), 322 at 3 (80) */
+#endif
 
 /* c + sum of the four unsigned bytes of w times the four signed bytes of taps */
 DSV_HD int dp4a_us(unsigned w, unsigned taps, int c)
@@ -54,41 +62,36 @@ DSV_HD int dp4a_us(unsigned w, unsigned taps, int c)
 #endif
 }
 
-/* out = clamp(in -/+ pred +/- 128) on four packed samples */
+/* four packed samples: mode 1 clamp(cur - pred + 128), mode 2 clamp(pred + cur - 128) (subf / addf, bmc.c:29-57).
+ * With both operands moved to signed bytes (x ^ 0x80 == x - 128) these are the signed saturating byte
+ * subtraction / addition, moved back: a dozen logic instructions per word instead of unpack - add - repack. */
 DSV_D unsigned bmc_combine4(unsigned cur, unsigned pw, int mode)
 {
-    const int p0 = byte_of(pw, 0), p1 = byte_of(pw, 1), p2 = byte_of(pw, 2), p3 = byte_of(pw, 3);
-    if (mode == 1) {
-        return pack_u8x4(byte_of(cur, 0) - p0 + 128, byte_of(cur, 1) - p1 + 128, byte_of(cur, 2) - p2 + 128, byte_of(cur, 3) - p3 + 128);
-    }
-    return pack_u8x4(byte_of(cur, 0) + p0 - 128, byte_of(cur, 1) + p1 - 128, byte_of(cur, 2) + p2 - 128, byte_of(cur, 3) + p3 - 128);
+    const unsigned a = cur ^ 0x80808080u, b = pw ^ 0x80808080u;
+    return (mode == 1 ? __vsubss4(a, b) : __vaddss4(a, b)) ^ 0x80808080u;
 }
 
-/* one row of a strip: 16 predicted samples in pw[4] (sample 0 in the lowest byte of pw[0]); n = valid samples */
-DSV_D void bmc_store_row(const BmcPlane &P, int mode, int gx, int gy, int n, bool vec16, const unsigned pw[4])
+/* one row of a strip: 8 predicted samples in pw[2] (sample 0 in the lowest byte of pw[0]); n = valid samples;
+ * cur = the co-located samples of `in` when vec8 (fetched ahead by the caller) */
+DSV_D void bmc_store_row(const BmcPlane &P, int mode, int gx, int gy, int n, bool vec8, uint2 cur, const unsigned pw[2])
 {
-    const size_t io = (size_t) gy * P.istride + gx, oo = (size_t) gy * P.ostride + gx;
-    if (vec16) { /* n == 16 and every row of the three frames 16-byte aligned at gx */
-        const uint4 cur = *reinterpret_cast<const uint4 *>(P.in + io);
-        uint4 o;
-        o.x = bmc_combine4(cur.x, pw[0], mode);
-        o.y = bmc_combine4(cur.y, pw[1], mode);
-        o.z = bmc_combine4(cur.z, pw[2], mode);
-        o.w = bmc_combine4(cur.w, pw[3], mode);
-        *reinterpret_cast<uint4 *>(P.out + oo) = o;
+    const size_t oo = (size_t) gy * P.ostride + gx;
+    if (vec8) { /* n == 8 and every row of the three frames 8-byte aligned at gx */
+        *reinterpret_cast<uint2 *>(P.out + oo) = make_uint2(bmc_combine4(cur.x, pw[0], mode), bmc_combine4(cur.y, pw[1], mode));
         if (P.pred) {
-            *reinterpret_cast<uint4 *>(P.pred + (size_t) gy * P.pstride + gx) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+            *reinterpret_cast<uint2 *>(P.pred + (size_t) gy * P.pstride + gx) = make_uint2(pw[0], pw[1]);
         }
         return;
     }
+    const size_t io = (size_t) gy * P.istride + gx;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < 2; k++) {
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             if (4 * k + e < n) {
                 const int pv = byte_of(pw[k], e);
-                const int cur = P.in[io + 4 * k + e];
-                P.out[oo + 4 * k + e] = mode == 1 ? clamp_u8(cur - pv + 128) : clamp_u8(pv + cur - 128);
+                const int c = P.in[io + 4 * k + e];
+                P.out[oo + 4 * k + e] = mode == 1 ? clamp_u8(c - pv + 128) : clamp_u8(pv + c - 128);
                 if (P.pred) {
                     P.pred[(size_t) gy * P.pstride + gx + 4 * k + e] = (uint8_t) pv;
                 }
@@ -99,12 +102,12 @@ DSV_D void bmc_store_row(const BmcPlane &P, int mode, int gx, int gy, int n, boo
 
 /* intra blocks (bmc.c:255-298): the flagged quadrants become their mean, the others keep the co-located reference
  * already in pw; odd edge blocks: the quadrants do not cover the last row / column (zeroed frame in the reference) */
-DSV_D void bmc_intra_row(unsigned pw[4], const DevMV &mv, unsigned means, int lx, int ly, int cw, int ch)
+DSV_D void bmc_intra_row(unsigned pw[2], const DevMV &mv, unsigned means, int lx, int ly, int cw, int ch)
 {
     const bool whole = mv.submask == 15;
     const int sbw = cw / 2, sbh = ch / 2;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < 2; k++) {
         unsigned w = 0;
 #pragma unroll
         for (int e = 0; e < 4; e++) {
@@ -124,6 +127,43 @@ DSV_D void bmc_intra_row(unsigned pw[4], const DevMV &mv, unsigned means, int lx
     }
 }
 
+/* block / quadrant means of an intra block (avgval, bmc.c:176-190), computed by the strip's own thread: a word holds
+ * the four quadrant means, or the block mean four times for an all-intra block.  Intra blocks are rare (a picture with
+ * more than intra_pct of them is coded as an I picture), so every strip of the block redoing the sums costs less than
+ * a separate pass over all blocks would. */
+DSV_D unsigned bmc_rect_mean(const uint8_t *r0, int rstride, int sw, int sh)
+{
+    if (sw <= 0 || sh <= 0) {
+        return 0u;
+    }
+    unsigned acc = 0;
+    for (int ly = 0; ly < sh; ly++) {
+        const uint8_t *p = r0 + (ptrdiff_t) ly * rstride;
+        int lx = 0;
+        for (; lx + 4 <= sw; lx += 4) {
+            acc = (unsigned) dp4a_us(ld4u(p + lx), 0x01010101u, (int) acc);
+        }
+        if (lx < sw) {
+            acc = (unsigned) dp4a_us(ld4u(p + lx) & (0xffffffffu >> (8 * (4 - (sw - lx)))), 0x01010101u, (int) acc);
+        }
+    }
+    return acc / (unsigned) (sw * sh);
+}
+DSV_D unsigned bmc_intra_means(const BmcPlane &P, const DevMV &mv, int x, int y, int cw, int ch)
+{
+    if (mv.submask == 15) {
+        return bmc_rect_mean(P.ref + (ptrdiff_t) y * P.rstride + x, P.rstride, cw, ch) * 0x01010101u;
+    }
+    const int sbw = cw / 2, sbh = ch / 2;
+    unsigned word = 0;
+    for (int qd = 0; qd < 4; qd++) {
+        if (mv.submask & (1 << qd)) {
+            word |= bmc_rect_mean(P.ref + (ptrdiff_t) (y + (qd >> 1) * sbh) * P.rstride + x + (qd & 1) * sbw, P.rstride, sbw, sbh) << (8 * qd);
+        }
+    }
+    return word;
+}
+
 struct BmcStrip {
     int b;          /* block index */
     int x, y;       /* block origin in the plane */
@@ -132,16 +172,18 @@ struct BmcStrip {
     int n, rows;    /* valid samples per row / rows */
     int px, py;     /* clamped integer reference position of the block */
     int xh, yh;     /* half-pel flags */
-    bool intra, vec16;
+    bool intra, vec8;
     DevMV mv;
 };
 
-template <int R> DSV_D bool bmc_strip_setup(const BmcArgs &a, const int c, const int u, BmcStrip &s)
+/* NOTE: the argument record lives in global memory and the kernel stores through pointers the compiler cannot
+ * tell apart from it, so every field is copied to a local ONCE (P by value, mode, means pointer); reading a.x
+ * in the row loop would be re-fetched from memory after every store. */
+template <int R> DSV_D bool bmc_strip_setup(const BmcArgs &a, const BmcPlane &P, const int c, const int u, BmcStrip &s)
 {
-    const BmcPlane &P = a.pl[c];
     const int sh = c ? a.hs : 0, sv = c ? a.vs : 0;
     const int bw = a.blk_w >> sh, bh = a.blk_h >> sv;
-    const int segs = (bw + 15) >> 4, rgs = (bh + R - 1) / R, upb = segs * rgs;
+    const int segs = (bw + BMC_W - 1) / BMC_W, rgs = (bh + R - 1) / R, upb = segs * rgs;
     if (u >= upb * a.nbh * a.nbv) {
         return false;
     }
@@ -153,12 +195,12 @@ template <int R> DSV_D bool bmc_strip_setup(const BmcArgs &a, const int c, const
     s.y = j * bh;
     s.cw = (s.x + bw >= P.w) ? P.w - s.x : bw;
     s.ch = (s.y + bh >= P.h) ? P.h - s.y : bh;
-    s.lx = 16 * seg;
+    s.lx = BMC_W * seg;
     s.ly = R * rg;
     if (s.lx >= s.cw || s.ly >= s.ch) {
         return false;
     }
-    s.n = imin(16, s.cw - s.lx);
+    s.n = imin(BMC_W, s.cw - s.lx);
     s.rows = imin(R, s.ch - s.ly);
     s.mv = a.mv[s.b];
     s.intra = s.mv.mode != 0;
@@ -173,7 +215,7 @@ template <int R> DSV_D bool bmc_strip_setup(const BmcArgs &a, const int c, const
     s.yh = dy & 1;
     const uintptr_t al = reinterpret_cast<uintptr_t>(P.in) | reinterpret_cast<uintptr_t>(P.out) | reinterpret_cast<uintptr_t>(P.pred) |
                          (uintptr_t) (unsigned) (P.istride | P.ostride | P.pstride | (s.x + s.lx));
-    s.vec16 = s.n == 16 && (al & 15) == 0;
+    s.vec8 = s.n == BMC_W && (al & 7) == 0;
     return true;
 }
 
@@ -190,14 +232,26 @@ DSV_D void bmc_edge_column(const BmcPlane &P, const BmcStrip &s, int mode)
     }
 }
 
+/* the co-located row of `in` for the 8-byte path (rows past the strip repeat its last row: the load stays valid and
+ * unconditional, so it can be issued rows ahead of its use) */
+DSV_D uint2 bmc_fetch_in(const BmcPlane &P, const BmcStrip &s, int t)
+{
+    if (!s.vec8) {
+        return make_uint2(0u, 0u);
+    }
+    const int gy = s.y + s.ly + imin(t, s.rows - 1);
+    return *reinterpret_cast<const uint2 *>(P.in + (size_t) gy * P.istride + s.x + s.lx);
+}
+
 DSV_D void bmc_luma_strip(const BmcArgs &a, const int u)
 {
+    const BmcPlane P = a.pl[0];
+    const int mode = a.mode;
     BmcStrip s = {};
-    if (!bmc_strip_setup<BMC_RL>(a, 0, u, s)) {
+    if (!bmc_strip_setup<BMC_RL>(a, P, 0, u, s)) {
         return;
     }
-    const BmcPlane &P = a.pl[0];
-    const unsigned means = s.intra ? a.means[s.b] : 0u;
+    const unsigned means = s.intra ? bmc_intra_means(P, s.mv, s.x, s.y, s.cw, s.ch) : 0u;
     /* taps: bytes (p[-1], p[0], p[1], p[2]); pairs (row a, row b) and (row c, row d) */
     const unsigned th = s.xh ? 0xff0909ffu : 0x00001000u;
     const unsigned t_ab = s.yh ? 0x09ffu : 0x1000u, t_cd = s.yh ? 0xff09u : 0x0000u;
@@ -207,75 +261,93 @@ DSV_D void bmc_luma_strip(const BmcArgs &a, const int u)
     const unsigned bsh = ((unsigned) reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
     const unsigned *q = reinterpret_cast<const unsigned *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t) 3);
     const int qs = rs >> 2; /* strides are multiples of 16 */
+    const int last = s.rows + 2; /* last reference row this strip needs; later rows repeat it (loads stay in bounds) */
 
-    int hprev[16];
-    unsigned pr0[16], pr1[16]; /* vertical pairs (row r-3, r-2) and (row r-2, r-1) of 16-bit H results */
+    /* reference rows travel through a ring of BMC_PF raw rows (bytes p[-1..10] = 4 aligned words), the rows of `in`
+     * through a ring of 3: enough loads in flight per thread to cover the memory latency at 2-3 CTAs per SM */
+    unsigned raw[BMC_PF][4];
 #pragma unroll
-    for (int e = 0; e < 16; e++) {
+    for (int d = 0; d < BMC_PF; d++) {
+        const unsigned *qr = q + (ptrdiff_t) imin(d, last) * qs;
+        raw[d][0] = qr[0], raw[d][1] = qr[1], raw[d][2] = qr[2], raw[d][3] = qr[3];
+    }
+    uint2 cur[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        cur[d] = bmc_fetch_in(P, s, d);
+    }
+    int hprev[BMC_W];
+    unsigned pr0[BMC_W], pr1[BMC_W]; /* vertical pairs (row r-3, r-2) and (row r-2, r-1) of 16-bit H results */
+#pragma unroll
+    for (int e = 0; e < BMC_W; e++) {
         hprev[e] = 0;
         pr0[e] = pr1[e] = 0;
     }
 #pragma unroll
     for (int r = 0; r < BMC_RL + 3; r++) {
-        if (r >= s.rows + 3) {
-            break;
+        const unsigned w0 = raw[r % BMC_PF][0], w1 = raw[r % BMC_PF][1], w2 = raw[r % BMC_PF][2], w3 = raw[r % BMC_PF][3];
+        if (r + BMC_PF < BMC_RL + 3) {
+            const unsigned *qr = q + (ptrdiff_t) imin(r + BMC_PF, last) * qs;
+            raw[r % BMC_PF][0] = qr[0], raw[r % BMC_PF][1] = qr[1], raw[r % BMC_PF][2] = qr[2], raw[r % BMC_PF][3] = qr[3];
         }
-        {
-            const unsigned *qr = q + (ptrdiff_t) r * qs;
-            const unsigned w0 = qr[0], w1 = qr[1], w2 = qr[2], w3 = qr[3], w4 = qr[4], w5 = qr[5];
-            unsigned v[5];
-            v[0] = __funnelshift_r(w0, w1, bsh);
-            v[1] = __funnelshift_r(w1, w2, bsh);
-            v[2] = __funnelshift_r(w2, w3, bsh);
-            v[3] = __funnelshift_r(w3, w4, bsh);
-            v[4] = __funnelshift_r(w4, w5, bsh);
-            int h[16];
+        unsigned v[3];
+        v[0] = __funnelshift_r(w0, w1, bsh);
+        v[1] = __funnelshift_r(w1, w2, bsh);
+        v[2] = __funnelshift_r(w2, w3, bsh);
+        int h[BMC_W];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                h[4 * k + 0] = dp4a_us(v[k], th, 0);
-                h[4 * k + 1] = dp4a_us(__funnelshift_r(v[k], v[k + 1], 8), th, 0);
-                h[4 * k + 2] = dp4a_us(__funnelshift_r(v[k], v[k + 1], 16), th, 0);
-                h[4 * k + 3] = dp4a_us(__funnelshift_r(v[k], v[k + 1], 24), th, 0);
+        for (int k = 0; k < 2; k++) {
+            h[4 * k + 0] = dp4a_us(v[k], th, 0);
+            h[4 * k + 1] = dp4a_us(__funnelshift_r(v[k], v[k + 1], 8), th, 0);
+            h[4 * k + 2] = dp4a_us(__funnelshift_r(v[k], v[k + 1], 16), th, 0);
+            h[4 * k + 3] = dp4a_us(__funnelshift_r(v[k], v[k + 1], 24), th, 0);
+        }
+        unsigned pr2[BMC_W]; /* pair (row r-1, row r) */
+#pragma unroll
+        for (int e = 0; e < BMC_W; e++) {
+            pr2[e] = __byte_perm((unsigned) hprev[e], (unsigned) h[e], 0x5410);
+            hprev[e] = h[e];
+        }
+        if (r >= 3) { /* output row r-3: rows a,b = pair (r-3, r-2), rows c,d = pair (r-1, r) */
+            const int t = r - 3;
+            unsigned pw[2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int v0 = dp2a_lo_s16(pr2[4 * k + 0], t_cd, dp2a_lo_s16(pr0[4 * k + 0], t_ab, 128)) >> 8;
+                const int v1 = dp2a_lo_s16(pr2[4 * k + 1], t_cd, dp2a_lo_s16(pr0[4 * k + 1], t_ab, 128)) >> 8;
+                const int v2 = dp2a_lo_s16(pr2[4 * k + 2], t_cd, dp2a_lo_s16(pr0[4 * k + 2], t_ab, 128)) >> 8;
+                const int v3 = dp2a_lo_s16(pr2[4 * k + 3], t_cd, dp2a_lo_s16(pr0[4 * k + 3], t_ab, 128)) >> 8;
+                pw[k] = pack_u8x4(v0, v1, v2, v3);
             }
-            unsigned pr2[16]; /* pair (row r-1, row r) */
-#pragma unroll
-            for (int e = 0; e < 16; e++) {
-                pr2[e] = __byte_perm((unsigned) hprev[e], (unsigned) h[e], 0x5410);
-                hprev[e] = h[e];
+            const uint2 c = cur[t % 3];
+            if (t + 3 < BMC_RL) {
+                cur[t % 3] = bmc_fetch_in(P, s, t + 3);
             }
-            if (r >= 3) { /* output row r-3: rows a,b = pair (r-3, r-2), rows c,d = pair (r-1, r) */
-                unsigned pw[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int v0 = dp2a_lo_s16(pr2[4 * k + 0], t_cd, dp2a_lo_s16(pr0[4 * k + 0], t_ab, 128)) >> 8;
-                    const int v1 = dp2a_lo_s16(pr2[4 * k + 1], t_cd, dp2a_lo_s16(pr0[4 * k + 1], t_ab, 128)) >> 8;
-                    const int v2 = dp2a_lo_s16(pr2[4 * k + 2], t_cd, dp2a_lo_s16(pr0[4 * k + 2], t_ab, 128)) >> 8;
-                    const int v3 = dp2a_lo_s16(pr2[4 * k + 3], t_cd, dp2a_lo_s16(pr0[4 * k + 3], t_ab, 128)) >> 8;
-                    pw[k] = pack_u8x4(v0, v1, v2, v3);
-                }
+            if (t < s.rows) {
                 if (s.intra) {
-                    bmc_intra_row(pw, s.mv, means, s.lx, s.ly + r - 3, s.cw, s.ch);
+                    bmc_intra_row(pw, s.mv, means, s.lx, s.ly + t, s.cw, s.ch);
                 }
-                bmc_store_row(P, a.mode, s.x + s.lx, s.y + s.ly + r - 3, s.n, s.vec16, pw);
+                bmc_store_row(P, mode, s.x + s.lx, s.y + s.ly + t, s.n, s.vec8, c, pw);
             }
+        }
 #pragma unroll
-            for (int e = 0; e < 16; e++) {
-                pr0[e] = pr1[e];
-                pr1[e] = pr2[e];
-            }
+        for (int e = 0; e < BMC_W; e++) {
+            pr0[e] = pr1[e];
+            pr1[e] = pr2[e];
         }
     }
-    bmc_edge_column(P, s, a.mode);
+    bmc_edge_column(P, s, mode);
 }
 
 DSV_D void bmc_chroma_strip(const BmcArgs &a, const int c, const int u)
 {
+    const BmcPlane P = a.pl[c];
+    const int mode = a.mode;
     BmcStrip s = {};
-    if (!bmc_strip_setup<BMC_RC>(a, c, u, s)) {
+    if (!bmc_strip_setup<BMC_RC>(a, P, c, u, s)) {
         return;
     }
-    const BmcPlane &P = a.pl[c];
-    const unsigned means = s.intra ? a.means[(size_t) c * a.nbh * a.nbv + s.b] : 0u;
+    const unsigned means = s.intra ? bmc_intra_means(P, s.mv, s.x, s.y, s.cw, s.ch) : 0u;
     /* weights for (p[0], p[1], p[rs], p[rs + 1]) */
     const unsigned wt = s.xh ? (s.yh ? 0x01010101u : 0x00000202u) : (s.yh ? 0x00020002u : 0x00000004u);
     const int rs = P.rstride;
@@ -283,60 +355,75 @@ DSV_D void bmc_chroma_strip(const BmcArgs &a, const int c, const int u)
     const unsigned bsh = ((unsigned) reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
     const unsigned *q = reinterpret_cast<const unsigned *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t) 3);
     const int qs = rs >> 2;
+    const int last = s.rows;
 
-    unsigned top[16]; /* (p[e], p[e + 1]) of the row above in the two low bytes */
+    unsigned raw[BMC_PF][3]; /* bytes p[0..8] */
 #pragma unroll
-    for (int e = 0; e < 16; e++) {
+    for (int d = 0; d < BMC_PF; d++) {
+        const unsigned *qr = q + (ptrdiff_t) imin(d, last) * qs;
+        raw[d][0] = qr[0], raw[d][1] = qr[1], raw[d][2] = qr[2];
+    }
+    uint2 cur[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        cur[d] = bmc_fetch_in(P, s, d);
+    }
+    unsigned top[BMC_W]; /* (p[e], p[e + 1]) of the row above in the two low bytes */
+#pragma unroll
+    for (int e = 0; e < BMC_W; e++) {
         top[e] = 0;
     }
 #pragma unroll
     for (int r = 0; r < BMC_RC + 1; r++) {
-        if (r >= s.rows + 1) {
-            break;
+        const unsigned w0 = raw[r % BMC_PF][0], w1 = raw[r % BMC_PF][1], w2 = raw[r % BMC_PF][2];
+        if (r + BMC_PF < BMC_RC + 1) {
+            const unsigned *qr = q + (ptrdiff_t) imin(r + BMC_PF, last) * qs;
+            raw[r % BMC_PF][0] = qr[0], raw[r % BMC_PF][1] = qr[1], raw[r % BMC_PF][2] = qr[2];
         }
-        {
-            const unsigned *qr = q + (ptrdiff_t) r * qs;
-            const unsigned w0 = qr[0], w1 = qr[1], w2 = qr[2], w3 = qr[3], w4 = qr[4];
-            unsigned v[5];
-            v[0] = __funnelshift_r(w0, w1, bsh);
-            v[1] = __funnelshift_r(w1, w2, bsh);
-            v[2] = __funnelshift_r(w2, w3, bsh);
-            v[3] = __funnelshift_r(w3, w4, bsh);
-            v[4] = w4 >> bsh; /* only sample 16 is needed */
-            unsigned cur[16];
+        unsigned v[3];
+        v[0] = __funnelshift_r(w0, w1, bsh);
+        v[1] = __funnelshift_r(w1, w2, bsh);
+        v[2] = w2 >> bsh; /* only sample 8 is needed */
+        unsigned row[BMC_W];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                cur[4 * k + 0] = v[k];
-                cur[4 * k + 1] = __funnelshift_r(v[k], v[k + 1], 8);
-                cur[4 * k + 2] = __funnelshift_r(v[k], v[k + 1], 16);
-                cur[4 * k + 3] = __funnelshift_r(v[k], v[k + 1], 24);
+        for (int k = 0; k < 2; k++) {
+            row[4 * k + 0] = v[k];
+            row[4 * k + 1] = __funnelshift_r(v[k], v[k + 1], 8);
+            row[4 * k + 2] = __funnelshift_r(v[k], v[k + 1], 16);
+            row[4 * k + 3] = __funnelshift_r(v[k], v[k + 1], 24);
+        }
+        if (r >= 1) {
+            const int t = r - 1;
+            unsigned pw[2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int v0 = dp4a_us(__byte_perm(top[4 * k + 0], row[4 * k + 0], 0x5410), wt, 2) >> 2;
+                const int v1 = dp4a_us(__byte_perm(top[4 * k + 1], row[4 * k + 1], 0x5410), wt, 2) >> 2;
+                const int v2 = dp4a_us(__byte_perm(top[4 * k + 2], row[4 * k + 2], 0x5410), wt, 2) >> 2;
+                const int v3 = dp4a_us(__byte_perm(top[4 * k + 3], row[4 * k + 3], 0x5410), wt, 2) >> 2;
+                pw[k] = pack_u8x4(v0, v1, v2, v3);
             }
-            if (r >= 1) {
-                unsigned pw[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int v0 = dp4a_us(__byte_perm(top[4 * k + 0], cur[4 * k + 0], 0x5410), wt, 2) >> 2;
-                    const int v1 = dp4a_us(__byte_perm(top[4 * k + 1], cur[4 * k + 1], 0x5410), wt, 2) >> 2;
-                    const int v2 = dp4a_us(__byte_perm(top[4 * k + 2], cur[4 * k + 2], 0x5410), wt, 2) >> 2;
-                    const int v3 = dp4a_us(__byte_perm(top[4 * k + 3], cur[4 * k + 3], 0x5410), wt, 2) >> 2;
-                    pw[k] = pack_u8x4(v0, v1, v2, v3);
-                }
+            const uint2 cc = cur[t % 3];
+            if (t + 3 < BMC_RC) {
+                cur[t % 3] = bmc_fetch_in(P, s, t + 3);
+            }
+            if (t < s.rows) {
                 if (s.intra) {
-                    bmc_intra_row(pw, s.mv, means, s.lx, s.ly + r - 1, s.cw, s.ch);
+                    bmc_intra_row(pw, s.mv, means, s.lx, s.ly + t, s.cw, s.ch);
                 }
-                bmc_store_row(P, a.mode, s.x + s.lx, s.y + s.ly + r - 1, s.n, s.vec16, pw);
+                bmc_store_row(P, mode, s.x + s.lx, s.y + s.ly + t, s.n, s.vec8, cc, pw);
             }
+        }
 #pragma unroll
-            for (int e = 0; e < 16; e++) {
-                top[e] = cur[e];
-            }
+        for (int e = 0; e < BMC_W; e++) {
+            top[e] = row[e];
         }
     }
-    bmc_edge_column(P, s, a.mode);
+    bmc_edge_column(P, s, mode);
 }
 
 /* grid.x = [luma strips | U strips | V strips] in CTAs of BMC_THREADS strips, grid.y = lane */
-__global__ void __launch_bounds__(BMC_THREADS, 2) bmc_kernel(const BmcArgs *args, int ctas_l, int ctas_c)
+__global__ void __launch_bounds__(BMC_THREADS, BMC_MINB) bmc_kernel(const BmcArgs *args, int ctas_l, int ctas_c)
 {
     const BmcArgs &a = args[blockIdx.y];
     int cta = blockIdx.x;
@@ -352,56 +439,7 @@ __global__ void __launch_bounds__(BMC_THREADS, 2) bmc_kernel(const BmcArgs *args
     bmc_chroma_strip(a, c, cta * BMC_THREADS + threadIdx.x);
 }
 
-/* means of the intra blocks: one warp per block, planes in turn; a word per (plane, block) holds the four quadrant
- * means (avgval, bmc.c:176-190), or the block mean four times for an all-intra block */
-__global__ void __launch_bounds__(BMC_THREADS) bmc_means_kernel(const BmcArgs *args)
-{
-    const BmcArgs &a = args[blockIdx.y];
-    const int nblk = a.nbh * a.nbv;
-    const int b = blockIdx.x * (BMC_THREADS / 32) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (b >= nblk) {
-        return;
-    }
-    const DevMV mv = a.mv[b];
-    if (mv.mode == 0) {
-        return;
-    }
-    const int j = b / a.nbh, i = b - j * a.nbh;
-    for (int c = 0; c < 3; c++) {
-        const BmcPlane &P = a.pl[c];
-        const int sh = c ? a.hs : 0, sv = c ? a.vs : 0;
-        const int bw = a.blk_w >> sh, bh = a.blk_h >> sv;
-        const int x = i * bw, y = j * bh;
-        const int cw = (x + bw >= P.w) ? P.w - x : bw;
-        const int ch = (y + bh >= P.h) ? P.h - y : bh;
-        const bool whole = mv.submask == 15;
-        const int sbw = whole ? cw : cw / 2, sbh = whole ? ch : ch / 2;
-        unsigned word = 0;
-        for (int qd = 0; qd < (whole ? 1 : 4); qd++) {
-            unsigned acc = 0;
-            if (whole || (mv.submask & (1 << qd))) {
-                const uint8_t *r0 = P.ref + (ptrdiff_t) (y + (qd >> 1) * sbh) * P.rstride + x + (qd & 1) * sbw;
-                for (int ly = 0; ly < sbh; ly++) {
-                    for (int lx = lane; lx < sbw; lx += 32) {
-                        acc += r0[(ptrdiff_t) ly * P.rstride + lx];
-                    }
-                }
-            }
-            acc = __reduce_add_sync(0xffffffffu, acc);
-            const unsigned m = (sbw > 0 && sbh > 0) ? acc / (unsigned) (sbw * sbh) : 0u;
-            word |= m << (8 * qd);
-        }
-        if (whole) {
-            word *= 0x01010101u;
-        }
-        if (lane == 0 && cw > 0 && ch > 0) {
-            a.means[(size_t) c * nblk + b] = word;
-        }
-    }
-}
-
-void bmc_fill_args(BmcArgs *a, const MotionGeom &g, const DevMV *d_mv, uint32_t *d_means, const DevFrame &ref, const DevFrame *pred,
+void bmc_fill_args(BmcArgs *a, const MotionGeom &g, const DevMV *d_mv, const DevFrame &ref, const DevFrame *pred,
                    const DevFrame &in, const DevFrame &out, int mode)
 {
     for (int c = 0; c < 3; c++) {
@@ -417,7 +455,6 @@ void bmc_fill_args(BmcArgs *a, const MotionGeom &g, const DevMV *d_mv, uint32_t 
         a->pl[c].h = out.h[c];
     }
     a->mv = d_mv;
-    a->means = d_means;
     a->blk_w = g.blk_w;
     a->blk_h = g.blk_h;
     a->nbh = g.nbh;
@@ -429,7 +466,7 @@ void bmc_fill_args(BmcArgs *a, const MotionGeom &g, const DevMV *d_mv, uint32_t 
 
 static int bmc_ctas(int bw, int bh, int rows, int nblk)
 {
-    const long long units = (long long) ((bw + 15) >> 4) * ((bh + rows - 1) / rows) * nblk;
+    const long long units = (long long) ((bw + BMC_W - 1) / BMC_W) * ((bh + rows - 1) / rows) * nblk;
     return (int) ((units + BMC_THREADS - 1) / BMC_THREADS);
 }
 
@@ -441,8 +478,6 @@ void bmc_launch(const BmcArgs *d_args, int n, const MotionGeom &g, cudaStream_t 
     const int nblk = g.nbh * g.nbv;
     const int ctas_l = bmc_ctas(g.blk_w, g.blk_h, BMC_RL, nblk);
     const int ctas_c = bmc_ctas(g.blk_w >> g.hs, g.blk_h >> g.vs, BMC_RC, nblk);
-    DSV_LAUNCH(bmc_means_kernel, dim3((nblk + BMC_THREADS / 32 - 1) / (BMC_THREADS / 32), n), dim3(BMC_THREADS), 0, st, d_args);
-    KERNEL_CHECK();
     DSV_LAUNCH(bmc_kernel, dim3(ctas_l + 2 * ctas_c, n), dim3(BMC_THREADS), 0, st, d_args, ctas_l, ctas_c);
     KERNEL_CHECK();
 }

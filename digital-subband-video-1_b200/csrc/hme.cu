@@ -24,70 +24,93 @@
 
 namespace dsv {
 
-#define HME_THREADS 256
+#define HME_WARPS 4 /* blocks per CTA: one warp each, no block-wide barrier anywhere */
+#define HME_THREADS (32 * HME_WARPS)
 #define HME_SRC_STRIDE 64 /* bytes per staged block row */
 #define HP_SAD_SZ 14
 #define HP_DIM 16
 #define HP_STRIDE 32
 
+/* per-warp shared memory of the search: the staged source block and the candidate list */
+struct HmeSearchSmem {
+    uint8_t src[64 * HME_SRC_STRIDE];
+    int cx[8], cy[8], valid[8];
+    int n;
+};
+/* level 0 adds the half-pel image of the 16x16 reference patch */
+struct HmeL0Smem {
+    HmeSearchSmem s;
+    int16_t hbuf[(HP_DIM + 4) * HP_DIM];
+    uint8_t tmp[HP_STRIDE * HP_STRIDE];
+    uint8_t refblk[HP_SAD_SZ * HP_SAD_SZ + 12];
+};
 
-/* block-wide sums of N per-thread values; every thread gets all totals.  scratch: >= 9 * N words.
- * Stage 1: one REDUX per value per warp; stage 2: thread k adds the warp partials of value k. */
-template <int N> DSV_D void block_reduce_n(unsigned (&acc)[N], unsigned *scratch)
+/* A block's words are dealt to the warp as (word column, row group): lanes_per_row = the power of two >= words,
+ * 32 / lanes_per_row row groups of consecutive rows.  A lane keeps its word column and walks its rows top to
+ * bottom, so vertically adjacent data slides through registers and the 9-point search loads every reference row
+ * once instead of three times. */
+struct BlockGeom {
+    int bx, by, bw, bh, words;
+    unsigned tail_mask;
+    int wx, r0, r1, rpg; /* this lane: word column, rows [r0, r1), rows per group (uniform trip count) */
+    bool active;         /* wx < words */
+    unsigned m;          /* byte mask of this lane's word (the block's last word column may be partial) */
+};
+
+template <int N> DSV_D void warp_reduce_n(unsigned (&acc)[N])
 {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
     for (int k = 0; k < N; k++) {
         acc[k] = __reduce_add_sync(0xffffffffu, acc[k]);
     }
-    __syncthreads();
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < N; k++) {
-            scratch[wid * N + k] = acc[k];
-        }
-    }
-    __syncthreads();
-    if ((int) threadIdx.x < N) {
-        unsigned t = 0;
-        for (int w = 0; w < nw; w++) {
-            t += scratch[w * N + threadIdx.x];
-        }
-        scratch[8 * N + threadIdx.x] = t;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < N; k++) {
-        acc[k] = scratch[8 * N + k];
-    }
 }
 
-struct BlockGeom {
-    int bx, by, bw, bh, words;
-    int wmag; /* (idx * wmag) >> 20 == idx / words for idx < 1024 (a block has at most 16 x 64 words) */
-    unsigned tail_mask;
-};
+/* stage the source block (bytes past bw zero) and deal the words to the lanes; false: the block lies outside */
+DSV_D bool block_setup(const HmeArgs &A, int i, int j, BlockGeom &G, uint8_t *s_src, int lane)
+{
+    G.bx = (i * A.blk_w) >> A.level;
+    G.by = (j * A.blk_h) >> A.level;
+    if (G.bx >= A.src.w || G.by >= A.src.h) {
+        return false;
+    }
+    G.bw = imin(A.src.w - G.bx, A.blk_w);
+    G.bh = imin(A.src.h - G.by, A.blk_h);
+    G.words = (G.bw + 3) >> 2;
+    const int tail = G.bw & 3;
+    G.tail_mask = tail ? ((1u << (8 * tail)) - 1u) : 0xffffffffu;
+    const int lg = G.words <= 1 ? 0 : 32 - __clz(G.words - 1);
+    const int rgs = 32 >> lg;
+    G.rpg = (G.bh + rgs - 1) / rgs;
+    G.wx = lane & ((1 << lg) - 1);
+    G.active = G.wx < G.words;
+    G.r0 = imin(G.bh, (lane >> lg) * G.rpg);
+    G.r1 = G.active ? imin(G.bh, G.r0 + G.rpg) : G.r0;
+    G.m = (G.wx == G.words - 1) ? G.tail_mask : 0xffffffffu;
+    const uint8_t *p = A.src.p + (ptrdiff_t) (G.by + G.r0) * A.src.stride + G.bx + 4 * G.wx;
+    for (int r = G.r0; r < G.r1; r++, p += A.src.stride) {
+        *reinterpret_cast<unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * G.wx) = ld4u(p) & G.m;
+    }
+    __syncwarp();
+    return true;
+}
 
 /*
- * Candidate selection + 9-point full-pel search (hme.c:439-541).  Every thread of the block calls;
- * the result (full-pel dx, dy at this level and the winning SAD) is returned to all threads.
- * s_src: staged source block (HME_SRC_STRIDE bytes per row, bytes past bw zero).
+ * Candidate selection + 9-point full-pel search (hme.c:439-541).  Every lane of the warp calls;
+ * the result (full-pel dx, dy at this level and the winning SAD) is returned to all lanes.
  */
-DSV_D void search_block(const HmeArgs &A, int i, int j, const BlockGeom &G, const uint8_t *s_src, unsigned *scratch,
-                        int *s_res, int &odx, int &ody, int &obest)
+DSV_D void search_block(const HmeArgs &A, int i, int j, const BlockGeom &G, HmeSearchSmem &S, int lane, int &odx, int &ody, int &obest)
 {
-    __shared__ int s_cx[8], s_cy[8], s_valid[8], s_n;
-    const int tid = threadIdx.x, nthr = blockDim.x;
     const int level = A.level;
     const int W = A.ref.w, H = A.ref.h;
     const int rs = A.ref.stride;
+    const uint8_t *s_src = S.src;
 
-    if (tid == 0) {
+    if (lane == 0) {
         int n = 0;
         int call[8];
         call[n] = 0;
-        s_cx[n] = 0;
-        s_cy[n] = 0;
+        S.cx[n] = 0;
+        S.cy[n] = 0;
         n++;
         if (A.parent) {
             const int step = 1 << level;
@@ -106,8 +129,8 @@ DSV_D void search_block(const HmeArgs &A, int i, int j, const BlockGeom &G, cons
                         }
                         if (!exists) {
                             call[n] = all;
-                            s_cx[n] = pm.x;
-                            s_cy[n] = pm.y;
+                            S.cx[n] = pm.x;
+                            S.cy[n] = pm.y;
                             n++;
                         }
                     }
@@ -115,56 +138,81 @@ DSV_D void search_block(const HmeArgs &A, int i, int j, const BlockGeom &G, cons
             }
         }
         for (int k = 0; k < n; k++) {
-            const int dx = s_cx[k] >> level, dy = s_cy[k] >> level;
+            const int dx = S.cx[k] >> level, dy = S.cy[k] >> level;
             const int x = G.bx + dx, y = G.by + dy;
-            s_valid[k] = !(x < -DSV_BORDER || y < -DSV_BORDER || x + G.bw > W + DSV_BORDER || y + G.bh > H + DSV_BORDER);
+            S.valid[k] = !(x < -DSV_BORDER || y < -DSV_BORDER || x + G.bw > W + DSV_BORDER || y + G.bh > H + DSV_BORDER);
         }
-        s_n = n;
+        S.n = n;
     }
-    __syncthreads();
-    const int n = s_n;
+    __syncwarp();
+    const int n = S.n;
     int best_k = n - 1;
     if (n > 1) {
         unsigned acc[6] = {0, 0, 0, 0, 0, 0};
-        for (int idx = tid; idx < G.words * G.bh; idx += nthr) {
-            const int r = (idx * G.wmag) >> 20, wx = idx - r * G.words;
-            const unsigned m = (wx == G.words - 1) ? G.tail_mask : 0xffffffffu;
-            const unsigned a = *reinterpret_cast<const unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * wx);
 #pragma unroll
-            for (int k = 0; k < 6; k++) {
-                if (k < n && s_valid[k]) {
-                    const int dx = s_cx[k] >> level, dy = s_cy[k] >> level;
-                    const unsigned b = ld4u(A.ref.p + (ptrdiff_t) (G.by + dy + r) * rs + G.bx + dx + 4 * wx) & m;
-                    acc[k] += __vsadu4(a, b);
+        for (int k = 0; k < 6; k++) {
+            if (k < n && S.valid[k]) {
+                const int dx = S.cx[k] >> level, dy = S.cy[k] >> level;
+                const uint8_t *p = A.ref.p + (ptrdiff_t) (G.by + dy + G.r0) * rs + G.bx + dx + 4 * G.wx;
+                unsigned t = 0;
+                for (int r = G.r0; r < G.r1; r++, p += rs) {
+                    t += __vsadu4(*reinterpret_cast<const unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * G.wx), ld4u(p) & G.m);
                 }
+                acc[k] = t;
             }
         }
-        block_reduce_n<6>(acc, scratch);
+        warp_reduce_n<6>(acc);
         int best_score = 0x7fffffff;
         for (int k = 0; k < n; k++) {
-            if (s_valid[k] && best_score > (int) acc[k]) {
+            if (S.valid[k] && best_score > (int) acc[k]) {
                 best_score = (int) acc[k];
                 best_k = k;
             }
         }
     }
-    int dx = s_cx[best_k] >> level, dy = s_cy[best_k] >> level;
+    int dx = S.cx[best_k] >> level, dy = S.cy[best_k] >> level;
     dx = iclamp(dx, -G.bw - G.bx, W - G.bx);
     dy = iclamp(dy, -G.bh - G.by, H - G.by);
     const int xx = G.bx + dx, yy = G.by + dy;
     const int xf[9] = {0, 1, -1, 0, 0, -1, 1, -1, 1}, yf[9] = {0, 0, 0, 1, -1, -1, -1, 1, 1};
     unsigned acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int idx = tid; idx < G.words * G.bh; idx += nthr) {
-        const int r = (idx * G.wmag) >> 20, wx = idx - r * G.words;
-        const unsigned m = (wx == G.words - 1) ? G.tail_mask : 0xffffffffu;
-        const unsigned a = *reinterpret_cast<const unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * wx);
-        const uint8_t *rp = A.ref.p + (ptrdiff_t) (yy + r) * rs + xx + 4 * wx;
-#pragma unroll
-        for (int k = 0; k < 9; k++) {
-            acc[k] += __vsadu4(a, ld4u(rp + yf[k] * rs + xf[k]) & m);
+    if (G.r1 > G.r0) {
+        /* reference rows r0-1 .. r1 of this lane's word column, each loaded once as bytes [-1, 5) around the word:
+         * the three horizontal candidates are the windows at byte offsets 0, 1, 2; a reference row t meets the
+         * source rows t (yf = 0), t - 1 (yf = +1) and t + 1 (yf = -1) */
+        const uint8_t *p = A.ref.p + (ptrdiff_t) (yy + G.r0 - 1) * rs + xx + 4 * G.wx - 1;
+        const unsigned *q = reinterpret_cast<const unsigned *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t) 3);
+        const unsigned bsh = ((unsigned) reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
+        const int qs = rs >> 2;
+        const uint8_t *sp = s_src + 4 * G.wx;
+        unsigned s_prev = 0, s_cur = 0, s_next = *reinterpret_cast<const unsigned *>(sp + G.r0 * HME_SRC_STRIDE);
+        for (int t = G.r0 - 1; t <= G.r1; t++, q += qs) {
+            s_prev = s_cur;
+            s_cur = s_next;
+            if (t + 1 < G.r1) {
+                s_next = *reinterpret_cast<const unsigned *>(sp + (t + 1) * HME_SRC_STRIDE);
+            }
+            const unsigned q0 = q[0], q1 = q[1], q2 = q[2];
+            const unsigned lo = __funnelshift_r(q0, q1, bsh), hi = __funnelshift_r(q1, q2, bsh);
+            const unsigned ra = lo & G.m, rb = __funnelshift_r(lo, hi, 8) & G.m, rc = __funnelshift_r(lo, hi, 16) & G.m;
+            if (t >= G.r0 && t < G.r1) {
+                acc[2] += __vsadu4(s_cur, ra);
+                acc[0] += __vsadu4(s_cur, rb);
+                acc[1] += __vsadu4(s_cur, rc);
+            }
+            if (t > G.r0) { /* source row t - 1 */
+                acc[7] += __vsadu4(s_prev, ra);
+                acc[3] += __vsadu4(s_prev, rb);
+                acc[8] += __vsadu4(s_prev, rc);
+            }
+            if (t + 1 < G.r1) { /* source row t + 1 */
+                acc[5] += __vsadu4(s_next, ra);
+                acc[4] += __vsadu4(s_next, rb);
+                acc[6] += __vsadu4(s_next, rc);
+            }
         }
     }
-    block_reduce_n<9>(acc, scratch);
+    warp_reduce_n<9>(acc);
     int best = 0x7fffffff, m = 0;
 #pragma unroll
     for (int k = 0; k < 9; k++) {
@@ -176,31 +224,7 @@ DSV_D void search_block(const HmeArgs &A, int i, int j, const BlockGeom &G, cons
     odx = dx + xf[m];
     ody = dy + yf[m];
     obest = best;
-    (void) s_res;
-    __syncthreads();
-}
-
-DSV_D bool block_setup(const HmeArgs &A, int i, int j, BlockGeom &G, uint8_t *s_src)
-{
-    G.bx = (i * A.blk_w) >> A.level;
-    G.by = (j * A.blk_h) >> A.level;
-    if (G.bx >= A.src.w || G.by >= A.src.h) {
-        return false;
-    }
-    G.bw = imin(A.src.w - G.bx, A.blk_w);
-    G.bh = imin(A.src.h - G.by, A.blk_h);
-    G.words = (G.bw + 3) >> 2;
-    G.wmag = magic20(G.words);
-    const int tail = G.bw & 3;
-    G.tail_mask = tail ? ((1u << (8 * tail)) - 1u) : 0xffffffffu;
-    for (int idx = threadIdx.x; idx < G.words * G.bh; idx += blockDim.x) {
-        const int r = (idx * G.wmag) >> 20, wx = idx - r * G.words;
-        const unsigned m = (wx == G.words - 1) ? G.tail_mask : 0xffffffffu;
-        *reinterpret_cast<unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * wx) =
-            ld4u(A.src.p + (ptrdiff_t) (G.by + r) * A.src.stride + G.bx + 4 * wx) & m;
-    }
-    __syncthreads();
-    return true;
+    (void) yf;
 }
 
 DSV_D void store_mv(DevMV *dst, int x, int y, int mode, int submask, int lo_var, int lo_tex)
@@ -217,26 +241,29 @@ DSV_D void store_mv(DevMV *dst, int x, int y, int mode, int submask, int lo_var,
     *dst = m;
 }
 
-#ifndef HME_LV_MINB
-#define HME_LV_MINB 8 /* measured: 8 -> 24.1 us, default -> 26.5, 5 -> 28.7 */
-#endif
-__global__ void __launch_bounds__(HME_THREADS, HME_LV_MINB) hme_level_kernel(const HmeArgs *args)
+__global__ void __launch_bounds__(HME_THREADS) hme_level_kernel(const HmeArgs *args, int nbx, int nby)
 {
     const HmeArgs &A = args[blockIdx.z];
-    __shared__ __align__(16) uint8_t s_src[64 * HME_SRC_STRIDE];
-    __shared__ unsigned scratch[9 * 9];
+    __shared__ __align__(16) HmeSearchSmem smem[HME_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wb = (int) blockIdx.x * HME_WARPS + warp;
+    if (wb >= nbx * nby) {
+        return;
+    }
     const int step = 1 << A.level;
-    const int i = (int) blockIdx.x * step, j = (int) blockIdx.y * step;
+    const int bj = wb / nbx;
+    const int i = (wb - bj * nbx) * step, j = bj * step;
+    HmeSearchSmem &S = smem[warp];
     BlockGeom G;
-    if (!block_setup(A, i, j, G, s_src)) {
-        if (threadIdx.x == 0) {
+    if (!block_setup(A, i, j, G, S.src, lane)) {
+        if (lane == 0) {
             store_mv(&A.out[i + j * A.nbh], 0, 0, 0, 0, 0, 0);
         }
         return;
     }
     int dx, dy, best;
-    search_block(A, i, j, G, s_src, scratch, nullptr, dx, dy, best);
-    if (threadIdx.x == 0) {
+    search_block(A, i, j, G, S, lane, dx, dy, best);
+    if (lane == 0) {
         store_mv(&A.out[i + j * A.nbh], dx << A.level, dy << A.level, 0, 0, 0, 0);
     }
 }
@@ -252,32 +279,53 @@ enum {
     SUM_COUNT
 };
 
-#ifndef HME_L0_MINB
-#define HME_L0_MINB 6 /* CTAs per SM, measured per 32 HD pictures: 6 -> 709 us, 5 -> 721, 4 (compiler default) -> 757, 3 -> 823 */
-#endif
-__global__ void __launch_bounds__(HME_THREADS, HME_L0_MINB) hme_l0_kernel(const HmeArgs *args)
+/* sum and sum of squares of a cw x ch byte rectangle, by one warp, into acc[0] / acc[1] (c_maxvar's inputs) */
+DSV_D void warp_rect_moments(const uint8_t *p0, int stride, int cw, int ch, int lane, unsigned &s1, unsigned &s2)
+{
+    if ((cw & 3) == 0) { /* words: lanes over (row, word) pairs */
+        const int wpr = cw >> 2;
+        for (int idx = lane; idx < wpr * ch; idx += 32) {
+            const int ly = idx / wpr, wx = idx - ly * wpr;
+            const unsigned w = ld4u(p0 + (ptrdiff_t) ly * stride + 4 * wx);
+            s1 += __vsadu4(w, 0u);
+            s2 = __dp4a(w, w, s2);
+        }
+        return;
+    }
+    for (int ly = 0; ly < ch; ly++) {
+        for (int lx = lane; lx < cw; lx += 32) {
+            const unsigned v = p0[(ptrdiff_t) ly * stride + lx];
+            s1 += v;
+            s2 += v * v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args)
 {
     const HmeArgs &A = args[blockIdx.z];
-    __shared__ __align__(16) uint8_t s_src[64 * HME_SRC_STRIDE];
-    __shared__ __align__(16) uint8_t s_ref0[64 * HME_SRC_STRIDE];
-    __shared__ unsigned scratch[9 * SUM_COUNT];
-    __shared__ int16_t s_hbuf[(HP_DIM + 4) * HP_DIM];
-    __shared__ uint8_t s_tmp[HP_STRIDE * HP_STRIDE];
-    __shared__ uint8_t s_refblk[HP_SAD_SZ * HP_SAD_SZ];
-    __shared__ int s_flag;
-    const int tid = threadIdx.x;
-    const int i = blockIdx.x, j = blockIdx.y;
+    __shared__ __align__(16) HmeL0Smem smem[HME_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wb = (int) blockIdx.x * HME_WARPS + warp;
+    if (wb >= A.nbh * A.nbv) {
+        return;
+    }
+    const int j = wb / A.nbh, i = wb - j * A.nbh;
+    HmeL0Smem &L = smem[warp];
+    uint8_t *s_src = L.s.src;
+    int16_t *s_hbuf = L.hbuf;
+    uint8_t *s_tmp = L.tmp, *s_refblk = L.refblk;
     DevMV *out = &A.out[i + j * A.nbh];
     BlockGeom G;
-    if (!block_setup(A, i, j, G, s_src)) {
-        if (tid == 0) {
+    if (!block_setup(A, i, j, G, s_src, lane)) {
+        if (lane == 0) {
             store_mv(out, 0, 0, 0, 0, 0, 0);
             A.aux[i + j * A.nbh] = make_int2(0, 0);
         }
         return;
     }
     int fx, fy, best;
-    search_block(A, i, j, G, s_src, scratch, nullptr, fx, fy, best);
+    search_block(A, i, j, G, L.s, lane, fx, fy, best);
 
     const int rs = A.ref.stride, ss = A.src.stride;
     const unsigned yarea = (unsigned) (G.bw * G.bh);
@@ -290,35 +338,41 @@ __global__ void __launch_bounds__(HME_THREADS, HME_L0_MINB) hme_l0_kernel(const 
     if (best > A.blk_w * A.blk_h) {
         int best_hp = (int) ((unsigned) (best * (HP_SAD_SZ * HP_SAD_SZ)) / yarea);
         const uint8_t *rp0 = A.ref.p + (ptrdiff_t) (cy + mvy - 1) * rs + (cx + mvx - 1); /* hpel()'s `ref` */
-        for (int k = tid; k < (HP_DIM + 4) * HP_DIM; k += HME_THREADS) {
-            const int jj = k / HP_DIM, ii = k - jj * HP_DIM;
-            const uint8_t *p = rp0 + (ptrdiff_t) (jj - 1) * rs + ii;
-            s_hbuf[k] = (int16_t) (9 * (p[0] + p[1]) - (p[-1] + p[2]));
+        /* H-filtered rows -1 .. 18 of the patch, four columns per lane and step: bytes p[-1..6] of the row */
+        for (int k = lane; k < (HP_DIM + 4) * (HP_DIM / 4); k += 32) {
+            const int jj = k >> 2, i0 = (k & 3) * 4;
+            const uint8_t *p = rp0 + (ptrdiff_t) (jj - 1) * rs + i0 - 1;
+            const unsigned wa = ld4u(p), wb2 = ld4u(p + 4);
+            int16_t *d = s_hbuf + jj * HP_DIM + i0;
+            d[0] = (int16_t) hp_taps_u8x4(wa);
+            d[1] = (int16_t) hp_taps_u8x4(__funnelshift_r(wa, wb2, 8));
+            d[2] = (int16_t) hp_taps_u8x4(__funnelshift_r(wa, wb2, 16));
+            d[3] = (int16_t) hp_taps_u8x4(__funnelshift_r(wa, wb2, 24));
         }
-        __syncthreads();
-        for (int k = tid; k < HP_DIM * HP_DIM; k += HME_THREADS) {
+        __syncwarp();
+        for (int k = lane; k < HP_DIM * HP_DIM; k += 32) {
             const int jj = k / HP_DIM, ii = k - jj * HP_DIM;
             const uint8_t *p = rp0 + (ptrdiff_t) jj * rs + ii;
             uint8_t *d = s_tmp + (2 * jj) * HP_STRIDE + 2 * ii;
+            const int16_t *b = s_hbuf + k;
             d[0] = p[0];
             d[HP_STRIDE] = clamp_u8((9 * (p[0] + p[rs]) - (p[-rs] + p[2 * rs]) + 8) >> 4);
-            d[1] = clamp_u8((9 * (p[0] + p[1]) - (p[-1] + p[2]) + 8) >> 4);
-            const int16_t *b = s_hbuf + k;
+            d[1] = clamp_u8((b[HP_DIM] + 8) >> 4); /* the H filter of this row is hbuf row jj + 1 */
             d[HP_STRIDE + 1] = clamp_u8((9 * (b[HP_DIM] + b[2 * HP_DIM]) - (b[0] + b[3 * HP_DIM]) + 128) >> 8);
         }
-        __syncthreads();
+        __syncwarp();
         const int xh[8] = {1, -1, 0, 0, -1, 1, -1, 1}, yh[8] = {0, 0, 1, -1, -1, -1, 1, 1};
         const uint8_t *tmph = s_tmp + 2 + 2 * HP_STRIDE;
         unsigned acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (tid < HP_SAD_SZ * HP_SAD_SZ) {
-            const int jj = tid / HP_SAD_SZ, ii = tid - jj * HP_SAD_SZ;
+        for (int k = lane; k < HP_SAD_SZ * HP_SAD_SZ; k += 32) {
+            const int jj = k / HP_SAD_SZ, ii = k - jj * HP_SAD_SZ;
             const int sp = A.src.p[(ptrdiff_t) (cy + jj) * ss + cx + ii];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                acc[k] = (unsigned) iabs(sp - (int) tmph[xh[k] + yh[k] * HP_STRIDE + 2 * ii + 2 * HP_STRIDE * jj]);
+            for (int c = 0; c < 8; c++) {
+                acc[c] += (unsigned) iabs(sp - (int) tmph[xh[c] + yh[c] * HP_STRIDE + 2 * ii + 2 * HP_STRIDE * jj]);
             }
         }
-        block_reduce_n<8>(acc, scratch);
+        warp_reduce_n<8>(acc);
         int m = -1;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -332,9 +386,9 @@ __global__ void __launch_bounds__(HME_THREADS, HME_L0_MINB) hme_l0_kernel(const 
         if (m != -1) {
             mvx += xh[m];
             mvy += yh[m];
-            if (tid < HP_SAD_SZ * HP_SAD_SZ) {
-                const int jj = tid / HP_SAD_SZ, ii = tid - jj * HP_SAD_SZ;
-                s_refblk[tid] = tmph[xh[m] + yh[m] * HP_STRIDE + 2 * ii + 2 * HP_STRIDE * jj];
+            for (int k = lane; k < HP_SAD_SZ * HP_SAD_SZ; k += 32) {
+                const int jj = k / HP_SAD_SZ, ii = k - jj * HP_SAD_SZ;
+                s_refblk[k] = tmph[xh[m] + yh[m] * HP_STRIDE + 2 * ii + 2 * HP_STRIDE * jj];
             }
             has_hp = true;
             best = (int) ((unsigned) best_hp * yarea / (unsigned) (HP_SAD_SZ * HP_SAD_SZ));
@@ -343,17 +397,13 @@ __global__ void __launch_bounds__(HME_THREADS, HME_L0_MINB) hme_l0_kernel(const 
         mvx <<= 1;
         mvy <<= 1;
     }
-    if (!has_hp && tid < HP_SAD_SZ * HP_SAD_SZ) {
-        const int jj = tid / HP_SAD_SZ, ii = tid - jj * HP_SAD_SZ;
-        s_refblk[tid] = A.ref.p[(ptrdiff_t) (cy + (mvy >> 1) + jj) * rs + cx + (mvx >> 1) + ii];
+    if (!has_hp) {
+        for (int k = lane; k < HP_SAD_SZ * HP_SAD_SZ; k += 32) {
+            const int jj = k / HP_SAD_SZ, ii = k - jj * HP_SAD_SZ;
+            s_refblk[k] = A.ref.p[(ptrdiff_t) (cy + (mvy >> 1) + jj) * rs + cx + (mvx >> 1) + ii];
+        }
     }
-    /* zero-MV reference block */
-    for (int idx = tid; idx < G.words * G.bh; idx += HME_THREADS) {
-        const int r = (idx * G.wmag) >> 20, wx = idx - r * G.words;
-        *reinterpret_cast<unsigned *>(s_ref0 + r * HME_SRC_STRIDE + 4 * wx) =
-            ld4u(A.ref.p + (ptrdiff_t) (G.by + r) * rs + G.bx + 4 * wx);
-    }
-    __syncthreads();
+    __syncwarp();
 
     /* ---- block sums ---- */
     unsigned sum[SUM_COUNT];
@@ -362,55 +412,67 @@ __global__ void __launch_bounds__(HME_THREADS, HME_L0_MINB) hme_l0_kernel(const 
         sum[k] = 0;
     }
     const int sbw = G.bw / 2, sbh = G.bh / 2;
-    const int lane = tid & 31, wid = tid >> 5;
+    const uint8_t *ref0 = A.ref.p + (ptrdiff_t) G.by * rs + G.bx; /* zero-MV reference block */
     if ((G.bw & 7) == 0) {
         /* four samples per step: the block sums of block_analysis / y_sqrvar / intra_metric are sums of absolute
-         * differences and squares, i.e. __vsadu4 / __dp4a on packed words (the staged rows are 4-byte aligned) */
-        const int words = G.bw >> 2;
+         * differences and squares, i.e. __vsadu4 / __dp4a on packed words.  A lane walks its rows downwards, so the
+         * row above is last step's word; the bytes left / right of a word come from the neighbouring lanes. */
         unsigned good[4] = {0, 0, 0, 0}, evil[4] = {0, 0, 0, 0};
-        for (int idx = tid; idx < G.bh * 16; idx += HME_THREADS) {
-            const int ly = idx >> 4, wx = idx & 15;
-            if (wx >= words) {
-                continue;
+        const int lx0 = 4 * G.wx;
+        const int rbase = G.active ? G.r0 : 0; /* idle lanes walk along (shuffles are warp-wide) */
+        unsigned w_up = 0, r_up = 0;
+        if (G.active && G.r0 > 0 && G.r0 < G.bh) {
+            w_up = *reinterpret_cast<const unsigned *>(s_src + (G.r0 - 1) * HME_SRC_STRIDE + lx0);
+            r_up = ld4u(ref0 + (ptrdiff_t) (G.r0 - 1) * rs + lx0);
+        }
+        for (int it = 0; it < G.rpg; it++) {
+            const int ly = rbase + it;
+            const bool on = G.active && ly < G.r1;
+            unsigned w = 0, r = 0;
+            if (on) {
+                w = *reinterpret_cast<const unsigned *>(s_src + ly * HME_SRC_STRIDE + lx0);
+                r = ld4u(ref0 + (ptrdiff_t) ly * rs + lx0);
             }
-            const int lx0 = 4 * wx;
-            const uint8_t *sp = s_src + ly * HME_SRC_STRIDE + lx0;
-            const uint8_t *rp = s_ref0 + ly * HME_SRC_STRIDE + lx0;
-            const unsigned w = *reinterpret_cast<const unsigned *>(sp), r = *reinterpret_cast<const unsigned *>(rp);
-            const unsigned nxt = lx0 + 4 < G.bw ? (unsigned) sp[4] : (w >> 24);
-            const unsigned wr = (w >> 8) | (nxt << 24);
-            const unsigned up = ly == 0 ? w : *reinterpret_cast<const unsigned *>(sp - HME_SRC_STRIDE);
-            sum[SUM_S] += __vsadu4(w, 0u);
-            sum[SUM_SS] = __dp4a(w, w, sum[SUM_SS]);
-            sum[SUM_SH] += __vsadu4(w, wr);
-            sum[SUM_SV] += __vsadu4(w, up);
-            sum[SUM_RS] += __vsadu4(r, 0u);
-            sum[SUM_RSS] = __dp4a(r, r, sum[SUM_RSS]);
-            if (ly < 2 * sbh) { /* intra_metric on the four quadrants, hme.c:87-134 */
-                const int qxi = lx0 >= sbw, qyi = ly >= sbh;
-                const int qi0 = lx0 - qxi * sbw, qj = ly - qyi * sbh;
-                const unsigned wl = (w << 8) | (qi0 == 0 ? (w & 0xffu) : (unsigned) sp[-1]);
-                const unsigned rl = (r << 8) | (qi0 == 0 ? (r & 0xffu) : (unsigned) rp[-1]);
-                const unsigned ua = qj == 0 ? w : up;
-                const unsigned ub = qj == 0 ? r : *reinterpret_cast<const unsigned *>(rp - HME_SRC_STRIDE);
-                unsigned g = __vsadu4(w, wl) + __vsadu4(w, ua) + __vsadu4(r, rl) + __vsadu4(r, ub);
-                unsigned e = 0;
-                const unsigned d = __vabsdiffu4(w, r);
+            const unsigned w_r = __shfl_down_sync(0xffffffffu, w, 1), w_l = __shfl_up_sync(0xffffffffu, w, 1);
+            const unsigned r_l = __shfl_up_sync(0xffffffffu, r, 1);
+            if (on) {
+                const unsigned nxt = lx0 + 4 < G.bw ? (w_r & 0xffu) : (w >> 24);
+                const unsigned wr = (w >> 8) | (nxt << 24);
+                const unsigned up = ly == 0 ? w : w_up;
+                sum[SUM_S] += __vsadu4(w, 0u);
+                sum[SUM_SS] = __dp4a(w, w, sum[SUM_SS]);
+                sum[SUM_SH] += __vsadu4(w, wr);
+                sum[SUM_SV] += __vsadu4(w, up);
+                sum[SUM_RS] += __vsadu4(r, 0u);
+                sum[SUM_RSS] = __dp4a(r, r, sum[SUM_RSS]);
+                if (ly < 2 * sbh) { /* intra_metric on the four quadrants, hme.c:87-134 */
+                    const int qxi = lx0 >= sbw, qyi = ly >= sbh;
+                    const int qi0 = lx0 - qxi * sbw, qj = ly - qyi * sbh;
+                    const unsigned wl = (w << 8) | (qi0 == 0 ? (w & 0xffu) : (w_l >> 24));
+                    const unsigned rl = (r << 8) | (qi0 == 0 ? (r & 0xffu) : (r_l >> 24));
+                    const unsigned ua = qj == 0 ? w : up;
+                    const unsigned ub = qj == 0 ? r : r_up;
+                    unsigned g = __vsadu4(w, wl) + __vsadu4(w, ua) + __vsadu4(r, rl) + __vsadu4(r, ub);
+                    unsigned e = 0;
+                    const unsigned d = __vabsdiffu4(w, r);
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const unsigned v = (d >> (8 * b)) & 0xffu;
-                    if (v > 2u) {
-                        e += v;
-                    } else {
-                        g += v == 0u ? 192u : (v == 1u ? 128u : 96u);
+                    for (int b = 0; b < 4; b++) {
+                        const unsigned v = (d >> (8 * b)) & 0xffu;
+                        if (v > 2u) {
+                            e += v;
+                        } else {
+                            g += v == 0u ? 192u : (v == 1u ? 128u : 96u);
+                        }
+                    }
+                    const int q = qxi | (qyi << 1);
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        good[t] += q == t ? g : 0u;
+                        evil[t] += q == t ? e : 0u;
                     }
                 }
-                const int q = qxi | (qyi << 1);
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    good[t] += q == t ? g : 0u;
-                    evil[t] += q == t ? e : 0u;
-                }
+                w_up = w;
+                r_up = r;
             }
         }
 #pragma unroll
@@ -418,111 +480,91 @@ __global__ void __launch_bounds__(HME_THREADS, HME_L0_MINB) hme_l0_kernel(const 
             sum[SUM_GOOD0 + t] += good[t];
             sum[SUM_EVIL0 + t] += evil[t];
         }
-    } else
-    /* general widths -- rows go to warps, columns to lanes: the quadrant row is warp-uniform, no per-sample divisions */
-    for (int ly = wid; ly < G.bh; ly += HME_THREADS / 32) {        const int qyi = ly >= sbh;
-        const bool inq_y = ly < 2 * sbh;
-        const int qj = ly - qyi * sbh;
-        unsigned good0 = 0, good1 = 0, evil0 = 0, evil1 = 0;
-        for (int lx = lane; lx < G.bw; lx += 32) {
-            const uint8_t *sp = s_src + ly * HME_SRC_STRIDE + lx;
-            const uint8_t *rp = s_ref0 + ly * HME_SRC_STRIDE + lx;
-            const int pa = sp[0], pb = rp[0];
-            const int right = lx == G.bw - 1 ? pa : sp[1];
-            const int up = ly == 0 ? pa : sp[-HME_SRC_STRIDE];
-            sum[SUM_S] += (unsigned) pa;
-            sum[SUM_SS] += (unsigned) (pa * pa);
-            sum[SUM_SH] += (unsigned) iabs(pa - right);
-            sum[SUM_SV] += (unsigned) iabs(pa - up);
-            sum[SUM_RS] += (unsigned) pb;
-            sum[SUM_RSS] += (unsigned) (pb * pb);
-            if (inq_y && lx < 2 * sbw) { /* intra_metric on the four quadrants, hme.c:87-134 */
-                const int qxi = lx >= sbw;
-                const int qi = lx - qxi * sbw;
-                const int la = qi == 0 ? pa : sp[-1], lb = qi == 0 ? pb : rp[-1];
-                const int ua = qj == 0 ? pa : up, ub = qj == 0 ? pb : rp[-HME_SRC_STRIDE];
-                unsigned good = (unsigned) (iabs(pa - la) + iabs(pa - ua) + iabs(pb - lb) + iabs(pb - ub));
-                unsigned evil = 0;
-                const int dif = iabs(pa - pb);
-                if (dif > 2) {
-                    evil = (unsigned) dif;
-                } else {
-                    good += dif == 0 ? 192u : (dif == 1 ? 128u : 96u);
+    } else {
+        /* general widths (blocks cut by the picture edge): rows in turn, columns to lanes */
+        for (int ly = 0; ly < G.bh; ly++) {
+            const int qyi = ly >= sbh;
+            const bool inq_y = ly < 2 * sbh;
+            const int qj = ly - qyi * sbh;
+            unsigned good0 = 0, good1 = 0, evil0 = 0, evil1 = 0;
+            for (int lx = lane; lx < G.bw; lx += 32) {
+                const uint8_t *sp = s_src + ly * HME_SRC_STRIDE + lx;
+                const uint8_t *rp = ref0 + (ptrdiff_t) ly * rs + lx;
+                const int pa = sp[0], pb = rp[0];
+                const int right = lx == G.bw - 1 ? pa : sp[1];
+                const int up = ly == 0 ? pa : sp[-HME_SRC_STRIDE];
+                sum[SUM_S] += (unsigned) pa;
+                sum[SUM_SS] += (unsigned) (pa * pa);
+                sum[SUM_SH] += (unsigned) iabs(pa - right);
+                sum[SUM_SV] += (unsigned) iabs(pa - up);
+                sum[SUM_RS] += (unsigned) pb;
+                sum[SUM_RSS] += (unsigned) (pb * pb);
+                if (inq_y && lx < 2 * sbw) { /* intra_metric on the four quadrants, hme.c:87-134 */
+                    const int qxi = lx >= sbw;
+                    const int qi = lx - qxi * sbw;
+                    const int la = qi == 0 ? pa : sp[-1], lb = qi == 0 ? pb : rp[-1];
+                    const int ua = qj == 0 ? pa : up, ub = qj == 0 ? pb : rp[-rs];
+                    unsigned good = (unsigned) (iabs(pa - la) + iabs(pa - ua) + iabs(pb - lb) + iabs(pb - ub));
+                    unsigned evil = 0;
+                    const int dif = iabs(pa - pb);
+                    if (dif > 2) {
+                        evil = (unsigned) dif;
+                    } else {
+                        good += dif == 0 ? 192u : (dif == 1 ? 128u : 96u);
+                    }
+                    good0 += qxi ? 0u : good;
+                    good1 += qxi ? good : 0u;
+                    evil0 += qxi ? 0u : evil;
+                    evil1 += qxi ? evil : 0u;
                 }
-                good0 += qxi ? 0u : good;
-                good1 += qxi ? good : 0u;
-                evil0 += qxi ? 0u : evil;
-                evil1 += qxi ? evil : 0u;
             }
-        }
-        if (qyi) {
-            sum[SUM_GOOD2] += good0; sum[SUM_GOOD3] += good1; sum[SUM_EVIL2] += evil0; sum[SUM_EVIL3] += evil1;
-        } else {
-            sum[SUM_GOOD0] += good0; sum[SUM_GOOD1] += good1; sum[SUM_EVIL0] += evil0; sum[SUM_EVIL1] += evil1;
+            if (qyi) {
+                sum[SUM_GOOD2] += good0; sum[SUM_GOOD3] += good1; sum[SUM_EVIL2] += evil0; sum[SUM_EVIL3] += evil1;
+            } else {
+                sum[SUM_GOOD0] += good0; sum[SUM_GOOD1] += good1; sum[SUM_EVIL0] += evil0; sum[SUM_EVIL1] += evil1;
+            }
         }
     }
     { /* chroma variance inputs, c_maxvar hme.c:270-300 */
         const int cbx = i * (A.blk_w >> A.hs), cby = j * (A.blk_h >> A.vs);
         const int cbw = G.bw >> A.hs, cbh = G.bh >> A.vs;
-        for (int ly = wid; ly < cbh; ly += HME_THREADS / 32) {
-            const uint8_t *su = A.srcU.p + (ptrdiff_t) (cby + ly) * A.srcU.stride + cbx;
-            const uint8_t *sv = A.srcV.p + (ptrdiff_t) (cby + ly) * A.srcV.stride + cbx;
-            const uint8_t *ru = A.refU.p + (ptrdiff_t) (cby + ly) * A.refU.stride + cbx;
-            const uint8_t *rv = A.refV.p + (ptrdiff_t) (cby + ly) * A.refV.stride + cbx;
-            for (int lx = lane; lx < cbw; lx += 32) {
-                unsigned p;
-                p = su[lx];
-                sum[SUM_CSU] += p;
-                sum[SUM_CSSU] += p * p;
-                p = sv[lx];
-                sum[SUM_CSV] += p;
-                sum[SUM_CSSV] += p * p;
-                p = ru[lx];
-                sum[SUM_CRU] += p;
-                sum[SUM_CRSU] += p * p;
-                p = rv[lx];
-                sum[SUM_CRV] += p;
-                sum[SUM_CRSV] += p * p;
-            }
-        }
+        warp_rect_moments(A.srcU.p + (ptrdiff_t) cby * A.srcU.stride + cbx, A.srcU.stride, cbw, cbh, lane, sum[SUM_CSU], sum[SUM_CSSU]);
+        warp_rect_moments(A.srcV.p + (ptrdiff_t) cby * A.srcV.stride + cbx, A.srcV.stride, cbw, cbh, lane, sum[SUM_CSV], sum[SUM_CSSV]);
+        warp_rect_moments(A.refU.p + (ptrdiff_t) cby * A.refU.stride + cbx, A.refU.stride, cbw, cbh, lane, sum[SUM_CRU], sum[SUM_CRSU]);
+        warp_rect_moments(A.refV.p + (ptrdiff_t) cby * A.refV.stride + cbx, A.refV.stride, cbw, cbh, lane, sum[SUM_CRV], sum[SUM_CRSV]);
     }
-    if (tid < HP_SAD_SZ * HP_SAD_SZ) { /* block_texture on the two 14x14 patches, hme.c:179-209 */
-        const int jj = tid / HP_SAD_SZ, ii = tid - jj * HP_SAD_SZ;
+    for (int k = lane; k < HP_SAD_SZ * HP_SAD_SZ; k += 32) { /* block_texture on the two 14x14 patches, hme.c:179-209 */
+        const int jj = k / HP_SAD_SZ, ii = k - jj * HP_SAD_SZ;
         const uint8_t *sp = A.src.p + (ptrdiff_t) (cy + jj) * ss + cx + ii;
         int px = sp[0];
         int right = ii == HP_SAD_SZ - 1 ? px : sp[1];
         int up = jj == 0 ? px : sp[-ss];
-        sum[SUM_PSH] = (unsigned) iabs(px - right);
-        sum[SUM_PSV] = (unsigned) iabs(px - up);
-        sum[SUM_PAV] = (unsigned) px;
-        sum[SUM_PAVS] = (unsigned) (px * px);
-        px = s_refblk[tid];
-        right = ii == HP_SAD_SZ - 1 ? px : s_refblk[tid + 1];
-        up = jj == 0 ? px : s_refblk[tid - HP_SAD_SZ];
-        sum[SUM_QSH] = (unsigned) iabs(px - right);
-        sum[SUM_QSV] = (unsigned) iabs(px - up);
-        sum[SUM_QAV] = (unsigned) px;
-        sum[SUM_QAVS] = (unsigned) (px * px);
+        sum[SUM_PSH] += (unsigned) iabs(px - right);
+        sum[SUM_PSV] += (unsigned) iabs(px - up);
+        sum[SUM_PAV] += (unsigned) px;
+        sum[SUM_PAVS] += (unsigned) (px * px);
+        px = s_refblk[k];
+        right = ii == HP_SAD_SZ - 1 ? px : s_refblk[k + 1];
+        up = jj == 0 ? px : s_refblk[k - HP_SAD_SZ];
+        sum[SUM_QSH] += (unsigned) iabs(px - right);
+        sum[SUM_QSV] += (unsigned) iabs(px - up);
+        sum[SUM_QAV] += (unsigned) px;
+        sum[SUM_QAVS] += (unsigned) (px * px);
     }
-    block_reduce_n<SUM_COUNT>(sum, scratch);
+    warp_reduce_n<SUM_COUNT>(sum);
 
     /* ---- block_intra_test (hme.c:141-177): any sample the reduced-range intra path cannot represent ---- */
     const int ravg = (int) sum[SUM_RS] / (G.bw * G.bh);
-    if (tid == 0) {
-        s_flag = 0;
-    }
-    __syncthreads();
+    int bad = 0;
     {
         /* clamp_u8(ravg + clamp_u8(p - ravg + 128) - 128) != p  <=>  the inner clamp is active  <=>  p outside
          * [ravg - 128, ravg + 127]; four samples per step from the staged words */
         const int lo = ravg - 128, hi = ravg + 127;
-        int bad = 0;
         if (lo > 0 || hi < 255) {
             const int tail = G.bw & 3;
-            for (int idx = tid; idx < G.words * G.bh; idx += HME_THREADS) {
-                const int r = (idx * G.wmag) >> 20, wx = idx - r * G.words;
-                const unsigned w = *reinterpret_cast<const unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * wx);
-                const int nb = (wx == G.words - 1 && tail) ? tail : 4;
+            const int nb = (G.wx == G.words - 1 && tail) ? tail : 4;
+            for (int r = G.r0; r < G.r1; r++) {
+                const unsigned w = *reinterpret_cast<const unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * G.wx);
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     const int p = byte_of(w, e);
@@ -530,13 +572,10 @@ __global__ void __launch_bounds__(HME_THREADS, HME_L0_MINB) hme_l0_kernel(const 
                 }
             }
         }
-        if (bad) {
-            s_flag = 1;
-        }
     }
-    __syncthreads();
+    const int flag = __any_sync(0xffffffffu, bad);
 
-    if (tid == 0) {
+    if (lane == 0) {
         const unsigned area = yarea;
         const unsigned luma_tex = ((sum[SUM_SH] + sum[SUM_SV]) / 2u) / area;
         const unsigned luma_var = sum[SUM_SS] - (sum[SUM_S] * sum[SUM_S]) / area;
@@ -572,7 +611,7 @@ __global__ void __launch_bounds__(HME_THREADS, HME_L0_MINB) hme_l0_kernel(const 
             }
         }
         int mode = 0, submask = 0;
-        if (intra && !s_flag) {
+        if (intra && !flag) {
             submask = 15;
             if (src_tex > 1) {
                 const unsigned wgt = (unsigned) ((sbw + sbh) >> 1);
@@ -671,9 +710,10 @@ void hme_launch(const HmeArgs *d_args, int n, const MotionGeom &g, cudaStream_t 
         const HmeArgs *a = d_args + (size_t) level * n;
         if (level > 0) {
             const int step = 1 << level;
-            DSV_LAUNCH(hme_level_kernel, dim3(ceil_div(g.nbh, step), ceil_div(g.nbv, step), n), dim3(HME_THREADS), 0, st, a);
+            const int nbx = ceil_div(g.nbh, step), nby = ceil_div(g.nbv, step);
+            DSV_LAUNCH(hme_level_kernel, dim3(ceil_div(nbx * nby, HME_WARPS), 1, n), dim3(HME_THREADS), 0, st, a, nbx, nby);
         } else {
-            DSV_LAUNCH(hme_l0_kernel, dim3(g.nbh, g.nbv, n), dim3(HME_THREADS), 0, st, a);
+            DSV_LAUNCH(hme_l0_kernel, dim3(ceil_div(g.nbh * g.nbv, HME_WARPS), 1, n), dim3(HME_THREADS), 0, st, a);
         }
         KERNEL_CHECK();
     }

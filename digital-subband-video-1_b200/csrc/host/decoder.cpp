@@ -107,7 +107,6 @@ DecEngine::DecEngine(const DSV_META &md, int lanes)
     pkt_cap_ = g.coef_total * 8 + 4096 + (size_t) g.nblk * 64;
     const size_t per_lane = 3 * (sizeof(SbtJob) + hzdec_job_size()) + sizeof(BmcArgs) + 8 * sizeof(PlaneRef) + 3 * sizeof(PackItem) + sizeof(ZeroItem) + sizeof(CopyItem) + sizeof(DrawItem) + sizeof(PackItem) + 2 * sizeof(To420Item) + 1024;
     CUDA_CHECK(cudaMalloc(&d_mv_, sizeof(DevMV) * (size_t) max_nblk_ * L_));
-    CUDA_CHECK(cudaMalloc(&d_means_, sizeof(uint32_t) * 3 * (size_t) max_nblk_ * L_));
     CUDA_CHECK(cudaMalloc(&d_stab_, (size_t) max_nblk_ * L_));
     for (int q = 0; q < 2; q++) {
         arena_[q].create(per_lane * (size_t) L_ + 4096);
@@ -161,7 +160,6 @@ DecEngine::~DecEngine()
     cudaFree(d_out_all_[0]);
     cudaFree(d_out_all_[1]);
     cudaFree(d_mv_);
-    cudaFree(d_means_);
     cudaFreeHost(h_mv_[0]);
     cudaFreeHost(h_mv_[1]);
     cudaFree(d_stab_);
@@ -492,7 +490,7 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
         }
         if (isP) {
             const MotionGeom mg = {g.w, g.h, g.hs, g.vs, g.blk_w, g.blk_h, g.nbh, g.nbv, 0};
-            bmc_fill_args(&ba[n_p++], mg, d_mv_ + (size_t) li * step_nblk, d_means_ + 3 * (size_t) li * step_nblk, l.out[l.cur ^ 1], nullptr, cur, cur, 2);
+            bmc_fill_args(&ba[n_p++], mg, d_mv_ + (size_t) li * step_nblk, l.out[l.cur ^ 1], nullptr, cur, cur, 2);
         }
         /* dsv_decoder.c:405: coefficient planes start zeroed.  Planes that were never coded (corrupt plen) stay
          * all-zero here; the reference leaves the zeroed residual plane untouched instead. */

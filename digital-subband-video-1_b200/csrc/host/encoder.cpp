@@ -372,7 +372,6 @@ EncEngine::EncEngine(const DSV_META &md, int gop, int pyramid_levels, int lanes)
                             sizeof(BmcArgs) + 8 * sizeof(PlaneRef) + 2 * sizeof(ZeroItem) + 2048;
     arena_.create(per_lane * (size_t) L_ + 4096);
     CUDA_CHECK(cudaMalloc(&d_mv0_, sizeof(DevMV) * (size_t) g_.nblk * L_));
-    CUDA_CHECK(cudaMalloc(&d_means_, sizeof(uint32_t) * 3 * (size_t) g_.nblk * L_));
     CUDA_CHECK(cudaMemset(d_mv0_, 0, sizeof(DevMV) * (size_t) g_.nblk * L_));
     CUDA_CHECK(cudaMallocHost(&h_mv0_, sizeof(DevMV) * (size_t) g_.nblk * L_));
     memset(h_mv0_, 0, sizeof(DevMV) * (size_t) g_.nblk * L_);
@@ -473,7 +472,6 @@ EncEngine::~EncEngine()
     cudaFree(d_in_all_[0]);
     cudaFree(d_in_all_[1]);
     cudaFree(d_mv0_);
-    cudaFree(d_means_);
     cudaFreeHost(h_mv0_);
     cudaFree(d_stab_);
     cudaFreeHost(h_stab_);
@@ -689,7 +687,7 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         for (int k = 0; k < n; k++) {
             EncLane &l = lanes_[(size_t) lane_ids[k]];
             if (l.has_ref) {
-                bmc_fill_args(&ba[q++], mg, l.d_mvf[0], d_means_ + 3 * (size_t) lane_ids[k] * g.nblk, l.recon[l.cur ^ 1], &l.pred, l.pad[l.cur], l.xf, 1);
+                bmc_fill_args(&ba[q++], mg, l.d_mvf[0], l.recon[l.cur ^ 1], &l.pred, l.pad[l.cur], l.xf, 1);
             }
         }
     }

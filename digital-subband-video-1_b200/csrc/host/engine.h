@@ -212,7 +212,6 @@ private:
     StepArena arena_;
     /* lane-major arrays shared by all lanes so that one copy moves every lane's data */
     DevMV *d_mv0_ = nullptr, *h_mv0_ = nullptr;  /* level-0 motion fields */
-    uint32_t *d_means_ = nullptr;                /* intra block / quadrant means of the compensation (bmc.cu) */
     uint8_t *d_stab_ = nullptr, *h_stab_ = nullptr;
     uint8_t *d_misc_ = nullptr, *h_misc_ = nullptr; /* per lane: u64 luma sum, i32 intra count, pad */
     HzChunk *d_chunks_ = nullptr;
@@ -292,7 +291,6 @@ private:
     std::vector<DecLane> lanes_;
     StepArena arena_[2];
     DevMV *d_mv_ = nullptr, *h_mv_[2] = {nullptr, nullptr};
-    uint32_t *d_means_ = nullptr; /* intra block / quadrant means of the compensation (bmc.cu) */
     uint8_t *d_stab_ = nullptr, *h_stab_[2] = {nullptr, nullptr};
     uint8_t *d_out_all_[2] = {nullptr, nullptr}; /* packed-picture egress staging of all lanes (step parity) */
     size_t out_pitch_ = 0;

@@ -388,9 +388,8 @@ extern "C" int dsvk_sub_pred(const void *mvs, int w, int h, int subsamp, int blk
     devframe_alloc(&pred, w, h, subsamp);
     DevBuf mv(sizeof(DevMV) * (size_t) g.nbh * g.nbv);
     CUDA_CHECK(cudaMemcpy(mv.p, mvs, sizeof(DevMV) * (size_t) g.nbh * g.nbv, cudaMemcpyHostToDevice));
-    DevBuf means(sizeof(uint32_t) * 3 * (size_t) g.nbh * g.nbv);
     BmcArgs ba;
-    bmc_fill_args(&ba, g, mv.as<DevMV>(), means.as<uint32_t>(), ref, &pred, inp, inp, 1);
+    bmc_fill_args(&ba, g, mv.as<DevMV>(), ref, &pred, inp, inp, 1);
     DevBuf dargs(sizeof(BmcArgs));
     CUDA_CHECK(cudaMemcpy(dargs.p, &ba, sizeof(ba), cudaMemcpyHostToDevice));
     bmc_launch(dargs.as<BmcArgs>(), 1, g, 0);
@@ -412,9 +411,8 @@ extern "C" int dsvk_add_pred(const void *mvs, int w, int h, int subsamp, int blk
     upload_frame(&ref, ref_yuv, w, h, subsamp);
     DevBuf mv(sizeof(DevMV) * (size_t) g.nbh * g.nbv);
     CUDA_CHECK(cudaMemcpy(mv.p, mvs, sizeof(DevMV) * (size_t) g.nbh * g.nbv, cudaMemcpyHostToDevice));
-    DevBuf means(sizeof(uint32_t) * 3 * (size_t) g.nbh * g.nbv);
     BmcArgs ba;
-    bmc_fill_args(&ba, g, mv.as<DevMV>(), means.as<uint32_t>(), ref, nullptr, io, io, 2);
+    bmc_fill_args(&ba, g, mv.as<DevMV>(), ref, nullptr, io, io, 2);
     DevBuf dargs(sizeof(BmcArgs));
     CUDA_CHECK(cudaMemcpy(dargs.p, &ba, sizeof(ba), cudaMemcpyHostToDevice));
     bmc_launch(dargs.as<BmcArgs>(), 1, g, 0);

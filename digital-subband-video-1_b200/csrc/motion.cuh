@@ -59,13 +59,12 @@ struct BmcPlane {
 struct BmcArgs {
     BmcPlane pl[3];
     const DevMV *mv;
-    uint32_t *means; /* 3 x nbh*nbv words: block / quadrant means of the intra blocks (written by the launch itself) */
     int blk_w, blk_h, nbh, nbv, hs, vs, mode;
 };
 /* prediction from `ref` (kept in `pred` unless null) for all three planes, fused with
  *   mode 1 (encoder, dsv_sub_pred):  out = clamp(in - pred + 128)
  *   mode 2 (decoder, dsv_add_pred):  out = clamp(pred + in - 128)   (in may alias out) */
-void bmc_fill_args(BmcArgs *a, const MotionGeom &g, const DevMV *d_mv, uint32_t *d_means, const DevFrame &ref, const DevFrame *pred,
+void bmc_fill_args(BmcArgs *a, const MotionGeom &g, const DevMV *d_mv, const DevFrame &ref, const DevFrame *pred,
                    const DevFrame &in, const DevFrame &out, int mode);
 void bmc_launch(const BmcArgs *d_args, int n, const MotionGeom &g, cudaStream_t st);
 

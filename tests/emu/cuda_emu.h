@@ -211,6 +211,26 @@ static inline unsigned __vabsdiffu4(unsigned a, unsigned b)
     }
     return r;
 }
+static inline unsigned __vaddss4(unsigned a, unsigned b)
+{
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) {
+        int v = (int) (signed char) (a >> (8 * i)) + (int) (signed char) (b >> (8 * i));
+        v = v > 127 ? 127 : (v < -128 ? -128 : v);
+        r |= (unsigned) (v & 0xff) << (8 * i);
+    }
+    return r;
+}
+static inline unsigned __vsubss4(unsigned a, unsigned b)
+{
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) {
+        int v = (int) (signed char) (a >> (8 * i)) - (int) (signed char) (b >> (8 * i));
+        v = v > 127 ? 127 : (v < -128 ? -128 : v);
+        r |= (unsigned) (v & 0xff) << (8 * i);
+    }
+    return r;
+}
 static inline unsigned __vsadu4(unsigned a, unsigned b)
 {
     unsigned r = 0;

@@ -19,7 +19,7 @@ sp = [h_streams.data_ptr() + s * cap for s in range(B)]; sdp = [d_streams.data_p
 import time
 for it in range(4):
     if it == 1:
-        enc.stats(reset=True); dec.stats(reset=True); torch.cuda.synchronize(); t0 = time.perf_counter()
+        enc.stats(reset=True); dec.stats(reset=True); enc.kernel_times(reset=True); dec.kernel_times(reset=True); torch.cuda.synchronize(); t0 = time.perf_counter()
     rc, lens = enc.encode_ptrs([d_yuv.data_ptr() + s * seq for s in range(B)], NFR, 1, sp, [cap] * B)
     if it == 0:
         d_streams.copy_(h_streams)
@@ -31,3 +31,10 @@ print(os.path.basename(L.GPU_SO), "step %.2f ms" % (dt * 1e3),
       "bmc enc %.1f us dec %.1f us" % (1e3 * es["bmc_ms"] / max(es["bmc_launches"], 1), 1e3 * ds["bmc_ms"] / max(ds["bmc_launches"], 1)),
       "fwd %.1f inv %.1f/%.1f us" % (1e3 * es["sbt_fwd_ms"] / es["sbt_fwd_launches"], 1e3 * es["sbt_inv_ms"] / es["sbt_inv_launches"], 1e3 * ds["sbt_inv_ms"] / ds["sbt_inv_launches"]),
       "out md5", hashlib.md5(d_out[:fb * 3].cpu().numpy().tobytes()).hexdigest()[:8])
+
+ek, dk = enc.kernel_times(), dec.kernel_times()
+want = sys.argv[2].split(",") if len(sys.argv) > 2 else []
+for side, kt in (("enc", ek), ("dec", dk)):
+    for name, v in kt.items():
+        if not want or any(w in name for w in want):
+            print("   %-26s %s  %8.1f us/launch  x%d" % (name, side, 1e3 * v["ms"] / v["launches"], v["launches"] / 3))
