@@ -3,10 +3,9 @@
  * reconstruction (decoder).  Replaces compensate / hpelL / hpel / avgval / cpyzero / subf / addf /
  * dsv_sub_pred / dsv_add_pred (bmc.c:29-346).
  *
- * Streaming formulation: the unit of work is a strip of 8 samples x R rows of ONE motion block (R = 16 luma,
- * 8 chroma), one strip per thread, the strips of all blocks / planes / lanes flattened into one grid.  A thread
- * keeps everything in registers -- no shared memory, no barriers -- and keeps BMC_PF reference rows plus three
- * rows of the current picture in flight (explicit prefetch rings):
+ * Streaming formulation: the unit of work is a strip of 8 samples x up to 24 rows of ONE motion block, one strip per thread, the strips of all blocks / planes / lanes flattened into one grid.  A thread
+ * keeps its filter state in registers, shares nothing and meets no barrier; the rows it will need are fetched
+ * BMC_D rows ahead by cp.async into thread-private shared-memory slots:
  *
  *   luma    every inter block goes through the SAME separable 4-tap path whatever its half-pel phase: the phase
  *           only selects the tap words, (-1,9,9,-1) or (0,16,0,0), per direction.  With 16 = the taps' DC gain
@@ -37,13 +36,13 @@ namespace dsv {
 
 #define BMC_THREADS 256
 #define BMC_W 8   /* samples per strip row */
-#define BMC_RL 16 /* luma rows per strip */
-#define BMC_RC 8  /* chroma rows per strip */
-#ifndef BMC_PF
-#define BMC_PF 4  /* reference rows in flight per thread */
+#define BMC_RL 24 /* luma rows per strip */
+#define BMC_RC 24 /* chroma rows per strip */
+#ifndef BMC_D
+#define BMC_D 6   /* rows in flight per thread (cp.async ring depth); a multiple of 3 */
 #endif
 #ifndef BMC_MINB
-#define BMC_MINB 3 /* CTAs per SM the register budget is held to: 369 us per 64 HD pictures at 2 (96 registers), 322 at 3 (80) */
+#define BMC_MINB 3 /* CTAs per SM the register budget is held to */
 #endif
 
 /* c + sum of the four unsigned bytes of w times the four signed bytes of taps */
@@ -69,62 +68,6 @@ DSV_D unsigned bmc_combine4(unsigned cur, unsigned pw, int mode)
 {
     const unsigned a = cur ^ 0x80808080u, b = pw ^ 0x80808080u;
     return (mode == 1 ? __vsubss4(a, b) : __vaddss4(a, b)) ^ 0x80808080u;
-}
-
-/* one row of a strip: 8 predicted samples in pw[2] (sample 0 in the lowest byte of pw[0]); n = valid samples;
- * cur = the co-located samples of `in` when vec8 (fetched ahead by the caller) */
-DSV_D void bmc_store_row(const BmcPlane &P, int mode, int gx, int gy, int n, bool vec8, uint2 cur, const unsigned pw[2])
-{
-    const size_t oo = (size_t) gy * P.ostride + gx;
-    if (vec8) { /* n == 8 and every row of the three frames 8-byte aligned at gx */
-        *reinterpret_cast<uint2 *>(P.out + oo) = make_uint2(bmc_combine4(cur.x, pw[0], mode), bmc_combine4(cur.y, pw[1], mode));
-        if (P.pred) {
-            *reinterpret_cast<uint2 *>(P.pred + (size_t) gy * P.pstride + gx) = make_uint2(pw[0], pw[1]);
-        }
-        return;
-    }
-    const size_t io = (size_t) gy * P.istride + gx;
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            if (4 * k + e < n) {
-                const int pv = byte_of(pw[k], e);
-                const int c = P.in[io + 4 * k + e];
-                P.out[oo + 4 * k + e] = mode == 1 ? clamp_u8(c - pv + 128) : clamp_u8(pv + c - 128);
-                if (P.pred) {
-                    P.pred[(size_t) gy * P.pstride + gx + 4 * k + e] = (uint8_t) pv;
-                }
-            }
-        }
-    }
-}
-
-/* intra blocks (bmc.c:255-298): the flagged quadrants become their mean, the others keep the co-located reference
- * already in pw; odd edge blocks: the quadrants do not cover the last row / column (zeroed frame in the reference) */
-DSV_D void bmc_intra_row(unsigned pw[2], const DevMV &mv, unsigned means, int lx, int ly, int cw, int ch)
-{
-    const bool whole = mv.submask == 15;
-    const int sbw = cw / 2, sbh = ch / 2;
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        unsigned w = 0;
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int x = lx + 4 * k + e;
-            unsigned v;
-            if (whole) {
-                v = means & 0xffu;
-            } else if (x >= 2 * sbw || ly >= 2 * sbh) {
-                v = 0;
-            } else {
-                const int q = (x >= sbw ? 1 : 0) | (ly >= sbh ? 2 : 0);
-                v = (mv.submask & (1 << q)) ? ((means >> (8 * q)) & 0xffu) : (unsigned) byte_of(pw[k], e);
-            }
-            w |= v << (8 * e);
-        }
-        pw[k] = w;
-    }
 }
 
 /* block / quadrant means of an intra block (avgval, bmc.c:176-190), computed by the strip's own thread: a word holds
@@ -232,203 +175,341 @@ DSV_D void bmc_edge_column(const BmcPlane &P, const BmcStrip &s, int mode)
     }
 }
 
-/* the co-located row of `in` for the 8-byte path (rows past the strip repeat its last row: the load stays valid and
- * unconditional, so it can be issued rows ahead of its use) */
-DSV_D uint2 bmc_fetch_in(const BmcPlane &P, const BmcStrip &s, int t)
+/*
+ * Strips that are cut (fewer than 8 samples or unaligned: picture edge, block widths that are not multiples of 8) or
+ * belong to an intra block take this plain per-sample path: the reference's formulas as written (bmc.c:58-174,
+ * 255-298).  Out of line, so the streaming path below carries none of its state.
+ */
+template <bool LUMA> __device__ __noinline__ void bmc_slow_strip(const BmcPlane &P, const BmcStrip &s, int mode)
 {
-    if (!s.vec8) {
-        return make_uint2(0u, 0u);
+    const unsigned means = s.intra ? bmc_intra_means(P, s.mv, s.x, s.y, s.cw, s.ch) : 0u;
+    const bool whole = s.mv.submask == 15;
+    const int sbw = s.cw / 2, sbh = s.ch / 2;
+    const int rs = P.rstride;
+    for (int t = 0; t < s.rows; t++) {
+        const int ly = s.ly + t, gy = s.y + ly;
+        for (int e = 0; e < s.n; e++) {
+            const int lx = s.lx + e, gx = s.x + lx;
+            const uint8_t *p = P.ref + (ptrdiff_t) (s.py + ly) * rs + s.px + lx;
+            int pv;
+            if (LUMA) {
+                if (!s.xh && !s.yh) {
+                    pv = p[0];
+                } else if (!s.xh) {
+                    pv = clamp_u8((9 * (p[0] + p[rs]) - (p[-rs] + p[2 * rs]) + 8) >> 4);
+                } else if (!s.yh) {
+                    pv = clamp_u8((9 * (p[0] + p[1]) - (p[-1] + p[2]) + 8) >> 4);
+                } else {
+                    int h[4];
+                    for (int k = 0; k < 4; k++) {
+                        const uint8_t *q = p + (ptrdiff_t) (k - 1) * rs;
+                        h[k] = 9 * (q[0] + q[1]) - (q[-1] + q[2]);
+                    }
+                    pv = clamp_u8((9 * (h[1] + h[2]) - (h[0] + h[3]) + 128) >> 8);
+                }
+            } else {
+                if (!s.xh && !s.yh) {
+                    pv = p[0];
+                } else if (!s.xh) {
+                    pv = (p[0] + p[rs] + 1) >> 1;
+                } else if (!s.yh) {
+                    pv = (p[0] + p[1] + 1) >> 1;
+                } else {
+                    pv = (p[0] + p[1] + p[rs] + p[rs + 1] + 2) >> 2;
+                }
+            }
+            if (s.intra) { /* pv is the co-located sample here (zero vector) */
+                if (whole) {
+                    pv = (int) (means & 0xffu);
+                } else if (lx >= 2 * sbw || ly >= 2 * sbh) {
+                    pv = 0; /* odd edge blocks: the quadrants do not cover the last row / column (zeroed frame) */
+                } else {
+                    const int qd = (lx >= sbw ? 1 : 0) | (ly >= sbh ? 2 : 0);
+                    if (s.mv.submask & (1 << qd)) {
+                        pv = (int) ((means >> (8 * qd)) & 0xffu);
+                    }
+                }
+            }
+            const int c = P.in[(size_t) gy * P.istride + gx];
+            P.out[(size_t) gy * P.ostride + gx] = mode == 1 ? clamp_u8(c - pv + 128) : clamp_u8(pv + c - 128);
+            if (P.pred) {
+                P.pred[(size_t) gy * P.pstride + gx] = (uint8_t) pv;
+            }
+        }
     }
-    const int gy = s.y + s.ly + imin(t, s.rows - 1);
-    return *reinterpret_cast<const uint2 *>(P.in + (size_t) gy * P.istride + s.x + s.lx);
 }
 
-DSV_D void bmc_luma_strip(const BmcArgs &a, const int u)
+/*
+ * Rows in flight.  Reference rows (bytes p[-1..10] of a luma strip row = 4 aligned words, 3 for chroma) and the
+ * co-located rows of `in` (8 bytes) are fetched BMC_D rows ahead with cp.async into thread-private slots of a
+ * shared-memory ring -- reference words as [slot][word][thread], `in` rows as [slot][thread] word pairs, so both the
+ * asynchronous writes and the reads are conflict-free.  Nothing in flight holds a register.  The row loop runs
+ * BMC_D row bodies per trip (ring slots and the period-3 rotation of the pair registers are then compile-time
+ * names; BMC_D is a multiple of 3) plus single-row trips for the remainder.
+ * Group g = reference row g + `in` row g - LAG (LAG = rows between a reference row arriving and the output row it
+ * completes); one group is committed per row body, empty past the end.
+ */
+struct BmcFeed {
+    unsigned *ref;      /* this thread's column of [BMC_D][4][BMC_THREADS] */
+    unsigned *cur;      /* this thread's pair in [BMC_D][BMC_THREADS][2] */
+    const unsigned *q;  /* next reference row to issue (aligned words) */
+    const uint8_t *in;  /* next row of `in` to issue */
+    int qs, istride;
+    int nref, rows;     /* reference rows / rows of `in` this strip needs: later groups are empty */
+};
+
+template <int NW, int LAG> DSV_D void bmc_issue(BmcFeed &f, int slot, int g)
+{
+    if (g < f.nref) {
+        unsigned *d = f.ref + slot * 4 * BMC_THREADS;
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            cp_async4(d + k * BMC_THREADS, f.q + k);
+        }
+        f.q += f.qs;
+        if (g >= LAG) { /* g - LAG < rows follows from g < nref = rows + LAG */
+            cp_async8(f.cur + slot * 2 * BMC_THREADS, f.in);
+            f.in += f.istride;
+        }
+    }
+    cp_async_commit();
+}
+
+/* store one output row of the 8-byte path and step the pointers */
+template <int MODE> DSV_D void bmc_emit(uint8_t *&outp, uint8_t *&predp, int ostride, int pstride, uint2 cur, const unsigned pw[2])
+{
+    *reinterpret_cast<uint2 *>(outp) = make_uint2(bmc_combine4(cur.x, pw[0], MODE), bmc_combine4(cur.y, pw[1], MODE));
+    outp += ostride;
+    if (MODE == 1) { /* the encoder keeps the prediction */
+        *reinterpret_cast<uint2 *>(predp) = make_uint2(pw[0], pw[1]);
+        predp += pstride;
+    }
+}
+
+struct BmcOut {
+    uint8_t *outp, *predp;
+    int ostride, pstride, rows;
+};
+
+/* one reference row of a luma strip: wait for it, refill its ring slot, H pass, pair it with the row above, and
+ * (from the fourth row on) finish the output row three rows up.  rd: pair (r - 3, r - 2); wr receives (r - 1, r). */
+template <int MODE>
+DSV_D void bmc_luma_row(BmcFeed &f, BmcOut &o, int slot, int r, unsigned bsh, unsigned th, unsigned t_ab, unsigned t_cd,
+                        int (&hprev)[BMC_W], const unsigned (&rd)[BMC_W], unsigned (&wr)[BMC_W])
+{
+    cp_async_wait<BMC_D - 1>();
+    const unsigned *sl = f.ref + slot * 4 * BMC_THREADS;
+    const unsigned w0 = sl[0], w1 = sl[BMC_THREADS], w2 = sl[2 * BMC_THREADS], w3 = sl[3 * BMC_THREADS];
+    const uint2 c = *reinterpret_cast<const uint2 *>(f.cur + slot * 2 * BMC_THREADS);
+    bmc_issue<4, 3>(f, slot, r + BMC_D);
+    unsigned v[3];
+    v[0] = __funnelshift_r(w0, w1, bsh);
+    v[1] = __funnelshift_r(w1, w2, bsh);
+    v[2] = __funnelshift_r(w2, w3, bsh);
+    int h[BMC_W];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        h[4 * k + 0] = dp4a_us(v[k], th, 0);
+        h[4 * k + 1] = dp4a_us(__funnelshift_r(v[k], v[k + 1], 8), th, 0);
+        h[4 * k + 2] = dp4a_us(__funnelshift_r(v[k], v[k + 1], 16), th, 0);
+        h[4 * k + 3] = dp4a_us(__funnelshift_r(v[k], v[k + 1], 24), th, 0);
+    }
+    unsigned pnew[BMC_W];
+#pragma unroll
+    for (int e = 0; e < BMC_W; e++) {
+        pnew[e] = __byte_perm((unsigned) hprev[e], (unsigned) h[e], 0x5410);
+        hprev[e] = h[e];
+    }
+    if (r >= 3 && r - 3 < o.rows) {
+        unsigned pw[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int v0 = dp2a_lo_s16(pnew[4 * k + 0], t_cd, dp2a_lo_s16(rd[4 * k + 0], t_ab, 128)) >> 8;
+            const int v1 = dp2a_lo_s16(pnew[4 * k + 1], t_cd, dp2a_lo_s16(rd[4 * k + 1], t_ab, 128)) >> 8;
+            const int v2 = dp2a_lo_s16(pnew[4 * k + 2], t_cd, dp2a_lo_s16(rd[4 * k + 2], t_ab, 128)) >> 8;
+            const int v3 = dp2a_lo_s16(pnew[4 * k + 3], t_cd, dp2a_lo_s16(rd[4 * k + 3], t_ab, 128)) >> 8;
+            pw[k] = pack_u8x4(v0, v1, v2, v3);
+        }
+        bmc_emit<MODE>(o.outp, o.predp, o.ostride, o.pstride, c, pw);
+    }
+#pragma unroll
+    for (int e = 0; e < BMC_W; e++) {
+        wr[e] = pnew[e];
+    }
+}
+
+template <int MODE> DSV_D void bmc_luma_strip(const BmcArgs &a, const int u, unsigned *smem)
 {
     const BmcPlane P = a.pl[0];
-    const int mode = a.mode;
     BmcStrip s = {};
     if (!bmc_strip_setup<BMC_RL>(a, P, 0, u, s)) {
         return;
     }
-    const unsigned means = s.intra ? bmc_intra_means(P, s.mv, s.x, s.y, s.cw, s.ch) : 0u;
+    bmc_edge_column(P, s, MODE);
+    if (s.intra || !s.vec8) {
+        const BmcStrip sc = s; /* only the copy's address escapes: s itself stays in registers */
+        const BmcPlane Pc = P;
+        bmc_slow_strip<true>(Pc, sc, MODE);
+        return;
+    }
     /* taps: bytes (p[-1], p[0], p[1], p[2]); pairs (row a, row b) and (row c, row d) */
     const unsigned th = s.xh ? 0xff0909ffu : 0x00001000u;
     const unsigned t_ab = s.yh ? 0x09ffu : 0x1000u, t_cd = s.yh ? 0xff09u : 0x0000u;
-    const int rs = P.rstride;
     /* first byte needed: one row above and one sample left of the strip's reference position */
-    const uint8_t *src = P.ref + (ptrdiff_t) (s.py + s.ly - 1) * rs + (s.px + s.lx - 1);
+    const uint8_t *src = P.ref + (ptrdiff_t) (s.py + s.ly - 1) * P.rstride + (s.px + s.lx - 1);
     const unsigned bsh = ((unsigned) reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
-    const unsigned *q = reinterpret_cast<const unsigned *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t) 3);
-    const int qs = rs >> 2; /* strides are multiples of 16 */
-    const int last = s.rows + 2; /* last reference row this strip needs; later rows repeat it (loads stay in bounds) */
+    BmcOut o;
+    o.rows = s.rows;
+    o.outp = P.out + (size_t) (s.y + s.ly) * P.ostride + s.x + s.lx;
+    o.predp = MODE == 1 ? P.pred + (size_t) (s.y + s.ly) * P.pstride + s.x + s.lx : nullptr;
+    o.ostride = P.ostride;
+    o.pstride = P.pstride;
+    BmcFeed f;
+    f.ref = smem + threadIdx.x;
+    f.cur = smem + BMC_D * 4 * BMC_THREADS + 2 * threadIdx.x;
+    f.q = reinterpret_cast<const unsigned *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t) 3);
+    f.qs = P.rstride >> 2; /* strides are multiples of 16 */
+    f.in = P.in + (size_t) (s.y + s.ly) * P.istride + s.x + s.lx;
+    f.istride = P.istride;
+    f.nref = s.rows + 3;
+    f.rows = s.rows;
+    const int nref = f.nref;
 
-    /* reference rows travel through a ring of BMC_PF raw rows (bytes p[-1..10] = 4 aligned words), the rows of `in`
-     * through a ring of 3: enough loads in flight per thread to cover the memory latency at 2-3 CTAs per SM */
-    unsigned raw[BMC_PF][4];
 #pragma unroll
-    for (int d = 0; d < BMC_PF; d++) {
-        const unsigned *qr = q + (ptrdiff_t) imin(d, last) * qs;
-        raw[d][0] = qr[0], raw[d][1] = qr[1], raw[d][2] = qr[2], raw[d][3] = qr[3];
-    }
-    uint2 cur[3];
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-        cur[d] = bmc_fetch_in(P, s, d);
+    for (int g = 0; g < BMC_D; g++) {
+        bmc_issue<4, 3>(f, g, g);
     }
     int hprev[BMC_W];
-    unsigned pr0[BMC_W], pr1[BMC_W]; /* vertical pairs (row r-3, r-2) and (row r-2, r-1) of 16-bit H results */
+    unsigned p0[BMC_W], p1[BMC_W], p2[BMC_W]; /* vertical pairs of 16-bit H results: pair j = rows (j, j + 1) in p<j % 3> */
 #pragma unroll
     for (int e = 0; e < BMC_W; e++) {
         hprev[e] = 0;
-        pr0[e] = pr1[e] = 0;
+        p0[e] = p1[e] = p2[e] = 0;
     }
+    int r = 0;
+#pragma unroll 1
+    for (; r + BMC_D <= nref; r += BMC_D) { /* r % 3 == 0: row r reads pair r - 3 in p0 and writes pair r - 1 into p2, ... */
 #pragma unroll
-    for (int r = 0; r < BMC_RL + 3; r++) {
-        const unsigned w0 = raw[r % BMC_PF][0], w1 = raw[r % BMC_PF][1], w2 = raw[r % BMC_PF][2], w3 = raw[r % BMC_PF][3];
-        if (r + BMC_PF < BMC_RL + 3) {
-            const unsigned *qr = q + (ptrdiff_t) imin(r + BMC_PF, last) * qs;
-            raw[r % BMC_PF][0] = qr[0], raw[r % BMC_PF][1] = qr[1], raw[r % BMC_PF][2] = qr[2], raw[r % BMC_PF][3] = qr[3];
-        }
-        unsigned v[3];
-        v[0] = __funnelshift_r(w0, w1, bsh);
-        v[1] = __funnelshift_r(w1, w2, bsh);
-        v[2] = __funnelshift_r(w2, w3, bsh);
-        int h[BMC_W];
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            h[4 * k + 0] = dp4a_us(v[k], th, 0);
-            h[4 * k + 1] = dp4a_us(__funnelshift_r(v[k], v[k + 1], 8), th, 0);
-            h[4 * k + 2] = dp4a_us(__funnelshift_r(v[k], v[k + 1], 16), th, 0);
-            h[4 * k + 3] = dp4a_us(__funnelshift_r(v[k], v[k + 1], 24), th, 0);
-        }
-        unsigned pr2[BMC_W]; /* pair (row r-1, row r) */
-#pragma unroll
-        for (int e = 0; e < BMC_W; e++) {
-            pr2[e] = __byte_perm((unsigned) hprev[e], (unsigned) h[e], 0x5410);
-            hprev[e] = h[e];
-        }
-        if (r >= 3) { /* output row r-3: rows a,b = pair (r-3, r-2), rows c,d = pair (r-1, r) */
-            const int t = r - 3;
-            unsigned pw[2];
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const int v0 = dp2a_lo_s16(pr2[4 * k + 0], t_cd, dp2a_lo_s16(pr0[4 * k + 0], t_ab, 128)) >> 8;
-                const int v1 = dp2a_lo_s16(pr2[4 * k + 1], t_cd, dp2a_lo_s16(pr0[4 * k + 1], t_ab, 128)) >> 8;
-                const int v2 = dp2a_lo_s16(pr2[4 * k + 2], t_cd, dp2a_lo_s16(pr0[4 * k + 2], t_ab, 128)) >> 8;
-                const int v3 = dp2a_lo_s16(pr2[4 * k + 3], t_cd, dp2a_lo_s16(pr0[4 * k + 3], t_ab, 128)) >> 8;
-                pw[k] = pack_u8x4(v0, v1, v2, v3);
-            }
-            const uint2 c = cur[t % 3];
-            if (t + 3 < BMC_RL) {
-                cur[t % 3] = bmc_fetch_in(P, s, t + 3);
-            }
-            if (t < s.rows) {
-                if (s.intra) {
-                    bmc_intra_row(pw, s.mv, means, s.lx, s.ly + t, s.cw, s.ch);
-                }
-                bmc_store_row(P, mode, s.x + s.lx, s.y + s.ly + t, s.n, s.vec8, c, pw);
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < BMC_W; e++) {
-            pr0[e] = pr1[e];
-            pr1[e] = pr2[e];
+        for (int jj = 0; jj < BMC_D; jj += 3) {
+            bmc_luma_row<MODE>(f, o, jj + 0, r + jj + 0, bsh, th, t_ab, t_cd, hprev, p0, p2);
+            bmc_luma_row<MODE>(f, o, jj + 1, r + jj + 1, bsh, th, t_ab, t_cd, hprev, p1, p0);
+            bmc_luma_row<MODE>(f, o, jj + 2, r + jj + 2, bsh, th, t_ab, t_cd, hprev, p2, p1);
         }
     }
-    bmc_edge_column(P, s, mode);
+#pragma unroll 1
+    for (int slot = 0; r < nref; r++, slot++) { /* remainder: one row per trip, the pair registers rotate by moves */
+        bmc_luma_row<MODE>(f, o, slot, r, bsh, th, t_ab, t_cd, hprev, p0, p2);
+#pragma unroll
+        for (int e = 0; e < BMC_W; e++) {
+            const unsigned t = p0[e];
+            p0[e] = p1[e];
+            p1[e] = p2[e];
+            p2[e] = t;
+        }
+    }
 }
 
-DSV_D void bmc_chroma_strip(const BmcArgs &a, const int c, const int u)
+/* one reference row of a chroma strip; top: (p[e], p[e + 1]) of the row above in the two low bytes */
+template <int MODE> DSV_D void bmc_chroma_row(BmcFeed &f, BmcOut &o, int slot, int r, unsigned bsh, unsigned wt, unsigned (&top)[BMC_W])
+{
+    cp_async_wait<BMC_D - 1>();
+    const unsigned *sl = f.ref + slot * 4 * BMC_THREADS;
+    const unsigned w0 = sl[0], w1 = sl[BMC_THREADS], w2 = sl[2 * BMC_THREADS];
+    const uint2 cc = *reinterpret_cast<const uint2 *>(f.cur + slot * 2 * BMC_THREADS);
+    bmc_issue<3, 1>(f, slot, r + BMC_D);
+    unsigned v[3];
+    v[0] = __funnelshift_r(w0, w1, bsh);
+    v[1] = __funnelshift_r(w1, w2, bsh);
+    v[2] = w2 >> bsh; /* only sample 8 is needed */
+    unsigned row[BMC_W];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        row[4 * k + 0] = v[k];
+        row[4 * k + 1] = __funnelshift_r(v[k], v[k + 1], 8);
+        row[4 * k + 2] = __funnelshift_r(v[k], v[k + 1], 16);
+        row[4 * k + 3] = __funnelshift_r(v[k], v[k + 1], 24);
+    }
+    if (r >= 1 && r - 1 < o.rows) {
+        unsigned pw[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int v0 = dp4a_us(__byte_perm(top[4 * k + 0], row[4 * k + 0], 0x5410), wt, 2) >> 2;
+            const int v1 = dp4a_us(__byte_perm(top[4 * k + 1], row[4 * k + 1], 0x5410), wt, 2) >> 2;
+            const int v2 = dp4a_us(__byte_perm(top[4 * k + 2], row[4 * k + 2], 0x5410), wt, 2) >> 2;
+            const int v3 = dp4a_us(__byte_perm(top[4 * k + 3], row[4 * k + 3], 0x5410), wt, 2) >> 2;
+            pw[k] = pack_u8x4(v0, v1, v2, v3);
+        }
+        bmc_emit<MODE>(o.outp, o.predp, o.ostride, o.pstride, cc, pw);
+    }
+#pragma unroll
+    for (int e = 0; e < BMC_W; e++) {
+        top[e] = row[e];
+    }
+}
+
+template <int MODE> DSV_D void bmc_chroma_strip(const BmcArgs &a, const int c, const int u, unsigned *smem)
 {
     const BmcPlane P = a.pl[c];
-    const int mode = a.mode;
     BmcStrip s = {};
     if (!bmc_strip_setup<BMC_RC>(a, P, c, u, s)) {
         return;
     }
-    const unsigned means = s.intra ? bmc_intra_means(P, s.mv, s.x, s.y, s.cw, s.ch) : 0u;
+    bmc_edge_column(P, s, MODE);
+    if (s.intra || !s.vec8) {
+        const BmcStrip sc = s;
+        const BmcPlane Pc = P;
+        bmc_slow_strip<false>(Pc, sc, MODE);
+        return;
+    }
     /* weights for (p[0], p[1], p[rs], p[rs + 1]) */
     const unsigned wt = s.xh ? (s.yh ? 0x01010101u : 0x00000202u) : (s.yh ? 0x00020002u : 0x00000004u);
-    const int rs = P.rstride;
-    const uint8_t *src = P.ref + (ptrdiff_t) (s.py + s.ly) * rs + (s.px + s.lx);
+    const uint8_t *src = P.ref + (ptrdiff_t) (s.py + s.ly) * P.rstride + (s.px + s.lx);
     const unsigned bsh = ((unsigned) reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
-    const unsigned *q = reinterpret_cast<const unsigned *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t) 3);
-    const int qs = rs >> 2;
-    const int last = s.rows;
+    BmcOut o;
+    o.rows = s.rows;
+    o.outp = P.out + (size_t) (s.y + s.ly) * P.ostride + s.x + s.lx;
+    o.predp = MODE == 1 ? P.pred + (size_t) (s.y + s.ly) * P.pstride + s.x + s.lx : nullptr;
+    o.ostride = P.ostride;
+    o.pstride = P.pstride;
+    BmcFeed f;
+    f.ref = smem + threadIdx.x;
+    f.cur = smem + BMC_D * 4 * BMC_THREADS + 2 * threadIdx.x;
+    f.q = reinterpret_cast<const unsigned *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t) 3);
+    f.qs = P.rstride >> 2;
+    f.in = P.in + (size_t) (s.y + s.ly) * P.istride + s.x + s.lx;
+    f.istride = P.istride;
+    f.nref = s.rows + 1;
+    f.rows = s.rows;
+    const int nref = f.nref;
 
-    unsigned raw[BMC_PF][3]; /* bytes p[0..8] */
 #pragma unroll
-    for (int d = 0; d < BMC_PF; d++) {
-        const unsigned *qr = q + (ptrdiff_t) imin(d, last) * qs;
-        raw[d][0] = qr[0], raw[d][1] = qr[1], raw[d][2] = qr[2];
+    for (int g = 0; g < BMC_D; g++) {
+        bmc_issue<3, 1>(f, g, g);
     }
-    uint2 cur[3];
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-        cur[d] = bmc_fetch_in(P, s, d);
-    }
-    unsigned top[BMC_W]; /* (p[e], p[e + 1]) of the row above in the two low bytes */
+    unsigned top[BMC_W];
 #pragma unroll
     for (int e = 0; e < BMC_W; e++) {
         top[e] = 0;
     }
+    int r = 0;
+#pragma unroll 1
+    for (; r + BMC_D <= nref; r += BMC_D) {
 #pragma unroll
-    for (int r = 0; r < BMC_RC + 1; r++) {
-        const unsigned w0 = raw[r % BMC_PF][0], w1 = raw[r % BMC_PF][1], w2 = raw[r % BMC_PF][2];
-        if (r + BMC_PF < BMC_RC + 1) {
-            const unsigned *qr = q + (ptrdiff_t) imin(r + BMC_PF, last) * qs;
-            raw[r % BMC_PF][0] = qr[0], raw[r % BMC_PF][1] = qr[1], raw[r % BMC_PF][2] = qr[2];
-        }
-        unsigned v[3];
-        v[0] = __funnelshift_r(w0, w1, bsh);
-        v[1] = __funnelshift_r(w1, w2, bsh);
-        v[2] = w2 >> bsh; /* only sample 8 is needed */
-        unsigned row[BMC_W];
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            row[4 * k + 0] = v[k];
-            row[4 * k + 1] = __funnelshift_r(v[k], v[k + 1], 8);
-            row[4 * k + 2] = __funnelshift_r(v[k], v[k + 1], 16);
-            row[4 * k + 3] = __funnelshift_r(v[k], v[k + 1], 24);
-        }
-        if (r >= 1) {
-            const int t = r - 1;
-            unsigned pw[2];
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const int v0 = dp4a_us(__byte_perm(top[4 * k + 0], row[4 * k + 0], 0x5410), wt, 2) >> 2;
-                const int v1 = dp4a_us(__byte_perm(top[4 * k + 1], row[4 * k + 1], 0x5410), wt, 2) >> 2;
-                const int v2 = dp4a_us(__byte_perm(top[4 * k + 2], row[4 * k + 2], 0x5410), wt, 2) >> 2;
-                const int v3 = dp4a_us(__byte_perm(top[4 * k + 3], row[4 * k + 3], 0x5410), wt, 2) >> 2;
-                pw[k] = pack_u8x4(v0, v1, v2, v3);
-            }
-            const uint2 cc = cur[t % 3];
-            if (t + 3 < BMC_RC) {
-                cur[t % 3] = bmc_fetch_in(P, s, t + 3);
-            }
-            if (t < s.rows) {
-                if (s.intra) {
-                    bmc_intra_row(pw, s.mv, means, s.lx, s.ly + t, s.cw, s.ch);
-                }
-                bmc_store_row(P, mode, s.x + s.lx, s.y + s.ly + t, s.n, s.vec8, cc, pw);
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < BMC_W; e++) {
-            top[e] = row[e];
+        for (int jj = 0; jj < BMC_D; jj++) {
+            bmc_chroma_row<MODE>(f, o, jj, r + jj, bsh, wt, top);
         }
     }
-    bmc_edge_column(P, s, mode);
+#pragma unroll 1
+    for (int slot = 0; r < nref; r++, slot++) {
+        bmc_chroma_row<MODE>(f, o, slot, r, bsh, wt, top);
+    }
 }
 
-/* grid.x = [luma strips | U strips | V strips] in CTAs of BMC_THREADS strips, grid.y = lane */
-__global__ void __launch_bounds__(BMC_THREADS, BMC_MINB) bmc_kernel(const BmcArgs *args, int ctas_l, int ctas_c)
+template <int MODE> DSV_D void bmc_strips(const BmcArgs &a, int ctas_l, int ctas_c, unsigned *smem)
 {
-    const BmcArgs &a = args[blockIdx.y];
     int cta = blockIdx.x;
     if (cta < ctas_l) {
-        bmc_luma_strip(a, cta * BMC_THREADS + threadIdx.x);
+        bmc_luma_strip<MODE>(a, cta * BMC_THREADS + threadIdx.x, smem);
         return;
     }
     cta -= ctas_l;
@@ -436,7 +517,19 @@ __global__ void __launch_bounds__(BMC_THREADS, BMC_MINB) bmc_kernel(const BmcArg
     if (c == 2) {
         cta -= ctas_c;
     }
-    bmc_chroma_strip(a, c, cta * BMC_THREADS + threadIdx.x);
+    bmc_chroma_strip<MODE>(a, c, cta * BMC_THREADS + threadIdx.x, smem);
+}
+
+/* grid.x = [luma strips | U strips | V strips] in CTAs of BMC_THREADS strips, grid.y = lane */
+__global__ void __launch_bounds__(BMC_THREADS, BMC_MINB) bmc_kernel(const BmcArgs *args, int ctas_l, int ctas_c)
+{
+    DSV_DYN_SMEM(unsigned, smem); /* BMC_D x (4 + 2) x BMC_THREADS words */
+    const BmcArgs &a = args[blockIdx.y];
+    if (a.mode == 1) { /* one mode per launch: uniform */
+        bmc_strips<1>(a, ctas_l, ctas_c, smem);
+    } else {
+        bmc_strips<2>(a, ctas_l, ctas_c, smem);
+    }
 }
 
 void bmc_fill_args(BmcArgs *a, const MotionGeom &g, const DevMV *d_mv, const DevFrame &ref, const DevFrame *pred,
@@ -478,7 +571,13 @@ void bmc_launch(const BmcArgs *d_args, int n, const MotionGeom &g, cudaStream_t 
     const int nblk = g.nbh * g.nbv;
     const int ctas_l = bmc_ctas(g.blk_w, g.blk_h, BMC_RL, nblk);
     const int ctas_c = bmc_ctas(g.blk_w >> g.hs, g.blk_h >> g.vs, BMC_RC, nblk);
-    DSV_LAUNCH(bmc_kernel, dim3(ctas_l + 2 * ctas_c, n), dim3(BMC_THREADS), 0, st, d_args, ctas_l, ctas_c);
+    const size_t smem = (size_t) BMC_D * 6 * BMC_THREADS * sizeof(unsigned);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(bmc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        attr_set = true;
+    }
+    DSV_LAUNCH(bmc_kernel, dim3(ctas_l + 2 * ctas_c, n), dim3(BMC_THREADS), smem, st, d_args, ctas_l, ctas_c);
     KERNEL_CHECK();
 }
 

@@ -204,6 +204,37 @@ DSV_D unsigned ld4u(const uint8_t *p)
     const unsigned sh = (unsigned) (a & 3) * 8;
     return __funnelshift_r(q[0], q[1], sh); /* sh == 0 yields q[0]; q[1] is always readable (guard band / padding) */
 }
+/* asynchronous global -> shared copies (cp.async, SASS LDGSTS): the data never occupies a register while in flight,
+ * so a thread can keep many rows outstanding.  dst: shared memory; src: global memory, aligned to the copy size. */
+DSV_D void cp_async4(void *dst, const void *src)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned) __cvta_generic_to_shared(dst)), "l"(__cvta_generic_to_global(src)) : "memory");
+#else
+    *reinterpret_cast<uint32_t *>(dst) = *reinterpret_cast<const uint32_t *>(src);
+#endif
+}
+DSV_D void cp_async8(void *dst, const void *src)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned) __cvta_generic_to_shared(dst)), "l"(__cvta_generic_to_global(src)) : "memory");
+#else
+    *reinterpret_cast<uint64_t *>(dst) = *reinterpret_cast<const uint64_t *>(src);
+#endif
+}
+DSV_D void cp_async_commit()
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N> DSV_D void cp_async_wait() /* at most N of this thread's committed groups still pending */
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
 DSV_HD int byte_of(unsigned w, int i) { return (int) ((w >> (8 * i)) & 0xff); }
 /* four ints -> four saturated bytes, a in the lowest byte: two cvt.pack.sat instructions on the device */
 DSV_HD unsigned pack_u8x4(int a, int b, int c, int d)
