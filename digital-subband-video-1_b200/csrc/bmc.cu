@@ -34,7 +34,9 @@
 
 namespace dsv {
 
+#ifndef BMC_THREADS
 #define BMC_THREADS 256
+#endif
 #define BMC_W 8   /* samples per strip row */
 #define BMC_RL 24 /* luma rows per strip */
 #define BMC_RC 24 /* chroma rows per strip */

@@ -128,8 +128,8 @@ DSV_HD int get_quant(int q, int isP, int level)
 /* round half away from zero, divide by 2^S (sbt.c:63-88) */
 template <int S> DSV_HD int rnd_shift(int v)
 {
-    const int half = 1 << (S - 1);
-    return v < 0 ? -((-v + half) >> S) : ((v + half) >> S);
+    /* v < 0: -((-v + half) >> S) == ceil((v - half) / 2^S) == (v + half - 1) >> S; branch-free with the sign word */
+    return (v + (1 << (S - 1)) + (v >> 31)) >> S;
 }
 
 /* LL scaling, C truncation (sbt.c:20-21) */
