@@ -2,9 +2,10 @@
  * hzcc_enc.cu -- HZCC coefficient coder, encoder side: hzcc_enc's token stream (hzcc.c:137-293)
  * and dsv_encode_plane's framing (hzcc.c:449-476) as three data-parallel passes over the scan order.
  *
- *   hzcc_scan_kernel    per 2048-position chunk: gather symbols in scan order (coalesced row
- *                       segments; the quantised symbol is re-derived from the dequantised
- *                       coefficient the SBT epilogue stored), count non-zeros, find the chunk's
+ *   hzcc_scan_kernel    one warp per 2048-position chunk: coalesced 16-byte zero tests mark the groups of
+ *                       4 positions that hold something, the marked groups are visited in scan order
+ *                       (the quantised symbol of a non-zero is re-derived from the dequantised
+ *                       coefficient the SBT epilogue stored): count non-zeros, find the chunk's
  *                       first/last non-zero and the bits of all groups that are fully determined
  *                       inside the chunk.
  *   hzcc_prefix_kernel  one CTA per frame: exclusive scans over the chunk summaries (previous
@@ -190,122 +191,301 @@ DSV_D unsigned group_bits(int pos, int prev_pos, int prev_sym)
     return b;
 }
 
-/* load the chunk's symbols and find, for every thread, the last non-zero before its first item */
-DSV_D void chunk_load(const HzJob &J, int chunk_local, int sym[HZ_ITEMS], int &base,
-                      unsigned long long *scratch, unsigned long long &excl_key, unsigned long long &chunk_last)
+/*
+ * One WARP per 2048-position chunk, in two phases.  (The previous formulation, 8 positions per thread with block-wide
+ * scans, spent ~50 instructions per position on set-up and barriers: 97 000 CTAs per launch, each caching the job
+ * record for 2048 coefficients, while well under 1 % of a P picture's symbols are non-zero.)
+ *
+ *   sweep   the chunk as 512 groups of 4 scan positions; group 32k + l belongs to lane l in step k, so a step's 32
+ *           groups are 512 contiguous bytes wherever the chunk stays inside one region row: coalesced 16-byte loads,
+ *           all 16 steps independent.  A group that is contiguous and 16-byte aligned in the coefficient plane
+ *           (inside one row of one region, away from the DC and the double-visited row / column) and all zero is
+ *           done; a ballot per step leaves a 512-bit map of the groups that need a look.
+ *   rounds  32 marked groups at a time, in scan order: a lane derives the symbols of its group's positions
+ *           (hz_symbol_at re-derives the quantised symbol from the dequantised coefficient the SBT epilogue stored)
+ *           and the warp strings the non-zeros together with shuffles; the visitor (scan: summary, pack: bit
+ *           offsets + emission) sees every lane's up-to-4 non-zeros.
+ */
+#define HZW_WARPS (HZ_THREADS / 32)
+#define HZW_STEPS (HZ_CHUNK / 128)
+#define HZW_ITEMS (HZ_CHUNK / 32)
+#define HZW_DENSE 128 /* marked groups (of 512) from which a chunk is walked lane by lane (see hz_walk) */
+
+DSV_D int nth_set_bit(unsigned m, int n)
 {
-    base = chunk_local * HZ_CHUNK + (int) threadIdx.x * HZ_ITEMS;
-    unsigned long long mine = KEY_NONE;
-    const int total = J.rg.base[HZ_NREG];
-    HzCursor cur;
-    bool all_zero = false;
-    if (base < total) {
-        hz_locate(J.rg, base, cur);
-        /* the thread's 8 positions usually sit in one row of one region, contiguous in memory: two 16-byte loads
-         * tell whether there is anything to quantise at all (rarely, in a P picture) */
-        const HzRegions &rg = J.rg;
-        const int r = cur.r, lvl = rg.lvl[r];
-        const bool dv = r > 0 && lvl >= 2 && (J.dg.dvx[lvl - 1] >= 0 || J.dg.dvy[lvl - 1] >= 0);
-        if (!dv && cur.x + HZ_ITEMS <= rg.sw[r] && !(r == 0 && (cur.x | cur.y) == 0)) {
-            const int32_t *p = J.coef + (size_t) (rg.y0[r] + cur.y) * J.cw + rg.x0[r] + cur.x;
-            if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-                const int4 a = *reinterpret_cast<const int4 *>(p), b = *reinterpret_cast<const int4 *>(p + 4);
-                all_zero = (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) == 0;
-            }
-        }
+    for (int i = 0; i < n; i++) {
+        m &= m - 1;
     }
-#pragma unroll
-    for (int i = 0; i < HZ_ITEMS; i++) {
-        sym[i] = 0;
-        if (!all_zero && base + i < total) {
-            sym[i] = hz_symbol_at(J, cur);
-            hz_advance(J.rg, cur);
-        }
-        if (sym[i]) {
-            mine = mk_key(base + i, sym[i]);
-        }
-    }
-    excl_key = block_scan_excl<OpMaxS64>(mine, scratch, &chunk_last);
+    return __ffs((int) m) - 1;
 }
 
-#define HZ_CPB 1 /* chunks per CTA (measured: 8 is slower; most chunks of a P picture still hold a few non-zeros) */
-
-/* (re)load the job record of `chunk` into shared memory unless the cached one already covers it */
-DSV_D void hz_cache_job(HzJob *sJ, int *s_have, const HzJob *jobs, int njobs, int chunk, const HzMap &map)
+/* can the 4 positions starting at the cursor be zero-tested with one aligned 16-byte load? (then *p is its address) */
+DSV_D bool hz_group_plain(const HzJob &J, const HzCursor &c, const int32_t **p)
 {
-    __syncthreads(); /* everybody is done with the previous chunk (and with *sJ) */
-    const bool hit = *s_have && chunk >= sJ->chunk_base && chunk < sJ->chunk_base + sJ->nchunks;
-    __syncthreads();
-    if (!hit) {
-        const int jid = hz_job_of_chunk(jobs, njobs, chunk, map);
-        const int *src = reinterpret_cast<const int *>(&jobs[jid]);
-        int *dst = reinterpret_cast<int *>(sJ);
-        for (int i = threadIdx.x; i < (int) (sizeof(HzJob) / sizeof(int)); i += HZ_THREADS) {
-            dst[i] = src[i];
-        }
-        if (threadIdx.x == 0) {
-            *s_have = 1;
-        }
-        __syncthreads();
+    const HzRegions &rg = J.rg;
+    const int r = c.r;
+    if (c.x + 4 > rg.sw[r] || (r == 0 && (c.x | c.y) == 0)) {
+        return false;
     }
+    const int ax = rg.x0[r] + c.x, ay = rg.y0[r] + c.y, lvl = rg.lvl[r];
+    if (r > 0 && lvl >= 2) { /* first visits of double-visited positions live in the side buffer */
+        const DvGeom &g = J.dg;
+        const int L = lvl - 1;
+        if ((g.dvx[L] >= ax && g.dvx[L] < ax + 4 && ay < g.dvey[L]) || (ay == g.dvy[L] && ax < g.dvex[L])) {
+            return false;
+        }
+    }
+    *p = J.coef + (size_t) ay * J.cw + ax;
+    return (reinterpret_cast<uintptr_t>(*p) & 15) == 0;
 }
 
-#ifndef HZ_SCAN_MINB
-#define HZ_SCAN_MINB 8 /* measured: 8 -> 252 us, default (40 registers) -> 268 */
-#endif
-__global__ void __launch_bounds__(HZ_THREADS, HZ_SCAN_MINB) hzcc_scan_kernel(const HzJob *jobs, int njobs, HzChunk *chunks, int total_chunks, const HzMap map)
+/* a lane's group in a round: its non-zeros in scan order */
+struct HzGroup {
+    int cnt;
+    int pos[4], sym[4];
+};
+
+template <class Visitor> DSV_D void hz_chunk_rounds(const HzJob &J, int cbase, int total, int lane, Visitor &V)
 {
-    __shared__ HzJob J;
-    __shared__ unsigned long long scratch[40];
-    __shared__ int s_first, s_have;
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-        s_have = 0;
-    }
-    for (int ci = 0; ci < HZ_CPB; ci++) {
-        const int chunk = (int) blockIdx.x * HZ_CPB + ci;
-        if (chunk >= total_chunks) {
-            return;
+    const HzRegions &rg = J.rg;
+    unsigned marks[HZW_STEPS];
+    {
+        HzCursor c;
+        int pos = cbase + 4 * lane;
+        if (pos < total) {
+            hz_locate(rg, pos, c);
         }
-        hz_cache_job(&J, &s_have, jobs, njobs, chunk, map);
-        if (tid == 0) {
-            s_first = -1;
-        }
-        __syncthreads();
-
-        int sym[HZ_ITEMS], base;
-        unsigned long long excl, last;
-        chunk_load(J, chunk - J.chunk_base, sym, base, scratch, excl, last);
-
-        int prev_pos = key_pos(excl), prev_sym = key_sym(excl);
-        unsigned bits = 0, cnt = 0;
 #pragma unroll
-        for (int i = 0; i < HZ_ITEMS; i++) {
-            if (sym[i]) {
-                if (prev_pos >= 0) {
-                    bits += group_bits(base + i, prev_pos, prev_sym);
-                } else {
-                    s_first = base + i; /* exactly one thread sees the chunk's first non-zero */
+        for (int k = 0; k < HZW_STEPS; k++) {
+            bool mark = false;
+            if (pos < total) {
+                mark = true;
+                const int32_t *p;
+                if (pos + 4 <= total && hz_group_plain(J, c, &p)) {
+                    const int4 v = *reinterpret_cast<const int4 *>(p);
+                    mark = (v.x | v.y | v.z | v.w) != 0;
                 }
-                prev_pos = base + i;
-                prev_sym = sym[i];
-                cnt++;
+                /* 128 positions on */
+                pos += 128;
+                if (pos < total) {
+                    c.x += 128;
+                    while (c.x >= rg.sw[c.r]) {
+                        c.x -= rg.sw[c.r];
+                        if (++c.y == rg.sh[c.r]) {
+                            c.y = 0;
+                            c.r++;
+                        }
+                    }
+                }
+            }
+            marks[k] = __ballot_sync(0xffffffffu, mark);
+        }
+    }
+    int G = 0;
+#pragma unroll
+    for (int k = 0; k < HZW_STEPS; k++) {
+        G += __popc(marks[k]);
+    }
+    if (G >= HZW_DENSE) {
+        V.dense(J, cbase + lane * HZW_ITEMS, imin(total, cbase + HZ_CHUNK), lane);
+        return;
+    }
+    for (int g0 = 0; g0 < G; g0 += 32) {
+        HzGroup grp;
+        grp.cnt = 0;
+        int n = g0 + lane;
+        if (n < G) {
+            int k = 0;
+#pragma unroll
+            for (int kk = 0; kk < HZW_STEPS; kk++) { /* marks[] is indexed by constants only: it stays in registers */
+                const int c = __popc(marks[kk]);
+                if (n >= 0 && n < c) {
+                    k = 128 * kk + 4 * nth_set_bit(marks[kk], n);
+                    n = -1;
+                } else if (n >= 0) {
+                    n -= c;
+                }
+            }
+            const int pos = cbase + k;
+            HzCursor c;
+            hz_locate(rg, pos, c);
+            const int e_end = imin(4, total - pos);
+            for (int e = 0; e < e_end; e++) {
+                const int sym = hz_symbol_at(J, c);
+                hz_advance(rg, c);
+                if (sym) {
+                    grp.pos[grp.cnt] = pos + e;
+                    grp.sym[grp.cnt] = sym;
+                    grp.cnt++;
+                }
             }
         }
-        unsigned long long tot;
-        block_scan_incl<OpAdd64>(((unsigned long long) cnt << 40) | bits, scratch, &tot);
-        if (tid == 0) {
-            HzChunk c;
-            c.cnt = (int) (tot >> 40);
-            c.bits_inner = (unsigned) (tot & 0xFFFFFFFFFFull);
-            c.first_pos = s_first;
-            c.last_pos = key_pos(last);
-            c.last_sym = key_sym(last);
-            c.prev_pos = -1;
-            c.prev_sym = 0;
-            c.bit_off = 0;
-            chunks[chunk] = c;
+        V.round(grp, lane);
+    }
+}
+
+/* last non-zero of the lanes before this one (KEY_NONE if there is none); *all = the last of the whole warp */
+DSV_D unsigned long long warp_prev_key(unsigned long long key, int lane, unsigned long long *all)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long n = __shfl_up_sync(0xffffffffu, key, o);
+        if (lane >= o) {
+            key = OpMaxS64::apply(n, key);
         }
+    }
+    *all = __shfl_sync(0xffffffffu, key, 31);
+    const unsigned long long ex = __shfl_up_sync(0xffffffffu, key, 1);
+    return lane == 0 ? KEY_NONE : ex;
+}
+
+/* what a lane contributes to its chunk: its non-zeros' count, first position, last (position, symbol), and the bits of
+ * the groups whose predecessor is the lane's own */
+struct HzSummary {
+    int cnt, first_pos;
+    unsigned long long last_key;
+    unsigned bits;
+};
+DSV_D HzSummary hz_group_summary(const HzGroup &g)
+{
+    HzSummary s;
+    s.cnt = g.cnt;
+    s.first_pos = g.cnt ? g.pos[0] : -1;
+    s.last_key = KEY_NONE;
+    s.bits = 0;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        if (e < g.cnt) {
+            s.last_key = mk_key(g.pos[e], g.sym[e]);
+            if (e > 0) {
+                s.bits += group_bits(g.pos[e], g.pos[e - 1], g.sym[e - 1]);
+            }
+        }
+    }
+    return s;
+}
+
+/*
+ * Dense chunks (I pictures: most groups hold something) skip the rounds: a lane walks its own 64 consecutive scan
+ * positions, so the per-round shuffles are paid once per chunk instead of once per 32 groups.
+ */
+
+template <class F> DSV_D void hz_walk(const HzJob &J, int base, int total, F on_nonzero)
+{
+    if (base >= total) {
+        return;
+    }
+    const HzRegions &rg = J.rg;
+    const int end = imin(base + HZW_ITEMS, total);
+    HzCursor c;
+    hz_locate(rg, base, c);
+    int pos = base;
+    while (pos < end) {
+        const int32_t *p;
+        if (pos + 4 <= end && hz_group_plain(J, c, &p)) {
+            const int4 v = *reinterpret_cast<const int4 *>(p);
+            if ((v.x | v.y | v.z | v.w) == 0) {
+                pos += 4;
+                c.x += 4;
+                if (c.x == rg.sw[c.r]) {
+                    c.x = 0;
+                    if (++c.y == rg.sh[c.r]) {
+                        c.y = 0;
+                        c.r++;
+                    }
+                }
+                continue;
+            }
+        }
+        const int sym = hz_symbol_at(J, c);
+        hz_advance(rg, c);
+        if (sym) {
+            on_nonzero(pos, sym);
+        }
+        pos++;
+    }
+}
+DSV_D HzSummary hz_walk_summary(const HzJob &J, int base, int total)
+{
+    HzSummary s;
+    s.cnt = 0;
+    s.first_pos = -1;
+    s.last_key = KEY_NONE;
+    s.bits = 0;
+    int prev_pos = -1, prev_sym = 0;
+    hz_walk(J, base, total, [&](int pos, int sym) {
+        if (prev_pos >= 0) {
+            s.bits += group_bits(pos, prev_pos, prev_sym);
+        } else {
+            s.first_pos = pos;
+        }
+        prev_pos = pos;
+        prev_sym = sym;
+        s.cnt++;
+    });
+    if (s.cnt) {
+        s.last_key = mk_key(prev_pos, prev_sym);
+    }
+    return s;
+}
+
+/* chunk summary, accumulated over rounds (or one walk) */
+struct HzScanAcc {
+    unsigned long long carry = KEY_NONE; /* last non-zero of the chunk so far */
+    unsigned cnt = 0, bits = 0;
+    int first = -1;
+    DSV_D void add(const HzSummary &s, int lane)
+    {
+        unsigned long long all;
+        unsigned long long ex = warp_prev_key(s.last_key, lane, &all);
+        if (key_pos(ex) < 0) {
+            ex = carry;
+        }
+        unsigned b = s.bits;
+        int f = 0x7fffffff;
+        if (s.cnt) {
+            if (key_pos(ex) >= 0) {
+                b += group_bits(s.first_pos, key_pos(ex), key_sym(ex));
+            } else {
+                f = s.first_pos; /* the chunk's first non-zero: its group depends on earlier chunks */
+            }
+        }
+        cnt += __reduce_add_sync(0xffffffffu, (unsigned) s.cnt);
+        bits += __reduce_add_sync(0xffffffffu, b);
+        f = __reduce_min_sync(0xffffffffu, f);
+        if (f != 0x7fffffff) {
+            first = f;
+        }
+        carry = OpMaxS64::apply(carry, all);
+    }
+};
+struct HzScanVisitor {
+    HzScanAcc acc;
+    DSV_D void round(const HzGroup &g, int lane) { acc.add(hz_group_summary(g), lane); }
+    DSV_D void dense(const HzJob &J, int base, int total, int lane) { acc.add(hz_walk_summary(J, base, total), lane); }
+};
+
+__global__ void __launch_bounds__(HZ_THREADS) hzcc_scan_kernel(const HzJob *jobs, int njobs, HzChunk *chunks, int total_chunks, const HzMap map)
+{
+    const int lane = threadIdx.x & 31;
+    const int chunk = (int) blockIdx.x * HZW_WARPS + (threadIdx.x >> 5);
+    if (chunk >= total_chunks) {
+        return;
+    }
+    const HzJob &J = jobs[hz_job_of_chunk(jobs, njobs, chunk, map)];
+    HzScanVisitor V;
+    hz_chunk_rounds(J, (chunk - J.chunk_base) * HZ_CHUNK, J.rg.base[HZ_NREG], lane, V);
+    if (lane == 0) {
+        HzChunk c;
+        c.cnt = (int) V.acc.cnt;
+        c.bits_inner = V.acc.bits;
+        c.first_pos = V.acc.first;
+        c.last_pos = key_pos(V.acc.carry);
+        c.last_sym = key_sym(V.acc.carry);
+        c.prev_pos = -1;
+        c.prev_sym = 0;
+        c.bit_off = 0;
+        chunks[chunk] = c;
     }
 }
 
@@ -441,71 +621,156 @@ DSV_D void or_bits_atomic(unsigned *words, unsigned long long bitpos, int len, u
     }
 }
 
-#ifndef HZ_PACK_MINB
-#define HZ_PACK_MINB 8 /* measured: 8 -> 193 us, 6 -> 202, default (48 registers) -> 216 */
-#endif
-__global__ void __launch_bounds__(HZ_THREADS, HZ_PACK_MINB) hzcc_pack_kernel(const HzJob *jobs, int njobs, const HzChunk *chunks,
-                                                               const HzFrame *frames, int total_chunks, const HzMap map)
-{
-    __shared__ HzJob J;
-    __shared__ unsigned long long scratch[40];
-    __shared__ int s_have;
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-        s_have = 0;
+/* a lane's contiguous piece of the bit stream: whole 32-bit words are stored plainly (the packet starts zeroed and
+ * nobody else owns a bit of them), only the first and last word, shared with the neighbours, are OR-ed atomically */
+struct HzBitWriter {
+    unsigned *words;
+    unsigned long long wi; /* next word */
+    unsigned long long acc;
+    int n;                 /* pending bits in acc (low n bits), < 32 after put() */
+    bool first;
+    DSV_D void begin(unsigned *w, unsigned long long bitpos)
+    {
+        words = w;
+        wi = bitpos >> 5;
+        n = (int) (bitpos & 31); /* the bits before our start belong to someone else: zeros here, OR-ed in */
+        acc = 0;
+        first = true;
     }
-    __syncthreads();
-    for (int ci = 0; ci < HZ_CPB; ci++) {
-        const int chunk = (int) blockIdx.x * HZ_CPB + ci;
-        if (chunk >= total_chunks) {
-            return;
+    DSV_D void flush_word(unsigned be)
+    {
+        const unsigned v = __byte_perm(be, 0, 0x0123); /* big-endian bit order in little-endian words */
+        if (first) {
+            atomicOr(&words[wi], v);
+            first = false;
+        } else {
+            words[wi] = v;
         }
-        const HzChunk C = chunks[chunk];
-        if (C.cnt == 0) {
-            continue; /* nothing to write (most chunks of a P picture); uniform for the whole block */
+        wi++;
+    }
+    DSV_D void put32(int len, unsigned code) /* len <= 32 */
+    {
+        acc = (acc << len) | (unsigned long long) code;
+        n += len;
+        if (n >= 32) {
+            flush_word((unsigned) (acc >> (n - 32)));
+            n -= 32;
         }
-        hz_cache_job(&J, &s_have, jobs, njobs, chunk, map);
-        int sym[HZ_ITEMS], base;
-        unsigned long long excl, last;
-        chunk_load(J, chunk - J.chunk_base, sym, base, scratch, excl, last);
+    }
+    DSV_D void put(int len, unsigned long long code) /* len <= 64 */
+    {
+        if (len > 32) {
+            put32(len - 32, (unsigned) (code >> 32));
+            put32(32, (unsigned) code);
+        } else {
+            put32(len, (unsigned) code);
+        }
+    }
+    DSV_D void end()
+    {
+        if (n > 0) {
+            atomicOr(&words[wi], __byte_perm((unsigned) (acc << (32 - n)), 0, 0x0123));
+        }
+    }
+};
 
-        int prev_pos = key_pos(excl), prev_sym = key_sym(excl);
-        if (prev_pos < 0) { /* nothing earlier in this chunk: continue from the previous chunks */
-            prev_pos = C.prev_pos;
-            prev_sym = C.prev_sym;
+/* bit offsets, accumulated over rounds (or one walk) */
+struct HzPackAcc {
+    unsigned long long carry; /* last non-zero before this round: from the previous chunks at first */
+    unsigned long long off;   /* bit position of this round's first group */
+    DSV_D void place(const HzSummary &s, int lane, int &prev_pos, int &prev_sym, unsigned long long &at)
+    {
+        unsigned long long all;
+        unsigned long long ex = warp_prev_key(s.last_key, lane, &all);
+        if (key_pos(ex) < 0) {
+            ex = carry;
         }
-        const int pp0 = prev_pos, ps0 = prev_sym;
-        unsigned long long bits = 0;
-    #pragma unroll
-        for (int i = 0; i < HZ_ITEMS; i++) {
-            if (sym[i]) {
-                bits += group_bits(base + i, prev_pos, prev_sym);
-                prev_pos = base + i;
-                prev_sym = sym[i];
+        prev_pos = key_pos(ex);
+        prev_sym = key_sym(ex);
+        unsigned mybits = s.bits;
+        if (s.cnt) {
+            mybits += group_bits(s.first_pos, prev_pos, prev_sym);
+        }
+        unsigned incl = mybits;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) {
+                incl += n;
             }
         }
-        unsigned long long tot;
-        unsigned long long off = C.bit_off + block_scan_excl<OpAdd64>(bits, scratch, &tot);
-        unsigned *words = reinterpret_cast<unsigned *>(frames[J.frame].pkt);
-        prev_pos = pp0;
-        prev_sym = ps0;
-    #pragma unroll
-        for (int i = 0; i < HZ_ITEMS; i++) {
-            if (sym[i]) {
-                unsigned run = (unsigned) (base + i - prev_pos - 1);
+        at = off + (unsigned long long) (incl - mybits);
+        off += (unsigned long long) __shfl_sync(0xffffffffu, incl, 31);
+        carry = OpMaxS64::apply(carry, all);
+    }
+};
+struct HzPackVisitor {
+    HzPackAcc acc;
+    unsigned *words;
+    DSV_D void round(const HzGroup &g, int lane)
+    {
+        int prev_pos, prev_sym;
+        unsigned long long at;
+        acc.place(hz_group_summary(g), lane, prev_pos, prev_sym, at);
+#pragma unroll
+        for (int e = 0; e < 4; e++) { /* every non-zero ORs its group (UEG(run) ++ NEG(prev)) at its bit offset */
+            if (e < g.cnt) {
+                const unsigned run = (unsigned) (g.pos[e] - prev_pos - 1);
                 int l = ueg_len(run);
-                or_bits_atomic(words, off, l, ueg_code(run));
-                off += (unsigned long long) l;
+                or_bits_atomic(words, at, l, ueg_code(run));
+                at += (unsigned long long) l;
                 if (prev_pos >= 0) {
                     l = neg_len(prev_sym);
-                    or_bits_atomic(words, off, l, neg_code(prev_sym));
-                    off += (unsigned long long) l;
+                    or_bits_atomic(words, at, l, neg_code(prev_sym));
+                    at += (unsigned long long) l;
                 }
-                prev_pos = base + i;
-                prev_sym = sym[i];
+                prev_pos = g.pos[e];
+                prev_sym = g.sym[e];
             }
         }
     }
+    DSV_D void dense(const HzJob &J, int base, int total, int lane)
+    {
+        int prev_pos, prev_sym;
+        unsigned long long at;
+        const HzSummary s = hz_walk_summary(J, base, total);
+        acc.place(s, lane, prev_pos, prev_sym, at);
+        if (s.cnt == 0) {
+            return;
+        }
+        HzBitWriter bw;
+        bw.begin(words, at);
+        hz_walk(J, base, total, [&](int pos, int sym) {
+            const unsigned run = (unsigned) (pos - prev_pos - 1);
+            bw.put(ueg_len(run), ueg_code(run));
+            if (prev_pos >= 0) {
+                bw.put(neg_len(prev_sym), neg_code(prev_sym));
+            }
+            prev_pos = pos;
+            prev_sym = sym;
+        });
+        bw.end();
+    }
+};
+
+__global__ void __launch_bounds__(HZ_THREADS) hzcc_pack_kernel(const HzJob *jobs, int njobs, const HzChunk *chunks,
+                                                               const HzFrame *frames, int total_chunks, const HzMap map)
+{
+    const int lane = threadIdx.x & 31;
+    const int chunk = (int) blockIdx.x * HZW_WARPS + (threadIdx.x >> 5);
+    if (chunk >= total_chunks) {
+        return;
+    }
+    const HzChunk C = chunks[chunk];
+    if (C.cnt == 0) {
+        return; /* nothing to write; uniform for the warp */
+    }
+    const HzJob &J = jobs[hz_job_of_chunk(jobs, njobs, chunk, map)];
+    HzPackVisitor V;
+    V.acc.carry = mk_key(C.prev_pos, C.prev_sym);
+    V.acc.off = C.bit_off;
+    V.words = reinterpret_cast<unsigned *>(frames[J.frame].pkt);
+    hz_chunk_rounds(J, (chunk - J.chunk_base) * HZ_CHUNK, J.rg.base[HZ_NREG], lane, V);
 }
 
 void hzcc_enc_launch(const HzJob *d_jobs, int njobs, HzChunk *d_chunks, int total_chunks,
@@ -516,11 +781,11 @@ void hzcc_enc_launch(const HzJob *d_jobs, int njobs, HzChunk *d_chunks, int tota
     map.c0 = chunks_y;
     map.c1 = chunks_u;
     map.per_pic_fd = make_fastdiv(chunks_per_pic > 0 ? chunks_per_pic : 1);
-    DSV_LAUNCH(hzcc_scan_kernel, dim3(ceil_div(total_chunks, HZ_CPB)), dim3(HZ_THREADS), 0, st, d_jobs, njobs, d_chunks, total_chunks, map);
+    DSV_LAUNCH(hzcc_scan_kernel, dim3(ceil_div(total_chunks, HZW_WARPS)), dim3(HZ_THREADS), 0, st, d_jobs, njobs, d_chunks, total_chunks, map);
     KERNEL_CHECK();
     DSV_LAUNCH(hzcc_prefix_kernel, dim3(nframes), dim3(HZP_THREADS), 0, st, d_jobs, d_chunks, d_frames);
     KERNEL_CHECK();
-    DSV_LAUNCH(hzcc_pack_kernel, dim3(ceil_div(total_chunks, HZ_CPB)), dim3(HZ_THREADS), 0, st, d_jobs, njobs, d_chunks, d_frames, total_chunks, map);
+    DSV_LAUNCH(hzcc_pack_kernel, dim3(ceil_div(total_chunks, HZW_WARPS)), dim3(HZ_THREADS), 0, st, d_jobs, njobs, d_chunks, d_frames, total_chunks, map);
     KERNEL_CHECK();
 }
 

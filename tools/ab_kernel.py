@@ -4,6 +4,7 @@ import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
 import torch, dsvlibs as L, bench
+bench.GOP = int(os.environ.get("AB_GOP", bench.GOP))  # AB_GOP=0: intra-only pictures
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 W, H, FMT, NFR = bench.W, bench.H, bench.FMT, bench.NFR
 gpu = L.gpu(); lib = gpu.lib; sub = L.SUBSAMP[FMT]; fb = L.frame_bytes(W, H, sub); seq = fb * NFR
@@ -29,7 +30,7 @@ es, ds = enc.stats(), dec.stats()
 import hashlib
 print(os.path.basename(L.GPU_SO), "step %.2f ms" % (dt * 1e3),
       "bmc enc %.1f us dec %.1f us" % (1e3 * es["bmc_ms"] / max(es["bmc_launches"], 1), 1e3 * ds["bmc_ms"] / max(ds["bmc_launches"], 1)),
-      "fwd %.1f inv %.1f/%.1f us" % (1e3 * es["sbt_fwd_ms"] / es["sbt_fwd_launches"], 1e3 * es["sbt_inv_ms"] / es["sbt_inv_launches"], 1e3 * ds["sbt_inv_ms"] / ds["sbt_inv_launches"]),
+      "fwd %.1f inv %.1f/%.1f us" % (1e3 * es["sbt_fwd_ms"] / es["sbt_fwd_launches"], 1e3 * es["sbt_inv_ms"] / max(es["sbt_inv_launches"], 1), 1e3 * ds["sbt_inv_ms"] / ds["sbt_inv_launches"]),
       "out md5", hashlib.md5(d_out[:fb * 3].cpu().numpy().tobytes()).hexdigest()[:8])
 
 ek, dk = enc.kernel_times(), dec.kernel_times()
