@@ -12,6 +12,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <new>
+
 #ifndef DSV_CPU_EMU
 #include <cuda_runtime.h>
 /* every launch goes through here: when the calling thread has a KernelTimes collector active (an engine step,
@@ -30,17 +32,42 @@
 #define DSV_HD __host__ __device__ __forceinline__
 #define DSV_D __device__ __forceinline__
 
-/* Any CUDA failure is fatal: there is no CPU fallback to continue on. */
+/* There is no CPU fallback to continue on, but a CUDA failure (out of memory, lost device) must not take the caller's
+ * process down either: it is logged and thrown as dsv::CudaError, and every C entry point turns that into the
+ * reference's own error return (dsv_enc: no packets + DSV_ERROR, dsv_dec: DSV_DEC_ERROR, dsvb_ / dsvk_: negative / NULL). */
+namespace dsv {
+struct CudaError {
+    int code;
+};
+struct Unsupported {
+};
+[[noreturn]] void cuda_fail(int code, const char *msg, const char *file, int line, const char *expr);
+} // namespace dsv
 #define CUDA_CHECK(expr)                                                                            \
     do {                                                                                            \
         cudaError_t e_ = (expr);                                                                    \
         if (e_ != cudaSuccess) {                                                                    \
-            fprintf(stderr, "[dsv1_b200] CUDA error %d (%s) at %s:%d: %s\n", (int) e_,              \
-                    cudaGetErrorString(e_), __FILE__, __LINE__, #expr);                             \
-            abort();                                                                                \
+            dsv::cuda_fail((int) e_, cudaGetErrorString(e_), __FILE__, __LINE__, #expr);            \
         }                                                                                           \
     } while (0)
 #define KERNEL_CHECK() CUDA_CHECK(cudaGetLastError())
+/* first and last line of a C entry point's body: nothing thrown below crosses the C ABI */
+#define DSV_API_BEGIN try {
+#define DSV_API_END(ret)                                                                            \
+    }                                                                                               \
+    catch (const dsv::CudaError &)                                                                  \
+    {                                                                                               \
+        return ret;                                                                                 \
+    }                                                                                               \
+    catch (const dsv::Unsupported &)                                                                \
+    {                                                                                               \
+        return ret;                                                                                 \
+    }                                                                                               \
+    catch (const std::bad_alloc &)                                                                  \
+    {                                                                                               \
+        fprintf(stderr, "[dsv1_b200] out of host memory\n");                                        \
+        return ret;                                                                                 \
+    }
 
 namespace dsv {
 

@@ -115,6 +115,7 @@ static void fill_stats(const EngineStats &s, int device, int lanes, double *out)
 
 extern "C" DSVB_ENC *dsvb_enc_create(const int *cfg, int lanes, int device)
 {
+    DSV_API_BEGIN
     if (lanes < 1 || lanes > 1024) {
         return nullptr;
     }
@@ -131,6 +132,7 @@ extern "C" DSVB_ENC *dsvb_enc_create(const int *cfg, int lanes, int device)
     e->eng = new EncEngine(probe.vidmeta, probe.gop, probe.pyramid_levels, lanes);
     release_state(&probe);
     return e;
+    DSV_API_END(nullptr)
 }
 
 extern "C" void dsvb_enc_destroy(DSVB_ENC *e)
@@ -172,6 +174,7 @@ extern "C" void dsvb_enc_kernel_times(DSVB_ENC *e, double *ms, double *launches,
 extern "C" int dsvb_encode(DSVB_ENC *e, int nseq, int nframes, const uint8_t *const *yuv, int on_device,
                            uint8_t *const *streams, const long *caps, long *lens)
 {
+    DSV_API_BEGIN
     use_device(e->device);
     const CodecGeom &g = e->eng->geom();
     const int L = e->lanes;
@@ -236,6 +239,7 @@ extern "C" int dsvb_encode(DSVB_ENC *e, int nseq, int nframes, const uint8_t *co
         }
     }
     return rc;
+    DSV_API_END(-100)
 }
 
 extern "C" DSVB_DEC *dsvb_dec_create(int lanes, int device)
@@ -318,6 +322,7 @@ static unsigned be32(const uint8_t *p) { return ((unsigned) p[0] << 24) | ((unsi
 extern "C" int dsvb_decode(DSVB_DEC *d, int nseq, const uint8_t *const *streams, const uint8_t *const *streams_dev,
                            const long *lens, uint8_t *const *out, const long *out_caps, int out_on_device, int *frames)
 {
+    DSV_API_BEGIN
     use_device(d->device);
     const int L = d->lanes;
     int rc = 0;
@@ -441,23 +446,28 @@ extern "C" int dsvb_decode(DSVB_DEC *d, int nseq, const uint8_t *const *streams,
         d->eng->flush(); /* the last pictures are still leaving on the copy stream */
     }
     return rc;
+    DSV_API_END(-100)
 }
 
 extern "C" void *dsvb_host_alloc(size_t bytes)
 {
+    DSV_API_BEGIN
     void *p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
         return nullptr;
     }
     return p;
+    DSV_API_END(nullptr)
 }
 
 extern "C" void dsvb_host_free(void *p) { cudaFreeHost(p); }
 
 extern "C" int dsvb_synth_device(int w, int h, int subsamp, int start, int n, int seed, int cut, uint8_t *d_out, int device)
 {
+    DSV_API_BEGIN
     use_device(device);
     synth_launch(w, h, (subsamp >> 2) & 3, subsamp & 3, start, n, seed, cut, d_out, 0);
     CUDA_CHECK(cudaDeviceSynchronize());
     return 0;
+    DSV_API_END(-100)
 }

@@ -642,6 +642,7 @@ void dsv::parse_metadata_packet(const uint8_t *pkt, unsigned len, DSV_META *m) /
 
 extern "C" int dsv_dec(DSV_DECODER *d, DSV_BUF *buffer, DSV_FRAME **out, DSV_FNUM *fn)
 {
+    DSV_API_BEGIN
     *fn = (DSV_FNUM) -1;
     const uint8_t *pkt = buffer->data;
     const unsigned pkt_len = buffer->len;
@@ -708,4 +709,5 @@ extern "C" int dsv_dec(DSV_DECODER *d, DSV_BUF *buffer, DSV_FRAME **out, DSV_FNU
     dsv_buf_free(buffer);
     *out = f;
     return DSV_DEC_OK;
+    DSV_API_END(DSV_DEC_ERROR)
 }

@@ -351,7 +351,7 @@ EncEngine::EncEngine(const DSV_META &md, int gop, int pyramid_levels, int lanes)
     if (!meta_supported(md)) {
         DSV_ERROR(("unsupported picture format %dx%d subsamp %d: width and height must be even and >= 16", md.width,
                    md.height, md.subsamp));
-        exit(-1);
+        throw Unsupported();
     }
     CUDA_CHECK(cudaGetDevice(&device));
     plan_geometry(&g_, md.width, md.height, md.subsamp);
@@ -412,10 +412,16 @@ void EncEngine::alloc_lane(EncLane &l)
         CUDA_CHECK(cudaMalloc(&l.dv[p], sbt_dv_elems(g.cw[p], g.ch[p]) * sizeof(int32_t)));
         CUDA_CHECK(cudaMemset(l.dv[p], 0, sbt_dv_elems(g.cw[p], g.ch[p]) * sizeof(int32_t)));
     }
-    /* packet upper bound as in dsv_encoder.c:472-491 */
+    /* The reference sizes its packet by a heuristic (w*h*{2,4,6}, dsv_encoder.c:472-491) that noise-like content at
+     * top quality can exceed.  Here the bound is structural: a coefficient costs at most UEG(run = 0) + NEG(symbol)
+     * = 1 + 2 * 17 + 2 bits for symbols below 2^17 (8-bit samples through 6 levels of 3.2x LL gain, divided by a
+     * quantiser >= 16, stay below 2^14), i.e. < 4.75 bytes; hzcc_prefix_kernel refuses what still would not fit. */
     size_t ub = (size_t) g.w * g.h;
     ub *= (g.subsamp == DSV_SUBSAMP_444) ? 6 : (g.subsamp == DSV_SUBSAMP_422) ? 4 : 2;
-    const size_t pkt_cap = ub + 4096 + (size_t) g.nblk * 48;
+    size_t pkt_cap = ub + 4096 + (size_t) g.nblk * 48;
+    const size_t bound = g.coef_total * 19 / 4 + 4096 + (size_t) g.nblk * 48;
+    pkt_cap = ((pkt_cap > bound ? pkt_cap : bound) + 255) & ~(size_t) 255;
+    l.pkt_cap = pkt_cap;
     CUDA_CHECK(cudaMalloc(&l.d_pkt, pkt_cap));
     CUDA_CHECK(cudaMemset(l.d_pkt, 0, pkt_cap));
     CUDA_CHECK(cudaMallocHost(&l.h_head, 512 + (size_t) g.nblk * 48));
@@ -864,6 +870,7 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         HzFrame &hf = h_frames_[k];
         memset(&hf, 0, sizeof(hf));
         hf.pkt = l.d_pkt;
+        hf.cap = (unsigned) l.pkt_cap;
         hf.start_byte = l.head_bytes;
         hf.nplanes = 3;
         hf.job[0] = 3 * k;
@@ -900,6 +907,15 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         const unsigned total = h_frames_[k].total_bytes;
         DSV_BUF outbuf;
         int nb = 0;
+        if (h_frames_[k].overflow) { /* cannot happen for 8-bit input (see alloc_lane); never trust the size if it does */
+            DSV_ERROR(("coded picture does not fit the packet buffer (%u bytes): picture dropped", (unsigned) l.pkt_cap));
+            l.pkt_dirty = (unsigned) l.pkt_cap - 64;
+            nbufs[k] = 0;
+            if (sinks) {
+                sinks[k].overflow = 1;
+            }
+            continue;
+        }
         if (sinks) { /* caller-provided stream memory: metadata packet, then the picture, back to back */
             PktSink &sk = sinks[k];
             if (l.gop_start) {
@@ -990,6 +1006,9 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         }
         if (l.has_ref) {
             enc->refresh_ctr++;
+        }
+        if (nbufs[k] == 0) {
+            continue; /* picture dropped (packet overflow) */
         }
         DSV_BUF *pic = &bufs[k][nbufs[k] - 1];
         if (pic->data) {
@@ -1084,6 +1103,7 @@ void dsv::enc_prepare_state(DSV_ENCODER *enc)
 
 extern "C" int dsv_enc(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_BUF *bufs)
 {
+    DSV_API_BEGIN
     if (bufs == NULL) {
         DSV_ERROR(("null buffer list passed to encoder!"));
         return 0;
@@ -1110,4 +1130,5 @@ extern "C" int dsv_enc(DSV_ENCODER *enc, DSV_FRAME *frame, DSV_BUF *bufs)
         bufs[i] = out[0][i];
     }
     return nb;
+    DSV_API_END(0)
 }

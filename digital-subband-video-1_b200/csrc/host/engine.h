@@ -161,6 +161,7 @@ struct EncLane {
     int in_sel = 0;                 /* staging buffer the next inline copy / prefetch writes */
     const uint8_t *stage_src[2] = {nullptr, nullptr}; /* host picture on its way into / held by each staging buffer */
     unsigned pkt_dirty = 0;
+    size_t pkt_cap = 0; /* bytes allocated at d_pkt */
     uint8_t *h_head = nullptr; /* pinned: packet head assembled on the host */
     /* per-step decisions */
     DSV_FNUM fnum = 0;

@@ -56,6 +56,8 @@ struct HzChunk {
 struct HzFrame {
     uint8_t *pkt;        /* zeroed packet buffer (device) */
     unsigned start_byte; /* where plane 0 begins (after header/side info written by the host) */
+    unsigned cap;        /* bytes allocated at pkt: nothing is written at or beyond pkt + cap */
+    unsigned overflow;   /* out: the coded picture does not fit (total_bytes is then start_byte and no plane byte is valid) */
     unsigned total_bytes; /* out: packet length after the three planes */
     unsigned plane_bytes[3];
     unsigned plane_nruns[3];

@@ -512,14 +512,16 @@ __global__ void __launch_bounds__(HZP_THREADS) hzcc_prefix_kernel(const HzJob *j
     __shared__ unsigned long long scratch[40];
     __shared__ unsigned long long s_carry_key, s_carry_bits;
     __shared__ unsigned s_P;
+    __shared__ int s_overflow;
     const int tid = threadIdx.x;
     HzFrame &F = frames[blockIdx.x];
     if (tid == 0) {
         s_P = F.start_byte;
+        s_overflow = 0;
     }
     __syncthreads();
 
-    for (int p = 0; p < F.nplanes; p++) {
+    for (int p = 0; p < F.nplanes && !s_overflow; p++) {
         const HzJob &J = jobs[F.job[p]];
         HzChunk *ck = chunks + J.chunk_base;
         const int n = J.nchunks;
@@ -579,8 +581,18 @@ __global__ void __launch_bounds__(HZP_THREADS) hzcc_prefix_kernel(const HzJob *j
             total_cnt += ctot;
             __syncthreads();
         }
-        /* framing (hzcc.c:151-154,283-292,457-474) */
+        /* framing (hzcc.c:151-154,283-292,457-474).  The bit total is known before a single token is packed: a
+         * picture that does not fit its packet buffer (the reference's w*h*{2,4,6} heuristic overflows its heap
+         * there) is refused here, and hzcc_pack_kernel skips it */
         if (tid == 0) {
+            uint8_t *pkt = F.pkt;
+            unsigned long long end = token_base + total_bits;
+            if (((end + 64 + 7) >> 3) + 16 > (unsigned long long) F.cap) {
+                s_overflow = 1;
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && !s_overflow) {
             uint8_t *pkt = F.pkt;
             unsigned long long end = token_base + total_bits;
             put_bits_plain(pkt, (unsigned long long) (P + 4) * 8ull, seg_len(dc),
@@ -602,7 +614,8 @@ __global__ void __launch_bounds__(HZP_THREADS) hzcc_prefix_kernel(const HzJob *j
         __syncthreads();
     }
     if (tid == 0) {
-        F.total_bytes = s_P;
+        F.overflow = (unsigned) s_overflow;
+        F.total_bytes = s_overflow ? F.start_byte : s_P;
     }
 }
 
@@ -766,6 +779,9 @@ __global__ void __launch_bounds__(HZ_THREADS) hzcc_pack_kernel(const HzJob *jobs
         return; /* nothing to write; uniform for the warp */
     }
     const HzJob &J = jobs[hz_job_of_chunk(jobs, njobs, chunk, map)];
+    if (frames[J.frame].overflow) {
+        return; /* refused by the prefix pass: nothing of this picture is written */
+    }
     HzPackVisitor V;
     V.acc.carry = mk_key(C.prev_pos, C.prev_sym);
     V.acc.off = C.bit_off;

@@ -41,6 +41,7 @@ struct DevPlane {
 
 extern "C" int dsvk_fwd_sbt(const uint8_t *pix, int stride, int pw, int ph, int cw, int ch, int isP, int32_t *coef_out)
 {
+    DSV_API_BEGIN
     if ((cw & 1) || (ch & 1) || cw < 16 || ch < 16) {
         return -1;
     }
@@ -63,10 +64,12 @@ extern "C" int dsvk_fwd_sbt(const uint8_t *pix, int stride, int pw, int ph, int 
     CUDA_CHECK(cudaDeviceSynchronize());
     CUDA_CHECK(cudaMemcpy(coef_out, coef.p, (size_t) cw * ch * 4, cudaMemcpyDeviceToHost));
     return 0;
+    DSV_API_END(-100)
 }
 
 extern "C" int dsvk_inv_sbt(int32_t *coef_io, int cw, int ch, int q, int isP, int c, uint8_t *pix_out, int stride, int pw, int ph)
 {
+    DSV_API_BEGIN
     if ((cw & 1) || (ch & 1) || cw < 16 || ch < 16) {
         return -1;
     }
@@ -89,12 +92,14 @@ extern "C" int dsvk_inv_sbt(int32_t *coef_io, int cw, int ch, int q, int isP, in
     CUDA_CHECK(cudaDeviceSynchronize());
     CUDA_CHECK(cudaMemcpy2D(pix_out, stride, dp.origin, dp.stride, pw, ph, cudaMemcpyDeviceToHost));
     return 0;
+    DSV_API_END(-100)
 }
 
 /* forward transform with the fused quantiser, exactly as the encoder runs it (do_quant = 1) */
 extern "C" int dsvk_fwd_sbt_q(const uint8_t *pix, int stride, int pw, int ph, int cw, int ch, int isP, int c, int q,
                               const uint8_t *stable, int nbh, int nbv, int32_t *coef_out, int32_t *dv_out)
 {
+    DSV_API_BEGIN
     if ((cw & 1) || (ch & 1) || cw < 16 || ch < 16) {
         return -1;
     }
@@ -125,12 +130,14 @@ extern "C" int dsvk_fwd_sbt_q(const uint8_t *pix, int stride, int pw, int ph, in
         CUDA_CHECK(cudaMemcpy(dv_out, dv.p, (size_t) j.dg.total * 4, cudaMemcpyDeviceToHost));
     }
     return j.dg.total;
+    DSV_API_END(-100)
 }
 
 /* dsv_encode_plane semantics (hzcc.c:449-476): raw coefficients in, plane bytes out, coef <- dequantised */
 extern "C" int dsvk_encode_plane(int32_t *coef_io, int cw, int ch, int q, int isP, int c, const uint8_t *stable,
                                  int nbh, int nbv, uint8_t *out, int out_cap)
 {
+    DSV_API_BEGIN
     if ((cw & 1) || (ch & 1) || cw < 16 || ch < 16) {
         return -1;
     }
@@ -153,6 +160,7 @@ extern "C" int dsvk_encode_plane(int32_t *coef_io, int cw, int ch, int q, int is
     memset(&f, 0, sizeof(f));
     f.pkt = pkt.as<uint8_t>();
     f.start_byte = 0;
+    f.cap = (unsigned) cap;
     f.nplanes = 1;
     CUDA_CHECK(cudaMemcpy(jobs.p, &j, sizeof(j), cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(frames.p, &f, sizeof(f), cudaMemcpyHostToDevice));
@@ -160,18 +168,20 @@ extern "C" int dsvk_encode_plane(int32_t *coef_io, int cw, int ch, int q, int is
     hzcc_enc_launch(jobs.as<HzJob>(), 1, chunks.as<HzChunk>(), j.nchunks, frames.as<HzFrame>(), 1, 0);
     CUDA_CHECK(cudaDeviceSynchronize());
     CUDA_CHECK(cudaMemcpy(&f, frames.p, sizeof(f), cudaMemcpyDeviceToHost));
-    if ((int) f.total_bytes > out_cap) {
+    if (f.overflow || (int) f.total_bytes > out_cap) {
         return -2;
     }
     CUDA_CHECK(cudaMemcpy(out, pkt.p, f.total_bytes, cudaMemcpyDeviceToHost));
     CUDA_CHECK(cudaMemcpy(coef_io, coef.p, (size_t) cw * ch * 4, cudaMemcpyDeviceToHost));
     return (int) f.total_bytes;
+    DSV_API_END(-100)
 }
 
 /* dsv_decode_plane semantics (hzcc.c:478-496): `in` points just after the 32-bit plen field */
 extern "C" int dsvk_decode_plane(const uint8_t *in, int plen, int cw, int ch, int q, int isP, int c,
                                  const uint8_t *stable, int nbh, int nbv, int32_t *coef_out)
 {
+    DSV_API_BEGIN
     if ((cw & 1) || (ch & 1) || cw < 16 || ch < 16 || plen <= 0) {
         return -1;
     }
@@ -202,6 +212,7 @@ extern "C" int dsvk_decode_plane(const uint8_t *in, int plen, int cw, int ch, in
     CUDA_CHECK(cudaMemcpy(coef_out, coef.p, (size_t) cw * ch * 4, cudaMemcpyDeviceToHost));
     hzdec_plane_free(&bufs);
     return 0;
+    DSV_API_END(-100)
 }
 
 /* ---- motion: pyramid, HME, BMC ------------------------------------------------------------------ */
@@ -251,6 +262,7 @@ MotionGeom motion_geom(int w, int h, int subsamp, int blk_w, int blk_h, int leve
 
 extern "C" int dsvk_pyramid(const uint8_t *yuv, int w, int h, int subsamp, int levels, uint8_t *out, int *out_w, int *out_h)
 {
+    DSV_API_BEGIN
     if (levels < 1 || levels > 5) {
         return -1;
     }
@@ -271,11 +283,13 @@ extern "C" int dsvk_pyramid(const uint8_t *yuv, int w, int h, int subsamp, int l
         devframe_free(&f[l]);
     }
     return 0;
+    DSV_API_END(-100)
 }
 
 extern "C" int dsvk_hme(const uint8_t *src_yuv, const uint8_t *ref_yuv, int w, int h, int subsamp, int blk_w, int blk_h,
                         int levels, void *mv_out)
 {
+    DSV_API_BEGIN
     if (levels < 0 || levels > 5) {
         return -1;
     }
@@ -313,6 +327,7 @@ extern "C" int dsvk_hme(const uint8_t *src_yuv, const uint8_t *ref_yuv, int w, i
         devframe_free(&rf[l]);
     }
     return nintra * 100 / nblk;
+    DSV_API_END(-100)
 }
 
 /* a caller's host frame -> device frame, border included when the caller's frame has one (the search reads it) */
@@ -338,6 +353,7 @@ static void upload_host_frame(DevFrame *f, const DSV_FRAME *src)
 /* drop-in for the reference's exported dsv_hme (dsv_encoder.h:122-132, hme.c:730-741) */
 extern "C" int dsv_hme(DSV_HME *hme)
 {
+    DSV_API_BEGIN
     const DSV_PARAMS *pr = hme->params;
     const int levels = hme->levels;
     if (levels < 0 || levels > DSV_MAX_PYRAMID_LEVELS) {
@@ -376,11 +392,13 @@ extern "C" int dsv_hme(DSV_HME *hme)
         devframe_free(&rf[l]);
     }
     return nintra * 100 / nblk;
+    DSV_API_END(-100)
 }
 
 extern "C" int dsvk_sub_pred(const void *mvs, int w, int h, int subsamp, int blk_w, int blk_h, const uint8_t *inp_yuv,
                              const uint8_t *ref_yuv, uint8_t *pred_out, uint8_t *resid_out)
 {
+    DSV_API_BEGIN
     const MotionGeom g = motion_geom(w, h, subsamp, blk_w, blk_h, 0);
     DevFrame inp, ref, pred;
     upload_frame(&inp, inp_yuv, w, h, subsamp);
@@ -400,11 +418,13 @@ extern "C" int dsvk_sub_pred(const void *mvs, int w, int h, int subsamp, int blk
     devframe_free(&ref);
     devframe_free(&pred);
     return 0;
+    DSV_API_END(-100)
 }
 
 extern "C" int dsvk_add_pred(const void *mvs, int w, int h, int subsamp, int blk_w, int blk_h, const uint8_t *resid_yuv,
                              const uint8_t *ref_yuv, uint8_t *out_yuv)
 {
+    DSV_API_BEGIN
     const MotionGeom g = motion_geom(w, h, subsamp, blk_w, blk_h, 0);
     DevFrame io, ref;
     upload_frame(&io, resid_yuv, w, h, subsamp);
@@ -421,4 +441,5 @@ extern "C" int dsvk_add_pred(const void *mvs, int w, int h, int subsamp, int blk
     devframe_free(&io);
     devframe_free(&ref);
     return 0;
+    DSV_API_END(-100)
 }

@@ -9,6 +9,15 @@
 
 namespace dsv {
 
+void cuda_fail(int code, const char *msg, const char *file, int line, const char *expr)
+{
+    fprintf(stderr, "[dsv1_b200] CUDA error %d (%s) at %s:%d: %s\n", code, msg, file, line, expr);
+#ifndef DSV_CPU_EMU
+    cudaGetLastError(); /* clear the sticky-less error state so that later calls report their own */
+#endif
+    throw CudaError{code};
+}
+
 static std::mutex kt_mutex;
 static const char *kt_names[KT_MAX_SLOTS];
 static int kt_n = 0;
@@ -49,7 +58,7 @@ KernelTimes::Rec *KernelTimes::next()
         const int ncap = cap[g] ? cap[g] * 2 : 64;
         Rec *nr = (Rec *) realloc(recs[g], sizeof(Rec) * (size_t) ncap);
         if (!nr) {
-            abort();
+            throw std::bad_alloc();
         }
         for (int i = cap[g]; i < ncap; i++) {
             CUDA_CHECK(cudaEventCreate(&nr[i].e0));
