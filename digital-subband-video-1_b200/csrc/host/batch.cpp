@@ -4,12 +4,9 @@
  * step.  Streams come out exactly as the per-picture API emits them (metadata at every GOP start, link
  * fields, EOS), because every lane runs the same host-side state machine (a DSV_ENCODER per lane).
  */
-#include "dsv1_b200_batch.h"
-
-#include "dsv1_b200.h"
+#include "batch_state.h"
 
 #include "bits.h"
-#include "engine.h"
 
 using namespace dsv;
 
@@ -17,31 +14,12 @@ namespace dsv {
 void synth_launch(int w, int h, int hs, int vs, int start, int n, int seed, int cut, uint8_t *d_out, cudaStream_t st);
 }
 
-enum {
-    CFG_W, CFG_H, CFG_SUBSAMP, CFG_FPS_NUM, CFG_FPS_DEN, CFG_ASPECT_NUM, CFG_ASPECT_DEN,
-    CFG_GOP, CFG_QUALITY, CFG_RC_MODE, CFG_BITRATE, CFG_DO_SCD, CFG_SCD_DELTA, CFG_INTRA_PCT,
-    CFG_PYR_LEVELS, CFG_STABLE_REFRESH, CFG_MAX_Q_STEP, CFG_MIN_QUALITY, CFG_MAX_QUALITY,
-    CFG_MIN_I_QUALITY, CFG_HM_NUDGE, CFG_COUNT
-};
+namespace dsv {
 
-struct DSVB_ENC {
-    int cfg[CFG_COUNT];
-    int lanes, device;
-    EncEngine *eng;
-    std::vector<DSV_ENCODER> state;
-};
-
-struct DSVB_DEC {
-    int lanes, device;
-    int draw_info = 0, out420 = 0;
-    DecEngine *eng;
-    EngineStats carried; /* stats of engines replaced after a format change */
-};
-
-static void use_device(int device) { CUDA_CHECK(cudaSetDevice(device)); }
+void use_device(int device) { CUDA_CHECK(cudaSetDevice(device)); }
 
 /* pinned (cudaMallocHost / cudaHostRegister) host memory is addressable by kernels under UVA */
-static int host_mapped(const void *p)
+int host_mapped(const void *p)
 {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -51,7 +29,7 @@ static int host_mapped(const void *p)
     return a.type == cudaMemoryTypeHost;
 }
 
-static void apply_cfg(DSV_ENCODER *enc, const int *cfg)
+void apply_cfg(DSV_ENCODER *enc, const int *cfg)
 {
     DSV_META md;
     memset(&md, 0, sizeof(md));
@@ -81,7 +59,7 @@ static void apply_cfg(DSV_ENCODER *enc, const int *cfg)
     dsv_enc_start(enc);
 }
 
-static void release_state(DSV_ENCODER *enc)
+void release_state(DSV_ENCODER *enc)
 {
     if (enc->stability) {
         dsv_free(enc->stability);
@@ -92,6 +70,8 @@ static void release_state(DSV_ENCODER *enc)
         enc->stable_blocks = NULL;
     }
 }
+
+} // namespace dsv
 
 static void fill_stats(const EngineStats &s, int device, int lanes, double *out)
 {
@@ -140,6 +120,13 @@ extern "C" void dsvb_enc_destroy(DSVB_ENC *e)
     if (e) {
         use_device(e->device);
         delete e->eng;
+        cudaFreeHost(e->h_stage);
+        cudaFree(e->d_cache);
+        if (e->cache_stream) {
+            cudaStreamDestroy(e->cache_stream);
+            cudaEventDestroy(e->cache_ev[0]);
+            cudaEventDestroy(e->cache_ev[1]);
+        }
         delete e;
     }
 }
@@ -319,131 +306,153 @@ extern "C" void dsvb_dec_stats(DSVB_DEC *d, double *stats, int reset)
 
 static unsigned be32(const uint8_t *p) { return ((unsigned) p[0] << 24) | ((unsigned) p[1] << 16) | ((unsigned) p[2] << 8) | p[3]; }
 
-extern "C" int dsvb_decode(DSVB_DEC *d, int nseq, const uint8_t *const *streams, const uint8_t *const *streams_dev,
-                           const long *lens, uint8_t *const *out, const long *out_caps, int out_on_device, int *frames)
+/*
+ * Lock-step decode of a set of container segments: every lane walks its segment packet by packet (metadata / EOS
+ * are host-only), picture packets of all lanes are one engine step; a lane that finishes its segment takes the
+ * next one from the queue, so ragged segment lengths do not leave lanes idle.
+ */
+int dsv::decode_segments(DSVB_DEC *d, int nseg, DecSegment *segs, int out_on_device)
 {
-    DSV_API_BEGIN
-    use_device(d->device);
     const int L = d->lanes;
     int rc = 0;
     std::vector<long> pos((size_t) L);
-    std::vector<int> done((size_t) L), got_meta((size_t) L);
-    std::vector<int> ids((size_t) L), seq_of((size_t) L), codes((size_t) L);
+    std::vector<int> cur((size_t) L, -1), got_meta((size_t) L);
+    std::vector<int> ids((size_t) L), seg_of((size_t) L), codes((size_t) L);
     std::vector<PktRef> pk((size_t) L);
     std::vector<OutRef> outs((size_t) L);
     std::vector<DSV_FNUM> fn((size_t) L);
-    std::vector<uint8_t *> scratch_out; /* device scratch for pictures that do not fit the caller's buffer */
-    for (int base = 0; base < nseq; base += L) {
-        const int n = nseq - base < L ? nseq - base : L;
-        for (int k = 0; k < n; k++) {
-            pos[(size_t) k] = 0;
-            done[(size_t) k] = 0;
-            got_meta[(size_t) k] = 0;
-            frames[base + k] = 0;
-            if (d->eng) {
-                d->eng->reset_lane(k);
-            }
-        }
-        for (;;) {
-            /* advance every lane to its next picture packet (metadata / EOS are host-only) */
-            int m = 0;
-            for (int k = 0; k < n; k++) {
-                const int s = base + k;
-                while (!done[(size_t) k]) {
-                    const long at = pos[(size_t) k];
-                    if (at + DSV_PACKET_HDR_SIZE > lens[s]) {
-                        done[(size_t) k] = 1;
+    int next_seg = 0;
+    bool stepped = false; /* the engine (= the picture format) can only be replaced before the first step of a call */
+    for (int s = 0; s < nseg; s++) {
+        segs[s].frames = 0;
+    }
+    for (;;) {
+        /* advance every lane to its next picture packet */
+        int m = 0;
+        for (int k = 0; k < L; k++) {
+            for (;;) {
+                if (cur[(size_t) k] < 0) {
+                    if (next_seg >= nseg) {
                         break;
                     }
-                    const uint8_t *hdr = streams[s] + at;
-                    if (hdr[0] != DSV_FOURCC_0 || hdr[1] != DSV_FOURCC_1 || hdr[2] != DSV_FOURCC_2 || hdr[3] != DSV_FOURCC_3) {
-                        done[(size_t) k] = 1;
-                        rc = -4;
-                        break;
+                    cur[(size_t) k] = next_seg++;
+                    pos[(size_t) k] = 0;
+                    got_meta[(size_t) k] = segs[cur[(size_t) k]].got_meta;
+                    if (d->eng) {
+                        d->eng->reset_lane(k);
                     }
-                    long size = (long) be32(hdr + DSV_PACKET_NEXT_OFFSET);
-                    if (size == 0) {
-                        size = DSV_PACKET_HDR_SIZE;
-                    }
-                    if (size < DSV_PACKET_HDR_SIZE || at + size > lens[s]) {
-                        done[(size_t) k] = 1;
-                        rc = -3;
-                        break;
-                    }
-                    const int type = hdr[DSV_PACKET_TYPE_OFFSET];
-                    pos[(size_t) k] = at + size;
-                    if (type == DSV_PT_META) {
-                        DSV_META md;
-                        memset(&md, 0, sizeof(md));
-                        parse_metadata_packet(hdr, (unsigned) size, &md);
-                        if (!meta_supported(md)) {
-                            done[(size_t) k] = 1;
-                            rc = -5;
-                            break;
-                        }
-                        if (d->eng && !d->eng->matches(md)) {
-                            if (m > 0 || frames[s] > 0 || k > 0) {
-                                done[(size_t) k] = 1; /* one picture format per call */
-                                rc = -6;
-                                break;
-                            }
-                            add_stats(d->carried, d->eng->stats);
-                            delete d->eng;
-                            d->eng = nullptr;
-                        }
-                        if (!d->eng) {
-                            d->eng = new DecEngine(md, L);
-                            d->eng->draw_mode = d->draw_info;
-                            d->eng->set_out420(d->out420 != 0);
-                        }
-                        got_meta[(size_t) k] = 1;
+                }
+                DecSegment &sg = segs[cur[(size_t) k]];
+                const long at = pos[(size_t) k];
+                if (at + DSV_PACKET_HDR_SIZE > sg.len) {
+                    cur[(size_t) k] = -1;
+                    continue;
+                }
+                const uint8_t *hdr = sg.data + at;
+                if (hdr[0] != DSV_FOURCC_0 || hdr[1] != DSV_FOURCC_1 || hdr[2] != DSV_FOURCC_2 || hdr[3] != DSV_FOURCC_3) {
+                    cur[(size_t) k] = -1;
+                    rc = -4;
+                    continue;
+                }
+                long size = (long) be32(hdr + DSV_PACKET_NEXT_OFFSET);
+                if (size == 0) {
+                    size = DSV_PACKET_HDR_SIZE;
+                }
+                if (size < DSV_PACKET_HDR_SIZE || at + size > sg.len) {
+                    cur[(size_t) k] = -1;
+                    rc = -3;
+                    continue;
+                }
+                const int type = hdr[DSV_PACKET_TYPE_OFFSET];
+                pos[(size_t) k] = at + size;
+                if (type == DSV_PT_META) {
+                    DSV_META md;
+                    memset(&md, 0, sizeof(md));
+                    parse_metadata_packet(hdr, (unsigned) size, &md);
+                    if (!meta_supported(md)) {
+                        cur[(size_t) k] = -1;
+                        rc = -5;
                         continue;
                     }
-                    if (type == DSV_PT_EOS) {
-                        done[(size_t) k] = 1;
-                        break;
-                    }
-                    if (!DSV_PT_IS_PIC(type) || !got_meta[(size_t) k]) {
-                        continue; /* pictures before metadata are skipped (dsv_decoder.c:327-331) */
-                    }
-                    ids[(size_t) m] = k;
-                    seq_of[(size_t) m] = s;
-                    pk[(size_t) m].data = hdr;
-                    pk[(size_t) m].dev_data = streams_dev ? streams_dev[s] + at : nullptr;
-                    pk[(size_t) m].len = (unsigned) size;
-                    /* frame number decides where the picture lands: peek it (fnum follows the header) */
-                    const CodecGeom &g = d->eng->out_geom();
-                    const DSV_FNUM fno = be32(hdr + DSV_PACKET_HDR_SIZE);
-                    const size_t off = (size_t) fno * g.frame_bytes;
-                    if (off + g.frame_bytes > (size_t) out_caps[s]) {
-                        /* no room: decode (references must stay in step) into the lane's own frame only */
-                        for (int p = 0; p < 3; p++) {
-                            outs[(size_t) m].plane[p] = nullptr;
+                    if (d->eng && !d->eng->matches(md)) {
+                        if (stepped || m > 0) {
+                            cur[(size_t) k] = -1; /* one picture format per call */
+                            rc = -6;
+                            continue;
                         }
-                    } else {
-                        for (int p = 0; p < 3; p++) {
-                            outs[(size_t) m].plane[p] = out[s] + off + g.plane_off[p];
-                            outs[(size_t) m].stride[p] = g.pw[p];
-                        }
+                        add_stats(d->carried, d->eng->stats);
+                        delete d->eng;
+                        d->eng = nullptr;
                     }
-                    outs[(size_t) m].on_device = out_on_device;
-                    m++;
-                    break;
+                    if (!d->eng) {
+                        d->eng = new DecEngine(md, L);
+                        d->eng->draw_mode = d->draw_info;
+                        d->eng->set_out420(d->out420 != 0);
+                    }
+                    got_meta[(size_t) k] = 1;
+                    continue;
                 }
-            }
-            if (m == 0) {
+                if (type == DSV_PT_EOS) {
+                    cur[(size_t) k] = -1;
+                    continue;
+                }
+                if (!DSV_PT_IS_PIC(type) || !got_meta[(size_t) k] || !d->eng) {
+                    continue; /* pictures before metadata are skipped (dsv_decoder.c:327-331) */
+                }
+                ids[(size_t) m] = k;
+                seg_of[(size_t) m] = cur[(size_t) k];
+                pk[(size_t) m].data = hdr;
+                pk[(size_t) m].dev_data = sg.dev ? sg.dev + at : nullptr;
+                pk[(size_t) m].len = (unsigned) size;
+                /* frame number decides where the picture lands: peek it (fnum follows the header) */
+                const CodecGeom &g = d->eng->out_geom();
+                const DSV_FNUM fno = be32(hdr + DSV_PACKET_HDR_SIZE);
+                const size_t off = (size_t) fno * g.frame_bytes;
+                if (off + g.frame_bytes > (size_t) sg.out_cap) {
+                    /* no room: decode (references must stay in step) into the lane's own frame only */
+                    for (int p = 0; p < 3; p++) {
+                        outs[(size_t) m].plane[p] = nullptr;
+                    }
+                } else {
+                    for (int p = 0; p < 3; p++) {
+                        outs[(size_t) m].plane[p] = sg.out + off + g.plane_off[p];
+                        outs[(size_t) m].stride[p] = g.pw[p];
+                    }
+                }
+                outs[(size_t) m].on_device = out_on_device;
+                m++;
                 break;
             }
-            d->eng->step(m, ids.data(), pk.data(), outs.data(), codes.data(), fn.data());
-            for (int q = 0; q < m; q++) {
-                if (codes[(size_t) q] == DSV_DEC_OK && outs[(size_t) q].plane[0]) {
-                    frames[seq_of[(size_t) q]]++;
-                }
+        }
+        if (m == 0) {
+            break;
+        }
+        d->eng->step(m, ids.data(), pk.data(), outs.data(), codes.data(), fn.data());
+        stepped = true;
+        for (int q = 0; q < m; q++) {
+            if (codes[(size_t) q] == DSV_DEC_OK && outs[(size_t) q].plane[0]) {
+                segs[seg_of[(size_t) q]].frames++;
             }
         }
     }
     if (d->eng) {
         d->eng->flush(); /* the last pictures are still leaving on the copy stream */
+    }
+    return rc;
+}
+
+extern "C" int dsvb_decode(DSVB_DEC *d, int nseq, const uint8_t *const *streams, const uint8_t *const *streams_dev,
+                           const long *lens, uint8_t *const *out, const long *out_caps, int out_on_device, int *frames)
+{
+    DSV_API_BEGIN
+    use_device(d->device);
+    std::vector<DecSegment> segs((size_t) nseq);
+    for (int s = 0; s < nseq; s++) {
+        segs[(size_t) s] = DecSegment{streams[s], streams_dev ? streams_dev[s] : nullptr, lens[s], 0, out[s], out_caps[s], 0};
+    }
+    const int rc = decode_segments(d, nseq, segs.data(), out_on_device);
+    for (int s = 0; s < nseq; s++) {
+        frames[s] = segs[(size_t) s].frames;
     }
     return rc;
     DSV_API_END(-100)

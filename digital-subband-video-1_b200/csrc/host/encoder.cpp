@@ -118,7 +118,7 @@ static void set_links(DSV_ENCODER *enc, DSV_BUF *buf, int is_eos) /* dsv_encoder
     enc->prev_link = (int) next;
 }
 
-static void make_metadata_packet(DSV_ENCODER *enc, DSV_BUF *buf) /* dsv_encoder.c:426-461 */
+void dsv::make_metadata_packet(DSV_ENCODER *enc, DSV_BUF *buf) /* dsv_encoder.c:426-461 */
 {
     const DSV_META &m = enc->vidmeta;
     dsv_mk_buf(buf, 64);
@@ -555,8 +555,70 @@ void EncEngine::prefetch(int n, const int *lane_ids, const PicRef *src)
     }
 }
 
-void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bufs)[2], int *nbufs, PktSink *sinks)
+void gop_bookkeeping(DSV_ENCODER *enc, bool inter, DSV_FNUM fnum, int *gop_start, int *is_ref, int *has_ref)
 {
+    *gop_start = 0;
+    *is_ref = *has_ref = 0;
+    if (enc->force_metadata || ((enc->prev_gop + (DSV_FNUM) enc->gop) <= fnum)) {
+        *gop_start = 1;
+        enc->prev_gop = fnum;
+        enc->force_metadata = 0;
+    }
+    if (inter) {
+        *is_ref = 1;
+        *has_ref = !*gop_start;
+    }
+}
+
+void decide_and_head(DSV_ENCODER *enc, const CodecGeom &g, bool inter, int top_samples, unsigned long long luma_sum, int nintra,
+                     const DevMV *mvs, DSV_FNUM fnum, int is_ref, int *has_ref, int *forced_intra, int *quant, uint8_t *head,
+                     unsigned *head_bytes)
+{
+    if (inter) {
+        if (enc->do_scd) { /* check_scene_change, dsv_encoder.c:538-554 */
+            int al = (int) (luma_sum / (unsigned long long) top_samples);
+            if (iabs(enc->prev_avg_luma - al) > enc->scene_change_delta) {
+                *has_ref = 0;
+                *forced_intra = 1;
+            }
+            enc->prev_avg_luma = al;
+        }
+        if (*has_ref) { /* motion_est's verdict, dsv_encoder.c:246-253 */
+            int pct = nintra * 100 / g.nblk;
+            *forced_intra = 0;
+            if (pct > enc->intra_pct_thresh) {
+                *has_ref = 0;
+                *forced_intra = 1;
+            }
+        }
+    }
+    const int isP = *has_ref;
+    const int quality = rate_control_quality(enc, isP, *forced_intra);
+    *quant = DSV_MAX_QUALITY - ((DSV_MAX_QUALITY - 5) * quality / DSV_MAX_QUALITY); /* dsv_encoder.c:165 */
+
+    memset(head, 0, 256 + (size_t) g.nblk * 12); /* head <= 20 + stability map + 4 motion sub-streams (<= ~10 B per block) */
+    BitWriter bw(head);
+    put_packet_hdr(bw, DSV_MAKE_PT(is_ref, *has_ref));
+    bw.align();
+    bw.put_bits(32, fnum);
+    bw.align();
+    bw.put_ueg((uint32_t) (g.blk_w >> 2));
+    bw.put_ueg((uint32_t) (g.blk_h >> 2));
+    bw.align();
+    put_stable_blocks(enc, g, isP, mvs, bw);
+    if (isP) {
+        bw.align();
+        put_motion(g, mvs, bw);
+    }
+    bw.align();
+    bw.put_bits(DSV_MAX_QP_BITS, (uint32_t) *quant);
+    bw.align(); /* dsv_encode_plane aligns before each plane (hzcc.c:457) */
+    *head_bytes = bw.byte_pos();
+}
+
+void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bufs)[2], int *nbufs, PktSink *sinks, const LongPlan *plan)
+{
+    const bool analyse = plan && plan[0].analyse, code = plan && !plan[0].analyse;
     const CodecGeom &g = g_;
     cudaStream_t st = st_;
     const MotionGeom mg = {g.w, g.h, g.hs, g.vs, g.blk_w, g.blk_h, g.nbh, g.nbv, levels_};
@@ -571,7 +633,7 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     bool wait_pref[2] = {false, false};
     for (int k = 0; k < n; k++) {
         EncLane &l = lanes_[(size_t) lane_ids[k]];
-        l.fnum = l.enc->next_fnum++;
+        l.fnum = plan ? plan[k].fnum : l.enc->next_fnum++;
         const DevFrame &dst = inter_ ? l.pad[l.cur] : l.xf;
         int pb = -1;
         if (!src[k].on_device) {
@@ -619,27 +681,26 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     for (int k = 0; k < n; k++) {
         EncLane &l = lanes_[(size_t) lane_ids[k]];
         DSV_ENCODER *enc = l.enc;
-        l.gop_start = 0;
-        l.is_ref = l.has_ref = l.forced_intra = 0;
-        if (enc->force_metadata || ((enc->prev_gop + (DSV_FNUM) enc->gop) <= l.fnum)) {
-            l.gop_start = 1;
-            enc->prev_gop = l.fnum;
-            enc->force_metadata = 0;
+        l.forced_intra = 0;
+        if (plan) { /* metadata packets of a sharded sequence are written by the gather */
+            l.gop_start = 0;
+            l.is_ref = analyse ? 1 : plan[k].is_ref;
+            l.has_ref = analyse ? (plan[k].search && l.have_ref) : plan[k].has_ref;
+        } else {
+            gop_bookkeeping(enc, inter_, l.fnum, &l.gop_start, &l.is_ref, &l.has_ref);
         }
         if (inter_) {
-            l.is_ref = 1;
-            l.has_ref = !l.gop_start;
             if (l.has_ref && !l.have_ref) {
                 DSV_ASSERT(0 && "P frame without a reference");
             }
             n_search += l.has_ref;
-            n_sum += enc->do_scd ? 1 : 0;
+            n_sum += (analyse || (!plan && enc->do_scd)) ? 1 : 0;
         }
     }
     Down2Item *d_dn[DSV_MAX_PYRAMID_LEVELS] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     SumItem *d_sum = nullptr;
     HmeArgs *d_hme = nullptr;
-    if (inter_) {
+    if (inter_ && !code) {
         for (int lv = 0; lv < levels_; lv++) {
             Down2Item *dn = arena_.push_n<Down2Item>((size_t) n, &d_dn[lv]);
             for (int k = 0; k < n; k++) {
@@ -653,7 +714,7 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
             int q = 0;
             for (int k = 0; k < n; k++) {
                 EncLane &l = lanes_[(size_t) lane_ids[k]];
-                if (l.enc->do_scd) {
+                if (analyse || l.enc->do_scd) {
                     sm[q].src = plane_ref(l.pyr[l.cur][levels_ - 1], 0);
                     sm[q].out = &d_misc[lane_ids[k]].luma_sum;
                     q++;
@@ -687,7 +748,7 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
      * the picture into an I picture its output (prediction + residual frames) is simply not used.  The GPU works
      * on it while the host writes the packet heads. */
     BmcArgs *d_bmc = nullptr;
-    if (n_search) {
+    if (n_search && !analyse) {
         BmcArgs *ba = arena_.push_n<BmcArgs>((size_t) n_search, &d_bmc);
         int q = 0;
         for (int k = 0; k < n; k++) {
@@ -705,7 +766,19 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     ingest_launch(d_ing, 3 * n, g.w, g.h, st);
     stats.kernel_launches += 1;
     bool need_sync = false;
-    if (inter_) {
+    if (code && n_search) { /* the vectors found by the analysis pass */
+        for (int k = 0; k < n; k++) {
+            if (plan[k].has_ref) {
+                memcpy(h_mv0_ + (size_t) lane_ids[k] * g.nblk, plan[k].mvs, sizeof(DevMV) * (size_t) g.nblk);
+            }
+        }
+        copy1_launch(d_mv0_, h_mv0_, sizeof(DevMV) * (size_t) g.nblk * L_, st);
+        CUDA_CHECK(cudaEventRecord(ev_[5], st));
+        bmc_launch(d_bmc, n_search, mg, st);
+        CUDA_CHECK(cudaEventRecord(ev_[6], st));
+        stats.kernel_launches += 2;
+    }
+    if (inter_ && !code) {
         for (int lv = 0; lv < levels_; lv++) {
             down2_launch(d_dn[lv], n, ceil_shift(g.w, lv + 1), ceil_shift(g.h, lv + 1), st);
         }
@@ -727,7 +800,7 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
             need_sync = true;
             CUDA_CHECK(cudaEventRecord(ev_search_, st));
         }
-        if (n_search) {
+        if (n_search && !analyse) {
             CUDA_CHECK(cudaEventRecord(ev_[5], st));
             bmc_launch(d_bmc, n_search, mg, st);
             CUDA_CHECK(cudaEventRecord(ev_[6], st));
@@ -737,6 +810,29 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     if (need_sync) {
         CUDA_CHECK(cudaEventSynchronize(ev_search_));
     }
+    if (analyse) { /* results to the caller; this picture is the lane's next search reference */
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        ktimes.collect(0);
+        for (int k = 0; k < n; k++) {
+            const int li = lane_ids[k];
+            EncLane &l = lanes_[(size_t) li];
+            LongAnalysis *out = plan[k].out;
+            if (out) {
+                out->luma_sum = inter_ ? h_misc[li].luma_sum : 0;
+                out->nintra = l.has_ref ? h_misc[li].nintra : 0;
+                if (l.has_ref && out->mvs) {
+                    memcpy(out->mvs, h_mv0_ + (size_t) li * g.nblk, sizeof(DevMV) * (size_t) g.nblk);
+                }
+            }
+            l.have_ref = 1;
+            l.cur ^= 1;
+            if (nbufs) {
+                nbufs[k] = 0;
+            }
+        }
+        stats.pictures += (unsigned) n;
+        return;
+    }
 
     /* ---- phase 2: host decisions + packet heads --------------------------------------------------- */
     const double t_host0 = host_now_ms();
@@ -744,49 +840,17 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     const std::function<void(int)> lane_head = [&](int k) {
         const int li = lane_ids[k];
         EncLane &l = lanes_[(size_t) li];
+        if (code) { /* decided by the serial pass of dsvb_encode_long */
+            l.quant = plan[k].quant;
+            l.head_bytes = plan[k].head_bytes;
+            memcpy(l.h_head, plan[k].head, plan[k].head_bytes);
+            memcpy(h_stab_ + (size_t) li * g.nblk, plan[k].stable, (size_t) g.nblk);
+            return;
+        }
         DSV_ENCODER *enc = l.enc;
-        if (inter_) {
-            if (enc->do_scd) { /* check_scene_change, dsv_encoder.c:538-554 */
-                const DevFrame &top = l.pyr[l.cur][levels_ - 1];
-                int al = (int) (h_misc[li].luma_sum / (unsigned long long) (top.w[0] * top.h[0]));
-                if (iabs(enc->prev_avg_luma - al) > enc->scene_change_delta) {
-                    l.has_ref = 0;
-                    l.forced_intra = 1;
-                }
-                enc->prev_avg_luma = al;
-            }
-            if (l.has_ref) { /* motion_est's verdict, dsv_encoder.c:246-253 */
-                int pct = h_misc[li].nintra * 100 / g.nblk;
-                l.forced_intra = 0;
-                if (pct > enc->intra_pct_thresh) {
-                    l.has_ref = 0;
-                    l.forced_intra = 1;
-                }
-            }
-        }
-        const int isP = l.has_ref;
-        const int quality = rate_control_quality(enc, isP, l.forced_intra);
-        l.quant = DSV_MAX_QUALITY - ((DSV_MAX_QUALITY - 5) * quality / DSV_MAX_QUALITY); /* dsv_encoder.c:165 */
-
-        const DevMV *mvs = h_mv0_ + (size_t) li * g.nblk;
-        memset(l.h_head, 0, 256 + (size_t) g.nblk * 12); /* head <= 20 + stability map + 4 motion sub-streams (<= ~10 B per block) */
-        BitWriter bw(l.h_head);
-        put_packet_hdr(bw, DSV_MAKE_PT(l.is_ref, l.has_ref));
-        bw.align();
-        bw.put_bits(32, l.fnum);
-        bw.align();
-        bw.put_ueg((uint32_t) (g.blk_w >> 2));
-        bw.put_ueg((uint32_t) (g.blk_h >> 2));
-        bw.align();
-        put_stable_blocks(enc, g, isP, mvs, bw);
-        if (l.has_ref) {
-            bw.align();
-            put_motion(g, mvs, bw);
-        }
-        bw.align();
-        bw.put_bits(DSV_MAX_QP_BITS, (uint32_t) l.quant);
-        bw.align(); /* dsv_encode_plane aligns before each plane (hzcc.c:457) */
-        l.head_bytes = bw.byte_pos();
+        const DevFrame *top = inter_ ? &l.pyr[l.cur][levels_ - 1] : nullptr;
+        decide_and_head(enc, g, inter_, top ? top->w[0] * top->h[0] : 1, h_misc[li].luma_sum, h_misc[li].nintra,
+                        h_mv0_ + (size_t) li * g.nblk, l.fnum, l.is_ref, &l.has_ref, &l.forced_intra, &l.quant, l.h_head, &l.head_bytes);
         memcpy(h_stab_ + (size_t) li * g.nblk, enc->stable_blocks, (size_t) g.nblk);
     };
     if (pool_) {
@@ -1003,6 +1067,9 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         if (l.is_ref) {
             l.have_ref = 1;
             l.cur ^= 1;
+        }
+        if (plan) {
+            continue; /* links and the serial state belong to the gather / the serial pass */
         }
         if (l.has_ref) {
             enc->refresh_ctr++;

@@ -177,13 +177,61 @@ struct PktSink {
     int mapped; /* destination is mapped pinned host memory: packets leave through an SM copy kernel */
 };
 
+/*
+ * Single-sequence sharding (long.cpp, dsvb_encode_long): the three phases of a picture run at different times.
+ *   analyse  phase 1 only -- ingest, pyramid, luma sum and the motion search against the lane's previous ORIGINAL
+ *            picture (source-only data, dsv_encoder.c:231-236): any lane can do it for any picture;
+ *   (host)   the serial pass over all pictures in order makes the decisions and writes the packet heads;
+ *   code     phase 3 with those decisions given: residual, transform, entropy coding, reconstruction.  Pictures
+ *            between two I pictures form a chain; chains are independent and run one per lane.
+ */
+struct LongAnalysis {
+    unsigned long long luma_sum; /* of the smallest pyramid level */
+    int nintra;                  /* blocks the search marked intra */
+    DevMV *mvs;                  /* nblk vectors of level 0 (host memory) */
+};
+struct LongPlan {
+    int analyse;       /* 1: analysis step (all lanes of a step share the mode) */
+    int search;        /* analyse: search against the lane's previous picture (0: the lane's first picture) */
+    LongAnalysis *out; /* analyse: results */
+    /* code: */
+    DSV_FNUM fnum;
+    int has_ref, is_ref, quant;
+    const DevMV *mvs;      /* has_ref: vectors from the analysis pass */
+    const uint8_t *stable; /* stable_blocks of this picture (nblk bytes) */
+    const uint8_t *head;   /* packet head: header .. quantiser, head_bytes long */
+    unsigned head_bytes;
+};
+
+/* GOP bookkeeping of one picture (dsv_encoder.c:624-652): host state only */
+void gop_bookkeeping(DSV_ENCODER *enc, bool inter, DSV_FNUM fnum, int *gop_start, int *is_ref, int *has_ref);
+/* phase 2 of one picture: scene cut / intra share -> frame type, quantiser, stability map, motion side info ->
+ * packet head.  top_samples = samples of the smallest pyramid level (the luma average's divisor). */
+void decide_and_head(DSV_ENCODER *enc, const CodecGeom &g, bool inter, int top_samples, unsigned long long luma_sum, int nintra,
+                     const DevMV *mvs, DSV_FNUM fnum, int is_ref, int *has_ref, int *forced_intra, int *quant, uint8_t *head,
+                     unsigned *head_bytes);
+static inline size_t head_capacity(const CodecGeom &g) { return 512 + (size_t) g.nblk * 48; }
+void make_metadata_packet(DSV_ENCODER *enc, DSV_BUF *buf);
+
 class EncEngine {
 public:
     EncEngine(const DSV_META &md, int gop, int pyramid_levels, int lanes);
     ~EncEngine();
     /* encode one picture on each of lane_ids[0..n): src[k] is that lane's input, bufs[k] receives 1 or 2
-     * packets (metadata first), nbufs[k] their count */
-    void step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bufs)[2], int *nbufs, PktSink *sinks = nullptr);
+     * packets (metadata first), nbufs[k] their count.  plan (optional, n entries): see LongPlan. */
+    void step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bufs)[2], int *nbufs, PktSink *sinks = nullptr,
+              const LongPlan *plan = nullptr);
+    /* forget a lane's references (a new chain starts on it) */
+    void reset_lane(int lane) { lanes_[(size_t) lane].have_ref = 0; }
+    /* the next step's kernels start after `ev` (uploads made by the caller on a stream of its own) */
+    void wait_event(cudaEvent_t ev)
+    {
+        if (ev) {
+            CUDA_CHECK(cudaStreamWaitEvent(st_, ev, 0));
+        }
+    }
+    int pyramid_levels() const { return levels_; }
+    bool inter() const { return inter_; }
     /* start copying the NEXT step's host pictures to the device on the copy stream while the current step computes */
     void prefetch(int n, const int *lane_ids, const PicRef *src);
     /* attach a sequence's host state to a lane and forget the lane's references */

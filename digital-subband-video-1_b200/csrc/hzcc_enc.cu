@@ -585,7 +585,6 @@ __global__ void __launch_bounds__(HZP_THREADS) hzcc_prefix_kernel(const HzJob *j
          * picture that does not fit its packet buffer (the reference's w*h*{2,4,6} heuristic overflows its heap
          * there) is refused here, and hzcc_pack_kernel skips it */
         if (tid == 0) {
-            uint8_t *pkt = F.pkt;
             unsigned long long end = token_base + total_bits;
             if (((end + 64 + 7) >> 3) + 16 > (unsigned long long) F.cap) {
                 s_overflow = 1;

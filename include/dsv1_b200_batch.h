@@ -62,6 +62,47 @@ void dsvb_dec_set_draw_info(DSVB_DEC *d, int mode);
  * written to `out` as packed 4:2:0 (frame size w*h + 2*ceil(w/2)*ceil(h/2)), converted on the device */
 void dsvb_dec_set_out420p(DSVB_DEC *d, int on);
 
+/*
+ * ONE long sequence sharded over the lanes of a GPU (csrc/host/long.cpp).  Pictures between two I pictures
+ * (periodic GOP starts AND forced ones: scene cuts, too many intra blocks) form a chain; chains are independent
+ * once the serial per-picture decisions are made, so they run one per lane.  Three phases: (A) pyramid + motion
+ * search of every picture against its ORIGINAL predecessor, batched over the lanes (source-only data,
+ * dsv_encoder.c:231-236); (B) one serial host pass in picture order for frame types, the stability tracker
+ * (dsv_encoder.c:329-408) and the packet heads; (C) residual / transform / entropy coding / reconstruction of
+ * the chains; then an ordered gather with metadata packets, frame numbers and prev/next links
+ * (dsv_encoder.c:170-192,427-461) exactly as dsv_enc writes them: the stream is byte-identical to feeding the
+ * pictures to dsv_enc one by one.  ABR streams (rc_mode != CRF) serialise on packet sizes and run on one lane.
+ * yuv: nframes packed planar pictures (host, or device when on_device = 1).  info (optional, 4 ints):
+ * chains, forced I pictures, longest chain, GPUs used (0: single-GPU entry, 1: serial ABR path).
+ * Returns 0, -1 if `stream` (cap bytes) is too small, -100 on a CUDA failure.
+ */
+int dsvb_encode_long(DSVB_ENC *e, int nframes, const uint8_t *yuv, int on_device, uint8_t *stream, long cap, long *len,
+                     int *info);
+/* One container decoded with its chains (cut at every picture that has no reference, dsv_decoder.c:286-472)
+ * spread over the lanes.  stream_dev (optional): device copy of the same bytes.  Pictures land at
+ * out + fnum * frame_bytes like dsvb_decode. */
+int dsvb_decode_long(DSVB_DEC *d, const uint8_t *stream, const uint8_t *stream_dev, long len, uint8_t *out, long out_cap,
+                     int out_on_device, int *frames);
+
+/*
+ * Several GPUs of one box behind one object: one engine and one host thread per GPU, no collective (SURVEY.md
+ * section 8e: replicas + ordered host gather).  devices: ndev CUDA ordinals (NULL: 0..ndev-1); cfg may be NULL
+ * for a decode-only object.  All buffers are host memory (pinned memory avoids staging copies).
+ *   dsvb_multi_encode / _decode        whole sequences / streams dealt to the GPUs in contiguous runs
+ *   dsvb_multi_encode_long             one sequence: phase A over contiguous runs of pictures, phase B on the
+ *                                      calling thread, phase C over contiguous runs of chains, ordered gather
+ *   dsvb_multi_decode_long             one container cut at GOP starts into one run of chains per GPU
+ */
+typedef struct DSVB_MULTI DSVB_MULTI;
+DSVB_MULTI *dsvb_multi_create(const int *cfg, int lanes, int ndev, const int *devices);
+void dsvb_multi_destroy(DSVB_MULTI *m);
+int dsvb_multi_encode(DSVB_MULTI *m, int nseq, int nframes, const uint8_t *const *yuv, uint8_t *const *streams,
+                      const long *caps, long *lens);
+int dsvb_multi_decode(DSVB_MULTI *m, int nseq, const uint8_t *const *streams, const long *lens, uint8_t *const *out,
+                      const long *out_caps, int *frames);
+int dsvb_multi_encode_long(DSVB_MULTI *m, int nframes, const uint8_t *yuv, uint8_t *stream, long cap, long *len, int *info);
+int dsvb_multi_decode_long(DSVB_MULTI *m, const uint8_t *stream, long len, uint8_t *out, long out_cap, int *frames);
+
 /* Live per-kernel timing: every kernel launch of an engine step is bracketed by CUDA events on the engine's stream.
  * dsvb_kernel_count() names are registered so far (at most 64, in order of first launch); ms[i] / launches[i]
  * (arrays of at least 64 doubles) receive the accumulated device time and launch count of kernel i since the last

@@ -317,6 +317,20 @@ class BatchEncoder:
         assert rc == 0, rc
         return [o[:n].tobytes() for o, n in zip(outs, lens)]
 
+    def encode_long_ptr(self, yuv_ptr, nframes, on_device, stream_ptr, cap):
+        ln = C.c_long()
+        info = (C.c_int * 4)()
+        rc = self.lib.dsvb_encode_long(self.h, nframes, C.c_void_p(yuv_ptr), int(on_device), C.c_void_p(stream_ptr), C.c_long(cap),
+                                       C.byref(ln), info)
+        return rc, ln.value, list(info)
+
+    def encode_long(self, yuv, nframes):
+        """ONE sequence sharded by I-delimited chains over the lanes. Returns (bytes, info)."""
+        out = np.zeros(len(yuv) * 2 + 65536, dtype=np.uint8)
+        rc, ln, info = self.encode_long_ptr(yuv.ctypes.data, nframes, 0, out.ctypes.data, len(out))
+        assert rc == 0, rc
+        return out[:ln].tobytes(), info
+
     def stats(self, reset=False):
         st = (C.c_double * NSTATS)()
         self.lib.dsvb_enc_stats(self.h, st, int(reset))
@@ -329,6 +343,64 @@ class BatchEncoder:
     def close(self):
         if self.h:
             self.lib.dsvb_enc_destroy(self.h)
+            self.h = None
+
+
+class MultiGpu:
+    """dsvb_multi_*: one engine + host thread per GPU behind one object (host buffers only)."""
+
+    def __init__(self, lib, cfg, lanes, devices):
+        self.lib = lib.lib
+        self.lib.dsvb_multi_create.restype = C.c_void_p
+        dv = (C.c_int * len(devices))(*devices)
+        self.h = C.c_void_p(self.lib.dsvb_multi_create(cfg, lanes, len(devices), dv))
+        assert self.h.value, "dsvb_multi_create failed"
+
+    def encode(self, seqs, nframes):
+        n = len(seqs)
+        outs = [np.zeros(len(s) * 2 + 65536, dtype=np.uint8) for s in seqs]
+        a_y = (C.c_void_p * n)(*[s.ctypes.data for s in seqs])
+        a_s = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        a_c = (C.c_long * n)(*[len(o) for o in outs])
+        lens = (C.c_long * n)()
+        rc = self.lib.dsvb_multi_encode(self.h, n, nframes, a_y, a_s, a_c, lens)
+        assert rc == 0, rc
+        return [o[:k].tobytes() for o, k in zip(outs, lens)]
+
+    def decode(self, streams, frame_bytes, nframes):
+        n = len(streams)
+        bufs = [np.frombuffer(s, dtype=np.uint8) for s in streams]
+        outs = [np.zeros(frame_bytes * nframes, dtype=np.uint8) for _ in streams]
+        a_s = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        a_l = (C.c_long * n)(*[len(b) for b in bufs])
+        a_o = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        a_c = (C.c_long * n)(*[len(o) for o in outs])
+        fr = (C.c_int * n)()
+        rc = self.lib.dsvb_multi_decode(self.h, n, a_s, a_l, a_o, a_c, fr)
+        assert rc == 0, rc
+        return outs, list(fr)
+
+    def encode_long(self, yuv, nframes):
+        out = np.zeros(len(yuv) * 2 + 65536, dtype=np.uint8)
+        ln = C.c_long()
+        info = (C.c_int * 4)()
+        rc = self.lib.dsvb_multi_encode_long(self.h, nframes, C.c_void_p(yuv.ctypes.data), C.c_void_p(out.ctypes.data),
+                                             C.c_long(len(out)), C.byref(ln), info)
+        assert rc == 0, rc
+        return out[:ln.value].tobytes(), list(info)
+
+    def decode_long(self, stream, frame_bytes, nframes):
+        buf = np.frombuffer(stream, dtype=np.uint8)
+        out = np.zeros(frame_bytes * nframes, dtype=np.uint8)
+        fr = C.c_int()
+        rc = self.lib.dsvb_multi_decode_long(self.h, C.c_void_p(buf.ctypes.data), C.c_long(len(buf)), C.c_void_p(out.ctypes.data),
+                                             C.c_long(len(out)), C.byref(fr))
+        assert rc == 0, rc
+        return out, fr.value
+
+    def close(self):
+        if self.h:
+            self.lib.dsvb_multi_destroy(self.h)
             self.h = None
 
 
@@ -349,6 +421,16 @@ class BatchDecoder:
         fr = (C.c_int * n)()
         rc = self.lib.dsvb_decode(self.h, n, a_s, a_d, a_l, a_o, a_c, int(out_on_device), fr)
         return rc, list(fr)
+
+    def decode_long(self, stream, frame_bytes, nframes):
+        """one container, its chains spread over the lanes. Returns (pictures, count)."""
+        buf = np.frombuffer(stream, dtype=np.uint8)
+        out = np.zeros(frame_bytes * nframes, dtype=np.uint8)
+        fr = C.c_int()
+        rc = self.lib.dsvb_decode_long(self.h, C.c_void_p(buf.ctypes.data), None, C.c_long(len(buf)), C.c_void_p(out.ctypes.data),
+                                       C.c_long(len(out)), 0, C.byref(fr))
+        assert rc == 0, rc
+        return out, fr.value
 
     def set_draw_info(self, mode):
         self.lib.dsvb_dec_set_draw_info(self.h, int(mode))

@@ -152,3 +152,31 @@ def test_dsv_hme_exported_interface_tiny(emu, ref):
     pe, me = emu.hme_api(fs, fr, w, h, sub, lv)
     assert pr == pe and all(np.array_equal(mr[k], me[k]) for k in mr.dtype.names if k != "pad")
     assert (mr[0]["mode"] == 1).any() and (mr[1]["x"] != 0).any()
+
+
+def test_long_sequence_chain_sharding_tiny(emu, ref):
+    """dsvb_encode_long / dsvb_decode_long: ONE sequence sharded by I-delimited chains over the lanes (phase A search
+    of every picture, serial host pass, chains on lanes, ordered gather) is byte-identical to feeding the pictures
+    to the reference one by one -- across GOP starts, a forced I picture at a scene cut (which does not restart the
+    GOP) and a stability refresh; then the same over two (emulated) devices.  Larger cases: tests/test_gpu_long.py."""
+    w, h, fmt, n = 32, 32, "420", 7
+    sub = L.SUBSAMP[fmt]
+    fb = L.frame_bytes(w, h, sub)
+    yuv = L.synth_sequence(w, h, fmt, n, 7, 4)  # scene cut at picture 4
+    cfg = L.make_cfg(w, h, fmt, gop=3, qp=70, stable_refresh=2)
+    want, pk, _ = ref.encode_sequence(cfg, yuv, n)
+    be = L.BatchEncoder(emu, cfg, 2)
+    got, info = be.encode_long(yuv, n)
+    be.close()
+    assert got == want, info
+    assert info[0] == 4 and info[1] == 1  # chains: GOP starts at 0, 3, 6 + the forced I picture at the cut
+    _, wdec, _, _ = ref.decode_stream(want, w, h, sub, n)
+    bd = L.BatchDecoder(emu, 2)
+    out, fr = bd.decode_long(want, fb, n)
+    bd.close()
+    assert fr == n and np.array_equal(out, wdec)
+    # two (emulated) devices: one engine + host thread per device, pictures / chains dealt in contiguous runs
+    mg = L.MultiGpu(emu, cfg, 1, [0, 0])
+    got, info = mg.encode_long(yuv[:fb * 5], 5)
+    mg.close()
+    assert got == ref.encode_sequence(cfg, yuv[:fb * 5], 5)[0] and info[3] == 2
