@@ -151,6 +151,17 @@ static void fill_ktimes(KernelTimes *kt, double *ms, double *launches, int reset
     }
 }
 
+extern "C" int dsvb_enc_tile_flags(DSVB_ENC *e, int lane, uint8_t *out, int cap)
+{
+    DSV_API_BEGIN
+    use_device(e->device);
+    if (lane < 0 || lane >= e->lanes) {
+        return -1;
+    }
+    return e->eng->tile_flags(lane, out, cap);
+    DSV_API_END(-100)
+}
+
 extern "C" int dsvb_kernel_count(void) { return kt_count(); }
 extern "C" const char *dsvb_kernel_name(int i) { return kt_name(i); }
 extern "C" void dsvb_enc_kernel_times(DSVB_ENC *e, double *ms, double *launches, int reset)

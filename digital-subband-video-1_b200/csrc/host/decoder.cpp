@@ -105,7 +105,7 @@ DecEngine::DecEngine(const DSV_META &md, int lanes)
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_copied_[1], cudaEventDisableTiming));
     /* a picture packet holds three planes of at most 2 * 4 * cw * ch bytes each (dsv_decoder.c:397-401) */
     pkt_cap_ = g.coef_total * 8 + 4096 + (size_t) g.nblk * 64;
-    const size_t per_lane = 3 * (sizeof(SbtJob) + hzdec_job_size()) + sizeof(BmcArgs) + 8 * sizeof(PlaneRef) + 3 * sizeof(PackItem) + sizeof(ZeroItem) + sizeof(CopyItem) + sizeof(DrawItem) + sizeof(PackItem) + 2 * sizeof(To420Item) + 1024;
+    const size_t per_lane = 3 * (sizeof(SbtJob) + hzdec_job_size()) + sizeof(BmcArgs) + 8 * sizeof(PlaneRef) + 3 * sizeof(PackItem) + 3 * sizeof(HzCleanItem) + sizeof(CopyItem) + sizeof(DrawItem) + sizeof(PackItem) + 2 * sizeof(To420Item) + 1024;
     CUDA_CHECK(cudaMalloc(&d_mv_, sizeof(DevMV) * (size_t) max_nblk_ * L_));
     CUDA_CHECK(cudaMalloc(&d_stab_, (size_t) max_nblk_ * L_));
     for (int q = 0; q < 2; q++) {
@@ -124,7 +124,16 @@ DecEngine::DecEngine(const DSV_META &md, int lanes)
     CUDA_CHECK(cudaMalloc(&d_out_all_[1], out_pitch_ * L_ + 256));
     lanes_.resize((size_t) L_);
     for (auto &l : lanes_) {
+        /* coefficient planes are kept all-zero between pictures by the flag-guided clean-up (hzdec_clean_kernel) */
         CUDA_CHECK(cudaMalloc(&l.coef, g.coef_total * sizeof(int32_t)));
+        CUDA_CHECK(cudaMemset(l.coef, 0, g.coef_total * sizeof(int32_t)));
+        CUDA_CHECK(cudaMalloc(&l.tflags, (size_t) g.total_tiles + 16));
+        for (int p = 0, off = 0; p < 3; off += g.tiles[p], p++) {
+            SbtJob probe;
+            memset(&probe, 0, sizeof(probe));
+            sbt_fill_geometry(&probe, g.pw[p], g.ph[p], g.cw[p], g.ch[p], 1, p);
+            CUDA_CHECK(cudaMemset(l.tflags + off, hz_flag_base(probe.dg), (size_t) g.tiles[p] + (p == 2 ? 16 : 0)));
+        }
         for (int p = 0; p < 3; p++) {
             CUDA_CHECK(cudaMalloc(&l.llx[p], sbt_llx_elems(g.cw[p], g.ch[p]) * sizeof(int32_t)));
             HzDecPlan pl;
@@ -144,6 +153,7 @@ DecEngine::~DecEngine()
     cudaStreamSynchronize(st_copy_);
     for (auto &l : lanes_) {
         cudaFree(l.coef);
+        cudaFree(l.tflags);
         for (int p = 0; p < 3; p++) {
             cudaFree(l.llx[p]);
             hzdec_plane_free(&l.hz[p]);
@@ -255,9 +265,9 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
     To420Item *d_cv;
     To420Item *cv = arena_.push_n<To420Item>((size_t) 2 * n, &d_cv);
     int n_draw = 0, n_pack2 = 0, n_cv = 0;
-    ZeroItem *d_zero;
-    ZeroItem *zero = arena_.push_n<ZeroItem>((size_t) n, &d_zero);
-    int n_zero = 0;
+    HzCleanItem *d_clean;
+    HzCleanItem *clean = arena_.push_n<HzCleanItem>((size_t) 3 * n, &d_clean);
+    int n_clean = 0;
     CopyItem *d_cpy;
     CopyItem *cpy = arena_.push_n<CopyItem>((size_t) n, &d_cpy);
     int n_cpy = 0;
@@ -385,18 +395,24 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
             s.coef = l.coef + g.coef_off[p];
             s.llx = l.llx[p];
             s.stable = d_stab_ + (size_t) li * step_nblk;
+            s.tflags = l.tflags + (p > 0 ? g.tiles[0] : 0) + (p > 1 ? g.tiles[1] : 0);
+            HzJob h;
+            memset(&h, 0, sizeof(h));
+            h.cw = g.cw[p];
+            h.ch = g.ch[p];
+            h.plane = p;
+            h.isP = isP;
+            h.pq = s.pq;
+            h.dg = s.dg;
+            hz_fill_regions(&h.rg, g.cw[p], g.ch[p]);
+            h.coef = s.coef;
+            h.stable = s.stable;
+            h.tflags = s.tflags;
+            h.tiles_x = s.tiles_x;
+            /* dsv_decoder.c:405: coefficient planes start zeroed.  Planes that were never coded (corrupt plen) stay
+             * all-zero here; the reference leaves the zeroed residual plane untouched instead. */
+            hzdec_fill_clean(&clean[n_clean++], h, s.tiles_y);
             if (p < l.nplanes) {
-                HzJob h;
-                memset(&h, 0, sizeof(h));
-                h.cw = g.cw[p];
-                h.ch = g.ch[p];
-                h.plane = p;
-                h.isP = isP;
-                h.pq = s.pq;
-                h.dg = s.dg;
-                hz_fill_regions(&h.rg, g.cw[p], g.ch[p]);
-                h.coef = s.coef;
-                h.stable = s.stable;
                 hzdec_fill_job(hzj + hzdec_job_size() * (size_t) dims.njobs, h, l.pd[p], l.hz[p], &dims);
             }
             n_sj++;
@@ -492,11 +508,6 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
             const MotionGeom mg = {g.w, g.h, g.hs, g.vs, g.blk_w, g.blk_h, g.nbh, g.nbv, 0};
             bmc_fill_args(&ba[n_p++], mg, d_mv_ + (size_t) li * step_nblk, l.out[l.cur ^ 1], nullptr, cur, cur, 2);
         }
-        /* dsv_decoder.c:405: coefficient planes start zeroed.  Planes that were never coded (corrupt plen) stay
-         * all-zero here; the reference leaves the zeroed residual plane untouched instead. */
-        zero[n_zero].p = l.coef;
-        zero[n_zero].bytes = g.coef_total * sizeof(int32_t);
-        n_zero++;
     }
     stats.host_ms += host_now_ms() - t_host0;
     if (n_sj == 0) {
@@ -516,7 +527,7 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
     if (n_p) {
         copy1_launch(d_mv_, h_mv_, sizeof(DevMV) * (size_t) step_nblk * L_, st);
     }
-    zero_launch(d_zero, n_zero, g_.coef_total * sizeof(int32_t), st);
+    hzdec_clean_launch(d_clean, n_clean, g_.tiles[0], st);
     hzdec_launch_jobs(d_hzj, dims, st);
     sbt_inv_launch(d_sj, sdims, g_.lo_smem, st, ev_[0], ev_[1]);
     if (n_p) {

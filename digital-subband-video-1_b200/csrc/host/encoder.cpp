@@ -407,6 +407,8 @@ void EncEngine::alloc_lane(EncLane &l)
 {
     const CodecGeom &g = g_;
     CUDA_CHECK(cudaMalloc(&l.coef, g.coef_total * sizeof(int32_t)));
+    CUDA_CHECK(cudaMalloc(&l.tflags, (size_t) g.total_tiles + 16));
+    CUDA_CHECK(cudaMemset(l.tflags, 3, (size_t) g.total_tiles + 16));
     for (int p = 0; p < 3; p++) {
         CUDA_CHECK(cudaMalloc(&l.llx[p], sbt_llx_elems(g.cw[p], g.ch[p]) * sizeof(int32_t)));
         CUDA_CHECK(cudaMalloc(&l.dv[p], sbt_dv_elems(g.cw[p], g.ch[p]) * sizeof(int32_t)));
@@ -446,6 +448,7 @@ void EncEngine::alloc_lane(EncLane &l)
 void EncEngine::free_lane(EncLane &l)
 {
     cudaFree(l.coef);
+    cudaFree(l.tflags);
     for (int p = 0; p < 3; p++) {
         cudaFree(l.llx[p]);
         cudaFree(l.dv[p]);
@@ -909,6 +912,7 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
             s.coef = l.coef + g.coef_off[p];
             s.llx = l.llx[p];
             s.dv = l.dv[p];
+            s.tflags = l.tflags + (p > 0 ? g.tiles[0] : 0) + (p > 1 ? g.tiles[1] : 0);
             s.stable = d_stab_ + (size_t) li * g.nblk;
             s.do_quant = 1;
 
@@ -924,6 +928,8 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
             h.nchunks = g.chunks[p];
             h.coef = s.coef;
             h.dv = s.dv;
+            h.tflags = s.tflags;
+            h.tiles_x = ceil_div(g.cw[p], SBT_TW);
             h.stable = s.stable;
             h.chunk_base = k * g.total_chunks + (p > 0 ? g.chunks[0] : 0) + (p > 1 ? g.chunks[1] : 0);
             h.frame = k;

@@ -157,6 +157,7 @@ struct EncLane {
     DevMV *d_mvf[DSV_MAX_PYRAMID_LEVELS + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int2 *d_aux = nullptr;
     int32_t *coef = nullptr, *llx[3] = {nullptr, nullptr, nullptr}, *dv[3] = {nullptr, nullptr, nullptr};
+    uint8_t *tflags = nullptr; /* tile flags of the three planes (sbt.cuh), g.total_tiles bytes */
     uint8_t *d_pkt = nullptr, *d_in[2] = {nullptr, nullptr};
     int in_sel = 0;                 /* staging buffer the next inline copy / prefetch writes */
     const uint8_t *stage_src[2] = {nullptr, nullptr}; /* host picture on its way into / held by each staging buffer */
@@ -230,6 +231,13 @@ public:
             CUDA_CHECK(cudaStreamWaitEvent(st_, ev, 0));
         }
     }
+    /* test hook: the tile flags (sbt.cuh) the lane's last picture left behind, Y then U then V; returns their count */
+    int tile_flags(int lane, uint8_t *out, int cap)
+    {
+        const int n = g_.total_tiles < cap ? g_.total_tiles : cap;
+        CUDA_CHECK(cudaMemcpy(out, lanes_[(size_t) lane].tflags, (size_t) n, cudaMemcpyDeviceToHost));
+        return g_.total_tiles;
+    }
     int pyramid_levels() const { return levels_; }
     bool inter() const { return inter_; }
     /* start copying the NEXT step's host pictures to the device on the copy stream while the current step computes */
@@ -275,6 +283,7 @@ struct DecLane {
     DevFrame out[2];
     int cur = 0, have_ref = 0;
     int32_t *coef = nullptr, *llx[3] = {nullptr, nullptr, nullptr};
+    uint8_t *tflags = nullptr; /* tile flags of the three planes (sbt.cuh), g.total_tiles bytes, 16-byte padded */
     HzDecPlaneBufs hz[3];
     uint8_t *d_pkt = nullptr, *h_pkt[2] = {nullptr, nullptr}; /* host staging alternates with the step parity */
     size_t pkt_alloc = 0;

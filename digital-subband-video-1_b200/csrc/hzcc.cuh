@@ -30,6 +30,8 @@ struct HzJob {
     int32_t *coef; /* dequantised coefficients (encoder: read; decoder: written) */
     int32_t *dv;   /* first-visit symbols (encoder) / values (decoder) of double-visited positions */
     const uint8_t *stable;
+    const uint8_t *tflags; /* optional tile flags of the plane (sbt.cuh): clear bits let the scan skip chunks unread */
+    int tiles_x;
     int cw, ch;
     int plane, isP;
     int chunk_base, nchunks; /* this plane's chunks inside the launch-wide chunk arrays */

@@ -23,7 +23,7 @@
  *                        atomicCAS on the first visit.
  * R0 (the first token), SEG(DC) and nruns are read on the host while it parses the packet head.
  */
-#include "hzcc.cuh"
+#include "hzcc_dec.cuh"
 #include "scan.cuh"
 
 namespace dsv {
@@ -467,6 +467,14 @@ DSV_D void scatter_one(const HzDecJob &D, unsigned long long s, int v)
             first_visit = ((ax == g.dvx[L]) && (ay < g.dvey[L])) || ((ay == g.dvy[L]) && (ax < g.dvex[L]));
         }
     }
+    if (J.tflags && r > 0 && lvl <= 2) {
+        /* tile flag (sbt.cuh): this tile's level-`lvl` blocks are no longer empty.  Byte inside an aligned word. */
+        const uint8_t *fb = J.tflags + (y >> (6 - lvl)) * J.tiles_x + (x >> (7 - lvl));
+        if (!(*fb & lvl)) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(fb);
+            atomicOr(reinterpret_cast<unsigned *>(a & ~(uintptr_t) 3), (unsigned) lvl << (8 * (a & 3)));
+        }
+    }
     int32_t *dst = J.coef + (size_t) ay * J.cw + ax;
     if (first_visit) {
         /* the next hzcc level scans this element again and overwrites it if it codes a value there */
@@ -509,6 +517,84 @@ __global__ void hzdec_dc_kernel(const HzDecJob *jobs, int njobs)
     int j = (int) (blockIdx.x * blockDim.x + threadIdx.x);
     if (j < njobs) {
         jobs[j].hz.coef[0] = jobs[j].dc;
+    }
+}
+
+/*
+ * Coefficient planes start zeroed (dsv_decoder.c:405).  Instead of clearing 4 * cw * ch bytes per plane and picture,
+ * the clean-up follows the tile flags the previous picture's scatter left behind: a tile clears the level-1 / level-2
+ * blocks it flagged and its share of the small level >= 3 corner (always), then puts its flag back to the plane's
+ * base value.  P pictures at qp85 touch no level-1 block at all: 3/4 of the plane is neither cleared nor, in the
+ * inverse transform, read.  One CTA per tile and plane.
+ */
+__global__ void __launch_bounds__(256) hzdec_clean_kernel(const HzCleanItem *items)
+{
+    const HzCleanItem &C = items[blockIdx.y];
+    const int t = (int) blockIdx.x;
+    if (t >= C.tiles_x * C.tiles_y) {
+        return;
+    }
+    const int ty = t / C.tiles_x, tx = t - ty * C.tiles_x;
+    const int f = C.tflags[t];
+    __syncthreads(); /* every thread has the flag before thread 0 resets it */
+    /* rectangle q: 0 = the corner [0, x2) x [0, y2) in 32x16 shares, 1..3 = level-2 regions, 4..6 = level-1 regions */
+    for (int q = 0; q < 7; q++) {
+        const int lvl = q == 0 ? 2 : (q < 4 ? 2 : 1);
+        if (q > 0 && !(f & lvl)) {
+            continue;
+        }
+        const int bw = 128 >> lvl, bh = 64 >> lvl;
+        const int rx = q == 0 ? 0 : C.rx[q - 1], ry = q == 0 ? 0 : C.ry[q - 1];
+        const int rw = q == 0 ? C.x2 : C.rw[q - 1], rh = q == 0 ? C.y2 : C.rh[q - 1];
+        const int xa = tx * bw, xb = imin(xa + bw, rw), ya = ty * bh, yb = imin(ya + bh, rh);
+        const int w = xb - xa;
+        if (w <= 0 || yb <= ya) {
+            continue;
+        }
+        for (int i = (int) threadIdx.x; i < bw * (yb - ya); i += 256) {
+            const int yy = i / bw, xx = i - yy * bw;
+            if (xx < w) {
+                C.coef[(size_t) (ry + ya + yy) * C.cw + rx + xa + xx] = 0;
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        C.tflags[t] = (uint8_t) C.base;
+    }
+}
+
+int hz_flag_base(const DvGeom &g)
+{
+    /* levels with double-visited positions (odd sizes one level up) exchange values with the
+     * neighbouring level's blocks: their flags stay set, nothing is skipped there */
+    return ((g.dvx[1] >= 0 || g.dvy[1] >= 0) ? 1 : 0) | ((g.dvx[2] >= 0 || g.dvy[2] >= 0) ? 2 : 0);
+}
+
+void hzdec_fill_clean(HzCleanItem *c, const HzJob &h, int tiles_y)
+{
+    memset(c, 0, sizeof(*c));
+    c->coef = h.coef;
+    c->tflags = const_cast<uint8_t *>(h.tflags);
+    c->cw = h.cw;
+    c->tiles_x = h.tiles_x;
+    c->tiles_y = tiles_y;
+    c->base = hz_flag_base(h.dg);
+    c->x2 = h.rg.x0[4]; /* level-2 LH starts where the corner ends */
+    c->y2 = h.rg.y0[5];
+    for (int q = 0; q < 6; q++) {
+        c->rx[q] = h.rg.x0[4 + q];
+        c->ry[q] = h.rg.y0[4 + q];
+        /* a region may be one column / row wider than the plane's band when the size one level down is odd: stay inside the plane */
+        c->rw[q] = imin(h.rg.sw[4 + q], h.cw - h.rg.x0[4 + q]);
+        c->rh[q] = imin(h.rg.sh[4 + q], h.ch - h.rg.y0[4 + q]);
+    }
+}
+
+void hzdec_clean_launch(const HzCleanItem *d_items, int n, int max_tiles, cudaStream_t st)
+{
+    if (n > 0 && max_tiles > 0) {
+        DSV_LAUNCH(hzdec_clean_kernel, dim3((unsigned) max_tiles, (unsigned) n), dim3(256), 0, st, d_items);
+        KERNEL_CHECK();
     }
 }
 

@@ -34,6 +34,18 @@ struct HzDecDims {
     int njobs = 0, fsm_total = 0, scan_total = 0;
 };
 
+/* flag-guided clean-up of one coefficient plane before it is decoded into (hzdec_clean_kernel) */
+struct HzCleanItem {
+    int32_t *coef;
+    uint8_t *tflags;
+    int cw, tiles_x, tiles_y, base;
+    int x2, y2;                     /* the level >= 3 corner, always cleared */
+    int rx[6], ry[6], rw[6], rh[6]; /* level-2 (0..2) and level-1 (3..5) regions LH, HL, HH */
+};
+int hz_flag_base(const DvGeom &g);
+void hzdec_fill_clean(HzCleanItem *c, const HzJob &h, int tiles_y);
+void hzdec_clean_launch(const HzCleanItem *d_items, int n, int max_tiles, cudaStream_t st);
+
 /* host: read SEG(DC), nruns and the first run from the plane head (hzcc.c:309-316,485-486) */
 void hzdec_parse_head(const uint8_t *host_body, unsigned avail, unsigned plen, HzPlaneData *pd);
 void hzdec_plan(HzDecPlan *pl, int cw, int ch);

@@ -465,6 +465,38 @@ struct HzScanVisitor {
     DSV_D void dense(const HzJob &J, int base, int total, int lane) { acc.add(hz_walk_summary(J, base, total), lane); }
 };
 
+/* Tile flags (sbt.cuh): a chunk that lies inside one level-1 or level-2 band whose tiles over the chunk's rows are all
+ * flagged empty holds no symbol -- decided from a few flag bytes, without touching the 8 KB of coefficients.  (P
+ * pictures at qp85: every level-1 band, 3/4 of the plane.)  Warp-uniform. */
+DSV_D bool hz_chunk_flagged_empty(const HzJob &J, int cbase, int total, int lane)
+{
+    if (!J.tflags) {
+        return false;
+    }
+    const HzRegions &rg = J.rg;
+    const int last = imin(cbase + HZ_CHUNK, total) - 1;
+    int r = 0;
+    while (r < HZ_NREG - 1 && cbase >= rg.base[r + 1]) {
+        r++;
+    }
+    const int lvl = rg.lvl[r];
+    if (r == 0 || lvl > 2 || last >= rg.base[r + 1]) {
+        return false;
+    }
+    if (lvl == 2 && (J.dg.dvx[1] >= 0 || J.dg.dvy[1] >= 0)) {
+        return false; /* first visits of double-visited positions come from the side buffer, not from the plane */
+    }
+    const int y0 = (int) fastdiv((unsigned) (cbase - rg.base[r]), rg.fdw[r]), y1 = (int) fastdiv((unsigned) (last - rg.base[r]), rg.fdw[r]);
+    const int sh = lvl == 1 ? 5 : 4; /* a 128x64 tile holds 32 band rows of level 1, 16 of level 2 */
+    const int n = ((y1 >> sh) - (y0 >> sh) + 1) * J.tiles_x;
+    const uint8_t *f = J.tflags + (y0 >> sh) * J.tiles_x;
+    int any = 0;
+    for (int i = lane; i < n; i += 32) {
+        any |= f[i] & lvl; /* bit 0 for level 1, bit 1 for level 2 */
+    }
+    return !__any_sync(0xffffffffu, any != 0);
+}
+
 __global__ void __launch_bounds__(HZ_THREADS) hzcc_scan_kernel(const HzJob *jobs, int njobs, HzChunk *chunks, int total_chunks, const HzMap map)
 {
     const int lane = threadIdx.x & 31;
@@ -474,7 +506,10 @@ __global__ void __launch_bounds__(HZ_THREADS) hzcc_scan_kernel(const HzJob *jobs
     }
     const HzJob &J = jobs[hz_job_of_chunk(jobs, njobs, chunk, map)];
     HzScanVisitor V;
-    hz_chunk_rounds(J, (chunk - J.chunk_base) * HZ_CHUNK, J.rg.base[HZ_NREG], lane, V);
+    const int cbase = (chunk - J.chunk_base) * HZ_CHUNK;
+    if (!hz_chunk_flagged_empty(J, cbase, J.rg.base[HZ_NREG], lane)) {
+        hz_chunk_rounds(J, cbase, J.rg.base[HZ_NREG], lane, V);
+    }
     if (lane == 0) {
         HzChunk c;
         c.cnt = (int) V.acc.cnt;

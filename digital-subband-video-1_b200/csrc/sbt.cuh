@@ -66,6 +66,12 @@ struct SbtJob {
     int32_t *llx; /* hand-over scratch: LL_nlt (wo_nlt * ho_nlt ints), then LL_2 at ll2_off */
     int ll2_off;
     int32_t *dv;  /* first-visit symbols of double-visited positions (encoder) / values (decoder) */
+    /* optional, one byte per 128x64 tile (tiles_x * tiles_y): bit 0 = the tile's level-1 band blocks (64x32 each of
+     * LH, HL, HH) hold a non-zero coefficient, bit 1 = its level-2 blocks (32x16) do.  Written by the forward tile
+     * kernel's quantiser (encoder) or by the entropy decoder's scatter pass; a clear bit lets the inverse tile
+     * kernel, the HZCC scan and the decoder's clean-up skip the block without reading it.  At qp85 the level-1
+     * bands of P pictures are zero by construction (|LH| <= 4 * 255 < 2^10 = the quantiser step). */
+    uint8_t *tflags;
     const uint8_t *stable;
     int lvls, nlt;
     int isP;

@@ -94,8 +94,8 @@ DSV_D void store_n(int32_t *dst, const int *v, int n, int nvalid)
  * B-1) take the generic per-coefficient path.
  */
 template <int N>
-DSV_D void emit_quads(const SbtJob &J, const uint8_t *stab, int lvl, int wo, int ho, int bx, int by, int nvalid,
-                      int *lh, int *hl, int *hh)
+DSV_D int emit_quads(const SbtJob &J, const uint8_t *stab, int lvl, int wo, int ho, int bx, int by, int nvalid,
+                     int *lh, int *hl, int *hh)
 {
     const int cw = J.cw;
     if (J.do_quant) {
@@ -108,7 +108,7 @@ DSV_D void emit_quads(const SbtJob &J, const uint8_t *stab, int lvl, int wo, int
                     emit_h(J, true, stab, lvl, 3, bx + i, by, hh[i]);
                 }
             }
-            return;
+            return 1; /* values go through the generic path: reported as "may be non-zero" */
         }
         const int rowterm = ((by * J.pq.dby[lvl]) >> 14) * J.pq.nbh;
         const int dbx = J.pq.dbx[lvl];
@@ -135,6 +135,14 @@ DSV_D void emit_quads(const SbtJob &J, const uint8_t *stab, int lvl, int wo, int
     store_n(row0 + wo, lh, N, nvalid);
     store_n(row1, hl, N, nvalid);
     store_n(row1 + wo, hh, N, nvalid);
+    int any = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        if (i < nvalid) {
+            any |= lh[i] | hl[i] | hh[i];
+        }
+    }
+    return any;
 }
 
 #define FWD_HB_STRIDE 136 /* int16 per row of the B4T row-pass buffer: 64 L + 64 H, padded */
@@ -206,6 +214,7 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_FWD_MINB) sbt_fwd_tile_k
     const int wo1 = cw >> 1, ho1 = ch >> 1; /* cw, ch are even */
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(J.pix) | (uintptr_t) J.pstride) & 7) == 0;
     int32_t *llA = s_ll1;
+    int any1 = isI ? 1 : 0, any2 = 0; /* tile flags (sbt.cuh): level 1 of an I picture is dense anyway */
 
     /* ---- level 1 ------------------------------------------------------------------------- */
     if (!isI) {
@@ -251,7 +260,7 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_FWD_MINB) sbt_fwd_tile_k
                 hh[i] = b - d;
             }
             *reinterpret_cast<int4 *>(llA + qrow * (SBT_TW / 2) + qc) = make_int4(ll[0], ll[1], ll[2], ll[3]);
-            emit_quads<4>(J, stab, 1, wo1, ho1, gxs[it], gys[it], nv[it], lh, hl, hh);
+            any1 |= emit_quads<4>(J, stab, 1, wo1, ho1, gxs[it], gys[it], nv[it], lh, hl, hh);
         }
     } else {
         /* B4T rows (sbt.c:91-126) straight from global memory: s_hb[r][k] = L, s_hb[r][64 + k] = H for the
@@ -353,7 +362,7 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_FWD_MINB) sbt_fwd_tile_k
             }
         }
     }
-    __syncthreads();
+    any1 = __syncthreads_or(any1);
 
     /* ---- level 2: a thread owns 2 adjacent quads (LL scaled by 4/5: I always, P for level > 1) ---- */
     {
@@ -381,8 +390,9 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_FWD_MINB) sbt_fwd_tile_k
             store_n(ll2 + (size_t) gy * wo + gx, ll, 2, nv);
             const bool all2 = row2 && (2 * gx + 2 * nv - 1 < ws);
             if (all2) {
-                emit_quads<2>(J, stab, 2, wo, ho, gx, gy, nv, lh, hl, hh);
+                any2 |= emit_quads<2>(J, stab, 2, wo, ho, gx, gy, nv, lh, hl, hh);
             } else {
+                any2 = 1; /* odd edges: generic path */
 #pragma unroll
                 for (int i = 0; i < 2; i++) {
                     const bool col2 = i < nv && 2 * (gx + i) + 1 < ws;
@@ -400,6 +410,15 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_FWD_MINB) sbt_fwd_tile_k
                     }
                 }
             }
+        }
+    }
+    if (J.tflags) { /* uniform */
+        any2 = __syncthreads_or(any2);
+        if (tid == 0) {
+            J.tflags[t] = (uint8_t) ((any1 ? 1 : 0) | (any2 ? 2 : 0));
+#ifdef DSV_CPU_EMU
+            if (getenv("DSV_DEBUG_FLAGS")) fprintf(stderr, "fwd plane %d isP %d tile %d flags %d sh %d/%d\n", J.plane, J.isP, t, J.tflags[t], J.pq.sh_plain, J.pq.sh_hq);
+#endif
         }
     }
 }

@@ -76,7 +76,9 @@ struct Win {
 
 static size_t inv_tile_smem(bool anyI)
 {
-    return (size_t) (INV_OFF3 + (anyI ? INV_I_EXTRA : 0)) * sizeof(int32_t);
+    const size_t generic = (size_t) INV_OFF3 + (anyI ? INV_I_EXTRA : 0);
+    const size_t fast = (size_t) 72 * 36 + 36 * 20; /* INV_FAST_ELEMS: interior tiles of P pictures */
+    return (generic > fast ? generic : fast) * sizeof(int32_t);
 }
 
 DSV_D unsigned pack4_u8(int a, int b, int c, int d) { return pack_u8x4(a + 128, b + 128, c + 128, d + 128); }
@@ -118,6 +120,354 @@ DSV_D void store_row8(const SbtJob &J, int oy, int ox, const int *v)
             }
         }
     }
+}
+
+/* 8 samples of one output row whose residual is exactly zero: 128, or the prediction itself */
+DSV_D void store_row8_zero(const SbtJob &J, int oy, int ox)
+{
+    if (oy >= J.ph || ox >= J.pw) {
+        return;
+    }
+    uint8_t *dst = J.opix + (size_t) oy * J.ostride + ox;
+    const uint8_t *ap = J.addp ? J.addp + (size_t) oy * J.addstride + ox : nullptr;
+    if (ox + 8 <= J.pw && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(ap)) & 7) == 0) {
+        *reinterpret_cast<uint2 *>(dst) = ap ? *reinterpret_cast<const uint2 *>(ap) : make_uint2(0x80808080u, 0x80808080u);
+    } else {
+        for (int e = 0; e < 8 && ox + e < J.pw; e++) {
+            dst[e] = ap ? ap[e] : (uint8_t) 128;
+        }
+    }
+}
+
+/* smooth_nudge_d for a zero high-band coefficient: non-zero only where LL is strictly monotonic across the pair */
+DSV_D int smooth_nudge_z(int mn0, int mx0, int bound)
+{
+    const int mx = imin(imax(mn0, mx0), 0), mn = imax(imin(mn0, mx0), 0);
+    const int t = iclamp(rnd_shift<2>(mn0 + mx0), mx, mn); /* mx == mn == 0 clamps t to 0, and 0 nudges to 0 */
+    return iclamp(rnd_shift<1>(t), -bound, bound);
+}
+
+/*
+ * Level 1 of a P picture for one tile: a thread owns 4 adjacent pairs = 8 x 2 output samples (cw, ch are even, so
+ * every pair is complete; no LL scaling at level 1 of P frames).  EMPTY: the tile's three level-1 band blocks are all
+ * zero (tile flag): no coefficient is loaded, and a warp whose whole LL neighbourhood is zero as well stores the
+ * zero residual (128, or the prediction) without any arithmetic.
+ */
+template <bool EMPTY> DSV_D void inv_level1_p(const SbtJob &J, const Win &w, const int32_t *LLw, int tx, int ty, int tid)
+{
+    const int cw = J.cw, ch = J.ch;
+    const bool filtered = J.plane == 0;
+    const int ww = w.b - w.a;
+    const int wo = cw >> 1, ho = ch >> 1;
+    const int bound = J.hqp[1];
+#pragma unroll 1
+    for (int g = tid; g < (SBT_TW / 8) * (SBT_TH / 2); g += SBT_TILE_THREADS) {
+        const int qrow = g >> 4, qc = (g & 15) * 4;
+        const int jy = ty * (SBT_TH / 2) + qrow, jx = tx * (SBT_TW / 2) + qc;
+        const bool active = jy < ho && jx < wo;
+        if (!EMPTY && !active) {
+            continue;
+        }
+        const int32_t *pc = LLw + (jy - w.ha) * ww + (jx - w.a);
+        int r0[8], r1[8];
+        int Lc[4];
+        if (EMPTY) {
+            /* the warp's trip count is uniform (512 groups, 256 threads); inactive lanes vote "zero" */
+            int z = 0;
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    Lc[i] = pc[i];
+                    z |= Lc[i];
+                }
+                if (filtered) {
+                    z |= pc[4] | (jx > 0 ? pc[-1] : 0);
+                    if (jy > 0) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            z |= pc[i - ww] | pc[i + ww];
+                        }
+                    }
+                }
+            }
+            if (__all_sync(0xffffffffu, z == 0)) {
+                if (active) {
+                    store_row8_zero(J, 2 * jy, 2 * jx);
+                    store_row8_zero(J, 2 * jy + 1, 2 * jx);
+                }
+                continue;
+            }
+            if (!active) {
+                continue;
+            }
+            int h[4] = {0, 0, 0, 0}, v[4] = {0, 0, 0, 0};
+            if (filtered) {
+                int d[5];
+                d[0] = (jx > 0 ? pc[-1] : Lc[0]) - Lc[0];
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    d[i + 1] = Lc[i] - Lc[i + 1];
+                }
+                d[4] = Lc[3] - pc[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (i > 0 || jx > 0) {
+                        h[i] = smooth_nudge_z(d[i], d[i + 1], bound);
+                    }
+                }
+                if (jy > 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        v[i] = smooth_nudge_z(pc[i - ww] - Lc[i], Lc[i] - pc[i + ww], bound);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int sa = Lc[i] + h[i], sb = Lc[i] - h[i];
+                r0[2 * i] = div4_trunc(sa + v[i]);
+                r0[2 * i + 1] = div4_trunc(sb + v[i]);
+                r1[2 * i] = div4_trunc(sa - v[i]);
+                r1[2 * i + 1] = div4_trunc(sb - v[i]);
+            }
+        } else {
+            const int nv = imin(4, wo - jx);
+            const int32_t *pLH = J.coef + (size_t) jy * cw + wo + jx;
+            const int32_t *pHL = J.coef + (size_t) (ho + jy) * cw + jx;
+            const int32_t *pHH = pHL + wo;
+            int LH[4] = {0, 0, 0, 0}, HL[4] = {0, 0, 0, 0}, HH[4] = {0, 0, 0, 0};
+            if (nv == 4 && ((reinterpret_cast<uintptr_t>(pLH) | reinterpret_cast<uintptr_t>(pHL) | reinterpret_cast<uintptr_t>(pHH)) & 15) == 0) {
+                const int4 a = *reinterpret_cast<const int4 *>(pLH), b = *reinterpret_cast<const int4 *>(pHL), c = *reinterpret_cast<const int4 *>(pHH);
+                LH[0] = a.x; LH[1] = a.y; LH[2] = a.z; LH[3] = a.w;
+                HL[0] = b.x; HL[1] = b.y; HL[2] = b.z; HL[3] = b.w;
+                HH[0] = c.x; HH[1] = c.y; HH[2] = c.z; HH[3] = c.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (i < nv) {
+                        LH[i] = pLH[i];
+                        HL[i] = pHL[i];
+                        HH[i] = pHH[i];
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                Lc[i] = pc[i];
+            }
+            if (filtered) {
+                /* horizontal nudges share the LL differences of neighbouring pairs; the window already holds the
+                 * reference's "next LL" values past the quadrant, only the first column / row of the plane is special */
+                int d[5];
+                d[0] = (jx > 0 ? pc[-1] : Lc[0]) - Lc[0];
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    d[i + 1] = Lc[i] - Lc[i + 1];
+                }
+                d[4] = Lc[3] - pc[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (i > 0 || jx > 0) {
+                        LH[i] = smooth_nudge_d(d[i], d[i + 1], LH[i], bound);
+                    }
+                }
+                if (jy > 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        HL[i] = smooth_nudge_d(pc[i - ww] - Lc[i], Lc[i] - pc[i + ww], HL[i], bound);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int LL = Lc[i];
+                const int sa = LL + LH[i], sb = LL - LH[i], sc = HL[i] + HH[i], sd = HL[i] - HH[i];
+                r0[2 * i] = div4_trunc(sa + sc);
+                r0[2 * i + 1] = div4_trunc(sb + sd);
+                r1[2 * i] = div4_trunc(sa - sc);
+                r1[2 * i + 1] = div4_trunc(sb - sd);
+            }
+        }
+        store_row8(J, 2 * jy, 2 * jx, r0);
+        store_row8(J, 2 * jy + 1, 2 * jx, r1);
+    }
+}
+
+/* ---- interior tiles of P pictures: compile-time geometry ---------------------------------------------------------
+ * A tile that has a full tile on every side needs none of the edge rules: every pair is complete, every nudge has
+ * both neighbours, every 8-sample row store is in bounds and aligned.  The windows then have fixed shapes, so the
+ * index arithmetic is constant-folded and the bounds tests (a third of the generic path's instructions) disappear.
+ *   LL_2 window  (32 + 4H) x (16 + 4H) at pitch FW2, element (jx2, jy2) of the plane at column jx2 - 32 tx + 2H, ...
+ *   LL_1 window  pitch FW1: element jx1 at column jx1 - 64 tx + 4 (the four values a thread owns are 16-byte aligned),
+ *                row jy1 - 32 ty + 2
+ * H = 1 for the filtered (luma) inverse, whose nudges look one LL value to each side. */
+#define FW1 72
+#define FH1 36
+#define FW2 36
+#define FH2 20
+#define INV_FAST_ELEMS (FW1 * FH1 + FW2 * FH2)
+
+DSV_D int clamp_s8(int v) { return imax(imin(v, 127), -128); }
+
+/* 8 reconstructed samples: clamp_u8(v + 128), or with a prediction clamp_u8(clamp_u8(v + 128) + p - 128)
+ * == clamp_u8(clamp(v, -128, 127) + p): the byte of p is added by a dp4a whose other operand selects it */
+template <bool ADDP> DSV_D void store8_fast(uint8_t *dst, const uint8_t *ap, const int *v)
+{
+    if (ADDP) {
+        const uint2 p = *reinterpret_cast<const uint2 *>(ap);
+        int o[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            o[e] = (int) __dp4a(e < 4 ? p.x : p.y, 1u << (8 * (e & 3)), (unsigned) clamp_s8(v[e]));
+        }
+        *reinterpret_cast<uint2 *>(dst) = make_uint2(pack_u8x4(o[0], o[1], o[2], o[3]), pack_u8x4(o[4], o[5], o[6], o[7]));
+    } else {
+        *reinterpret_cast<uint2 *>(dst) = make_uint2(pack4_u8(v[0], v[1], v[2], v[3]), pack4_u8(v[4], v[5], v[6], v[7]));
+    }
+}
+
+template <bool FILT, bool ADDP>
+DSV_D void inv_tile_fast_p(const SbtJob &J, int tx, int ty, int f1, int f2, int32_t *sm, int tid)
+{
+    constexpr int H = FILT ? 1 : 0;
+    const int cw = J.cw;
+    const int wo1 = cw >> 1, ho1 = J.ch >> 1, wo2 = sbt_wo(cw, 2), ho2 = sbt_wo(J.ch, 2);
+    int32_t *win1 = sm, *win2 = sm + FW1 * FH1;
+    {
+        const int32_t *ll2 = J.llx + J.ll2_off + (size_t) (ty * 16 - 2 * H) * wo2 + tx * 32 - 2 * H;
+        constexpr int W2 = 32 + 4 * H, H2 = 16 + 4 * H;
+        for (int i = tid; i < W2 * H2; i += SBT_TILE_THREADS) {
+            const int y = i / W2, x = i - y * W2;
+            win2[y * FW2 + x] = ll_up(ll2[(size_t) y * wo2 + x]); /* LL scaled by 5/4 (sbt.c:20-22) */
+        }
+    }
+    __syncthreads();
+    {
+        /* level 2: one pair per thread, 34 x 18 pairs (the tile's 32 x 16 and the ring level 1 looks at) */
+        constexpr int NPX = 32 + 2 * H, NPY = 16 + 2 * H;
+        const int bound = J.hqp[2];
+        const int32_t *bLH = J.coef + (size_t) (ty * 16 - H) * cw + wo2 + tx * 32 - H;
+        const int32_t *bHL = J.coef + (size_t) (ho2 + ty * 16 - H) * cw + tx * 32 - H;
+        for (int p = tid; p < NPX * NPY; p += SBT_TILE_THREADS) {
+            const int py = p / NPX, px = p - py * NPX;
+            const int32_t *pc = win2 + (py + H) * FW2 + px + H;
+            const int LL = pc[0];
+            int LH = 0, HL = 0, HH = 0;
+            if (f2) {
+                const size_t o = (size_t) py * cw + px;
+                LH = bLH[o];
+                HL = bHL[o];
+                HH = bHL[o + wo2];
+            }
+            if (FILT) {
+                LH = smooth_nudge_d(pc[-1] - LL, LL - pc[1], LH, bound);
+                HL = smooth_nudge_d(pc[-FW2] - LL, LL - pc[FW2], HL, bound);
+            }
+            const int sa = LL + LH, sb = LL - LH, sc = HL + HH, sd = HL - HH;
+            int32_t *dst = win1 + (2 * py - 2 * H + 2) * FW1 + 2 * px - 2 * H + 4;
+            *reinterpret_cast<int2 *>(dst) = make_int2(div4_trunc(sa + sc), div4_trunc(sb + sd));
+            *reinterpret_cast<int2 *>(dst + FW1) = make_int2(div4_trunc(sa - sc), div4_trunc(sb - sd));
+        }
+    }
+    __syncthreads();
+    /* level 1: a thread owns 4 adjacent pairs = 8 x 2 samples, twice */
+    const int bound = J.hqp[1];
+#pragma unroll 1
+    for (int it = 0; it < 2; it++) {
+        const int g = tid + it * SBT_TILE_THREADS;
+        const int qrow = g >> 4, qc = (g & 15) * 4;
+        const int jy = ty * (SBT_TH / 2) + qrow, jx = tx * (SBT_TW / 2) + qc;
+        const int32_t *pc = win1 + (qrow + 2) * FW1 + qc + 4;
+        const int4 c4 = *reinterpret_cast<const int4 *>(pc);
+        const int Lc[4] = {c4.x, c4.y, c4.z, c4.w};
+        int up[4] = {0, 0, 0, 0}, dn[4] = {0, 0, 0, 0}, lf = 0, rt = 0;
+        if (FILT) {
+            const int4 u4 = *reinterpret_cast<const int4 *>(pc - FW1), d4 = *reinterpret_cast<const int4 *>(pc + FW1);
+            up[0] = u4.x; up[1] = u4.y; up[2] = u4.z; up[3] = u4.w;
+            dn[0] = d4.x; dn[1] = d4.y; dn[2] = d4.z; dn[3] = d4.w;
+            lf = pc[-1];
+            rt = pc[4];
+        }
+        uint8_t *dst = J.opix + (size_t) (2 * jy) * J.ostride + 2 * jx;
+        const uint8_t *ap = ADDP ? J.addp + (size_t) (2 * jy) * J.addstride + 2 * jx : nullptr;
+        int LH[4] = {0, 0, 0, 0}, HL[4] = {0, 0, 0, 0}, HH[4] = {0, 0, 0, 0};
+        if (!f1) {
+            /* the tile's level-1 blocks are empty: nothing to load, and a warp whose LL neighbourhood is zero too
+             * has a zero residual */
+            int z = Lc[0] | Lc[1] | Lc[2] | Lc[3];
+            if (FILT) {
+                z |= lf | rt | up[0] | up[1] | up[2] | up[3] | dn[0] | dn[1] | dn[2] | dn[3];
+            }
+            if (__all_sync(0xffffffffu, z == 0)) {
+                if (ADDP) {
+                    *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<const uint2 *>(ap);
+                    *reinterpret_cast<uint2 *>(dst + J.ostride) = *reinterpret_cast<const uint2 *>(ap + J.addstride);
+                } else {
+                    *reinterpret_cast<uint2 *>(dst) = make_uint2(0x80808080u, 0x80808080u);
+                    *reinterpret_cast<uint2 *>(dst + J.ostride) = make_uint2(0x80808080u, 0x80808080u);
+                }
+                continue;
+            }
+            if (FILT) {
+                const int d[5] = {lf - Lc[0], Lc[0] - Lc[1], Lc[1] - Lc[2], Lc[2] - Lc[3], Lc[3] - rt};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    LH[i] = smooth_nudge_z(d[i], d[i + 1], bound);
+                    HL[i] = smooth_nudge_z(up[i] - Lc[i], Lc[i] - dn[i], bound);
+                }
+            }
+        } else {
+            const int32_t *pLH = J.coef + (size_t) jy * cw + wo1 + jx;
+            const int32_t *pHL = J.coef + (size_t) (ho1 + jy) * cw + jx;
+            const int4 a = *reinterpret_cast<const int4 *>(pLH), b = *reinterpret_cast<const int4 *>(pHL),
+                       c = *reinterpret_cast<const int4 *>(pHL + wo1);
+            LH[0] = a.x; LH[1] = a.y; LH[2] = a.z; LH[3] = a.w;
+            HL[0] = b.x; HL[1] = b.y; HL[2] = b.z; HL[3] = b.w;
+            HH[0] = c.x; HH[1] = c.y; HH[2] = c.z; HH[3] = c.w;
+            if (FILT) {
+                const int d[5] = {lf - Lc[0], Lc[0] - Lc[1], Lc[1] - Lc[2], Lc[2] - Lc[3], Lc[3] - rt};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    LH[i] = smooth_nudge_d(d[i], d[i + 1], LH[i], bound);
+                    HL[i] = smooth_nudge_d(up[i] - Lc[i], Lc[i] - dn[i], HL[i], bound);
+                }
+            }
+        }
+        int r0[8], r1[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int sa = Lc[i] + LH[i], sb = Lc[i] - LH[i], sc = HL[i] + HH[i], sd = HL[i] - HH[i];
+            r0[2 * i] = div4_trunc(sa + sc);
+            r0[2 * i + 1] = div4_trunc(sb + sd);
+            r1[2 * i] = div4_trunc(sa - sc);
+            r1[2 * i + 1] = div4_trunc(sb - sd);
+        }
+        store8_fast<ADDP>(dst, ap, r0);
+        store8_fast<ADDP>(dst + J.ostride, ADDP ? ap + J.addstride : nullptr, r1);
+    }
+}
+
+/* may tile (tx, ty) take the fast path?  (uniform; thread 0) */
+DSV_D bool inv_tile_is_interior(const SbtJob &J, int tx, int ty)
+{
+    if (!J.isP || tx < 1 || ty < 1) {
+        return false;
+    }
+    const int cw = J.cw, ch = J.ch;
+    const int wo1 = cw >> 1, ho1 = ch >> 1, wo2 = sbt_wo(cw, 2), ho2 = sbt_wo(ch, 2);
+    /* the windows (tile + ring) stay inside LL_1 / LL_2 proper, away from the planes' last pairs and their quirks */
+    if (tx * 64 + 66 > wo1 || ty * 32 + 34 > ho1 || tx * 32 + 34 > wo2 || ty * 16 + 18 > ho2) {
+        return false;
+    }
+    if ((tx + 1) * SBT_TW > J.pw || (ty + 1) * SBT_TH > J.ph) {
+        return false;
+    }
+    /* 16-byte coefficient loads, 8-byte sample stores */
+    uintptr_t a = reinterpret_cast<uintptr_t>(J.opix) | (uintptr_t) J.ostride;
+    if (J.addp) {
+        a |= reinterpret_cast<uintptr_t>(J.addp) | (uintptr_t) J.addstride;
+    }
+    return (a & 7) == 0 && (reinterpret_cast<uintptr_t>(J.coef) & 15) == 0 && (cw & 7) == 0;
 }
 
 template <bool MID> DSV_D int inv_load_job(SbtJob *sJ, const SbtJob *jobs, const SbtDims &dims)
@@ -306,10 +656,43 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_INV_MINB) sbt_inv_tile_k
 
     int32_t *win1 = sm, *win2 = sm + INV_OFF2;
     int32_t *ibase = sm + INV_OFF3; /* I frames only */
+    __shared__ int s_f1, s_f2; /* tile flags (sbt.cuh): level-1 blocks of this tile, level-2 blocks of the tile and its halo */
+    __shared__ int s_fast;
     if (tid == 0) {
-        inv_windows(J, W, 0, SBT_HI, gx0, gy0);
+        s_fast = inv_tile_is_interior(J, tx, ty) ? 1 : 0;
+        if (!s_fast) {
+            inv_windows(J, W, 0, SBT_HI, gx0, gy0);
+        }
+        int f1 = 1, f2 = 1;
+        if (J.tflags) {
+            f1 = J.tflags[t] & 1;
+            f2 = 0;
+            for (int ny = imax(ty - 1, 0); ny <= imin(ty + 1, J.tiles_y - 1); ny++) {
+                for (int nx = imax(tx - 1, 0); nx <= imin(tx + 1, J.tiles_x - 1); nx++) {
+                    f2 |= J.tflags[ny * J.tiles_x + nx] & 2;
+                }
+            }
+        }
+        s_f1 = f1;
+        s_f2 = f2;
     }
     __syncthreads();
+    if (s_fast) {
+        if (filtered) {
+            if (J.addp) {
+                inv_tile_fast_p<true, true>(J, tx, ty, s_f1, s_f2, sm, tid);
+            } else {
+                inv_tile_fast_p<true, false>(J, tx, ty, s_f1, s_f2, sm, tid);
+            }
+        } else {
+            if (J.addp) {
+                inv_tile_fast_p<false, true>(J, tx, ty, s_f1, s_f2, sm, tid);
+            } else {
+                inv_tile_fast_p<false, false>(J, tx, ty, s_f1, s_f2, sm, tid);
+            }
+        }
+        return;
+    }
     {
         /* LL_2 window, already scaled by 5/4 (sbt.c:20-22) and, for filtered planes, extended by the column / row
          * the reference reads as "next LL" of the last pair (Appendix B-2) */
@@ -338,6 +721,7 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_INV_MINB) sbt_inv_tile_k
         const int ww = w.b - w.a, oww = o.b - o.a;
         const int ws = sbt_ws(cw, 2), hs = sbt_ws(ch, 2), wo = sbt_wo(cw, 2), ho = sbt_wo(ch, 2);
         const int bound = J.hqp[2];
+        const int f2 = s_f2;
         const int npx = w.pb - w.pa, npy = w.qb - w.qa;
         const int mag = magic20(npx);
         const int o_b = imin(o.b, ws), o_hb = imin(o.hb, hs); /* level 2 produces LL_1 proper only */
@@ -349,11 +733,14 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_INV_MINB) sbt_inv_tile_k
             const int LL = pc[0];
             int v00, v01 = 0, v10 = 0, v11 = 0;
             if (col2 && row2) {
-                const int32_t *pb = J.coef + (size_t) jy * cw + wo + jx;
-                int LH = pb[0];
-                const int32_t *pb2 = J.coef + (size_t) (ho + jy) * cw + jx;
-                int HL = pb2[0];
-                const int HH = pb2[wo];
+                int LH = 0, HL = 0, HH = 0;
+                if (f2) {
+                    const int32_t *pb = J.coef + (size_t) jy * cw + wo + jx;
+                    LH = pb[0];
+                    const int32_t *pb2 = J.coef + (size_t) (ho + jy) * cw + jx;
+                    HL = pb2[0];
+                    HH = pb2[wo];
+                }
                 if (filtered) {
                     if (jx > 0) {
                         LH = smooth_nudge_d(pc[-1] - LL, LL - pc[1], LH, bound);
@@ -368,11 +755,11 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_INV_MINB) sbt_inv_tile_k
                 v10 = div4_trunc(sa - sc);
                 v11 = div4_trunc(sb - sd);
             } else if (row2) {
-                const int HL = J.coef[(size_t) (ho + jy) * cw + jx];
+                const int HL = f2 ? J.coef[(size_t) (ho + jy) * cw + jx] : 0;
                 v00 = div4_trunc(LL + HL);
                 v10 = div4_trunc(LL - HL);
             } else if (col2) {
-                const int LH = J.coef[(size_t) jy * cw + wo + jx];
+                const int LH = f2 ? J.coef[(size_t) jy * cw + wo + jx] : 0;
                 v00 = div4_trunc(LL + LH);
                 v01 = div4_trunc(LL - LH);
             } else {
@@ -409,81 +796,12 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_INV_MINB) sbt_inv_tile_k
     }
     __syncthreads();
 
-    /* ---- level 1 of P frames: a thread owns 4 adjacent pairs = 8 x 2 output samples (cw, ch are even, so
-     * every pair is complete; no LL scaling at level 1 of P frames) ---------------------------------- */
+    /* ---- level 1 of P frames (inv_level1_p) ----------------------------------------------------------- */
     if (!isI) {
-        const Win w = W[1];
-        const int ww = w.b - w.a;
-        const int wo = cw >> 1, ho = ch >> 1;
-        const int bound = J.hqp[1];
-        const int32_t *LLw = win1;
-        for (int g = tid; g < (SBT_TW / 8) * (SBT_TH / 2); g += SBT_TILE_THREADS) {
-            const int qrow = g >> 4, qc = (g & 15) * 4;
-            const int jy = ty * (SBT_TH / 2) + qrow, jx = tx * (SBT_TW / 2) + qc;
-            if (jy >= ho || jx >= wo) {
-                continue;
-            }
-            const int nv = imin(4, wo - jx);
-            const int32_t *pLH = J.coef + (size_t) jy * cw + wo + jx;
-            const int32_t *pHL = J.coef + (size_t) (ho + jy) * cw + jx;
-            const int32_t *pHH = pHL + wo;
-            int LH[4] = {0, 0, 0, 0}, HL[4] = {0, 0, 0, 0}, HH[4] = {0, 0, 0, 0};
-            if (nv == 4 && ((reinterpret_cast<uintptr_t>(pLH) | reinterpret_cast<uintptr_t>(pHL) | reinterpret_cast<uintptr_t>(pHH)) & 15) == 0) {
-                const int4 a = *reinterpret_cast<const int4 *>(pLH), b = *reinterpret_cast<const int4 *>(pHL), c = *reinterpret_cast<const int4 *>(pHH);
-                LH[0] = a.x; LH[1] = a.y; LH[2] = a.z; LH[3] = a.w;
-                HL[0] = b.x; HL[1] = b.y; HL[2] = b.z; HL[3] = b.w;
-                HH[0] = c.x; HH[1] = c.y; HH[2] = c.z; HH[3] = c.w;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (i < nv) {
-                        LH[i] = pLH[i];
-                        HL[i] = pHL[i];
-                        HH[i] = pHH[i];
-                    }
-                }
-            }
-            const int32_t *pc = LLw + (jy - w.ha) * ww + (jx - w.a);
-            int r0[8], r1[8];
-            int Lc[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                Lc[i] = pc[i];
-            }
-            if (filtered) {
-                /* horizontal nudges share the LL differences of neighbouring pairs; the window already holds the
-                 * reference's "next LL" values past the quadrant, only the first column / row of the plane is special */
-                int d[5];
-                d[0] = (jx > 0 ? pc[-1] : Lc[0]) - Lc[0];
-#pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    d[i + 1] = Lc[i] - Lc[i + 1];
-                }
-                d[4] = Lc[3] - pc[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (i > 0 || jx > 0) {
-                        LH[i] = smooth_nudge_d(d[i], d[i + 1], LH[i], bound);
-                    }
-                }
-                if (jy > 0) {
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        HL[i] = smooth_nudge_d(pc[i - ww] - Lc[i], Lc[i] - pc[i + ww], HL[i], bound);
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int LL = Lc[i];
-                const int sa = LL + LH[i], sb = LL - LH[i], sc = HL[i] + HH[i], sd = HL[i] - HH[i];
-                r0[2 * i] = div4_trunc(sa + sc);
-                r0[2 * i + 1] = div4_trunc(sb + sd);
-                r1[2 * i] = div4_trunc(sa - sc);
-                r1[2 * i + 1] = div4_trunc(sb - sd);
-            }
-            store_row8(J, 2 * jy, 2 * jx, r0);
-            store_row8(J, 2 * jy + 1, 2 * jx, r1);
+        if (s_f1) {
+            inv_level1_p<false>(J, W[1], win1, tx, ty, tid);
+        } else {
+            inv_level1_p<true>(J, W[1], win1, tx, ty, tid);
         }
     }
 

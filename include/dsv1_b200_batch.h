@@ -42,6 +42,10 @@ void dsvb_enc_destroy(DSVB_ENC *e);
 int dsvb_encode(DSVB_ENC *e, int nseq, int nframes, const uint8_t *const *yuv, int on_device,
                 uint8_t *const *streams, const long *caps, long *lens);
 void dsvb_enc_stats(DSVB_ENC *e, double *stats, int reset);
+/* Test hook: the per-tile band flags (one byte per 128x64 tile, planes Y, U, V back to back; bit 0 = the tile's
+ * level-1 band blocks hold a non-zero coefficient, bit 1 = its level-2 blocks do) that the last picture coded on
+ * `lane` left behind.  Returns the number of tiles per picture, at most `cap` bytes are written. */
+int dsvb_enc_tile_flags(DSVB_ENC *e, int lane, uint8_t *out, int cap);
 
 DSVB_DEC *dsvb_dec_create(int lanes, int device);
 void dsvb_dec_destroy(DSVB_DEC *d);

@@ -146,6 +146,18 @@ static inline int __all_sync(unsigned m, int p)
     unsigned full = wsz == 32 ? 0xffffffffu : ((1u << wsz) - 1);
     return __ballot_sync(m, p) == full;
 }
+/* block-wide OR of a predicate with barrier semantics: every thread of the block must call */
+static inline int __syncthreads_or(int pred)
+{
+    emu::g_blk->xchg[emu::t_lin] = pred ? 1 : 0;
+    __syncthreads();
+    int r = 0;
+    for (unsigned i = 0; i < emu::g_blk->nthreads; i++) {
+        r |= (int) (emu::g_blk->xchg[i] & 1);
+    }
+    __syncthreads();
+    return r;
+}
 static inline unsigned __activemask() { return 0xffffffffu; }
 static inline int __reduce_add_sync(unsigned m, int v)
 {

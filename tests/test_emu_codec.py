@@ -180,3 +180,18 @@ def test_long_sequence_chain_sharding_tiny(emu, ref):
     got, info = mg.encode_long(yuv[:fb * 5], 5)
     mg.close()
     assert got == ref.encode_sequence(cfg, yuv[:fb * 5], 5)[0] and info[3] == 2
+
+
+def test_codec_interior_tiles(emu, ref):
+    """384x192: the smallest picture with an interior 128x64 tile, i.e. the inverse transform's compile-time-geometry
+    path, combined with the empty-band tile flags of P pictures (encoder: flags from the quantiser, reconstruction
+    feeds the next P picture; decoder: flags from the scatter pass, flag-guided clean-up)."""
+    w, h, fmt, n = 384, 192, "420", 3
+    yuv = L.synth_sequence(w, h, fmt, n, 3, 0)
+    cfg = L.make_cfg(w, h, fmt, gop=12)
+    sa, pa, _ = ref.encode_sequence(cfg, yuv, n)
+    sb, pb, _ = emu.encode_sequence(cfg, yuv, n)
+    assert sa == sb
+    na, da, _, _ = ref.decode_stream(sa, w, h, L.SUBSAMP[fmt], n)
+    nb, db, _, _ = emu.decode_stream(sa, w, h, L.SUBSAMP[fmt], n)
+    assert na == nb == n and np.array_equal(da, db)

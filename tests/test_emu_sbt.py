@@ -15,7 +15,7 @@ def emu():
     return L.emu()
 
 
-@pytest.mark.parametrize("dims", [(16, 16, 16, 16), (120, 68, 120, 68), (135, 67, 136, 68), (427, 240, 428, 240)])
+@pytest.mark.parametrize("dims", [(16, 16, 16, 16), (120, 68, 120, 68), (135, 67, 136, 68), (427, 240, 428, 240), (384, 192, 384, 192)])
 @pytest.mark.parametrize("isP", [0, 1])
 def test_sbt(emu, port, dims, isP):
     pw, ph, cw, ch = dims
@@ -28,7 +28,7 @@ def test_sbt(emu, port, dims, isP):
         assert np.array_equal(port.inv_sbt(co, 313, isP, c, pw, ph), emu.inv_sbt(co, 313, isP, c, pw, ph))
 
 
-@pytest.mark.parametrize("dims", [(120, 68, 120, 68), (427, 240, 428, 240)])
+@pytest.mark.parametrize("dims", [(120, 68, 120, 68), (427, 240, 428, 240), (384, 192, 384, 192)])
 def test_inverse_sparse(emu, port, dims):
     """Mostly-zero coefficient planes (what P pictures look like): flat LL areas next to isolated values."""
     from test_gpu_sbt import sparse_coefs
