@@ -204,14 +204,16 @@ extern "C" int dsvb_encode(DSVB_ENC *e, int nseq, int nframes, const uint8_t *co
                 dst[(size_t) k].on_device = on_device;
             }
         };
-        /* host pictures: picture t+1 crosses PCIe on the copy stream while picture t is being encoded */
-        if (!on_device && nframes > 0) {
-            pictures(0, next);
+        /* host pictures cross PCIe on the copy stream up to ENC_STAGE_SLOTS - 1 steps ahead of the encoder: the copy
+         * engine keeps working through the long I-picture step and the short P-picture steps never wait for input */
+        const int ahead = ENC_STAGE_SLOTS - 1;
+        for (int t = 0; !on_device && t < ahead && t < nframes; t++) {
+            pictures(t, next);
             e->eng->prefetch(n, ids.data(), next.data());
         }
         for (int t = 0; t < nframes; t++) {
-            if (!on_device && t + 1 < nframes) {
-                pictures(t + 1, next);
+            if (!on_device && t + ahead < nframes) {
+                pictures(t + ahead, next);
                 e->eng->prefetch(n, ids.data(), next.data());
             }
             pictures(t, src);

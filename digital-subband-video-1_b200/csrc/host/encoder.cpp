@@ -366,8 +366,9 @@ EncEngine::EncEngine(const DSV_META &md, int gop, int pyramid_levels, int lanes)
         CUDA_CHECK(cudaEventCreate(&e));
     }
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_search_, cudaEventDisableTiming));
-    CUDA_CHECK(cudaEventCreateWithFlags(&ev_pref_[0], cudaEventDisableTiming));
-    CUDA_CHECK(cudaEventCreateWithFlags(&ev_pref_[1], cudaEventDisableTiming));
+    for (auto &e : ev_pref_) {
+        CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     const size_t per_lane = 3 * (sizeof(SbtJob) + sizeof(HzJob)) + sizeof(HzFrame) + (size_t) (levels_ + 1) * sizeof(HmeArgs) +
                             sizeof(BmcArgs) + 8 * sizeof(PlaneRef) + 2 * sizeof(ZeroItem) + 2048;
     arena_.create(per_lane * (size_t) L_ + 4096);
@@ -384,8 +385,9 @@ EncEngine::EncEngine(const DSV_META &md, int gop, int pyramid_levels, int lanes)
     CUDA_CHECK(cudaMallocHost(&h_frames_, sizeof(HzFrame) * (size_t) L_));
     CUDA_CHECK(cudaMallocHost(&h_pk_, sizeof(CopyItem) * (size_t) L_));
     in_pitch_ = (g_.frame_bytes + 255) & ~(size_t) 255;
-    CUDA_CHECK(cudaMalloc(&d_in_all_[0], in_pitch_ * L_ + 256));
-    CUDA_CHECK(cudaMalloc(&d_in_all_[1], in_pitch_ * L_ + 256));
+    for (auto &b : d_in_all_) {
+        CUDA_CHECK(cudaMalloc(&b, in_pitch_ * L_ + 256));
+    }
     if (L_ > 1) {
         int nt = (int) std::thread::hardware_concurrency() / 2;
         if (const char *e = getenv("DSV_HOST_THREADS")) {
@@ -398,8 +400,9 @@ EncEngine::EncEngine(const DSV_META &md, int gop, int pyramid_levels, int lanes)
     for (int i = 0; i < L_; i++) {
         alloc_lane(lanes_[(size_t) i]);
         lanes_[(size_t) i].d_mvf[0] = d_mv0_ + (size_t) i * g_.nblk;
-        lanes_[(size_t) i].d_in[0] = d_in_all_[0] + in_pitch_ * i;
-        lanes_[(size_t) i].d_in[1] = d_in_all_[1] + in_pitch_ * i;
+        for (int b = 0; b < ENC_STAGE_SLOTS; b++) {
+            lanes_[(size_t) i].d_in[b] = d_in_all_[b] + in_pitch_ * i;
+        }
     }
 }
 
@@ -478,8 +481,9 @@ EncEngine::~EncEngine()
         free_lane(l);
     }
     arena_.destroy();
-    cudaFree(d_in_all_[0]);
-    cudaFree(d_in_all_[1]);
+    for (auto &b : d_in_all_) {
+        cudaFree(b);
+    }
     cudaFree(d_mv0_);
     cudaFreeHost(h_mv0_);
     cudaFree(d_stab_);
@@ -495,8 +499,9 @@ EncEngine::~EncEngine()
     }
     ktimes.destroy();
     cudaEventDestroy(ev_search_);
-    cudaEventDestroy(ev_pref_[0]);
-    cudaEventDestroy(ev_pref_[1]);
+    for (auto &e : ev_pref_) {
+        cudaEventDestroy(e);
+    }
     cudaStreamDestroy(st_copy_);
     cudaStreamDestroy(st_);
 }
@@ -510,7 +515,7 @@ static bool packed_pic(const CodecGeom &g, const PicRef &r)
 void EncEngine::prefetch(int n, const int *lane_ids, const PicRef *src)
 {
     const CodecGeom &g = g_;
-    bool used[2] = {false, false};
+    bool used[ENC_STAGE_SLOTS] = {};
     /* common case (the batch API): lanes 0..n-1, packed pictures at a constant distance from each other and all
      * lanes on the same staging parity -> ONE strided copy for the whole step instead of 3n API calls */
     bool uniform = n > 0 && !src[0].on_device;
@@ -526,7 +531,7 @@ void EncEngine::prefetch(int n, const int *lane_ids, const PicRef *src)
         for (int k = 0; k < n; k++) {
             EncLane &l = lanes_[(size_t) k];
             l.stage_src[b] = src[k].plane[0];
-            l.in_sel ^= 1;
+            l.in_sel = (l.in_sel + 1) % ENC_STAGE_SLOTS;
         }
         CUDA_CHECK(cudaEventRecord(ev_pref_[b], st_copy_));
         return;
@@ -548,10 +553,10 @@ void EncEngine::prefetch(int n, const int *lane_ids, const PicRef *src)
         }
         stats.h2d_bytes += g.frame_bytes;
         l.stage_src[b] = src[k].plane[0];
-        l.in_sel ^= 1;
+        l.in_sel = (l.in_sel + 1) % ENC_STAGE_SLOTS;
         used[b] = true;
     }
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < ENC_STAGE_SLOTS; b++) {
         if (used[b]) {
             CUDA_CHECK(cudaEventRecord(ev_pref_[b], st_copy_));
         }
@@ -633,14 +638,16 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     /* ---- phase 1: ingest, pyramid, luma sums, motion search -------------------------------------- */
     IngestItem *d_ing;
     IngestItem *ing = arena_.push_n<IngestItem>((size_t) 3 * n, &d_ing);
-    bool wait_pref[2] = {false, false};
+    bool wait_pref[ENC_STAGE_SLOTS] = {};
     for (int k = 0; k < n; k++) {
         EncLane &l = lanes_[(size_t) lane_ids[k]];
         l.fnum = plan ? plan[k].fnum : l.enc->next_fnum++;
         const DevFrame &dst = inter_ ? l.pad[l.cur] : l.xf;
         int pb = -1;
         if (!src[k].on_device) {
-            pb = l.stage_src[0] == src[k].plane[0] ? 0 : (l.stage_src[1] == src[k].plane[0] ? 1 : -1);
+            for (int b = 0; b < ENC_STAGE_SLOTS && pb < 0; b++) {
+                pb = l.stage_src[b] == src[k].plane[0] ? b : -1;
+            }
         }
         const bool prefetched = pb >= 0;
         if (prefetched) {
@@ -671,10 +678,10 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         }
         if (staged) {
             l.stage_src[l.in_sel] = nullptr;
-            l.in_sel ^= 1;
+            l.in_sel = (l.in_sel + 1) % ENC_STAGE_SLOTS;
         }
     }
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < ENC_STAGE_SLOTS; b++) {
         if (wait_pref[b]) {
             CUDA_CHECK(cudaStreamWaitEvent(st, ev_pref_[b], 0));
         }

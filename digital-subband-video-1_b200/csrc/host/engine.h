@@ -150,6 +150,11 @@ private:
     bool quit_ = false;
 };
 
+/* host pictures are staged on the device through a ring of ENC_STAGE_SLOTS buffers: prefetch() may run that many
+ * steps minus one ahead of step(), which lets the copy engine work through the long I-picture steps of a GOP and
+ * keeps the short P-picture steps fed (H2D of a step's pictures takes longer than a P step's kernels) */
+#define ENC_STAGE_SLOTS 4
+
 struct EncLane {
     DSV_ENCODER *enc = nullptr; /* host-side state of this sequence */
     DevFrame pad[2], recon[2], pyr[2][DSV_MAX_PYRAMID_LEVELS], xf, pred;
@@ -158,9 +163,9 @@ struct EncLane {
     int2 *d_aux = nullptr;
     int32_t *coef = nullptr, *llx[3] = {nullptr, nullptr, nullptr}, *dv[3] = {nullptr, nullptr, nullptr};
     uint8_t *tflags = nullptr; /* tile flags of the three planes (sbt.cuh), g.total_tiles bytes */
-    uint8_t *d_pkt = nullptr, *d_in[2] = {nullptr, nullptr};
+    uint8_t *d_pkt = nullptr, *d_in[ENC_STAGE_SLOTS] = {};
     int in_sel = 0;                 /* staging buffer the next inline copy / prefetch writes */
-    const uint8_t *stage_src[2] = {nullptr, nullptr}; /* host picture on its way into / held by each staging buffer */
+    const uint8_t *stage_src[ENC_STAGE_SLOTS] = {}; /* host picture on its way into / held by each staging buffer */
     unsigned pkt_dirty = 0;
     size_t pkt_cap = 0; /* bytes allocated at d_pkt */
     uint8_t *h_head = nullptr; /* pinned: packet head assembled on the host */
@@ -264,7 +269,7 @@ private:
     cudaStream_t st_ = 0, st_copy_ = 0;
     cudaEvent_t ev_[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_search_ = nullptr; /* vectors and luma sums are on the host */
-    cudaEvent_t ev_pref_[2] = {nullptr, nullptr}; /* per staging-buffer parity: prefetch copies done */
+    cudaEvent_t ev_pref_[ENC_STAGE_SLOTS] = {}; /* per staging slot: prefetch copies done */
     std::vector<EncLane> lanes_;
     StepArena arena_;
     /* lane-major arrays shared by all lanes so that one copy moves every lane's data */
@@ -275,7 +280,7 @@ private:
     HzFrame *d_frames_ = nullptr, *h_frames_ = nullptr;
     void *h_pk_ = nullptr; /* packet egress copy list (mapped pinned) */
     HostPool *pool_ = nullptr;
-    uint8_t *d_in_all_[2] = {nullptr, nullptr}; /* packed-picture staging of all lanes, lane pitch in_pitch_ */
+    uint8_t *d_in_all_[ENC_STAGE_SLOTS] = {}; /* packed-picture staging of all lanes, lane pitch in_pitch_ */
     size_t in_pitch_ = 0;
 };
 

@@ -538,23 +538,36 @@ __global__ void __launch_bounds__(256) hzdec_clean_kernel(const HzCleanItem *ite
     const int f = C.tflags[t];
     __syncthreads(); /* every thread has the flag before thread 0 resets it */
     /* rectangle q: 0 = the corner [0, x2) x [0, y2) in 32x16 shares, 1..3 = level-2 regions, 4..6 = level-1 regions */
+#pragma unroll 1
     for (int q = 0; q < 7; q++) {
-        const int lvl = q == 0 ? 2 : (q < 4 ? 2 : 1);
+        const int lvl = q < 4 ? 2 : 1;
         if (q > 0 && !(f & lvl)) {
             continue;
         }
-        const int bw = 128 >> lvl, bh = 64 >> lvl;
+        const int ls = 7 - lvl;                  /* log2 of the block width: 32 or 64 coefficients */
+        const int bw = 1 << ls, bh = 64 >> lvl;
         const int rx = q == 0 ? 0 : C.rx[q - 1], ry = q == 0 ? 0 : C.ry[q - 1];
         const int rw = q == 0 ? C.x2 : C.rw[q - 1], rh = q == 0 ? C.y2 : C.rh[q - 1];
-        const int xa = tx * bw, xb = imin(xa + bw, rw), ya = ty * bh, yb = imin(ya + bh, rh);
-        const int w = xb - xa;
-        if (w <= 0 || yb <= ya) {
+        const int xa = tx * bw, ya = ty * bh;
+        const int w = imin(bw, rw - xa), nrow = imin(bh, rh - ya);
+        if (w <= 0 || nrow <= 0) {
             continue;
         }
-        for (int i = (int) threadIdx.x; i < bw * (yb - ya); i += 256) {
-            const int yy = i / bw, xx = i - yy * bw;
-            if (xx < w) {
-                C.coef[(size_t) (ry + ya + yy) * C.cw + rx + xa + xx] = 0;
+        int32_t *base = C.coef + (size_t) (ry + ya) * C.cw + rx + xa;
+        if (((reinterpret_cast<uintptr_t>(base) | (uintptr_t) (C.cw * 4)) & 15) == 0 && (w & 3) == 0) {
+            const int vs = ls - 2; /* 16-byte stores per full row: 8 or 16 */
+            for (int i = (int) threadIdx.x; i < (nrow << vs); i += 256) {
+                const int yy = i >> vs, xx = (i & ((1 << vs) - 1)) * 4;
+                if (xx < w) {
+                    *reinterpret_cast<int4 *>(base + (size_t) yy * C.cw + xx) = make_int4(0, 0, 0, 0);
+                }
+            }
+        } else {
+            for (int i = (int) threadIdx.x; i < (nrow << ls); i += 256) {
+                const int yy = i >> ls, xx = i & (bw - 1);
+                if (xx < w) {
+                    base[(size_t) yy * C.cw + xx] = 0;
+                }
             }
         }
     }
