@@ -162,6 +162,15 @@ extern "C" int dsvb_enc_tile_flags(DSVB_ENC *e, int lane, uint8_t *out, int cap)
     DSV_API_END(-100)
 }
 
+extern "C" void dsvb_enc_set_kernel_timing(DSVB_ENC *e, int on) { e->eng->time_kernels = on != 0; }
+extern "C" void dsvb_dec_set_kernel_timing(DSVB_DEC *d, int on)
+{
+    d->time_kernels = on != 0;
+    if (d->eng) {
+        d->eng->time_kernels = on != 0;
+    }
+}
+
 extern "C" int dsvb_kernel_count(void) { return kt_count(); }
 extern "C" const char *dsvb_kernel_name(int i) { return kt_name(i); }
 extern "C" void dsvb_enc_kernel_times(DSVB_ENC *e, double *ms, double *launches, int reset)
@@ -399,6 +408,9 @@ int dsv::decode_segments(DSVB_DEC *d, int nseg, DecSegment *segs, int out_on_dev
                     }
                     if (!d->eng) {
                         d->eng = new DecEngine(md, L);
+                        if (d->time_kernels >= 0) {
+                            d->eng->time_kernels = d->time_kernels != 0;
+                        }
                         d->eng->draw_mode = d->draw_info;
                         d->eng->set_out420(d->out420 != 0);
                     }

@@ -32,7 +32,7 @@ struct DSVB_ENC {
 
 struct DSVB_DEC {
     int lanes, device;
-    int draw_info = 0, out420 = 0;
+    int draw_info = 0, out420 = 0, time_kernels = -1; /* -1: the engine's default (DSV_KERNEL_TIMES) */
     dsv::DecEngine *eng;
     dsv::EngineStats carried; /* stats of engines replaced after a format change */
 };

@@ -92,6 +92,9 @@ DecEngine::DecEngine(const DSV_META &md, int lanes)
     const CodecGeom &g = g_;
     max_nblk_ = g.nblk;
     L_ = lanes;
+    if (const char *e = getenv("DSV_KERNEL_TIMES")) {
+        time_kernels = atoi(e) != 0;
+    }
     CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&st_copy_, cudaStreamNonBlocking));
     for (int q = 0; q < 2; q++) {
@@ -207,20 +210,22 @@ void DecEngine::collect(int parity)
     }
     CUDA_CHECK(cudaEventSynchronize(ev_end_[parity]));
     ktimes.collect(parity);
-    float ms = 0;
-    CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[parity][0], ev_[parity][1]));
-    stats.sbt_inv_ms += ms;
-    stats.sbt_inv_launches++;
-    unsigned long long bytes = 0;
-    for (int p = 0; p < 3; p++) {
-        bytes += (unsigned long long) g_.pw[p] * g_.ph[p] + 4ull * g_.cw[p] * g_.ch[p];
-    }
-    stats.sbt_inv_bytes += bytes * (unsigned) pd.pictures;
-    if (pd.p_pictures) {
-        CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[parity][2], ev_[parity][3]));
-        stats.bmc_ms += ms;
-        stats.bmc_launches++;
-        stats.bmc_bytes += 3ull * g_.frame_bytes * (unsigned) pd.p_pictures;
+    if (pd.timed) {
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[parity][0], ev_[parity][1]));
+        stats.sbt_inv_ms += ms;
+        stats.sbt_inv_launches++;
+        unsigned long long bytes = 0;
+        for (int p = 0; p < 3; p++) {
+            bytes += (unsigned long long) g_.pw[p] * g_.ph[p] + 4ull * g_.cw[p] * g_.ch[p];
+        }
+        stats.sbt_inv_bytes += bytes * (unsigned) pd.pictures;
+        if (pd.p_pictures) {
+            CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[parity][2], ev_[parity][3]));
+            stats.bmc_ms += ms;
+            stats.bmc_launches++;
+            stats.bmc_bytes += 3ull * g_.frame_bytes * (unsigned) pd.p_pictures;
+        }
     }
     stats.pictures += (unsigned) pd.pictures;
     pd.valid = false;
@@ -240,7 +245,8 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
     cudaStream_t st = st_;
     const int par = (int) (step_no_ & 1);
     collect(par);
-    KtActivate kt_on(&ktimes);
+    const bool timed = time_kernels;
+    KtActivate kt_on(timed ? &ktimes : nullptr);
     ktimes.open(par);
     StepArena &arena_ = this->arena_[par];
     uint8_t *const h_stab_ = this->h_stab_[par];
@@ -529,15 +535,15 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
     }
     hzdec_clean_launch(d_clean, n_clean, g_.tiles[0], st);
     hzdec_launch_jobs(d_hzj, dims, st);
-    sbt_inv_launch(d_sj, sdims, g_.lo_smem, st, ev_[0], ev_[1]);
-    if (n_p) {
+    sbt_inv_launch(d_sj, sdims, g_.lo_smem, st, timed ? ev_[0] : nullptr, timed ? ev_[1] : nullptr);
+    if (n_p && timed) {
         CUDA_CHECK(cudaEventRecord(ev_[2], st));
     }
     {
         const MotionGeom mg = {g_.w, g_.h, g_.hs, g_.vs, blk_w, blk_h, nbh, nbv, 0};
         bmc_launch(d_bmc, n_p, mg, st);
     }
-    if (n_p) {
+    if (n_p && timed) {
         CUDA_CHECK(cudaEventRecord(ev_[3], st));
     }
     extend_launch(d_ext, n_ext, g_.w, g_.h, st);
@@ -608,6 +614,7 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
     /* no wait here: the caller parses the next packets while this step runs (see collect()) */
     CUDA_CHECK(cudaEventRecord(ev_end_[par], st));
     pending_[par].valid = true;
+    pending_[par].timed = timed;
     pending_[par].pictures = n_sj / 3;
     pending_[par].p_pictures = n_p;
     for (int k = 0; k < n; k++) {

@@ -360,12 +360,16 @@ EncEngine::EncEngine(const DSV_META &md, int gop, int pyramid_levels, int lanes)
     inter_ = gop != DSV_GOP_INTRA;
     levels_ = pyramid_levels;
     L_ = lanes;
+    if (const char *e = getenv("DSV_KERNEL_TIMES")) {
+        time_kernels = atoi(e) != 0;
+    }
     CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     CUDA_CHECK(cudaStreamCreateWithFlags(&st_copy_, cudaStreamNonBlocking));
     for (auto &e : ev_) {
         CUDA_CHECK(cudaEventCreate(&e));
     }
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_search_, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_sizes_, cudaEventDisableTiming));
     for (auto &e : ev_pref_) {
         CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
@@ -499,6 +503,7 @@ EncEngine::~EncEngine()
     }
     ktimes.destroy();
     cudaEventDestroy(ev_search_);
+    cudaEventDestroy(ev_sizes_);
     for (auto &e : ev_pref_) {
         cudaEventDestroy(e);
     }
@@ -631,7 +636,8 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     cudaStream_t st = st_;
     const MotionGeom mg = {g.w, g.h, g.hs, g.vs, g.blk_w, g.blk_h, g.nbh, g.nbv, levels_};
     LaneMisc *h_misc = reinterpret_cast<LaneMisc *>(h_misc_), *d_misc = reinterpret_cast<LaneMisc *>(d_misc_);
-    KtActivate kt_on(&ktimes);
+    const bool timed = time_kernels;
+    KtActivate kt_on(timed ? &ktimes : nullptr);
     ktimes.open(0);
     arena_.reset();
 
@@ -783,9 +789,13 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
             }
         }
         copy1_launch(d_mv0_, h_mv0_, sizeof(DevMV) * (size_t) g.nblk * L_, st);
-        CUDA_CHECK(cudaEventRecord(ev_[5], st));
+        if (timed) {
+            CUDA_CHECK(cudaEventRecord(ev_[5], st));
+        }
         bmc_launch(d_bmc, n_search, mg, st);
-        CUDA_CHECK(cudaEventRecord(ev_[6], st));
+        if (timed) {
+            CUDA_CHECK(cudaEventRecord(ev_[6], st));
+        }
         stats.kernel_launches += 2;
     }
     if (inter_ && !code) {
@@ -811,9 +821,13 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
             CUDA_CHECK(cudaEventRecord(ev_search_, st));
         }
         if (n_search && !analyse) {
-            CUDA_CHECK(cudaEventRecord(ev_[5], st));
+            if (timed) {
+                CUDA_CHECK(cudaEventRecord(ev_[5], st));
+            }
             bmc_launch(d_bmc, n_search, mg, st);
-            CUDA_CHECK(cudaEventRecord(ev_[6], st));
+            if (timed) {
+                CUDA_CHECK(cudaEventRecord(ev_[6], st));
+            }
             stats.kernel_launches += 1;
         }
     }
@@ -962,18 +976,18 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     copy1_launch(d_stab_, h_stab_, (size_t) g.nblk * L_, st);
     copy1_launch(d_hf, h_frames_, sizeof(HzFrame) * (size_t) n, st);
     zero_launch(d_zero, n_zero, max_zero, st);
-    sbt_fwd_launch(d_sj, sdims, g.lo_smem, st, ev_[0], ev_[1]);
+    sbt_fwd_launch(d_sj, sdims, g.lo_smem, st, timed ? ev_[0] : nullptr, timed ? ev_[1] : nullptr);
     hzcc_enc_launch(d_hj, 3 * n, d_chunks_, n * g.total_chunks, d_hf, n, st, g.total_chunks, g.chunks[0], g.chunks[1]);
     stats.kernel_launches += 6;
     copy1_launch(h_frames_, d_hf, sizeof(HzFrame) * (size_t) n, st);
-    CUDA_CHECK(cudaEventRecord(ev_[4], st));
+    CUDA_CHECK(cudaEventRecord(ev_sizes_, st));
     if (n_ref) {
         /* closed loop: reconstruct exactly what the decoder will (dsv_encoder.c:525,662-674) */
-        sbt_inv_launch(d_sj, sdims, g.lo_smem, st, ev_[2], ev_[3]);
+        sbt_inv_launch(d_sj, sdims, g.lo_smem, st, timed ? ev_[2] : nullptr, timed ? ev_[3] : nullptr);
         extend_launch(d_ext, 3 * n_ref, g.w, g.h, st);
         stats.kernel_launches += 4;
     }
-    CUDA_CHECK(cudaEventSynchronize(ev_[4])); /* packet sizes are known; reconstruction keeps running */
+    CUDA_CHECK(cudaEventSynchronize(ev_sizes_)); /* packet sizes are known; reconstruction keeps running */
     CopyItem *pk = reinterpret_cast<CopyItem *>(h_pk_); /* mapped pinned: read by the copy kernel in place */
     int n_pk = 0;
     size_t max_pk = 0;
@@ -1049,7 +1063,8 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     copy_launch(pk, n_pk, max_pk, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
     ktimes.collect(0);
-    {
+    stats.pictures += (unsigned) n;
+    if (timed) {
         float ms = 0;
         CUDA_CHECK(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
         stats.sbt_fwd_ms += ms;
@@ -1072,7 +1087,6 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
             stats.bmc_launches++;
             stats.bmc_bytes += 4ull * g.frame_bytes * (unsigned) n_search;
         }
-        stats.pictures += (unsigned) n;
     }
     for (int k = 0; k < n; k++) {
         EncLane &l = lanes_[(size_t) lane_ids[k]];

@@ -257,6 +257,11 @@ public:
     const CodecGeom &geom() const { return g_; }
     EngineStats stats;
     KernelTimes ktimes; /* every launch of step(), by kernel name */
+    /* Live timing brackets every launch with two timing events, whose timestamps travel to host memory: cheap on an
+     * idle link, but a stream's next operation waits for them, and behind a saturated PCIe direction that adds
+     * ~40 us to EVERY launch (measured: device-resident encode 40 -> 81 ms next to an unrelated bulk D2H copy).
+     * Off unless asked for (dsvb_*_set_kernel_timing, DSV_KERNEL_TIMES=1). */
+    bool time_kernels = false;
     int device = 0;
 
 private:
@@ -269,6 +274,7 @@ private:
     cudaStream_t st_ = 0, st_copy_ = 0;
     cudaEvent_t ev_[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_search_ = nullptr; /* vectors and luma sums are on the host */
+    cudaEvent_t ev_sizes_ = nullptr;  /* packet sizes are on the host */
     cudaEvent_t ev_pref_[ENC_STAGE_SLOTS] = {}; /* per staging slot: prefetch copies done */
     std::vector<EncLane> lanes_;
     StepArena arena_;
@@ -331,6 +337,7 @@ public:
     bool matches(const DSV_META &md) const { return md.width == g_.w && md.height == g_.h && md.subsamp == g_.subsamp; }
     EngineStats stats;
     KernelTimes ktimes; /* every launch of step(), by kernel name; read one step late (collect) */
+    bool time_kernels = false; /* see EncEngine::time_kernels */
     int device = 0;
 
 private:
@@ -344,7 +351,7 @@ private:
     cudaEvent_t ev_[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
     cudaEvent_t ev_end_[2] = {nullptr, nullptr};
     struct Pending {
-        bool valid = false;
+        bool valid = false, timed = false;
         int pictures = 0, p_pictures = 0;
     } pending_[2];
     void collect(int parity);

@@ -111,6 +111,11 @@ int dsvb_multi_decode_long(DSVB_MULTI *m, const uint8_t *stream, long len, uint8
  * dsvb_kernel_count() names are registered so far (at most 64, in order of first launch); ms[i] / launches[i]
  * (arrays of at least 64 doubles) receive the accumulated device time and launch count of kernel i since the last
  * reset.  The decoder reads a step's events when the step has left the GPU (dsvb_decode returns after that). */
+/* Timing is OFF by default (or DSV_KERNEL_TIMES=1 in the environment): the two timing events per launch cost ~40 us
+ * per launch when a PCIe direction is saturated by picture traffic, because their timestamps go to host memory.
+ * The sbt / bmc entries of the stats block are filled only while timing is on. */
+void dsvb_enc_set_kernel_timing(DSVB_ENC *e, int on);
+void dsvb_dec_set_kernel_timing(DSVB_DEC *d, int on);
 int dsvb_kernel_count(void);
 const char *dsvb_kernel_name(int i);
 void dsvb_enc_kernel_times(DSVB_ENC *e, double *ms, double *launches, int reset);

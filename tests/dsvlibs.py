@@ -336,6 +336,9 @@ class BatchEncoder:
         self.lib.dsvb_enc_stats(self.h, st, int(reset))
         return dict(zip(STAT_KEYS, list(st)))
 
+    def set_kernel_timing(self, on):
+        self.lib.dsvb_enc_set_kernel_timing(self.h, int(on))
+
     def kernel_times(self, reset=False):
         """{kernel name: {ms, launches}} of every launch made by the engine's steps since the last reset"""
         return _kernel_times(self.lib, "dsvb_enc_kernel_times", self.h, reset)
@@ -431,6 +434,9 @@ class BatchDecoder:
                                        C.c_long(len(out)), 0, C.byref(fr))
         assert rc == 0, rc
         return out, fr.value
+
+    def set_kernel_timing(self, on):
+        self.lib.dsvb_dec_set_kernel_timing(self.h, int(on))
 
     def set_draw_info(self, mode):
         self.lib.dsvb_dec_set_draw_info(self.h, int(mode))

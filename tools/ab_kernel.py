@@ -15,7 +15,7 @@ for s in range(B):
 cap = 8 << 20
 h_streams = torch.zeros(B * cap, dtype=torch.uint8).pin_memory(); d_streams = torch.zeros(B * cap, dtype=torch.uint8, device="cuda")
 d_out = torch.empty(B * seq, dtype=torch.uint8, device="cuda")
-enc = L.BatchEncoder(gpu, cfg, B, 0); dec = L.BatchDecoder(gpu, B, 0)
+enc = L.BatchEncoder(gpu, cfg, B, 0); dec = L.BatchDecoder(gpu, B, 0); enc.set_kernel_timing(1); dec.set_kernel_timing(1)
 sp = [h_streams.data_ptr() + s * cap for s in range(B)]; sdp = [d_streams.data_ptr() + s * cap for s in range(B)]
 import time
 for it in range(4):

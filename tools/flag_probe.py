@@ -10,7 +10,7 @@ cfg = L.make_cfg(W, H, FMT, gop=12, qp=85)
 d = torch.empty(B * NFR * fb, dtype=torch.uint8, device="cuda")
 for s in range(B):
     lib.dsvb_synth_device(W, H, sub, 0, NFR, 100 + s, 0, C.c_void_p(d.data_ptr() + s * NFR * fb), 0)
-enc = L.BatchEncoder(gpu, cfg, B, 0); dec = L.BatchDecoder(gpu, B, 0)
+enc = L.BatchEncoder(gpu, cfg, B, 0); dec = L.BatchDecoder(gpu, B, 0); enc.set_kernel_timing(1); dec.set_kernel_timing(1)
 cap = 8 << 20
 out = torch.zeros(B * cap, dtype=torch.uint8).pin_memory()
 d_out = torch.empty(B * NFR * fb, dtype=torch.uint8, device="cuda")
