@@ -253,7 +253,8 @@ def kernel_models(L):
     sbt = sum(pw * ph for pw, ph in planes) + 4 * sum(cw * ch for cw, ch in coefs)
     coef4 = 4 * sum(cw * ch for cw, ch in coefs)
     return {
-        "sbt_fwd_tile_kernel": ("hbm", sbt), "sbt_inv_tile_kernel": ("hbm", sbt), "bmc_kernel": ("hbm", None),
+        "sbt_fwd_tile_kernel": ("hbm", sbt), "sbt_inv_tile_kernel": ("hbm", sbt), "sbt_inv_tile_intra_kernel": ("hbm", sbt),
+        "bmc_kernel": ("hbm", None), "hzdec_clean_kernel": ("hbm", None),
         "hzcc_scan_kernel": ("hbm", coef4), "hzcc_pack_kernel": ("hbm", coef4), "zero_kernel": ("hbm", None),
         "ingest_kernel": ("hbm", 2 * fb), "pack_kernel": ("hbm", 2 * fb), "down2_kernel": ("hbm", None),
         "hme_l0_kernel": ("issue", 2 * fb), "hme_level_kernel": ("issue", None), "hme_neigh_kernel": ("latency", None),
@@ -264,9 +265,20 @@ def kernel_table(L, B, steps, ms_dev, peak, es, ds, ekt, dkt):
     """every kernel that takes >= 1 % of the device-resident step: live CUDA-event time (events around each launch on
     the engine's stream), launches, share of the step, and for the streaming kernels algorithmic GB/s vs the measured peak"""
     models = kernel_models(L)
-    exact = {("enc", "sbt_fwd_tile_kernel"): es["sbt_fwd_bytes"], ("enc", "sbt_inv_tile_kernel"): es["sbt_inv_bytes"],
-             ("dec", "sbt_inv_tile_kernel"): ds["sbt_inv_bytes"], ("enc", "bmc_kernel"): es["bmc_bytes"], ("dec", "bmc_kernel"): ds["bmc_bytes"]}
+    sub = L.SUBSAMP[FMT]
+    fb = L.frame_bytes(W, H, sub)
+    sbt = models["sbt_fwd_tile_kernel"][1]
     pictures = B * NFR * steps
+    n_i = B * steps * (NFR if GOP == 0 else -(-NFR // GOP))  # no scene cuts in the bench content: I pictures = GOP starts
+    n_p = pictures - n_i
+    # the inverse transform of P pictures and of I pictures are separate kernels (different occupancy); the encoder's
+    # inverse of a P picture also reads the prediction it adds on the way out
+    exact = {("enc", "sbt_fwd_tile_kernel"): sbt * pictures,
+             ("enc", "sbt_inv_tile_kernel"): (sbt + fb) * n_p, ("dec", "sbt_inv_tile_kernel"): sbt * n_p,
+             ("enc", "sbt_inv_tile_intra_kernel"): sbt * n_i, ("dec", "sbt_inv_tile_intra_kernel"): sbt * n_i,
+             ("enc", "bmc_kernel"): es["bmc_bytes"], ("dec", "bmc_kernel"): ds["bmc_bytes"]}
+    if GOP == 0:  # intra-only: nothing is reconstructed in the encoder
+        exact[("enc", "sbt_inv_tile_intra_kernel")] = None
     out = {}
     for side, kt in (("enc", ekt), ("dec", dkt)):
         for name, v in kt.items():

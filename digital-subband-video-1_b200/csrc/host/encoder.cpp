@@ -901,7 +901,7 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     PlaneRef *ext = n_ref > 0 ? arena_.push_n<PlaneRef>((size_t) 3 * n_ref, &d_ext) : nullptr;
     int qi = 0;
     ZeroItem *d_zero;
-    ZeroItem *zero = arena_.push_n<ZeroItem>((size_t) n, &d_zero);
+    ZeroItem *zero = arena_.push_n<ZeroItem>((size_t) 2 * n, &d_zero);
     int n_zero = 0;
     size_t max_zero = 0;
     for (int k = 0; k < n; k++) {
@@ -911,6 +911,11 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         const DevFrame &fwd_in = isP ? l.xf : (inter_ ? l.pad[l.cur] : l.xf);
         /* P pictures: the inverse transform adds the prediction on its way out and writes the reconstruction */
         const DevFrame &inv_out = inter_ ? l.recon[l.cur] : l.xf;
+        /* tile flags (sbt.cuh): the forward transform ORs into zeroed bytes */
+        zero[n_zero].p = l.tflags;
+        zero[n_zero].bytes = ((size_t) g.total_tiles + 15) & ~(size_t) 15;
+        max_zero = max_zero > zero[n_zero].bytes ? max_zero : zero[n_zero].bytes;
+        n_zero++;
         if (l.pkt_dirty) {
             zero[n_zero].p = l.d_pkt;
             zero[n_zero].bytes = ((size_t) l.pkt_dirty + 64 + 15) & ~(size_t) 15;

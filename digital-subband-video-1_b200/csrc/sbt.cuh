@@ -97,7 +97,7 @@ size_t sbt_dv_elems(int cw, int ch);
 /* grid sizes of one launch over an array of jobs */
 struct SbtDims {
     int njobs = 0, tiles = 0, mtiles = 0;
-    bool any_intra = false;
+    bool any_intra = false, any_inter = false;
     /* uniform launches (the engines: planes Y,U,V of many pictures of one format): jobs come in groups of gsz
      * with identical tile counts per position, so tile -> job is arithmetic; gsz == 0: binary search */
     int gsz = 0, tg = 0, c0 = 0, c1 = 0, mtg = 0, mc0 = 0, mc1 = 0;

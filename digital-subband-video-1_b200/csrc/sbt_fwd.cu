@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_FWD_MINB) sbt_fwd_tile_k
             }
         }
     }
-    any1 = __syncthreads_or(any1);
+    __syncthreads();
 
     /* ---- level 2: a thread owns 2 adjacent quads (LL scaled by 4/5: I always, P for level > 1) ---- */
     {
@@ -412,13 +412,14 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_FWD_MINB) sbt_fwd_tile_k
             }
         }
     }
-    if (J.tflags) { /* uniform */
-        any2 = __syncthreads_or(any2);
-        if (tid == 0) {
-            J.tflags[t] = (uint8_t) ((any1 ? 1 : 0) | (any2 ? 2 : 0));
-#ifdef DSV_CPU_EMU
-            if (getenv("DSV_DEBUG_FLAGS")) fprintf(stderr, "fwd plane %d isP %d tile %d flags %d sh %d/%d\n", J.plane, J.isP, t, J.tflags[t], J.pq.sh_plain, J.pq.sh_hq);
-#endif
+    if (J.tflags) {
+        /* the flag bytes were zeroed before the launch: a warp that stored a non-zero coefficient ORs its bits in (one
+         * atomic per warp at most, none at all for the empty level-1 bands of a P picture) -- no block-wide barrier */
+        const unsigned m1 = __ballot_sync(0xffffffffu, any1 != 0), m2 = __ballot_sync(0xffffffffu, any2 != 0);
+        const unsigned bits = (m1 ? 1u : 0u) | (m2 ? 2u : 0u);
+        if (bits && (tid & 31) == 0) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(J.tflags + t);
+            atomicOr(reinterpret_cast<unsigned *>(a & ~(uintptr_t) 3), bits << (8 * (a & 3)));
         }
     }
 }

@@ -23,6 +23,7 @@ SbtDims sbt_assign_tiles(SbtJob *jobs, int n)
         jobs[i].mtile_base = d.mtiles;
         d.mtiles += jobs[i].mtiles_x * jobs[i].mtiles_y;
         d.any_intra |= !jobs[i].isP;
+        d.any_inter |= jobs[i].isP != 0;
     }
     /* uniform groups? */
     const int gsz = (n % 3 == 0) ? 3 : 1;

@@ -70,8 +70,10 @@ struct Win {
 #define INV_OFF4 (INV_OFF3 + 20 * 12)
 #define INV_OFF5 (INV_OFF4 + 12 * 8)
 #define INV_WIN_ELEMS (INV_OFF5 + 8 * 6)
-/* I frames: column-pass output of the inverse B4T, [64 rows][low 68 | high 68] */
-#define INV_VSTRIDE 136
+/* I frames: column-pass output of the inverse B4T, [64 rows][low 72 | high 72]: up to 66 window columns per half,
+ * shifted so that the tile's own 64 start at a multiple of 4 */
+#define INV_VHALF 72
+#define INV_VSTRIDE (2 * INV_VHALF)
 #define INV_I_EXTRA (SBT_TH * INV_VSTRIDE)
 
 static size_t inv_tile_smem(bool anyI)
@@ -640,18 +642,31 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS) sbt_inv_mid_kernel(const Sbt
 #define SBT_INV_MINB 6 /* CTAs per SM, measured per 32 HD pictures (decoder / encoder with fused prediction add):
                           6 -> 181 / 213 us, 8 -> 183 / 211, 5 -> 183 / 219, 4 -> 202 / 245 */
 #endif
-__global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_INV_MINB) sbt_inv_tile_kernel(const SbtJob *jobs, const SbtDims dims)
+#ifndef SBT_INV_MINB_I
+#define SBT_INV_MINB_I 4 /* tiles of I pictures (inverse B4T through a 37 KB column buffer): 64 registers instead of 40
+                            take the 64-lane launch from 934 to 652 us; the P path loses 20 % at that occupancy */
+#endif
+/* The body is compiled twice: INTRA = false with the P pictures' occupancy, true with the I pictures'.  A launch whose
+ * jobs are all of one kind (the usual lock-step case) runs one of them; a mixed launch runs both over the same grid and
+ * every CTA leaves at once when its tile belongs to the other kind. */
+template <bool INTRA> DSV_D void sbt_inv_tile_body(const SbtJob *jobs, const SbtDims &dims)
 {
     DSV_DYN_SMEM(int32_t, sm);
     __shared__ SbtJob J;
     __shared__ Win W[SBT_HI + 1];
     const int tid = threadIdx.x;
+    {
+        int tile;
+        if ((jobs[sbt_locate<false>(jobs, dims, (int) blockIdx.x, &tile)].isP == 0) != INTRA) {
+            return;
+        }
+    }
     const int t = inv_load_job<false>(&J, jobs, dims);
 
     const int ty = (int) fastdiv((unsigned) t, J.tiles_x_fd), tx = t - ty * J.tiles_x;
     const int gx0 = tx * SBT_TW, gy0 = ty * SBT_TH;
     const int cw = J.cw, ch = J.ch;
-    const bool isI = !J.isP;
+    constexpr bool isI = INTRA; /* checked against the job above */
     const bool filtered = J.plane == 0;
 
     int32_t *win1 = sm, *win2 = sm + INV_OFF2;
@@ -659,7 +674,7 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_INV_MINB) sbt_inv_tile_k
     __shared__ int s_f1, s_f2; /* tile flags (sbt.cuh): level-1 blocks of this tile, level-2 blocks of the tile and its halo */
     __shared__ int s_fast;
     if (tid == 0) {
-        s_fast = inv_tile_is_interior(J, tx, ty) ? 1 : 0;
+        s_fast = (!INTRA && inv_tile_is_interior(J, tx, ty)) ? 1 : 0;
         if (!s_fast) {
             inv_windows(J, W, 0, SBT_HI, gx0, gy0);
         }
@@ -677,7 +692,7 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_INV_MINB) sbt_inv_tile_k
         s_f2 = f2;
     }
     __syncthreads();
-    if (s_fast) {
+    if (!INTRA && s_fast) {
         if (filtered) {
             if (J.addp) {
                 inv_tile_fast_p<true, true>(J, tx, ty, s_f1, s_f2, sm, tid);
@@ -814,58 +829,83 @@ __global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_INV_MINB) sbt_inv_tile_k
         const Win w = W[1];
         const int ww = w.b - w.a;
         const int wo = cw >> 1, ho = ch >> 1;
-        int32_t *vbuf = ibase; /* [SBT_TH][INV_VSTRIDE]: low columns at 0.., high columns at 68.. */
+        int32_t *vbuf = ibase; /* [SBT_TH][INV_VSTRIDE]: low columns at voff.., high columns at INV_VHALF + voff.. */
         const int32_t *bLL = win1;
         const int rows = W[0].hb - W[0].ha; /* output rows of this tile (<= 64, even) */
         const int m_lo = gy0 >> 1, nm = rows >> 1;
-        /* tasks: (column in window) x (low | high) x (two halves of the row-pair range) */
-        const int half = (nm + 1) >> 1;
-        for (int task = tid; task < 4 * ww; task += SBT_TILE_THREADS) {
+        /* Column pass.  tasks: (column in window) x (low | high) x (runs of 4 row pairs).  A task first requests all
+         * the rows it needs (6 x 2 independent loads: one memory latency instead of one per row pair), then slides.
+         * vbuf keeps the tile's own columns 16-byte aligned: window column x sits at x + voff. */
+        const int voff = 4 - (tx * (SBT_TW / 2) - w.a);
+        constexpr int RUN = 4;
+        const int nrun = (nm + RUN - 1) / RUN;
+        for (int task = tid; task < 2 * ww * nrun; task += SBT_TILE_THREADS) {
             const int part = task / (2 * ww), c = task - part * 2 * ww;
             const bool hcol = c >= ww;
             const int x = hcol ? c - ww : c; /* window column */
             const int gx = w.a + x;          /* band column */
-            const int mA = m_lo + part * half, mB = imin(m_lo + nm, mA + half);
+            const int mA = m_lo + part * RUN, mB = imin(m_lo + nm, mA + RUN);
             if (mA >= mB) {
                 continue;
             }
-            auto ldL = [&](int m) -> int {
-                return hcol ? J.coef[(size_t) m * cw + wo + gx] : bLL[(m - w.ha) * ww + x];
-            };
-            auto ldH = [&](int m) -> int {
-                return J.coef[(size_t) (ho + m) * cw + (hcol ? wo : 0) + gx];
-            };
-            int Lp = ldL(imax(mA - 1, 0)), Hp = ldH(imax(mA - 1, 0));
-            int Lc = ldL(mA), Hc = ldH(mA);
-            int32_t *vcol = vbuf + (hcol ? 68 : 0) + x;
-            for (int m = mA; m < mB; m++) {
-                const int mn = imin(m + 1, ho - 1);
-                const int Ln = ldL(mn), Hn = ldH(mn);
-                const int ly = 2 * (m - m_lo);
-                vcol[ly * INV_VSTRIDE] = rnd_shift<3>(Lp + 3 * Lc + Hp - 3 * Hc);
-                vcol[(ly + 1) * INV_VSTRIDE] = rnd_shift<3>(3 * Lc + Ln + 3 * Hc - Hn);
-                Lp = Lc; Hp = Hc; Lc = Ln; Hc = Hn;
+            const int32_t *gL = J.coef + wo + gx, *gH = J.coef + (size_t) ho * cw + (hcol ? wo : 0) + gx;
+            const int32_t *sL = bLL + x - w.ha * ww;
+            int Lr[RUN + 2], Hr[RUN + 2];
+#pragma unroll
+            for (int i = 0; i < RUN + 2; i++) {
+                const int m = iclamp(mA - 1 + i, 0, ho - 1); /* L[-1] := L[0], L[n/2] := L[n/2-1] */
+                Lr[i] = hcol ? gL[(size_t) m * cw] : sL[m * ww];
+                Hr[i] = gH[(size_t) m * cw];
+            }
+            int32_t *vcol = vbuf + (hcol ? INV_VHALF : 0) + x + voff + 2 * (mA - m_lo) * INV_VSTRIDE;
+#pragma unroll
+            for (int i = 0; i < RUN; i++) {
+                if (mA + i < mB) {
+                    vcol[(2 * i) * INV_VSTRIDE] = rnd_shift<3>(Lr[i] + 3 * Lr[i + 1] + Hr[i] - 3 * Hr[i + 1]);
+                    vcol[(2 * i + 1) * INV_VSTRIDE] = rnd_shift<3>(3 * Lr[i + 1] + Lr[i + 2] + 3 * Hr[i + 1] - Hr[i + 2]);
+                }
             }
         }
         __syncthreads();
+        /* Row pass: the thread's four columns k0..k0+3 are one aligned 16-byte shared-memory load per band */
         for (int g = tid; g < (SBT_TW / 8) * SBT_TH; g += SBT_TILE_THREADS) {
             const int ly = g >> 4, k0l = (g & 15) * 4;
             const int k0 = tx * (SBT_TW / 2) + k0l; /* first of 4 band columns -> 8 samples */
             if (ly >= rows || k0 >= wo) {
                 continue;
             }
-            const int32_t *L = vbuf + ly * INV_VSTRIDE - w.a, *H = L + 68;
+            const int32_t *L = vbuf + ly * INV_VSTRIDE + voff - w.a, *H = L + INV_VHALF;
             int v[8];
+            if (k0 + 4 <= wo) {
+                const int4 l4 = *reinterpret_cast<const int4 *>(L + k0), h4 = *reinterpret_cast<const int4 *>(H + k0);
+                const int kp = imax(k0 - 1, 0), kn = imin(k0 + 4, wo - 1);
+                const int Lv[6] = {L[kp], l4.x, l4.y, l4.z, l4.w, L[kn]}, Hv[6] = {H[kp], h4.x, h4.y, h4.z, h4.w, H[kn]};
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int k = imin(k0 + i, wo - 1);
-                const int kp = imax(k - 1, 0), kn = imin(k + 1, wo - 1);
-                v[2 * i] = rnd_shift<3>(L[kp] + 3 * L[k] + H[kp] - 3 * H[k]);
-                v[2 * i + 1] = rnd_shift<3>(3 * L[k] + L[kn] + 3 * H[k] - H[kn]);
+                for (int i = 0; i < 4; i++) {
+                    v[2 * i] = rnd_shift<3>(Lv[i] + 3 * Lv[i + 1] + Hv[i] - 3 * Hv[i + 1]);
+                    v[2 * i + 1] = rnd_shift<3>(3 * Lv[i + 1] + Lv[i + 2] + 3 * Hv[i + 1] - Hv[i + 2]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int k = imin(k0 + i, wo - 1);
+                    const int kp = imax(k - 1, 0), kn = imin(k + 1, wo - 1);
+                    v[2 * i] = rnd_shift<3>(L[kp] + 3 * L[k] + H[kp] - 3 * H[k]);
+                    v[2 * i + 1] = rnd_shift<3>(3 * L[k] + L[kn] + 3 * H[k] - H[kn]);
+                }
             }
             store_row8(J, gy0 + ly, 2 * k0, v);
         }
     }
+}
+
+__global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_INV_MINB) sbt_inv_tile_kernel(const SbtJob *jobs, const SbtDims dims)
+{
+    sbt_inv_tile_body<false>(jobs, dims);
+}
+__global__ void __launch_bounds__(SBT_TILE_THREADS, SBT_INV_MINB_I) sbt_inv_tile_intra_kernel(const SbtJob *jobs, const SbtDims dims)
+{
+    sbt_inv_tile_body<true>(jobs, dims);
 }
 
 __global__ void __launch_bounds__(SBT_LO_THREADS) sbt_inv_lo_kernel(const SbtJob *jobs)
@@ -948,12 +988,12 @@ void sbt_inv_launch(const SbtJob *d_jobs, const SbtDims &dims, size_t lo_smem, c
     if (dims.njobs <= 0) {
         return;
     }
-    const size_t tile_smem = inv_tile_smem(dims.any_intra);
+    const size_t tile_smem = inv_tile_smem(false), tile_smem_i = inv_tile_smem(true);
     if (lo_smem > 48 * 1024) {
         CUDA_CHECK(cudaFuncSetAttribute(sbt_inv_lo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) lo_smem));
     }
-    if (tile_smem > 48 * 1024) {
-        CUDA_CHECK(cudaFuncSetAttribute(sbt_inv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tile_smem));
+    if (dims.any_intra) { /* static shared memory (job record, windows) counts against the 48 KB default too */
+        CUDA_CHECK(cudaFuncSetAttribute(sbt_inv_tile_intra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tile_smem_i));
     }
     DSV_LAUNCH(sbt_inv_lo_kernel, dim3(dims.njobs), dim3(SBT_LO_THREADS), lo_smem, st, d_jobs);
     KERNEL_CHECK();
@@ -962,8 +1002,14 @@ void sbt_inv_launch(const SbtJob *d_jobs, const SbtDims &dims, size_t lo_smem, c
     if (ev0) {
         CUDA_CHECK(cudaEventRecord(ev0, st));
     }
-    DSV_LAUNCH(sbt_inv_tile_kernel, dim3(dims.tiles), dim3(SBT_TILE_THREADS), tile_smem, st, d_jobs, dims);
-    KERNEL_CHECK();
+    if (dims.any_inter) {
+        DSV_LAUNCH(sbt_inv_tile_kernel, dim3(dims.tiles), dim3(SBT_TILE_THREADS), tile_smem, st, d_jobs, dims);
+        KERNEL_CHECK();
+    }
+    if (dims.any_intra) {
+        DSV_LAUNCH(sbt_inv_tile_intra_kernel, dim3(dims.tiles), dim3(SBT_TILE_THREADS), tile_smem_i, st, d_jobs, dims);
+        KERNEL_CHECK();
+    }
     if (ev1) {
         CUDA_CHECK(cudaEventRecord(ev1, st));
     }
