@@ -95,30 +95,39 @@ public:
             }
             return;
         }
+        unsigned long long ep;
         {
             std::lock_guard<std::mutex> lk(m_);
             fn_ = &f;
             n_ = n;
-            next_.store(0);
+            ep = ++epoch_;
             pending_.store(n);
-            epoch_++;
+            next_.store(ep << 32); /* published last: index 0 of this epoch */
         }
         cv_.notify_all();
-        drain();
+        drain(ep, n, &f);
         std::unique_lock<std::mutex> lk(m_);
         cv_done_.wait(lk, [this] { return pending_.load() == 0; });
         fn_ = nullptr;
     }
 
 private:
-    void drain()
+    /* Items are claimed by compare-and-swap on (epoch << 32 | next index): a worker that is still leaving the
+     * previous job when the next one is published cannot claim anything with its stale epoch, job size or function
+     * (it took all three together under the mutex), so no index runs twice and none is lost. */
+    void drain(unsigned long long ep, int n, const std::function<void(int)> *fn)
     {
         for (;;) {
-            const int i = next_.fetch_add(1);
-            if (i >= n_) {
-                return;
+            unsigned long long cur = next_.load();
+            for (;;) {
+                if ((cur >> 32) != ep || (int) (cur & 0xffffffffull) >= n) {
+                    return;
+                }
+                if (next_.compare_exchange_weak(cur, cur + 1)) {
+                    break;
+                }
             }
-            (*fn_)(i);
+            (*fn)((int) (cur & 0xffffffffull));
             if (pending_.fetch_sub(1) == 1) {
                 std::lock_guard<std::mutex> lk(m_);
                 cv_done_.notify_all();
@@ -129,6 +138,8 @@ private:
     {
         unsigned long long seen = 0;
         for (;;) {
+            int n;
+            const std::function<void(int)> *fn;
             {
                 std::unique_lock<std::mutex> lk(m_);
                 cv_.wait(lk, [&] { return quit_ || epoch_ != seen; });
@@ -136,8 +147,12 @@ private:
                     return;
                 }
                 seen = epoch_;
+                n = n_;
+                fn = fn_;
             }
-            drain();
+            if (fn) {
+                drain(seen, n, fn);
+            }
         }
     }
     std::vector<std::thread> th_;
@@ -145,7 +160,8 @@ private:
     std::condition_variable cv_, cv_done_;
     const std::function<void(int)> *fn_ = nullptr;
     int n_ = 0;
-    std::atomic<int> next_{0}, pending_{0};
+    std::atomic<unsigned long long> next_{0};
+    std::atomic<int> pending_{0};
     unsigned long long epoch_ = 0;
     bool quit_ = false;
 };

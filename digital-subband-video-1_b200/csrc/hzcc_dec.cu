@@ -527,52 +527,62 @@ __global__ void hzdec_dc_kernel(const HzDecJob *jobs, int njobs)
  * base value.  P pictures at qp85 touch no level-1 block at all: 3/4 of the plane is neither cleared nor, in the
  * inverse transform, read.  One CTA per tile and plane.
  */
+#define CLEAN_TPC 8 /* tiles per CTA: a P picture leaves ~8 KB to clear per tile, too little for a CTA of its own
+                        (one tile per CTA: 49 000 CTAs per 64 HD pictures, launch-rate bound at 70 us) */
 __global__ void __launch_bounds__(256) hzdec_clean_kernel(const HzCleanItem *items)
 {
+    __shared__ int s_f[CLEAN_TPC];
     const HzCleanItem &C = items[blockIdx.y];
-    const int t = (int) blockIdx.x;
-    if (t >= C.tiles_x * C.tiles_y) {
+    const int ntiles = C.tiles_x * C.tiles_y, t0 = (int) blockIdx.x * CLEAN_TPC;
+    if (t0 >= ntiles) {
         return;
     }
-    const int ty = t / C.tiles_x, tx = t - ty * C.tiles_x;
-    const int f = C.tflags[t];
-    __syncthreads(); /* every thread has the flag before thread 0 resets it */
-    /* rectangle q: 0 = the corner [0, x2) x [0, y2) in 32x16 shares, 1..3 = level-2 regions, 4..6 = level-1 regions */
-#pragma unroll 1
-    for (int q = 0; q < 7; q++) {
-        const int lvl = q < 4 ? 2 : 1;
-        if (q > 0 && !(f & lvl)) {
-            continue;
-        }
-        const int ls = 7 - lvl;                  /* log2 of the block width: 32 or 64 coefficients */
-        const int bw = 1 << ls, bh = 64 >> lvl;
-        const int rx = q == 0 ? 0 : C.rx[q - 1], ry = q == 0 ? 0 : C.ry[q - 1];
-        const int rw = q == 0 ? C.x2 : C.rw[q - 1], rh = q == 0 ? C.y2 : C.rh[q - 1];
-        const int xa = tx * bw, ya = ty * bh;
-        const int w = imin(bw, rw - xa), nrow = imin(bh, rh - ya);
-        if (w <= 0 || nrow <= 0) {
-            continue;
-        }
-        int32_t *base = C.coef + (size_t) (ry + ya) * C.cw + rx + xa;
-        if (((reinterpret_cast<uintptr_t>(base) | (uintptr_t) (C.cw * 4)) & 15) == 0 && (w & 3) == 0) {
-            const int vs = ls - 2; /* 16-byte stores per full row: 8 or 16 */
-            for (int i = (int) threadIdx.x; i < (nrow << vs); i += 256) {
-                const int yy = i >> vs, xx = (i & ((1 << vs) - 1)) * 4;
-                if (xx < w) {
-                    *reinterpret_cast<int4 *>(base + (size_t) yy * C.cw + xx) = make_int4(0, 0, 0, 0);
-                }
-            }
-        } else {
-            for (int i = (int) threadIdx.x; i < (nrow << ls); i += 256) {
-                const int yy = i >> ls, xx = i & (bw - 1);
-                if (xx < w) {
-                    base[(size_t) yy * C.cw + xx] = 0;
-                }
-            }
-        }
+    if (threadIdx.x < CLEAN_TPC) {
+        const int t = t0 + (int) threadIdx.x;
+        s_f[threadIdx.x] = t < ntiles ? C.tflags[t] : 0;
     }
-    if (threadIdx.x == 0) {
-        C.tflags[t] = (uint8_t) C.base;
+    __syncthreads(); /* every thread works from the copy: the flags themselves go back to the base value now */
+    if (threadIdx.x < CLEAN_TPC && t0 + (int) threadIdx.x < ntiles) {
+        C.tflags[t0 + threadIdx.x] = (uint8_t) C.base;
+    }
+#pragma unroll 1
+    for (int k = 0; k < CLEAN_TPC && t0 + k < ntiles; k++) {
+        const int t = t0 + k, f = s_f[k];
+        const int ty = t / C.tiles_x, tx = t - ty * C.tiles_x;
+        /* rectangle q: 0 = the corner [0, x2) x [0, y2) in 32x16 shares, 1..3 = level-2 regions, 4..6 = level-1 regions */
+#pragma unroll 1
+        for (int q = 0; q < 7; q++) {
+            const int lvl = q < 4 ? 2 : 1;
+            if (q > 0 && !(f & lvl)) {
+                continue;
+            }
+            const int ls = 7 - lvl;                  /* log2 of the block width: 32 or 64 coefficients */
+            const int bw = 1 << ls, bh = 64 >> lvl;
+            const int rx = q == 0 ? 0 : C.rx[q - 1], ry = q == 0 ? 0 : C.ry[q - 1];
+            const int rw = q == 0 ? C.x2 : C.rw[q - 1], rh = q == 0 ? C.y2 : C.rh[q - 1];
+            const int xa = tx * bw, ya = ty * bh;
+            const int w = imin(bw, rw - xa), nrow = imin(bh, rh - ya);
+            if (w <= 0 || nrow <= 0) {
+                continue;
+            }
+            int32_t *base = C.coef + (size_t) (ry + ya) * C.cw + rx + xa;
+            if (((reinterpret_cast<uintptr_t>(base) | (uintptr_t) (C.cw * 4)) & 15) == 0 && (w & 3) == 0) {
+                const int vs = ls - 2; /* 16-byte stores per full row: 8 or 16 */
+                for (int i = (int) threadIdx.x; i < (nrow << vs); i += 256) {
+                    const int yy = i >> vs, xx = (i & ((1 << vs) - 1)) * 4;
+                    if (xx < w) {
+                        *reinterpret_cast<int4 *>(base + (size_t) yy * C.cw + xx) = make_int4(0, 0, 0, 0);
+                    }
+                }
+            } else {
+                for (int i = (int) threadIdx.x; i < (nrow << ls); i += 256) {
+                    const int yy = i >> ls, xx = i & (bw - 1);
+                    if (xx < w) {
+                        base[(size_t) yy * C.cw + xx] = 0;
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -606,7 +616,7 @@ void hzdec_fill_clean(HzCleanItem *c, const HzJob &h, int tiles_y)
 void hzdec_clean_launch(const HzCleanItem *d_items, int n, int max_tiles, cudaStream_t st)
 {
     if (n > 0 && max_tiles > 0) {
-        DSV_LAUNCH(hzdec_clean_kernel, dim3((unsigned) max_tiles, (unsigned) n), dim3(256), 0, st, d_items);
+        DSV_LAUNCH(hzdec_clean_kernel, dim3((unsigned) ceil_div(max_tiles, CLEAN_TPC), (unsigned) n), dim3(256), 0, st, d_items);
         KERNEL_CHECK();
     }
 }

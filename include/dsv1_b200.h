@@ -314,7 +314,7 @@ typedef struct _DSV_IMAGE DSV_IMAGE; /* here: the decoder's device context */
 typedef struct {
     DSV_META vidmeta;
     DSV_IMAGE *ref;
-    int draw_info; /* accepted, ignored: debug overlay is out of scope */
+    int draw_info; /* DSV_DRAW_* bits: debug overlay painted on the returned P pictures (dsv_decoder.c:441-447) */
     int got_metadata;
 } DSV_DECODER;
 

@@ -78,19 +78,21 @@ def ptr(a, ty=u8p):
 class Lib:
     """Thin wrapper giving the flat API numpy-friendly signatures.  prefix is ref_/port_/dsvk_."""
 
-    def __init__(self, path, prefix, api_prefix=None):
+    def __init__(self, path, prefix, api_prefix=None, api_path=None):
         if not os.path.exists(path):
             raise FileNotFoundError(path)
         self.lib = C.CDLL(path)
+        # tools/api_harness.c (a caller of the drop-in API) lives in its own test-only library next to the product's
+        self.api_lib = C.CDLL(api_path) if api_path else self.lib
         self.p = prefix
         self.ap = api_prefix or prefix
         self.path = path
 
     def fn(self, name, api=False):
-        return getattr(self.lib, (self.ap if api else self.p) + name)
+        return getattr(self.api_lib if api else self.lib, (self.ap if api else self.p) + name)
 
     def has(self, name, api=False):
-        return hasattr(self.lib, (self.ap if api else self.p) + name)
+        return hasattr(self.api_lib if api else self.lib, (self.ap if api else self.p) + name)
 
     # -- SBT ---------------------------------------------------------------
     def fwd_sbt(self, pix, pw, ph, cw, ch, isP):
@@ -234,7 +236,10 @@ def port():
 def gpu():
     """The product.  No fallback: a missing/unloadable CUDA library is an error."""
     if "gpu" not in _cache:
-        _cache["gpu"] = Lib(GPU_SO, "dsvk_", api_prefix="dsvh_")
+        harness = os.path.join(os.path.dirname(GPU_SO), "libdsv1_b200_harness.so")
+        if os.environ.get("DSV1_B200_LIB"):  # an A/B build of the product: the harness library binds to the default one
+            harness = None
+        _cache["gpu"] = Lib(GPU_SO, "dsvk_", api_prefix="dsvh_", api_path=harness)
     return _cache["gpu"]
 
 
