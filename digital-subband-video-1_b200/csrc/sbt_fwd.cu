@@ -136,10 +136,17 @@ DSV_D int emit_quads(const SbtJob &J, const uint8_t *stab, int lvl, int wo, int 
     store_n(row1, hl, N, nvalid);
     store_n(row1 + wo, hh, N, nvalid);
     int any = 0;
+    if (nvalid == N) { /* the usual case: no per-quad predicate */
 #pragma unroll
-    for (int i = 0; i < N; i++) {
-        if (i < nvalid) {
+        for (int i = 0; i < N; i++) {
             any |= lh[i] | hl[i] | hh[i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            if (i < nvalid) {
+                any |= lh[i] | hl[i] | hh[i];
+            }
         }
     }
     return any;

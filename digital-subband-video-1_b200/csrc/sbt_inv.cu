@@ -328,8 +328,8 @@ template <bool ADDP> DSV_D void store8_fast(uint8_t *dst, const uint8_t *ap, con
     }
 }
 
-template <bool FILT, bool ADDP>
-DSV_D void inv_tile_fast_p(const SbtJob &J, int tx, int ty, int f1, int f2, int32_t *sm, int tid)
+template <bool FILT, bool ADDP, bool EMPTY1>
+DSV_D void inv_tile_fast_p(const SbtJob &J, int tx, int ty, int f2, int32_t *sm, int tid)
 {
     constexpr int H = FILT ? 1 : 0;
     const int cw = J.cw;
@@ -393,7 +393,7 @@ DSV_D void inv_tile_fast_p(const SbtJob &J, int tx, int ty, int f1, int f2, int3
         uint8_t *dst = J.opix + (size_t) (2 * jy) * J.ostride + 2 * jx;
         const uint8_t *ap = ADDP ? J.addp + (size_t) (2 * jy) * J.addstride + 2 * jx : nullptr;
         int LH[4] = {0, 0, 0, 0}, HL[4] = {0, 0, 0, 0}, HH[4] = {0, 0, 0, 0};
-        if (!f1) {
+        if (EMPTY1) {
             /* the tile's level-1 blocks are empty: nothing to load, and a warp whose LL neighbourhood is zero too
              * has a zero residual */
             int z = Lc[0] | Lc[1] | Lc[2] | Lc[3];
@@ -693,18 +693,16 @@ template <bool INTRA> DSV_D void sbt_inv_tile_body(const SbtJob *jobs, const Sbt
     }
     __syncthreads();
     if (!INTRA && s_fast) {
-        if (filtered) {
-            if (J.addp) {
-                inv_tile_fast_p<true, true>(J, tx, ty, s_f1, s_f2, sm, tid);
-            } else {
-                inv_tile_fast_p<true, false>(J, tx, ty, s_f1, s_f2, sm, tid);
-            }
-        } else {
-            if (J.addp) {
-                inv_tile_fast_p<false, true>(J, tx, ty, s_f1, s_f2, sm, tid);
-            } else {
-                inv_tile_fast_p<false, false>(J, tx, ty, s_f1, s_f2, sm, tid);
-            }
+        const int sel = (filtered ? 4 : 0) | (J.addp ? 2 : 0) | (s_f1 ? 0 : 1);
+        switch (sel) {
+            case 0: inv_tile_fast_p<false, false, false>(J, tx, ty, s_f2, sm, tid); break;
+            case 1: inv_tile_fast_p<false, false, true>(J, tx, ty, s_f2, sm, tid); break;
+            case 2: inv_tile_fast_p<false, true, false>(J, tx, ty, s_f2, sm, tid); break;
+            case 3: inv_tile_fast_p<false, true, true>(J, tx, ty, s_f2, sm, tid); break;
+            case 4: inv_tile_fast_p<true, false, false>(J, tx, ty, s_f2, sm, tid); break;
+            case 5: inv_tile_fast_p<true, false, true>(J, tx, ty, s_f2, sm, tid); break;
+            case 6: inv_tile_fast_p<true, true, false>(J, tx, ty, s_f2, sm, tid); break;
+            default: inv_tile_fast_p<true, true, true>(J, tx, ty, s_f2, sm, tid); break;
         }
         return;
     }
