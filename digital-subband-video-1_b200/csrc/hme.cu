@@ -301,7 +301,13 @@ DSV_D void warp_rect_moments(const uint8_t *p0, int stride, int cw, int ch, int 
     }
 }
 
+/* occupancy A/B at 64 lanes (round 2): no cap (80 registers, 6 CTAs of 4 warps per SM) 668 us; 8 CTAs / 64 registers
+ * 685 us; 10 CTAs / 48 registers 798 us; an explicit minimum of 1 CTA lets ptxas spend more registers: 807 us */
+#ifdef HME_L0_MINB
+__global__ void __launch_bounds__(HME_THREADS, HME_L0_MINB) hme_l0_kernel(const HmeArgs *args)
+#else
 __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args)
+#endif
 {
     const HmeArgs &A = args[blockIdx.z];
     __shared__ __align__(16) HmeL0Smem smem[HME_WARPS];
