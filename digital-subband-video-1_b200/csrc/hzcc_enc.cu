@@ -778,24 +778,52 @@ struct HzPackVisitor {
     }
     DSV_D void dense(const HzJob &J, int base, int total, int lane)
     {
+        /* one walk: the lane's non-zeros (offset inside its 64 positions, symbol) are kept in a small per-lane list
+         * (local memory, L1-resident) while the summary is formed; once the lane's bit offset is known the codes are
+         * emitted from the list -- no second pass over the coefficients, no second symbol derivation */
+        unsigned char off[HZW_ITEMS];
+        int sym[HZW_ITEMS];
+        HzSummary s;
+        s.cnt = 0;
+        s.first_pos = -1;
+        s.last_key = KEY_NONE;
+        s.bits = 0;
+        {
+            int pp = -1, ps = 0;
+            hz_walk(J, base, total, [&](int pos, int sy) {
+                if (pp >= 0) {
+                    s.bits += group_bits(pos, pp, ps);
+                } else {
+                    s.first_pos = pos;
+                }
+                off[s.cnt] = (unsigned char) (pos - base);
+                sym[s.cnt] = sy;
+                pp = pos;
+                ps = sy;
+                s.cnt++;
+            });
+            if (s.cnt) {
+                s.last_key = mk_key(pp, ps);
+            }
+        }
         int prev_pos, prev_sym;
         unsigned long long at;
-        const HzSummary s = hz_walk_summary(J, base, total);
         acc.place(s, lane, prev_pos, prev_sym, at);
         if (s.cnt == 0) {
             return;
         }
         HzBitWriter bw;
         bw.begin(words, at);
-        hz_walk(J, base, total, [&](int pos, int sym) {
+        for (int k = 0; k < s.cnt; k++) {
+            const int pos = base + off[k];
             const unsigned run = (unsigned) (pos - prev_pos - 1);
             bw.put(ueg_len(run), ueg_code(run));
             if (prev_pos >= 0) {
                 bw.put(neg_len(prev_sym), neg_code(prev_sym));
             }
             prev_pos = pos;
-            prev_sym = sym;
-        });
+            prev_sym = sym[k];
+        }
         bw.end();
     }
 };
