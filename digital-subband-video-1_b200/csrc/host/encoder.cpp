@@ -416,6 +416,7 @@ void EncEngine::alloc_lane(EncLane &l)
     CUDA_CHECK(cudaMalloc(&l.coef, g.coef_total * sizeof(int32_t)));
     CUDA_CHECK(cudaMalloc(&l.tflags, (size_t) g.total_tiles + 16));
     CUDA_CHECK(cudaMemset(l.tflags, 3, (size_t) g.total_tiles + 16));
+    CUDA_CHECK(cudaMalloc(&l.hz_dense, (size_t) g.total_chunks * HZ_DENSE_BYTES));
     for (int p = 0; p < 3; p++) {
         CUDA_CHECK(cudaMalloc(&l.llx[p], sbt_llx_elems(g.cw[p], g.ch[p]) * sizeof(int32_t)));
         CUDA_CHECK(cudaMalloc(&l.dv[p], sbt_dv_elems(g.cw[p], g.ch[p]) * sizeof(int32_t)));
@@ -456,6 +457,7 @@ void EncEngine::free_lane(EncLane &l)
 {
     cudaFree(l.coef);
     cudaFree(l.tflags);
+    cudaFree(l.hz_dense);
     for (int p = 0; p < 3; p++) {
         cudaFree(l.llx[p]);
         cudaFree(l.dv[p]);
@@ -956,6 +958,8 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
             h.dv = s.dv;
             h.tflags = s.tflags;
             h.tiles_x = ceil_div(g.cw[p], SBT_TW);
+            /* list scratch for the dense chunks of I pictures only: P pictures have a handful of them at most */
+            h.dense = isP ? nullptr : l.hz_dense + (size_t) ((p > 0 ? g.chunks[0] : 0) + (p > 1 ? g.chunks[1] : 0)) * HZ_DENSE_BYTES;
             h.stable = s.stable;
             h.chunk_base = k * g.total_chunks + (p > 0 ? g.chunks[0] : 0) + (p > 1 ? g.chunks[1] : 0);
             h.frame = k;
@@ -982,7 +986,7 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
     copy1_launch(d_hf, h_frames_, sizeof(HzFrame) * (size_t) n, st);
     zero_launch(d_zero, n_zero, max_zero, st);
     sbt_fwd_launch(d_sj, sdims, g.lo_smem, st, timed ? ev_[0] : nullptr, timed ? ev_[1] : nullptr);
-    hzcc_enc_launch(d_hj, 3 * n, d_chunks_, n * g.total_chunks, d_hf, n, st, g.total_chunks, g.chunks[0], g.chunks[1]);
+    hzcc_enc_launch(d_hj, 3 * n, d_chunks_, n * g.total_chunks, d_hf, n, st, g.total_chunks, g.chunks[0], g.chunks[1], n_p < n);
     stats.kernel_launches += 6;
     copy1_launch(h_frames_, d_hf, sizeof(HzFrame) * (size_t) n, st);
     CUDA_CHECK(cudaEventRecord(ev_sizes_, st));

@@ -179,6 +179,7 @@ struct EncLane {
     int2 *d_aux = nullptr;
     int32_t *coef = nullptr, *llx[3] = {nullptr, nullptr, nullptr}, *dv[3] = {nullptr, nullptr, nullptr};
     uint8_t *tflags = nullptr; /* tile flags of the three planes (sbt.cuh), g.total_tiles bytes */
+    uint8_t *hz_dense = nullptr; /* HZCC dense-chunk lists (hzcc.cuh), g.total_chunks * HZ_DENSE_BYTES */
     uint8_t *d_pkt = nullptr, *d_in[ENC_STAGE_SLOTS] = {};
     int in_sel = 0;                 /* staging buffer the next inline copy / prefetch writes */
     const uint8_t *stage_src[ENC_STAGE_SLOTS] = {}; /* host picture on its way into / held by each staging buffer */

@@ -32,6 +32,10 @@ struct HzJob {
     const uint8_t *stable;
     const uint8_t *tflags; /* optional tile flags of the plane (sbt.cuh): clear bits let the scan skip chunks unread */
     int tiles_x;
+    /* optional scratch, HZ_DENSE_BYTES per chunk of the plane: the scan pass leaves the non-zeros of a DENSE chunk
+     * (I pictures) there -- per lane: bit count, count, then (offset, symbol) lists, lane-interleaved -- so that the
+     * pack pass emits straight from the lists instead of walking the coefficients and re-deriving every symbol */
+    uint8_t *dense;
     int cw, ch;
     int plane, isP;
     int chunk_base, nchunks; /* this plane's chunks inside the launch-wide chunk arrays */
@@ -42,8 +46,15 @@ struct HzJob {
 };
 
 /* per-chunk summary produced by the scan pass */
+#define HZ_DENSE_BITS 0     /* unsigned bits[32] */
+#define HZ_DENSE_CNT 128    /* uint8 cnt[32] */
+#define HZ_DENSE_OFF 256    /* uint8 off[64][32] */
+#define HZ_DENSE_SYM 2304   /* int sym[64][32] */
+#define HZ_DENSE_BYTES (2304 + 64 * 32 * 4)
+
 struct HzChunk {
     int cnt;            /* non-zero symbols in the chunk */
+    int dense;          /* the chunk's lists are in the job's dense scratch */
     int first_pos;      /* scan position of the first / last non-zero, -1 if none */
     int last_pos;
     int last_sym;
@@ -78,7 +89,8 @@ struct HzMap {
 /* chunks_per_pic > 0 declares that regular layout: job 3k+p covers chunks [k * chunks_per_pic + offset_p, ...) with
  * chunks_y / chunks_u chunks in the first two planes */
 void hzcc_enc_launch(const HzJob *d_jobs, int njobs, HzChunk *d_chunks, int total_chunks,
-                     HzFrame *d_frames, int nframes, cudaStream_t st, int chunks_per_pic = 0, int chunks_y = 0, int chunks_u = 0);
+                     HzFrame *d_frames, int nframes, cudaStream_t st, int chunks_per_pic = 0, int chunks_y = 0, int chunks_u = 0,
+                     int any_dense = 0);
 
 /* ---- interleaved exp-Golomb code construction (bs.c:128-145) -------------------------------- */
 DSV_HD unsigned long long spread_bits(unsigned v)

@@ -461,8 +461,43 @@ struct HzScanAcc {
 };
 struct HzScanVisitor {
     HzScanAcc acc;
+    int saved = 0; /* the dense lists of this chunk were written to the job's scratch */
     DSV_D void round(const HzGroup &g, int lane) { acc.add(hz_group_summary(g), lane); }
-    DSV_D void dense(const HzJob &J, int base, int total, int lane) { acc.add(hz_walk_summary(J, base, total), lane); }
+    DSV_D void dense(const HzJob &J, int base, int total, int lane)
+    {
+        if (!J.dense) {
+            acc.add(hz_walk_summary(J, base, total), lane);
+            return;
+        }
+        uint8_t *sc = J.dense + (size_t) ((base - lane * HZW_ITEMS) / HZ_CHUNK) * HZ_DENSE_BYTES;
+        uint8_t *off = sc + HZ_DENSE_OFF + lane;
+        int *sym = reinterpret_cast<int *>(sc + HZ_DENSE_SYM) + lane;
+        HzSummary s;
+        s.cnt = 0;
+        s.first_pos = -1;
+        s.last_key = KEY_NONE;
+        s.bits = 0;
+        int pp = -1, ps = 0;
+        hz_walk(J, base, total, [&](int pos, int sy) {
+            if (pp >= 0) {
+                s.bits += group_bits(pos, pp, ps);
+            } else {
+                s.first_pos = pos;
+            }
+            off[s.cnt * 32] = (uint8_t) (pos - base);
+            sym[s.cnt * 32] = sy;
+            pp = pos;
+            ps = sy;
+            s.cnt++;
+        });
+        if (s.cnt) {
+            s.last_key = mk_key(pp, ps);
+        }
+        reinterpret_cast<unsigned *>(sc + HZ_DENSE_BITS)[lane] = s.bits;
+        sc[HZ_DENSE_CNT + lane] = (uint8_t) s.cnt;
+        saved = 1;
+        acc.add(s, lane);
+    }
 };
 
 /* Tile flags (sbt.cuh): a chunk that lies inside one level-1 or level-2 band whose tiles over the chunk's rows are all
@@ -513,6 +548,7 @@ __global__ void __launch_bounds__(HZ_THREADS) hzcc_scan_kernel(const HzJob *jobs
     if (lane == 0) {
         HzChunk c;
         c.cnt = (int) V.acc.cnt;
+        c.dense = V.saved;
         c.bits_inner = V.acc.bits;
         c.first_pos = V.acc.first;
         c.last_pos = key_pos(V.acc.carry);
@@ -751,6 +787,43 @@ struct HzPackAcc {
         carry = OpMaxS64::apply(carry, all);
     }
 };
+/* Pack pass of a dense chunk whose lists the scan pass saved (HzJob.dense): no coefficient is read.  A free function
+ * with its own accumulator, so that the sparse path's visitor never has its address taken. */
+DSV_D void hz_pack_from_lists(const HzJob &J, const HzChunk &C, unsigned *words, int cbase, int lane)
+{
+    HzPackAcc acc;
+    acc.carry = mk_key(C.prev_pos, C.prev_sym);
+    acc.off = C.bit_off;
+    const uint8_t *sc = J.dense + (size_t) (cbase / HZ_CHUNK) * HZ_DENSE_BYTES;
+    const uint8_t *off = sc + HZ_DENSE_OFF + lane;
+    const int *sym = reinterpret_cast<const int *>(sc + HZ_DENSE_SYM) + lane;
+    const int base = cbase + lane * HZW_ITEMS;
+    HzSummary s;
+    s.cnt = sc[HZ_DENSE_CNT + lane];
+    s.bits = reinterpret_cast<const unsigned *>(sc + HZ_DENSE_BITS)[lane];
+    s.first_pos = s.cnt ? base + off[0] : -1;
+    s.last_key = s.cnt ? mk_key(base + off[(s.cnt - 1) * 32], sym[(s.cnt - 1) * 32]) : KEY_NONE;
+    int prev_pos, prev_sym;
+    unsigned long long at;
+    acc.place(s, lane, prev_pos, prev_sym, at);
+    if (s.cnt == 0) {
+        return;
+    }
+    HzBitWriter bw;
+    bw.begin(words, at);
+    for (int k = 0; k < s.cnt; k++) {
+        const int pos = base + off[k * 32];
+        const unsigned run = (unsigned) (pos - prev_pos - 1);
+        bw.put(ueg_len(run), ueg_code(run));
+        if (prev_pos >= 0) {
+            bw.put(neg_len(prev_sym), neg_code(prev_sym));
+        }
+        prev_pos = pos;
+        prev_sym = sym[k * 32];
+    }
+    bw.end();
+}
+
 struct HzPackVisitor {
     HzPackAcc acc;
     unsigned *words;
@@ -828,6 +901,9 @@ struct HzPackVisitor {
     }
 };
 
+/* Dense chunks whose lists the scan pass saved (I pictures) are packed by hzcc_pack_dense_kernel: with that path
+ * inside, this kernel needs 64 registers instead of 40 and the sparse (P picture) path loses its occupancy
+ * (103 -> 137 us per 64 pictures). */
 __global__ void __launch_bounds__(HZ_THREADS) hzcc_pack_kernel(const HzJob *jobs, int njobs, const HzChunk *chunks,
                                                                const HzFrame *frames, int total_chunks, const HzMap map)
 {
@@ -844,6 +920,9 @@ __global__ void __launch_bounds__(HZ_THREADS) hzcc_pack_kernel(const HzJob *jobs
     if (frames[J.frame].overflow) {
         return; /* refused by the prefix pass: nothing of this picture is written */
     }
+    if (C.dense) {
+        return; /* hzcc_pack_dense_kernel's */
+    }
     HzPackVisitor V;
     V.acc.carry = mk_key(C.prev_pos, C.prev_sym);
     V.acc.off = C.bit_off;
@@ -851,8 +930,27 @@ __global__ void __launch_bounds__(HZ_THREADS) hzcc_pack_kernel(const HzJob *jobs
     hz_chunk_rounds(J, (chunk - J.chunk_base) * HZ_CHUNK, J.rg.base[HZ_NREG], lane, V);
 }
 
+__global__ void __launch_bounds__(HZ_THREADS) hzcc_pack_dense_kernel(const HzJob *jobs, int njobs, const HzChunk *chunks,
+                                                                     const HzFrame *frames, int total_chunks, const HzMap map)
+{
+    const int lane = threadIdx.x & 31;
+    const int chunk = (int) blockIdx.x * HZW_WARPS + (threadIdx.x >> 5);
+    if (chunk >= total_chunks) {
+        return;
+    }
+    const HzChunk C = chunks[chunk];
+    if (C.cnt == 0 || !C.dense) {
+        return;
+    }
+    const HzJob &J = jobs[hz_job_of_chunk(jobs, njobs, chunk, map)];
+    if (frames[J.frame].overflow) {
+        return;
+    }
+    hz_pack_from_lists(J, C, reinterpret_cast<unsigned *>(frames[J.frame].pkt), (chunk - J.chunk_base) * HZ_CHUNK, lane);
+}
+
 void hzcc_enc_launch(const HzJob *d_jobs, int njobs, HzChunk *d_chunks, int total_chunks,
-                     HzFrame *d_frames, int nframes, cudaStream_t st, int chunks_per_pic, int chunks_y, int chunks_u)
+                     HzFrame *d_frames, int nframes, cudaStream_t st, int chunks_per_pic, int chunks_y, int chunks_u, int any_dense)
 {
     HzMap map;
     map.per_pic = chunks_per_pic;
@@ -865,6 +963,10 @@ void hzcc_enc_launch(const HzJob *d_jobs, int njobs, HzChunk *d_chunks, int tota
     KERNEL_CHECK();
     DSV_LAUNCH(hzcc_pack_kernel, dim3(ceil_div(total_chunks, HZW_WARPS)), dim3(HZ_THREADS), 0, st, d_jobs, njobs, d_chunks, d_frames, total_chunks, map);
     KERNEL_CHECK();
+    if (any_dense) { /* some job has list scratch (HzJob.dense): its dense chunks were left to this kernel */
+        DSV_LAUNCH(hzcc_pack_dense_kernel, dim3(ceil_div(total_chunks, HZW_WARPS)), dim3(HZ_THREADS), 0, st, d_jobs, njobs, d_chunks, d_frames, total_chunks, map);
+        KERNEL_CHECK();
+    }
 }
 
 } // namespace dsv
