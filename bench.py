@@ -365,62 +365,72 @@ def run_product(args):
         split["dec_s"] += time.perf_counter() - t1   # pictures at their destination)
         return lens
 
-    # end-to-end arm: steps are software-pipelined two deep, the way a transcoding service runs: one host thread
-    # encodes step k+1 while a second one decodes step k (its streams sit in the other half of a double buffer), so
-    # pictures leave the GPU (D2H) while the next ones arrive (H2D) -- PCIe is full duplex, a strictly sequential
-    # encode-then-decode uses one direction at a time.  Same calls, same work, same bytes; every one of the K steps
-    # starts and completes inside the timed region (pipeline fill and drain included).
-    h_streams2 = torch.zeros(B * cap, dtype=torch.uint8).pin_memory() if args.e2e_pipeline else None
-    sp_alt = [h_streams2.data_ptr() + s * cap for s in range(B)] if args.e2e_pipeline else None
+    # end-to-end arm: software-pipelined the way a transcoding service runs.  In every tick one host thread encodes step t
+    # while a second one decodes step t-1, both started together and joined before the next tick, so pictures leave the GPU
+    # (D2H) while the next ones arrive (H2D) -- PCIe is full duplex, a strictly sequential encode-then-decode uses one
+    # direction at a time.  Same public calls, same work, same bytes; every one of the K steps starts and completes inside
+    # the timed region (pipeline fill and drain included).  (Free-running encoder / decoder threads coupled only through
+    # buffer availability measure the same on the same box: 11.73k / 11.81k against 11.59k / 11.83k pictures/s.)
+    # --e2e-parts P > 1 deals the step's sequences to P smaller engine pairs (shorter fill / drain, but smaller launches:
+    # measured slower).
+    P = max(1, min(args.e2e_parts, B)) if args.e2e_pipeline else 1
+    while B % P:
+        P -= 1
+    n_part = B // P
+    if args.e2e_pipeline and P > 1:
+        part_enc = [L.BatchEncoder(gpu, cfg, n_part, local) for _ in range(P)]
+        part_dec = [L.BatchDecoder(gpu, n_part, local) for _ in range(P)]
+    else:
+        part_enc, part_dec = [enc], [dec]
+    h_streams2 = torch.zeros(B * cap, dtype=torch.uint8).pin_memory() if (args.e2e_pipeline and P == 1) else None
+    sp_alt = [h_streams2.data_ptr() + s * cap for s in range(B)] if h_streams2 is not None else None
 
     def run_pipelined(steps):
         import threading
-        enc_done = [threading.Event() for _ in range(steps)]
-        dec_done = [threading.Event() for _ in range(steps)]
-        lens_k = [None] * steps
+        lens_all = [None] * B
         errs = []
+        ntask = steps * P  # task j = part j % P of step j // P
 
-        def fail(e):
-            errs.append(e)
-            for ev in enc_done + dec_done:
-                ev.set()
+        def seqs(j):
+            p = j % P
+            return range(p * n_part, (p + 1) * n_part)
 
-        def enc_worker():
+        def stream_ptrs(j):
+            # one part per buffer slice; with a single part the two halves of a double buffer alternate
+            base = sp if (P > 1 or (j % 2) == 0) else sp_alt
+            return [base[s] for s in seqs(j)]
+
+        def do_enc(j):
             try:
-                for k in range(steps):
-                    if k >= 2:
-                        dec_done[k - 2].wait()  # the stream buffers of step k-2 are free again
-                    if errs:
-                        return
-                    rc, ln = enc.encode_ptrs([h_yuv.data_ptr() + s * seq_bytes for s in range(B)], NFR, 0,
-                                             sp if k % 2 == 0 else sp_alt, caps)
-                    assert rc == 0, rc
-                    lens_k[k] = ln
-                    enc_done[k].set()
+                rc, ln = part_enc[j % P].encode_ptrs([h_yuv.data_ptr() + s * seq_bytes for s in seqs(j)], NFR, 0, stream_ptrs(j),
+                                                     [cap] * n_part)
+                assert rc == 0, rc
+                for s, v in zip(seqs(j), ln):
+                    lens_all[s] = v
             except BaseException as e:  # noqa: BLE001
-                fail(e)
+                errs.append(e)
 
-        def dec_worker():
+        def do_dec(j):
             try:
-                for k in range(steps):
-                    enc_done[k].wait()
-                    if errs:
-                        return
-                    rc, fr = dec.decode_ptrs(sp if k % 2 == 0 else sp_alt, None, lens_k[k],
-                                             [h_out.data_ptr() + s * seq_bytes for s in range(B)], [seq_bytes] * B, 0)
-                    assert rc == 0 and all(f == NFR for f in fr), (rc, fr)
-                    dec_done[k].set()
+                rc, fr = part_dec[j % P].decode_ptrs(stream_ptrs(j), None, [lens_all[s] for s in seqs(j)],
+                                                     [h_out.data_ptr() + s * seq_bytes for s in seqs(j)], [seq_bytes] * n_part, 0)
+                assert rc == 0 and all(f == NFR for f in fr), (rc, fr)
             except BaseException as e:  # noqa: BLE001
-                fail(e)
+                errs.append(e)
 
-        te, td = threading.Thread(target=enc_worker), threading.Thread(target=dec_worker)
-        te.start()
-        td.start()
-        te.join()
-        td.join()
-        if errs:
-            raise errs[0]
-        return lens_k[-1]
+        for t in range(ntask + 1):
+            th = []
+            if t < ntask:
+                th.append(threading.Thread(target=do_enc, args=(t,)))
+            if t >= 1:
+                th.append(threading.Thread(target=do_dec, args=(t - 1,)))
+            for x in th:
+                x.start()
+            for x in th:
+                x.join()
+            if errs:
+                raise errs[0]
+        return list(lens_all)
 
     def barrier():
         torch.cuda.synchronize()
@@ -434,7 +444,7 @@ def run_product(args):
         enc.set_kernel_timing(kernel_timing)
         dec.set_kernel_timing(kernel_timing)
         for _ in range(warmup):
-            lens = step(host)
+            lens = run_pipelined(1) if (host and args.e2e_pipeline) else step(host)  # warm the engines the timed region uses
         enc.stats(reset=True)
         dec.stats(reset=True)
         enc.kernel_times(reset=True)
@@ -529,8 +539,9 @@ def run_product(args):
                         "pcie_floor_ms": floor_ms,
                         "pcie_floor_note": "this step's pictures copied H2D and D2H at the same time from / to the same pinned "
                                            "buffers, nothing else running (max over ranks, all ranks copying at once)",
-                        "schedule": "steps pipelined two deep: decode of step k overlaps encode of step k+1 (two host threads, "
-                                    "double-buffered streams, full-duplex PCIe)" if args.e2e_pipeline
+                        "schedule": ("ticks: one host thread encodes step t while a second decodes step t-1 (started together, joined per "
+                                     "tick; %d engine pair(s) of %d lanes, double-buffered streams): full-duplex PCIe, pipeline fill and "
+                                     "drain inside the timed region" % (P, n_part)) if args.e2e_pipeline
                                     else "encode then decode, one step at a time"},
                 "gpu_launches": int(es["kernel_launches"] + ds["kernel_launches"]),
                 "roofline": roofline, "kernels": kern,
@@ -543,7 +554,7 @@ def run_product(args):
             # the reference codes a sample of the very sequences the timed steps just processed; its streams and
             # decoded pictures must equal the bytes the GPU produced for them in the last timed host-buffer step
             line["cpu_baseline"], kept = cpu_baseline_single(h_yuv.numpy(), seq_bytes)
-            last = h_streams2 if (args.e2e_pipeline and args.steps % 2 == 0) else h_streams
+            last = h_streams2 if (h_streams2 is not None and args.steps % 2 == 0) else h_streams
             hs_np, ho_np = last.numpy(), h_out.numpy()
             for s_i, (r_stream, r_dec) in enumerate(kept):
                 g_stream = bytes(hs_np[s_i * cap:s_i * cap + lens_h[s_i]])
@@ -556,8 +567,8 @@ def run_product(args):
                                 "what": "streams byte-for-byte and decoded pictures sample-for-sample equal to the unmodified reference "
                                         "for the first %d sequences of the last timed host-buffer step" % len(kept)}
         print(json.dumps(line))
-    enc.close()
-    dec.close()
+    for x in set(part_enc + part_dec + [enc, dec]):
+        x.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -571,6 +582,9 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="sequences per GPU per step (default: the config's)")
     ap.add_argument("--config", type=int, default=5, choices=sorted(CONFIGS), help="BASELINE.json configs index (5 = headline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-parts", type=int, default=1,
+                    help="e2e arm: engine pairs the step's sequences are dealt to (measured on one B200, 64 sequences: 1 -> 63 ms per "
+                         "step, 2 -> 69, 4 -> 82, 8 -> 109: small engines lose more than the shorter pipeline fill wins)")
     ap.add_argument("--no-e2e-pipeline", dest="e2e_pipeline", action="store_false",
                     help="e2e arm: strictly one step at a time instead of decode(k) overlapping encode(k+1)")
     args = ap.parse_args()
