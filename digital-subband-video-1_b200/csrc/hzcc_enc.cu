@@ -209,6 +209,9 @@ DSV_D unsigned group_bits(int pos, int prev_pos, int prev_sym)
 #define HZW_WARPS (HZ_THREADS / 32)
 #define HZW_STEPS (HZ_CHUNK / 128)
 #define HZW_ITEMS (HZ_CHUNK / 32)
+#ifndef HZW_BATCH
+#define HZW_BATCH 4 /* sweep loads in flight per lane */
+#endif
 #define HZW_DENSE 128 /* marked groups (of 512) from which a chunk is walked lane by lane (see hz_walk) */
 
 DSV_D int nth_set_bit(unsigned m, int n)
@@ -255,30 +258,42 @@ template <class Visitor> DSV_D void hz_chunk_rounds(const HzJob &J, int cbase, i
         if (pos < total) {
             hz_locate(rg, pos, c);
         }
+        /* HZW_BATCH loads are requested before the first of them is looked at: a chunk then waits for
+         * HZW_STEPS / HZW_BATCH memory latencies instead of one per step */
 #pragma unroll
-        for (int k = 0; k < HZW_STEPS; k++) {
-            bool mark = false;
-            if (pos < total) {
-                mark = true;
-                const int32_t *p;
-                if (pos + 4 <= total && hz_group_plain(J, c, &p)) {
-                    const int4 v = *reinterpret_cast<const int4 *>(p);
-                    mark = (v.x | v.y | v.z | v.w) != 0;
-                }
-                /* 128 positions on */
-                pos += 128;
+        for (int kb = 0; kb < HZW_STEPS; kb += HZW_BATCH) {
+            int4 v[HZW_BATCH];
+            int st[HZW_BATCH]; /* 0: past the end, 1: has to be looked at, 2: loaded */
+#pragma unroll
+            for (int i = 0; i < HZW_BATCH; i++) {
+                st[i] = 0;
+                v[i] = make_int4(0, 0, 0, 0);
                 if (pos < total) {
-                    c.x += 128;
-                    while (c.x >= rg.sw[c.r]) {
-                        c.x -= rg.sw[c.r];
-                        if (++c.y == rg.sh[c.r]) {
-                            c.y = 0;
-                            c.r++;
+                    st[i] = 1;
+                    const int32_t *p;
+                    if (pos + 4 <= total && hz_group_plain(J, c, &p)) {
+                        v[i] = *reinterpret_cast<const int4 *>(p);
+                        st[i] = 2;
+                    }
+                    /* 128 positions on */
+                    pos += 128;
+                    if (pos < total) {
+                        c.x += 128;
+                        while (c.x >= rg.sw[c.r]) {
+                            c.x -= rg.sw[c.r];
+                            if (++c.y == rg.sh[c.r]) {
+                                c.y = 0;
+                                c.r++;
+                            }
                         }
                     }
                 }
             }
-            marks[k] = __ballot_sync(0xffffffffu, mark);
+#pragma unroll
+            for (int i = 0; i < HZW_BATCH; i++) {
+                const bool mark = st[i] == 1 || (st[i] == 2 && (v[i].x | v[i].y | v[i].z | v[i].w) != 0);
+                marks[kb + i] = __ballot_sync(0xffffffffu, mark);
+            }
         }
     }
     int G = 0;
