@@ -335,6 +335,28 @@ DSV_D void inv_tile_fast_p(const SbtJob &J, int tx, int ty, int f2, int32_t *sm,
     const int cw = J.cw;
     const int wo1 = cw >> 1, ho1 = J.ch >> 1, wo2 = sbt_wo(cw, 2), ho2 = sbt_wo(J.ch, 2);
     int32_t *win1 = sm, *win2 = sm + FW1 * FH1;
+    /* level 2 works on 34 x 18 pairs (the tile's 32 x 16 and the ring level 1 looks at), one pair per thread and
+     * round.  The band coefficients of all of a thread's pairs are requested before anything else: their latency
+     * overlaps the LL_2 window fetch and the barrier behind it. */
+    constexpr int NPX = 32 + 2 * H, NPY = 16 + 2 * H;
+    constexpr int NIT = (NPX * NPY + SBT_TILE_THREADS - 1) / SBT_TILE_THREADS;
+    int cLH[NIT], cHL[NIT], cHH[NIT];
+    {
+        const int32_t *bLH = J.coef + (size_t) (ty * 16 - H) * cw + wo2 + tx * 32 - H;
+        const int32_t *bHL = J.coef + (size_t) (ho2 + ty * 16 - H) * cw + tx * 32 - H;
+#pragma unroll
+        for (int it = 0; it < NIT; it++) {
+            const int p = tid + it * SBT_TILE_THREADS;
+            cLH[it] = cHL[it] = cHH[it] = 0;
+            if (f2 && p < NPX * NPY) {
+                const int py = p / NPX, px = p - py * NPX;
+                const size_t o = (size_t) py * cw + px;
+                cLH[it] = bLH[o];
+                cHL[it] = bHL[o];
+                cHH[it] = bHL[o + wo2];
+            }
+        }
+    }
     {
         const int32_t *ll2 = J.llx + J.ll2_off + (size_t) (ty * 16 - 2 * H) * wo2 + tx * 32 - 2 * H;
         constexpr int W2 = 32 + 4 * H, H2 = 16 + 4 * H;
@@ -345,22 +367,18 @@ DSV_D void inv_tile_fast_p(const SbtJob &J, int tx, int ty, int f2, int32_t *sm,
     }
     __syncthreads();
     {
-        /* level 2: one pair per thread, 34 x 18 pairs (the tile's 32 x 16 and the ring level 1 looks at) */
-        constexpr int NPX = 32 + 2 * H, NPY = 16 + 2 * H;
         const int bound = J.hqp[2];
-        const int32_t *bLH = J.coef + (size_t) (ty * 16 - H) * cw + wo2 + tx * 32 - H;
-        const int32_t *bHL = J.coef + (size_t) (ho2 + ty * 16 - H) * cw + tx * 32 - H;
-        for (int p = tid; p < NPX * NPY; p += SBT_TILE_THREADS) {
+#pragma unroll
+        for (int it = 0; it < NIT; it++) {
+            const int p = tid + it * SBT_TILE_THREADS;
+            if (p >= NPX * NPY) {
+                break;
+            }
             const int py = p / NPX, px = p - py * NPX;
             const int32_t *pc = win2 + (py + H) * FW2 + px + H;
             const int LL = pc[0];
-            int LH = 0, HL = 0, HH = 0;
-            if (f2) {
-                const size_t o = (size_t) py * cw + px;
-                LH = bLH[o];
-                HL = bHL[o];
-                HH = bHL[o + wo2];
-            }
+            int LH = cLH[it], HL = cHL[it];
+            const int HH = cHH[it];
             if (FILT) {
                 LH = smooth_nudge_d(pc[-1] - LL, LL - pc[1], LH, bound);
                 HL = smooth_nudge_d(pc[-FW2] - LL, LL - pc[FW2], HL, bound);
