@@ -255,7 +255,9 @@ def kernel_models(L):
     return {
         "sbt_fwd_tile_kernel": ("hbm", sbt), "sbt_inv_tile_kernel": ("hbm", sbt), "sbt_inv_tile_intra_kernel": ("hbm", sbt),
         "bmc_kernel": ("hbm", None), "hzdec_clean_kernel": ("hbm", None),
-        "hzcc_scan_kernel": ("hbm", coef4), "hzcc_pack_kernel": ("hbm", coef4), "zero_kernel": ("hbm", None),
+        # the pack passes read the chunks that hold something (sparse) or the scan pass's lists (dense): no per-picture byte model
+        "hzcc_scan_kernel": ("hbm", coef4), "hzcc_pack_kernel": ("latency", None), "hzcc_pack_dense_kernel": ("issue", None),
+        "zero_kernel": ("hbm", None),
         "ingest_kernel": ("hbm", 2 * fb), "pack_kernel": ("hbm", 2 * fb), "down2_kernel": ("hbm", None),
         "hme_l0_kernel": ("issue", 2 * fb), "hme_level_kernel": ("issue", None), "hme_neigh_kernel": ("latency", None),
     }

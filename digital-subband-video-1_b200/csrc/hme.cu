@@ -27,6 +27,14 @@ namespace dsv {
 #define HME_WARPS 4 /* blocks per CTA: one warp each, no block-wide barrier anywhere */
 #define HME_THREADS (32 * HME_WARPS)
 #define HME_SRC_STRIDE 64 /* bytes per staged block row */
+#ifndef HME_UR_CAND
+#define HME_UR_CAND 8 /* reference rows requested ahead in the candidate SAD loops */
+#endif
+#ifndef HME_UR_9PT
+#define HME_UR_9PT 4 /* A/B at 64 lanes: (8, 4) 668 us, (4, 2) 678, (8, 8) 676, (1, 1) 807 */
+#endif
+#define HME_PRAGMA(x) _Pragma(#x)
+#define HME_UNROLL(n) HME_PRAGMA(unroll n)
 #define HP_SAD_SZ 14
 #define HP_DIM 16
 #define HP_STRIDE 32
@@ -155,6 +163,7 @@ DSV_D void search_block(const HmeArgs &A, int i, int j, const BlockGeom &G, HmeS
                 const int dx = S.cx[k] >> level, dy = S.cy[k] >> level;
                 const uint8_t *p = A.ref.p + (ptrdiff_t) (G.by + dy + G.r0) * rs + G.bx + dx + 4 * G.wx;
                 unsigned t = 0;
+                HME_UNROLL(HME_UR_CAND)
                 for (int r = G.r0; r < G.r1; r++, p += rs) {
                     t += __vsadu4(*reinterpret_cast<const unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * G.wx), ld4u(p) & G.m);
                 }
@@ -186,6 +195,7 @@ DSV_D void search_block(const HmeArgs &A, int i, int j, const BlockGeom &G, HmeS
         const int qs = rs >> 2;
         const uint8_t *sp = s_src + 4 * G.wx;
         unsigned s_prev = 0, s_cur = 0, s_next = *reinterpret_cast<const unsigned *>(sp + G.r0 * HME_SRC_STRIDE);
+        HME_UNROLL(HME_UR_9PT)
         for (int t = G.r0 - 1; t <= G.r1; t++, q += qs) {
             s_prev = s_cur;
             s_cur = s_next;
