@@ -103,3 +103,33 @@ def test_batch_contiguous_host_buffers(gpu):
     for s in range(nseq):
         nf, d, _, _ = gpu.decode_stream(want[s], w, h, sub, n)
         assert np.array_equal(d, dec_all[s * n * fb:(s + 1) * n * fb])
+
+
+def test_tile_flags_follow_the_quantiser(gpu):
+    """Tile band flags (sbt.cuh): one byte per 128x64 tile, bit 0 = the tile's level-1 band blocks hold a non-zero
+    coefficient, bit 1 = its level-2 blocks do.  At qp85 the level-1 quantiser step of a P picture (2^10, 2^9 in stable
+    blocks) exceeds most level-1 coefficients of a residual (|LH| <= 4 * 255): the flags say so and the inverse
+    transform, the HZCC scan and the decoder's clean-up skip those blocks; an I picture is dense at every level.  The
+    streams are the reference's either way (checked by every other test in this file)."""
+    w, h, fmt = 640, 384, "420"
+    sub = L.SUBSAMP[fmt]
+    fb = L.frame_bytes(w, h, sub)
+    yuv = L.synth_sequence(w, h, fmt, 3, 21, 0)
+    ntiles = (w // 128) * (h // 64) + 2 * ((w // 2 + 127) // 128) * ((h // 2 + 63) // 64)
+    buf = np.zeros(4096, dtype=np.uint8)
+
+    def flags_after(qp, nframes):
+        be = L.BatchEncoder(gpu, L.make_cfg(w, h, fmt, gop=12, qp=qp), 1)
+        be.encode([yuv[:fb * nframes]], nframes)
+        n = gpu.lib.dsvb_enc_tile_flags(be.h, 0, C.c_void_p(buf.ctypes.data), len(buf))
+        be.close()
+        assert n == ntiles
+        return buf[:n].copy()
+
+    f_i = flags_after(85, 1)
+    assert (f_i & 1).all() and (f_i & 2).all()          # I picture: every level-1 block flagged, level 2 dense as well
+    f_p = flags_after(85, 3)
+    luma = f_p[:(w // 128) * (h // 64)]
+    assert (luma & 1).sum() <= len(luma) // 4            # P picture at qp85: (nearly) no level-1 block holds anything
+    f_hq = flags_after(100, 3)
+    assert (f_hq & 1).sum() > (f_p & 1).sum()            # a finer quantiser keeps level-1 coefficients alive
