@@ -319,7 +319,6 @@ __global__ void __launch_bounds__(HZD_THREADS) hzdec_token_kernel(const HzDecJob
     long long next_tok = at_start ? tok : tok + 1;
     const long long last_tok = (long long) J.ntok - 1;
 
-    unsigned long long pos = pos0;
     const unsigned long long end = pos0 + HZD_WORD_BITS;
     /* a well-formed token (32-bit value) is at most 66 bits long; anything longer is corrupt data, and letting
      * every thread chase a never-ending token to the end of the packet would be quadratic work */
@@ -327,53 +326,72 @@ __global__ void __launch_bounds__(HZD_THREADS) hzdec_token_kernel(const HzDecJob
     if (hard_end > end + 160ull) {
         hard_end = end + 160ull;
     }
-    bool own = false;       /* currently inside a token this thread owns */
+    const int limit = hard_end > pos0 ? (int) (hard_end - pos0) : 0; /* <= 192 bits from the start of our word */
+    /* the 64 bits behind our word are the neighbours' words: a token that runs past the word end is finished out of
+     * registers (the last two lanes of a warp fetch theirs), only corrupt data goes further and reads bit by bit */
+    const int lane = (int) threadIdx.x & 31;
+    unsigned hi = w, mid = __shfl_down_sync(0xffffffffu, w, 1), lo = __shfl_down_sync(0xffffffffu, w, 2);
+    if (lane == 31) {
+        mid = body_word(J, pos0 + 32);
+    }
+    if (lane >= 30) {
+        lo = body_word(J, pos0 + 64);
+    }
+    /* next state for (state, bit), 3 bits each: R0/RF: 0 -> RD, 1 -> V0; RD -> RF; V0/VF: 0 -> VD, 1 -> VS; VD -> VF; VS -> R0 */
+    const unsigned long long tbl = 2ull | (3ull << 3) | (2ull << 6) | (3ull << 9) | (1ull << 12) | (1ull << 15) | (5ull << 18) |
+                                   (6ull << 21) | (5ull << 24) | (6ull << 27) | (4ull << 30) | (4ull << 33);
+    int next_i = (int) next_tok;
+    const int last_i = (int) last_tok;
+    bool own = false; /* currently inside a token this thread owns */
     unsigned v = 1;
-    unsigned dummy = 0;
-    while (pos < hard_end) {
+    int i = 0; /* bits consumed from pos0 */
+    while (i < limit) {
         const bool starting = (state == S_R0 || state == S_V0);
         if (starting) {
-            if (pos >= end || next_tok > last_tok) {
+            if (i >= HZD_WORD_BITS || next_i > last_i) {
                 break; /* tokens starting beyond our word belong to the next thread */
             }
             own = true;
             v = 1;
-            if (next_tok == last_tok) {
+            if (next_i == last_i) {
                 state = S_V0; /* the final token is V(n-1) even though an R is due (hzcc.c:283-285) */
             }
         }
-        if (!own && pos >= end) {
+        if (!own && i >= HZD_WORD_BITS) {
             break;
         }
-        const unsigned bit = (pos >= pos0 && pos < end) ? ((w >> (31 - (unsigned) (pos - pos0))) & 1u) : body_bit(J, pos);
+        unsigned bit;
+        if (i < 96) {
+            bit = hi >> 31;
+            hi = (hi << 1) | (mid >> 31);
+            mid = (mid << 1) | (lo >> 31);
+            lo <<= 1;
+        } else {
+            bit = body_bit(J, pos0 + (unsigned long long) i);
+        }
         const int prev = state;
-        state = fsm_step(state, (int) bit, dummy);
-        pos++;
+        state = (int) ((tbl >> (3 * (2 * prev + (int) bit))) & 7ull);
+        i++;
         if (own) {
             if (prev == S_RD || prev == S_VD) {
                 v = (v << 1) | bit;
-            } else if ((prev == S_R0 || prev == S_RF) && bit) {
-                /* R token complete: token index j = next_tok -> R_{j/2+1} */
-                long long k = (next_tok >> 1) + 1;
-                if (k < J.cap) {
-                    J.runs[k] = (int32_t) (v - 1u);
-                }
-                own = false;
-                next_tok++;
-            } else if (prev == S_VS) {
-                long long k = next_tok >> 1; /* V_k: token 2k+1, or the final token 2n-2 */
-                int val = (int) v; /* UEG + 1 (bs.c:214) */
-                if (val && bit) {
+            }
+            const bool r_end = (prev == S_R0 || prev == S_RF) && bit; /* token j = next_i -> R_{j/2+1} */
+            const bool v_end = prev == S_VS;                          /* V_k: token 2k+1, or the final token 2n-2 */
+            if (r_end || v_end) {
+                const int k = (next_i >> 1) + (r_end ? 1 : 0);
+                int val = r_end ? (int) (v - 1u) : (int) v; /* UEG, UEG + 1 (bs.c:214) */
+                if (v_end && val && bit) {
                     val = -val;
                 }
                 if (k < J.cap) {
-                    J.vals[k] = val;
+                    (r_end ? J.runs : J.vals)[k] = val;
                 }
-                if ((pos >> 3) >= (unsigned long long) J.plen) { /* byte pointer after the read (hzcc.c:337) */
-                    atomicMin(J.first_bad, (unsigned) (k < 0x7fffffff ? k : 0x7fffffff));
+                if (v_end && ((pos0 + (unsigned long long) i) >> 3) >= (unsigned long long) J.plen) { /* byte pointer after the read (hzcc.c:337) */
+                    atomicMin(J.first_bad, (unsigned) k);
                 }
                 own = false;
-                next_tok++;
+                next_i++;
             }
         }
     }
