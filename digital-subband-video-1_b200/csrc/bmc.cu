@@ -38,8 +38,12 @@ namespace dsv {
 #define BMC_THREADS 256
 #endif
 #define BMC_W 8   /* samples per strip row */
+#ifndef BMC_RL
 #define BMC_RL 24 /* luma rows per strip */
+#endif
+#ifndef BMC_RC
 #define BMC_RC 24 /* chroma rows per strip */
+#endif
 #ifndef BMC_D
 #define BMC_D 6   /* rows in flight per thread (cp.async ring depth); a multiple of 3 */
 #endif

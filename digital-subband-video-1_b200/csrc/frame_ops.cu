@@ -92,15 +92,42 @@ static dim3 fo_grid(int max_w, int max_h, int n, bool bordered)
 
 DSV_D bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+#ifndef ING_RY
+#define ING_RY 4 /* rows per thread in ingest_kernel: their 16-byte loads are all requested before the first store */
+#endif
 __global__ void __launch_bounds__(FO_BX *FO_BY) ingest_kernel(const IngestItem *items)
 {
     const IngestItem it = items[blockIdx.z];
     const PlaneRef D = it.dst;
-    FO_FOREACH_ROW()
-    {
-        const int x0 = ck * 16 - DSV_BORDER, y = row - DSV_BORDER;
-        if (x0 >= D.w + DSV_BORDER || y >= D.h + DSV_BORDER) {
-            continue;
+    const int ck = (int) (blockIdx.x * FO_BX + threadIdx.x);
+    const int x0 = ck * 16 - DSV_BORDER;
+    if (x0 >= D.w + DSV_BORDER) {
+        return;
+    }
+    const int row0 = (int) (blockIdx.y * FO_BY * ING_RY + threadIdx.y);
+    const bool fast_x = x0 >= 0 && x0 + 16 <= D.w && ((D.w | x0) & 15) == 0 && aligned16(it.src);
+    if (fast_x) { /* interior chunk of a plane whose rows keep the alignment: ING_RY independent loads, then the stores */
+        uint4 v[ING_RY];
+#pragma unroll
+        for (int i = 0; i < ING_RY; i++) {
+            const int y = row0 + i * FO_BY - DSV_BORDER;
+            if (y < D.h + DSV_BORDER) {
+                v[i] = *reinterpret_cast<const uint4 *>(it.src + (size_t) iclamp(y, 0, D.h - 1) * D.w + x0);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < ING_RY; i++) {
+            const int y = row0 + i * FO_BY - DSV_BORDER;
+            if (y < D.h + DSV_BORDER) {
+                *reinterpret_cast<uint4 *>(D.p + (ptrdiff_t) y * D.stride + x0) = v[i];
+            }
+        }
+        return;
+    }
+    for (int i = 0; i < ING_RY; i++) {
+        const int y = row0 + i * FO_BY - DSV_BORDER;
+        if (y >= D.h + DSV_BORDER) {
+            break;
         }
         const int sy = iclamp(y, 0, D.h - 1);
         const uint8_t *src = it.src + (size_t) sy * D.w;
@@ -110,7 +137,7 @@ __global__ void __launch_bounds__(FO_BX *FO_BY) ingest_kernel(const IngestItem *
             continue;
         }
         const int xend = D.w + DSV_BORDER;
-    #pragma unroll 4
+#pragma unroll 4
         for (int e = 0; e < 16; e++) {
             const int x = x0 + e;
             if (x < xend) {
@@ -359,7 +386,9 @@ void copy1_launch(void *dst, const void *src, size_t bytes, cudaStream_t st)
 void ingest_launch(const IngestItem *d_items, int n, int max_w, int max_h, cudaStream_t st)
 {
     if (n > 0) {
-        DSV_LAUNCH(ingest_kernel, fo_grid(max_w, max_h, n, true), dim3(FO_BX, FO_BY), 0, st, d_items);
+        dim3 grid = fo_grid(max_w, max_h, n, true);
+        grid.y = (unsigned) ceil_div(max_h + 2 * DSV_BORDER, FO_BY * ING_RY);
+        DSV_LAUNCH(ingest_kernel, grid, dim3(FO_BX, FO_BY), 0, st, d_items);
         KERNEL_CHECK();
     }
 }

@@ -39,6 +39,21 @@ namespace dsv {
 #define HP_DIM 16
 #define HP_STRIDE 32
 
+/* the search offsets in the reference's candidate order (hme.c:505-541 full-pel, hme.c:560-575 half-pel), packed two
+ * bits per entry (value + 1) so that picking the winner's offset is a shift instead of a table in local memory */
+template <int N> constexpr unsigned pack_offsets(const int (&v)[N])
+{
+    unsigned r = 0;
+    for (int i = 0; i < N; i++) {
+        r |= (unsigned) (v[i] + 1) << (2 * i);
+    }
+    return r;
+}
+constexpr int FP_X[9] = {0, 1, -1, 0, 0, -1, 1, -1, 1}, FP_Y[9] = {0, 0, 0, 1, -1, -1, -1, 1, 1};
+constexpr int HP_X[8] = {1, -1, 0, 0, -1, 1, -1, 1}, HP_Y[8] = {0, 0, 1, -1, -1, -1, 1, 1};
+constexpr unsigned FP_XP = pack_offsets(FP_X), FP_YP = pack_offsets(FP_Y), HP_XP = pack_offsets(HP_X), HP_YP = pack_offsets(HP_Y);
+DSV_D int offset_of(unsigned packed, int m) { return (int) ((packed >> (2 * m)) & 3u) - 1; }
+
 /* per-warp shared memory of the search: the staged source block and the candidate list */
 struct HmeSearchSmem {
     uint8_t src[64 * HME_SRC_STRIDE];
@@ -46,12 +61,42 @@ struct HmeSearchSmem {
     int n;
 };
 /* level 0 adds the half-pel image of the 16x16 reference patch */
+#define HP_PLANE (HP_DIM * HP_DIM) /* a half-pel phase plane of the patch: 16 rows of 16 bytes */
 struct HmeL0Smem {
     HmeSearchSmem s;
+    __align__(16) uint8_t tmp[3 * HP_PLANE];    /* phase planes H (x + 1/2), V (y + 1/2), HV */
+    __align__(16) uint8_t refblk[HP_SAD_SZ * 16]; /* the chosen reference patch, 16 bytes per row */
     int16_t hbuf[(HP_DIM + 4) * HP_DIM];
-    uint8_t tmp[HP_STRIDE * HP_STRIDE];
-    uint8_t refblk[HP_SAD_SZ * HP_SAD_SZ + 12];
 };
+
+/* ld4u on frame memory the kernel only reads (ld.global.nc instead of a generic load) */
+DSV_D unsigned ld4g(const uint8_t *p)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned *q = reinterpret_cast<const unsigned *>(a & ~(uintptr_t) 3);
+    return __funnelshift_r(__ldg(q), __ldg(q + 1), (unsigned) (a & 3) * 8);
+}
+/* 16 bytes at an arbitrary address of such memory: five aligned words, four funnel shifts */
+DSV_D void ld16g(const uint8_t *p, unsigned &w0, unsigned &w1, unsigned &w2, unsigned &w3)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned *q = reinterpret_cast<const unsigned *>(a & ~(uintptr_t) 3);
+    const unsigned sh = (unsigned) (a & 3) * 8;
+    const unsigned a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2), a3 = __ldg(q + 3), a4 = __ldg(q + 4);
+    w0 = __funnelshift_r(a0, a1, sh);
+    w1 = __funnelshift_r(a1, a2, sh);
+    w2 = __funnelshift_r(a2, a3, sh);
+    w3 = __funnelshift_r(a3, a4, sh);
+}
+/* SAD of the 14 bytes s0..s3 (bytes 14, 15 of s3 clear) against bytes OFF .. OFF + 13 of the 16-byte row r */
+template <int OFF> DSV_D unsigned sad14(const uint4 &r, unsigned s0, unsigned s1, unsigned s2, unsigned s3)
+{
+    if (OFF == 0) {
+        return __vsadu4(s0, r.x) + __vsadu4(s1, r.y) + __vsadu4(s2, r.z) + __vsadu4(s3, r.w & 0xffffu);
+    }
+    return __vsadu4(s0, __funnelshift_r(r.x, r.y, 8)) + __vsadu4(s1, __funnelshift_r(r.y, r.z, 8)) +
+           __vsadu4(s2, __funnelshift_r(r.z, r.w, 8)) + __vsadu4(s3, (r.w >> 8) & 0xffffu);
+}
 
 /* A block's words are dealt to the warp as (word column, row group): lanes_per_row = the power of two >= words,
  * 32 / lanes_per_row row groups of consecutive rows.  A lane keeps its word column and walks its rows top to
@@ -96,7 +141,7 @@ DSV_D bool block_setup(const HmeArgs &A, int i, int j, BlockGeom &G, uint8_t *s_
     G.m = (G.wx == G.words - 1) ? G.tail_mask : 0xffffffffu;
     const uint8_t *p = A.src.p + (ptrdiff_t) (G.by + G.r0) * A.src.stride + G.bx + 4 * G.wx;
     for (int r = G.r0; r < G.r1; r++, p += A.src.stride) {
-        *reinterpret_cast<unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * G.wx) = ld4u(p) & G.m;
+        *reinterpret_cast<unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * G.wx) = ld4g(p) & G.m;
     }
     __syncwarp();
     return true;
@@ -165,7 +210,7 @@ DSV_D void search_block(const HmeArgs &A, int i, int j, const BlockGeom &G, HmeS
                 unsigned t = 0;
                 HME_UNROLL(HME_UR_CAND)
                 for (int r = G.r0; r < G.r1; r++, p += rs) {
-                    t += __vsadu4(*reinterpret_cast<const unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * G.wx), ld4u(p) & G.m);
+                    t += __vsadu4(*reinterpret_cast<const unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * G.wx), ld4g(p) & G.m);
                 }
                 acc[k] = t;
             }
@@ -183,7 +228,6 @@ DSV_D void search_block(const HmeArgs &A, int i, int j, const BlockGeom &G, HmeS
     dx = iclamp(dx, -G.bw - G.bx, W - G.bx);
     dy = iclamp(dy, -G.bh - G.by, H - G.by);
     const int xx = G.bx + dx, yy = G.by + dy;
-    const int xf[9] = {0, 1, -1, 0, 0, -1, 1, -1, 1}, yf[9] = {0, 0, 0, 1, -1, -1, -1, 1, 1};
     unsigned acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (G.r1 > G.r0) {
         /* reference rows r0-1 .. r1 of this lane's word column, each loaded once as bytes [-1, 5) around the word:
@@ -202,7 +246,7 @@ DSV_D void search_block(const HmeArgs &A, int i, int j, const BlockGeom &G, HmeS
             if (t + 1 < G.r1) {
                 s_next = *reinterpret_cast<const unsigned *>(sp + (t + 1) * HME_SRC_STRIDE);
             }
-            const unsigned q0 = q[0], q1 = q[1], q2 = q[2];
+            const unsigned q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
             const unsigned lo = __funnelshift_r(q0, q1, bsh), hi = __funnelshift_r(q1, q2, bsh);
             const unsigned ra = lo & G.m, rb = __funnelshift_r(lo, hi, 8) & G.m, rc = __funnelshift_r(lo, hi, 16) & G.m;
             if (t >= G.r0 && t < G.r1) {
@@ -231,10 +275,9 @@ DSV_D void search_block(const HmeArgs &A, int i, int j, const BlockGeom &G, HmeS
             m = k;
         }
     }
-    odx = dx + xf[m];
-    ody = dy + yf[m];
+    odx = dx + offset_of(FP_XP, m);
+    ody = dy + offset_of(FP_YP, m);
     obest = best;
-    (void) yf;
 }
 
 DSV_D void store_mv(DevMV *dst, int x, int y, int mode, int submask, int lo_var, int lo_tex)
@@ -289,25 +332,82 @@ enum {
     SUM_COUNT
 };
 
-/* sum and sum of squares of a cw x ch byte rectangle, by one warp, into acc[0] / acc[1] (c_maxvar's inputs) */
-DSV_D void warp_rect_moments(const uint8_t *p0, int stride, int cw, int ch, int lane, unsigned &s1, unsigned &s2)
+/* Sums and sums of squares of the block's four chroma rectangles (source U, V, reference U, V: c_maxvar's inputs,
+ * hme.c:270-300) into sum[2k], sum[2k + 1].  One walk serves the four planes, so four loads are in flight per step;
+ * the (row, column) of a lane's item advances by additions instead of a division per item. */
+DSV_D void warp_chroma_moments(const HmeArgs &A, int cbx, int cby, int cw, int ch, int lane, unsigned *sum)
 {
-    if ((cw & 3) == 0) { /* words: lanes over (row, word) pairs */
-        const int wpr = cw >> 2;
-        for (int idx = lane; idx < wpr * ch; idx += 32) {
-            const int ly = idx / wpr, wx = idx - ly * wpr;
-            const unsigned w = ld4u(p0 + (ptrdiff_t) ly * stride + 4 * wx);
-            s1 += __vsadu4(w, 0u);
-            s2 = __dp4a(w, w, s2);
+    if (cw <= 0 || ch <= 0) {
+        return;
+    }
+    const HmePlane *pl[4] = {&A.srcU, &A.srcV, &A.refU, &A.refV};
+    const uint8_t *p0[4];
+    int st[4];
+    unsigned al = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        st[k] = pl[k]->stride;
+        p0[k] = pl[k]->p + (ptrdiff_t) cby * st[k] + cbx;
+        al |= (unsigned) reinterpret_cast<uintptr_t>(p0[k]) | (unsigned) st[k];
+    }
+    if ((cw & 3) == 0) {
+        const bool v16 = ((cw | (int) al) & 15) == 0; /* 16 samples per item, else 4 */
+        const int per = v16 ? cw >> 4 : cw >> 2;
+        int ly = lane / per, x = lane - ly * per;
+        const int dq = 32 / per, dr = 32 - dq * per;
+        if (v16) {
+            while (ly < ch) {
+                uint4 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    v[k] = __ldg(reinterpret_cast<const uint4 *>(p0[k] + (ptrdiff_t) ly * st[k]) + x);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    sum[2 * k] += __vsadu4(v[k].x, 0u) + __vsadu4(v[k].y, 0u) + __vsadu4(v[k].z, 0u) + __vsadu4(v[k].w, 0u);
+                    sum[2 * k + 1] = __dp4a(v[k].x, v[k].x, __dp4a(v[k].y, v[k].y, __dp4a(v[k].z, v[k].z, __dp4a(v[k].w, v[k].w, sum[2 * k + 1]))));
+                }
+                ly += dq;
+                x += dr;
+                if (x >= per) {
+                    x -= per;
+                    ly++;
+                }
+            }
+            return;
+        }
+        while (ly < ch) {
+            unsigned w[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                w[k] = ld4g(p0[k] + (ptrdiff_t) ly * st[k] + 4 * x);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                sum[2 * k] += __vsadu4(w[k], 0u);
+                sum[2 * k + 1] = __dp4a(w[k], w[k], sum[2 * k + 1]);
+            }
+            ly += dq;
+            x += dr;
+            if (x >= per) {
+                x -= per;
+                ly++;
+            }
         }
         return;
     }
-    for (int ly = 0; ly < ch; ly++) {
-        for (int lx = lane; lx < cw; lx += 32) {
-            const unsigned v = p0[(ptrdiff_t) ly * stride + lx];
-            s1 += v;
-            s2 += v * v;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        unsigned s1 = 0, s2 = 0;
+        for (int ly = 0; ly < ch; ly++) {
+            for (int lx = lane; lx < cw; lx += 32) {
+                const unsigned v = p0[k][(ptrdiff_t) ly * st[k] + lx];
+                s1 += v;
+                s2 += v * v;
+            }
         }
+        sum[2 * k] += s1;
+        sum[2 * k + 1] += s2;
     }
 }
 
@@ -350,6 +450,15 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
     int mvx = fx, mvy = fy;
     bool has_hp = false;
 
+    /* the 14 bytes of row (lane & 15) of the source's centre patch (lanes 0-13 and 16-29), bytes 14 / 15 clear */
+    const int prow = lane & 15;
+    unsigned s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    if (prow < HP_SAD_SZ) {
+        ld16g(A.src.p + (ptrdiff_t) (cy + prow) * ss + cx, s0, s1, s2, s3);
+        s3 &= 0xffffu;
+    }
+    unsigned *s_refblk_w = reinterpret_cast<unsigned *>(s_refblk);
+
     /* ---- half-pel refinement (hme.c:551-591) ---- */
     if (best > A.blk_w * A.blk_h) {
         int best_hp = (int) ((unsigned) (best * (HP_SAD_SZ * HP_SAD_SZ)) / yarea);
@@ -358,7 +467,7 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
         for (int k = lane; k < (HP_DIM + 4) * (HP_DIM / 4); k += 32) {
             const int jj = k >> 2, i0 = (k & 3) * 4;
             const uint8_t *p = rp0 + (ptrdiff_t) (jj - 1) * rs + i0 - 1;
-            const unsigned wa = ld4u(p), wb2 = ld4u(p + 4);
+            const unsigned wa = ld4g(p), wb2 = ld4g(p + 4);
             int16_t *d = s_hbuf + jj * HP_DIM + i0;
             d[0] = (int16_t) hp_taps_u8x4(wa);
             d[1] = (int16_t) hp_taps_u8x4(__funnelshift_r(wa, wb2, 8));
@@ -366,28 +475,49 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
             d[3] = (int16_t) hp_taps_u8x4(__funnelshift_r(wa, wb2, 24));
         }
         __syncwarp();
-        for (int k = lane; k < HP_DIM * HP_DIM; k += 32) {
-            const int jj = k / HP_DIM, ii = k - jj * HP_DIM;
-            const uint8_t *p = rp0 + (ptrdiff_t) jj * rs + ii;
-            uint8_t *d = s_tmp + (2 * jj) * HP_STRIDE + 2 * ii;
-            const int16_t *b = s_hbuf + k;
-            d[0] = p[0];
-            d[HP_STRIDE] = clamp_u8((9 * (p[0] + p[rs]) - (p[-rs] + p[2 * rs]) + 8) >> 4);
-            d[1] = clamp_u8((b[HP_DIM] + 8) >> 4); /* the H filter of this row is hbuf row jj + 1 */
-            d[HP_STRIDE + 1] = clamp_u8((9 * (b[HP_DIM] + b[2 * HP_DIM]) - (b[0] + b[3 * HP_DIM]) + 128) >> 8);
+        /* The half-pel image of the patch (hme.c:350-376) as three phase planes of 16 x 16 bytes -- H (x + 1/2),
+         * V (y + 1/2), HV -- so that a candidate's 14 samples of a row are consecutive bytes; the full-pel phase is
+         * never a candidate.  Four columns per lane and step; the H filter of patch row jj is hbuf row jj + 1. */
+        for (int k = lane; k < HP_DIM * (HP_DIM / 4); k += 32) {
+            const int jj = k >> 2, i0 = (k & 3) * 4;
+            const uint8_t *p = rp0 + (ptrdiff_t) jj * rs + i0;
+            const unsigned ra = ld4g(p - rs), rb = ld4g(p), rc = ld4g(p + rs), rd = ld4g(p + 2 * rs);
+            const int16_t *b = s_hbuf + jj * HP_DIM + i0;
+            unsigned hw = 0, vw = 0, xw = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int v = 9 * (byte_of(rb, e) + byte_of(rc, e)) - (byte_of(ra, e) + byte_of(rd, e));
+                vw |= (unsigned) clamp_u8((v + 8) >> 4) << (8 * e);
+                hw |= (unsigned) clamp_u8((b[HP_DIM + e] + 8) >> 4) << (8 * e);
+                xw |= (unsigned) clamp_u8((9 * (b[HP_DIM + e] + b[2 * HP_DIM + e]) - (b[e] + b[3 * HP_DIM + e]) + 128) >> 8) << (8 * e);
+            }
+            unsigned *d = reinterpret_cast<unsigned *>(s_tmp) + k;
+            d[0] = hw;
+            d[HP_PLANE / 4] = vw;
+            d[2 * (HP_PLANE / 4)] = xw;
         }
         __syncwarp();
-        const int xh[8] = {1, -1, 0, 0, -1, 1, -1, 1}, yh[8] = {0, 0, 1, -1, -1, -1, 1, 1};
-        const uint8_t *tmph = s_tmp + 2 + 2 * HP_STRIDE;
-        unsigned acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int k = lane; k < HP_SAD_SZ * HP_SAD_SZ; k += 32) {
-            const int jj = k / HP_SAD_SZ, ii = k - jj * HP_SAD_SZ;
-            const int sp = A.src.p[(ptrdiff_t) (cy + jj) * ss + cx + ii];
-#pragma unroll
-            for (int c = 0; c < 8; c++) {
-                acc[c] += (unsigned) iabs(sp - (int) tmph[xh[c] + yh[c] * HP_STRIDE + 2 * ii + 2 * HP_STRIDE * jj]);
+        /* candidate (xh, yh), sample (ii, jj) = plane[jj + (yh >= 0)][ii + (xh >= 0)]: lanes 0-13 take the H / V
+         * candidates of row jj = lane, lanes 16-29 the four HV candidates of row jj = lane - 16 */
+        unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        if (prow < HP_SAD_SZ) {
+            const uint4 *pl = reinterpret_cast<const uint4 *>(s_tmp);
+            if (lane < 16) {
+                const uint4 h = pl[prow + 1], v1 = pl[HP_DIM + prow + 1], v0 = pl[HP_DIM + prow];
+                a0 = sad14<1>(h, s0, s1, s2, s3);
+                a1 = sad14<0>(h, s0, s1, s2, s3);
+                a2 = sad14<1>(v1, s0, s1, s2, s3);
+                a3 = sad14<1>(v0, s0, s1, s2, s3);
+            } else {
+                const uint4 x0 = pl[2 * HP_DIM + prow], x1 = pl[2 * HP_DIM + prow + 1];
+                a0 = sad14<0>(x0, s0, s1, s2, s3);
+                a1 = sad14<1>(x0, s0, s1, s2, s3);
+                a2 = sad14<0>(x1, s0, s1, s2, s3);
+                a3 = sad14<1>(x1, s0, s1, s2, s3);
             }
         }
+        const bool hv = lane >= 16;
+        unsigned acc[8] = {hv ? 0u : a0, hv ? 0u : a1, hv ? 0u : a2, hv ? 0u : a3, hv ? a0 : 0u, hv ? a1 : 0u, hv ? a2 : 0u, hv ? a3 : 0u};
         warp_reduce_n<8>(acc);
         int m = -1;
 #pragma unroll
@@ -400,11 +530,14 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
         mvx <<= 1;
         mvy <<= 1;
         if (m != -1) {
-            mvx += xh[m];
-            mvy += yh[m];
-            for (int k = lane; k < HP_SAD_SZ * HP_SAD_SZ; k += 32) {
-                const int jj = k / HP_SAD_SZ, ii = k - jj * HP_SAD_SZ;
-                s_refblk[k] = tmph[xh[m] + yh[m] * HP_STRIDE + 2 * ii + 2 * HP_STRIDE * jj];
+            mvx += offset_of(HP_XP, m);
+            mvy += offset_of(HP_YP, m);
+            /* the winner's samples: its plane from the first row (yh >= 0) and byte (xh >= 0) on */
+            const int plane = m < 2 ? 0 : (m < 4 ? 1 : 2), dy = (0xc7 >> m) & 1, dx = (0xad >> m) & 1;
+            const unsigned *pw = reinterpret_cast<const unsigned *>(s_tmp + plane * HP_PLANE + dy * HP_DIM);
+            for (int k = lane; k < HP_SAD_SZ * 4; k += 32) {
+                const unsigned lo = pw[k], hi = pw[k + 1];
+                s_refblk_w[k] = dx ? __funnelshift_r(lo, hi, 8) : lo;
             }
             has_hp = true;
             best = (int) ((unsigned) best_hp * yarea / (unsigned) (HP_SAD_SZ * HP_SAD_SZ));
@@ -414,9 +547,9 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
         mvy <<= 1;
     }
     if (!has_hp) {
-        for (int k = lane; k < HP_SAD_SZ * HP_SAD_SZ; k += 32) {
-            const int jj = k / HP_SAD_SZ, ii = k - jj * HP_SAD_SZ;
-            s_refblk[k] = A.ref.p[(ptrdiff_t) (cy + (mvy >> 1) + jj) * rs + cx + (mvx >> 1) + ii];
+        const uint8_t *rp = A.ref.p + (ptrdiff_t) (cy + (mvy >> 1)) * rs + cx + (mvx >> 1);
+        for (int k = lane; k < HP_SAD_SZ * 4; k += 32) {
+            s_refblk_w[k] = ld4g(rp + (ptrdiff_t) (k >> 2) * rs + 4 * (k & 3));
         }
     }
     __syncwarp();
@@ -433,13 +566,14 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
         /* four samples per step: the block sums of block_analysis / y_sqrvar / intra_metric are sums of absolute
          * differences and squares, i.e. __vsadu4 / __dp4a on packed words.  A lane walks its rows downwards, so the
          * row above is last step's word; the bytes left / right of a word come from the neighbouring lanes. */
-        unsigned good[4] = {0, 0, 0, 0}, evil[4] = {0, 0, 0, 0};
+        unsigned g_all = 0, e_all = 0, g_top = 0, e_top = 0;
         const int lx0 = 4 * G.wx;
+        const int qxi = lx0 >= sbw; /* sbw is a multiple of 4 here: a word lies in one quadrant column */
         const int rbase = G.active ? G.r0 : 0; /* idle lanes walk along (shuffles are warp-wide) */
         unsigned w_up = 0, r_up = 0;
         if (G.active && G.r0 > 0 && G.r0 < G.bh) {
             w_up = *reinterpret_cast<const unsigned *>(s_src + (G.r0 - 1) * HME_SRC_STRIDE + lx0);
-            r_up = ld4u(ref0 + (ptrdiff_t) (G.r0 - 1) * rs + lx0);
+            r_up = ld4g(ref0 + (ptrdiff_t) (G.r0 - 1) * rs + lx0);
         }
         for (int it = 0; it < G.rpg; it++) {
             const int ly = rbase + it;
@@ -447,7 +581,7 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
             unsigned w = 0, r = 0;
             if (on) {
                 w = *reinterpret_cast<const unsigned *>(s_src + ly * HME_SRC_STRIDE + lx0);
-                r = ld4u(ref0 + (ptrdiff_t) ly * rs + lx0);
+                r = ld4g(ref0 + (ptrdiff_t) ly * rs + lx0);
             }
             const unsigned w_r = __shfl_down_sync(0xffffffffu, w, 1), w_l = __shfl_up_sync(0xffffffffu, w, 1);
             const unsigned r_l = __shfl_up_sync(0xffffffffu, r, 1);
@@ -462,40 +596,37 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
                 sum[SUM_RS] += __vsadu4(r, 0u);
                 sum[SUM_RSS] = __dp4a(r, r, sum[SUM_RSS]);
                 if (ly < 2 * sbh) { /* intra_metric on the four quadrants, hme.c:87-134 */
-                    const int qxi = lx0 >= sbw, qyi = ly >= sbh;
+                    const int qyi = ly >= sbh;
                     const int qi0 = lx0 - qxi * sbw, qj = ly - qyi * sbh;
                     const unsigned wl = (w << 8) | (qi0 == 0 ? (w & 0xffu) : (w_l >> 24));
                     const unsigned rl = (r << 8) | (qi0 == 0 ? (r & 0xffu) : (r_l >> 24));
                     const unsigned ua = qj == 0 ? w : up;
                     const unsigned ub = qj == 0 ? r : r_up;
                     unsigned g = __vsadu4(w, wl) + __vsadu4(w, ua) + __vsadu4(r, rl) + __vsadu4(r, ub);
-                    unsigned e = 0;
+                    /* |w - r| > 2 counts as evil; 0 / 1 / 2 add 192 / 128 / 96 = 192 - 64 v + 32 (v >> 1) to good */
                     const unsigned d = __vabsdiffu4(w, r);
-#pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        const unsigned v = (d >> (8 * b)) & 0xffu;
-                        if (v > 2u) {
-                            e += v;
-                        } else {
-                            g += v == 0u ? 192u : (v == 1u ? 128u : 96u);
-                        }
-                    }
-                    const int q = qxi | (qyi << 1);
-#pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        good[t] += q == t ? g : 0u;
-                        evil[t] += q == t ? e : 0u;
-                    }
+                    const unsigned big = __vcmpgtu4(d, 0x02020202u);
+                    const unsigned sm = d & ~big;
+                    const unsigned e = __vsadu4(d & big, 0u);
+                    g += 192u * (4u - ((unsigned) __popc(big) >> 3)) - 64u * __vsadu4(sm, 0u) + 32u * (unsigned) __popc(sm & 0x02020202u);
+                    g_all += g;
+                    e_all += e;
+                    g_top += qyi ? 0u : g;
+                    e_top += qyi ? 0u : e;
                 }
                 w_up = w;
                 r_up = r;
             }
         }
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            sum[SUM_GOOD0 + t] += good[t];
-            sum[SUM_EVIL0 + t] += evil[t];
-        }
+        const unsigned g_bot = g_all - g_top, e_bot = e_all - e_top;
+        sum[SUM_GOOD0] += qxi ? 0u : g_top;
+        sum[SUM_GOOD1] += qxi ? g_top : 0u;
+        sum[SUM_GOOD2] += qxi ? 0u : g_bot;
+        sum[SUM_GOOD3] += qxi ? g_bot : 0u;
+        sum[SUM_EVIL0] += qxi ? 0u : e_top;
+        sum[SUM_EVIL1] += qxi ? e_top : 0u;
+        sum[SUM_EVIL2] += qxi ? 0u : e_bot;
+        sum[SUM_EVIL3] += qxi ? e_bot : 0u;
     } else {
         /* general widths (blocks cut by the picture edge): rows in turn, columns to lanes */
         for (int ly = 0; ly < G.bh; ly++) {
@@ -541,31 +672,42 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
             }
         }
     }
-    { /* chroma variance inputs, c_maxvar hme.c:270-300 */
-        const int cbx = i * (A.blk_w >> A.hs), cby = j * (A.blk_h >> A.vs);
-        const int cbw = G.bw >> A.hs, cbh = G.bh >> A.vs;
-        warp_rect_moments(A.srcU.p + (ptrdiff_t) cby * A.srcU.stride + cbx, A.srcU.stride, cbw, cbh, lane, sum[SUM_CSU], sum[SUM_CSSU]);
-        warp_rect_moments(A.srcV.p + (ptrdiff_t) cby * A.srcV.stride + cbx, A.srcV.stride, cbw, cbh, lane, sum[SUM_CSV], sum[SUM_CSSV]);
-        warp_rect_moments(A.refU.p + (ptrdiff_t) cby * A.refU.stride + cbx, A.refU.stride, cbw, cbh, lane, sum[SUM_CRU], sum[SUM_CRSU]);
-        warp_rect_moments(A.refV.p + (ptrdiff_t) cby * A.refV.stride + cbx, A.refV.stride, cbw, cbh, lane, sum[SUM_CRV], sum[SUM_CRSV]);
-    }
-    for (int k = lane; k < HP_SAD_SZ * HP_SAD_SZ; k += 32) { /* block_texture on the two 14x14 patches, hme.c:179-209 */
-        const int jj = k / HP_SAD_SZ, ii = k - jj * HP_SAD_SZ;
-        const uint8_t *sp = A.src.p + (ptrdiff_t) (cy + jj) * ss + cx + ii;
-        int px = sp[0];
-        int right = ii == HP_SAD_SZ - 1 ? px : sp[1];
-        int up = jj == 0 ? px : sp[-ss];
-        sum[SUM_PSH] += (unsigned) iabs(px - right);
-        sum[SUM_PSV] += (unsigned) iabs(px - up);
-        sum[SUM_PAV] += (unsigned) px;
-        sum[SUM_PAVS] += (unsigned) (px * px);
-        px = s_refblk[k];
-        right = ii == HP_SAD_SZ - 1 ? px : s_refblk[k + 1];
-        up = jj == 0 ? px : s_refblk[k - HP_SAD_SZ];
-        sum[SUM_QSH] += (unsigned) iabs(px - right);
-        sum[SUM_QSV] += (unsigned) iabs(px - up);
-        sum[SUM_QAV] += (unsigned) px;
-        sum[SUM_QAVS] += (unsigned) (px * px);
+    warp_chroma_moments(A, i * (A.blk_w >> A.hs), j * (A.blk_h >> A.vs), G.bw >> A.hs, G.bh >> A.vs, lane, &sum[SUM_CSU]);
+    { /* block_texture on the two 14x14 patches (hme.c:179-209): lanes 0-13 a row of the source patch each, lanes
+       * 16-29 a row of the chosen reference patch; the row above comes from the lane below */
+        unsigned t0 = s0, t1 = s1, t2 = s2, t3 = s3;
+        if (lane >= 16 && prow < HP_SAD_SZ) {
+            const uint4 r = reinterpret_cast<const uint4 *>(s_refblk)[prow];
+            t0 = r.x;
+            t1 = r.y;
+            t2 = r.z;
+            t3 = r.w & 0xffffu;
+        }
+        unsigned u0 = __shfl_up_sync(0xffffffffu, t0, 1), u1 = __shfl_up_sync(0xffffffffu, t1, 1);
+        unsigned u2 = __shfl_up_sync(0xffffffffu, t2, 1), u3 = __shfl_up_sync(0xffffffffu, t3, 1);
+        if (prow == 0) {
+            u0 = t0;
+            u1 = t1;
+            u2 = t2;
+            u3 = t3;
+        }
+        if (prow < HP_SAD_SZ) {
+            const unsigned last = t3 >> 8; /* sample 13 is its own right neighbour */
+            const unsigned th = __vsadu4(t0, __funnelshift_r(t0, t1, 8)) + __vsadu4(t1, __funnelshift_r(t1, t2, 8)) +
+                                __vsadu4(t2, __funnelshift_r(t2, t3, 8)) + __vsadu4(t3, last | (last << 8));
+            const unsigned tv = __vsadu4(t0, u0) + __vsadu4(t1, u1) + __vsadu4(t2, u2) + __vsadu4(t3, u3);
+            const unsigned av = __vsadu4(t0, 0u) + __vsadu4(t1, 0u) + __vsadu4(t2, 0u) + __vsadu4(t3, 0u);
+            const unsigned avs = __dp4a(t0, t0, __dp4a(t1, t1, __dp4a(t2, t2, __dp4a(t3, t3, 0u))));
+            const bool q = lane >= 16;
+            sum[SUM_PSH] += q ? 0u : th;
+            sum[SUM_PSV] += q ? 0u : tv;
+            sum[SUM_PAV] += q ? 0u : av;
+            sum[SUM_PAVS] += q ? 0u : avs;
+            sum[SUM_QSH] += q ? th : 0u;
+            sum[SUM_QSV] += q ? tv : 0u;
+            sum[SUM_QAV] += q ? av : 0u;
+            sum[SUM_QAVS] += q ? avs : 0u;
+        }
     }
     warp_reduce_n<SUM_COUNT>(sum);
 
@@ -579,6 +721,15 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
         if (lo > 0 || hi < 255) {
             const int tail = G.bw & 3;
             const int nb = (G.wx == G.words - 1 && tail) ? tail : 4;
+            if (tail == 0) { /* whole words: only one of the two bounds can lie inside 0..255 */
+                const unsigned bound = (unsigned) (lo > 0 ? lo : hi) * 0x01010101u;
+                unsigned out = 0;
+                for (int r = G.r0; r < G.r1; r++) {
+                    const unsigned w = *reinterpret_cast<const unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * G.wx);
+                    out |= lo > 0 ? __vcmpltu4(w, bound) : __vcmpgtu4(w, bound);
+                }
+                bad = out != 0u;
+            } else
             for (int r = G.r0; r < G.r1; r++) {
                 const unsigned w = *reinterpret_cast<const unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * G.wx);
 #pragma unroll

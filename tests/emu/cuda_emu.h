@@ -243,6 +243,13 @@ static inline unsigned __vsubss4(unsigned a, unsigned b)
     }
     return r;
 }
+static inline unsigned __vcmpgtu4(unsigned a, unsigned b)
+{
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) r |= (((a >> (8 * i)) & 0xff) > ((b >> (8 * i)) & 0xff) ? 0xffu : 0u) << (8 * i);
+    return r;
+}
+static inline unsigned __vcmpltu4(unsigned a, unsigned b) { return __vcmpgtu4(b, a); }
 static inline unsigned __vsadu4(unsigned a, unsigned b)
 {
     unsigned r = 0;
