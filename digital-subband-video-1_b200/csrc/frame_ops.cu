@@ -105,14 +105,33 @@ __global__ void __launch_bounds__(FO_BX *FO_BY) ingest_kernel(const IngestItem *
         return;
     }
     const int row0 = (int) (blockIdx.y * FO_BY * ING_RY + threadIdx.y);
-    const bool fast_x = x0 >= 0 && x0 + 16 <= D.w && ((D.w | x0) & 15) == 0 && aligned16(it.src);
-    if (fast_x) { /* interior chunk of a plane whose rows keep the alignment: ING_RY independent loads, then the stores */
+    /* A chunk that lies wholly in the left / right border repeats the row's first / last sample (one byte load, one
+     * 16-byte store); an interior chunk of a plane whose rows keep the alignment is one 16-byte load.  Either way the
+     * ING_RY independent loads are requested before the first store.  (x0 is a multiple of 16.) */
+    enum { CK_MIXED, CK_INTERIOR, CK_LEFT, CK_RIGHT };
+    int kind = CK_MIXED;
+    if (aligned16(D.p) && (D.stride & 15) == 0) {
+        if (x0 + 16 <= 0) {
+            kind = CK_LEFT;
+        } else if (x0 >= D.w) {
+            kind = x0 + 16 <= D.w + DSV_BORDER ? CK_RIGHT : CK_MIXED;
+        } else if (x0 + 16 <= D.w && (D.w & 15) == 0 && aligned16(it.src)) {
+            kind = CK_INTERIOR;
+        }
+    }
+    if (kind != CK_MIXED) {
         uint4 v[ING_RY];
 #pragma unroll
         for (int i = 0; i < ING_RY; i++) {
             const int y = row0 + i * FO_BY - DSV_BORDER;
             if (y < D.h + DSV_BORDER) {
-                v[i] = *reinterpret_cast<const uint4 *>(it.src + (size_t) iclamp(y, 0, D.h - 1) * D.w + x0);
+                const uint8_t *srow = it.src + (size_t) iclamp(y, 0, D.h - 1) * D.w;
+                if (kind == CK_INTERIOR) {
+                    v[i] = *reinterpret_cast<const uint4 *>(srow + x0);
+                } else {
+                    const unsigned b = (unsigned) (kind == CK_LEFT ? srow[0] : srow[D.w - 1]) * 0x01010101u;
+                    v[i] = make_uint4(b, b, b, b);
+                }
             }
         }
 #pragma unroll
@@ -251,6 +270,13 @@ __global__ void __launch_bounds__(FO_BX *FO_BY) down2_kernel(const Down2Item *it
                 o[k] = r;
             }
             *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+            continue;
+        }
+        if ((x0 + 16 <= 0 || (x0 >= D.w && x0 + 16 <= D.w + DSV_BORDER)) && aligned16(dst)) {
+            /* wholly inside the left / right border: the row's first / last output sample, sixteen times */
+            const int sx = x0 < 0 ? 0 : 2 * (D.w - 1);
+            const unsigned v = (unsigned) ((s0[sx] + s0[sx + 1] + s1[sx] + s1[sx + 1] + 2) >> 2) * 0x01010101u;
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(v, v, v, v);
             continue;
         }
         const int xend = D.w + DSV_BORDER;

@@ -328,7 +328,6 @@ enum {
     SUM_CRU, SUM_CRSU, SUM_CRV, SUM_CRSV,   /* reference chroma */
     SUM_PSH, SUM_PSV, SUM_PAV, SUM_PAVS,    /* source 14x14 patch: block_texture */
     SUM_QSH, SUM_QSV, SUM_QAV, SUM_QAVS,    /* chosen reference patch */
-    SUM_GOOD0, SUM_GOOD1, SUM_GOOD2, SUM_GOOD3, SUM_EVIL0, SUM_EVIL1, SUM_EVIL2, SUM_EVIL3,
     SUM_COUNT
 };
 
@@ -409,6 +408,109 @@ DSV_D void warp_chroma_moments(const HmeArgs &A, int cbx, int cby, int cw, int c
         sum[2 * k] += s1;
         sum[2 * k + 1] += s2;
     }
+}
+
+/* intra_metric (hme.c:87-134) of the block's four quadrants against the zero-MV reference block, summed over the warp:
+ * ge[q] = good, ge[4 + q] = evil.  Only the blocks the cascade has already marked intra get here. */
+DSV_D void quadrant_metric(const BlockGeom &G, const uint8_t *s_src, const uint8_t *ref0, int rs, int lane, unsigned (&ge)[8])
+{
+    const int sbw = G.bw / 2, sbh = G.bh / 2;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        ge[k] = 0;
+    }
+    if ((G.bw & 7) == 0) {
+        /* sbw is a multiple of 4: a word lies in one quadrant column, so a lane keeps two running sums (all rows, top
+         * rows); the bytes left of a word come from the neighbouring lane, the row above is last step's word */
+        unsigned g_all = 0, e_all = 0, g_top = 0, e_top = 0;
+        const int lx0 = 4 * G.wx;
+        const int qxi = lx0 >= sbw;
+        const int rbase = G.active ? G.r0 : 0; /* idle lanes walk along (shuffles are warp-wide) */
+        unsigned w_up = 0, r_up = 0;
+        if (G.active && G.r0 > 0 && G.r0 < G.bh) {
+            w_up = *reinterpret_cast<const unsigned *>(s_src + (G.r0 - 1) * HME_SRC_STRIDE + lx0);
+            r_up = ld4g(ref0 + (ptrdiff_t) (G.r0 - 1) * rs + lx0);
+        }
+        for (int it = 0; it < G.rpg; it++) {
+            const int ly = rbase + it;
+            const bool on = G.active && ly < G.r1;
+            unsigned w = 0, r = 0;
+            if (on) {
+                w = *reinterpret_cast<const unsigned *>(s_src + ly * HME_SRC_STRIDE + lx0);
+                r = ld4g(ref0 + (ptrdiff_t) ly * rs + lx0);
+            }
+            const unsigned w_l = __shfl_up_sync(0xffffffffu, w, 1), r_l = __shfl_up_sync(0xffffffffu, r, 1);
+            if (on) {
+                if (ly < 2 * sbh) {
+                    const int qyi = ly >= sbh;
+                    const int qi0 = lx0 - qxi * sbw, qj = ly - qyi * sbh;
+                    const unsigned wl = (w << 8) | (qi0 == 0 ? (w & 0xffu) : (w_l >> 24));
+                    const unsigned rl = (r << 8) | (qi0 == 0 ? (r & 0xffu) : (r_l >> 24));
+                    const unsigned ua = qj == 0 ? w : w_up;
+                    const unsigned ub = qj == 0 ? r : r_up;
+                    unsigned g = __vsadu4(w, wl) + __vsadu4(w, ua) + __vsadu4(r, rl) + __vsadu4(r, ub);
+                    /* |w - r| > 2 counts as evil; 0 / 1 / 2 add 192 / 128 / 96 = 192 - 64 v + 32 (v >> 1) to good */
+                    const unsigned d = __vabsdiffu4(w, r);
+                    const unsigned big = __vcmpgtu4(d, 0x02020202u);
+                    const unsigned sm = d & ~big;
+                    const unsigned e = __vsadu4(d & big, 0u);
+                    g += 192u * (4u - ((unsigned) __popc(big) >> 3)) - 64u * __vsadu4(sm, 0u) + 32u * (unsigned) __popc(sm & 0x02020202u);
+                    g_all += g;
+                    e_all += e;
+                    g_top += qyi ? 0u : g;
+                    e_top += qyi ? 0u : e;
+                }
+                w_up = w;
+                r_up = r;
+            }
+        }
+        const unsigned g_bot = g_all - g_top, e_bot = e_all - e_top;
+        ge[0] = qxi ? 0u : g_top;
+        ge[1] = qxi ? g_top : 0u;
+        ge[2] = qxi ? 0u : g_bot;
+        ge[3] = qxi ? g_bot : 0u;
+        ge[4] = qxi ? 0u : e_top;
+        ge[5] = qxi ? e_top : 0u;
+        ge[6] = qxi ? 0u : e_bot;
+        ge[7] = qxi ? e_bot : 0u;
+    } else {
+        /* general widths (blocks cut by the picture edge): rows in turn, columns to lanes */
+        for (int ly = 0; ly < 2 * sbh; ly++) {
+            const int qyi = ly >= sbh;
+            const int qj = ly - qyi * sbh;
+            unsigned good0 = 0, good1 = 0, evil0 = 0, evil1 = 0;
+            for (int lx = lane; lx < 2 * sbw; lx += 32) {
+                const uint8_t *sp = s_src + ly * HME_SRC_STRIDE + lx;
+                const uint8_t *rp = ref0 + (ptrdiff_t) ly * rs + lx;
+                const int pa = sp[0], pb = rp[0];
+                const int qxi = lx >= sbw;
+                const int qi = lx - qxi * sbw;
+                const int la = qi == 0 ? pa : sp[-1], lb = qi == 0 ? pb : rp[-1];
+                const int ua = qj == 0 ? pa : sp[-HME_SRC_STRIDE], ub = qj == 0 ? pb : rp[-rs];
+                unsigned good = (unsigned) (iabs(pa - la) + iabs(pa - ua) + iabs(pb - lb) + iabs(pb - ub));
+                unsigned evil = 0;
+                const int dif = iabs(pa - pb);
+                if (dif > 2) {
+                    evil = (unsigned) dif;
+                } else {
+                    good += dif == 0 ? 192u : (dif == 1 ? 128u : 96u);
+                }
+                good0 += qxi ? 0u : good;
+                good1 += qxi ? good : 0u;
+                evil0 += qxi ? 0u : evil;
+                evil1 += qxi ? evil : 0u;
+            }
+            ge[0] += qyi ? 0u : good0;
+            ge[1] += qyi ? 0u : good1;
+            ge[2] += qyi ? good0 : 0u;
+            ge[3] += qyi ? good1 : 0u;
+            ge[4] += qyi ? 0u : evil0;
+            ge[5] += qyi ? 0u : evil1;
+            ge[6] += qyi ? evil0 : 0u;
+            ge[7] += qyi ? evil1 : 0u;
+        }
+    }
+    warp_reduce_n<8>(ge);
 }
 
 /* occupancy A/B at 64 lanes (round 2): no cap (80 registers, 6 CTAs of 4 warps per SM) 668 us; 8 CTAs / 64 registers
@@ -563,17 +665,14 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
     const int sbw = G.bw / 2, sbh = G.bh / 2;
     const uint8_t *ref0 = A.ref.p + (ptrdiff_t) G.by * rs + G.bx; /* zero-MV reference block */
     if ((G.bw & 7) == 0) {
-        /* four samples per step: the block sums of block_analysis / y_sqrvar / intra_metric are sums of absolute
-         * differences and squares, i.e. __vsadu4 / __dp4a on packed words.  A lane walks its rows downwards, so the
-         * row above is last step's word; the bytes left / right of a word come from the neighbouring lanes. */
-        unsigned g_all = 0, e_all = 0, g_top = 0, e_top = 0;
+        /* four samples per step: the block sums of block_analysis / y_sqrvar are sums of absolute differences and
+         * squares, i.e. __vsadu4 / __dp4a on packed words.  A lane walks its rows downwards, so the row above is last
+         * step's word; the byte right of a word comes from the neighbouring lane. */
         const int lx0 = 4 * G.wx;
-        const int qxi = lx0 >= sbw; /* sbw is a multiple of 4 here: a word lies in one quadrant column */
         const int rbase = G.active ? G.r0 : 0; /* idle lanes walk along (shuffles are warp-wide) */
-        unsigned w_up = 0, r_up = 0;
+        unsigned w_up = 0;
         if (G.active && G.r0 > 0 && G.r0 < G.bh) {
             w_up = *reinterpret_cast<const unsigned *>(s_src + (G.r0 - 1) * HME_SRC_STRIDE + lx0);
-            r_up = ld4g(ref0 + (ptrdiff_t) (G.r0 - 1) * rs + lx0);
         }
         for (int it = 0; it < G.rpg; it++) {
             const int ly = rbase + it;
@@ -583,8 +682,7 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
                 w = *reinterpret_cast<const unsigned *>(s_src + ly * HME_SRC_STRIDE + lx0);
                 r = ld4g(ref0 + (ptrdiff_t) ly * rs + lx0);
             }
-            const unsigned w_r = __shfl_down_sync(0xffffffffu, w, 1), w_l = __shfl_up_sync(0xffffffffu, w, 1);
-            const unsigned r_l = __shfl_up_sync(0xffffffffu, r, 1);
+            const unsigned w_r = __shfl_down_sync(0xffffffffu, w, 1);
             if (on) {
                 const unsigned nxt = lx0 + 4 < G.bw ? (w_r & 0xffu) : (w >> 24);
                 const unsigned wr = (w >> 8) | (nxt << 24);
@@ -595,49 +693,15 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
                 sum[SUM_SV] += __vsadu4(w, up);
                 sum[SUM_RS] += __vsadu4(r, 0u);
                 sum[SUM_RSS] = __dp4a(r, r, sum[SUM_RSS]);
-                if (ly < 2 * sbh) { /* intra_metric on the four quadrants, hme.c:87-134 */
-                    const int qyi = ly >= sbh;
-                    const int qi0 = lx0 - qxi * sbw, qj = ly - qyi * sbh;
-                    const unsigned wl = (w << 8) | (qi0 == 0 ? (w & 0xffu) : (w_l >> 24));
-                    const unsigned rl = (r << 8) | (qi0 == 0 ? (r & 0xffu) : (r_l >> 24));
-                    const unsigned ua = qj == 0 ? w : up;
-                    const unsigned ub = qj == 0 ? r : r_up;
-                    unsigned g = __vsadu4(w, wl) + __vsadu4(w, ua) + __vsadu4(r, rl) + __vsadu4(r, ub);
-                    /* |w - r| > 2 counts as evil; 0 / 1 / 2 add 192 / 128 / 96 = 192 - 64 v + 32 (v >> 1) to good */
-                    const unsigned d = __vabsdiffu4(w, r);
-                    const unsigned big = __vcmpgtu4(d, 0x02020202u);
-                    const unsigned sm = d & ~big;
-                    const unsigned e = __vsadu4(d & big, 0u);
-                    g += 192u * (4u - ((unsigned) __popc(big) >> 3)) - 64u * __vsadu4(sm, 0u) + 32u * (unsigned) __popc(sm & 0x02020202u);
-                    g_all += g;
-                    e_all += e;
-                    g_top += qyi ? 0u : g;
-                    e_top += qyi ? 0u : e;
-                }
                 w_up = w;
-                r_up = r;
             }
         }
-        const unsigned g_bot = g_all - g_top, e_bot = e_all - e_top;
-        sum[SUM_GOOD0] += qxi ? 0u : g_top;
-        sum[SUM_GOOD1] += qxi ? g_top : 0u;
-        sum[SUM_GOOD2] += qxi ? 0u : g_bot;
-        sum[SUM_GOOD3] += qxi ? g_bot : 0u;
-        sum[SUM_EVIL0] += qxi ? 0u : e_top;
-        sum[SUM_EVIL1] += qxi ? e_top : 0u;
-        sum[SUM_EVIL2] += qxi ? 0u : e_bot;
-        sum[SUM_EVIL3] += qxi ? e_bot : 0u;
     } else {
         /* general widths (blocks cut by the picture edge): rows in turn, columns to lanes */
         for (int ly = 0; ly < G.bh; ly++) {
-            const int qyi = ly >= sbh;
-            const bool inq_y = ly < 2 * sbh;
-            const int qj = ly - qyi * sbh;
-            unsigned good0 = 0, good1 = 0, evil0 = 0, evil1 = 0;
             for (int lx = lane; lx < G.bw; lx += 32) {
                 const uint8_t *sp = s_src + ly * HME_SRC_STRIDE + lx;
-                const uint8_t *rp = ref0 + (ptrdiff_t) ly * rs + lx;
-                const int pa = sp[0], pb = rp[0];
+                const int pa = sp[0], pb = ref0[(ptrdiff_t) ly * rs + lx];
                 const int right = lx == G.bw - 1 ? pa : sp[1];
                 const int up = ly == 0 ? pa : sp[-HME_SRC_STRIDE];
                 sum[SUM_S] += (unsigned) pa;
@@ -646,29 +710,6 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
                 sum[SUM_SV] += (unsigned) iabs(pa - up);
                 sum[SUM_RS] += (unsigned) pb;
                 sum[SUM_RSS] += (unsigned) (pb * pb);
-                if (inq_y && lx < 2 * sbw) { /* intra_metric on the four quadrants, hme.c:87-134 */
-                    const int qxi = lx >= sbw;
-                    const int qi = lx - qxi * sbw;
-                    const int la = qi == 0 ? pa : sp[-1], lb = qi == 0 ? pb : rp[-1];
-                    const int ua = qj == 0 ? pa : up, ub = qj == 0 ? pb : rp[-rs];
-                    unsigned good = (unsigned) (iabs(pa - la) + iabs(pa - ua) + iabs(pb - lb) + iabs(pb - ub));
-                    unsigned evil = 0;
-                    const int dif = iabs(pa - pb);
-                    if (dif > 2) {
-                        evil = (unsigned) dif;
-                    } else {
-                        good += dif == 0 ? 192u : (dif == 1 ? 128u : 96u);
-                    }
-                    good0 += qxi ? 0u : good;
-                    good1 += qxi ? good : 0u;
-                    evil0 += qxi ? 0u : evil;
-                    evil1 += qxi ? evil : 0u;
-                }
-            }
-            if (qyi) {
-                sum[SUM_GOOD2] += good0; sum[SUM_GOOD3] += good1; sum[SUM_EVIL2] += evil0; sum[SUM_EVIL3] += evil1;
-            } else {
-                sum[SUM_GOOD0] += good0; sum[SUM_GOOD1] += good1; sum[SUM_EVIL0] += evil0; sum[SUM_EVIL1] += evil1;
             }
         }
     }
@@ -711,13 +752,50 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
     }
     warp_reduce_n<SUM_COUNT>(sum);
 
-    /* ---- block_intra_test (hme.c:141-177): any sample the reduced-range intra path cannot represent ---- */
-    const int ravg = (int) sum[SUM_RS] / (G.bw * G.bh);
-    int bad = 0;
-    {
-        /* clamp_u8(ravg + clamp_u8(p - ravg + 128) - 128) != p  <=>  the inner clamp is active  <=>  p outside
+    /* ---- the decision cascade (hme.c:651-718).  The sums are warp-uniform, so every lane runs it and the rare intra
+     * blocks take the two passes only they need (the range test and the quadrant metric) as a whole warp ---- */
+    const unsigned area = yarea;
+    const unsigned luma_tex = ((sum[SUM_SH] + sum[SUM_SV]) / 2u) / area;
+    const unsigned luma_var = sum[SUM_SS] - (sum[SUM_S] * sum[SUM_S]) / area;
+    const int lo_tex = luma_tex <= 2, lo_var = luma_var < yareasq;
+    const unsigned pn = HP_SAD_SZ * HP_SAD_SZ;
+    const int src_tex = (int) (((sum[SUM_PSH] + sum[SUM_PSV]) / 2u) / pn);
+    const int src_avg = (int) (sum[SUM_PAV] / pn);
+    const int src_var = (int) (sum[SUM_PAVS] - (sum[SUM_PAV] * sum[SUM_PAV]) / pn);
+    const int ref_tex = (int) (((sum[SUM_QSH] + sum[SUM_QSV]) / 2u) / pn);
+    const int ref_avg = (int) (sum[SUM_QAV] / pn);
+    const int ref_var = (int) (sum[SUM_QAVS] - (sum[SUM_QAV] * sum[SUM_QAV]) / pn);
+    const unsigned ubest = (unsigned) best;
+    bool intra = false;
+    if (src_tex < 2 && (sum[SUM_RSS] - (sum[SUM_RS] * sum[SUM_RS]) / area) > luma_var * 2u) {
+        intra = true;
+    } else if (ref_var > src_var * 2) {
+        intra = true;
+    } else if (src_tex == 0 && ref_tex != 0) {
+        intra = true;
+    } else if (iabs(src_avg - ref_avg) > 8) {
+        intra = true;
+    } else if (luma_tex <= 10 && ubest > yareasq / 16u) {
+        intra = true;
+    } else {
+        const unsigned carea = (unsigned) ((G.bw >> A.hs) * (G.bh >> A.vs));
+        if (carea) {
+            const unsigned vsu = sum[SUM_CSSU] - (sum[SUM_CSU] * sum[SUM_CSU]) / carea;
+            const unsigned vsv = sum[SUM_CSSV] - (sum[SUM_CSV] * sum[SUM_CSV]) / carea;
+            const unsigned vru = sum[SUM_CRSU] - (sum[SUM_CRU] * sum[SUM_CRU]) / carea;
+            const unsigned vrv = sum[SUM_CRSV] - (sum[SUM_CRV] * sum[SUM_CRV]) / carea;
+            const unsigned cvarS = vsu > vsv ? vsu : vsv, cvarR = vru > vrv ? vru : vrv;
+            intra = cvarR > 4u * cvarS;
+        }
+    }
+    int mode = 0, submask = 0;
+    if (intra) {
+        /* block_intra_test (hme.c:141-177): any sample the reduced-range intra path cannot represent.
+         * clamp_u8(ravg + clamp_u8(p - ravg + 128) - 128) != p  <=>  the inner clamp is active  <=>  p outside
          * [ravg - 128, ravg + 127]; four samples per step from the staged words */
+        const int ravg = (int) sum[SUM_RS] / (G.bw * G.bh);
         const int lo = ravg - 128, hi = ravg + 127;
+        int bad = 0;
         if (lo > 0 || hi < 255) {
             const int tail = G.bw & 3;
             const int nb = (G.wx == G.words - 1 && tail) ? tail : 4;
@@ -729,70 +807,39 @@ __global__ void __launch_bounds__(HME_THREADS) hme_l0_kernel(const HmeArgs *args
                     out |= lo > 0 ? __vcmpltu4(w, bound) : __vcmpgtu4(w, bound);
                 }
                 bad = out != 0u;
-            } else
-            for (int r = G.r0; r < G.r1; r++) {
-                const unsigned w = *reinterpret_cast<const unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * G.wx);
+            } else {
+                for (int r = G.r0; r < G.r1; r++) {
+                    const unsigned w = *reinterpret_cast<const unsigned *>(s_src + r * HME_SRC_STRIDE + 4 * G.wx);
 #pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const int p = byte_of(w, e);
-                    bad |= (e < nb) & ((p < lo) | (p > hi));
+                    for (int e = 0; e < 4; e++) {
+                        const int p = byte_of(w, e);
+                        bad |= (e < nb) & ((p < lo) | (p > hi));
+                    }
                 }
             }
         }
-    }
-    const int flag = __any_sync(0xffffffffu, bad);
-
-    if (lane == 0) {
-        const unsigned area = yarea;
-        const unsigned luma_tex = ((sum[SUM_SH] + sum[SUM_SV]) / 2u) / area;
-        const unsigned luma_var = sum[SUM_SS] - (sum[SUM_S] * sum[SUM_S]) / area;
-        const int lo_tex = luma_tex <= 2, lo_var = luma_var < yareasq;
-        const unsigned pn = HP_SAD_SZ * HP_SAD_SZ;
-        const int src_tex = (int) (((sum[SUM_PSH] + sum[SUM_PSV]) / 2u) / pn);
-        const int src_avg = (int) (sum[SUM_PAV] / pn);
-        const int src_var = (int) (sum[SUM_PAVS] - (sum[SUM_PAV] * sum[SUM_PAV]) / pn);
-        const int ref_tex = (int) (((sum[SUM_QSH] + sum[SUM_QSV]) / 2u) / pn);
-        const int ref_avg = (int) (sum[SUM_QAV] / pn);
-        const int ref_var = (int) (sum[SUM_QAVS] - (sum[SUM_QAV] * sum[SUM_QAV]) / pn);
-        const unsigned ubest = (unsigned) best;
-        bool intra = false;
-        if (src_tex < 2 && (sum[SUM_RSS] - (sum[SUM_RS] * sum[SUM_RS]) / area) > luma_var * 2u) {
-            intra = true;
-        } else if (ref_var > src_var * 2) {
-            intra = true;
-        } else if (src_tex == 0 && ref_tex != 0) {
-            intra = true;
-        } else if (iabs(src_avg - ref_avg) > 8) {
-            intra = true;
-        } else if (luma_tex <= 10 && ubest > yareasq / 16u) {
-            intra = true;
-        } else {
-            const unsigned carea = (unsigned) ((G.bw >> A.hs) * (G.bh >> A.vs));
-            if (carea) {
-                const unsigned vsu = sum[SUM_CSSU] - (sum[SUM_CSU] * sum[SUM_CSU]) / carea;
-                const unsigned vsv = sum[SUM_CSSV] - (sum[SUM_CSV] * sum[SUM_CSV]) / carea;
-                const unsigned vru = sum[SUM_CRSU] - (sum[SUM_CRU] * sum[SUM_CRU]) / carea;
-                const unsigned vrv = sum[SUM_CRSV] - (sum[SUM_CRV] * sum[SUM_CRV]) / carea;
-                const unsigned cvarS = vsu > vsv ? vsu : vsv, cvarR = vru > vrv ? vru : vrv;
-                intra = cvarR > 4u * cvarS;
-            }
-        }
-        int mode = 0, submask = 0;
-        if (intra && !flag) {
+        if (!__any_sync(0xffffffffu, bad)) {
             submask = 15;
             if (src_tex > 1) {
+                unsigned ge[8];
+                quadrant_metric(G, s_src, ref0, rs, lane, ge);
                 const unsigned wgt = (unsigned) ((sbw + sbh) >> 1);
+#pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    if (sum[SUM_GOOD0 + q] >= wgt * sum[SUM_EVIL0 + q]) {
+                    if (ge[q] >= wgt * ge[4 + q]) {
                         submask &= ~(1 << q);
                     }
                 }
             }
             if (submask) {
                 mode = 1;
-                atomicAdd(A.nintra, 1);
+                if (lane == 0) {
+                    atomicAdd(A.nintra, 1);
+                }
             }
         }
+    }
+    if (lane == 0) {
         store_mv(out, mvx, mvy, mode, submask, lo_var, lo_tex);
         A.aux[i + j * A.nbh] = make_int2((int) luma_tex, src_var);
     }
