@@ -166,15 +166,40 @@ __global__ void __launch_bounds__(FO_BX *FO_BY) ingest_kernel(const IngestItem *
     }
 }
 
+#ifndef PK_RY
+#define PK_RY 4 /* rows per thread in pack_kernel */
+#endif
 __global__ void __launch_bounds__(FO_BX *FO_BY) pack_kernel(const PackItem *items)
 {
     const PackItem it = items[blockIdx.z];
     const PlaneRef S = it.src;
-    FO_FOREACH_ROW()
-    {
-        const int x0 = ck * 16, y = row;
-        if (x0 >= S.w || y >= S.h) {
-            continue;
+    const int ck = (int) (blockIdx.x * FO_BX + threadIdx.x);
+    if (ck * 16 >= S.w) {
+        return;
+    }
+    const int row0 = (int) (blockIdx.y * FO_BY * PK_RY + threadIdx.y);
+    if ((S.w & 15) == 0 && aligned16(it.dst)) { /* every chunk of the packed plane is aligned: PK_RY loads, then the stores */
+        uint4 v[PK_RY];
+#pragma unroll
+        for (int i = 0; i < PK_RY; i++) {
+            const int y = row0 + i * FO_BY;
+            if (y < S.h) {
+                v[i] = *reinterpret_cast<const uint4 *>(S.p + (size_t) y * S.stride + ck * 16);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < PK_RY; i++) {
+            const int y = row0 + i * FO_BY;
+            if (y < S.h) {
+                *reinterpret_cast<uint4 *>(it.dst + (size_t) y * S.w + ck * 16) = v[i];
+            }
+        }
+        return;
+    }
+    for (int i = 0; i < PK_RY; i++) {
+        const int x0 = ck * 16, y = row0 + i * FO_BY;
+        if (y >= S.h) {
+            break;
         }
         const uint8_t *src = S.p + (size_t) y * S.stride + x0;
         uint8_t *dst = it.dst + (size_t) y * S.w + x0;
@@ -421,7 +446,9 @@ void ingest_launch(const IngestItem *d_items, int n, int max_w, int max_h, cudaS
 void pack_launch(const PackItem *d_items, int n, int max_w, int max_h, cudaStream_t st)
 {
     if (n > 0) {
-        DSV_LAUNCH(pack_kernel, fo_grid(max_w, max_h, n, false), dim3(FO_BX, FO_BY), 0, st, d_items);
+        dim3 grid = fo_grid(max_w, max_h, n, false);
+        grid.y = (unsigned) ceil_div(max_h, FO_BY * PK_RY);
+        DSV_LAUNCH(pack_kernel, grid, dim3(FO_BX, FO_BY), 0, st, d_items);
         KERNEL_CHECK();
     }
 }

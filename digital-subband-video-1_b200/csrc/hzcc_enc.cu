@@ -138,6 +138,23 @@ DSV_D void hz_advance(const HzRegions &rg, HzCursor &c)
     }
 }
 
+/* quantised symbol of the coefficient v != 0 at (x, y) of region r: the LL region away from the DC, or a detail band
+ * position that is not the first visit of a double-visited row / column */
+DSV_D int hz_symbol_plain(const HzJob &J, int r, int x, int y, int v)
+{
+    if (r == 0) {
+        return dz_quant(v, J.pq.ll_q, J.pq.ll_fd);
+    }
+    const int lvl = J.rg.lvl[r];
+    int f = J.stable[((y * J.pq.dby[lvl]) >> 14) * J.pq.nbh + ((x * J.pq.dbx[lvl]) >> 14)];
+    if (lvl == 1) {
+        return p2_quant(v, f ? J.pq.sh_hq : J.pq.sh_plain);
+    }
+    int sel = (f & 2) ? 2 : (f ? 1 : 0);
+    const LevelQ &Lq = J.pq.lv[3 - lvl];
+    return dz_quant(v, Lq.q[sel], Lq.fd[sel]);
+}
+
 /* quantised symbol at the cursor (which must be inside the plane's scan order): re-derived from the dequantised
  * coefficient the SBT epilogue stored; zero coefficients (the vast majority) cost one load and a compare */
 DSV_D int hz_symbol_at(const HzJob &J, const HzCursor &c)
@@ -165,16 +182,17 @@ DSV_D int hz_symbol_at(const HzJob &J, const HzCursor &c)
         }
     }
     int v = J.coef[(size_t) ay * J.cw + ax];
-    if (!v) {
-        return 0;
+    return v ? hz_symbol_plain(J, r, x, y, v) : 0;
+}
+/* the symbols of the four positions of a group hz_group_plain accepted, from its one 16-byte load: the four
+ * derivations (block-flag load + division) are independent of each other */
+DSV_D void hz_symbols_of_group(const HzJob &J, const HzCursor &c, const int4 &v, int (&sym)[4])
+{
+    const int vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        sym[e] = vv[e] ? hz_symbol_plain(J, c.r, c.x + e, c.y, vv[e]) : 0;
     }
-    int f = J.stable[((y * J.pq.dby[lvl]) >> 14) * J.pq.nbh + ((x * J.pq.dbx[lvl]) >> 14)];
-    if (lvl == 1) {
-        return p2_quant(v, f ? J.pq.sh_hq : J.pq.sh_plain);
-    }
-    int sel = (f & 2) ? 2 : (f ? 1 : 0);
-    const LevelQ &Lq = J.pq.lv[3 - lvl];
-    return dz_quant(v, Lq.q[sel], Lq.fd[sel]);
 }
 
 DSV_D unsigned long long mk_key(int pos, int sym) { return ((unsigned long long) (unsigned) pos << 32) | (unsigned) sym; }
@@ -325,13 +343,27 @@ template <class Visitor> DSV_D void hz_chunk_rounds(const HzJob &J, int cbase, i
             HzCursor c;
             hz_locate(rg, pos, c);
             const int e_end = imin(4, total - pos);
-            for (int e = 0; e < e_end; e++) {
-                const int sym = hz_symbol_at(J, c);
-                hz_advance(rg, c);
-                if (sym) {
-                    grp.pos[grp.cnt] = pos + e;
-                    grp.sym[grp.cnt] = sym;
-                    grp.cnt++;
+            const int32_t *p;
+            if (e_end == 4 && hz_group_plain(J, c, &p)) {
+                int sy[4];
+                hz_symbols_of_group(J, c, *reinterpret_cast<const int4 *>(p), sy);
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    if (sy[e]) {
+                        grp.pos[grp.cnt] = pos + e;
+                        grp.sym[grp.cnt] = sy[e];
+                        grp.cnt++;
+                    }
+                }
+            } else {
+                for (int e = 0; e < e_end; e++) {
+                    const int sym = hz_symbol_at(J, c);
+                    hz_advance(rg, c);
+                    if (sym) {
+                        grp.pos[grp.cnt] = pos + e;
+                        grp.sym[grp.cnt] = sym;
+                        grp.cnt++;
+                    }
                 }
             }
         }
@@ -399,18 +431,26 @@ template <class F> DSV_D void hz_walk(const HzJob &J, int base, int total, F on_
         const int32_t *p;
         if (pos + 4 <= end && hz_group_plain(J, c, &p)) {
             const int4 v = *reinterpret_cast<const int4 *>(p);
-            if ((v.x | v.y | v.z | v.w) == 0) {
-                pos += 4;
-                c.x += 4;
-                if (c.x == rg.sw[c.r]) {
-                    c.x = 0;
-                    if (++c.y == rg.sh[c.r]) {
-                        c.y = 0;
-                        c.r++;
+            if ((v.x | v.y | v.z | v.w) != 0) {
+                int sy[4];
+                hz_symbols_of_group(J, c, v, sy);
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    if (sy[e]) {
+                        on_nonzero(pos + e, sy[e]);
                     }
                 }
-                continue;
             }
+            pos += 4;
+            c.x += 4;
+            if (c.x == rg.sw[c.r]) {
+                c.x = 0;
+                if (++c.y == rg.sh[c.r]) {
+                    c.y = 0;
+                    c.r++;
+                }
+            }
+            continue;
         }
         const int sym = hz_symbol_at(J, c);
         hz_advance(rg, c);
