@@ -958,8 +958,10 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
             h.dv = s.dv;
             h.tflags = s.tflags;
             h.tiles_x = ceil_div(g.cw[p], SBT_TW);
-            /* list scratch for the dense chunks of I pictures only: P pictures have a handful of them at most */
-            h.dense = isP ? nullptr : l.hz_dense + (size_t) ((p > 0 ? g.chunks[0] : 0) + (p > 1 ? g.chunks[1] : 0)) * HZ_DENSE_BYTES;
+            /* list scratch: the pack pass then reads no coefficient.  P pictures have a handful of dense chunks at
+             * most; those are walked again rather than paying for the dense pack kernel's launch */
+            h.dense = l.hz_dense + (size_t) ((p > 0 ? g.chunks[0] : 0) + (p > 1 ? g.chunks[1] : 0)) * HZ_DENSE_BYTES;
+            h.list_mode = isP ? HZ_LISTS_SPARSE : HZ_LISTS_BOTH;
             h.stable = s.stable;
             h.chunk_base = k * g.total_chunks + (p > 0 ? g.chunks[0] : 0) + (p > 1 ? g.chunks[1] : 0);
             h.frame = k;

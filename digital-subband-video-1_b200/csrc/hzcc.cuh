@@ -36,6 +36,11 @@ struct HzJob {
      * (I pictures) there -- per lane: bit count, count, then (offset, symbol) lists, lane-interleaved -- so that the
      * pack pass emits straight from the lists instead of walking the coefficients and re-deriving every symbol */
     uint8_t *dense;
+    /* what the scan pass leaves in that scratch: HZ_LISTS_DENSE (0, the default) = the lists of dense chunks;
+     * HZ_LISTS_BOTH = also the (offset, symbol) list of every sparse chunk, in scan order, so that the pack pass reads
+     * no coefficient at all; HZ_LISTS_SPARSE = sparse chunks only (P pictures: their handful of dense chunks is not
+     * worth the launch of the dense pack kernel) */
+    int list_mode;
     int cw, ch;
     int plane, isP;
     int chunk_base, nchunks; /* this plane's chunks inside the launch-wide chunk arrays */
@@ -51,10 +56,12 @@ struct HzJob {
 #define HZ_DENSE_OFF 256    /* uint8 off[64][32] */
 #define HZ_DENSE_SYM 2304   /* int sym[64][32] */
 #define HZ_DENSE_BYTES (2304 + 64 * 32 * 4)
+/* a sparse chunk's list lives in the same scratch: uint16 offset[<= 508] at HZ_DENSE_OFF, int sym[<= 508] at HZ_DENSE_SYM */
+enum { HZ_LISTS_DENSE = 0, HZ_LISTS_SPARSE = 1, HZ_LISTS_BOTH = 2 };
 
 struct HzChunk {
     int cnt;            /* non-zero symbols in the chunk */
-    int dense;          /* the chunk's lists are in the job's dense scratch */
+    int dense;          /* the chunk's lists are in the job's scratch: 1 = per-lane lists of a dense chunk, 2 = one sparse list */
     int first_pos;      /* scan position of the first / last non-zero, -1 if none */
     int last_pos;
     int last_sym;

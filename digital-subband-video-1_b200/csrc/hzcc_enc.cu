@@ -520,11 +520,38 @@ struct HzScanAcc {
 };
 struct HzScanVisitor {
     HzScanAcc acc;
-    int saved = 0; /* the dense lists of this chunk were written to the job's scratch */
-    DSV_D void round(const HzGroup &g, int lane) { acc.add(hz_group_summary(g), lane); }
+    int saved = 0;           /* which lists of this chunk were written to the job's scratch (HzChunk.dense) */
+    uint8_t *sparse = nullptr; /* the chunk's scratch if sparse lists are wanted */
+    int nlist = 0;
+    DSV_D void round(const HzGroup &g, int lane)
+    {
+        if (sparse) { /* append the round's non-zeros, in scan order: lanes in turn, a lane's group in order */
+            unsigned incl = (unsigned) g.cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) {
+                    incl += n;
+                }
+            }
+            const int at = nlist + (int) incl - g.cnt;
+            uint16_t *lp = reinterpret_cast<uint16_t *>(sparse + HZ_DENSE_OFF);
+            int *ls = reinterpret_cast<int *>(sparse + HZ_DENSE_SYM);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                if (e < g.cnt) {
+                    lp[at + e] = (uint16_t) (g.pos[e] & (HZ_CHUNK - 1));
+                    ls[at + e] = g.sym[e];
+                }
+            }
+            nlist += (int) __shfl_sync(0xffffffffu, incl, 31);
+            saved = 2;
+        }
+        acc.add(hz_group_summary(g), lane);
+    }
     DSV_D void dense(const HzJob &J, int base, int total, int lane)
     {
-        if (!J.dense) {
+        if (!J.dense || J.list_mode == HZ_LISTS_SPARSE) {
             acc.add(hz_walk_summary(J, base, total), lane);
             return;
         }
@@ -601,6 +628,9 @@ __global__ void __launch_bounds__(HZ_THREADS) hzcc_scan_kernel(const HzJob *jobs
     const HzJob &J = jobs[hz_job_of_chunk(jobs, njobs, chunk, map)];
     HzScanVisitor V;
     const int cbase = (chunk - J.chunk_base) * HZ_CHUNK;
+    if (J.dense && J.list_mode != HZ_LISTS_DENSE) {
+        V.sparse = J.dense + (size_t) (chunk - J.chunk_base) * HZ_DENSE_BYTES;
+    }
     if (!hz_chunk_flagged_empty(J, cbase, J.rg.base[HZ_NREG], lane)) {
         hz_chunk_rounds(J, cbase, J.rg.base[HZ_NREG], lane, V);
     }
@@ -883,6 +913,52 @@ DSV_D void hz_pack_from_lists(const HzJob &J, const HzChunk &C, unsigned *words,
     bw.end();
 }
 
+/* Pack pass of a sparse chunk whose list the scan pass saved: 32 non-zeros per round, one per lane */
+DSV_D void hz_pack_from_sparse_list(const HzJob &J, const HzChunk &C, unsigned *words, int cbase, int lane)
+{
+    const uint8_t *sc = J.dense + (size_t) (cbase / HZ_CHUNK) * HZ_DENSE_BYTES;
+    const uint16_t *lp = reinterpret_cast<const uint16_t *>(sc + HZ_DENSE_OFF);
+    const int *ls = reinterpret_cast<const int *>(sc + HZ_DENSE_SYM);
+    int carry_pos = C.prev_pos, carry_sym = C.prev_sym;
+    unsigned long long off = C.bit_off;
+    for (int e0 = 0; e0 < C.cnt; e0 += 32) {
+        const int e = e0 + lane;
+        const bool on = e < C.cnt;
+        int pos = -1, sym = 0;
+        if (on) {
+            pos = cbase + lp[e];
+            sym = ls[e];
+        }
+        int prev_pos = __shfl_up_sync(0xffffffffu, pos, 1), prev_sym = __shfl_up_sync(0xffffffffu, sym, 1);
+        if (lane == 0) {
+            prev_pos = carry_pos;
+            prev_sym = carry_sym;
+        }
+        const unsigned bits = on ? group_bits(pos, prev_pos, prev_sym) : 0u;
+        unsigned incl = bits;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) {
+                incl += n;
+            }
+        }
+        if (on) { /* the non-zero ORs its group (UEG(run) ++ NEG(prev)) at its bit offset */
+            unsigned long long at = off + (unsigned long long) (incl - bits);
+            const unsigned run = (unsigned) (pos - prev_pos - 1);
+            const int l = ueg_len(run);
+            or_bits_atomic(words, at, l, ueg_code(run));
+            if (prev_pos >= 0) {
+                or_bits_atomic(words, at + (unsigned long long) l, neg_len(prev_sym), neg_code(prev_sym));
+            }
+        }
+        off += (unsigned long long) __shfl_sync(0xffffffffu, incl, 31);
+        const int last = imin(31, C.cnt - e0 - 1);
+        carry_pos = __shfl_sync(0xffffffffu, pos, last);
+        carry_sym = __shfl_sync(0xffffffffu, sym, last);
+    }
+}
+
 struct HzPackVisitor {
     HzPackAcc acc;
     unsigned *words;
@@ -979,8 +1055,12 @@ __global__ void __launch_bounds__(HZ_THREADS) hzcc_pack_kernel(const HzJob *jobs
     if (frames[J.frame].overflow) {
         return; /* refused by the prefix pass: nothing of this picture is written */
     }
-    if (C.dense) {
+    if (C.dense == 1) {
         return; /* hzcc_pack_dense_kernel's */
+    }
+    if (C.dense == 2) {
+        hz_pack_from_sparse_list(J, C, reinterpret_cast<unsigned *>(frames[J.frame].pkt), (chunk - J.chunk_base) * HZ_CHUNK, lane);
+        return;
     }
     HzPackVisitor V;
     V.acc.carry = mk_key(C.prev_pos, C.prev_sym);
@@ -998,7 +1078,7 @@ __global__ void __launch_bounds__(HZ_THREADS) hzcc_pack_dense_kernel(const HzJob
         return;
     }
     const HzChunk C = chunks[chunk];
-    if (C.cnt == 0 || !C.dense) {
+    if (C.cnt == 0 || C.dense != 1) {
         return;
     }
     const HzJob &J = jobs[hz_job_of_chunk(jobs, njobs, chunk, map)];
