@@ -107,6 +107,8 @@ struct StepArena {
         return hp;
     }
     void upload(cudaStream_t st); /* everything appended since the last upload */
+    /* the same upload as a copy item for copyn_launch (marks it done); false: nothing is pending */
+    bool take_upload(struct CopyItem *it);
 };
 
 /* launches; every list pointer is a DEVICE pointer, max_* bound the grid */
@@ -120,6 +122,10 @@ void zero_launch(const ZeroItem *d_items, int n, size_t max_bytes, cudaStream_t 
  * mapped pinned host memory */
 void copy_launch(const CopyItem *items, int n, size_t max_bytes, cudaStream_t st);
 void copy1_launch(void *dst, const void *src, size_t bytes, cudaStream_t st);
+/* up to COPYN_MAX independent control-plane copies in ONE launch (each launch that reads mapped host memory costs a PCIe
+ * round trip of ~14 us on the stream); items (host array) with bytes == 0 are skipped */
+#define COPYN_MAX 4
+void copyn_launch(const CopyItem *items, int n, cudaStream_t st);
 void overlay_launch(const DrawItem *d_items, int n, cudaStream_t st);
 void to420_launch(const To420Item *d_items, int n, int max_dw, int max_dh, cudaStream_t st);
 

@@ -68,6 +68,18 @@ void *StepArena::push(size_t bytes, void **dev)
     *dev = d + at;
     return h + at;
 }
+bool StepArena::take_upload(CopyItem *it)
+{
+    if (used <= uploaded) {
+        return false;
+    }
+    const size_t from = uploaded & ~(size_t) 15;
+    it->dst = d + from;
+    it->src = h + from;
+    it->bytes = used - from;
+    uploaded = used;
+    return true;
+}
 void StepArena::upload(cudaStream_t st)
 {
     if (used > uploaded) {
@@ -413,6 +425,36 @@ __global__ void __launch_bounds__(256) copy_kernel(const CopyItem *items)
 __global__ void __launch_bounds__(256) copy1_kernel(CopyItem it)
 {
     copy_span(reinterpret_cast<uint8_t *>(it.dst), reinterpret_cast<const uint8_t *>(it.src), it.bytes, (size_t) blockIdx.x * COPY_PER_CTA);
+}
+
+struct CopyItemsN {
+    CopyItem it[COPYN_MAX];
+};
+__global__ void __launch_bounds__(256) copyn_kernel(const CopyItemsN its)
+{
+    const CopyItem it = its.it[blockIdx.y];
+    copy_span(reinterpret_cast<uint8_t *>(it.dst), reinterpret_cast<const uint8_t *>(it.src), it.bytes, (size_t) blockIdx.x * COPY_PER_CTA);
+}
+void copyn_launch(const CopyItem *items, int n, cudaStream_t st)
+{
+    CopyItemsN its;
+    memset(&its, 0, sizeof(its));
+    int m = 0;
+    size_t max_bytes = 0;
+    for (int i = 0; i < n; i++) {
+        if (items[i].bytes > 0) {
+            if (m == COPYN_MAX) { /* more than one launch's worth */
+                copyn_launch(items + i, n - i, st);
+                break;
+            }
+            its.it[m++] = items[i];
+            max_bytes = items[i].bytes > max_bytes ? items[i].bytes : max_bytes;
+        }
+    }
+    if (m > 0) {
+        DSV_LAUNCH(copyn_kernel, dim3((unsigned) ((max_bytes + COPY_PER_CTA - 1) / COPY_PER_CTA), (unsigned) m), dim3(256), 0, st, its);
+        KERNEL_CHECK();
+    }
 }
 
 void copy_launch(const CopyItem *items, int n, size_t max_bytes, cudaStream_t st)

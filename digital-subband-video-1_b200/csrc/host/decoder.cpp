@@ -527,12 +527,13 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
     if (prev_nonref_) {
         CUDA_CHECK(cudaStreamWaitEvent(st, ev_copied_[(step_no_ ^ 1) & 1], 0));
     }
-    arena_.upload(st);
-    copy_launch(d_cpy, n_cpy, max_cpy, st);
-    copy1_launch(d_stab_, h_stab_, (size_t) step_nblk * L_, st);
-    if (n_p) {
-        copy1_launch(d_mv_, h_mv_, sizeof(DevMV) * (size_t) step_nblk * L_, st);
+    {
+        CopyItem up[3] = {{nullptr, nullptr, 0}, {d_stab_, h_stab_, (size_t) step_nblk * L_},
+                          {d_mv_, h_mv_, n_p ? sizeof(DevMV) * (size_t) step_nblk * L_ : 0}};
+        arena_.take_upload(&up[0]);
+        copyn_launch(up, 3, st);
     }
+    copy_launch(d_cpy, n_cpy, max_cpy, st);
     hzdec_clean_launch(d_clean, n_clean, g_.tiles[0], st);
     hzdec_launch_jobs(d_hzj, dims, st);
     sbt_inv_launch(d_sj, sdims, g_.lo_smem, st, timed ? ev_[0] : nullptr, timed ? ev_[1] : nullptr);
@@ -551,7 +552,7 @@ void DecEngine::step(int n, const int *lane_ids, const PktRef *pkts, const OutRe
     overlay_launch(d_draw, n_draw, st);
     pack_launch(d_pack2, n_pack2, g_.w, g_.h, st);
     to420_launch(d_cv, n_cv, og_.pw[1], og_.ph[1], st);
-    stats.kernel_launches += 14 + (n_p ? 1 : 0) + (n_ext ? 1 : 0) + (n_pack ? 1 : 0) + (n_draw ? 1 : 0) + (n_pack2 ? 1 : 0) + (n_cv ? 1 : 0);
+    stats.kernel_launches += 13 + (n_p ? 1 : 0) + (n_ext ? 1 : 0) + (n_pack ? 1 : 0) + (n_draw ? 1 : 0) + (n_pack2 ? 1 : 0) + (n_cv ? 1 : 0);
     CUDA_CHECK(cudaEventRecord(ev_done_, st));
     CUDA_CHECK(cudaStreamWaitEvent(st_copy_, ev_done_, 0));
     bool nonref = false;

@@ -815,10 +815,11 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         if (n_search) {
             hme_launch(d_hme, n_search, mg, st);
             stats.kernel_launches += (unsigned) levels_ + 2;
-            copy1_launch(h_mv0_, d_mv0_, sizeof(DevMV) * (size_t) g.nblk * L_, st);
         }
-        if (n_sum || n_search) {
-            copy1_launch(h_misc_, d_misc_, sizeof(LaneMisc) * (size_t) L_, st);
+        if (n_sum || n_search) { /* the vectors and the per-lane sums come back in one launch */
+            const CopyItem back[2] = {{h_mv0_, d_mv0_, n_search ? sizeof(DevMV) * (size_t) g.nblk * L_ : 0},
+                                      {h_misc_, d_misc_, sizeof(LaneMisc) * (size_t) L_}};
+            copyn_launch(back, 2, st);
             need_sync = true;
             CUDA_CHECK(cudaEventRecord(ev_search_, st));
         }
@@ -983,9 +984,11 @@ void EncEngine::step(int n, const int *lane_ids, const PicRef *src, DSV_BUF (*bu
         }
     }
     const SbtDims sdims = sbt_assign_tiles(sj, 3 * n);
-    arena_.upload(st);
-    copy1_launch(d_stab_, h_stab_, (size_t) g.nblk * L_, st);
-    copy1_launch(d_hf, h_frames_, sizeof(HzFrame) * (size_t) n, st);
+    {
+        CopyItem up[3] = {{nullptr, nullptr, 0}, {d_stab_, h_stab_, (size_t) g.nblk * L_}, {d_hf, h_frames_, sizeof(HzFrame) * (size_t) n}};
+        arena_.take_upload(&up[0]);
+        copyn_launch(up, 3, st);
+    }
     zero_launch(d_zero, n_zero, max_zero, st);
     sbt_fwd_launch(d_sj, sdims, g.lo_smem, st, timed ? ev_[0] : nullptr, timed ? ev_[1] : nullptr);
     hzcc_enc_launch(d_hj, 3 * n, d_chunks_, n * g.total_chunks, d_hf, n, st, g.total_chunks, g.chunks[0], g.chunks[1], n_p < n);

@@ -1,1 +1,3 @@
-for v in base new; do echo "== $v"; if [ $v = base ]; then export DSV1_B200_LIB=digital-subband-video-1_b200/build/ab/libdsv1_b200_base.so; else unset DSV1_B200_LIB; fi; python tools/flag_probe.py 2>&1 | grep -E "hzcc_"; done
+O=gpurun_out/r2r; mkdir -p $O
+python tools/quick_time.py hd_gop12 cif_gop12 2>&1 | grep -v "^ref" | tail -4
+python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; python tools/parse_bench.py < $O/bench_n1.json | head -40
