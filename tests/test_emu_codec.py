@@ -142,6 +142,33 @@ def test_odd_geometry_tiny(emu, ref):
     assert np.array_equal(ref.decode_stream(sa, w, h, sub, n)[1], emu.decode_stream(sa, w, h, sub, n)[1])
 
 
+def test_motion_scene_cut_quadrants(emu, ref):
+    """Source and reference from unrelated content (a scene cut): most blocks go through the cascade's intra branch,
+    i.e. through the passes only intra blocks take (reduced-range test, quadrant good / evil metric with partial
+    submasks), on 32-wide blocks (packed-word path) and with half-pel winners next to them."""
+    w, h, fmt = 352, 288, "420"
+    sub = L.SUBSAMP[fmt]
+    for kind_s, kind_r, st in ((2, 4, 9), (0, 2, 1)):
+        fr = L.synth_sequence(w, h, fmt, 1, kind_r, 7, start=st)
+        fs = L.synth_sequence(w, h, fmt, 1, kind_s, 0, start=4)
+        pr, mr = ref.hme(fs, fr, w, h, sub, 3)
+        pe, me = emu.hme(fs, fr, w, h, sub, 3)
+        assert pr == pe and all(np.array_equal(mr[k], me[k]) for k in mr.dtype.names if k != "pad")
+        assert (mr["mode"] == 1).sum() > 100 and ((mr["x"] | mr["y"]) & 1).any()
+    assert len(set(mr["submask"].tolist()) - {0, 15}) > 0, "no partial quadrant mask in the sample"
+
+
+def test_encoder_chunk_lists(emu, ref):
+    """The encoder hands the HZCC passes a list scratch: dense chunks of the I picture leave per-lane lists, sparse
+    chunks (the P pictures, the I picture's tail) one list in scan order, and the pack pass emits from them."""
+    w, h, fmt, n = 176, 144, "420", 3
+    yuv = L.synth_sequence(w, h, fmt, n, 0, 0)
+    cfg = L.make_cfg(w, h, fmt, gop=12, qp=85)
+    sa, pa, _ = ref.encode_sequence(cfg, yuv, n)
+    sb, pb, _ = emu.encode_sequence(cfg, yuv, n)
+    assert pa == pb and sa == sb
+
+
 def test_dsv_hme_exported_interface_tiny(emu, ref):
     """The reference also exports dsv_hme(DSV_HME *): same call, caller-built pyramids, all levels compared."""
     w, h, fmt, lv = 90, 70, "444", 2
