@@ -1,3 +1,2 @@
-O=gpurun_out/r2r; mkdir -p $O
-python tools/quick_time.py hd_gop12 cif_gop12 2>&1 | grep -v "^ref" | tail -4
-python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; python tools/parse_bench.py < $O/bench_n1.json | head -40
+O=gpurun_out/r2t; mkdir -p $O
+timeout 40 python bench.py --config 3 --steps 3 --warmup 3 --no-cpu > $O/bench_config3.json 2> $O/bench_config3.err; python tools/parse_bench.py < $O/bench_config3.json | head -1
