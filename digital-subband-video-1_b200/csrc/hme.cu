@@ -4,16 +4,21 @@
  * level 0 the half-pel refinement on the 14x14 centre patch, the block statistics and the
  * intra / inter decision with its quadrant mask.
  *
- *   hme_level_kernel   levels > 0: one CTA per visited block.  The source block is staged once in
- *                      shared memory as aligned 32-bit words; every candidate's SAD is accumulated
- *                      with __vsadu4 over unaligned reference words (two aligned loads + funnel
- *                      shift), reduced with warp shuffles; thread 0 takes the FIRST minimum in the
- *                      reference's candidate order (strict '<', hme.c:503,531).
- *   hme_l0_kernel      level 0: the same search, then the 32x32 half-pel image of the 16x16
- *                      reference patch (hme.c:350-376) built in shared memory, 8 half-pel SADs,
- *                      and ~30 block sums (variance / texture / chroma variance / quadrant
- *                      good-vs-evil metric) reduced in one pass; thread 0 runs the decision cascade
- *                      (hme.c:651-718).  All unsigned 32-bit wrap-arounds of the reference are kept.
+ *   hme_level_kernel   levels > 0: one WARP per visited block, four blocks per CTA, no block barrier.
+ *                      The source block is staged once in shared memory as aligned 32-bit words;
+ *                      every candidate's SAD is accumulated with __vsadu4 over unaligned reference
+ *                      words (two aligned ld.global.nc + funnel shift), reduced with warp
+ *                      reductions; the FIRST minimum in the reference's candidate order wins
+ *                      (strict '<', hme.c:503,531).
+ *   hme_l0_kernel      level 0: the same search, then the half-pel image of the 16x16 reference
+ *                      patch (hme.c:350-376) as three phase planes in shared memory (H, V, HV: a
+ *                      candidate's 14 samples of a row are consecutive bytes), 8 half-pel SADs on
+ *                      packed words with a patch row per lane, and 22 block sums (variance /
+ *                      texture / chroma variance / patch textures) reduced in one pass.  The
+ *                      decision cascade (hme.c:651-718) runs on every lane -- its inputs are
+ *                      warp-uniform -- and only the blocks it marks intra take the two passes
+ *                      nothing else needs: the reduced-range test and the quadrant good-vs-evil
+ *                      metric.  All unsigned 32-bit wrap-arounds of the reference are kept.
  *   hme_neigh_kernel   high_detail needs the left / top / top-left blocks' final mode and flags
  *                      (hme.c:621-648): a second, one-thread-per-block pass.
  *
@@ -37,7 +42,6 @@ namespace dsv {
 #define HME_UNROLL(n) HME_PRAGMA(unroll n)
 #define HP_SAD_SZ 14
 #define HP_DIM 16
-#define HP_STRIDE 32
 
 /* the search offsets in the reference's candidate order (hme.c:505-541 full-pel, hme.c:560-575 half-pel), packed two
  * bits per entry (value + 1) so that picking the winner's offset is a shift instead of a table in local memory */

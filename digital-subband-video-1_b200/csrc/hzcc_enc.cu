@@ -12,7 +12,11 @@
  *                       non-zero, bit offsets), plane framing (plen, SEG(DC), nruns, final NEG,
  *                       0x55) and plane base offsets; yields the packet length.
  *   hzcc_pack_kernel    per chunk again: every non-zero ORs its group (UEG(run) ++ NEG(prev))
- *                       at its bit offset into the zeroed packet (MSB-first, bs.c:76-91).
+ *                       at its bit offset into the zeroed packet (MSB-first, bs.c:76-91).  With a
+ *                       list scratch (HzJob.dense, the encoder always passes one) the scan pass has
+ *                       left the chunk's non-zeros there -- one (offset, symbol) list in scan order
+ *                       for a sparse chunk, per-lane lists for a dense one (those are emitted by
+ *                       hzcc_pack_dense_kernel) -- and no coefficient is read a second time.
  */
 #include "hzcc.cuh"
 #include "scan.cuh"
