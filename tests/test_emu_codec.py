@@ -148,13 +148,12 @@ def test_motion_scene_cut_quadrants(emu, ref):
     submasks), on 32-wide blocks (packed-word path) and with half-pel winners next to them."""
     w, h, fmt = 352, 288, "420"
     sub = L.SUBSAMP[fmt]
-    for kind_s, kind_r, st in ((2, 4, 9), (0, 2, 1)):
-        fr = L.synth_sequence(w, h, fmt, 1, kind_r, 7, start=st)
-        fs = L.synth_sequence(w, h, fmt, 1, kind_s, 0, start=4)
-        pr, mr = ref.hme(fs, fr, w, h, sub, 3)
-        pe, me = emu.hme(fs, fr, w, h, sub, 3)
-        assert pr == pe and all(np.array_equal(mr[k], me[k]) for k in mr.dtype.names if k != "pad")
-        assert (mr["mode"] == 1).sum() > 100 and ((mr["x"] | mr["y"]) & 1).any()
+    fr = L.synth_sequence(w, h, fmt, 1, 4, 7, start=9)
+    fs = L.synth_sequence(w, h, fmt, 1, 2, 0, start=4)
+    pr, mr = ref.hme(fs, fr, w, h, sub, 3)
+    pe, me = emu.hme(fs, fr, w, h, sub, 3)
+    assert pr == pe and all(np.array_equal(mr[k], me[k]) for k in mr.dtype.names if k != "pad")
+    assert (mr["mode"] == 1).sum() > 100 and ((mr["x"] | mr["y"]) & 1).any()
     assert len(set(mr["submask"].tolist()) - {0, 15}) > 0, "no partial quadrant mask in the sample"
 
 
